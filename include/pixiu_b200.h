@@ -1,0 +1,124 @@
+/* pixiu_b200 — C ABI of the B200-native PiXiu hot path.
+ *
+ * Drop-in boundary for the reference's `struct PiXiuCtrl`
+ * (/root/reference/src/proj/PiXiuCtrl.h:7-26; public API README.md:104-119).  The
+ * reference has no FFI of its own: its only API is that C++ struct, whose methods
+ * these entry points replace one for one, batched:
+ *
+ *   PiXiuCtrl::init_prop  (PiXiuCtrl.cpp:77-81)  -> pixiu_create
+ *   PiXiuCtrl::free_prop  (PiXiuCtrl.cpp:83-86)  -> pixiu_destroy
+ *   PiXiuCtrl::setitem    (PiXiuCtrl.cpp:12-47)  -> pixiu_setitem_batch   (in-order semantics of n calls)
+ *   PiXiuCtrl::contains   (PiXiuCtrl.cpp:55-57)  -> pixiu_contains_batch
+ *   PiXiuCtrl::getitem    (PiXiuCtrl.cpp:59-61)  -> pixiu_getitem_batch   (drained PXSGen streams)
+ *   PiXiuCtrl::delitem    (PiXiuCtrl.cpp:63-69)  -> pixiu_delitem_batch
+ *   PiXiuCtrl::iter       (PiXiuCtrl.cpp:71-75)  -> pixiu_iter
+ *   ctrl.st.cbt_chunk->getitem(i)->{len,data} (main.cpp:67) -> pixiu_encoded_view
+ *
+ * Conventions: plain pointers and sizes; inputs are borrowed; outputs go to caller
+ * buffers (query the size first by passing cap = 0); return 0 on success, a negative
+ * PIXIU_E* code otherwise (the reference only asserts — oversize records are an explicit
+ * error here).  Batches are *packed*: `data` holds the items back to back and
+ * `off[n+1]` (int64) their boundaries.  A store may be used by one host thread at a
+ * time; several stores per process are fine (no globals).  All compute runs on the
+ * GPU chosen at create time; there is no CPU fallback.
+ */
+#ifndef PIXIU_B200_H
+#define PIXIU_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pixiu_store pixiu_store;
+
+#define PIXIU_OK 0
+#define PIXIU_EINVAL (-1)      /* bad argument */
+#define PIXIU_ETOOLONG (-2)    /* record longer than 65,535 escaped bytes (PiXiuStr.cpp:123,:238) */
+#define PIXIU_ECUDA (-3)       /* CUDA failure; see pixiu_last_error */
+#define PIXIU_ENOSPC (-4)      /* caller buffer too small; required size reported */
+#define PIXIU_ECORRUPT (-5)    /* malformed encoded record */
+#define PIXIU_EINTERNAL (-6)
+
+#define PIXIU_CBT_SET_REPLACE 1   /* data_struct/CritBitTree.h:7 */
+#define PIXIU_CBT_DEL_NOT_FOUND 1 /* data_struct/CritBitTree.h:8 */
+
+/* window (= chunk) rotation policy, PiXiuCtrl.cpp:13-17 */
+#define PIXIU_ROTATE_REFERENCE 0 /* the reference's rule: arena pools >= 2048 or 65,535 records */
+#define PIXIU_ROTATE_BYTES 1     /* start a new chunk when the window text would exceed window_bytes */
+#define PIXIU_ROTATE_RECORDS 2   /* only the format limit of 65,535 records per chunk */
+
+typedef struct pixiu_config {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t rotate_policy;   /* PIXIU_ROTATE_* */
+    int64_t window_bytes;    /* for PIXIU_ROTATE_BYTES */
+    int32_t strict251;       /* 1: reproduce reference bug B1 (run of 251 -> ambiguous FB FB form) */
+    int32_t reserved;
+} pixiu_config;
+
+typedef struct pixiu_stats {
+    int64_t records;        /* records ever stored (tombstoned included) */
+    int64_t live_records;
+    int64_t chunks;
+    int64_t raw_bytes;      /* sum of key+value bytes stored */
+    int64_t doc_bytes;      /* sum of escaped doc lengths */
+    int64_t encoded_bytes;  /* sum of encoded record lengths */
+    int64_t window_bytes;   /* text currently resident in the open window */
+    int64_t kernel_launches;/* kernels launched by this store so far */
+    double last_setitem_gpu_ms; /* device time of the last setitem batch (CUDA events) */
+    double last_getitem_gpu_ms;
+    double last_lookup_gpu_ms;
+} pixiu_stats;
+
+void pixiu_default_config(pixiu_config *cfg);
+pixiu_store *pixiu_create(const pixiu_config *cfg);   /* NULL on failure */
+void pixiu_destroy(pixiu_store *s);
+const char *pixiu_last_error(const pixiu_store *s);
+int pixiu_get_stats(pixiu_store *s, pixiu_stats *out);
+
+/* n sequential setitem calls. val_off[i]==val_off[i+1] stores a key-only record
+ * (PiXiuCtrl.cpp:41-44).  rc[i] = 0 or PIXIU_CBT_SET_REPLACE; saved[i] = doc_len - encoded_len
+ * (main.cpp:67); either may be NULL.  Host pointers. */
+int pixiu_setitem_batch(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off,
+                        const uint8_t *vals, const int64_t *val_off, int32_t *rc, int32_t *saved);
+/* same with DEVICE pointers for keys/key_off/vals/val_off (inputs already in HBM) */
+int pixiu_setitem_batch_dev(pixiu_store *s, int64_t n, const uint8_t *d_keys, const int64_t *d_key_off,
+                            const uint8_t *d_vals, const int64_t *d_val_off, int32_t *rc, int32_t *saved);
+
+int pixiu_contains_batch(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off, uint8_t *found);
+int pixiu_delitem_batch(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off, int32_t *rc);
+
+/* Decoded records `esc(k) 251 0 [esc(v) 251 2]` (what draining PXSGen yields, README.md:157)
+ * packed into out[0..out_off[n]); absent keys get an empty slot and found[i]=0.
+ * Returns PIXIU_ENOSPC with *need set when out_cap is too small (pass out_cap=0 to query). */
+int pixiu_getitem_batch(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off,
+                        uint8_t *out, int64_t out_cap, int64_t *out_off, uint8_t *found, int64_t *need);
+/* same, output left in device memory (d_out: device pointer, out_off/found: host) */
+int pixiu_getitem_batch_dev(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off,
+                            uint8_t *d_out, int64_t out_cap, int64_t *out_off, uint8_t *found, int64_t *need);
+
+/* iter(prefix): decoded records of all live keys starting with `prefix`, ascending key
+ * order (CritBitTree.h:55-157). *count = number of records. */
+int pixiu_iter(pixiu_store *s, const uint8_t *prefix, int64_t prefix_len, uint8_t *out, int64_t out_cap,
+               int64_t *out_off, int64_t off_cap, int64_t *count, int64_t *need);
+
+/* encoded bytes of record (chunk, idx) copied to out; returns length or negative error */
+int pixiu_encoded_view(pixiu_store *s, int64_t chunk, int64_t idx, uint8_t *out, int64_t out_cap);
+/* (chunk, idx) of the i-th record ever inserted */
+int pixiu_record_location(pixiu_store *s, int64_t record, int64_t *chunk, int64_t *idx);
+
+/* Import one pre-encoded chunk (array of PiXiu-encoded records, e.g. produced by the
+ * reference) as a new closed chunk and index its keys; used by parity tests and as the
+ * load path of a serialised store.  Returns the chunk id or a negative error. */
+int64_t pixiu_import_chunk(pixiu_store *s, int64_t n, const uint8_t *enc, const int64_t *enc_off);
+
+/* Decode every record of one chunk (tombstoned included) in idx order. */
+int pixiu_decode_chunk(pixiu_store *s, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *need);
+
+/* force the open window to close (next setitem starts a new chunk) */
+int pixiu_rotate(pixiu_store *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

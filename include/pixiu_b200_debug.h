@@ -1,0 +1,16 @@
+/* Test hooks of libpixiu_b200.so — used by tests/ only, not part of the drop-in surface. */
+#ifndef PIXIU_B200_DEBUG_H
+#define PIXIU_B200_DEBUG_H
+#include "pixiu_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* GPU radix sort (radix_sort.cuh) of host (key,value) pairs on bits [0,end_bit); vals == NULL sorts indices */
+int pixiu_debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, int64_t n, int end_bit, uint32_t *vals_out);
+/* copy an internal array of the last encode of the open window (sa, rank, lcp, reach, off, prevp, nextp: u32;
+ * text, flagp, flagc: u8; dist: u16); returns the window length */
+int64_t pixiu_debug_window_array(pixiu_store *s, const char *name, void *out, int64_t cap_bytes);
+#ifdef __cplusplus
+}
+#endif
+#endif

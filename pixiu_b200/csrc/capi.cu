@@ -1,0 +1,427 @@
+// C ABI (include/pixiu_b200.h) over the Store: argument checking, staging of host batches,
+// error translation.  No compute happens here.
+#include <algorithm>
+#include <cstring>
+
+#include "index.h"
+#include "store.h"
+
+namespace pixiu {
+
+Store::~Store() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (st) cudaStreamDestroy(st);
+}
+
+void Store::init(const pixiu_config &c) {
+    cfg = c;
+    PX_CUDA(cudaSetDevice(cfg.device));
+    PX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    PX_CUDA(cudaEventCreate(&ev0));
+    PX_CUDA(cudaEventCreate(&ev1));
+    index.reset(new HostIndex());
+}
+
+void Store::grow_record_tables(size_t n_total, uint64_t enc_total, uint64_t tiles_total) {
+    const size_t n_old = n_records();
+    d_enc.reserve_keep(enc_total + 64, enc_bytes, st);
+    d_enc_off.reserve_keep(n_total + 1, n_old, st);
+    d_enc_len.reserve_keep(n_total + 1, n_old, st);
+    d_dec_len.reserve_keep(n_total + 1, n_old, st);
+    d_first.reserve_keep(n_total + 1, n_old, st);
+    d_tile_base.reserve_keep(n_total + 1, n_old, st);
+    d_tile_desc.reserve_keep(tiles_total + 2, n_tiles, st);
+}
+
+void Store::open_window() {
+    win_open = true;
+    win_R = 0;
+    win_N = 0;
+    h_win_rec_start.assign(1, 0u);
+    chunk_first.push_back((uint32_t) n_records());
+    chunk_count.push_back(0);
+}
+
+void Store::close_window() {
+    // SuffixTree::free_prop + init_prop (PiXiuCtrl.cpp:13-17): the uncompressed window is dropped
+    win_open = false;
+    win_R = 0;
+    win_N = 0;
+    h_win_rec_start.clear();
+}
+
+}  // namespace pixiu
+
+using pixiu::Store;
+
+struct pixiu_store {
+    Store s;
+};
+
+namespace {
+template <typename F>
+int guarded(pixiu_store *h, F &&f) {
+    if (!h) return PIXIU_EINVAL;
+    try {
+        cudaSetDevice(h->s.cfg.device);
+        return f(h->s);
+    } catch (const pixiu::CudaError &e) {
+        h->s.err = e.what();
+        return PIXIU_ECUDA;
+    } catch (const std::exception &e) {
+        h->s.err = e.what();
+        return PIXIU_EINTERNAL;
+    }
+}
+
+// stage a packed host batch on the device: returns rebased offsets on the device
+void stage(Store &S, int64_t n, const uint8_t *data, const int64_t *off, pixiu::DevBuf<uint8_t> &d_data,
+           pixiu::DevBuf<int64_t> &d_off) {
+    const int64_t bytes = off[n] - off[0];
+    d_data.reserve_discard((size_t) bytes + 16);
+    d_off.reserve_discard((size_t) n + 1);
+    if (bytes) PX_CUDA(cudaMemcpyAsync(d_data.p, data + off[0], (size_t) bytes, cudaMemcpyHostToDevice, S.st));
+    if (off[0] == 0) {
+        PX_CUDA(cudaMemcpyAsync(d_off.p, off, (size_t) (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, S.st));
+    } else {
+        std::vector<int64_t> rel((size_t) n + 1);
+        for (int64_t i = 0; i <= n; i++) rel[i] = off[i] - off[0];
+        PX_CUDA(cudaMemcpyAsync(d_off.p, rel.data(), (size_t) (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, S.st));
+        PX_CUDA(cudaStreamSynchronize(S.st));
+    }
+}
+
+bool offsets_ok(int64_t n, const int64_t *off) {
+    if (!off) return false;
+    for (int64_t i = 0; i < n; i++)
+        if (off[i + 1] < off[i]) return false;
+    return true;
+}
+
+// decode `recs` into a device buffer laid out by out_off; shared by getitem / iter / decode_chunk
+int decode_to(Store &S, const std::vector<uint32_t> &recs, const std::vector<uint64_t> &offs, uint8_t *out,
+              int64_t out_cap, bool out_is_device, int64_t *need) {
+    const uint64_t total = offs.back();
+    if (need) *need = (int64_t) total;
+    if ((int64_t) total > out_cap) return PIXIU_ENOSPC;
+    if (recs.empty() || total == 0) return PIXIU_OK;
+    if (out_is_device) {
+        S.decode_records(recs, out, offs);
+    } else {
+        S.out_stage.reserve_discard(total + 64);
+        S.decode_records(recs, S.out_stage.p, offs);
+        PX_CUDA(cudaMemcpyAsync(out, S.out_stage.p, total, cudaMemcpyDeviceToHost, S.st));
+        PX_CUDA(cudaStreamSynchronize(S.st));
+    }
+    return PIXIU_OK;
+}
+
+int getitem_common(Store &S, int64_t n, const uint8_t *keys, const int64_t *key_off, uint8_t *out, int64_t out_cap,
+                   int64_t *out_off, uint8_t *found, int64_t *need, bool dev) {
+    if (n < 0 || (n && (!keys || !offsets_ok(n, key_off))) || !out_off) return PIXIU_EINVAL;
+    std::vector<uint32_t> rec;
+    pixiu::lookup_batch(S, n, keys, key_off, rec);
+    std::vector<uint32_t> recs;
+    std::vector<uint64_t> offs(1, 0);
+    out_off[0] = 0;
+    for (int64_t i = 0; i < n; i++) {
+        bool f = rec[i] != 0xFFFFFFFFu;
+        if (found) found[i] = f;
+        if (f) {
+            recs.push_back(rec[i]);
+            offs.push_back(offs.back() + S.h_dec_len[rec[i]]);
+        }
+        out_off[i + 1] = (int64_t) offs.back();
+    }
+    return decode_to(S, recs, offs, out, out_cap, dev, need);
+}
+}  // namespace
+
+extern "C" {
+
+void pixiu_default_config(pixiu_config *cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->rotate_policy = PIXIU_ROTATE_REFERENCE;
+    cfg->window_bytes = 12500000;
+    cfg->strict251 = 0;
+}
+
+pixiu_store *pixiu_create(const pixiu_config *cfg) {
+    pixiu_config c;
+    if (cfg) c = *cfg;
+    else pixiu_default_config(&c);
+    if (c.window_bytes <= 0) c.window_bytes = 12500000;
+    pixiu_store *h = nullptr;
+    try {
+        h = new pixiu_store();
+        h->s.init(c);
+        return h;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "pixiu_create: %s\n", e.what());
+        delete h;
+        return nullptr;
+    }
+}
+
+void pixiu_destroy(pixiu_store *h) {
+    if (!h) return;
+    cudaSetDevice(h->s.cfg.device);
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+const char *pixiu_last_error(const pixiu_store *h) { return h ? h->s.err.c_str() : "null store"; }
+
+int pixiu_get_stats(pixiu_store *h, pixiu_stats *o) {
+    if (!h || !o) return PIXIU_EINVAL;
+    Store &S = h->s;
+    o->records = (int64_t) S.n_records();
+    o->live_records = S.live_records;
+    o->chunks = (int64_t) S.n_chunks();
+    o->raw_bytes = S.raw_bytes;
+    o->doc_bytes = S.doc_bytes;
+    o->encoded_bytes = (int64_t) S.enc_bytes;
+    o->window_bytes = S.win_open ? S.win_N : 0;
+    o->kernel_launches = S.launches;
+    o->last_setitem_gpu_ms = S.last_set_ms;
+    o->last_getitem_gpu_ms = S.last_get_ms;
+    o->last_lookup_gpu_ms = S.last_lookup_ms;
+    return PIXIU_OK;
+}
+
+int pixiu_setitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, const uint8_t *vals,
+                        const int64_t *val_off, int32_t *rc, int32_t *saved) {
+    return guarded(h, [&](Store &S) -> int {
+        if (n < 0 || (n && (!keys || !offsets_ok(n, key_off) || !offsets_ok(n, val_off)))) return PIXIU_EINVAL;
+        if (n == 0) return PIXIU_OK;
+        if (val_off[n] > val_off[0] && !vals) return PIXIU_EINVAL;
+        stage(S, n, keys, key_off, S.in_keys, S.in_koff);
+        stage(S, n, vals, val_off, S.in_vals, S.in_voff);
+        return S.setitem_batch(n, S.in_keys.p, S.in_koff.p, S.in_vals.p, S.in_voff.p, keys, key_off, val_off, rc, saved);
+    });
+}
+
+int pixiu_setitem_batch_dev(pixiu_store *h, int64_t n, const uint8_t *d_keys, const int64_t *d_key_off,
+                            const uint8_t *d_vals, const int64_t *d_val_off, int32_t *rc, int32_t *saved) {
+    return guarded(h, [&](Store &S) -> int {
+        if (n < 0 || (n && (!d_keys || !d_key_off || !d_val_off))) return PIXIU_EINVAL;
+        if (n == 0) return PIXIU_OK;
+        // the host index needs the keys (small next to the values): copy keys + offsets back
+        std::vector<int64_t> koff((size_t) n + 1), voff((size_t) n + 1);
+        PX_CUDA(cudaMemcpyAsync(koff.data(), d_key_off, (size_t) (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, S.st));
+        PX_CUDA(cudaMemcpyAsync(voff.data(), d_val_off, (size_t) (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, S.st));
+        PX_CUDA(cudaStreamSynchronize(S.st));
+        if (koff[0] != 0 || voff[0] != 0 || !offsets_ok(n, koff.data()) || !offsets_ok(n, voff.data())) return PIXIU_EINVAL;
+        std::vector<uint8_t> hk((size_t) koff[n] + 1);
+        PX_CUDA(cudaMemcpyAsync(hk.data(), d_keys, (size_t) koff[n], cudaMemcpyDeviceToHost, S.st));
+        PX_CUDA(cudaStreamSynchronize(S.st));
+        return S.setitem_batch(n, d_keys, d_key_off, d_vals, d_val_off, hk.data(), koff.data(), voff.data(), rc, saved);
+    });
+}
+
+int pixiu_contains_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, uint8_t *found) {
+    return guarded(h, [&](Store &S) -> int {
+        if (n < 0 || (n && (!keys || !offsets_ok(n, key_off) || !found))) return PIXIU_EINVAL;
+        std::vector<uint32_t> rec;
+        pixiu::lookup_batch(S, n, keys, key_off, rec);
+        for (int64_t i = 0; i < n; i++) found[i] = rec[i] != 0xFFFFFFFFu;
+        return PIXIU_OK;
+    });
+}
+
+int pixiu_delitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, int32_t *rc) {
+    return guarded(h, [&](Store &S) -> int {
+        if (n < 0 || (n && (!keys || !offsets_ok(n, key_off)))) return PIXIU_EINVAL;
+        std::vector<uint8_t> q;
+        for (int64_t i = 0; i < n; i++) {
+            pixiu::escape_key(keys + key_off[i], (size_t) (key_off[i + 1] - key_off[i]), q);
+            int64_t r = S.index->del(q.data(), (uint32_t) q.size());
+            if (r >= 0) {
+                S.h_live[r] = 0;  // tombstone: bytes stay, later records may reference them (PiXiuStr.cpp:178-187)
+                S.live_records--;
+            }
+            if (rc) rc[i] = r >= 0 ? 0 : PIXIU_CBT_DEL_NOT_FOUND;
+        }
+        return PIXIU_OK;
+    });
+}
+
+int pixiu_getitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, uint8_t *out,
+                        int64_t out_cap, int64_t *out_off, uint8_t *found, int64_t *need) {
+    return guarded(h, [&](Store &S) -> int {
+        return getitem_common(S, n, keys, key_off, out, out_cap, out_off, found, need, false);
+    });
+}
+
+int pixiu_getitem_batch_dev(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, uint8_t *d_out,
+                            int64_t out_cap, int64_t *out_off, uint8_t *found, int64_t *need) {
+    return guarded(h, [&](Store &S) -> int {
+        return getitem_common(S, n, keys, key_off, d_out, out_cap, out_off, found, need, true);
+    });
+}
+
+int pixiu_iter(pixiu_store *h, const uint8_t *prefix, int64_t prefix_len, uint8_t *out, int64_t out_cap,
+               int64_t *out_off, int64_t off_cap, int64_t *count, int64_t *need) {
+    return guarded(h, [&](Store &S) -> int {
+        if (prefix_len < 0 || (prefix_len && !prefix) || !count) return PIXIU_EINVAL;
+        std::vector<uint8_t> q;
+        pixiu::escape_key(prefix, (size_t) prefix_len, q, false);
+        std::vector<uint32_t> recs;
+        S.index->iter(q.data(), (uint32_t) q.size(), recs);
+        *count = (int64_t) recs.size();
+        std::vector<uint64_t> offs(1, 0);
+        for (uint32_t g : recs) offs.push_back(offs.back() + S.h_dec_len[g]);
+        if (need) *need = (int64_t) offs.back();
+        if ((int64_t) recs.size() + 1 > off_cap || (int64_t) offs.back() > out_cap) return PIXIU_ENOSPC;
+        if (!out_off) return PIXIU_EINVAL;
+        for (size_t i = 0; i < offs.size(); i++) out_off[i] = (int64_t) offs[i];
+        return decode_to(S, recs, offs, out, out_cap, false, need);
+    });
+}
+
+int pixiu_encoded_view(pixiu_store *h, int64_t chunk, int64_t idx, uint8_t *out, int64_t out_cap) {
+    return guarded(h, [&](Store &S) -> int {
+        if (chunk < 0 || chunk >= (int64_t) S.n_chunks() || idx < 0 || idx >= (int64_t) S.chunk_count[chunk]) return PIXIU_EINVAL;
+        uint32_t g = S.chunk_first[chunk] + (uint32_t) idx;
+        uint32_t len = S.h_enc_len[g];
+        if ((int64_t) len > out_cap) return PIXIU_ENOSPC;
+        PX_CUDA(cudaMemcpyAsync(out, S.d_enc.p + S.h_enc_off[g], len, cudaMemcpyDeviceToHost, S.st));
+        PX_CUDA(cudaStreamSynchronize(S.st));
+        return (int) len;
+    });
+}
+
+int pixiu_record_location(pixiu_store *h, int64_t record, int64_t *chunk, int64_t *idx) {
+    if (!h || record < 0 || record >= (int64_t) h->s.n_records() || !chunk || !idx) return PIXIU_EINVAL;
+    Store &S = h->s;
+    uint32_t f = S.h_first[record];
+    size_t c = std::upper_bound(S.chunk_first.begin(), S.chunk_first.end(), (uint32_t) record) - S.chunk_first.begin() - 1;
+    *chunk = (int64_t) c;
+    *idx = record - f;
+    return PIXIU_OK;
+}
+
+int pixiu_decode_chunk(pixiu_store *h, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *need) {
+    return guarded(h, [&](Store &S) -> int {
+        if (chunk < 0 || chunk >= (int64_t) S.n_chunks() || !out_off) return PIXIU_EINVAL;
+        std::vector<uint32_t> recs;
+        std::vector<uint64_t> offs(1, 0);
+        for (uint32_t r = 0; r < S.chunk_count[chunk]; r++) {
+            uint32_t g = S.chunk_first[chunk] + r;
+            recs.push_back(g);
+            offs.push_back(offs.back() + S.h_dec_len[g]);
+        }
+        for (size_t i = 0; i < offs.size(); i++) out_off[i] = (int64_t) offs[i];
+        return decode_to(S, recs, offs, out, out_cap, false, need);
+    });
+}
+
+int64_t pixiu_import_chunk(pixiu_store *h, int64_t n, const uint8_t *enc, const int64_t *enc_off) {
+    int64_t chunk_id = -1;
+    int rc = guarded(h, [&](Store &S) -> int {
+        if (!enc || !offsets_ok(n, enc_off)) return PIXIU_EINVAL;
+        int64_t c = S.import_chunk(n, enc, enc_off);
+        if (c < 0) return (int) c;
+        chunk_id = c;
+        // index the keys: decode the chunk once and read each record's escaped key (up to 251,0)
+        std::vector<uint32_t> recs;
+        std::vector<uint64_t> offs(1, 0);
+        for (uint32_t r = 0; r < S.chunk_count[c]; r++) {
+            recs.push_back(S.chunk_first[c] + r);
+            offs.push_back(offs.back() + S.h_dec_len[recs.back()]);
+        }
+        std::vector<uint8_t> dec(offs.back() + 1);
+        int d = decode_to(S, recs, offs, dec.data(), (int64_t) dec.size(), false, nullptr);
+        if (d != PIXIU_OK) return d;
+        for (size_t r = 0; r < recs.size(); r++) {
+            const uint8_t *p = dec.data() + offs[r];
+            uint32_t len = (uint32_t) (offs[r + 1] - offs[r]), k = 0;
+            while (k + 1 < len && !(p[k] == 251 && p[k + 1] == 0)) k += (p[k] == 251) ? 2 : 1;
+            if (k + 1 >= len) return PIXIU_ECORRUPT;
+            int64_t old = S.index->set(p, k + 2, recs[r]);
+            if (old >= 0) {
+                S.h_live[old] = 0;
+                S.live_records--;
+            }
+            S.live_records++;
+            S.doc_bytes += len;
+        }
+        return PIXIU_OK;
+    });
+    return rc == PIXIU_OK ? chunk_id : rc;
+}
+
+int pixiu_rotate(pixiu_store *h) {
+    return guarded(h, [&](Store &S) -> int {
+        if (S.win_open) S.close_window();
+        return PIXIU_OK;
+    });
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------
+// debug / test hooks (declared in include/pixiu_b200_debug.h; used by tests/ only)
+// ---------------------------------------------------------------------------------
+extern "C" {
+
+// GPU radix sort of host (key,value) pairs on bits [0,end_bit); vals == NULL sorts indices.
+int pixiu_debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, int64_t n, int end_bit, uint32_t *vals_out) {
+    try {
+        PX_CUDA(cudaSetDevice(device));
+        pixiu::DevBuf<uint64_t> k0, k1;
+        pixiu::DevBuf<uint32_t> v0, v1, err;
+        pixiu::RadixSortTemp tmp;
+        k0.reserve_discard(n);
+        k1.reserve_discard(n);
+        v0.reserve_discard(n);
+        v1.reserve_discard(n);
+        err.reserve_discard(4);
+        PX_CUDA(cudaMemset(err.p, 0, 16));
+        PX_CUDA(cudaMemcpy(k0.p, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        if (vals) PX_CUDA(cudaMemcpy(v0.p, vals, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        int cur = pixiu::radix_sort_pairs<uint64_t>(k0.p, k1.p, v0.p, v1.p, (uint32_t) n, 0, end_bit, vals == nullptr,
+                                                    tmp, err.p, 0);
+        PX_CUDA(cudaDeviceSynchronize());
+        PX_CUDA(cudaMemcpy(keys, cur ? k1.p : k0.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        PX_CUDA(cudaMemcpy(vals_out, cur ? v1.p : v0.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        uint32_t e = 0;
+        PX_CUDA(cudaMemcpy(&e, err.p, 4, cudaMemcpyDeviceToHost));
+        return e ? PIXIU_EINTERNAL : PIXIU_OK;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "pixiu_debug_sort_pairs: %s\n", e.what());
+        return PIXIU_ECUDA;
+    }
+}
+
+// copies an internal array of the last encode (open window) to the host:
+// name in {"sa","rank","lcp","reach","off","prevp","nextp"} -> u32[win_N]; {"text","flagp","flagc"} -> u8[win_N]
+int64_t pixiu_debug_window_array(pixiu_store *h, const char *name, void *out, int64_t cap_bytes) {
+    if (!h || !name) return PIXIU_EINVAL;
+    Store &S = h->s;
+    std::string nm(name);
+    const void *src = nullptr;
+    size_t esz = 4;
+    if (nm == "sa") src = S.es.sa.p;
+    else if (nm == "rank") src = S.es.rank.p;
+    else if (nm == "lcp") src = S.es.lcp.p;
+    else if (nm == "reach") src = S.es.reach.p;
+    else if (nm == "off") src = S.es.off.p;
+    else if (nm == "prevp") src = S.es.prevp.p;
+    else if (nm == "nextp") src = S.es.nextp.p;
+    else if (nm == "text") { src = S.w_text.p; esz = 1; }
+    else if (nm == "flagp") { src = S.es.flagp.p; esz = 1; }
+    else if (nm == "flagc") { src = S.es.flagc.p; esz = 1; }
+    else if (nm == "dist") { src = S.w_dist.p; esz = 2; }
+    if (!src) return PIXIU_EINVAL;
+    size_t bytes = (size_t) S.win_N * esz;
+    if ((int64_t) bytes > cap_bytes) return PIXIU_ENOSPC;
+    cudaSetDevice(S.cfg.device);
+    if (cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return PIXIU_ECUDA;
+    return (int64_t) S.win_N;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Common host/device helpers for the pixiu_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+namespace pixiu {
+
+struct CudaError : std::runtime_error {
+    cudaError_t code;
+    CudaError(cudaError_t c, const char *what_, const char *file, int line)
+        : std::runtime_error(std::string(what_) + ": " + cudaGetErrorString(c) + " @" + file + ":" + std::to_string(line)),
+          code(c) {}
+};
+
+#define PX_CUDA(expr)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) throw ::pixiu::CudaError(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define PX_LAUNCH_CHECK() PX_CUDA(cudaGetLastError())
+
+template <typename T>
+static inline T div_up(T a, T b) { return (a + b - 1) / b; }
+
+// Growable device array (capacity doubling).  HBM is 180 GB: slack is cheap, realloc is not.
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;   // elements
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // ensure capacity >= n elements; contents are NOT preserved
+    void reserve_discard(size_t n) {
+        if (n <= cap) return;
+        release();
+        size_t want = n + n / 4 + 256;
+        PX_CUDA(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+    }
+    // ensure capacity >= n elements, preserving the first `keep` elements
+    void reserve_keep(size_t n, size_t keep, cudaStream_t st) {
+        if (n <= cap) return;
+        size_t want = n + n / 2 + 256;
+        T *q = nullptr;
+        PX_CUDA(cudaMalloc(&q, want * sizeof(T)));
+        if (p && keep) PX_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        if (p) {
+            PX_CUDA(cudaStreamSynchronize(st));
+            cudaFree(p);
+        }
+        p = q;
+        cap = want;
+    }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#endif
+
+}  // namespace pixiu

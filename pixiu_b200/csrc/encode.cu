@@ -1,0 +1,811 @@
+// setitem hot path: batched compression of incoming records against the open window.
+//
+// Replaces, with flat-array kernels (all HBM-bound integer work, no tensor cores):
+//   doc assembly + 251 escaping   PiXiuCtrl.cpp:31-44, PiXiuStr.cpp:228-271      -> k_doc_len, k_write_docs
+//   online suffix tree            SuffixTree.cpp:144-304 (+ScapegoatTree.h)       -> suffix array by prefix
+//                                 doubling over radix sort, LCP, block-min trees, longest previous factor
+//   stream encoder                PiXiuStr.cpp:16-118                              -> flag scatter, pair rule,
+//                                 run scans, output-size scan, token emission
+// The closed form (checked against the reference by the oracle and by
+// tests/pipeline_model.py):  M(s) = longest prefix of D[s..] starting earlier in the window,
+// reach(s) = s+M(s);  byte i is PASS iff i is a value of reach;  the pointer of a run ending at j
+// is the end of the leftmost occurrence of D[s*(j)..j],  s*(j) = min{s : reach(s) > j}.
+#include <algorithm>
+#include <cstring>
+
+#include "index.h"
+#include "scan.cuh"
+#include "store.h"
+
+namespace pixiu {
+
+// ---------------------------------------------------------------------------------
+// K1: doc assembly
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// doc_len[r] = |esc(k)| + 2 [+ |esc(v)| + 2]; 0xFFFFFFFF marks an empty key (invalid)
+__global__ void __launch_bounds__(256)
+k_doc_len(uint32_t n, const uint8_t *__restrict__ keys, const int64_t *__restrict__ koff,
+          const uint8_t *__restrict__ vals, const int64_t *__restrict__ voff, uint32_t *__restrict__ doc_len) {
+    uint32_t r = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const int lane = lane_id();
+    int64_t k0 = koff[r], k1 = koff[r + 1], v0 = voff[r], v1 = voff[r + 1];
+    uint32_t c = 0;
+    for (int64_t i = k0 + lane; i < k1; i += 32) c += keys[i] == 251;
+    for (int64_t i = v0 + lane; i < v1; i += 32) c += vals[i] == 251;
+    c = warp_sum(c);
+    if (lane == 0) {
+        uint64_t len = (uint64_t) (k1 - k0) + c + 2 + (v1 > v0 ? (uint64_t) (v1 - v0) + 2 : 0);
+        doc_len[r] = (k1 <= k0) ? 0xFFFFFFFFu : (len > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t) len);
+    }
+}
+
+__device__ __forceinline__ uint32_t write_escaped(const uint8_t *__restrict__ src, int64_t a, int64_t b,
+                                                  uint8_t *__restrict__ text, uint32_t dst) {
+    const int lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1;
+    for (int64_t base = a; base < b; base += 32) {
+        int64_t i = base + lane;
+        bool valid = i < b;
+        uint8_t byte = valid ? src[i] : 0;
+        bool esc = valid && byte == 251;
+        uint32_t bal = __ballot_sync(0xffffffffu, esc);
+        if (valid) {
+            uint32_t p = dst + lane + __popc(bal & lt);
+            text[p] = byte;
+            if (esc) text[p + 1] = 251;
+        }
+        int64_t cnt = b - base < 32 ? b - base : 32;
+        dst += (uint32_t) cnt + __popc(bal);
+    }
+    return dst;
+}
+
+// one warp per new record: text = esc(k) 251 0 [esc(v) 251 2] 0(separator); dist; recid
+__global__ void __launch_bounds__(256)
+k_write_docs(uint32_t n_new, uint32_t batch_first, uint32_t win_first, const uint8_t *__restrict__ keys,
+             const int64_t *__restrict__ koff, const uint8_t *__restrict__ vals, const int64_t *__restrict__ voff,
+             const uint32_t *__restrict__ rec_start, uint8_t *__restrict__ text, uint16_t *__restrict__ dist,
+             uint16_t *__restrict__ recid) {
+    uint32_t w = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (w >= n_new) return;
+    const int lane = lane_id();
+    const uint32_t src = batch_first + w, idx = win_first + w;
+    const uint32_t base = rec_start[idx], len = rec_start[idx + 1] - base - 1;
+    uint32_t dst = write_escaped(keys, koff[src], koff[src + 1], text, base);
+    if (lane == 0) {
+        text[dst] = 251;
+        text[dst + 1] = 0;
+    }
+    dst += 2;
+    int64_t v0 = voff[src], v1 = voff[src + 1];
+    if (v1 > v0) {
+        dst = write_escaped(vals, v0, v1, text, dst);
+        if (lane == 0) {
+            text[dst] = 251;
+            text[dst + 1] = 2;
+        }
+        dst += 2;
+    }
+    if (lane == 0) text[base + len] = 0;
+    for (uint32_t p = lane; p <= len; p += 32) {
+        dist[base + p] = (uint16_t) (len - p);
+        recid[base + p] = (uint16_t) idx;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K2-K4: suffix array by prefix doubling
+// ---------------------------------------------------------------------------------
+// initial key = first 7 symbols, 9 bits each (byte+1; 0 from the record end on)
+__global__ void __launch_bounds__(256)
+k_init_keys(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, uint32_t n, uint64_t *__restrict__ keys) {
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t d = dist[i];
+    uint64_t k = 0;
+#pragma unroll
+    for (int j = 0; j < 7; j++) k = (k << 9) | (uint64_t) (j < (int) d ? (uint32_t) text[i + j] + 1u : 0u);
+    keys[i] = k;
+}
+
+struct HeadFn {
+    const uint64_t *keys;
+    uint32_t n;
+    int initial;
+    __device__ __forceinline__ bool operator()(uint32_t a) const {
+        if (a == 0 || a >= n) return true;
+        uint64_t k = keys[a];
+        if (k != keys[a - 1]) return true;
+        return initial && (k & 0x1ff) == 0;  // a suffix that hit its record end is its own group
+    }
+};
+
+// key'[x] = (group << kb) | rank[val[x] + h]
+__global__ void __launch_bounds__(256)
+k_round_keys(uint32_t A, const uint32_t *__restrict__ vals, const uint32_t *__restrict__ gk,
+             const uint32_t *__restrict__ rank, uint32_t h, int kb, uint64_t *__restrict__ keys) {
+    uint32_t x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= A) return;
+    keys[x] = ((uint64_t) gk[x] << kb) | (uint64_t) rank[vals[x] + h];
+}
+
+// ---------------------------------------------------------------------------------
+// K5: LCP (Kasai over 32-position segments; restarts cost one direct compare per segment)
+// ---------------------------------------------------------------------------------
+constexpr int LCP_SEG = 32;
+__global__ void __launch_bounds__(128)
+k_lcp(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const uint32_t *__restrict__ sa,
+      const uint32_t *__restrict__ rank, uint32_t n, uint32_t *__restrict__ lcp) {
+    uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    uint64_t i0 = (uint64_t) t * LCP_SEG;
+    if (i0 >= n) return;
+    uint32_t i1 = (uint32_t) (i0 + LCP_SEG < n ? i0 + LCP_SEG : n);
+    uint32_t h = 0;
+    for (uint32_t i = (uint32_t) i0; i < i1; i++) {
+        uint32_t r = rank[i];
+        if (r == 0) {
+            lcp[0] = 0;
+            h = 0;
+            continue;
+        }
+        uint32_t p = sa[r - 1];
+        uint32_t lim = min((uint32_t) dist[i], (uint32_t) dist[p]);
+        if (h > lim) h = lim;
+        while (h < lim && text[i + h] == text[p + h]) h++;
+        lcp[r] = h;
+        if (h) h--;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// block-min trees over sa and lcp
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tree_level(const uint32_t *__restrict__ in_a, const uint32_t *__restrict__ in_l, uint32_t n_in,
+             uint32_t *__restrict__ out_a, uint32_t *__restrict__ out_l, uint32_t n_out) {
+    uint32_t o = blockIdx.x * 256 + threadIdx.x;
+    if (o >= n_out) return;
+    uint32_t b = o * TREE_B, e = min(b + TREE_B, n_in);
+    uint32_t ma = 0xFFFFFFFFu, ml = 0xFFFFFFFFu;
+    for (uint32_t j = b; j < e; j++) {
+        ma = min(ma, in_a[j]);
+        ml = min(ml, in_l[j]);
+    }
+    out_a[o] = ma;
+    out_l[o] = ml;
+}
+
+// Generic nearest-smaller search over the block-min tree.
+//  LEFT : visits j = start-1, start-2, ...      RIGHT: visits j = start+1, start+2, ...
+//  stops at the first visited j with KEY[j] < thr and returns it (else -1 / n).
+//  acc = min of ACC over the visited elements; INCL decides whether the found element counts.
+//  The walk gives up early (returns not-found) once acc <= floor_ — the caller cannot improve.
+//  KEYA: KEY is the sa tree (ACC the lcp tree); otherwise KEY is the lcp tree (ACC the sa tree).
+template <bool LEFT, bool INCL, bool KEYA>
+__device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start, uint32_t thr, uint32_t &acc,
+                                               uint32_t floor_) {
+    auto KEY = [&](int lv, uint32_t j) { return KEYA ? T.a[lv][j] : T.l[lv][j]; };
+    auto ACC = [&](int lv, uint32_t j) { return KEYA ? T.l[lv][j] : T.a[lv][j]; };
+    int lv = 0;
+    int64_t pos = start;  // in units of level lv; entries beyond pos (in walk direction) are unvisited
+    const int64_t NOTFOUND = LEFT ? -1 : (int64_t) T.size[0];
+    int64_t hit = -1;
+    // ---- ascend ----
+    while (true) {
+        bool found = false;
+        if (LEFT) {
+            while (pos % TREE_B != 0) {
+                pos--;
+                uint32_t k = KEY(lv, (uint32_t) pos);
+                if (lv == 0) {
+                    if (INCL) acc = min(acc, ACC(0, (uint32_t) pos));
+                    if (k < thr) return pos;
+                    if (!INCL) acc = min(acc, ACC(0, (uint32_t) pos));
+                } else {
+                    if (k < thr) { found = true; hit = pos; break; }
+                    acc = min(acc, ACC(lv, (uint32_t) pos));
+                }
+                if (acc <= floor_) return NOTFOUND;
+            }
+            if (found) break;
+            if (pos == 0) return NOTFOUND;
+            pos /= TREE_B;
+        } else {
+            while ((pos + 1) % TREE_B != 0 && pos + 1 < (int64_t) T.size[lv]) {
+                pos++;
+                uint32_t k = KEY(lv, (uint32_t) pos);
+                if (lv == 0) {
+                    if (INCL) acc = min(acc, ACC(0, (uint32_t) pos));
+                    if (k < thr) return pos;
+                    if (!INCL) acc = min(acc, ACC(0, (uint32_t) pos));
+                } else {
+                    if (k < thr) { found = true; hit = pos; break; }
+                    acc = min(acc, ACC(lv, (uint32_t) pos));
+                }
+                if (acc <= floor_) return NOTFOUND;
+            }
+            if (found) break;
+            if (pos + 1 >= (int64_t) T.size[lv]) return NOTFOUND;
+            pos /= TREE_B;
+        }
+        lv++;
+        if (lv >= T.nlev) return NOTFOUND;
+    }
+    // ---- descend into entry `hit` of level lv (lv >= 1): the answer is inside ----
+    while (lv > 0) {
+        int64_t b = hit * TREE_B, e = b + TREE_B < (int64_t) T.size[lv - 1] ? b + TREE_B : (int64_t) T.size[lv - 1];
+        lv--;
+        bool found = false;
+        if (LEFT) {
+            for (int64_t c = e - 1; c >= b; c--) {
+                uint32_t k = KEY(lv, (uint32_t) c);
+                if (lv == 0) {
+                    if (INCL) acc = min(acc, ACC(0, (uint32_t) c));
+                    if (k < thr) return c;
+                    if (!INCL) acc = min(acc, ACC(0, (uint32_t) c));
+                } else {
+                    if (k < thr) { hit = c; found = true; break; }
+                    acc = min(acc, ACC(lv, (uint32_t) c));
+                }
+                if (acc <= floor_) return NOTFOUND;
+            }
+        } else {
+            for (int64_t c = b; c < e; c++) {
+                uint32_t k = KEY(lv, (uint32_t) c);
+                if (lv == 0) {
+                    if (INCL) acc = min(acc, ACC(0, (uint32_t) c));
+                    if (k < thr) return c;
+                    if (!INCL) acc = min(acc, ACC(0, (uint32_t) c));
+                } else {
+                    if (k < thr) { hit = c; found = true; break; }
+                    acc = min(acc, ACC(lv, (uint32_t) c));
+                }
+                if (acc <= floor_) return NOTFOUND;
+            }
+        }
+        if (!found) return NOTFOUND;  // cannot happen: the block minimum promised a hit
+    }
+    return NOTFOUND;
+}
+
+// ---------------------------------------------------------------------------------
+// K6: longest previous factor. reach[s] = s + M(s) for the new positions s >= s0.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_lpf(MinTree T, const uint32_t *__restrict__ rank, const uint16_t *__restrict__ dist, uint32_t s0, uint32_t n,
+      uint32_t *__restrict__ reach) {
+    uint32_t s = s0 + blockIdx.x * 256 + threadIdx.x;
+    if (s >= n) return;
+    uint32_t best = 0;
+    if (dist[s] != 0) {
+        uint32_t r = rank[s];
+        // nearest smaller text position above r: lcp = min L[j+1..r]
+        uint32_t acc = T.l[0][r];
+        int64_t j = acc ? tree_search<true, false, true>(T, r, s, acc, 0u) : -1;
+        if (j >= 0) best = acc;
+        // nearest smaller text position below r: lcp = min L[r+1..j]
+        acc = 0xFFFFFFFFu;
+        j = tree_search<false, true, true>(T, r, s, acc, best);
+        if (j < (int64_t) n && acc > best) best = acc;
+    }
+    reach[s] = s + best;
+}
+
+// ---------------------------------------------------------------------------------
+// K7: flags
+// ---------------------------------------------------------------------------------
+// PASS flags = image of reach, plus the separators
+__global__ void __launch_bounds__(256)
+k_flag_scatter(const uint32_t *__restrict__ reach, const uint16_t *__restrict__ dist, uint32_t s0, uint32_t n,
+               uint8_t *__restrict__ flagp) {
+    uint32_t s = s0 + blockIdx.x * 256 + threadIdx.x;
+    if (s >= n) return;
+    if (dist[s] == 0) flagp[s] = 1;
+    else flagp[reach[s]] = 1;
+}
+
+// escape-pair coherence (PiXiuStr.cpp:34-54): flagc[i] = 1 iff byte i stays COMPRESS
+__global__ void __launch_bounds__(256)
+k_pair_rule(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const uint8_t *__restrict__ flagp,
+            const uint32_t *__restrict__ lastnon, uint32_t s0, uint32_t n, uint8_t *__restrict__ flagc) {
+    uint32_t i = s0 + blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (dist[i] == 0) {
+        flagc[i] = 0;
+        return;
+    }
+    bool c = !flagp[i];
+    int64_t partner = -1;
+    if (text[i] == 251) {
+        uint32_t k = i - lastnon[i];  // 1-based position inside the run of 251s (lastnon is +1 biased)
+        partner = (k & 1) ? (int64_t) i + 1 : (int64_t) i - 1;
+    } else if (i > s0 && text[i - 1] == 251 && ((i - 1 - lastnon[i - 1]) & 1)) {
+        partner = (int64_t) i - 1;
+    }
+    if (partner >= 0 && partner < (int64_t) n && dist[partner] != 0 && flagp[partner]) c = false;
+    flagc[i] = c;
+}
+
+// output bytes contributed by position i: PASS / short run byte -> 1; last byte of a long run -> 6 or 8
+__device__ __forceinline__ uint32_t contrib_at(uint32_t i, const uint8_t *flagc, const uint16_t *dist,
+                                               const uint32_t *prevp, const uint32_t *nextp, int strict251) {
+    if (dist[i] == 0) return 0;
+    if (!flagc[i]) return 1;
+    uint32_t rl = nextp[i] - prevp[i];  // prevp is +1 biased: run = [prevp, nextp)
+    if (rl <= 6) return 1;
+    if (i != nextp[i] - 1) return 0;
+    return (rl > 255 || (rl == 251 && !strict251)) ? 8 : 6;
+}
+
+// ---------------------------------------------------------------------------------
+// K8+K9: run-end pointer query and emission
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_emit(MinTree T, const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist,
+       const uint16_t *__restrict__ recid, const uint32_t *__restrict__ rec_start, const uint32_t *__restrict__ rank,
+       const uint32_t *__restrict__ reach, const uint8_t *__restrict__ flagc, const uint32_t *__restrict__ prevp,
+       const uint32_t *__restrict__ nextp, const uint32_t *__restrict__ off, uint32_t s0, uint32_t n, int strict251,
+       uint8_t *__restrict__ enc_out /* already offset so that off[] indexes it directly */, uint32_t *__restrict__ err) {
+    uint32_t i = s0 + blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = contrib_at(i, flagc, dist, prevp, nextp, strict251);
+    if (c == 0) return;
+    uint32_t o = off[i];
+    if (c == 1) {
+        enc_out[o] = text[i];
+        return;
+    }
+    // long run ending at i.  s* = min{s in record : reach(s) > i}
+    uint32_t rl = nextp[i] - prevp[i];
+    uint32_t rec = recid[i];
+    uint32_t lo = rec_start[rec], hi = i + 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (reach[mid] > i) hi = mid;
+        else lo = mid + 1;
+    }
+    uint32_t sstar = lo, E = i + 1 - sstar;
+    uint32_t r = rank[sstar];
+    uint32_t accl = 0xFFFFFFFFu, accr = 0xFFFFFFFFu;
+    // SA interval of D[s*..i]: [x, y) with L[x] < E and L[y] < E; leftmost occurrence = min sa over it
+    tree_search<true, true, false>(T, r + 1, E, accl, 0u);
+    tree_search<false, false, false>(T, r, E, accr, 0u);
+    uint32_t left = min(accl, accr);
+    if (left >= sstar || E < rl) {
+        atomicExch(err, 2u);
+        return;
+    }
+    uint32_t src = recid[left];
+    uint32_t to = left + E - rec_start[src];
+    enc_out[o] = 251;
+    if (c == 8) {
+        uint32_t from = to - rl;
+        enc_out[o + 1] = 1;
+        enc_out[o + 2] = (uint8_t) src;
+        enc_out[o + 3] = (uint8_t) (src >> 8);
+        enc_out[o + 4] = (uint8_t) to;
+        enc_out[o + 5] = (uint8_t) (to >> 8);
+        enc_out[o + 6] = (uint8_t) from;
+        enc_out[o + 7] = (uint8_t) (from >> 8);
+    } else {
+        enc_out[o + 1] = (uint8_t) rl;
+        enc_out[o + 2] = (uint8_t) src;
+        enc_out[o + 3] = (uint8_t) (src >> 8);
+        enc_out[o + 4] = (uint8_t) to;
+        enc_out[o + 5] = (uint8_t) (to >> 8);
+    }
+}
+
+// per new record: encoded offset/length, decoded length, tile descriptors
+__global__ void __launch_bounds__(256)
+k_record_tables(uint32_t n_new, uint32_t win_first, uint32_t g_first, uint32_t g_chunk_first,
+                const uint32_t *__restrict__ rec_start, const uint32_t *__restrict__ off, uint32_t off_s0,
+                uint64_t enc_base, uint64_t *__restrict__ rec_enc_off, uint32_t *__restrict__ rec_enc_len,
+                uint32_t *__restrict__ rec_dec_len, uint32_t *__restrict__ rec_first) {
+    uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= n_new) return;
+    uint32_t a = rec_start[win_first + r], b = rec_start[win_first + r + 1] - 1;
+    uint32_t g = g_first + r;
+    rec_enc_off[g] = enc_base + (off[a] - off_s0);
+    rec_enc_len[g] = off[b] - off[a];
+    rec_dec_len[g] = b - a;
+    rec_first[g] = g_chunk_first;
+}
+
+// tile descriptor: enc offset (within the record) of the token holding decoded byte t*TILE,
+// and how many bytes of that token lie before it
+__global__ void __launch_bounds__(256)
+k_tile_desc(uint32_t n_tiles_new, uint32_t tile_first, uint32_t n_new, uint32_t win_first, uint32_t g_first,
+            const uint32_t *__restrict__ rec_tile_base, const uint32_t *__restrict__ rec_start,
+            const uint32_t *__restrict__ off, const uint8_t *__restrict__ flagc, const uint32_t *__restrict__ prevp,
+            const uint32_t *__restrict__ nextp, const uint8_t *__restrict__ text, const uint32_t *__restrict__ lastnon,
+            uint32_t *__restrict__ tile_desc) {
+    uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= n_tiles_new) return;
+    uint32_t gt = tile_first + t;
+    // record owning tile gt: binary search over rec_tile_base[g_first .. g_first+n_new)
+    uint32_t lo = 0, hi = n_new;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (rec_tile_base[g_first + mid] <= gt) lo = mid;
+        else hi = mid;
+    }
+    uint32_t a = rec_start[win_first + lo];
+    uint32_t i = a + (gt - rec_tile_base[g_first + lo]) * TILE;
+    uint32_t skip = 0;
+    bool in_ref = false;
+    if (flagc[i]) {
+        uint32_t rl = nextp[i] - prevp[i];
+        if (rl > 6) {
+            skip = i - prevp[i];
+            in_ref = true;
+        }
+    }
+    if (!in_ref) {
+        // a tile that starts on the 2nd byte of an escape pair must take that byte literally
+        uint8_t b = text[i];
+        bool second = false;
+        if (b == 251) second = ((i - lastnon[i]) & 1) == 0;
+        else if (i > a && text[i - 1] == 251) second = ((i - 1 - lastnon[i - 1]) & 1) != 0;
+        if (second) skip = 0xFFFF;
+    }
+    tile_desc[gt] = (off[i] - off[a]) | (skip << 16);
+}
+
+// ---------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------
+static int bits_for(uint64_t v) {  // bits needed to represent values in [0, v]
+    int b = 0;
+    while (v) {
+        b++;
+        v >>= 1;
+    }
+    return b ? b : 1;
+}
+
+// Builds sa/rank over the window text [0, N)
+static void build_suffix_array(Store &S, uint32_t N) {
+    EncodeScratch &E = S.es;
+    cudaStream_t st = S.st;
+    E.keys0.reserve_discard(N);
+    E.keys1.reserve_discard(N);
+    E.vals0.reserve_discard(N);
+    E.vals1.reserve_discard(N);
+    E.slot0.reserve_discard(N);
+    E.slot1.reserve_discard(N);
+    E.gk.reserve_discard(N);
+    E.sa.reserve_discard(N);
+    E.rank.reserve_discard(N + 8);
+    E.scan_tmp.reserve_discard(scan_tmp_elems(N));
+    E.scan_tmp64.reserve_discard(scan_tmp_elems(N));
+    E.counters.reserve_discard(16);
+    PX_CUDA(cudaMemsetAsync(E.counters.p, 0, 16 * sizeof(uint32_t), st));
+    int L = 0;
+
+    k_init_keys<<<div_up<uint32_t>(N, 256), 256, 0, st>>>(S.w_text.p, S.w_dist.p, N, E.keys0.p);
+    L++;
+    int cur = radix_sort_pairs<uint64_t>(E.keys0.p, E.keys1.p, E.vals0.p, E.vals1.p, N, 0, 63, true, E.rs, E.counters.p + 2, st, &L);
+    uint64_t *skeys = cur ? E.keys1.p : E.keys0.p;
+    uint32_t *svals = cur ? E.vals1.p : E.vals0.p;
+    uint32_t *slot_cur = nullptr;  // nullptr: slot[a] = a (first round)
+    uint32_t *slot_next = E.slot0.p;
+    uint32_t A = N;
+    uint32_t h = 7;
+    const int kb = bits_for(N);
+    bool initial = true;
+    uint32_t *d_cnt = E.counters.p;
+    uint32_t *sa = E.sa.p, *rank = E.rank.p, *gk = E.gk.p;
+
+    while (true) {
+        HeadFn head{skeys, A, initial ? 1 : 0};
+        // (1) rank of every element = slot of its group head; write sa and rank
+        {
+            const uint32_t *sl = slot_cur;
+            const uint32_t *sv = svals;
+            device_scan<uint32_t>(
+                A, [=] __device__(size_t a) -> uint32_t { return head((uint32_t) a) ? (uint32_t) a : 0u; },
+                [=] __device__(size_t a, uint32_t hp) {
+                    uint32_t v = sv[a];
+                    sa[sl ? sl[a] : (uint32_t) a] = v;
+                    rank[v] = sl ? sl[hp] : hp;
+                },
+                OpMax(), 0u, false, E.scan_tmp.p, st);
+            L += 3;
+        }
+        // (2) keep the elements of groups larger than one; number the surviving groups
+        {
+            const uint32_t *sl = slot_cur;
+            const uint32_t *sv = svals;
+            uint32_t *sl_out = slot_next;
+            uint32_t *vals_out = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
+            uint32_t An = A;
+            device_scan<uint64_t>(
+                A,
+                [=] __device__(size_t a) -> uint64_t {
+                    bool hd = head((uint32_t) a), hn = head((uint32_t) a + 1);
+                    bool act = !(hd && hn);
+                    return act ? (1ull | ((uint64_t) hd << 32)) : 0ull;
+                },
+                [=] __device__(size_t a, uint64_t ex) {
+                    bool hd = head((uint32_t) a), hn = head((uint32_t) a + 1);
+                    bool act = !(hd && hn);
+                    uint32_t dst = (uint32_t) ex, g = (uint32_t) (ex >> 32);
+                    if (act) {
+                        sl_out[dst] = sl ? sl[a] : (uint32_t) a;
+                        vals_out[dst] = sv[a];
+                        gk[dst] = hd ? g : g - 1;
+                    }
+                    if (a == An - 1) {
+                        d_cnt[0] = dst + (act ? 1u : 0u);
+                        d_cnt[1] = g + ((act && hd) ? 1u : 0u);
+                    }
+                },
+                OpSum(), 0ull, true, E.scan_tmp64.p, st);
+            L += 3;
+            svals = vals_out;  // compacted values (unsorted for the next key) live here now
+        }
+        uint32_t h_cnt[3];
+        PX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaStreamSynchronize(st));
+        if (h_cnt[2]) throw std::runtime_error("radix sort look-back timed out");
+        uint32_t An = h_cnt[0], G = h_cnt[1];
+        if (An == 0) break;
+        if (h > 65535u) throw std::runtime_error("suffix array: groups left after h > 65535");
+        // (3) next keys: (group, rank[i+h]) and sort
+        uint64_t *kin = E.keys0.p, *kalt = E.keys1.p;
+        k_round_keys<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, svals, gk, rank, h, kb, kin);
+        L++;
+        uint32_t *vin = svals, *valt = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
+        int gb = bits_for(G ? G - 1 : 0);
+        int c2 = radix_sort_pairs<uint64_t>(kin, kalt, vin, valt, An, 0, kb + gb, false, E.rs, E.counters.p + 2, st, &L);
+        skeys = c2 ? kalt : kin;
+        svals = c2 ? valt : vin;
+        slot_cur = slot_next;
+        slot_next = (slot_next == E.slot0.p) ? E.slot1.p : E.slot0.p;
+        A = An;
+        h *= 2;
+        initial = false;
+    }
+    S.launches += L;
+}
+
+void Store::encode_window_records(uint32_t first_new) {
+    EncodeScratch &E = es;
+    const uint32_t N = win_N, R = win_R;
+    const uint32_t s0 = h_win_rec_start[first_new];
+    const uint32_t n_new = R - first_new;
+    const uint32_t M = N - s0;  // new positions
+    int L = 0;
+
+    build_suffix_array(*this, N);
+
+    // ---- LCP + trees ----
+    E.lcp.reserve_discard(N);
+    k_lcp<<<div_up<uint32_t>(div_up<uint32_t>(N, LCP_SEG), 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, N, E.lcp.p);
+    L++;
+    MinTree T{};
+    {
+        size_t total = 0;
+        uint32_t sz = N;
+        int nlev = 1;
+        while (sz > 1 && nlev < TREE_MAX_LEVELS) {
+            sz = div_up<uint32_t>(sz, TREE_B);
+            total += sz;
+            nlev++;
+        }
+        E.tree_a.reserve_discard(total + 1);
+        E.tree_l.reserve_discard(total + 1);
+        T.a[0] = E.sa.p;
+        T.l[0] = E.lcp.p;
+        T.size[0] = N;
+        T.nlev = 1;
+        sz = N;
+        size_t o = 0;
+        while (sz > 1 && T.nlev < TREE_MAX_LEVELS) {
+            uint32_t so = div_up<uint32_t>(sz, TREE_B);
+            k_tree_level<<<div_up<uint32_t>(so, 256), 256, 0, st>>>(T.a[T.nlev - 1], T.l[T.nlev - 1], sz,
+                                                                     E.tree_a.p + o, E.tree_l.p + o, so);
+            L++;
+            T.a[T.nlev] = E.tree_a.p + o;
+            T.l[T.nlev] = E.tree_l.p + o;
+            T.size[T.nlev] = so;
+            T.nlev++;
+            o += so;
+            sz = so;
+        }
+    }
+
+    // ---- M / reach, flags ----
+    E.reach.reserve_discard(N + 1);
+    E.flagp.reserve_discard(N + 2);
+    E.flagc.reserve_discard(N + 2);
+    E.lastnon.reserve_discard(N + 1);
+    E.prevp.reserve_discard(N + 1);
+    E.nextp.reserve_discard(N + 1);
+    E.off.reserve_discard(N + 2);
+    PX_CUDA(cudaMemsetAsync(E.flagp.p + s0, 0, (size_t) M + 2, st));
+    uint32_t gridM = div_up<uint32_t>(M, 256);
+    k_lpf<<<gridM, 256, 0, st>>>(T, E.rank.p, w_dist.p, s0, N, E.reach.p);
+    k_flag_scatter<<<gridM, 256, 0, st>>>(E.reach.p, w_dist.p, s0, N, E.flagp.p);
+    L += 2;
+    {
+        // lastnon[i] = index of the last non-251 byte at or before i (max-scan of index+1, stored -1).
+        // Position s0-1 is a separator (or the text start), i.e. "non-251": seed element 0 with it.
+        const uint8_t *text = w_text.p;
+        uint32_t *ln = E.lastnon.p;
+        device_scan<uint32_t>(
+            M,
+            [=] __device__(size_t k) -> uint32_t {
+                return text[s0 + k] != 251 ? (uint32_t) (s0 + k) + 1u : (k == 0 ? s0 : 0u);
+            },
+            [=] __device__(size_t k, uint32_t v) { ln[s0 + k] = v - 1u; }, OpMax(), 0u, false, E.scan_tmp.p, st);
+        L += 3;
+    }
+    k_pair_rule<<<gridM, 256, 0, st>>>(w_text.p, w_dist.p, E.flagp.p, E.lastnon.p, s0, N, E.flagc.p);
+    L++;
+    {
+        const uint8_t *fc = E.flagc.p;
+        uint32_t *pp = E.prevp.p, *np = E.nextp.p;
+        // prevp[i] = 1 + index of the last non-COMPRESS position at or before i  (run start if i is COMPRESS)
+        device_scan<uint32_t>(
+            M, [=] __device__(size_t k) -> uint32_t { return fc[s0 + k] ? (k == 0 ? s0 : 0u) : (uint32_t) (s0 + k) + 1u; },
+            [=] __device__(size_t k, uint32_t v) { pp[s0 + k] = v; }, OpMax(), 0u, false, E.scan_tmp.p, st);
+        // nextp[i] = index of the first non-COMPRESS position at or after i (suffix min-scan, reversed index)
+        const uint32_t last = N - 1;
+        device_scan<uint32_t>(
+            M, [=] __device__(size_t k) -> uint32_t { return fc[last - k] ? 0xFFFFFFFFu : (uint32_t) (last - k); },
+            [=] __device__(size_t k, uint32_t v) { np[last - k] = v; }, OpMin(), 0xFFFFFFFFu, false, E.scan_tmp.p, st);
+        L += 6;
+    }
+    {
+        const uint8_t *fc = E.flagc.p;
+        const uint16_t *dist = w_dist.p;
+        const uint32_t *pp = E.prevp.p, *np = E.nextp.p;
+        uint32_t *off = E.off.p;
+        const int strict = cfg.strict251;
+        // exclusive scan of the per-position output sizes; off[N] = total (one extra slot)
+        device_scan<uint32_t>(
+            (size_t) M + 1,
+            [=] __device__(size_t k) -> uint32_t { return k < M ? contrib_at(s0 + (uint32_t) k, fc, dist, pp, np, strict) : 0u; },
+            [=] __device__(size_t k, uint32_t v) { off[s0 + k] = v; }, OpSum(), 0u, true, E.scan_tmp.p, st);
+        L += 3;
+    }
+    uint32_t enc_total = 0;
+    PX_CUDA(cudaMemcpyAsync(&enc_total, E.off.p + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+
+    // ---- grow the store, emit ----
+    const size_t g_first = n_records();
+    uint64_t new_tiles = 0;
+    std::vector<uint32_t> tile_base(n_new);
+    for (uint32_t r = 0; r < n_new; r++) {
+        uint32_t dl = h_win_rec_start[first_new + r + 1] - h_win_rec_start[first_new + r] - 1;
+        tile_base[r] = (uint32_t) (n_tiles + new_tiles);
+        new_tiles += div_up<uint32_t>(dl, TILE);
+    }
+    grow_record_tables(g_first + n_new, enc_bytes + enc_total, n_tiles + new_tiles);
+    PX_CUDA(cudaMemcpyAsync(d_tile_base.p + g_first, tile_base.data(), n_new * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    uint32_t g_chunk_first = chunk_first.back();
+    k_emit<<<gridM, 256, 0, st>>>(T, w_text.p, w_dist.p, w_recid.p, w_rec_start.p, E.rank.p, E.reach.p, E.flagc.p,
+                                  E.prevp.p, E.nextp.p, E.off.p, s0, N, cfg.strict251, d_enc.p + enc_bytes,
+                                  E.counters.p + 2);
+    k_record_tables<<<div_up<uint32_t>(n_new, 256), 256, 0, st>>>(n_new, first_new, (uint32_t) g_first, g_chunk_first,
+                                                                  w_rec_start.p, E.off.p, 0u, enc_bytes, d_enc_off.p,
+                                                                  d_enc_len.p, d_dec_len.p, d_first.p);
+    if (new_tiles)
+        k_tile_desc<<<div_up<uint32_t>((uint32_t) new_tiles, 256), 256, 0, st>>>(
+            (uint32_t) new_tiles, (uint32_t) n_tiles, n_new, first_new, (uint32_t) g_first, d_tile_base.p,
+            w_rec_start.p, E.off.p, E.flagc.p, E.prevp.p, E.nextp.p, w_text.p, E.lastnon.p, d_tile_desc.p);
+    L += 3;
+    // host mirrors
+    size_t old = h_enc_len.size();
+    h_enc_off.resize(old + n_new);
+    h_enc_len.resize(old + n_new);
+    h_dec_len.resize(old + n_new);
+    h_first.resize(old + n_new, g_chunk_first);
+    h_tile_base.insert(h_tile_base.end(), tile_base.begin(), tile_base.end());
+    h_live.resize(old + n_new, 1);
+    PX_CUDA(cudaMemcpyAsync(h_enc_off.data() + old, d_enc_off.p + old, n_new * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(h_enc_len.data() + old, d_enc_len.p + old, n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(h_dec_len.data() + old, d_dec_len.p + old, n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    uint32_t errflag = 0;
+    PX_CUDA(cudaMemcpyAsync(&errflag, E.counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    if (errflag) throw std::runtime_error("encode: internal inconsistency (err=" + std::to_string(errflag) + ")");
+    enc_bytes += enc_total;
+    n_tiles += new_tiles;
+    chunk_count.back() += n_new;
+    launches += L;
+}
+
+int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals,
+                         const int64_t *d_voff, const uint8_t *h_keys, const int64_t *h_koff,
+                         const int64_t *h_voff, int32_t *rc, int32_t *saved) {
+    if (n == 0) return PIXIU_OK;
+    if (n > 0x7fffffff) return PIXIU_EINVAL;
+    const uint32_t nn = (uint32_t) n;
+    PX_CUDA(cudaEventRecord(ev0, st));
+    doc_len.reserve_discard(nn);
+    k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p);
+    launches++;
+    std::vector<uint32_t> h_doc_len(nn);
+    PX_CUDA(cudaMemcpyAsync(h_doc_len.data(), doc_len.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < nn; i++) {
+        if (h_doc_len[i] == 0xFFFFFFFFu) {
+            err = "setitem: empty key at record " + std::to_string(i);
+            return PIXIU_EINVAL;
+        }
+        if (h_doc_len[i] > MAX_DOC) {
+            err = "setitem: record " + std::to_string(i) + " longer than 65535 escaped bytes";
+            return PIXIU_ETOOLONG;
+        }
+    }
+    // the sort's look-back words carry 30-bit counts: a window never exceeds 2^30 - 2^17 positions
+    const int64_t hard_cap = (1ll << 30) - (1ll << 17);
+    const int64_t budget = cfg.rotate_policy == PIXIU_ROTATE_RECORDS ? hard_cap : std::min<int64_t>(cfg.window_bytes, hard_cap);
+    const size_t g_batch_first = n_records();
+    uint32_t a = 0;
+    while (a < nn) {
+        if (win_open && (win_R >= MAX_CHUNK_RECS || (int64_t) win_N + h_doc_len[a] + 1 > budget)) close_window();
+        if (!win_open) open_window();
+        // records [a, b) go into the open window
+        uint32_t b = a;
+        uint64_t bytes = win_N;
+        std::vector<uint32_t> &rs = h_win_rec_start;
+        while (b < nn && win_R + (b - a) < MAX_CHUNK_RECS &&
+               (b == a ? true : (int64_t) (bytes + h_doc_len[b] + 1) <= budget)) {
+            bytes += h_doc_len[b] + 1;
+            rs.push_back((uint32_t) bytes);
+            b++;
+        }
+        const uint32_t first_new = win_R, n_new = b - a;
+        const uint32_t newN = (uint32_t) bytes;
+        w_text.reserve_keep(newN + 16, win_N, st);
+        w_dist.reserve_keep(newN + 16, win_N, st);
+        w_recid.reserve_keep(newN + 16, win_N, st);
+        w_rec_start.reserve_discard(rs.size() + 1);
+        PX_CUDA(cudaMemcpyAsync(w_rec_start.p, rs.data(), rs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        k_write_docs<<<(unsigned) div_up<uint64_t>((uint64_t) n_new * 32u, 256), 256, 0, st>>>(n_new, a, first_new, d_keys, d_koff, d_vals, d_voff,
+                                                                         w_rec_start.p, w_text.p, w_dist.p, w_recid.p);
+        launches++;
+        win_R += n_new;
+        win_N = newN;
+        encode_window_records(first_new);
+        a = b;
+    }
+    PX_CUDA(cudaEventRecord(ev1, st));
+    // ---- index maintenance (host CritBit; in-order semantics of n sequential setitem calls) ----
+    std::vector<uint8_t> q;
+    for (uint32_t i = 0; i < nn; i++) {
+        const uint8_t *k = h_keys + h_koff[i];
+        size_t kl = (size_t) (h_koff[i + 1] - h_koff[i]);
+        escape_key(k, kl, q);
+        uint32_t g = (uint32_t) (g_batch_first + i);
+        int64_t old = index->set(q.data(), (uint32_t) q.size(), g);
+        if (old >= 0) {
+            h_live[old] = 0;
+            live_records--;
+        }
+        live_records++;
+        if (rc) rc[i] = old >= 0 ? PIXIU_CBT_SET_REPLACE : 0;
+        if (saved) saved[i] = (int32_t) h_doc_len[i] - (int32_t) h_enc_len[g];
+        raw_bytes += (int64_t) kl + (h_voff[i + 1] - h_voff[i]);
+        doc_bytes += h_doc_len[i];
+    }
+    PX_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0;
+    PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_set_ms = ms;
+    return PIXIU_OK;
+}
+
+}  // namespace pixiu

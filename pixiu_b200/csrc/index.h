@@ -1,0 +1,75 @@
+// CritBit key index (replaces data_struct/CritBitTree.{h,cpp}).
+//
+// Host side: the tree lives in flat arrays (no per-node malloc, no tagged pointers):
+//   inner node i : child[0][i], child[1][i] (>= 0 inner node, < 0 leaf ~slot), diff_at[i], mask[i]
+//   leaf slot s  : leaf_rec[s] = global record id; its escaped key (with the 251,0 terminator)
+//                  sits in a host key arena so inserts need no decode of stored records.
+// Device side: the same arrays mirrored as SoA for the batched level-synchronous walk
+// (find_best_match, CritBitTree.cpp:253-269); candidates are verified against the
+// decoded prefix of the stored record (key_eq / contains, PiXiuStr.cpp:129-143,
+// CritBitTree.cpp:154-178) straight from the compressed store.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pixiu {
+
+// esc(k) 251 0   (PiXiuStr_init_key, proj/PiXiuStr.cpp:12-14)
+void escape_key(const uint8_t *k, size_t n, std::vector<uint8_t> &out, bool terminator = true);
+
+class HostIndex {
+   public:
+    // returns the record id that was replaced, or -1 when the key is new (CritBitTree.cpp:13-105)
+    int64_t set(const uint8_t *q, uint32_t qlen, uint32_t rec);
+    int64_t get(const uint8_t *q, uint32_t qlen) const;  // record id or -1
+    int64_t del(const uint8_t *q, uint32_t qlen);        // record id or -1 (CritBitTree.cpp:107-152)
+    // record ids of all keys starting with the escaped prefix, ascending key order (CritBitTree.h:55-157)
+    void iter(const uint8_t *prefix, uint32_t plen, std::vector<uint32_t> &out) const;
+    size_t size() const { return n_live; }
+
+    // ---- device mirror ----
+    struct DeviceView {
+        const int32_t *child0, *child1;
+        const uint16_t *diff_at;
+        const uint8_t *mask;
+        const uint32_t *leaf_rec;
+        int32_t root;
+        int32_t has_root;
+    };
+    DeviceView device_view(cudaStream_t st);  // uploads when dirty
+
+   private:
+    std::vector<int32_t> child[2];
+    std::vector<uint16_t> diff_at;
+    std::vector<uint8_t> mask;
+    std::vector<uint32_t> leaf_rec, leaf_klen;
+    std::vector<uint64_t> leaf_koff;
+    std::vector<uint8_t> arena;
+    std::vector<int32_t> free_inner, free_leaf;
+    int32_t root = 0;
+    bool has_root = false;
+    size_t n_live = 0;
+    bool dirty = true;
+    DevBuf<int32_t> d_child0, d_child1;
+    DevBuf<uint16_t> d_diff;
+    DevBuf<uint8_t> d_mask;
+    DevBuf<uint32_t> d_leaf_rec;
+
+    int32_t new_leaf(const uint8_t *q, uint32_t qlen, uint32_t rec);
+    int32_t new_inner();
+    int dir_of(int32_t node, const uint8_t *q, uint32_t qlen) const {
+        uint8_t b = qlen > diff_at[node] ? q[diff_at[node]] : 0;
+        return (1 + (mask[node] | b)) >> 8;
+    }
+    void iter_rec(int32_t p, const uint8_t *pre, uint32_t plen, bool include_all, bool &harvest, bool &stop,
+                  std::vector<uint32_t> &out) const;
+};
+
+struct Store;
+// GPU batched lookup: escapes the n packed keys on the device, walks the SoA tree and verifies the
+// candidates against the compressed store.  rec_out[i] = record id or 0xFFFFFFFF.
+void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, std::vector<uint32_t> &rec_out);
+
+}  // namespace pixiu

@@ -1,0 +1,194 @@
+// Hand-written LSD radix sort of (key, u32 value) pairs for sm_100a.
+//
+// One up-front histogram launch counts every 8-bit digit of every pass; each pass
+// is then ONE launch ("onesweep"): a CTA takes a tile of 256 x 16 keys in ticket
+// order, ranks them stably with warp match-any + shared-memory digit counters,
+// resolves its global digit offsets by decoupled look-back over the tile-status
+// table, and scatters keys and values.  Per pass each element is read once and
+// written once (8|4 B key + 4 B value), the histogram launch reads the keys once.
+//
+// Used by the suffix-array construction (encode.cu): the initial 63-bit
+// 7-symbol keys and the (group, rank[i+h]) keys of every prefix-doubling round.
+#pragma once
+#include "common.cuh"
+
+namespace pixiu {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
+constexpr int RS_BINS = 256;
+constexpr int RS_MAX_PASSES = 8;
+constexpr uint32_t RS_FLAG_AGG = 1u << 30;
+constexpr uint32_t RS_FLAG_PREFIX = 2u << 30;
+constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
+constexpr uint32_t RS_SPIN_LIMIT = 1u << 27;
+
+// hist[pass][bin] += count, for passes [0, npass) covering bits [begin_bit + 8*pass, ..)
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_histogram(const KeyT *__restrict__ keys, uint32_t n, int begin_bit, int npass, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[RS_MAX_PASSES * RS_BINS];
+    for (int i = threadIdx.x; i < npass * RS_BINS; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * RS_THREADS;
+    for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
+        KeyT k = keys[i];
+        for (int p = 0; p < npass; p++) atomicAdd(&sh[p * RS_BINS + (uint32_t) ((k >> (begin_bit + 8 * p)) & 0xff)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * RS_BINS; i += RS_THREADS)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// exclusive scan of each pass's 256 bins, in place: one CTA of 256 threads per pass
+static __global__ void __launch_bounds__(RS_BINS) k_rs_scan_bins(uint32_t *hist) {
+    __shared__ uint32_t sm[RS_BINS];
+    uint32_t *h = hist + blockIdx.x * RS_BINS;
+    uint32_t v = h[threadIdx.x];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < RS_BINS; d <<= 1) {
+        uint32_t o = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
+        __syncthreads();
+        sm[threadIdx.x] += o;
+        __syncthreads();
+    }
+    h[threadIdx.x] = sm[threadIdx.x] - v;
+}
+
+// One onesweep pass.  status: [tiles][256] zero-initialised; ticket: zero-initialised counter.
+// vals_in == nullptr means "value = input index" (first pass of an index sort).
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const uint32_t *__restrict__ vals_in,
+              uint32_t *__restrict__ vals_out, uint32_t n, int shift, const uint32_t *__restrict__ bin_base,
+              uint32_t *__restrict__ status, uint32_t *__restrict__ ticket, uint32_t *__restrict__ err) {
+    __shared__ uint32_t warp_hist[RS_WARPS][RS_BINS];  // per-warp digit counts, then exclusive warp prefixes
+    __shared__ uint32_t tile_off[RS_BINS];             // global offset of this tile's first key per digit
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const uint32_t wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
+
+    KeyT key[RS_ITEMS];
+    uint16_t off[RS_ITEMS];
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        uint32_t i = wbase + k * 32 + lane;
+        key[k] = i < n ? keys_in[i] : (KeyT) ~(KeyT) 0;
+    }
+    // stable ranking: the warp walks its 512 consecutive keys 32 at a time
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        uint32_t i = wbase + k * 32 + lane;
+        bool valid = i < n;
+        uint32_t d = (uint32_t) ((key[k] >> shift) & 0xff);
+        uint32_t active = __ballot_sync(0xffffffffu, valid);
+        uint32_t m = __match_any_sync(0xffffffffu, valid ? d : 0x100u + (uint32_t) lane) & active;
+        uint32_t c = valid ? warp_hist[warp][d] : 0;
+        __syncwarp();
+        if (valid && (m & lt_mask) == 0) warp_hist[warp][d] = c + __popc(m);
+        __syncwarp();
+        off[k] = (uint16_t) (c + __popc(m & lt_mask));
+    }
+    __syncthreads();
+    // digit `t`: exclusive prefix over the warps, tile total, decoupled look-back
+    {
+        const int t = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c = warp_hist[w][t];
+            warp_hist[w][t] = run;
+            run += c;
+        }
+        volatile uint32_t *st = status;
+        uint32_t *mine = status + (size_t) tile * RS_BINS + t;
+        if (tile == 0) {
+            st_release_u32(mine, RS_FLAG_PREFIX | run);
+            tile_off[t] = bin_base[t];
+        } else {
+            st_release_u32(mine, RS_FLAG_AGG | run);
+            uint32_t excl = 0;
+            int64_t look = (int64_t) tile - 1;
+            uint32_t spins = 0;
+            while (look >= 0) {
+                uint32_t s = ld_acquire_u32(status + (size_t) look * RS_BINS + t);
+                uint32_t flag = s & ~RS_VALUE_MASK;
+                if (flag == 0) {
+                    if (++spins > RS_SPIN_LIMIT) {
+                        atomicExch(err, 1u);
+                        break;
+                    }
+                    continue;
+                }
+                excl += s & RS_VALUE_MASK;
+                if (flag == RS_FLAG_PREFIX) break;
+                look--;
+            }
+            st_release_u32(mine, RS_FLAG_PREFIX | (excl + run));
+            tile_off[t] = bin_base[t] + excl;
+        }
+        (void) st;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        uint32_t i = wbase + k * 32 + lane;
+        if (i < n) {
+            uint32_t d = (uint32_t) ((key[k] >> shift) & 0xff);
+            uint32_t pos = tile_off[d] + warp_hist[warp][d] + off[k];
+            keys_out[pos] = key[k];
+            vals_out[pos] = vals_in ? vals_in[i] : i;
+        }
+    }
+}
+
+struct RadixSortTemp {
+    DevBuf<uint32_t> hist;     // [RS_MAX_PASSES][256]
+    DevBuf<uint32_t> status;   // [passes][tiles][256]
+    DevBuf<uint32_t> ticket;   // [passes] + err
+};
+
+// Sorts n (key,value) pairs on bits [begin_bit, end_bit) ascending, stable.
+// Ping-pongs between (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 otherwise.
+// iota => the input values are taken to be the input indices (v0 is only used as a buffer).
+template <typename KeyT>
+int radix_sort_pairs(KeyT *k0, KeyT *k1, uint32_t *v0, uint32_t *v1, uint32_t n, int begin_bit, int end_bit,
+                     bool iota, RadixSortTemp &tmp, uint32_t *d_err, cudaStream_t st, int *launches = nullptr) {
+    if (n == 0) return 0;
+    if (end_bit <= begin_bit) throw std::runtime_error("radix_sort_pairs: empty bit range");
+    int npass = (end_bit - begin_bit + 7) / 8;
+    if (npass > RS_MAX_PASSES) throw std::runtime_error("radix_sort_pairs: too many passes");
+    uint32_t tiles = div_up<uint32_t>(n, RS_TILE);
+    tmp.hist.reserve_discard(RS_MAX_PASSES * RS_BINS);
+    tmp.status.reserve_discard((size_t) npass * tiles * RS_BINS);
+    tmp.ticket.reserve_discard(RS_MAX_PASSES);
+    PX_CUDA(cudaMemsetAsync(tmp.hist.p, 0, RS_MAX_PASSES * RS_BINS * sizeof(uint32_t), st));
+    PX_CUDA(cudaMemsetAsync(tmp.status.p, 0, (size_t) npass * tiles * RS_BINS * sizeof(uint32_t), st));
+    PX_CUDA(cudaMemsetAsync(tmp.ticket.p, 0, RS_MAX_PASSES * sizeof(uint32_t), st));
+    uint32_t hgrid = tiles < 148u * 8u ? tiles : 148u * 8u;
+    k_rs_histogram<KeyT><<<hgrid, RS_THREADS, 0, st>>>(k0, n, begin_bit, npass, tmp.hist.p);
+    k_rs_scan_bins<<<npass, RS_BINS, 0, st>>>(tmp.hist.p);
+    int cur = 0;
+    for (int p = 0; p < npass; p++) {
+        KeyT *ki = cur ? k1 : k0, *ko = cur ? k0 : k1;
+        uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
+        k_rs_onesweep<KeyT><<<tiles, RS_THREADS, 0, st>>>(ki, ko, (p == 0 && iota) ? nullptr : vi, vo, n,
+                                                          begin_bit + 8 * p, tmp.hist.p + p * RS_BINS,
+                                                          tmp.status.p + (size_t) p * tiles * RS_BINS,
+                                                          tmp.ticket.p + p, d_err);
+        cur ^= 1;
+    }
+    PX_LAUNCH_CHECK();
+    if (launches) *launches += 2 + npass;
+    return cur;
+}
+
+}  // namespace pixiu

@@ -1,0 +1,121 @@
+// Internal definition of the store behind the C ABI (include/pixiu_b200.h).
+//
+// HBM layout
+//   compressed store (all chunks):  enc u8[]          encoded records back to back
+//                                   rec_enc_off u64[] start of record g in enc
+//                                   rec_enc_len u32[] / rec_dec_len u32[]
+//                                   rec_first   u32[] global id of the first record of g's chunk
+//                                                     (back references carry chunk-local idx)
+//                                   rec_tile_base u32[] first decode tile of record g
+//                                   tile_desc u32[]   per 2 KiB of decoded bytes: enc offset (lo16)
+//                                                     of the token holding the tile's first byte and
+//                                                     the bytes of that token to skip (hi16)
+//   open window (= current chunk):  text u8[N]  escaped docs, one 0 separator after each
+//                                   dist u16[N] bytes to the end of the own record (0 at separator)
+//                                   recid u16[N] chunk-local record index
+//                                   rec_start u32[R+1]
+//   index mirror:                   CritBit nodes as SoA (child0/child1 i32, diff_at u16, mask u8)
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pixiu_b200.h"
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace pixiu {
+
+constexpr uint32_t TILE = 2048;          // decoded bytes per decode tile
+constexpr uint32_t MAX_DOC = 65535;      // PXSG_MAX_TO (proj/PiXiuStr.h:21)
+constexpr uint32_t MAX_CHUNK_RECS = 65535;  // PXC_STR_NUM (proj/PiXiuStr.h:20)
+constexpr int TREE_B = 16;               // branching of the block-min trees
+constexpr int TREE_MAX_LEVELS = 9;
+
+struct MinTree {
+    const uint32_t *a[TREE_MAX_LEVELS];   // block minima of the suffix array (level 0 = sa)
+    const uint32_t *l[TREE_MAX_LEVELS];   // block minima of the LCP array   (level 0 = lcp)
+    uint32_t size[TREE_MAX_LEVELS];
+    int nlev;
+};
+
+class HostIndex;  // CritBit (index.cu)
+
+struct EncodeScratch {
+    DevBuf<uint64_t> keys0, keys1;
+    DevBuf<uint32_t> vals0, vals1, slot0, slot1, gk, sa, rank, lcp, reach, lastnon, prevp, nextp, off, scan_tmp;
+    DevBuf<uint64_t> scan_tmp64;
+    DevBuf<uint32_t> tree_a, tree_l;
+    DevBuf<uint8_t> flagp, flagc;
+    DevBuf<uint32_t> counters;  // [0] active count, [1] group count, [2] error flag, [3..] misc
+    RadixSortTemp rs;
+};
+
+struct Store {
+    pixiu_config cfg{};
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double last_set_ms = 0, last_get_ms = 0, last_lookup_ms = 0;
+
+    // ---- record tables (host mirrors) ----
+    std::vector<uint64_t> h_enc_off;
+    std::vector<uint32_t> h_enc_len, h_dec_len, h_first, h_tile_base;
+    std::vector<uint8_t> h_live;
+    std::vector<uint32_t> chunk_first;  // global id of the first record of chunk c
+    std::vector<uint32_t> chunk_count;  // records in chunk c
+    uint64_t enc_bytes = 0, n_tiles = 0;
+    int64_t raw_bytes = 0, doc_bytes = 0, live_records = 0;
+
+    // ---- device store ----
+    DevBuf<uint8_t> d_enc;
+    DevBuf<uint64_t> d_enc_off;
+    DevBuf<uint32_t> d_enc_len, d_dec_len, d_first, d_tile_base, d_tile_desc;
+
+    // ---- open window ----
+    bool win_open = false;
+    uint32_t win_R = 0, win_N = 0;
+    DevBuf<uint8_t> w_text;
+    DevBuf<uint16_t> w_dist, w_recid;
+    DevBuf<uint32_t> w_rec_start;
+    std::vector<uint32_t> h_win_rec_start;  // R+1
+
+    EncodeScratch es;
+    std::unique_ptr<HostIndex> index;
+
+    // ---- decode scratch ----
+    DevBuf<uint8_t> dec_scratch;
+    DevBuf<uint64_t> dec_loc;      // per record: byte address (device pointer) of its decoded bytes
+    DevBuf<uint32_t> dec_flags;    // per tile: epoch when done
+    DevBuf<uint32_t> dec_work;     // work list of tiles (global tile ids) in ticket order
+    DevBuf<uint32_t> dec_ctr;      // [0] ticket, [1] error
+    uint32_t dec_epoch = 0;
+
+    // ---- staging for batches ----
+    DevBuf<uint8_t> in_keys, in_vals, out_stage;
+    DevBuf<int64_t> in_koff, in_voff;
+    DevBuf<uint32_t> doc_len, doc_off;
+
+    Store() = default;
+    ~Store();
+
+    size_t n_records() const { return h_enc_len.size(); }
+    size_t n_chunks() const { return chunk_first.size(); }
+
+    void init(const pixiu_config &c);
+    void grow_record_tables(size_t n_total, uint64_t enc_total, uint64_t tiles_total);
+    void open_window();
+    void close_window();
+
+    // encode.cu
+    int setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals,
+                      const int64_t *d_voff, const uint8_t *h_keys, const int64_t *h_koff,
+                      const int64_t *h_voff, int32_t *rc, int32_t *saved);
+    void encode_window_records(uint32_t first_new);
+    // decode.cu
+    void decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off);
+    int64_t import_chunk(int64_t n, const uint8_t *enc, const int64_t *enc_off);
+};
+
+}  // namespace pixiu

@@ -1,0 +1,356 @@
+"""Host-side mirror of the reference's ``PiXiuCtrl`` (proj/PiXiuCtrl.h:7-26) over the C ABI.
+
+``PiXiuCtrl`` keeps the reference's method names and return conventions
+(``setitem`` -> 0 / 1=CBT_SET_REPLACE, ``delitem`` -> 0 / 1=CBT_DEL_NOT_FOUND,
+``getitem`` -> a ``PXSGen`` or None, ``iter`` -> a ``CBTGen`` or None) and adds the
+batched forms the GPU path is built for.  Everything runs in
+``libpixiu_b200.so`` (hand-written sm_100a CUDA); importing this module on a
+machine where the library is missing raises — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpixiu_b200.so")
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_u32p = C.POINTER(C.c_uint32)
+_i64p = C.POINTER(C.c_int64)
+_u64p = C.POINTER(C.c_uint64)
+
+OK, EINVAL, ETOOLONG, ECUDA, ENOSPC, ECORRUPT, EINTERNAL = 0, -1, -2, -3, -4, -5, -6
+CBT_SET_REPLACE = 1
+CBT_DEL_NOT_FOUND = 1
+ROTATE_REFERENCE, ROTATE_BYTES, ROTATE_RECORDS = 0, 1, 2
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rotate_policy", C.c_int32), ("window_bytes", C.c_int64),
+                ("strict251", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("records", C.c_int64), ("live_records", C.c_int64), ("chunks", C.c_int64),
+                ("raw_bytes", C.c_int64), ("doc_bytes", C.c_int64), ("encoded_bytes", C.c_int64),
+                ("window_bytes", C.c_int64), ("kernel_launches", C.c_int64),
+                ("last_setitem_gpu_ms", C.c_double), ("last_getitem_gpu_ms", C.c_double),
+                ("last_lookup_gpu_ms", C.c_double)]
+
+
+EXPORTS = [
+    "pixiu_default_config", "pixiu_create", "pixiu_destroy", "pixiu_last_error", "pixiu_get_stats",
+    "pixiu_setitem_batch", "pixiu_setitem_batch_dev", "pixiu_contains_batch", "pixiu_delitem_batch",
+    "pixiu_getitem_batch", "pixiu_getitem_batch_dev", "pixiu_iter", "pixiu_encoded_view",
+    "pixiu_record_location", "pixiu_import_chunk", "pixiu_decode_chunk", "pixiu_rotate",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libpixiu_b200.so and declare its prototypes (fails loudly when it is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.pixiu_default_config.argtypes = [C.POINTER(Config)]
+    L.pixiu_create.argtypes = [C.POINTER(Config)]
+    L.pixiu_create.restype = C.c_void_p
+    L.pixiu_destroy.argtypes = [C.c_void_p]
+    L.pixiu_last_error.argtypes = [C.c_void_p]
+    L.pixiu_last_error.restype = C.c_char_p
+    L.pixiu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.pixiu_setitem_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32p, _i32p]
+    L.pixiu_setitem_batch_dev.argtypes = L.pixiu_setitem_batch.argtypes
+    L.pixiu_contains_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, _u8p]
+    L.pixiu_delitem_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, _i32p]
+    L.pixiu_getitem_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p, _u8p, _i64p]
+    L.pixiu_getitem_batch_dev.argtypes = L.pixiu_getitem_batch.argtypes
+    L.pixiu_iter.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, C.c_int64, _i64p, _i64p]
+    L.pixiu_encoded_view.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]
+    L.pixiu_record_location.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p]
+    L.pixiu_import_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.pixiu_import_chunk.restype = C.c_int64
+    L.pixiu_decode_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p]
+    L.pixiu_rotate.argtypes = [C.c_void_p]
+    # test hooks
+    L.pixiu_debug_sort_pairs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    L.pixiu_debug_window_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+    L.pixiu_debug_window_array.restype = C.c_int64
+    _lib = L
+    return L
+
+
+class PiXiuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pixiu error {code}: {msg}")
+        self.code = code
+
+
+def _pack(items):
+    off = np.zeros(len(items) + 1, dtype=np.int64)
+    if items:
+        np.cumsum([len(x) for x in items], out=off[1:])
+    data = np.frombuffer(b"".join(items), dtype=np.uint8) if off[-1] else np.zeros(1, dtype=np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PXSGen:
+    """Byte generator over one decoded record — the protocol of the reference's
+    ``$gen(PXSGen)`` (proj/PiXiuStr.h:110-212): calling it yields ``esc(k) 251 0 esc(v) 251 2``
+    one byte at a time; ``consume_repr()`` returns the visible bytes (33..126)."""
+
+    def __init__(self, data: bytes):
+        self._data = data
+        self._pos = 0
+
+    def __call__(self):
+        """returns (True, byte) or (False, None) — `bool operator()(uint8_t&)`"""
+        if self._pos < len(self._data):
+            b = self._data[self._pos]
+            self._pos += 1
+            return True, b
+        return False, None
+
+    def __iter__(self):
+        while self._pos < len(self._data):
+            b = self._data[self._pos]
+            self._pos += 1
+            yield b
+
+    def bytes(self) -> bytes:
+        return self._data
+
+    def consume_repr(self) -> str:
+        out = bytes(b for b in self._data[self._pos:] if 33 <= b <= 126)
+        self._pos = len(self._data)
+        return out.decode("latin-1")
+
+
+class CBTGen:
+    """Generator of PXSGen objects in key order (``$gen(CBTGen)``, CritBitTree.h:130-157)."""
+
+    def __init__(self, docs):
+        self._docs = docs
+        self._pos = 0
+
+    def __call__(self):
+        if self._pos < len(self._docs):
+            g = PXSGen(self._docs[self._pos])
+            self._pos += 1
+            return True, g
+        return False, None
+
+    def __iter__(self):
+        while self._pos < len(self._docs):
+            g = PXSGen(self._docs[self._pos])
+            self._pos += 1
+            yield g
+
+
+def unescape(esc: bytes) -> bytes:
+    if 251 not in esc:
+        return esc
+    out = bytearray()
+    i = 0
+    while i < len(esc):
+        out.append(esc[i])
+        i += 2 if esc[i] == 251 else 1
+    return bytes(out)
+
+
+def split_doc(doc: bytes):
+    """decoded doc -> (key, value) un-escaped (README.md:157: the caller un-escapes)"""
+    i = 0
+    n = len(doc)
+    while i + 1 < n and not (doc[i] == 251 and doc[i + 1] == 0):
+        i += 2 if doc[i] == 251 else 1
+    k = unescape(doc[:i])
+    rest = doc[i + 2:]
+    return (k, unescape(rest[:-2])) if rest else (k, b"")
+
+
+class PiXiuCtrl:
+    """Drop-in for the reference's ``struct PiXiuCtrl`` — same methods, plus ``*_batch``."""
+
+    def __init__(self, device: int = 0, rotate_policy: int = ROTATE_REFERENCE, window_bytes: int = 12_500_000,
+                 strict251: bool = False):
+        self._L = load_library()
+        self._cfg = Config(device, rotate_policy, window_bytes, int(strict251), 0)
+        self._h = None
+        self.init_prop()
+
+    # -- lifecycle (PiXiuCtrl.cpp:77-86) --
+    def init_prop(self):
+        if self._h:
+            self.free_prop()
+        self._h = self._L.pixiu_create(C.byref(self._cfg))
+        if not self._h:
+            raise PiXiuError(ECUDA, "pixiu_create failed (no usable CUDA device?)")
+
+    def free_prop(self):
+        if self._h:
+            self._L.pixiu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free_prop()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise PiXiuError(rc, self._L.pixiu_last_error(self._h).decode("utf-8", "replace"))
+        return rc
+
+    # -- batched API --
+    def setitem_batch(self, keys, vals, want_saved=True):
+        """keys/vals: lists of bytes, or packed (data u8[], off i64[n+1]) tuples. -> (rc, saved)"""
+        kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
+        vd, vo = vals if isinstance(vals, tuple) else _pack(vals)
+        n = len(ko) - 1
+        rc = np.zeros(n, dtype=np.int32)
+        saved = np.zeros(n, dtype=np.int32)
+        self._check(self._L.pixiu_setitem_batch(self._h, n, _ptr(kd), _ptr(ko), _ptr(vd), _ptr(vo),
+                                                rc.ctypes.data_as(_i32p), saved.ctypes.data_as(_i32p)))
+        return rc, saved
+
+    def setitem_batch_dev(self, d_keys, d_koff, d_vals, d_voff, n):
+        """device pointers (ints) of a packed batch already resident in HBM"""
+        rc = np.zeros(n, dtype=np.int32)
+        saved = np.zeros(n, dtype=np.int32)
+        self._check(self._L.pixiu_setitem_batch_dev(self._h, n, d_keys, d_koff, d_vals, d_voff,
+                                                    rc.ctypes.data_as(_i32p), saved.ctypes.data_as(_i32p)))
+        return rc, saved
+
+    def contains_batch(self, keys):
+        kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
+        n = len(ko) - 1
+        found = np.zeros(max(n, 1), dtype=np.uint8)
+        self._check(self._L.pixiu_contains_batch(self._h, n, _ptr(kd), _ptr(ko), found.ctypes.data_as(_u8p)))
+        return found[:n].astype(bool)
+
+    def delitem_batch(self, keys):
+        kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
+        n = len(ko) - 1
+        rc = np.zeros(max(n, 1), dtype=np.int32)
+        self._check(self._L.pixiu_delitem_batch(self._h, n, _ptr(kd), _ptr(ko), rc.ctypes.data_as(_i32p)))
+        return rc[:n]
+
+    def getitem_batch(self, keys, out=None):
+        """-> (data u8[], off i64[n+1], found bool[n]); decoded docs in escaped form"""
+        kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
+        n = len(ko) - 1
+        off = np.zeros(n + 1, dtype=np.int64)
+        found = np.zeros(max(n, 1), dtype=np.uint8)
+        need = C.c_int64(0)
+        cap = 0 if out is None else out.size
+        buf = out if out is not None else np.zeros(1, dtype=np.uint8)
+        rc = self._L.pixiu_getitem_batch(self._h, n, _ptr(kd), _ptr(ko), _ptr(buf), cap, off.ctypes.data_as(_i64p),
+                                         found.ctypes.data_as(_u8p), C.byref(need))
+        if rc == ENOSPC:
+            buf = np.zeros(max(need.value, 1), dtype=np.uint8)
+            rc = self._L.pixiu_getitem_batch(self._h, n, _ptr(kd), _ptr(ko), _ptr(buf), buf.size,
+                                             off.ctypes.data_as(_i64p), found.ctypes.data_as(_u8p), C.byref(need))
+        self._check(rc)
+        return buf, off, found[:n].astype(bool)
+
+    def getitem_batch_dev(self, keys, d_out, cap):
+        kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
+        n = len(ko) - 1
+        off = np.zeros(n + 1, dtype=np.int64)
+        found = np.zeros(max(n, 1), dtype=np.uint8)
+        need = C.c_int64(0)
+        self._check(self._L.pixiu_getitem_batch_dev(self._h, n, _ptr(kd), _ptr(ko), d_out, cap,
+                                                    off.ctypes.data_as(_i64p), found.ctypes.data_as(_u8p), C.byref(need)))
+        return off, found[:n].astype(bool)
+
+    def iter_docs(self, prefix: bytes):
+        p = np.frombuffer(prefix, dtype=np.uint8) if prefix else np.zeros(1, dtype=np.uint8)
+        count, need = C.c_int64(0), C.c_int64(0)
+        rc = self._L.pixiu_iter(self._h, _ptr(p), len(prefix), None, 0, None, 0, C.byref(count), C.byref(need))
+        if rc not in (OK, ENOSPC):
+            self._check(rc)
+        if count.value == 0:
+            return []
+        buf = np.zeros(max(need.value, 1), dtype=np.uint8)
+        off = np.zeros(count.value + 1, dtype=np.int64)
+        self._check(self._L.pixiu_iter(self._h, _ptr(p), len(prefix), _ptr(buf), buf.size, off.ctypes.data_as(_i64p),
+                                       off.size, C.byref(count), C.byref(need)))
+        b = buf.tobytes()
+        return [b[off[i]:off[i + 1]] for i in range(count.value)]
+
+    # -- the reference's single-record API (PiXiuCtrl.h:11-19) --
+    def setitem(self, k: bytes, v: bytes = b"") -> int:
+        rc, _ = self.setitem_batch([bytes(k)], [bytes(v)])
+        return int(rc[0])
+
+    def contains(self, k: bytes) -> bool:
+        return bool(self.contains_batch([bytes(k)])[0])
+
+    def getitem(self, k: bytes):
+        buf, off, found = self.getitem_batch([bytes(k)])
+        return PXSGen(buf[:off[1]].tobytes()) if found[0] else None
+
+    def delitem(self, k: bytes) -> int:
+        return int(self.delitem_batch([bytes(k)])[0])
+
+    def iter(self, prefix: bytes = b""):
+        if self.stats().live_records == 0:
+            return None  # CritBitTree::iter returns NULL on an empty tree (CritBitTree.cpp:271-274)
+        return CBTGen(self.iter_docs(bytes(prefix)))
+
+    # -- inspection --
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self._L.pixiu_get_stats(self._h, C.byref(s)))
+        return s
+
+    def encoded(self, chunk: int, idx: int) -> bytes:
+        buf = np.zeros(65536, dtype=np.uint8)
+        n = self._check(self._L.pixiu_encoded_view(self._h, chunk, idx, _ptr(buf), buf.size))
+        return buf[:n].tobytes()
+
+    def record_location(self, record: int):
+        c, i = C.c_int64(), C.c_int64()
+        self._check(self._L.pixiu_record_location(self._h, record, C.byref(c), C.byref(i)))
+        return c.value, i.value
+
+    def import_chunk(self, encs) -> int:
+        ed, eo = encs if isinstance(encs, tuple) else _pack(encs)
+        return self._check(self._L.pixiu_import_chunk(self._h, len(eo) - 1, _ptr(ed), _ptr(eo)))
+
+    def decode_chunk(self, chunk: int):
+        n_off = 65536 + 1
+        off = np.zeros(n_off, dtype=np.int64)
+        need = C.c_int64(0)
+        rc = self._L.pixiu_decode_chunk(self._h, chunk, None, 0, off.ctypes.data_as(_i64p), C.byref(need))
+        if rc not in (OK, ENOSPC):
+            self._check(rc)
+        buf = np.zeros(max(need.value, 1), dtype=np.uint8)
+        self._check(self._L.pixiu_decode_chunk(self._h, chunk, _ptr(buf), buf.size, off.ctypes.data_as(_i64p), C.byref(need)))
+        return buf, off
+
+    def rotate(self):
+        self._check(self._L.pixiu_rotate(self._h))
+
+    def debug_window_array(self, name: str, dtype):
+        n = self.stats().window_bytes
+        out = np.zeros(max(n, 1), dtype=dtype)
+        r = self._L.pixiu_debug_window_array(self._h, name.encode(), _ptr(out), out.nbytes)
+        if r < 0:
+            raise PiXiuError(r, "debug_window_array")
+        return out[:r]

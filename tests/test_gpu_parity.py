@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+committed reference fixtures.  Bit-exact: encoded bytes, rc, saved bytes, decoded bytes.
+
+Nothing here reads /root/reference; the oracle (oracle/liboracle.so) is the checker.
+"""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN, load
+from oracle import pyoracle as po
+from pixiu_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctrl_mod():
+    import torch  # noqa: F401  (only to fail fast with a clear message when there is no GPU)
+
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from pixiu_b200 import ctrl
+
+    return ctrl
+
+
+def _oracle_encode_all(keys, vals, strict):
+    w = po.OracleWindow(strict251=strict)
+    docs = [po.make_doc(k, v) for k, v in zip(keys, vals)]
+    return docs, [w.encode(d) for d in docs]
+
+
+# --------------------------------------------------------------------------- sort
+@pytest.mark.parametrize("n,bits", [(1, 8), (1000, 13), (4096, 32), (100003, 47), (1 << 20, 63)])
+def test_radix_sort_matches_numpy(ctrl_mod, n, bits):
+    L = ctrl_mod.load_library()
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << bits, size=n, dtype=np.uint64)
+    if n > 10:
+        keys[: n // 3] = keys[n // 3: 2 * (n // 3)]  # many duplicates: stability matters
+    k = keys.copy()
+    vout = np.zeros(n, dtype=np.uint32)
+    rc = L.pixiu_debug_sort_pairs(0, k.ctypes.data_as(C.c_void_p), None, n, bits, vout.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order])
+    assert np.array_equal(vout, order.astype(np.uint32))
+
+
+# --------------------------------------------------------------------------- encode
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("n_batches", [1, 3])
+def test_setitem_matches_reference_fixture(ctrl_mod, name, n_batches):
+    g = load(name)
+    keys, vals = g["keys"], g["vals"]
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS, strict251=True)
+    n = len(keys)
+    cuts = [round(i * n / n_batches) for i in range(n_batches + 1)]
+    rcs, saveds = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        rc, saved = c.setitem_batch(keys[a:b], vals[a:b])
+        rcs.append(rc)
+        saveds.append(saved)
+    rc = np.concatenate(rcs)
+    saved = np.concatenate(saveds)
+    assert rc.tolist() == g["rc"].tolist()
+    for i in range(n):
+        enc = c.encoded(0, i)
+        assert enc == g["enc"][i], f"{name}: record {i} encoded bytes differ from the reference"
+        assert saved[i] == len(po.make_doc(keys[i], vals[i])) - len(enc)
+    c.free_prop()
+
+
+def test_window_arrays_match_model(ctrl_mod):
+    """SA / LCP / reach of a small window against the numpy model (pinpoints a failing stage)."""
+    from pipeline_model import build_text, lcp_array, suffix_array
+
+    g = load("fuzz_mode1")
+    keys, vals = g["keys"][:40], g["vals"][:40]
+    docs = [po.make_doc(k, v) for k, v in zip(keys, vals)]
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS, strict251=True)
+    c.setitem_batch(keys, vals)
+    text, is_sep, rec_start, rec_id, dist = build_text(docs)
+    assert np.array_equal(c.debug_window_array("text", np.uint8), text)
+    assert np.array_equal(c.debug_window_array("dist", np.uint16), dist.astype(np.uint16))
+    sa = suffix_array(text, is_sep)
+    assert np.array_equal(c.debug_window_array("sa", np.uint32), sa.astype(np.uint32))
+    lcp = lcp_array(text, dist, sa)
+    assert np.array_equal(c.debug_window_array("lcp", np.uint32), lcp.astype(np.uint32))
+    c.free_prop()
+
+
+def test_setitem_html_pages_vs_oracle(ctrl_mod):
+    kd, ko, vd, vo = synth.gen_html_pages(40, seed=7, max_len=60000)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    docs, encs = _oracle_encode_all(keys, vals, strict=False)
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
+    rc, saved = c.setitem_batch((kd, ko), (vd, vo))
+    assert not rc.any()
+    for i in range(len(keys)):
+        assert c.encoded(0, i) == encs[i], f"page {i}"
+    assert saved.tolist() == [len(d) - len(e) for d, e in zip(docs, encs)]
+    st = c.stats()
+    assert st.encoded_bytes == sum(map(len, encs)) and st.raw_bytes == int(ko[-1] + vo[-1])
+    # decode everything back through getitem
+    buf, off, found = c.getitem_batch((kd, ko))
+    assert found.all()
+    for i, d in enumerate(docs):
+        assert buf[off[i]:off[i + 1]].tobytes() == d, f"page {i} round trip"
+    c.free_prop()
+
+
+def test_setitem_nested_and_periodic_vs_oracle(ctrl_mod):
+    kd, ko, vd, vo = synth.gen_nested(1500, seed=3)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    docs, encs = _oracle_encode_all(keys, vals, strict=False)
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
+    c.setitem_batch((kd, ko), (vd, vo))
+    for i in range(len(keys)):
+        assert c.encoded(0, i) == encs[i], f"record {i}"
+    buf, off, found = c.getitem_batch((kd, ko))
+    assert found.all()
+    for i, d in enumerate(docs):
+        assert buf[off[i]:off[i + 1]].tobytes() == d
+    c.free_prop()
+
+
+def test_edge_records(ctrl_mod):
+    """maximum lengths (PiXiuCtrl.cpp:121-174), key-only docs, long runs of 251, long periodic values"""
+    recs = [
+        (b"A" * 65533, b""),                       # max key-only record: 65,535 decoded bytes
+        (b"k1", b"B" * 65527),                     # max k+v
+        (b"k2", bytes([251]) * 30000),             # escapes double it: 60,000 + terminators
+        (b"k3", b"xyz" * 20000),
+        (b"k4", bytes(range(256)) * 200),
+        (bytes([251, 0, 251, 2, 251]), bytes([0, 2, 251, 251, 0])),
+        (b"k5", b""),
+        (b"k6", b"B" * 251 + b"!" + b"B" * 251),   # runs of exactly 251 (reference bug B1 territory)
+    ]
+    keys, vals = [r[0] for r in recs], [r[1] for r in recs]
+    docs, encs = _oracle_encode_all(keys, vals, strict=False)
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
+    rc, saved = c.setitem_batch(keys, vals)
+    for i in range(len(recs)):
+        assert c.encoded(0, i) == encs[i], f"record {i}"
+    buf, off, found = c.getitem_batch(keys)
+    assert found.all()
+    for i, d in enumerate(docs):
+        assert buf[off[i]:off[i + 1]].tobytes() == d, f"record {i}"
+    # oversize records are an explicit error and leave the store untouched
+    with pytest.raises(ctrl_mod.PiXiuError) as e:
+        c.setitem_batch([b"big"], [b"C" * 65529])
+    assert e.value.code == ctrl_mod.ETOOLONG
+    with pytest.raises(ctrl_mod.PiXiuError):
+        c.setitem_batch([b""], [b"v"])
+    assert c.stats().records == len(recs)
+    c.free_prop()
+
+
+# --------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("name", GOLDEN)
+def test_import_and_decode_chunk(ctrl_mod, name):
+    g = load(name)
+    docs, encs = _oracle_encode_all(g["keys"], g["vals"], strict=False)
+    c = ctrl_mod.PiXiuCtrl()
+    chunk = c.import_chunk(encs)
+    assert chunk == 0
+    buf, off = c.decode_chunk(0)
+    for i, d in enumerate(docs):
+        assert buf[off[i]:off[i + 1]].tobytes() == d, f"{name}: record {i}"
+    # the index was rebuilt from the decoded keys: latest value wins
+    latest = dict(zip(g["keys"], g["vals"]))
+    ks = list(latest)[:100]
+    b2, o2, found = c.getitem_batch(ks)
+    assert found.all()
+    for i, k in enumerate(ks):
+        assert ctrl_mod.split_doc(b2[o2[i]:o2[i + 1]].tobytes()) == (k, latest[k])
+    c.free_prop()
+
+
+# --------------------------------------------------------------------------- CRUD (t_PiXiuCtrl, PiXiuCtrl.cpp:176-255)
+def test_crud_differential(ctrl_mod):
+    rng = random.Random(11)
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=4000)  # forces many rotations
+    st = po.OracleStore()
+    model = {}
+    for rnd in range(30):
+        ks = [bytes(rng.choice(b"ABCDE") for _ in range(rng.randint(1, 6))) for _ in range(60)]
+        vs = [bytes(rng.choice(b"ABCDE") for _ in range(rng.randint(1, 50))) for _ in range(60)]
+        rc, _ = c.setitem_batch(ks, vs)
+        want = []
+        for k, v in zip(ks, vs):
+            want.append(int(k in model))
+            model[k] = v
+            st.setitem(k, v)
+        assert rc.tolist() == want
+        dk = [bytes(rng.choice(b"ABCDE") for _ in range(rng.randint(1, 4))) for _ in range(15)]
+        want = []
+        for k in dk:
+            want.append(int(k not in model))
+            model.pop(k, None)
+            st.delitem(k)
+        assert c.delitem_batch(dk).tolist() == want
+        qk = [bytes(rng.choice(b"ABCDEF") for _ in range(rng.randint(1, 6))) for _ in range(80)]
+        assert c.contains_batch(qk).tolist() == [k in model for k in qk]
+        buf, off, found = c.getitem_batch(qk)
+        assert found.tolist() == [k in model for k in qk]
+        for i, k in enumerate(qk):
+            if k in model:
+                assert ctrl_mod.split_doc(buf[off[i]:off[i + 1]].tobytes()) == (k, model[k])
+    assert c.stats().chunks > 3
+    assert c.stats().live_records == len(model)
+    for prefix in [b"", b"A", b"AB", b"E", b"ABCDEA", b"Z"]:
+        want = sorted(po.make_doc(k, v) for k, v in model.items() if k.startswith(prefix))
+        assert c.iter_docs(prefix) == want
+        assert st.iter(prefix) == want
+    # single-record API (the reference's call shapes)
+    assert c.setitem(b"solo", b"value") == 0
+    assert c.setitem(b"solo", b"value2") == 1
+    gen = c.getitem(b"solo")
+    assert gen.bytes() == po.make_doc(b"solo", b"value2")
+    assert c.getitem(b"missing") is None
+    assert c.delitem(b"solo") == 0 and c.delitem(b"solo") == 1
+    c.free_prop()
