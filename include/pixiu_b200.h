@@ -115,6 +115,14 @@ int64_t pixiu_import_chunk(pixiu_store *s, int64_t n, const uint8_t *enc, const 
 /* Decode every record of one chunk (tombstoned included) in idx order. */
 int pixiu_decode_chunk(pixiu_store *s, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *need);
 
+/* Per-kernel-class device timing (CUDA events on the store's stream), for the roofline report.
+ * enable(1) resets the counters; get() returns 1 once cls is past the last class. `bytes` are the
+ * ALGORITHMIC bytes of the launches (DESIGN.md states the per-unit figures). */
+int pixiu_profile_enable(pixiu_store *s, int on);
+int pixiu_profile_get(pixiu_store *s, int cls, const char **name, double *ms, double *bytes, int64_t *launches);
+/* the CUDA stream (cudaStream_t) all of this store's work is issued on */
+void *pixiu_stream(pixiu_store *s);
+
 /* force the open window to close (next setitem starts a new chunk) */
 int pixiu_rotate(pixiu_store *s);
 

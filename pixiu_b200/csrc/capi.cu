@@ -354,6 +354,25 @@ int64_t pixiu_import_chunk(pixiu_store *h, int64_t n, const uint8_t *enc, const 
     return rc == PIXIU_OK ? chunk_id : rc;
 }
 
+int pixiu_profile_enable(pixiu_store *h, int on) {
+    if (!h) return PIXIU_EINVAL;
+    h->s.prof.reset();
+    h->s.prof.on = on != 0;
+    return PIXIU_OK;
+}
+
+int pixiu_profile_get(pixiu_store *h, int cls, const char **name, double *ms, double *bytes, int64_t *launches) {
+    if (!h || cls < 0) return PIXIU_EINVAL;
+    if (cls >= pixiu::PC_COUNT) return 1;  /* past the end */
+    if (name) *name = pixiu::prof_class_name(cls);
+    if (ms) *ms = h->s.prof.ms[cls];
+    if (bytes) *bytes = h->s.prof.bytes[cls];
+    if (launches) *launches = h->s.prof.launches[cls];
+    return PIXIU_OK;
+}
+
+void *pixiu_stream(pixiu_store *h) { return h ? (void *) h->s.st : nullptr; }
+
 int pixiu_rotate(pixiu_store *h) {
     return guarded(h, [&](Store &S) -> int {
         if (S.win_open) S.close_window();

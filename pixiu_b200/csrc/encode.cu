@@ -490,9 +490,12 @@ static void build_suffix_array(Store &S, uint32_t N) {
     PX_CUDA(cudaMemsetAsync(E.counters.p, 0, 16 * sizeof(uint32_t), st));
     int L = 0;
 
+    Profiler *PF = S.prof.on ? &S.prof : nullptr;
+    S.prof.begin(PC_INIT_KEYS, st);
     k_init_keys<<<div_up<uint32_t>(N, 256), 256, 0, st>>>(S.w_text.p, S.w_dist.p, N, E.keys0.p);
+    S.prof.end(st, 11.0 * N, 1);
     L++;
-    int cur = radix_sort_pairs<uint64_t>(E.keys0.p, E.keys1.p, E.vals0.p, E.vals1.p, N, 0, 63, true, E.rs, E.counters.p + 2, st, &L);
+    int cur = radix_sort_pairs<uint64_t>(E.keys0.p, E.keys1.p, E.vals0.p, E.vals1.p, N, 0, 63, true, E.rs, E.counters.p + 2, st, &L, PF);
     uint64_t *skeys = cur ? E.keys1.p : E.keys0.p;
     uint32_t *svals = cur ? E.vals1.p : E.vals0.p;
     uint32_t *slot_cur = nullptr;  // nullptr: slot[a] = a (first round)
@@ -506,6 +509,7 @@ static void build_suffix_array(Store &S, uint32_t N) {
 
     while (true) {
         HeadFn head{skeys, A, initial ? 1 : 0};
+        S.prof.begin(PC_RANK_SCAN, st);
         // (1) rank of every element = slot of its group head; write sa and rank
         {
             const uint32_t *sl = slot_cur;
@@ -552,6 +556,7 @@ static void build_suffix_array(Store &S, uint32_t N) {
             L += 3;
             svals = vals_out;  // compacted values (unsorted for the next key) live here now
         }
+        S.prof.end(st, 60.0 * A, 6);
         uint32_t h_cnt[3];
         PX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         PX_CUDA(cudaStreamSynchronize(st));
@@ -561,11 +566,13 @@ static void build_suffix_array(Store &S, uint32_t N) {
         if (h > 65535u) throw std::runtime_error("suffix array: groups left after h > 65535");
         // (3) next keys: (group, rank[i+h]) and sort
         uint64_t *kin = E.keys0.p, *kalt = E.keys1.p;
+        S.prof.begin(PC_ROUND_KEYS, st);
         k_round_keys<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, svals, gk, rank, h, kb, kin);
+        S.prof.end(st, 20.0 * An, 1);
         L++;
         uint32_t *vin = svals, *valt = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
         int gb = bits_for(G ? G - 1 : 0);
-        int c2 = radix_sort_pairs<uint64_t>(kin, kalt, vin, valt, An, 0, kb + gb, false, E.rs, E.counters.p + 2, st, &L);
+        int c2 = radix_sort_pairs<uint64_t>(kin, kalt, vin, valt, An, 0, kb + gb, false, E.rs, E.counters.p + 2, st, &L, PF);
         skeys = c2 ? kalt : kin;
         svals = c2 ? valt : vin;
         slot_cur = slot_next;
@@ -589,7 +596,9 @@ void Store::encode_window_records(uint32_t first_new) {
 
     // ---- LCP + trees ----
     E.lcp.reserve_discard(N);
+    prof.begin(PC_LCP, st);
     k_lcp<<<div_up<uint32_t>(div_up<uint32_t>(N, LCP_SEG), 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, N, E.lcp.p);
+    prof.end(st, 16.0 * N, 1);
     L++;
     MinTree T{};
     {
@@ -603,6 +612,7 @@ void Store::encode_window_records(uint32_t first_new) {
         }
         E.tree_a.reserve_discard(total + 1);
         E.tree_l.reserve_discard(total + 1);
+        prof.begin(PC_TREE, st);
         T.a[0] = E.sa.p;
         T.l[0] = E.lcp.p;
         T.size[0] = N;
@@ -621,6 +631,7 @@ void Store::encode_window_records(uint32_t first_new) {
             o += so;
             sz = so;
         }
+        prof.end(st, 8.5 * N, T.nlev - 1);
     }
 
     // ---- M / reach, flags ----
@@ -633,7 +644,10 @@ void Store::encode_window_records(uint32_t first_new) {
     E.off.reserve_discard(N + 2);
     PX_CUDA(cudaMemsetAsync(E.flagp.p + s0, 0, (size_t) M + 2, st));
     uint32_t gridM = div_up<uint32_t>(M, 256);
+    prof.begin(PC_LPF, st);
     k_lpf<<<gridM, 256, 0, st>>>(T, E.rank.p, w_dist.p, s0, N, E.reach.p);
+    prof.end(st, 18.0 * M, 1);
+    prof.begin(PC_FLAGS, st);
     k_flag_scatter<<<gridM, 256, 0, st>>>(E.reach.p, w_dist.p, s0, N, E.flagp.p);
     L += 2;
     {
@@ -678,6 +692,7 @@ void Store::encode_window_records(uint32_t first_new) {
             [=] __device__(size_t k, uint32_t v) { off[s0 + k] = v; }, OpSum(), 0u, true, E.scan_tmp.p, st);
         L += 3;
     }
+    prof.end(st, 60.0 * M, 14);
     uint32_t enc_total = 0;
     PX_CUDA(cudaMemcpyAsync(&enc_total, E.off.p + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
@@ -694,9 +709,12 @@ void Store::encode_window_records(uint32_t first_new) {
     grow_record_tables(g_first + n_new, enc_bytes + enc_total, n_tiles + new_tiles);
     PX_CUDA(cudaMemcpyAsync(d_tile_base.p + g_first, tile_base.data(), n_new * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     uint32_t g_chunk_first = chunk_first.back();
+    prof.begin(PC_EMIT, st);
     k_emit<<<gridM, 256, 0, st>>>(T, w_text.p, w_dist.p, w_recid.p, w_rec_start.p, E.rank.p, E.reach.p, E.flagc.p,
                                   E.prevp.p, E.nextp.p, E.off.p, s0, N, cfg.strict251, d_enc.p + enc_bytes,
                                   E.counters.p + 2);
+    prof.end(st, 20.0 * M, 1);
+    prof.begin(PC_TABLES, st);
     k_record_tables<<<div_up<uint32_t>(n_new, 256), 256, 0, st>>>(n_new, first_new, (uint32_t) g_first, g_chunk_first,
                                                                   w_rec_start.p, E.off.p, 0u, enc_bytes, d_enc_off.p,
                                                                   d_enc_len.p, d_dec_len.p, d_first.p);
@@ -704,6 +722,7 @@ void Store::encode_window_records(uint32_t first_new) {
         k_tile_desc<<<div_up<uint32_t>((uint32_t) new_tiles, 256), 256, 0, st>>>(
             (uint32_t) new_tiles, (uint32_t) n_tiles, n_new, first_new, (uint32_t) g_first, d_tile_base.p,
             w_rec_start.p, E.off.p, E.flagc.p, E.prevp.p, E.nextp.p, w_text.p, E.lastnon.p, d_tile_desc.p);
+    prof.end(st, 24.0 * n_new, 2);
     L += 3;
     // host mirrors
     size_t old = h_enc_len.size();
@@ -734,7 +753,9 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     const uint32_t nn = (uint32_t) n;
     PX_CUDA(cudaEventRecord(ev0, st));
     doc_len.reserve_discard(nn);
+    prof.begin(PC_DOCS, st);
     k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p);
+    prof.end(st, 0.0, 1);
     launches++;
     std::vector<uint32_t> h_doc_len(nn);
     PX_CUDA(cudaMemcpyAsync(h_doc_len.data(), doc_len.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -774,8 +795,10 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         w_recid.reserve_keep(newN + 16, win_N, st);
         w_rec_start.reserve_discard(rs.size() + 1);
         PX_CUDA(cudaMemcpyAsync(w_rec_start.p, rs.data(), rs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        prof.begin(PC_DOCS, st);
         k_write_docs<<<(unsigned) div_up<uint64_t>((uint64_t) n_new * 32u, 256), 256, 0, st>>>(n_new, a, first_new, d_keys, d_koff, d_vals, d_voff,
                                                                          w_rec_start.p, w_text.p, w_dist.p, w_recid.p);
+        prof.end(st, 7.0 * (newN - win_N), 1);
         launches++;
         win_R += n_new;
         win_N = newN;
@@ -805,6 +828,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     float ms = 0;
     PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     last_set_ms = ms;
+    prof.collect();
     return PIXIU_OK;
 }
 

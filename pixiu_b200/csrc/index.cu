@@ -405,6 +405,7 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     PX_CUDA(cudaMemcpyAsync(S.in_koff.p, rel.data(), (nn + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     HostIndex::DeviceView T = S.index->device_view(st);
     PX_CUDA(cudaEventRecord(S.ev0, st));
+    S.prof.begin(PC_LOOKUP, st);
     S.doc_len.reserve_discard(nn + 1);
     DevBuf<uint64_t> &qoff = S.es.scan_tmp64;  // reuse: needs nn+1 + scan temp
     size_t need = (size_t) nn + 2 + scan_tmp_elems(nn + 1);
@@ -426,6 +427,7 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     ChaseView V{S.d_enc.p, S.d_enc_off.p, S.d_enc_len.p, S.d_dec_len.p, S.d_first.p, S.d_tile_base.p, S.d_tile_desc.p};
     k_lookup<<<div_up<uint32_t>(nn, 128), 128, 0, st>>>(nn, T, V, S.in_vals.p, d_qoff, S.doc_len.p, S.doc_off.p);
     PX_LAUNCH_CHECK();
+    S.prof.end(st, 0.0, 6);
     S.launches += 6;
     PX_CUDA(cudaEventRecord(S.ev1, st));
     PX_CUDA(cudaMemcpyAsync(rec_out.data(), S.doc_off.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -433,6 +435,7 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     float ms = 0;
     PX_CUDA(cudaEventElapsedTime(&ms, S.ev0, S.ev1));
     S.last_lookup_ms = ms;
+    S.prof.collect();
 }
 
 }  // namespace pixiu

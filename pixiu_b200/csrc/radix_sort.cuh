@@ -11,6 +11,7 @@
 // 7-symbol keys and the (group, rank[i+h]) keys of every prefix-doubling round.
 #pragma once
 #include "common.cuh"
+#include "prof.h"
 
 namespace pixiu {
 
@@ -161,7 +162,8 @@ struct RadixSortTemp {
 // iota => the input values are taken to be the input indices (v0 is only used as a buffer).
 template <typename KeyT>
 int radix_sort_pairs(KeyT *k0, KeyT *k1, uint32_t *v0, uint32_t *v1, uint32_t n, int begin_bit, int end_bit,
-                     bool iota, RadixSortTemp &tmp, uint32_t *d_err, cudaStream_t st, int *launches = nullptr) {
+                     bool iota, RadixSortTemp &tmp, uint32_t *d_err, cudaStream_t st, int *launches = nullptr,
+                     Profiler *prof = nullptr) {
     if (n == 0) return 0;
     if (end_bit <= begin_bit) throw std::runtime_error("radix_sort_pairs: empty bit range");
     int npass = (end_bit - begin_bit + 7) / 8;
@@ -174,16 +176,20 @@ int radix_sort_pairs(KeyT *k0, KeyT *k1, uint32_t *v0, uint32_t *v1, uint32_t n,
     PX_CUDA(cudaMemsetAsync(tmp.status.p, 0, (size_t) npass * tiles * RS_BINS * sizeof(uint32_t), st));
     PX_CUDA(cudaMemsetAsync(tmp.ticket.p, 0, RS_MAX_PASSES * sizeof(uint32_t), st));
     uint32_t hgrid = tiles < 148u * 8u ? tiles : 148u * 8u;
+    if (prof) prof->begin(PC_SORT_HIST, st);
     k_rs_histogram<KeyT><<<hgrid, RS_THREADS, 0, st>>>(k0, n, begin_bit, npass, tmp.hist.p);
     k_rs_scan_bins<<<npass, RS_BINS, 0, st>>>(tmp.hist.p);
+    if (prof) prof->end(st, (double) n * sizeof(KeyT), 2);
     int cur = 0;
     for (int p = 0; p < npass; p++) {
         KeyT *ki = cur ? k1 : k0, *ko = cur ? k0 : k1;
         uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
+        if (prof) prof->begin(PC_SORT_PASS, st);
         k_rs_onesweep<KeyT><<<tiles, RS_THREADS, 0, st>>>(ki, ko, (p == 0 && iota) ? nullptr : vi, vo, n,
                                                           begin_bit + 8 * p, tmp.hist.p + p * RS_BINS,
                                                           tmp.status.p + (size_t) p * tiles * RS_BINS,
                                                           tmp.ticket.p + p, d_err);
+        if (prof) prof->end(st, (double) n * (2.0 * sizeof(KeyT) + ((p == 0 && iota) ? 4.0 : 8.0)), 1);
         cur ^= 1;
     }
     PX_LAUNCH_CHECK();

@@ -22,6 +22,7 @@
 
 #include "../../include/pixiu_b200.h"
 #include "common.cuh"
+#include "prof.h"
 #include "radix_sort.cuh"
 
 namespace pixiu {
@@ -57,6 +58,7 @@ struct Store {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int64_t launches = 0;
+    Profiler prof;
     double last_set_ms = 0, last_get_ms = 0, last_lookup_ms = 0;
 
     // ---- record tables (host mirrors) ----
@@ -85,12 +87,14 @@ struct Store {
     std::unique_ptr<HostIndex> index;
 
     // ---- decode scratch ----
-    DevBuf<uint8_t> dec_scratch;
-    DevBuf<uint64_t> dec_loc;      // per record: byte address (device pointer) of its decoded bytes
-    DevBuf<uint32_t> dec_flags;    // per tile: epoch when done
-    DevBuf<uint32_t> dec_work;     // work list of tiles (global tile ids) in ticket order
-    DevBuf<uint32_t> dec_ctr;      // [0] ticket, [1] error
-    uint32_t dec_epoch = 0;
+    DevBuf<uint8_t> dec_scratch;   // decoded arena when the caller's layout differs from arena order
+    DevBuf<uint64_t> dec_loc;      // output offsets of the requested records
+    DevBuf<uint32_t> dec_flags;    // literal bitmap of the arena (1 bit per byte)
+    DevBuf<uint32_t> dec_ptr;      // source pointer of every non-literal arena byte
+    DevBuf<uint32_t> dec_aoff;     // per record: offset in the arena
+    DevBuf<uint32_t> dec_reqs;     // requested record ids
+    DevBuf<uint32_t> dec_work;     // work list: tile ids, then record ids
+    DevBuf<uint32_t> dec_ctr;      // [0] error, [1+r] unfinished CTAs of resolve round r
 
     // ---- staging for batches ----
     DevBuf<uint8_t> in_keys, in_vals, out_stage;

@@ -47,6 +47,7 @@ EXPORTS = [
     "pixiu_setitem_batch", "pixiu_setitem_batch_dev", "pixiu_contains_batch", "pixiu_delitem_batch",
     "pixiu_getitem_batch", "pixiu_getitem_batch_dev", "pixiu_iter", "pixiu_encoded_view",
     "pixiu_record_location", "pixiu_import_chunk", "pixiu_decode_chunk", "pixiu_rotate",
+    "pixiu_profile_enable", "pixiu_profile_get", "pixiu_stream",
 ]
 
 _lib = None
@@ -81,6 +82,11 @@ def load_library():
     L.pixiu_import_chunk.restype = C.c_int64
     L.pixiu_decode_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p]
     L.pixiu_rotate.argtypes = [C.c_void_p]
+    L.pixiu_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.pixiu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), _i64p]
+    L.pixiu_stream.argtypes = [C.c_void_p]
+    L.pixiu_stream.restype = C.c_void_p
     # test hooks
     L.pixiu_debug_sort_pairs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     L.pixiu_debug_window_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
@@ -343,6 +349,25 @@ class PiXiuCtrl:
         buf = np.zeros(max(need.value, 1), dtype=np.uint8)
         self._check(self._L.pixiu_decode_chunk(self._h, chunk, _ptr(buf), buf.size, off.ctypes.data_as(_i64p), C.byref(need)))
         return buf, off
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._L.pixiu_profile_enable(self._h, int(on)))
+
+    def profile(self) -> dict:
+        """{class: dict(ms, bytes, launches)} accumulated since profile_enable(True)"""
+        out = {}
+        cls = 0
+        while True:
+            name, ms, by, ln = C.c_char_p(), C.c_double(), C.c_double(), C.c_int64()
+            rc = self._L.pixiu_profile_get(self._h, cls, C.byref(name), C.byref(ms), C.byref(by), C.byref(ln))
+            if rc != 0:
+                break
+            out[name.value.decode()] = dict(ms=ms.value, bytes=by.value, launches=ln.value)
+            cls += 1
+        return out
+
+    def stream(self) -> int:
+        return int(self._L.pixiu_stream(self._h) or 0)
 
     def rotate(self):
         self._check(self._L.pixiu_rotate(self._h))
