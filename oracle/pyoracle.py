@@ -325,7 +325,7 @@ class Ref:
         L.ref_delitem.argtypes = [_u8p, C.c_int]
         L.ref_getitem.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
         L.ref_iter.argtypes = [_u8p, C.c_int, _u8p, C.c_longlong, _i64p, C.c_int]
-        L.ref_setitem_batch.argtypes = [C.c_int, _u8p, _i64p, _u8p, _i64p, _i32p, _i32p, _i64p, _i32p, _i32p]
+        L.ref_setitem_batch.argtypes = [C.c_int, _u8p, _i64p, _u8p, _i64p, _i32p, _i32p, _i64p, _i32p, _i32p, _i32p]
         L.ref_setitem_batch.restype = C.c_double
         L.ref_getitem_batch.argtypes = [C.c_int, _u8p, _i64p, _i64p, _i32p]
         L.ref_getitem_batch.restype = C.c_double
@@ -398,12 +398,13 @@ class Ref:
         ch = np.zeros(n, dtype=np.int64)
         idx = np.zeros(n, dtype=np.int32)
         pools = np.zeros(n, dtype=np.int32)
+        used = np.zeros(n, dtype=np.int32)
         dt = self.L.ref_setitem_batch(n, kd.ctypes.data_as(_u8p), ko.ctypes.data_as(_i64p),
                                       vd.ctypes.data_as(_u8p), vo.ctypes.data_as(_i64p),
                                       rc.ctypes.data_as(_i32p), el.ctypes.data_as(_i32p),
                                       ch.ctypes.data_as(_i64p), idx.ctypes.data_as(_i32p),
-                                      pools.ctypes.data_as(_i32p))
-        return dict(seconds=dt, rc=rc, enc_len=el, chunk=ch, idx=idx, pools=pools)
+                                      pools.ctypes.data_as(_i32p), used.ctypes.data_as(_i32p))
+        return dict(seconds=dt, rc=rc, enc_len=el, chunk=ch, idx=idx, pools=pools, pool_used=used)
 
     def getitem_batch(self, keys: list[bytes]):
         kd, ko = _pack(keys)

@@ -122,10 +122,10 @@ int ref_iter(const uint8_t *prefix, int pl, uint8_t *out, long long cap, long lo
 }
 
 // Timed batch insert (timing only the setitem loop). Per record: rc, encoded
-// length, chunk serial, idx, pools. Any out pointer may be NULL.
+// length, chunk serial, idx, pools (MemPool::nth), blocks used in the current pool. Any out pointer may be NULL.
 double ref_setitem_batch(int n, const uint8_t *keys, const long long *koff, const uint8_t *vals,
                          const long long *voff, int *rc, int *enc_len, long long *chunk, int *idx,
-                         int *pools) {
+                         int *pools, int *pool_used) {
     double t0 = now_s();
     for (int i = 0; i < n; i++) {
         int r = do_setitem(keys + koff[i], (int) (koff[i + 1] - koff[i]), vals + voff[i],
@@ -136,6 +136,7 @@ double ref_setitem_batch(int n, const uint8_t *keys, const long long *koff, cons
         if (chunk) chunk[i] = g_chunk_serial;
         if (idx) idx[i] = j;
         if (pools) pools[i] = g_ctrl->st.local_pool.nth;
+        if (pool_used) pool_used[i] = g_ctrl->st.local_pool.used_num;
     }
     return now_s() - t0;
 }

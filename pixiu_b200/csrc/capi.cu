@@ -39,6 +39,8 @@ void Store::open_window() {
     win_R = 0;
     win_N = 0;
     h_win_rec_start.assign(1, 0u);
+    pool_nth = 1;  // SuffixTree::init_prop allocates the root: first pool, 5 blocks (SuffixTree.cpp:69)
+    pool_used = 5;
     chunk_first.push_back((uint32_t) n_records());
     chunk_count.push_back(0);
 }
@@ -414,6 +416,14 @@ int pixiu_debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, int64_t n
         fprintf(stderr, "pixiu_debug_sort_pairs: %s\n", e.what());
         return PIXIU_ECUDA;
     }
+}
+
+// arena state the reference's suffix tree would have for the open window (MemPool::nth, used_num)
+int pixiu_debug_pool_state(pixiu_store *h, int32_t *nth, int32_t *used) {
+    if (!h || !nth || !used) return PIXIU_EINVAL;
+    *nth = (int32_t) h->s.pool_nth;
+    *used = (int32_t) h->s.pool_used;
+    return PIXIU_OK;
 }
 
 // copies an internal array of the last encode (open window) to the host:

@@ -190,7 +190,7 @@ k_tree_level(const uint32_t *__restrict__ in_a, const uint32_t *__restrict__ in_
 //  KEYA: KEY is the sa tree (ACC the lcp tree); otherwise KEY is the lcp tree (ACC the sa tree).
 template <bool LEFT, bool INCL, bool KEYA>
 __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start, uint32_t thr, uint32_t &acc,
-                                               uint32_t floor_) {
+                                               int64_t floor_ /* -1: never give up */) {
     auto KEY = [&](int lv, uint32_t j) { return KEYA ? T.a[lv][j] : T.l[lv][j]; };
     auto ACC = [&](int lv, uint32_t j) { return KEYA ? T.l[lv][j] : T.a[lv][j]; };
     int lv = 0;
@@ -212,7 +212,7 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
                     if (k < thr) { found = true; hit = pos; break; }
                     acc = min(acc, ACC(lv, (uint32_t) pos));
                 }
-                if (acc <= floor_) return NOTFOUND;
+                if ((int64_t) acc <= floor_) return NOTFOUND;
             }
             if (found) break;
             if (pos == 0) return NOTFOUND;
@@ -229,7 +229,7 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
                     if (k < thr) { found = true; hit = pos; break; }
                     acc = min(acc, ACC(lv, (uint32_t) pos));
                 }
-                if (acc <= floor_) return NOTFOUND;
+                if ((int64_t) acc <= floor_) return NOTFOUND;
             }
             if (found) break;
             if (pos + 1 >= (int64_t) T.size[lv]) return NOTFOUND;
@@ -254,7 +254,7 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
                     if (k < thr) { hit = c; found = true; break; }
                     acc = min(acc, ACC(lv, (uint32_t) c));
                 }
-                if (acc <= floor_) return NOTFOUND;
+                if ((int64_t) acc <= floor_) return NOTFOUND;
             }
         } else {
             for (int64_t c = b; c < e; c++) {
@@ -267,7 +267,7 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
                     if (k < thr) { hit = c; found = true; break; }
                     acc = min(acc, ACC(lv, (uint32_t) c));
                 }
-                if (acc <= floor_) return NOTFOUND;
+                if ((int64_t) acc <= floor_) return NOTFOUND;
             }
         }
         if (!found) return NOTFOUND;  // cannot happen: the block minimum promised a hit
@@ -288,14 +288,90 @@ k_lpf(MinTree T, const uint32_t *__restrict__ rank, const uint16_t *__restrict__
         uint32_t r = rank[s];
         // nearest smaller text position above r: lcp = min L[j+1..r]
         uint32_t acc = T.l[0][r];
-        int64_t j = acc ? tree_search<true, false, true>(T, r, s, acc, 0u) : -1;
+        int64_t j = acc ? tree_search<true, false, true>(T, r, s, acc, 0) : -1;
         if (j >= 0) best = acc;
         // nearest smaller text position below r: lcp = min L[r+1..j]
         acc = 0xFFFFFFFFu;
-        j = tree_search<false, true, true>(T, r, s, acc, best);
+        j = tree_search<false, true, true>(T, r, s, acc, (int64_t) best);
         if (j < (int64_t) n && acc > best) best = acc;
     }
     reach[s] = s + best;
+}
+
+// ---------------------------------------------------------------------------------
+// Arena law of the reference's window rotation (PiXiuCtrl.cpp:13; MemPool.cpp:7-37): which
+// suffixes of the new records create a suffix-tree leaf, and which of those also split an
+// edge.  Verified against the reference's MemPool counters (DESIGN.md "Window rotation"):
+//   leaf(s)   <=>  the longest earlier match M(s) ends before the record does (suffixes still
+//                  pending at SuffixTree::reset() are dropped, SuffixTree.cpp:302);
+//   split(s)  <=>  leaf(s), M > 0 and the locus of w = T[s..s+M) is not yet an explicit node:
+//                  the leftmost occurrence of w does not end its record (it would be an ex-leaf)
+//                  and all earlier occurrences of w continue with the same byte.
+// One bit per position, packed with warp ballots.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_nodes(MinTree T, const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist,
+        const uint32_t *__restrict__ rank, const uint32_t *__restrict__ reach, uint32_t s0, uint32_t n,
+        uint32_t *__restrict__ leafmask, uint32_t *__restrict__ splitmask) {
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t s = s0 + k;
+    bool leaf = false, split = false;
+    if (s < n && dist[s] != 0) {
+        const uint32_t M = reach[s] - s;
+        leaf = M < dist[s];
+        if (leaf && M > 0) {
+            const uint32_t r = rank[s];
+            const uint32_t *A = T.a[0], *L = T.l[0];
+            uint32_t accl = 0xFFFFFFFFu, accr = 0xFFFFFFFFu;
+            int64_t lo = tree_search<true, true, false>(T, r + 1, M, accl, -1);   // L[lo] < M
+            int64_t y = tree_search<false, false, false>(T, r, M, accr, -1);      // first index > r with L < M
+            int64_t hi = y - 1;
+            uint32_t t0 = min(accl, accr);                                        // leftmost occurrence of w
+            if (dist[t0] != M) {                                                  // not an ex-leaf
+                int cnt = 0;
+                // earlier occurrences above r (smaller next byte)
+                uint32_t acc = L[r];
+                if (acc >= M) {
+                    int64_t jl = tree_search<true, false, true>(T, r, s, acc, (int64_t) M - 1);
+                    if (jl >= 0 && acc >= M && dist[A[jl]] > M) {
+                        cnt++;
+                        uint32_t a2 = 0xFFFFFFFFu;
+                        int64_t x1 = tree_search<true, true, false>(T, (uint32_t) jl + 1, M + 1, a2, -1);  // child interval start
+                        if (x1 > lo) {
+                            uint32_t acc2 = L[x1];
+                            if (acc2 >= M) {
+                                int64_t j2 = tree_search<true, false, true>(T, (uint32_t) x1, s, acc2, (int64_t) M - 1);
+                                if (j2 >= lo && acc2 >= M && dist[A[j2]] > M) cnt++;
+                            }
+                        }
+                    }
+                }
+                // earlier occurrences below r (larger next byte; never terminal)
+                if (cnt < 2) {
+                    acc = 0xFFFFFFFFu;
+                    int64_t jr = tree_search<false, true, true>(T, r, s, acc, (int64_t) M - 1);
+                    if (jr <= hi && jr < (int64_t) n && acc >= M) {
+                        cnt++;
+                        if (cnt < 2) {
+                            uint32_t a2 = 0xFFFFFFFFu;
+                            int64_t y1 = tree_search<false, false, false>(T, (uint32_t) jr, M + 1, a2, -1);  // child interval end
+                            if (y1 <= hi) {
+                                uint32_t acc2 = 0xFFFFFFFFu;
+                                int64_t j2 = tree_search<false, true, true>(T, (uint32_t) y1 - 1, s, acc2, (int64_t) M - 1);
+                                if (j2 <= hi && acc2 >= M) cnt++;
+                            }
+                        }
+                    }
+                }
+                split = cnt == 1;
+            }
+        }
+    }
+    uint32_t lm = __ballot_sync(0xffffffffu, leaf), sm = __ballot_sync(0xffffffffu, split);
+    if ((threadIdx.x & 31) == 0) {
+        leafmask[k >> 5] = lm;
+        splitmask[k >> 5] = sm;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -375,8 +451,8 @@ k_emit(MinTree T, const uint8_t *__restrict__ text, const uint16_t *__restrict__
     uint32_t r = rank[sstar];
     uint32_t accl = 0xFFFFFFFFu, accr = 0xFFFFFFFFu;
     // SA interval of D[s*..i]: [x, y) with L[x] < E and L[y] < E; leftmost occurrence = min sa over it
-    tree_search<true, true, false>(T, r + 1, E, accl, 0u);
-    tree_search<false, false, false>(T, r, E, accr, 0u);
+    tree_search<true, true, false>(T, r + 1, E, accl, 0);
+    tree_search<false, false, false>(T, r, E, accr, 0);
     uint32_t left = min(accl, accr);
     if (left >= sstar || E < rl) {
         atomicExch(err, 2u);
@@ -562,6 +638,7 @@ static void build_suffix_array(Store &S, uint32_t N) {
         PX_CUDA(cudaStreamSynchronize(st));
         if (h_cnt[2]) throw std::runtime_error("radix sort look-back timed out");
         uint32_t An = h_cnt[0], G = h_cnt[1];
+        if (getenv("PIXIU_TRACE")) fprintf(stderr, "[sa] N=%u sorted_by=%u active=%u groups=%u\n", N, h, An, G);
         if (An == 0) break;
         if (h > 65535u) throw std::runtime_error("suffix array: groups left after h > 65535");
         // (3) next keys: (group, rank[i+h]) and sort
@@ -584,12 +661,83 @@ static void build_suffix_array(Store &S, uint32_t N) {
     S.launches += L;
 }
 
-void Store::encode_window_records(uint32_t first_new) {
+// Replays the reference's arena allocations (MemPool::p_malloc, MemPool.cpp:7-37) for the leaf /
+// split events of the candidate records and returns how many of them fit before the rotation
+// trigger `nth >= 2048` (PiXiuCtrl.cpp:13).  Commits pool_nth/pool_used for the accepted ones.
+uint32_t Store::count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32_t s0, uint32_t N) {
     EncodeScratch &E = es;
-    const uint32_t N = win_N, R = win_R;
+    const uint32_t M = N - s0;
+    const uint32_t grid = div_up<uint32_t>(M, 256);
+    const size_t words = (size_t) grid * 8;
+    E.leafmask.reserve_discard(words);
+    E.splitmask.reserve_discard(words);
+    prof.begin(PC_NODES, st);
+    k_nodes<<<grid, 256, 0, st>>>(T, w_text.p, w_dist.p, E.rank.p, E.reach.p, s0, N, E.leafmask.p, E.splitmask.p);
+    prof.end(st, 30.0 * M, 1);
+    launches++;
+    std::vector<uint32_t> lm(words), sm(words);
+    PX_CUDA(cudaMemcpyAsync(lm.data(), E.leafmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(sm.data(), E.splitmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    constexpr uint32_t C = 65535;  // POOL_BLOCK_NUM (MemPool.h:6)
+    uint32_t nth = pool_nth, used = pool_used;
+    auto alloc = [&](uint32_t blocks) {
+        if (blocks > C - used) {  // does not fit: next pool (MemPool.cpp:23-29)
+            nth++;
+            used = 0;
+        }
+        used += blocks;
+    };
+    uint32_t accepted = 0;
+    uint64_t node_blocks = 0;
+    for (uint32_t r = first_new; r < win_R; r++) {
+        if (r > first_new && nth >= 2048) break;  // PiXiuCtrl.cpp:13: checked before inserting record r
+        uint32_t ka = h_win_rec_start[r] - s0, kb = h_win_rec_start[r + 1] - 1 - s0;  // bit range of the record
+        for (uint32_t k = ka; k < kb;) {
+            uint32_t w = k >> 5, b0 = k & 31;
+            uint32_t b1 = std::min<uint32_t>(32, b0 + (kb - k));
+            uint32_t mask = (b1 == 32 ? 0xFFFFFFFFu : ((1u << b1) - 1)) & ~((1u << b0) - 1);
+            uint32_t ml = lm[w] & mask, ms = sm[w] & ml;
+            uint32_t blocks = 8u * (uint32_t) (__builtin_popcount(ml) + __builtin_popcount(ms));
+            node_blocks += blocks;
+            if (blocks <= C - used) {
+                used += blocks;  // everything fits in the current pool: no tail waste possible
+            } else {
+                while (ml) {  // allocation by allocation: leaf 5,3 / leaf+split 5,5,3,3 (SuffixTree.cpp:193-231)
+                    uint32_t bit = ml & (0u - ml);
+                    if (ms & bit) {
+                        alloc(5);
+                        alloc(5);
+                        alloc(3);
+                        alloc(3);
+                    } else {
+                        alloc(5);
+                        alloc(3);
+                    }
+                    ml ^= bit;
+                }
+            }
+            k += b1 - b0;
+        }
+        accepted++;
+        pool_nth = nth;
+        pool_used = used;
+    }
+    uint32_t bytes = h_win_rec_start[first_new + accepted] - s0;
+    if (bytes > 4096) {
+        // node_blocks covers all candidates scanned; good enough for the running estimate
+        double r_new = (double) node_blocks / 8.0 / (double) (h_win_rec_start[std::min(win_R, first_new + accepted + 1)] - s0);
+        if (r_new > 0.01) rho = 0.5 * rho + 0.5 * r_new;
+    }
+    return accepted;
+}
+
+uint32_t Store::encode_window_records(uint32_t first_new) {
+    EncodeScratch &E = es;
+    uint32_t N = win_N, R = win_R;
     const uint32_t s0 = h_win_rec_start[first_new];
-    const uint32_t n_new = R - first_new;
-    const uint32_t M = N - s0;  // new positions
+    uint32_t n_new = R - first_new;
+    uint32_t M = N - s0;  // new positions
     int L = 0;
 
     build_suffix_array(*this, N);
@@ -647,9 +795,24 @@ void Store::encode_window_records(uint32_t first_new) {
     prof.begin(PC_LPF, st);
     k_lpf<<<gridM, 256, 0, st>>>(T, E.rank.p, w_dist.p, s0, N, E.reach.p);
     prof.end(st, 18.0 * M, 1);
+    L++;
+    // ---- reference rotation rule: keep only the records that fit the arena budget ----
+    if (cfg.rotate_policy == PIXIU_ROTATE_REFERENCE) {
+        uint32_t acc = count_nodes_and_cut(T, first_new, s0, N);
+        if (acc < n_new) {
+            n_new = acc;
+            R = first_new + acc;
+            N = h_win_rec_start[R];
+            M = N - s0;
+            win_R = R;
+            win_N = N;
+            h_win_rec_start.resize(R + 1);
+            gridM = div_up<uint32_t>(M, 256);
+        }
+    }
     prof.begin(PC_FLAGS, st);
     k_flag_scatter<<<gridM, 256, 0, st>>>(E.reach.p, w_dist.p, s0, N, E.flagp.p);
-    L += 2;
+    L++;
     {
         // lastnon[i] = index of the last non-251 byte at or before i (max-scan of index+1, stored -1).
         // Position s0-1 is a separator (or the text start), i.e. "non-251": seed element 0 with it.
@@ -743,6 +906,7 @@ void Store::encode_window_records(uint32_t first_new) {
     n_tiles += new_tiles;
     chunk_count.back() += n_new;
     launches += L;
+    return n_new;
 }
 
 int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals,
@@ -774,16 +938,30 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     const int64_t hard_cap = (1ll << 30) - (1ll << 17);
     const int64_t budget = cfg.rotate_policy == PIXIU_ROTATE_RECORDS ? hard_cap : std::min<int64_t>(cfg.window_bytes, hard_cap);
     const size_t g_batch_first = n_records();
+    const bool ref_policy = cfg.rotate_policy == PIXIU_ROTATE_REFERENCE;
     uint32_t a = 0;
     while (a < nn) {
-        if (win_open && (win_R >= MAX_CHUNK_RECS || (int64_t) win_N + h_doc_len[a] + 1 > budget)) close_window();
+        if (win_open) {
+            bool full = win_R >= MAX_CHUNK_RECS;
+            if (ref_policy) full = full || pool_nth >= 2048;                       // PiXiuCtrl.cpp:13
+            else full = full || (int64_t) win_N + h_doc_len[a] + 1 > budget;
+            if (full) close_window();
+        }
         if (!win_open) open_window();
+        int64_t lim = budget;
+        if (ref_policy) {
+            // candidates: what the remaining arena is expected to hold (+4% and one record); the exact cut is
+            // found by count_nodes_and_cut.  At least double the window so re-sorting stays geometric.
+            double blocks_left = (2048.0 - pool_nth) * 65535.0 + (65535.0 - pool_used);
+            double est = blocks_left / (8.0 * rho) * 1.04 + 70000.0;
+            lim = std::min<int64_t>(hard_cap, (int64_t) win_N + (int64_t) std::max<double>(est, (double) win_N));
+        }
         // records [a, b) go into the open window
         uint32_t b = a;
         uint64_t bytes = win_N;
         std::vector<uint32_t> &rs = h_win_rec_start;
         while (b < nn && win_R + (b - a) < MAX_CHUNK_RECS &&
-               (b == a ? true : (int64_t) (bytes + h_doc_len[b] + 1) <= budget)) {
+               (b == a ? true : (int64_t) (bytes + h_doc_len[b] + 1) <= lim)) {
             bytes += h_doc_len[b] + 1;
             rs.push_back((uint32_t) bytes);
             b++;
@@ -802,8 +980,9 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         launches++;
         win_R += n_new;
         win_N = newN;
-        encode_window_records(first_new);
-        a = b;
+        uint32_t acc = encode_window_records(first_new);
+        a += acc;
+        if (acc < n_new) close_window();  // the arena budget was reached inside the candidates: rotate
     }
     PX_CUDA(cudaEventRecord(ev1, st));
     // ---- index maintenance (host CritBit; in-order semantics of n sequential setitem calls) ----

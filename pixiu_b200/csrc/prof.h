@@ -18,6 +18,7 @@ enum ProfClass {
     PC_LCP,          // k_lcp
     PC_TREE,         // k_tree_level
     PC_LPF,          // k_lpf
+    PC_NODES,        // k_nodes (reference rotation rule)
     PC_FLAGS,        // k_flag_scatter, k_pair_rule, run/offset scans
     PC_EMIT,         // k_emit
     PC_TABLES,       // k_record_tables, k_tile_desc
@@ -28,7 +29,7 @@ enum ProfClass {
 
 inline const char *prof_class_name(int c) {
     static const char *names[PC_COUNT] = {"docs", "init_keys", "sort_hist", "sort_pass", "rank_scan", "round_keys", "lcp",
-                                          "tree", "lpf", "flags", "emit", "tables", "decode", "lookup"};
+                                          "tree", "lpf", "nodes", "flags", "emit", "tables", "decode", "lookup"};
     return c >= 0 && c < PC_COUNT ? names[c] : "?";
 }
 

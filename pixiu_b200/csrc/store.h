@@ -48,6 +48,7 @@ struct EncodeScratch {
     DevBuf<uint64_t> scan_tmp64;
     DevBuf<uint32_t> tree_a, tree_l;
     DevBuf<uint8_t> flagp, flagc;
+    DevBuf<uint32_t> leafmask, splitmask;
     DevBuf<uint32_t> counters;  // [0] active count, [1] group count, [2] error flag, [3..] misc
     RadixSortTemp rs;
 };
@@ -82,6 +83,9 @@ struct Store {
     DevBuf<uint16_t> w_dist, w_recid;
     DevBuf<uint32_t> w_rec_start;
     std::vector<uint32_t> h_win_rec_start;  // R+1
+    // arena state of the reference's suffix tree for the open window (MemPool::nth / used_num)
+    uint32_t pool_nth = 1, pool_used = 5;
+    double rho = 1.35;  // running estimate of suffix-tree nodes per window byte
 
     EncodeScratch es;
     std::unique_ptr<HostIndex> index;
@@ -116,7 +120,8 @@ struct Store {
     int setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals,
                       const int64_t *d_voff, const uint8_t *h_keys, const int64_t *h_koff,
                       const int64_t *h_voff, int32_t *rc, int32_t *saved);
-    void encode_window_records(uint32_t first_new);
+    uint32_t encode_window_records(uint32_t first_new);  // returns the number of records accepted
+    uint32_t count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32_t s0, uint32_t N);
     // decode.cu
     void decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off);
     int64_t import_chunk(int64_t n, const uint8_t *enc, const int64_t *enc_off);

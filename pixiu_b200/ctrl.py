@@ -91,6 +91,7 @@ def load_library():
     L.pixiu_debug_sort_pairs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     L.pixiu_debug_window_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
     L.pixiu_debug_window_array.restype = C.c_int64
+    L.pixiu_debug_pool_state.argtypes = [C.c_void_p, _i32p, _i32p]
     _lib = L
     return L
 
@@ -371,6 +372,11 @@ class PiXiuCtrl:
 
     def rotate(self):
         self._check(self._L.pixiu_rotate(self._h))
+
+    def debug_pool_state(self):
+        nth, used = C.c_int32(), C.c_int32()
+        self._L.pixiu_debug_pool_state(self._h, C.byref(nth), C.byref(used))
+        return nth.value, used.value
 
     def debug_window_array(self, name: str, dtype):
         n = self.stats().window_bytes

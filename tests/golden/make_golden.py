@@ -3,7 +3,7 @@
 Run here (where /root/reference is mounted):  python tests/golden/make_golden.py
 The fixtures pin the oracle (and through it the CUDA path) to what the
 unmodified reference stores for seeded inputs: per record the encoded bytes,
-setitem rc, chunk serial / idx, and arena pools (MemPool::nth).
+setitem rc, chunk serial / idx, arena pools (MemPool::nth) and blocks used in the current pool.
 """
 import os
 import random
@@ -50,7 +50,7 @@ def dump(name, ref, keys, vals):
     vd, vo = synth.pack(vals)
     ed, eo = synth.pack(encs)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), keys=kd, key_off=ko, vals=vd, val_off=vo,
-                        enc=ed, enc_off=eo, rc=r["rc"], pools=r["pools"])
+                        enc=ed, enc_off=eo, rc=r["rc"], pools=r["pools"], pool_used=r["pool_used"])
     print(name, len(keys), "records", int(vo[-1]), "value bytes ->", int(eo[-1]), "encoded")
 
 

@@ -16,5 +16,5 @@ def _split(data, off):
 def load(name):
     z = np.load(os.path.join(HERE, "golden", name + ".npz"))
     return dict(keys=_split(z["keys"], z["key_off"]), vals=_split(z["vals"], z["val_off"]),
-                enc=_split(z["enc"], z["enc_off"]), rc=z["rc"], pools=z["pools"],
+                enc=_split(z["enc"], z["enc_off"]), rc=z["rc"], pools=z["pools"], pool_used=z["pool_used"],
                 packed=(z["keys"], z["key_off"], z["vals"], z["val_off"]))

@@ -224,3 +224,46 @@ def test_crud_differential(ctrl_mod):
     assert c.getitem(b"missing") is None
     assert c.delitem(b"solo") == 0 and c.delitem(b"solo") == 1
     c.free_prop()
+
+
+# --------------------------------------------------------------------------- window rotation (PiXiuCtrl.cpp:13-17)
+@pytest.mark.parametrize("name", GOLDEN)
+def test_arena_accounting_matches_reference_fixture(ctrl_mod, name):
+    """MemPool::nth / used_num predicted from the suffix array == what the reference's arena held"""
+    g = load(name)
+    keys, vals = g["keys"], g["vals"]
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_REFERENCE, strict251=True)
+    rng = random.Random(3)
+    a = 0
+    while a < len(keys):
+        b = min(len(keys), a + rng.randint(1, 40))
+        c.setitem_batch(keys[a:b], vals[a:b])
+        assert c.debug_pool_state() == (int(g["pools"][b - 1]), int(g["pool_used"][b - 1])), f"{name}: after record {b - 1}"
+        a = b
+    for i in range(len(keys)):
+        assert c.encoded(0, i) == g["enc"][i]
+    c.free_prop()
+
+
+def test_reference_rotation_live(ctrl_mod, ref):
+    """More than one full reference window of pages: same rotation record, same bytes on both sides."""
+    kd, ko, vd, vo = synth.gen_html_pages(520, seed=2)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    ref.reset()
+    r = ref.setitem_batch(keys, vals)
+    chunk_of = r["chunk"]
+    assert chunk_of[-1] >= 1, "the sample must make the reference rotate at least once"
+    first_rot = int(np.argmax(chunk_of > 0))
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_REFERENCE, strict251=True)
+    _, saved = c.setitem_batch((kd, ko), (vd, vo))
+    locs = [c.record_location(i) for i in range(len(keys))]
+    assert [l[0] for l in locs] == chunk_of.tolist(), f"rotation differs (reference rotates at record {first_rot})"
+    assert [l[1] for l in locs] == r["idx"].tolist()
+    enc_len = np.array([len(po.make_doc(k, v)) for k, v in zip(keys, vals)]) - saved
+    assert enc_len.tolist() == r["enc_len"].tolist()
+    # bytes of the records of the open (last) reference chunk
+    last = int(chunk_of[-1])
+    for i in range(len(keys)):
+        if chunk_of[i] == last:
+            assert c.encoded(last, int(r["idx"][i])) == ref.encoded(int(r["idx"][i]))
+    c.free_prop()
