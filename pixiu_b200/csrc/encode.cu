@@ -11,6 +11,7 @@
 // reach(s) = s+M(s);  byte i is PASS iff i is a value of reach;  the pointer of a run ending at j
 // is the end of the leftmost occurrence of D[s*(j)..j],  s*(j) = min{s : reach(s) > j}.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "index.h"
@@ -277,100 +278,96 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
 
 // ---------------------------------------------------------------------------------
 // K6: longest previous factor. reach[s] = s + M(s) for the new positions s >= s0.
+//
+// With NODES the same two neighbour searches also answer the arena law of the reference's window
+// rotation (PiXiuCtrl.cpp:13; MemPool.cpp:7-37) — which suffixes of the new records create a
+// suffix-tree leaf and which of those also split an edge (verified against the reference's MemPool
+// counters, DESIGN.md "Window rotation"):
+//   leaf(s)   <=>  M(s) ends before the record does (suffixes still pending at SuffixTree::reset()
+//                  are dropped, SuffixTree.cpp:302);
+//   split(s)  <=>  leaf(s), M > 0 and the locus of w = T[s..s+M) is not yet an explicit node, i.e. the
+//                  leftmost occurrence of w does not end its record (it would be an ex-leaf that simply
+//                  gains a child, SuffixTree.cpp:223-230) and all earlier occurrences of w that continue
+//                  do so with the same byte.
+// Earlier occurrences of w with a smaller next byte sit above rank[s] in the suffix array, those with a
+// larger one below; occurrences that end their record ("terminal") sort first.  One bit per position.
 // ---------------------------------------------------------------------------------
+template <bool NODES>
 __global__ void __launch_bounds__(256)
-k_lpf(MinTree T, const uint32_t *__restrict__ rank, const uint16_t *__restrict__ dist, uint32_t s0, uint32_t n,
-      uint32_t *__restrict__ reach) {
-    uint32_t s = s0 + blockIdx.x * 256 + threadIdx.x;
-    if (s >= n) return;
-    uint32_t best = 0;
-    if (dist[s] != 0) {
-        uint32_t r = rank[s];
-        // nearest smaller text position above r: lcp = min L[j+1..r]
-        uint32_t acc = T.l[0][r];
-        int64_t j = acc ? tree_search<true, false, true>(T, r, s, acc, 0) : -1;
-        if (j >= 0) best = acc;
-        // nearest smaller text position below r: lcp = min L[r+1..j]
-        acc = 0xFFFFFFFFu;
-        j = tree_search<false, true, true>(T, r, s, acc, (int64_t) best);
-        if (j < (int64_t) n && acc > best) best = acc;
-    }
-    reach[s] = s + best;
-}
-
-// ---------------------------------------------------------------------------------
-// Arena law of the reference's window rotation (PiXiuCtrl.cpp:13; MemPool.cpp:7-37): which
-// suffixes of the new records create a suffix-tree leaf, and which of those also split an
-// edge.  Verified against the reference's MemPool counters (DESIGN.md "Window rotation"):
-//   leaf(s)   <=>  the longest earlier match M(s) ends before the record does (suffixes still
-//                  pending at SuffixTree::reset() are dropped, SuffixTree.cpp:302);
-//   split(s)  <=>  leaf(s), M > 0 and the locus of w = T[s..s+M) is not yet an explicit node:
-//                  the leftmost occurrence of w does not end its record (it would be an ex-leaf)
-//                  and all earlier occurrences of w continue with the same byte.
-// One bit per position, packed with warp ballots.
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_nodes(MinTree T, const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist,
-        const uint32_t *__restrict__ rank, const uint32_t *__restrict__ reach, uint32_t s0, uint32_t n,
-        uint32_t *__restrict__ leafmask, uint32_t *__restrict__ splitmask) {
+k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ rank, const uint16_t *__restrict__ dist,
+      uint32_t s0, uint32_t n, uint32_t *__restrict__ reach, uint32_t *__restrict__ leafmask,
+      uint32_t *__restrict__ splitmask) {
     const uint32_t k = blockIdx.x * 256 + threadIdx.x;
     const uint32_t s = s0 + k;
     bool leaf = false, split = false;
-    if (s < n && dist[s] != 0) {
-        const uint32_t M = reach[s] - s;
-        leaf = M < dist[s];
-        if (leaf && M > 0) {
-            const uint32_t r = rank[s];
+    if (s < n) {
+        uint32_t best = 0;
+        const uint32_t d = dist[s];
+        if (d != 0) {
             const uint32_t *A = T.a[0], *L = T.l[0];
-            uint32_t accl = 0xFFFFFFFFu, accr = 0xFFFFFFFFu;
-            int64_t lo = tree_search<true, true, false>(T, r + 1, M, accl, -1);   // L[lo] < M
-            int64_t y = tree_search<false, false, false>(T, r, M, accr, -1);      // first index > r with L < M
-            int64_t hi = y - 1;
-            uint32_t t0 = min(accl, accr);                                        // leftmost occurrence of w
-            if (dist[t0] != M) {                                                  // not an ex-leaf
-                int cnt = 0;
-                // earlier occurrences above r (smaller next byte)
-                uint32_t acc = L[r];
-                if (acc >= M) {
-                    int64_t jl = tree_search<true, false, true>(T, r, s, acc, (int64_t) M - 1);
-                    if (jl >= 0 && acc >= M && dist[A[jl]] > M) {
-                        cnt++;
-                        uint32_t a2 = 0xFFFFFFFFu;
-                        int64_t x1 = tree_search<true, true, false>(T, (uint32_t) jl + 1, M + 1, a2, -1);  // child interval start
-                        if (x1 > lo) {
+            const uint32_t r = rank[s];
+            // nearest smaller text position above r: lcp = min L[j+1..r]
+            uint32_t l1 = L[r];
+            int64_t jl = l1 ? tree_search<true, false, true>(T, r, s, l1, 0) : -1;
+            if (jl < 0) l1 = 0;
+            // nearest smaller text position below r: lcp = min L[r+1..j]; ties with l1 matter for NODES
+            uint32_t l2 = 0xFFFFFFFFu;
+            int64_t jr = tree_search<false, true, true>(T, r, s, l2, (NODES && l1 > 0) ? (int64_t) l1 - 1 : (int64_t) l1);
+            if (jr >= (int64_t) n) l2 = 0;
+            best = max(l1, l2);
+            if (NODES) {
+                const uint32_t M = best;
+                leaf = M < d;
+                if (leaf && M > 0) {
+                    bool up = l1 == M && dist[A[jl]] > M;  // a continuing earlier occurrence above
+                    bool dn = l2 == M;                      // ... below (never terminal)
+                    bool is_explicit = (up && dn) || (!up && !dn);  // two next bytes | only ex-leaf occurrences
+                    if (!is_explicit) {
+                        // exactly one side: a second distinct next byte needs an earlier occurrence beyond the
+                        // child interval of (w + that side's byte), still inside w's interval (lcp >= M)
+                        if (up) {
+                            uint32_t a2 = 0xFFFFFFFFu;
+                            int64_t x1 = tree_search<true, true, false>(T, (uint32_t) jl + 1, M + 1, a2, -1);
                             uint32_t acc2 = L[x1];
                             if (acc2 >= M) {
                                 int64_t j2 = tree_search<true, false, true>(T, (uint32_t) x1, s, acc2, (int64_t) M - 1);
-                                if (j2 >= lo && acc2 >= M && dist[A[j2]] > M) cnt++;
+                                if (j2 >= 0 && acc2 >= M && dist[A[j2]] > M) is_explicit = true;
                             }
-                        }
-                    }
-                }
-                // earlier occurrences below r (larger next byte; never terminal)
-                if (cnt < 2) {
-                    acc = 0xFFFFFFFFu;
-                    int64_t jr = tree_search<false, true, true>(T, r, s, acc, (int64_t) M - 1);
-                    if (jr <= hi && jr < (int64_t) n && acc >= M) {
-                        cnt++;
-                        if (cnt < 2) {
+                        } else {
                             uint32_t a2 = 0xFFFFFFFFu;
-                            int64_t y1 = tree_search<false, false, false>(T, (uint32_t) jr, M + 1, a2, -1);  // child interval end
-                            if (y1 <= hi) {
+                            int64_t y1 = tree_search<false, false, false>(T, (uint32_t) jr, M + 1, a2, -1);
+                            if (y1 < (int64_t) n) {
                                 uint32_t acc2 = 0xFFFFFFFFu;
                                 int64_t j2 = tree_search<false, true, true>(T, (uint32_t) y1 - 1, s, acc2, (int64_t) M - 1);
-                                if (j2 <= hi && acc2 >= M) cnt++;
+                                if (j2 < (int64_t) n && acc2 >= M) is_explicit = true;
+                            }
+                        }
+                        // ex-leaf: the leftmost occurrence of w ends its record.  Every record ends with
+                        // 251,0 or 251,2, so this needs w to end in 0 or 2 — rare; only then pay for the
+                        // SA interval of w and its minimum.
+                        if (!is_explicit) {
+                            uint8_t lastb = text[s + M - 1];
+                            if (lastb == 0 || lastb == 2) {
+                                uint32_t accl = 0xFFFFFFFFu, accr = 0xFFFFFFFFu;
+                                tree_search<true, true, false>(T, r + 1, M, accl, 0);
+                                tree_search<false, false, false>(T, r, M, accr, 0);
+                                uint32_t t0 = min(accl, accr);
+                                if (dist[t0] == M) is_explicit = true;
                             }
                         }
                     }
+                    split = !is_explicit;
                 }
-                split = cnt == 1;
             }
         }
+        reach[s] = s + best;
     }
-    uint32_t lm = __ballot_sync(0xffffffffu, leaf), sm = __ballot_sync(0xffffffffu, split);
-    if ((threadIdx.x & 31) == 0) {
-        leafmask[k >> 5] = lm;
-        splitmask[k >> 5] = sm;
+    if (NODES) {
+        uint32_t lm = __ballot_sync(0xffffffffu, leaf), sm = __ballot_sync(0xffffffffu, split);
+        if ((threadIdx.x & 31) == 0) {
+            leafmask[k >> 5] = lm;
+            splitmask[k >> 5] = sm;
+        }
     }
 }
 
@@ -667,18 +664,13 @@ static void build_suffix_array(Store &S, uint32_t N) {
 uint32_t Store::count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32_t s0, uint32_t N) {
     EncodeScratch &E = es;
     const uint32_t M = N - s0;
-    const uint32_t grid = div_up<uint32_t>(M, 256);
-    const size_t words = (size_t) grid * 8;
-    E.leafmask.reserve_discard(words);
-    E.splitmask.reserve_discard(words);
-    prof.begin(PC_NODES, st);
-    k_nodes<<<grid, 256, 0, st>>>(T, w_text.p, w_dist.p, E.rank.p, E.reach.p, s0, N, E.leafmask.p, E.splitmask.p);
-    prof.end(st, 30.0 * M, 1);
-    launches++;
+    const size_t words = (size_t) div_up<uint32_t>(M, 256) * 8;  // written by k_lpf<true>
+    auto t_a = std::chrono::steady_clock::now();
     std::vector<uint32_t> lm(words), sm(words);
     PX_CUDA(cudaMemcpyAsync(lm.data(), E.leafmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaMemcpyAsync(sm.data(), E.splitmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
+    auto t_b = std::chrono::steady_clock::now();
     constexpr uint32_t C = 65535;  // POOL_BLOCK_NUM (MemPool.h:6)
     uint32_t nth = pool_nth, used = pool_used;
     auto alloc = [&](uint32_t blocks) {
@@ -723,12 +715,15 @@ uint32_t Store::count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32
         pool_nth = nth;
         pool_used = used;
     }
-    uint32_t bytes = h_win_rec_start[first_new + accepted] - s0;
-    if (bytes > 4096) {
-        // node_blocks covers all candidates scanned; good enough for the running estimate
-        double r_new = (double) node_blocks / 8.0 / (double) (h_win_rec_start[std::min(win_R, first_new + accepted + 1)] - s0);
-        if (r_new > 0.01) rho = 0.5 * rho + 0.5 * r_new;
+    if (getenv("PIXIU_TRACE")) {
+        auto t_c = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rot] cand=%u accepted=%u nth=%u wait+d2h=%.3f ms replay=%.3f ms rho=%.3f\n", win_R - first_new, accepted,
+                pool_nth, std::chrono::duration<double, std::milli>(t_b - t_a).count(),
+                std::chrono::duration<double, std::milli>(t_c - t_b).count(), rho);
     }
+    // running estimate of nodes per byte (drives the next candidate selection only; the cut is exact)
+    uint32_t bytes = h_win_rec_start[first_new + accepted] - s0;
+    if (bytes > (2u << 20)) rho = std::max(0.02, (double) node_blocks / 8.0 / (double) bytes);
     return accepted;
 }
 
@@ -793,7 +788,13 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
     PX_CUDA(cudaMemsetAsync(E.flagp.p + s0, 0, (size_t) M + 2, st));
     uint32_t gridM = div_up<uint32_t>(M, 256);
     prof.begin(PC_LPF, st);
-    k_lpf<<<gridM, 256, 0, st>>>(T, E.rank.p, w_dist.p, s0, N, E.reach.p);
+    if (cfg.rotate_policy == PIXIU_ROTATE_REFERENCE) {
+        E.leafmask.reserve_discard((size_t) gridM * 8);
+        E.splitmask.reserve_discard((size_t) gridM * 8);
+        k_lpf<true><<<gridM, 256, 0, st>>>(T, w_text.p, E.rank.p, w_dist.p, s0, N, E.reach.p, E.leafmask.p, E.splitmask.p);
+    } else {
+        k_lpf<false><<<gridM, 256, 0, st>>>(T, w_text.p, E.rank.p, w_dist.p, s0, N, E.reach.p, nullptr, nullptr);
+    }
     prof.end(st, 18.0 * M, 1);
     L++;
     // ---- reference rotation rule: keep only the records that fit the arena budget ----
@@ -951,10 +952,10 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         int64_t lim = budget;
         if (ref_policy) {
             // candidates: what the remaining arena is expected to hold (+4% and one record); the exact cut is
-            // found by count_nodes_and_cut.  At least double the window so re-sorting stays geometric.
+            // found by count_nodes_and_cut.  At least a quarter of the window so re-sorting stays geometric.
             double blocks_left = (2048.0 - pool_nth) * 65535.0 + (65535.0 - pool_used);
             double est = blocks_left / (8.0 * rho) * 1.04 + 70000.0;
-            lim = std::min<int64_t>(hard_cap, (int64_t) win_N + (int64_t) std::max<double>(est, (double) win_N));
+            lim = std::min<int64_t>(hard_cap, (int64_t) win_N + (int64_t) std::max<double>(est, (double) win_N / 4));
         }
         // records [a, b) go into the open window
         uint32_t b = a;

@@ -267,3 +267,15 @@ def test_reference_rotation_live(ctrl_mod, ref):
         if chunk_of[i] == last:
             assert c.encoded(last, int(r["idx"][i])) == ref.encoded(int(r["idx"][i]))
     c.free_prop()
+
+
+def test_cpp_facade_reference_call_shapes(ctrl_mod):
+    """tests/cpp/facade_test.cpp: the reference's t_PiXiuCtrl scenario against include/PiXiuCtrl.hpp"""
+    import os
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "facade_test")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "facade_test ok" in r.stdout
