@@ -25,13 +25,17 @@ void Store::init(const pixiu_config &c) {
 
 void Store::grow_record_tables(size_t n_total, uint64_t enc_total, uint64_t tiles_total) {
     const size_t n_old = n_records();
-    d_enc.reserve_keep(enc_total + 64, enc_bytes, st);
-    d_enc_off.reserve_keep(n_total + 1, n_old, st);
-    d_enc_len.reserve_keep(n_total + 1, n_old, st);
-    d_dec_len.reserve_keep(n_total + 1, n_old, st);
-    d_first.reserve_keep(n_total + 1, n_old, st);
-    d_tile_base.reserve_keep(n_total + 1, n_old, st);
-    d_tile_desc.reserve_keep(tiles_total + 2, n_tiles, st);
+    // the compressed arena starts at 1 GiB and doubles: re-allocating GBs (cudaMalloc + copy + cudaFree) stalls ingest
+    d_enc.reserve_keep(std::max<uint64_t>(enc_total + 64, d_enc.cap ? 0 : (1ull << 30)), enc_bytes, st);
+    // record tables start at 1 M records / 4 M tiles (a few MB): every re-allocation is a cudaMalloc + copy +
+    // stream sync + cudaFree, which stalls ingest for milliseconds
+    const size_t rmin = d_enc_off.cap ? 0 : (1u << 20), tmin = d_tile_desc.cap ? 0 : (4u << 20);
+    d_enc_off.reserve_keep(std::max(n_total + 1, rmin), n_old, st);
+    d_enc_len.reserve_keep(std::max(n_total + 1, rmin), n_old, st);
+    d_dec_len.reserve_keep(std::max(n_total + 1, rmin), n_old, st);
+    d_first.reserve_keep(std::max(n_total + 1, rmin), n_old, st);
+    d_tile_base.reserve_keep(std::max(n_total + 1, rmin), n_old, st);
+    d_tile_desc.reserve_keep(std::max<size_t>(tiles_total + 2, tmin), n_tiles, st);
 }
 
 void Store::open_window() {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -47,14 +48,16 @@ struct DevBuf {
         if (n <= cap) return;
         release();
         size_t want = n + n / 4 + 256;
+        if (getenv("PIXIU_TRACE")) fprintf(stderr, "[mem] alloc %zu bytes\n", want * sizeof(T));
         PX_CUDA(cudaMalloc(&p, want * sizeof(T)));
         cap = want;
     }
     // ensure capacity >= n elements, preserving the first `keep` elements
     void reserve_keep(size_t n, size_t keep, cudaStream_t st) {
         if (n <= cap) return;
-        size_t want = n + n / 2 + 256;
+        size_t want = std::max<size_t>(2 * cap, n + n / 2 + 256);
         T *q = nullptr;
+        if (getenv("PIXIU_TRACE")) fprintf(stderr, "[mem] grow %zu -> %zu bytes (keep %zu)\n", cap * sizeof(T), want * sizeof(T), keep * sizeof(T));
         PX_CUDA(cudaMalloc(&q, want * sizeof(T)));
         if (p && keep) PX_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
         if (p) {
@@ -62,6 +65,27 @@ struct DevBuf {
             cudaFree(p);
         }
         p = q;
+        cap = want;
+    }
+};
+
+// Growable pinned host buffer (D2H targets that the host then walks)
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    void reserve_discard(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        size_t want = n + n / 4 + 256;
+        PX_CUDA(cudaMallocHost(&p, want * sizeof(T)));
         cap = want;
     }
 };
@@ -76,6 +100,24 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 }
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// relaxed (no fence) device-scope accesses for look-back status words: the word itself carries the
+// whole message (flag + value), so no ordering with other memory is needed and loads can overlap
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v));
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 #endif
 

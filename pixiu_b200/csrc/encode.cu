@@ -47,55 +47,69 @@ k_doc_len(uint32_t n, const uint8_t *__restrict__ keys, const int64_t *__restric
     }
 }
 
-__device__ __forceinline__ uint32_t write_escaped(const uint8_t *__restrict__ src, int64_t a, int64_t b,
-                                                  uint8_t *__restrict__ text, uint32_t dst) {
-    const int lane = lane_id();
-    const uint32_t lt = (1u << lane) - 1;
-    for (int64_t base = a; base < b; base += 32) {
-        int64_t i = base + lane;
-        bool valid = i < b;
-        uint8_t byte = valid ? src[i] : 0;
-        bool esc = valid && byte == 251;
-        uint32_t bal = __ballot_sync(0xffffffffu, esc);
-        if (valid) {
-            uint32_t p = dst + lane + __popc(bal & lt);
-            text[p] = byte;
-            if (esc) text[p + 1] = 251;
+// CTA-cooperative escaped copy of src[a, b) to text[dst..]: 16 bytes per thread and iteration, the
+// positions shifted by the number of 251s before them (block scan).  Returns the new dst.
+__device__ __forceinline__ uint32_t block_write_escaped(const uint8_t *__restrict__ src, int64_t a, int64_t b,
+                                                        uint8_t *__restrict__ text, uint32_t dst, uint32_t *sm) {
+    constexpr int PER = 16;
+    for (int64_t base = a; base < b; base += 256 * PER) {
+        int64_t i0 = base + (int64_t) threadIdx.x * PER;
+        uint8_t v[PER];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            v[k] = i0 + k < b ? src[i0 + k] : 0;
+            cnt += (i0 + k < b) && v[k] == 251;
         }
-        int64_t cnt = b - base < 32 ? b - base : 32;
-        dst += (uint32_t) cnt + __popc(bal);
+        uint32_t total;
+        uint32_t pre = block_scan_exclusive<uint32_t>(cnt, OpSum(), 0u, sm, &total);
+        uint32_t p = dst + threadIdx.x * PER + pre;
+        if (total == 0) {
+#pragma unroll
+            for (int k = 0; k < PER; k++)
+                if (i0 + k < b) text[p + k] = v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < PER; k++)
+                if (i0 + k < b) {
+                    text[p++] = v[k];
+                    if (v[k] == 251) text[p++] = 251;
+                }
+        }
+        int64_t chunk = b - base < 256 * PER ? b - base : 256 * PER;
+        dst += (uint32_t) chunk + total;
     }
     return dst;
 }
 
-// one warp per new record: text = esc(k) 251 0 [esc(v) 251 2] 0(separator); dist; recid
+// one CTA per new record: text = esc(k) 251 0 [esc(v) 251 2] 0(separator); dist; recid
 __global__ void __launch_bounds__(256)
 k_write_docs(uint32_t n_new, uint32_t batch_first, uint32_t win_first, const uint8_t *__restrict__ keys,
              const int64_t *__restrict__ koff, const uint8_t *__restrict__ vals, const int64_t *__restrict__ voff,
              const uint32_t *__restrict__ rec_start, uint8_t *__restrict__ text, uint16_t *__restrict__ dist,
              uint16_t *__restrict__ recid) {
-    uint32_t w = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    __shared__ uint32_t sm[33];
+    const uint32_t w = blockIdx.x;
     if (w >= n_new) return;
-    const int lane = lane_id();
     const uint32_t src = batch_first + w, idx = win_first + w;
     const uint32_t base = rec_start[idx], len = rec_start[idx + 1] - base - 1;
-    uint32_t dst = write_escaped(keys, koff[src], koff[src + 1], text, base);
-    if (lane == 0) {
+    uint32_t dst = block_write_escaped(keys, koff[src], koff[src + 1], text, base, sm);
+    if (threadIdx.x == 0) {
         text[dst] = 251;
         text[dst + 1] = 0;
     }
     dst += 2;
     int64_t v0 = voff[src], v1 = voff[src + 1];
     if (v1 > v0) {
-        dst = write_escaped(vals, v0, v1, text, dst);
-        if (lane == 0) {
+        dst = block_write_escaped(vals, v0, v1, text, dst, sm);
+        if (threadIdx.x == 0) {
             text[dst] = 251;
             text[dst + 1] = 2;
         }
         dst += 2;
     }
-    if (lane == 0) text[base + len] = 0;
-    for (uint32_t p = lane; p <= len; p += 32) {
+    if (threadIdx.x == 0) text[base + len] = 0;
+    for (uint32_t p = threadIdx.x; p <= len; p += 256) {
         dist[base + p] = (uint16_t) (len - p);
         recid[base + p] = (uint16_t) idx;
     }
@@ -557,8 +571,6 @@ static void build_suffix_array(Store &S, uint32_t N) {
     E.gk.reserve_discard(N);
     E.sa.reserve_discard(N);
     E.rank.reserve_discard(N + 8);
-    E.scan_tmp.reserve_discard(scan_tmp_elems(N));
-    E.scan_tmp64.reserve_discard(scan_tmp_elems(N));
     E.counters.reserve_discard(16);
     PX_CUDA(cudaMemsetAsync(E.counters.p, 0, 16 * sizeof(uint32_t), st));
     int L = 0;
@@ -594,8 +606,8 @@ static void build_suffix_array(Store &S, uint32_t N) {
                     sa[sl ? sl[a] : (uint32_t) a] = v;
                     rank[v] = sl ? sl[hp] : hp;
                 },
-                OpMax(), 0u, false, E.scan_tmp.p, st);
-            L += 3;
+                OpMax(), 0u, false, E.scanws, st);
+            L += 1;
         }
         // (2) keep the elements of groups larger than one; number the surviving groups
         {
@@ -625,11 +637,11 @@ static void build_suffix_array(Store &S, uint32_t N) {
                         d_cnt[1] = g + ((act && hd) ? 1u : 0u);
                     }
                 },
-                OpSum(), 0ull, true, E.scan_tmp64.p, st);
-            L += 3;
+                OpSum(), 0ull, true, E.scanws, st);
+            L += 1;
             svals = vals_out;  // compacted values (unsorted for the next key) live here now
         }
-        S.prof.end(st, 60.0 * A, 6);
+        S.prof.end(st, 44.0 * A, 2);
         uint32_t h_cnt[3];
         PX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         PX_CUDA(cudaStreamSynchronize(st));
@@ -663,14 +675,35 @@ static void build_suffix_array(Store &S, uint32_t N) {
 // trigger `nth >= 2048` (PiXiuCtrl.cpp:13).  Commits pool_nth/pool_used for the accepted ones.
 uint32_t Store::count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32_t s0, uint32_t N) {
     EncodeScratch &E = es;
+    (void) T;
     const uint32_t M = N - s0;
-    const size_t words = (size_t) div_up<uint32_t>(M, 256) * 8;  // written by k_lpf<true>
+    const size_t words = (size_t) div_up<uint32_t>(M, 256) * 8;  // masks written by k_lpf<true>
     auto t_a = std::chrono::steady_clock::now();
-    std::vector<uint32_t> lm(words), sm(words);
-    PX_CUDA(cudaMemcpyAsync(lm.data(), E.leafmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaMemcpyAsync(sm.data(), E.splitmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    // blocks per 32-position word (8 per leaf + 8 per split), exclusive prefix: the host then finds every
+    // pool boundary by binary search instead of walking all words
+    E.wordpre.reserve_discard(words + 1);
+    {
+        const uint32_t *lmk = E.leafmask.p, *smk = E.splitmask.p;
+        uint32_t *wp = E.wordpre.p;
+        device_scan<uint32_t>(
+            words + 1,
+            [=] __device__(size_t w) -> uint32_t {
+                if (w >= words) return 0u;
+                uint32_t l = lmk[w];
+                return 8u * (uint32_t) (__popc(l) + __popc(smk[w] & l));
+            },
+            [=] __device__(size_t w, uint32_t v) { wp[w] = v; }, OpSum(), 0u, true, E.scanws, st);
+        launches++;
+    }
+    E.h_leafmask.reserve_discard(words);
+    E.h_splitmask.reserve_discard(words);
+    E.h_wordpre.reserve_discard(words + 1);
+    PX_CUDA(cudaMemcpyAsync(E.h_leafmask.p, E.leafmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(E.h_splitmask.p, E.splitmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(E.h_wordpre.p, E.wordpre.p, (words + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
     auto t_b = std::chrono::steady_clock::now();
+    const uint32_t *lm = E.h_leafmask.p, *sm = E.h_splitmask.p, *wp = E.h_wordpre.p;
     constexpr uint32_t C = 65535;  // POOL_BLOCK_NUM (MemPool.h:6)
     uint32_t nth = pool_nth, used = pool_used;
     auto alloc = [&](uint32_t blocks) {
@@ -680,36 +713,62 @@ uint32_t Store::count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32
         }
         used += blocks;
     };
+    // blocks of the events at bit positions [0, k)
+    auto P = [&](uint32_t k) -> uint64_t {
+        uint32_t w = k >> 5, b = k & 31;
+        uint64_t v = wp[w];
+        if (b) {
+            uint32_t mask = (1u << b) - 1, l = lm[w] & mask;
+            v += 8u * (uint32_t) (__builtin_popcount(l) + __builtin_popcount(sm[w] & l));
+        }
+        return v;
+    };
+    // allocation by allocation over bits [k, k1) of one word: leaf 5,3 / leaf+split 5,5,3,3 (SuffixTree.cpp:193-231)
+    auto walk_bits = [&](uint32_t k, uint32_t k1) {
+        uint32_t w = k >> 5, b0 = k & 31, b1 = b0 + (k1 - k);
+        uint32_t mask = (b1 >= 32 ? 0xFFFFFFFFu : ((1u << b1) - 1)) & ~((1u << b0) - 1);
+        uint32_t ml = lm[w] & mask, ms = sm[w] & ml;
+        while (ml) {
+            uint32_t bit = ml & (0u - ml);
+            if (ms & bit) {
+                alloc(5);
+                alloc(5);
+                alloc(3);
+                alloc(3);
+            } else {
+                alloc(5);
+                alloc(3);
+            }
+            ml ^= bit;
+        }
+    };
     uint32_t accepted = 0;
     uint64_t node_blocks = 0;
     for (uint32_t r = first_new; r < win_R; r++) {
         if (r > first_new && nth >= 2048) break;  // PiXiuCtrl.cpp:13: checked before inserting record r
-        uint32_t ka = h_win_rec_start[r] - s0, kb = h_win_rec_start[r + 1] - 1 - s0;  // bit range of the record
-        for (uint32_t k = ka; k < kb;) {
-            uint32_t w = k >> 5, b0 = k & 31;
-            uint32_t b1 = std::min<uint32_t>(32, b0 + (kb - k));
-            uint32_t mask = (b1 == 32 ? 0xFFFFFFFFu : ((1u << b1) - 1)) & ~((1u << b0) - 1);
-            uint32_t ml = lm[w] & mask, ms = sm[w] & ml;
-            uint32_t blocks = 8u * (uint32_t) (__builtin_popcount(ml) + __builtin_popcount(ms));
-            node_blocks += blocks;
-            if (blocks <= C - used) {
-                used += blocks;  // everything fits in the current pool: no tail waste possible
-            } else {
-                while (ml) {  // allocation by allocation: leaf 5,3 / leaf+split 5,5,3,3 (SuffixTree.cpp:193-231)
-                    uint32_t bit = ml & (0u - ml);
-                    if (ms & bit) {
-                        alloc(5);
-                        alloc(5);
-                        alloc(3);
-                        alloc(3);
-                    } else {
-                        alloc(5);
-                        alloc(3);
-                    }
-                    ml ^= bit;
-                }
+        uint32_t k = h_win_rec_start[r] - s0;
+        const uint32_t kb = h_win_rec_start[r + 1] - 1 - s0;  // bit range [k, kb) of the record
+        const uint64_t Pend = P(kb);
+        node_blocks += Pend - P(k);
+        while (k < kb) {
+            uint64_t Pk = P(k);
+            if (Pend - Pk <= C - used) {  // the rest of the record fits the current pool: no tail waste possible
+                used += (uint32_t) (Pend - Pk);
+                break;
             }
-            k += b1 - b0;
+            // first word whose end exceeds the room left: everything before it fits as a whole
+            uint64_t limit = Pk + (C - used);
+            uint32_t lo = k >> 5, hi = (kb - 1) >> 5;  // find the smallest w in [lo, hi] with blocks up to end of w > limit
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                uint32_t wend = std::min<uint32_t>((mid + 1) << 5, kb);
+                if (P(wend) > limit) hi = mid;
+                else lo = mid + 1;
+            }
+            uint32_t wstart = std::max<uint32_t>(lo << 5, k), wend = std::min<uint32_t>((lo + 1) << 5, kb);
+            used += (uint32_t) (P(wstart) - Pk);
+            walk_bits(wstart, wend);
+            k = wend;
         }
         accepted++;
         pool_nth = nth;
@@ -824,8 +883,8 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
             [=] __device__(size_t k) -> uint32_t {
                 return text[s0 + k] != 251 ? (uint32_t) (s0 + k) + 1u : (k == 0 ? s0 : 0u);
             },
-            [=] __device__(size_t k, uint32_t v) { ln[s0 + k] = v - 1u; }, OpMax(), 0u, false, E.scan_tmp.p, st);
-        L += 3;
+            [=] __device__(size_t k, uint32_t v) { ln[s0 + k] = v - 1u; }, OpMax(), 0u, false, E.scanws, st);
+        L += 1;
     }
     k_pair_rule<<<gridM, 256, 0, st>>>(w_text.p, w_dist.p, E.flagp.p, E.lastnon.p, s0, N, E.flagc.p);
     L++;
@@ -835,13 +894,13 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
         // prevp[i] = 1 + index of the last non-COMPRESS position at or before i  (run start if i is COMPRESS)
         device_scan<uint32_t>(
             M, [=] __device__(size_t k) -> uint32_t { return fc[s0 + k] ? (k == 0 ? s0 : 0u) : (uint32_t) (s0 + k) + 1u; },
-            [=] __device__(size_t k, uint32_t v) { pp[s0 + k] = v; }, OpMax(), 0u, false, E.scan_tmp.p, st);
+            [=] __device__(size_t k, uint32_t v) { pp[s0 + k] = v; }, OpMax(), 0u, false, E.scanws, st);
         // nextp[i] = index of the first non-COMPRESS position at or after i (suffix min-scan, reversed index)
         const uint32_t last = N - 1;
         device_scan<uint32_t>(
             M, [=] __device__(size_t k) -> uint32_t { return fc[last - k] ? 0xFFFFFFFFu : (uint32_t) (last - k); },
-            [=] __device__(size_t k, uint32_t v) { np[last - k] = v; }, OpMin(), 0xFFFFFFFFu, false, E.scan_tmp.p, st);
-        L += 6;
+            [=] __device__(size_t k, uint32_t v) { np[last - k] = v; }, OpMin(), 0xFFFFFFFFu, false, E.scanws, st);
+        L += 2;
     }
     {
         const uint8_t *fc = E.flagc.p;
@@ -853,10 +912,10 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
         device_scan<uint32_t>(
             (size_t) M + 1,
             [=] __device__(size_t k) -> uint32_t { return k < M ? contrib_at(s0 + (uint32_t) k, fc, dist, pp, np, strict) : 0u; },
-            [=] __device__(size_t k, uint32_t v) { off[s0 + k] = v; }, OpSum(), 0u, true, E.scan_tmp.p, st);
-        L += 3;
+            [=] __device__(size_t k, uint32_t v) { off[s0 + k] = v; }, OpSum(), 0u, true, E.scanws, st);
+        L += 1;
     }
-    prof.end(st, 60.0 * M, 14);
+    prof.end(st, 45.0 * M, 6);
     uint32_t enc_total = 0;
     PX_CUDA(cudaMemcpyAsync(&enc_total, E.off.p + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
@@ -899,9 +958,11 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
     PX_CUDA(cudaMemcpyAsync(h_enc_off.data() + old, d_enc_off.p + old, n_new * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaMemcpyAsync(h_enc_len.data() + old, d_enc_len.p + old, n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaMemcpyAsync(h_dec_len.data() + old, d_dec_len.p + old, n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    uint32_t errflag = 0;
+    uint32_t errflag = 0, scanerr = 0;
     PX_CUDA(cudaMemcpyAsync(&errflag, E.counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(&scanerr, E.scanws.ctl.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
+    if (scanerr) throw std::runtime_error("encode: scan look-back timed out");
     if (errflag) throw std::runtime_error("encode: internal inconsistency (err=" + std::to_string(errflag) + ")");
     enc_bytes += enc_total;
     n_tiles += new_tiles;
@@ -916,6 +977,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     if (n == 0) return PIXIU_OK;
     if (n > 0x7fffffff) return PIXIU_EINVAL;
     const uint32_t nn = (uint32_t) n;
+    const auto t_begin = std::chrono::steady_clock::now();
     PX_CUDA(cudaEventRecord(ev0, st));
     doc_len.reserve_discard(nn);
     prof.begin(PC_DOCS, st);
@@ -975,7 +1037,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         w_rec_start.reserve_discard(rs.size() + 1);
         PX_CUDA(cudaMemcpyAsync(w_rec_start.p, rs.data(), rs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         prof.begin(PC_DOCS, st);
-        k_write_docs<<<(unsigned) div_up<uint64_t>((uint64_t) n_new * 32u, 256), 256, 0, st>>>(n_new, a, first_new, d_keys, d_koff, d_vals, d_voff,
+        k_write_docs<<<n_new, 256, 0, st>>>(n_new, a, first_new, d_keys, d_koff, d_vals, d_voff,
                                                                          w_rec_start.p, w_text.p, w_dist.p, w_recid.p);
         prof.end(st, 7.0 * (newN - win_N), 1);
         launches++;
@@ -985,6 +1047,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         a += acc;
         if (acc < n_new) close_window();  // the arena budget was reached inside the candidates: rotate
     }
+    const auto t_gpu_done = std::chrono::steady_clock::now();
     PX_CUDA(cudaEventRecord(ev1, st));
     // ---- index maintenance (host CritBit; in-order semantics of n sequential setitem calls) ----
     std::vector<uint8_t> q;
@@ -1009,6 +1072,12 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     last_set_ms = ms;
     prof.collect();
+    if (getenv("PIXIU_TRACE")) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[setitem] n=%u encode(wall)=%.3f ms index=%.3f ms gpu(events)=%.3f ms\n", nn,
+                std::chrono::duration<double, std::milli>(t_gpu_done - t_begin).count(),
+                std::chrono::duration<double, std::milli>(t_end - t_gpu_done).count(), ms);
+    }
     return PIXIU_OK;
 }
 

@@ -407,16 +407,15 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     PX_CUDA(cudaEventRecord(S.ev0, st));
     S.prof.begin(PC_LOOKUP, st);
     S.doc_len.reserve_discard(nn + 1);
-    DevBuf<uint64_t> &qoff = S.es.scan_tmp64;  // reuse: needs nn+1 + scan temp
-    size_t need = (size_t) nn + 2 + scan_tmp_elems(nn + 1);
-    qoff.reserve_discard(need);
-    uint64_t *d_qoff = qoff.p, *d_tmp = qoff.p + nn + 2;
+    DevBuf<uint64_t> &qoff = S.es.qoff;
+    qoff.reserve_discard((size_t) nn + 2);
+    uint64_t *d_qoff = qoff.p;
     k_query_len<<<div_up<uint32_t>(nn, 256), 256, 0, st>>>(nn, S.in_keys.p, S.in_koff.p, S.doc_len.p);
     {
         const uint32_t *ql = S.doc_len.p;
         device_scan<uint64_t>(
             (size_t) nn + 1, [=] __device__(size_t i) -> uint64_t { return i < nn ? (uint64_t) ql[i] : 0ull; },
-            [=] __device__(size_t i, uint64_t v) { d_qoff[i] = v; }, OpSum(), 0ull, true, d_tmp, st);
+            [=] __device__(size_t i, uint64_t v) { d_qoff[i] = v; }, OpSum(), 0ull, true, S.es.scanws, st);
     }
     uint64_t qbytes = 0;
     PX_CUDA(cudaMemcpyAsync(&qbytes, d_qoff + nn, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -427,8 +426,8 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     ChaseView V{S.d_enc.p, S.d_enc_off.p, S.d_enc_len.p, S.d_dec_len.p, S.d_first.p, S.d_tile_base.p, S.d_tile_desc.p};
     k_lookup<<<div_up<uint32_t>(nn, 128), 128, 0, st>>>(nn, T, V, S.in_vals.p, d_qoff, S.doc_len.p, S.doc_off.p);
     PX_LAUNCH_CHECK();
-    S.prof.end(st, 0.0, 6);
-    S.launches += 6;
+    S.prof.end(st, 0.0, 4);
+    S.launches += 4;
     PX_CUDA(cudaEventRecord(S.ev1, st));
     PX_CUDA(cudaMemcpyAsync(rec_out.data(), S.doc_off.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));

@@ -25,6 +25,7 @@ constexpr uint32_t RS_FLAG_AGG = 1u << 30;
 constexpr uint32_t RS_FLAG_PREFIX = 2u << 30;
 constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
 constexpr uint32_t RS_SPIN_LIMIT = 1u << 27;
+constexpr int RS_LOOK = 8;
 
 // hist[pass][bin] += count, for passes [0, npass) covering bits [begin_bit + 8*pass, ..)
 template <typename KeyT>
@@ -61,13 +62,20 @@ static __global__ void __launch_bounds__(RS_BINS) k_rs_scan_bins(uint32_t *hist)
 
 // One onesweep pass.  status: [tiles][256] zero-initialised; ticket: zero-initialised counter.
 // vals_in == nullptr means "value = input index" (first pass of an index sort).
+// Dynamic shared memory: RS_TILE keys + RS_TILE values (the tile is re-ordered by digit in shared
+// memory so that the global stores of one digit are consecutive: coalesced 128-byte runs on average).
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 3)
 k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const uint32_t *__restrict__ vals_in,
               uint32_t *__restrict__ vals_out, uint32_t n, int shift, const uint32_t *__restrict__ bin_base,
               uint32_t *__restrict__ status, uint32_t *__restrict__ ticket, uint32_t *__restrict__ err) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    KeyT *keys_s = reinterpret_cast<KeyT *>(rs_smem);
+    uint32_t *vals_s = reinterpret_cast<uint32_t *>(rs_smem + sizeof(KeyT) * RS_TILE);
     __shared__ uint32_t warp_hist[RS_WARPS][RS_BINS];  // per-warp digit counts, then exclusive warp prefixes
-    __shared__ uint32_t tile_off[RS_BINS];             // global offset of this tile's first key per digit
+    __shared__ uint32_t digit_start[RS_BINS];          // first tile-local slot of each digit
+    __shared__ uint32_t adj[RS_BINS];                  // global position of slot j of digit d = adj[d] + j
+    __shared__ uint32_t warp_tot[RS_WARPS];
     __shared__ uint32_t s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
@@ -76,6 +84,7 @@ k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1;
     const uint32_t wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
+    const uint32_t tile_count = min((uint32_t) RS_TILE, n - tile * RS_TILE);
 
     KeyT key[RS_ITEMS];
     uint16_t off[RS_ITEMS];
@@ -99,7 +108,7 @@ k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, con
         off[k] = (uint16_t) (c + __popc(m & lt_mask));
     }
     __syncthreads();
-    // digit `t`: exclusive prefix over the warps, tile total, decoupled look-back
+    // digit `t`: exclusive prefix over the warps, tile total, tile-local digit start, decoupled look-back
     {
         const int t = threadIdx.x;
         uint32_t run = 0;
@@ -109,47 +118,80 @@ k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, con
             warp_hist[w][t] = run;
             run += c;
         }
-        volatile uint32_t *st = status;
+        // exclusive scan of `run` over the 256 digits
+        uint32_t inc = run;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
+            if (lane >= dd) inc += o;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        uint32_t wpre = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) wpre += (w < warp) ? warp_tot[w] : 0u;
+        const uint32_t dstart = wpre + inc - run;
+        digit_start[t] = dstart;
+
         uint32_t *mine = status + (size_t) tile * RS_BINS + t;
+        uint32_t excl = 0;
         if (tile == 0) {
-            st_release_u32(mine, RS_FLAG_PREFIX | run);
-            tile_off[t] = bin_base[t];
+            st_relaxed_u32(mine, RS_FLAG_PREFIX | run);
         } else {
-            st_release_u32(mine, RS_FLAG_AGG | run);
-            uint32_t excl = 0;
+            st_relaxed_u32(mine, RS_FLAG_AGG | run);
+            // look back RS_LOOK predecessors at a time (independent relaxed loads overlap): the first wave
+            // of tiles runs in lock step and would otherwise walk hundreds of rows one round trip each
             int64_t look = (int64_t) tile - 1;
             uint32_t spins = 0;
-            while (look >= 0) {
-                uint32_t s = ld_acquire_u32(status + (size_t) look * RS_BINS + t);
-                uint32_t flag = s & ~RS_VALUE_MASK;
-                if (flag == 0) {
-                    if (++spins > RS_SPIN_LIMIT) {
-                        atomicExch(err, 1u);
-                        break;
-                    }
-                    continue;
+            bool done = false;
+            while (!done && look >= 0) {
+                uint32_t sv[RS_LOOK];
+#pragma unroll
+                for (int b = 0; b < RS_LOOK; b++)
+                    sv[b] = look - b >= 0 ? ld_relaxed_u32(status + (size_t) (look - b) * RS_BINS + t) : RS_FLAG_PREFIX;
+                int used = 0;
+#pragma unroll
+                for (int b = 0; b < RS_LOOK; b++) {
+                    if (done || used != b) continue;
+                    uint32_t flag = sv[b] & ~RS_VALUE_MASK;
+                    if (flag == 0) continue;  // not published yet: retry from here
+                    excl += sv[b] & RS_VALUE_MASK;
+                    used = b + 1;
+                    if (flag == RS_FLAG_PREFIX) done = true;
                 }
-                excl += s & RS_VALUE_MASK;
-                if (flag == RS_FLAG_PREFIX) break;
-                look--;
+                look -= used;
+                if (used == 0 && ++spins > RS_SPIN_LIMIT) {
+                    atomicExch(err, 1u);
+                    break;
+                }
             }
-            st_release_u32(mine, RS_FLAG_PREFIX | (excl + run));
-            tile_off[t] = bin_base[t] + excl;
+            st_relaxed_u32(mine, RS_FLAG_PREFIX | (excl + run));
         }
-        (void) st;
+        adj[t] = bin_base[t] + excl - dstart;
     }
     __syncthreads();
+    // re-order the tile by digit in shared memory
 #pragma unroll
     for (int k = 0; k < RS_ITEMS; k++) {
         uint32_t i = wbase + k * 32 + lane;
         if (i < n) {
             uint32_t d = (uint32_t) ((key[k] >> shift) & 0xff);
-            uint32_t pos = tile_off[d] + warp_hist[warp][d] + off[k];
-            keys_out[pos] = key[k];
-            vals_out[pos] = vals_in ? vals_in[i] : i;
+            uint32_t lp = digit_start[d] + warp_hist[warp][d] + off[k];
+            keys_s[lp] = key[k];
+            vals_s[lp] = vals_in ? vals_in[i] : i;
         }
     }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < tile_count; j += RS_THREADS) {
+        KeyT kk = keys_s[j];
+        uint32_t pos = adj[(uint32_t) ((kk >> shift) & 0xff)] + j;
+        keys_out[pos] = kk;
+        vals_out[pos] = vals_s[j];
+    }
 }
+
+template <typename KeyT>
+constexpr size_t rs_dyn_smem() { return (sizeof(KeyT) + sizeof(uint32_t)) * RS_TILE; }
 
 struct RadixSortTemp {
     DevBuf<uint32_t> hist;     // [RS_MAX_PASSES][256]
@@ -180,12 +222,17 @@ int radix_sort_pairs(KeyT *k0, KeyT *k1, uint32_t *v0, uint32_t *v1, uint32_t n,
     k_rs_histogram<KeyT><<<hgrid, RS_THREADS, 0, st>>>(k0, n, begin_bit, npass, tmp.hist.p);
     k_rs_scan_bins<<<npass, RS_BINS, 0, st>>>(tmp.hist.p);
     if (prof) prof->end(st, (double) n * sizeof(KeyT), 2);
+    static bool attr_done = false;  // (one instantiation per KeyT; the attribute is per function)
+    if (!attr_done) {
+        PX_CUDA(cudaFuncSetAttribute(k_rs_onesweep<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rs_dyn_smem<KeyT>()));
+        attr_done = true;
+    }
     int cur = 0;
     for (int p = 0; p < npass; p++) {
         KeyT *ki = cur ? k1 : k0, *ko = cur ? k0 : k1;
         uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
         if (prof) prof->begin(PC_SORT_PASS, st);
-        k_rs_onesweep<KeyT><<<tiles, RS_THREADS, 0, st>>>(ki, ko, (p == 0 && iota) ? nullptr : vi, vo, n,
+        k_rs_onesweep<KeyT><<<tiles, RS_THREADS, rs_dyn_smem<KeyT>(), st>>>(ki, ko, (p == 0 && iota) ? nullptr : vi, vo, n,
                                                           begin_bit + 8 * p, tmp.hist.p + p * RS_BINS,
                                                           tmp.status.p + (size_t) p * tiles * RS_BINS,
                                                           tmp.ticket.p + p, d_err);

@@ -1,9 +1,10 @@
-// Device-wide scans (sum / max / min) with fused input and output transforms.
+// Device-wide scans (sum / max / min) with fused input and output transforms — ONE launch.
 //
-// Three launches (tile reduce -> scan of tile partials -> tile down-sweep), tiles of
-// 256 threads x 8 items.  Input and output are functors so the callers fuse flag
-// tests, index reversal (for suffix scans) and scattering into the scan itself.
-// HBM traffic: input read twice, output written once.
+// Single-pass "decoupled look-back": CTAs take tiles of 256 threads x 8 items by ticket, publish
+// their tile aggregate in a 64-bit status word (2 flag bits + value), and warp 0 resolves the
+// exclusive prefix by looking back over up to 32 predecessor tiles at a time.  Input and output are
+// functors, so callers fuse flag tests, index reversal (suffix scans) and scatters into the scan.
+// HBM traffic: input read once, output written once.  Values must fit 62 bits.
 #pragma once
 #include "common.cuh"
 
@@ -12,6 +13,20 @@ namespace pixiu {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned long long SCAN_FLAG_AGG = 1ull << 62;
+constexpr unsigned long long SCAN_FLAG_PREFIX = 2ull << 62;
+constexpr unsigned long long SCAN_VALUE_MASK = (1ull << 62) - 1;
+constexpr uint32_t SCAN_SPIN_LIMIT = 1u << 27;
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 template <typename T, typename Op>
 __device__ __forceinline__ T warp_scan_inclusive(T v, Op op) {
@@ -45,39 +60,17 @@ __device__ __forceinline__ T block_scan_exclusive(T v, Op op, T identity, T *sme
     return op(warp_prefix, exc);
 }
 
-template <typename T, typename Op, typename InFn>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(size_t n, InFn in, Op op, T identity, T *partials) {
-    __shared__ T sm[33];
-    size_t base = (size_t) blockIdx.x * SCAN_TILE + (size_t) threadIdx.x * SCAN_ITEMS;
-    T acc = identity;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++)
-        if (base + k < n) acc = op(acc, in(base + k));
-    T total;
-    block_scan_exclusive(acc, op, identity, sm, &total);
-    if (threadIdx.x == 0) partials[blockIdx.x] = total;
-}
-
-template <typename T, typename Op>
-__global__ void __launch_bounds__(1024) k_scan_partials(size_t m, Op op, T identity, T *partials) {
-    __shared__ T sm[33];
-    T carry = identity;
-    for (size_t base = 0; base < m; base += 1024) {
-        size_t i = base + threadIdx.x;
-        T v = i < m ? partials[i] : identity;
-        T total;
-        T exc = block_scan_exclusive(v, op, identity, sm, &total);
-        if (i < m) partials[i] = op(carry, exc);
-        carry = op(carry, total);
-        __syncthreads();
-    }
-}
-
 template <typename T, typename Op, typename InFn, typename OutFn>
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_down(size_t n, InFn in, OutFn out, Op op, T identity, const T *partials, int exclusive) {
+k_scan_lookback(size_t n, InFn in, OutFn out, Op op, T identity, int exclusive, unsigned long long *__restrict__ status,
+                uint32_t *__restrict__ ticket, uint32_t *__restrict__ err) {
     __shared__ T sm[33];
-    size_t base = (size_t) blockIdx.x * SCAN_TILE + (size_t) threadIdx.x * SCAN_ITEMS;
+    __shared__ T s_prefix;
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const size_t base = (size_t) tile * SCAN_TILE + (size_t) threadIdx.x * SCAN_ITEMS;
     T v[SCAN_ITEMS];
     T acc = identity;
 #pragma unroll
@@ -87,7 +80,42 @@ k_scan_down(size_t n, InFn in, OutFn out, Op op, T identity, const T *partials, 
     }
     T total;
     T pre = block_scan_exclusive(acc, op, identity, sm, &total);
-    pre = op(partials[blockIdx.x], pre);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        T excl = identity;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed_u64(status, SCAN_FLAG_PREFIX | (unsigned long long) total);
+        } else {
+            if (lane == 0) st_relaxed_u64(status + tile, SCAN_FLAG_AGG | (unsigned long long) total);
+            int64_t look = (int64_t) tile - 1 - lane;
+            while (true) {
+                unsigned long long sv = SCAN_FLAG_PREFIX | (unsigned long long) identity;  // before tile 0
+                if (look >= 0) {
+                    uint32_t spins = 0;
+                    while (((sv = ld_relaxed_u64(status + look)) >> 62) == 0) {
+                        if (++spins > SCAN_SPIN_LIMIT) {
+                            atomicExch(err, 1u);
+                            sv = SCAN_FLAG_PREFIX | (unsigned long long) identity;
+                            break;
+                        }
+                    }
+                }
+                const bool is_prefix = (sv >> 62) == 2;
+                const uint32_t pm = __ballot_sync(0xffffffffu, is_prefix);
+                const int first = pm ? __ffs(pm) - 1 : 31;
+                T contrib = lane <= first ? (T) (sv & SCAN_VALUE_MASK) : identity;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) contrib = op(contrib, (T) __shfl_xor_sync(0xffffffffu, contrib, d));
+                excl = op(contrib, excl);
+                if (pm) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(status + tile, SCAN_FLAG_PREFIX | (unsigned long long) op(excl, total));
+        }
+        if (lane == 0) s_prefix = excl;
+    }
+    __syncthreads();
+    pre = op(s_prefix, pre);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         T inc = op(pre, v[k]);
@@ -95,31 +123,43 @@ k_scan_down(size_t n, InFn in, OutFn out, Op op, T identity, const T *partials, 
         pre = inc;
     }
 }
+#endif  // __CUDACC__
 
 struct OpSum {
     template <typename T>
-    __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
+    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
 };
 struct OpMax {
     template <typename T>
-    __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; }
+    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; }
 };
 struct OpMin {
     template <typename T>
-    __device__ __forceinline__ T operator()(T a, T b) const { return a < b ? a : b; }
+    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a < b ? a : b; }
 };
 
-// tmp must hold div_up(n, SCAN_TILE) elements of T
+// workspace shared by all scans of a store (status words + ticket + sticky error flag)
+struct ScanWorkspace {
+    DevBuf<unsigned long long> status;
+    DevBuf<uint32_t> ctl;  // [0] ticket, [1] error
+};
+
+#ifdef __CUDACC__
 template <typename T, typename Op, typename InFn, typename OutFn>
-void device_scan(size_t n, InFn in, OutFn out, Op op, T identity, bool exclusive, T *tmp, cudaStream_t st) {
+void device_scan(size_t n, InFn in, OutFn out, Op op, T identity, bool exclusive, ScanWorkspace &ws, cudaStream_t st) {
     if (n == 0) return;
     unsigned tiles = (unsigned) div_up<size_t>(n, SCAN_TILE);
-    k_scan_reduce<T><<<tiles, SCAN_THREADS, 0, st>>>(n, in, op, identity, tmp);
-    k_scan_partials<T><<<1, 1024, 0, st>>>((size_t) tiles, op, identity, tmp);
-    k_scan_down<T><<<tiles, SCAN_THREADS, 0, st>>>(n, in, out, op, identity, tmp, exclusive ? 1 : 0);
+    ws.status.reserve_discard(tiles + 1);
+    if (!ws.ctl.p) {
+        ws.ctl.reserve_discard(4);
+        PX_CUDA(cudaMemsetAsync(ws.ctl.p, 0, 4 * sizeof(uint32_t), st));
+    }
+    PX_CUDA(cudaMemsetAsync(ws.status.p, 0, (size_t) tiles * sizeof(unsigned long long), st));
+    PX_CUDA(cudaMemsetAsync(ws.ctl.p, 0, sizeof(uint32_t), st));
+    k_scan_lookback<T><<<tiles, SCAN_THREADS, 0, st>>>(n, in, out, op, identity, exclusive ? 1 : 0, ws.status.p, ws.ctl.p,
+                                                      ws.ctl.p + 1);
     PX_LAUNCH_CHECK();
 }
-
-inline size_t scan_tmp_elems(size_t n) { return div_up<size_t>(n, SCAN_TILE) + 1; }
+#endif
 
 }  // namespace pixiu

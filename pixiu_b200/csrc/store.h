@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "prof.h"
 #include "radix_sort.cuh"
+#include "scan.cuh"
 
 namespace pixiu {
 
@@ -44,11 +45,13 @@ class HostIndex;  // CritBit (index.cu)
 
 struct EncodeScratch {
     DevBuf<uint64_t> keys0, keys1;
-    DevBuf<uint32_t> vals0, vals1, slot0, slot1, gk, sa, rank, lcp, reach, lastnon, prevp, nextp, off, scan_tmp;
-    DevBuf<uint64_t> scan_tmp64;
+    DevBuf<uint32_t> vals0, vals1, slot0, slot1, gk, sa, rank, lcp, reach, lastnon, prevp, nextp, off;
+    DevBuf<uint64_t> qoff;
+    ScanWorkspace scanws;
     DevBuf<uint32_t> tree_a, tree_l;
     DevBuf<uint8_t> flagp, flagc;
-    DevBuf<uint32_t> leafmask, splitmask;
+    DevBuf<uint32_t> leafmask, splitmask, wordpre;
+    PinnedBuf<uint32_t> h_leafmask, h_splitmask, h_wordpre;
     DevBuf<uint32_t> counters;  // [0] active count, [1] group count, [2] error flag, [3..] misc
     RadixSortTemp rs;
 };

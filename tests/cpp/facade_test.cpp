@@ -76,12 +76,14 @@ int main() {
             }
         }
     }
-    // prefix iteration order == std::map order (PiXiuCtrl.cpp:228-255)
+    // prefix iteration (PiXiuCtrl.cpp:228-255): the order is byte-lexicographic on esc(key) 251 0, i.e. a key
+    // sorts AFTER the keys it is a prefix of (251 > 'A'); the reference's own test sorts before comparing
     for (std::string prefix : {std::string(""), std::string("A"), std::string("CD"), std::string("EEEEEE")}) {
         std::vector<std::string> want;
         for (auto &kv : model)
             if (kv.first.compare(0, prefix.size(), prefix) == 0)
                 want.push_back(kv.first + "\xfb" + std::string(1, '\0') + kv.second + "\xfb\x02");
+        std::sort(want.begin(), want.end());  // std::string compares as unsigned bytes
         std::vector<std::string> got;
         CBTGen *it = ctrl.iter((uint8_t *) prefix.data(), (int) prefix.size());
         if (it) {
