@@ -115,6 +115,20 @@ int64_t pixiu_import_chunk(pixiu_store *s, int64_t n, const uint8_t *enc, const 
 /* Decode every record of one chunk (tombstoned included) in idx order. */
 int pixiu_decode_chunk(pixiu_store *s, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *need);
 
+/* ---- multi-GPU extended window (one store per GPU / rank) ----
+ * The open window is sharded by record over `world` stores (record idx -> rank idx % world); a batch is
+ * given to every rank.  setitem is split in three phases around the two collectives the caller issues
+ * (torch.distributed / NCCL all_reduce on the returned DEVICE buffers, in place):
+ *     begin -> d_m[count]    uint32 longest earlier match per batch position   -> all_reduce(MAX)
+ *     mid   -> d_cand[count] uint32 (idx << 16 | to) leftmost source per run   -> all_reduce(MIN)
+ *     end   -> every rank stores the identical encoded batch (compressed store and index are replicated)
+ * Requires PIXIU_ROTATE_BYTES (window_bytes is per GPU) or PIXIU_ROTATE_RECORDS; a batch holds <= 65,535 records. */
+int pixiu_mg_config(pixiu_store *s, int rank, int world);
+int pixiu_mg_setitem_begin(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off, const uint8_t *vals,
+                           const int64_t *val_off, uint32_t **d_m, int64_t *count);
+int pixiu_mg_setitem_mid(pixiu_store *s, uint32_t **d_cand, int64_t *count);
+int pixiu_mg_setitem_end(pixiu_store *s, int32_t *rc, int32_t *saved);
+
 /* Per-kernel-class device timing (CUDA events on the store's stream), for the roofline report.
  * enable(1) resets the counters; get() returns 1 once cls is past the last class. `bytes` are the
  * ALGORITHMIC bytes of the launches (DESIGN.md states the per-unit figures). */

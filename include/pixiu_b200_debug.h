@@ -10,6 +10,8 @@ int pixiu_debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, int64_t n
 /* copy an internal array of the last encode of the open window (sa, rank, lcp, reach, off, prevp, nextp: u32;
  * text, flagp, flagc: u8; dist: u16); returns the window length */
 int64_t pixiu_debug_window_array(pixiu_store *s, const char *name, void *out, int64_t cap_bytes);
+/* cudaMemcpy for tests that play the collective of the multi-GPU mode: kind 1 = D2H, 2 = H2D */
+int pixiu_debug_memcpy(void *dst, const void *src, int64_t bytes, int kind);
 /* MemPool::nth / used_num the reference would show for the open window (PIXIU_ROTATE_REFERENCE only) */
 int pixiu_debug_pool_state(pixiu_store *s, int32_t *nth, int32_t *used);
 #ifdef __cplusplus

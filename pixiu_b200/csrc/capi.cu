@@ -360,6 +360,35 @@ int64_t pixiu_import_chunk(pixiu_store *h, int64_t n, const uint8_t *enc, const 
     return rc == PIXIU_OK ? chunk_id : rc;
 }
 
+int pixiu_mg_config(pixiu_store *h, int rank, int world) {
+    if (!h || world < 1 || rank < 0 || rank >= world || h->s.n_records() != 0) return PIXIU_EINVAL;
+    h->s.mg_rank = rank;
+    h->s.mg_world = world;
+    return PIXIU_OK;
+}
+
+int pixiu_mg_setitem_begin(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, const uint8_t *vals,
+                           const int64_t *val_off, uint32_t **d_m, int64_t *count) {
+    return guarded(h, [&](Store &S) -> int {
+        if (n <= 0 || !keys || !offsets_ok(n, key_off) || !offsets_ok(n, val_off) || !d_m || !count) return PIXIU_EINVAL;
+        if (val_off[n] > val_off[0] && !vals) return PIXIU_EINVAL;
+        stage(S, n, keys, key_off, S.in_keys, S.in_koff);
+        stage(S, n, vals, val_off, S.in_vals, S.in_voff);
+        return S.mg_begin(n, S.in_keys.p, S.in_koff.p, S.in_vals.p, S.in_voff.p, keys, key_off, val_off, d_m, count);
+    });
+}
+
+int pixiu_mg_setitem_mid(pixiu_store *h, uint32_t **d_cand, int64_t *count) {
+    return guarded(h, [&](Store &S) -> int {
+        if (!d_cand || !count) return PIXIU_EINVAL;
+        return S.mg_mid(d_cand, count);
+    });
+}
+
+int pixiu_mg_setitem_end(pixiu_store *h, int32_t *rc, int32_t *saved) {
+    return guarded(h, [&](Store &S) -> int { return S.mg_end(rc, saved); });
+}
+
 int pixiu_profile_enable(pixiu_store *h, int on) {
     if (!h) return PIXIU_EINVAL;
     h->s.prof.reset();
@@ -420,6 +449,12 @@ int pixiu_debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, int64_t n
         fprintf(stderr, "pixiu_debug_sort_pairs: %s\n", e.what());
         return PIXIU_ECUDA;
     }
+}
+
+// plain cudaMemcpy for tests that play the role of the collective: kind 1 = device->host, 2 = host->device
+int pixiu_debug_memcpy(void *dst, const void *src, int64_t bytes, int kind) {
+    cudaError_t e = cudaMemcpy(dst, src, (size_t) bytes, kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? PIXIU_OK : PIXIU_ECUDA;
 }
 
 // arena state the reference's suffix tree would have for the open window (MemPool::nth, used_num)

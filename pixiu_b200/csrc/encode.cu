@@ -87,11 +87,11 @@ __global__ void __launch_bounds__(256)
 k_write_docs(uint32_t n_new, uint32_t batch_first, uint32_t win_first, const uint8_t *__restrict__ keys,
              const int64_t *__restrict__ koff, const uint8_t *__restrict__ vals, const int64_t *__restrict__ voff,
              const uint32_t *__restrict__ rec_start, uint8_t *__restrict__ text, uint16_t *__restrict__ dist,
-             uint16_t *__restrict__ recid) {
+             uint16_t *__restrict__ recid, const uint32_t *__restrict__ src_list) {
     __shared__ uint32_t sm[33];
     const uint32_t w = blockIdx.x;
     if (w >= n_new) return;
-    const uint32_t src = batch_first + w, idx = win_first + w;
+    const uint32_t src = src_list ? src_list[w] : batch_first + w, idx = win_first + w;
     const uint32_t base = rec_start[idx], len = rec_start[idx + 1] - base - 1;
     uint32_t dst = block_write_escaped(keys, koff[src], koff[src + 1], text, base, sm);
     if (threadIdx.x == 0) {
@@ -434,23 +434,13 @@ __device__ __forceinline__ uint32_t contrib_at(uint32_t i, const uint8_t *flagc,
 // ---------------------------------------------------------------------------------
 // K8+K9: run-end pointer query and emission
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_emit(MinTree T, const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist,
-       const uint16_t *__restrict__ recid, const uint32_t *__restrict__ rec_start, const uint32_t *__restrict__ rank,
-       const uint32_t *__restrict__ reach, const uint8_t *__restrict__ flagc, const uint32_t *__restrict__ prevp,
-       const uint32_t *__restrict__ nextp, const uint32_t *__restrict__ off, uint32_t s0, uint32_t n, int strict251,
-       uint8_t *__restrict__ enc_out /* already offset so that off[] indexes it directly */, uint32_t *__restrict__ err) {
-    uint32_t i = s0 + blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    uint32_t c = contrib_at(i, flagc, dist, prevp, nextp, strict251);
-    if (c == 0) return;
-    uint32_t o = off[i];
-    if (c == 1) {
-        enc_out[o] = text[i];
-        return;
-    }
-    // long run ending at i.  s* = min{s in record : reach(s) > i}
-    uint32_t rl = nextp[i] - prevp[i];
+// (idx << 16 | to) of the reference's pointer for the long run ending at i (length rl), or 0xFFFFFFFF when the
+// window holds no earlier occurrence:  s* = min{s in record : reach(s) > i} by binary search (reach is
+// monotone), then the leftmost occurrence of D[s*..i] = minimum text position in its SA interval.
+__device__ __forceinline__ uint32_t run_pointer(const MinTree &T, const uint16_t *__restrict__ recid,
+                                                const uint32_t *__restrict__ rec_start, const uint32_t *__restrict__ rank,
+                                                const uint32_t *__restrict__ reach, const uint16_t *__restrict__ gidx,
+                                                uint32_t i, uint32_t rl) {
     uint32_t rec = recid[i];
     uint32_t lo = rec_start[rec], hi = i + 1;
     while (lo < hi) {
@@ -465,12 +455,61 @@ k_emit(MinTree T, const uint8_t *__restrict__ text, const uint16_t *__restrict__
     tree_search<true, true, false>(T, r + 1, E, accl, 0);
     tree_search<false, false, false>(T, r, E, accr, 0);
     uint32_t left = min(accl, accr);
-    if (left >= sstar || E < rl) {
-        atomicExch(err, 2u);
-        return;
-    }
+    if (left >= sstar || E < rl) return 0xFFFFFFFFu;
     uint32_t src = recid[left];
     uint32_t to = left + E - rec_start[src];
+    return ((gidx ? (uint32_t) gidx[src] : src) << 16) | to;
+}
+
+// multi-GPU: this shard's candidate pointer of every long run (slot = number of long runs before it)
+__global__ void __launch_bounds__(256)
+k_candidates(MinTree T, const uint16_t *__restrict__ dist, const uint16_t *__restrict__ recid,
+             const uint32_t *__restrict__ rec_start, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ reach,
+             const uint8_t *__restrict__ flagc, const uint32_t *__restrict__ prevp, const uint32_t *__restrict__ nextp,
+             const uint32_t *__restrict__ runidx, const uint16_t *__restrict__ gidx, uint32_t s0, uint32_t n, int strict251,
+             uint32_t *__restrict__ cand) {
+    uint32_t i = s0 + blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (contrib_at(i, flagc, dist, prevp, nextp, strict251) <= 1) return;
+    cand[runidx[i]] = run_pointer(T, recid, rec_start, rank, reach, gidx, i, nextp[i] - prevp[i]);
+}
+
+__global__ void __launch_bounds__(256)
+k_emit(MinTree T, const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist,
+       const uint16_t *__restrict__ recid, const uint32_t *__restrict__ rec_start, const uint32_t *__restrict__ rank,
+       const uint32_t *__restrict__ reach, const uint8_t *__restrict__ flagc, const uint32_t *__restrict__ prevp,
+       const uint32_t *__restrict__ nextp, const uint32_t *__restrict__ off, uint32_t s0, uint32_t n, int strict251,
+       uint8_t *__restrict__ enc_out /* already offset so that off[] indexes it directly */, uint32_t *__restrict__ err,
+       const uint32_t *__restrict__ cand, const uint32_t *__restrict__ runidx, const uint16_t *__restrict__ gidx) {
+    uint32_t i = s0 + blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = contrib_at(i, flagc, dist, prevp, nextp, strict251);
+    if (c == 0) return;
+    uint32_t o = off[i];
+    if (c == 1) {
+        enc_out[o] = text[i];
+        return;
+    }
+    // long run ending at i
+    uint32_t rl = nextp[i] - prevp[i];
+    uint32_t src, to;
+    if (cand) {  // multi-GPU: the pointer was min-reduced across the shards
+        uint32_t key = cand[runidx[i]];
+        if (key == 0xFFFFFFFFu) {
+            atomicExch(err, 8u);
+            return;
+        }
+        src = key >> 16;
+        to = key & 0xffff;
+    } else {
+        uint32_t key = run_pointer(T, recid, rec_start, rank, reach, gidx, i, rl);
+        if (key == 0xFFFFFFFFu) {
+            atomicExch(err, 2u);
+            return;
+        }
+        src = key >> 16;
+        to = key & 0xffff;
+    }
     enc_out[o] = 251;
     if (c == 8) {
         uint32_t from = to - rl;
@@ -786,7 +825,9 @@ uint32_t Store::count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32
     return accepted;
 }
 
-uint32_t Store::encode_window_records(uint32_t first_new) {
+// Phase A: suffix array, LCP, trees, longest previous factor of the records [first_new, win_R) of the open
+// window (and, under the reference policy, the cut of the candidates at the rotation record).
+void Store::enc_phase_a(uint32_t first_new) {
     EncodeScratch &E = es;
     uint32_t N = win_N, R = win_R;
     const uint32_t s0 = h_win_rec_start[first_new];
@@ -870,6 +911,20 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
             gridM = div_up<uint32_t>(M, 256);
         }
     }
+    E.tree = T;
+    ep_first_new = first_new;
+    ep_s0 = s0;
+    ep_N = N;
+    ep_n_new = n_new;
+    launches += L;
+}
+
+// Phase B: PASS/COMPRESS flags from reach[], escape-pair rule, runs, output offsets.
+void Store::enc_phase_b() {
+    EncodeScratch &E = es;
+    const uint32_t s0 = ep_s0, N = ep_N, M = N - s0;
+    const uint32_t gridM = div_up<uint32_t>(M, 256);
+    int L = 0;
     prof.begin(PC_FLAGS, st);
     k_flag_scatter<<<gridM, 256, 0, st>>>(E.reach.p, w_dist.p, s0, N, E.flagp.p);
     L++;
@@ -916,6 +971,17 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
         L += 1;
     }
     prof.end(st, 45.0 * M, 6);
+    launches += L;
+}
+
+// Phase C: grow the store, emit the encoded records and their tables.  `cand`/`runidx` (multi-GPU mode)
+// carry the globally reduced (idx << 16 | to) of every long run; `gidx` maps window records to chunk indices.
+uint32_t Store::enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const uint16_t *gidx) {
+    EncodeScratch &E = es;
+    const MinTree &T = E.tree;
+    const uint32_t first_new = ep_first_new, s0 = ep_s0, N = ep_N, n_new = ep_n_new, M = N - s0;
+    const uint32_t gridM = div_up<uint32_t>(M, 256);
+    int L = 0;
     uint32_t enc_total = 0;
     PX_CUDA(cudaMemcpyAsync(&enc_total, E.off.p + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
@@ -935,7 +1001,7 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
     prof.begin(PC_EMIT, st);
     k_emit<<<gridM, 256, 0, st>>>(T, w_text.p, w_dist.p, w_recid.p, w_rec_start.p, E.rank.p, E.reach.p, E.flagc.p,
                                   E.prevp.p, E.nextp.p, E.off.p, s0, N, cfg.strict251, d_enc.p + enc_bytes,
-                                  E.counters.p + 2);
+                                  E.counters.p + 2, cand, runidx, gidx);
     prof.end(st, 20.0 * M, 1);
     prof.begin(PC_TABLES, st);
     k_record_tables<<<div_up<uint32_t>(n_new, 256), 256, 0, st>>>(n_new, first_new, (uint32_t) g_first, g_chunk_first,
@@ -969,6 +1035,34 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
     chunk_count.back() += n_new;
     launches += L;
     return n_new;
+}
+
+uint32_t Store::encode_window_records(uint32_t first_new) {
+    enc_phase_a(first_new);
+    enc_phase_b();
+    return enc_phase_c(nullptr, nullptr, nullptr);
+}
+
+// index maintenance (host CritBit; in-order semantics of n sequential setitem calls) + rc / saved outputs
+void Store::finish_index(uint32_t nn, size_t g_batch_first, const uint8_t *h_keys, const int64_t *h_koff,
+                         const int64_t *h_voff, const uint32_t *h_doc_len, int32_t *rc, int32_t *saved) {
+    std::vector<uint8_t> q;
+    for (uint32_t i = 0; i < nn; i++) {
+        const uint8_t *k = h_keys + h_koff[i];
+        size_t kl = (size_t) (h_koff[i + 1] - h_koff[i]);
+        escape_key(k, kl, q);
+        uint32_t g = (uint32_t) (g_batch_first + i);
+        int64_t old = index->set(q.data(), (uint32_t) q.size(), g);
+        if (old >= 0) {
+            h_live[old] = 0;
+            live_records--;
+        }
+        live_records++;
+        if (rc) rc[i] = old >= 0 ? PIXIU_CBT_SET_REPLACE : 0;
+        if (saved) saved[i] = (int32_t) h_doc_len[i] - (int32_t) h_enc_len[g];
+        raw_bytes += (int64_t) kl + (h_voff[i + 1] - h_voff[i]);
+        doc_bytes += h_doc_len[i];
+    }
 }
 
 int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals,
@@ -1038,7 +1132,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         PX_CUDA(cudaMemcpyAsync(w_rec_start.p, rs.data(), rs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         prof.begin(PC_DOCS, st);
         k_write_docs<<<n_new, 256, 0, st>>>(n_new, a, first_new, d_keys, d_koff, d_vals, d_voff,
-                                                                         w_rec_start.p, w_text.p, w_dist.p, w_recid.p);
+                                                                         w_rec_start.p, w_text.p, w_dist.p, w_recid.p, nullptr);
         prof.end(st, 7.0 * (newN - win_N), 1);
         launches++;
         win_R += n_new;
@@ -1049,24 +1143,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     }
     const auto t_gpu_done = std::chrono::steady_clock::now();
     PX_CUDA(cudaEventRecord(ev1, st));
-    // ---- index maintenance (host CritBit; in-order semantics of n sequential setitem calls) ----
-    std::vector<uint8_t> q;
-    for (uint32_t i = 0; i < nn; i++) {
-        const uint8_t *k = h_keys + h_koff[i];
-        size_t kl = (size_t) (h_koff[i + 1] - h_koff[i]);
-        escape_key(k, kl, q);
-        uint32_t g = (uint32_t) (g_batch_first + i);
-        int64_t old = index->set(q.data(), (uint32_t) q.size(), g);
-        if (old >= 0) {
-            h_live[old] = 0;
-            live_records--;
-        }
-        live_records++;
-        if (rc) rc[i] = old >= 0 ? PIXIU_CBT_SET_REPLACE : 0;
-        if (saved) saved[i] = (int32_t) h_doc_len[i] - (int32_t) h_enc_len[g];
-        raw_bytes += (int64_t) kl + (h_voff[i + 1] - h_voff[i]);
-        doc_bytes += h_doc_len[i];
-    }
+    finish_index(nn, g_batch_first, h_keys, h_koff, h_voff, h_doc_len.data(), rc, saved);
     PX_CUDA(cudaEventSynchronize(ev1));
     float ms = 0;
     PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1078,6 +1155,186 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
                 std::chrono::duration<double, std::milli>(t_gpu_done - t_begin).count(),
                 std::chrono::duration<double, std::milli>(t_end - t_gpu_done).count(), ms);
     }
+    return PIXIU_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Multi-GPU extended window: the open window is sharded by record over `world` stores (one per GPU,
+// record idx -> rank idx % world); an incoming batch is replicated.  Every rank builds the suffix
+// array of (its shard + the batch) and computes its local M(s); the global M is the element-wise MAX
+// over ranks (collective 1), from which every rank derives identical flags and runs; each rank's
+// leftmost-occurrence candidate (idx << 16 | to) per long run is MIN-reduced (collective 2: lowest
+// record, then lowest offset = leftmost in insertion order); every rank then emits the identical
+// encoded batch.  The collectives themselves are issued by the caller (torch.distributed / NCCL) on
+// the device buffers these phases hand out.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_extract_m(const uint32_t *__restrict__ reach, uint32_t s0, uint32_t m, uint32_t *__restrict__ out) {
+    uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k < m) out[k] = reach[s0 + k] - (s0 + k);
+}
+
+__global__ void __launch_bounds__(256)
+k_apply_m(const uint32_t *__restrict__ in, uint32_t s0, uint32_t m, uint32_t *__restrict__ reach) {
+    uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k < m) reach[s0 + k] = s0 + k + in[k];
+}
+
+int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals, const int64_t *d_voff,
+                    const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff, uint32_t **d_m, int64_t *count) {
+    if (mg_world < 1 || mg_pending) return PIXIU_EINVAL;
+    if (n <= 0 || n > (int64_t) MAX_CHUNK_RECS) return PIXIU_EINVAL;  // a batch must fit one chunk
+    if (cfg.rotate_policy == PIXIU_ROTATE_REFERENCE) {
+        err = "multi-GPU mode extends the window beyond the reference's arena rule: use PIXIU_ROTATE_BYTES or _RECORDS";
+        return PIXIU_EINVAL;
+    }
+    const uint32_t nn = (uint32_t) n;
+    PX_CUDA(cudaEventRecord(ev0, st));
+    doc_len.reserve_discard(nn);
+    k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p);
+    launches++;
+    mg_doc_len.resize(nn);
+    PX_CUDA(cudaMemcpyAsync(mg_doc_len.data(), doc_len.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    uint64_t batch_bytes = 0;
+    for (uint32_t i = 0; i < nn; i++) {
+        if (mg_doc_len[i] == 0xFFFFFFFFu) return PIXIU_EINVAL;
+        if (mg_doc_len[i] > MAX_DOC) return PIXIU_ETOOLONG;
+        batch_bytes += mg_doc_len[i] + 1;
+    }
+    // rotation is decided from global counters only, so every rank takes the same decision
+    const uint64_t byte_budget = cfg.rotate_policy == PIXIU_ROTATE_BYTES ? (uint64_t) cfg.window_bytes * mg_world : ~0ull;
+    if (win_open && (mg_gR + nn > MAX_CHUNK_RECS || (mg_gbytes && mg_gbytes + batch_bytes > byte_budget))) close_window();
+    if (!win_open) {
+        open_window();
+        mg_gR = 0;
+        mg_gbytes = 0;
+        mg_h_gidx.clear();
+    }
+    // local window = shard records + the whole batch
+    const uint32_t first_new = win_R;
+    uint64_t bytes = win_N;
+    for (uint32_t i = 0; i < nn; i++) {
+        bytes += mg_doc_len[i] + 1;
+        h_win_rec_start.push_back((uint32_t) bytes);
+        mg_h_gidx.push_back((uint16_t) (mg_gR + i));
+    }
+    if (bytes >= (1ull << 30) - (1ull << 17)) return PIXIU_EINVAL;
+    const uint32_t newN = (uint32_t) bytes;
+    w_text.reserve_keep(newN + 16, win_N, st);
+    w_dist.reserve_keep(newN + 16, win_N, st);
+    w_recid.reserve_keep(newN + 16, win_N, st);
+    w_rec_start.reserve_discard(h_win_rec_start.size() + 1);
+    es.gidx.reserve_discard(mg_h_gidx.size() + 1);
+    PX_CUDA(cudaMemcpyAsync(w_rec_start.p, h_win_rec_start.data(), h_win_rec_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PX_CUDA(cudaMemcpyAsync(es.gidx.p, mg_h_gidx.data(), mg_h_gidx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    k_write_docs<<<nn, 256, 0, st>>>(nn, 0, first_new, d_keys, d_koff, d_vals, d_voff, w_rec_start.p, w_text.p, w_dist.p,
+                                     w_recid.p, nullptr);
+    launches++;
+    win_R += nn;
+    win_N = newN;
+    enc_phase_a(first_new);
+    const uint32_t m = ep_N - ep_s0;
+    es.mg_m.reserve_discard(m + 1);
+    k_extract_m<<<div_up<uint32_t>(m, 256), 256, 0, st>>>(es.reach.p, ep_s0, m, es.mg_m.p);
+    launches++;
+    PX_CUDA(cudaStreamSynchronize(st));
+    // keep what the later phases need
+    mg_d_keys = d_keys;
+    mg_d_koff = d_koff;
+    mg_d_vals = d_vals;
+    mg_d_voff = d_voff;
+    mg_h_keys.assign(h_keys + h_koff[0], h_keys + h_koff[nn]);
+    mg_h_koff.resize(nn + 1);
+    mg_h_voff.resize(nn + 1);
+    for (uint32_t i = 0; i <= nn; i++) {
+        mg_h_koff[i] = h_koff[i] - h_koff[0];
+        mg_h_voff[i] = h_voff[i] - h_voff[0];
+    }
+    mg_pending = 1;
+    mg_batch_bytes = batch_bytes;
+    *d_m = es.mg_m.p;
+    *count = m;
+    return PIXIU_OK;
+}
+
+int Store::mg_mid(uint32_t **d_cand, int64_t *count) {
+    if (mg_pending != 1) return PIXIU_EINVAL;
+    EncodeScratch &E = es;
+    const uint32_t s0 = ep_s0, N = ep_N, m = N - s0;
+    k_apply_m<<<div_up<uint32_t>(m, 256), 256, 0, st>>>(E.mg_m.p, s0, m, E.reach.p);
+    launches++;
+    enc_phase_b();
+    // number the long runs: runidx[i] = long runs ending before i
+    E.runidx.reserve_discard((size_t) N + 2);
+    {
+        const uint8_t *fc = E.flagc.p;
+        const uint16_t *dist = w_dist.p;
+        const uint32_t *pp = E.prevp.p, *np = E.nextp.p;
+        uint32_t *ri = E.runidx.p;
+        const int strict = cfg.strict251;
+        device_scan<uint32_t>(
+            (size_t) m + 1,
+            [=] __device__(size_t k) -> uint32_t { return k < m && contrib_at(s0 + (uint32_t) k, fc, dist, pp, np, strict) > 1 ? 1u : 0u; },
+            [=] __device__(size_t k, uint32_t v) { ri[s0 + k] = v; }, OpSum(), 0u, true, E.scanws, st);
+        launches++;
+    }
+    uint32_t nruns = 0;
+    PX_CUDA(cudaMemcpyAsync(&nruns, E.runidx.p + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    E.mg_cand.reserve_discard((size_t) nruns + 1);
+    if (nruns) {
+        k_candidates<<<div_up<uint32_t>(m, 256), 256, 0, st>>>(E.tree, w_dist.p, w_recid.p, w_rec_start.p, E.rank.p, E.reach.p,
+                                                             E.flagc.p, E.prevp.p, E.nextp.p, E.runidx.p, E.gidx.p, s0, N,
+                                                             cfg.strict251, E.mg_cand.p);
+        launches++;
+    }
+    PX_CUDA(cudaStreamSynchronize(st));
+    mg_pending = 2;
+    *d_cand = E.mg_cand.p;
+    *count = nruns;
+    return PIXIU_OK;
+}
+
+int Store::mg_end(int32_t *rc, int32_t *saved) {
+    if (mg_pending != 2) return PIXIU_EINVAL;
+    EncodeScratch &E = es;
+    const uint32_t first_new = ep_first_new, nn = ep_n_new;
+    const size_t g_batch_first = n_records();
+    enc_phase_c(E.mg_cand.p, E.runidx.p, E.gidx.p);
+    // shard maintenance: drop the batch from the local window, keep only the records this rank owns
+    std::vector<uint32_t> own;
+    for (uint32_t b = 0; b < nn; b++)
+        if ((mg_gR + b) % (uint32_t) mg_world == (uint32_t) mg_rank) own.push_back(b);
+    h_win_rec_start.resize(first_new + 1);
+    mg_h_gidx.resize(first_new);
+    uint64_t bytes = h_win_rec_start.back();
+    for (uint32_t b : own) {
+        bytes += mg_doc_len[b] + 1;
+        h_win_rec_start.push_back((uint32_t) bytes);
+        mg_h_gidx.push_back((uint16_t) (mg_gR + b));
+    }
+    win_R = first_new + (uint32_t) own.size();
+    win_N = (uint32_t) bytes;
+    if (!own.empty()) {
+        DevBuf<uint32_t> &lst = E.mg_m;  // free after the reduce: reuse as the source list
+        lst.reserve_discard(own.size() + 1);
+        PX_CUDA(cudaMemcpyAsync(lst.p, own.data(), own.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        PX_CUDA(cudaMemcpyAsync(w_rec_start.p, h_win_rec_start.data(), h_win_rec_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        k_write_docs<<<(unsigned) own.size(), 256, 0, st>>>((uint32_t) own.size(), 0, first_new, mg_d_keys, mg_d_koff, mg_d_vals,
+                                                          mg_d_voff, w_rec_start.p, w_text.p, w_dist.p, w_recid.p, lst.p);
+        launches++;
+    }
+    PX_CUDA(cudaEventRecord(ev1, st));
+    mg_gR += nn;
+    mg_gbytes += mg_batch_bytes;
+    finish_index(nn, g_batch_first, mg_h_keys.data(), mg_h_koff.data(), mg_h_voff.data(), mg_doc_len.data(), rc, saved);
+    PX_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0;
+    PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_set_ms = ms;
+    prof.collect();
+    mg_pending = 0;
     return PIXIU_OK;
 }
 

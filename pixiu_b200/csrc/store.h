@@ -54,6 +54,10 @@ struct EncodeScratch {
     PinnedBuf<uint32_t> h_leafmask, h_splitmask, h_wordpre;
     DevBuf<uint32_t> counters;  // [0] active count, [1] group count, [2] error flag, [3..] misc
     RadixSortTemp rs;
+    MinTree tree{};  // block-min trees of the last phase A
+    // multi-GPU exchange buffers
+    DevBuf<uint32_t> mg_m, mg_cand, runidx;
+    DevBuf<uint16_t> gidx;
 };
 
 struct Store {
@@ -124,6 +128,26 @@ struct Store {
                       const int64_t *d_voff, const uint8_t *h_keys, const int64_t *h_koff,
                       const int64_t *h_voff, int32_t *rc, int32_t *saved);
     uint32_t encode_window_records(uint32_t first_new);  // returns the number of records accepted
+    void enc_phase_a(uint32_t first_new);
+    void enc_phase_b();
+    uint32_t enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const uint16_t *gidx);
+    uint32_t ep_first_new = 0, ep_s0 = 0, ep_N = 0, ep_n_new = 0;  // state shared by the phases
+    void finish_index(uint32_t nn, size_t g_batch_first, const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff,
+                      const uint32_t *h_doc_len, int32_t *rc, int32_t *saved);
+    // multi-GPU extended window (encode.cu, "Multi-GPU extended window")
+    int mg_rank = 0, mg_world = 0, mg_pending = 0;
+    uint32_t mg_gR = 0;          // records of the open chunk over all ranks
+    uint64_t mg_gbytes = 0, mg_batch_bytes = 0;
+    std::vector<uint16_t> mg_h_gidx;  // chunk index of every local window record
+    std::vector<uint32_t> mg_doc_len;
+    std::vector<uint8_t> mg_h_keys;
+    std::vector<int64_t> mg_h_koff, mg_h_voff;
+    const uint8_t *mg_d_keys = nullptr, *mg_d_vals = nullptr;
+    const int64_t *mg_d_koff = nullptr, *mg_d_voff = nullptr;
+    int mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals, const int64_t *d_voff,
+                 const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff, uint32_t **d_m, int64_t *count);
+    int mg_mid(uint32_t **d_cand, int64_t *count);
+    int mg_end(int32_t *rc, int32_t *saved);
     uint32_t count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32_t s0, uint32_t N);
     // decode.cu
     void decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off);

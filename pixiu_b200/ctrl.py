@@ -48,6 +48,7 @@ EXPORTS = [
     "pixiu_getitem_batch", "pixiu_getitem_batch_dev", "pixiu_iter", "pixiu_encoded_view",
     "pixiu_record_location", "pixiu_import_chunk", "pixiu_decode_chunk", "pixiu_rotate",
     "pixiu_profile_enable", "pixiu_profile_get", "pixiu_stream",
+    "pixiu_mg_config", "pixiu_mg_setitem_begin", "pixiu_mg_setitem_mid", "pixiu_mg_setitem_end",
 ]
 
 _lib = None
@@ -87,7 +88,13 @@ def load_library():
                                     C.POINTER(C.c_double), _i64p]
     L.pixiu_stream.argtypes = [C.c_void_p]
     L.pixiu_stream.restype = C.c_void_p
+    L.pixiu_mg_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.pixiu_mg_setitem_begin.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_void_p), _i64p]
+    L.pixiu_mg_setitem_mid.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _i64p]
+    L.pixiu_mg_setitem_end.argtypes = [C.c_void_p, _i32p, _i32p]
     # test hooks
+    L.pixiu_debug_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     L.pixiu_debug_sort_pairs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     L.pixiu_debug_window_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
     L.pixiu_debug_window_array.restype = C.c_int64
@@ -350,6 +357,32 @@ class PiXiuCtrl:
         buf = np.zeros(max(need.value, 1), dtype=np.uint8)
         self._check(self._L.pixiu_decode_chunk(self._h, chunk, _ptr(buf), buf.size, off.ctypes.data_as(_i64p), C.byref(need)))
         return buf, off
+
+    # -- multi-GPU extended window: three phases around the caller's two all-reduces --
+    def mg_config(self, rank: int, world: int):
+        self._check(self._L.pixiu_mg_config(self._h, rank, world))
+
+    def mg_setitem_begin(self, keys, vals):
+        """-> (device pointer of uint32 M[count], count): all_reduce(MAX) it in place"""
+        kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
+        vd, vo = vals if isinstance(vals, tuple) else _pack(vals)
+        self._mg_n = len(ko) - 1
+        p, cnt = C.c_void_p(), C.c_int64()
+        self._check(self._L.pixiu_mg_setitem_begin(self._h, self._mg_n, _ptr(kd), _ptr(ko), _ptr(vd), _ptr(vo),
+                                                   C.byref(p), C.byref(cnt)))
+        return p.value or 0, cnt.value
+
+    def mg_setitem_mid(self):
+        """-> (device pointer of uint32 cand[count], count): all_reduce(MIN) it in place"""
+        p, cnt = C.c_void_p(), C.c_int64()
+        self._check(self._L.pixiu_mg_setitem_mid(self._h, C.byref(p), C.byref(cnt)))
+        return p.value or 0, cnt.value
+
+    def mg_setitem_end(self):
+        rc = np.zeros(self._mg_n, dtype=np.int32)
+        saved = np.zeros(self._mg_n, dtype=np.int32)
+        self._check(self._L.pixiu_mg_setitem_end(self._h, rc.ctypes.data_as(_i32p), saved.ctypes.data_as(_i32p)))
+        return rc, saved
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.pixiu_profile_enable(self._h, int(on)))
