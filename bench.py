@@ -313,6 +313,71 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_sharded(args, rank, world, local_rank):
+    """BASELINE config 5 style: ONE extended window sharded by record over the GPUs; every batch goes to
+    all ranks, match lengths are MAX-reduced and leftmost candidates MIN-reduced by NCCL."""
+    import torch
+    import torch.distributed as dist
+
+    from pixiu_b200 import ctrl, multigpu, shard, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kd, ko, vd, vo = gen_corpus(args.pages, 2)          # the same corpus on every rank
+    n = len(ko) - 1
+    raw = int(ko[-1] + vo[-1])
+    bp = args.batch_pages
+    batches = []
+    for a in range(0, n, bp):
+        idx = np.arange(a, min(n, a + bp))
+        batches.append((shard.take_packed(kd, ko, idx), shard.take_packed(vd, vo, idx)))
+
+    def one_pass():
+        c = ctrl.PiXiuCtrl(device=local_rank, rotate_policy=ctrl.ROTATE_BYTES, window_bytes=args.window_bytes)
+        c.mg_config(rank, world)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for kb, vb in batches:
+            if world > 1:
+                multigpu.setitem_sharded(c, kb, vb, device=dev)
+            else:
+                c.mg_setitem_begin(kb, vb)
+                c.mg_setitem_mid()
+                c.mg_setitem_end()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+        st = c.stats()
+        out = (dt, st.encoded_bytes / max(st.raw_bytes, 1), st.chunks, st.kernel_launches)
+        c.free_prop()
+        return out
+
+    for _ in range(args.warmup):
+        one_pass()
+    res = [one_pass() for _ in range(args.steps)]
+    t = torch.tensor([sum(r[0] for r in res)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sec = float(t) / args.steps
+        print(json.dumps({
+            "metric": METRIC, "value": raw / sec / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"C5 style: {args.pages} synthetic HTML-like pages, ONE window sharded over {world} GPU(s), "
+                                   f"{args.window_bytes} window bytes per GPU, batches of {bp} pages replicated to all ranks",
+                       "mode": "sharded window + NCCL all_reduce(MAX) of M / all_reduce(MIN) of leftmost candidates",
+                       "raw_bytes": raw, "stored_over_raw": res[-1][1], "chunks": res[-1][2]},
+            "gpu_launches": int(res[-1][3]), "collectives_per_step": 2 * len(batches) if world > 1 else 0}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -325,12 +390,18 @@ def main():
     ap.add_argument("--ref-pages", type=int, default=150, help="bounded sample for the CPU reference leg")
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mode", default="partition", choices=["partition", "shard"],
+                    help="partition: one store per GPU, corpus partitioned by key (default, weak scaling); "
+                         "shard: one extended window sharded over the GPUs with NCCL reduces (config 5 style)")
+    ap.add_argument("--batch-pages", type=int, default=256)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.mode == "shard":
+        run_sharded(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 
