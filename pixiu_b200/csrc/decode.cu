@@ -26,7 +26,7 @@
 
 namespace pixiu {
 
-constexpr int DEC_WARPS = 8;
+constexpr int DEC_WARPS = 4;
 constexpr uint32_t ENC_MAX = TILE + 16;
 constexpr int RESOLVE_HOPS = 48;
 enum : uint8_t { K_LIT = 0, K_COV = 1, K_SREF = 2, K_BREF = 3 };
@@ -41,48 +41,57 @@ struct DecodeView {
     uint32_t *litmap;           // per arena byte: 1 bit, set = literal
 };
 
+constexpr uint32_t SEG_MAX = (ENC_MAX + 8) / 6 + 2;  // a reference token takes at least 6 encoded bytes
+
 struct WarpSmem {
-    uint8_t enc[ENC_MAX];
-    uint8_t kind[ENC_MAX];
-    uint8_t out[TILE];
-    uint32_t lit[TILE / 32];
-    uint16_t queue[256];
-    uint32_t qn;
+    // encoded bytes (word aligned copy; byte p of the tile at enc8[a0 + p]) followed by the token kinds;
+    // after the row loop the same 4 KB hold the per-byte segment markers (u16 x TILE)
+    uint32_t encw[(ENC_MAX + 8) / 4];
+    uint8_t kind[ENC_MAX + 8];
+    uint32_t outw[TILE / 4];  // the tile's decoded bytes (literal positions); before that: the list of 251 positions
+    uint32_t lit[TILE / 32];  // literal bitmap of the tile
+    // reference segments clipped to the tile, in output order
+    uint32_t seg_base[SEG_MAX];  // arena position of the token's source byte 0
+    uint16_t seg_k0[SEG_MAX];    // first token byte inside the tile
+    uint16_t seg_per[SEG_MAX];   // period of a self-overlapping reference (0: none)
+    uint16_t seg_rel[SEG_MAX];   // tile-relative output position of byte k0
+    uint16_t seg_len[SEG_MAX];
 };
+static_assert(sizeof(uint32_t) * ((ENC_MAX + 8) / 4) + (ENC_MAX + 8) >= sizeof(uint16_t) * TILE, "marker alias");
 
-// bytes [k0, k1) of a reference token (token-relative): write their source pointers
-// rel0: tile-relative decoded offset of the token's first byte (may be negative)
-__device__ __forceinline__ void emit_ref_ptrs(const DecodeView &V, uint32_t g, uint32_t rec_base, uint32_t t0, int rel0,
-                                              uint32_t idx, uint32_t from, uint32_t k0, uint32_t k1, uint32_t step,
-                                              uint32_t lane_off, uint32_t *err) {
-    uint32_t src_g = V.first[g] + idx;
-    uint32_t *dst = V.ptr + rec_base + t0;
-    if (src_g == g) {
-        // self reference (PiXiuStr.h:168-181): overlapping copies repeat with period = token start - from
-        uint32_t period = (uint32_t) ((int) t0 + rel0) - from;
-        uint32_t base = rec_base + from;
-        if (from + k1 <= from + period) {
-            for (uint32_t k = k0 + lane_off; k < k1; k += step) dst[rel0 + (int) k] = base + k;
+// one 251 at tile position p that surely starts a token: walk its cluster (PiXiuStr.h:142-160 dispatch)
+__device__ __forceinline__ void walk_cluster(WarpSmem &S, const uint8_t *EB, uint32_t p, uint32_t ne, uint32_t *err) {
+    uint32_t e = p;
+    while (true) {
+        if (e + 1 >= ne) {  // first half of an escape pair cut by the tile boundary
+            S.kind[e] = K_LIT;
+            break;
+        }
+        uint32_t nx = EB[e + 1];
+        uint32_t tl;
+        if (nx == 0 || nx == 251 || nx == 2) {
+            S.kind[e] = K_LIT;
+            S.kind[e + 1] = K_LIT;
+            tl = 2;
+        } else if (nx == 1) {
+            S.kind[e] = K_BREF;
+            tl = 8;
+        } else if (nx > 6) {
+            S.kind[e] = K_SREF;
+            tl = 6;
         } else {
-            for (uint32_t k = k0 + lane_off; k < k1; k += step) dst[rel0 + (int) k] = base + (k % period);
+            atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
+            break;
         }
-    } else {
-        if (src_g > g) {
-            atomicExch(err, 3u);
-            return;
-        }
-        uint32_t base = V.arena_off[src_g] + from;
-        for (uint32_t k = k0 + lane_off; k < k1; k += step) dst[rel0 + (int) k] = base + k;
+        if (tl > 2)
+            for (uint32_t q = e + 1; q < e + tl && q < ne; q++) S.kind[q] = K_COV;
+        e += tl;
+        // the next 251 of the same cluster lies within 7 bytes of the last one seen
+        uint32_t q = e;
+        while (q < ne && q < e + 7 && EB[q] != 251) q++;
+        if (q >= ne || q >= e + 7) break;
+        e = q;
     }
-}
-
-__device__ __forceinline__ uint32_t tok_dlen(const WarpSmem &S, uint32_t p) {
-    uint8_t k = S.kind[p];
-    if (k == K_LIT) return 1;
-    if (k == K_SREF) return S.enc[p + 1];
-    if (k == K_BREF)
-        return (uint32_t) (S.enc[p + 4] | (S.enc[p + 5] << 8)) - (uint32_t) (S.enc[p + 6] | (S.enc[p + 7] << 8));
-    return 0;
 }
 
 __global__ void __launch_bounds__(DEC_WARPS * 32)
@@ -91,13 +100,14 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1;
     const uint32_t w = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
     if (w >= n_work) return;
     const uint32_t gt = work_tile[w], g = work_rec[w];
     const uint32_t t = gt - V.tile_base[g];
     const uint32_t dl = V.dec_len[g], el = V.enc_len[g];
     const uint32_t t0 = t * TILE, t1 = min(dl, t0 + TILE), nbytes = t1 - t0;
-    const uint32_t rec_base = V.arena_off[g];
+    const uint32_t rec_base = V.arena_off[g], chunk_first = V.first[g];
     const uint8_t *encp = V.enc + V.enc_off[g];
     uint32_t desc = V.tile_desc[gt];
     const uint32_t e0 = desc & 0xffff;
@@ -116,120 +126,149 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
         if (lane == 0) atomicExch(err, 4u);
         return;
     }
-    // ---- 1. stage encoded bytes; default token kinds ----
-    for (uint32_t p = lane; p < ne; p += 32) {
-        uint8_t b = encp[e0 + p];
-        S.enc[p] = b;
-        S.kind[p] = b == 251 ? K_COV : K_LIT;
-    }
-    for (uint32_t j = lane; j < TILE / 32; j += 32) S.lit[j] = 0;
-    if (lane == 0) {
-        S.qn = 0;
-        if (raw_first) S.kind[0] = K_LIT;
+    // ---- 1. stage the encoded bytes with aligned word loads (the arena has slack past its end) ----
+    const uint8_t *gsrc = encp + e0;
+    const uint32_t a0 = (uint32_t) ((uintptr_t) gsrc & 3);
+    const uint32_t *gw = reinterpret_cast<const uint32_t *>(gsrc - a0);
+    const uint32_t nw = (a0 + ne + 3) >> 2;
+    for (uint32_t j = lane; j < nw; j += 32) S.encw[j] = gw[j];
+    __syncwarp();
+    const uint8_t *EB = reinterpret_cast<const uint8_t *>(S.encw) + a0;
+    // ---- 2. token kinds.  Default: a 251 is "covered" until a walk proves it a head.  The 251 positions are
+    //         compacted into a list (in outw) so that the cluster walks run 32 at a time ----
+    const uint32_t pstart = raw_first ? 1u : 0u;
+    uint16_t *cands = reinterpret_cast<uint16_t *>(S.outw);
+    uint32_t ncand = 0;
+    for (uint32_t r0 = 0; r0 < ne; r0 += 32) {
+        const uint32_t p = r0 + lane;
+        const bool is251 = p < ne && EB[p] == 251;
+        if (p < ne) S.kind[p] = is251 ? K_COV : K_LIT;
+        const uint32_t m = __ballot_sync(0xffffffffu, is251 && p >= pstart);
+        if (is251 && p >= pstart) {
+            uint32_t slot = ncand + __popc(m & lt);
+            if (slot < TILE / 2) cands[slot] = (uint16_t) p;
+        }
+        ncand += __popc(m);
     }
     __syncwarp();
-    // ---- 2. token heads: a 251 with no 251 among the 7 bytes before it surely starts a token;
-    //         its owner walks the cluster of nearby 251s (PiXiuStr.h:142-160 dispatch) ----
-    const uint32_t pstart = raw_first ? 1u : 0u;
-    for (uint32_t p = pstart + lane; p < ne; p += 32) {
-        if (S.enc[p] != 251) continue;
-        bool certain = true;
-        for (uint32_t q = (p >= pstart + 7 ? p - 7 : pstart); q < p; q++) certain &= S.enc[q] != 251;
-        if (!certain) continue;
-        uint32_t e = p;
-        while (true) {
-            if (e + 1 >= ne) {  // first half of an escape pair cut by the tile boundary
-                S.kind[e] = K_LIT;
-                break;
+    if (lane == 0 && raw_first) S.kind[0] = K_LIT;
+    __syncwarp();
+    if (ncand <= TILE / 2) {
+        for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            if (c < ncand) {
+                const uint32_t p = cands[c];
+                // a 251 with no 251 among the 7 bytes before it surely starts a token
+                bool certain = c == 0 || (uint32_t) cands[c - 1] + 7 < p;
+                if (certain) walk_cluster(S, EB, p, ne, err);
             }
-            uint32_t nx = S.enc[e + 1];
-            uint32_t tl;
-            if (nx == 0 || nx == 251 || nx == 2) {
-                S.kind[e] = K_LIT;
-                S.kind[e + 1] = K_LIT;
-                tl = 2;
-            } else if (nx == 1) {
-                S.kind[e] = K_BREF;
-                tl = 8;
-            } else if (nx > 6) {
-                S.kind[e] = K_SREF;
-                tl = 6;
-            } else {
-                atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
-                break;
-            }
-            if (tl > 2)
-                for (uint32_t q = e + 1; q < e + tl && q < ne; q++) S.kind[q] = K_COV;
-            e += tl;
-            // the next 251 of the same cluster lies within 7 bytes of the last one seen
-            uint32_t q = e;
-            while (q < ne && q < e + 7 && S.enc[q] != 251) q++;
-            if (q >= ne || q >= e + 7) break;
-            e = q;
+        }
+    } else {  // 251-dense tile: scan positions directly
+        for (uint32_t p = pstart + lane; p < ne; p += 32) {
+            if (EB[p] != 251) continue;
+            bool certain = true;
+            for (uint32_t q = (p >= pstart + 7 ? p - 7 : pstart); q < p; q++) certain &= EB[q] != 251;
+            if (certain) walk_cluster(S, EB, p, ne, err);
         }
     }
     __syncwarp();
-    // ---- 3. decoded offset of every token: per-lane strips + warp scan ----
-    const uint32_t strip = (ne + 31) / 32;
-    const uint32_t p0 = min(lane * strip, ne), p1 = min(p0 + strip, ne);
-    uint32_t sum = 0;
-    for (uint32_t p = p0; p < p1; p++) sum += tok_dlen(S, p);
-    uint32_t inc = sum;
+    // ---- 3. rows of 32 encoded positions: decoded offsets by warp scan; literals go to the tile buffer,
+    //         references become segments (clipped to the tile, in output order) ----
+    uint8_t *out8 = reinterpret_cast<uint8_t *>(S.outw);
+    uint32_t base = 0;  // decoded bytes of the tokens before this row (counted from the first token's start)
+    uint32_t nseg = 0;
+    for (uint32_t r0 = 0; r0 < ne; r0 += 32) {
+        const uint32_t p = r0 + lane;
+        const uint8_t k = p < ne ? S.kind[p] : (uint8_t) K_COV;
+        uint32_t idx = 0, from = 0, tl = k == K_LIT ? 1u : 0u;
+        const bool isref = k == K_SREF || k == K_BREF;
+        if (isref) {
+            idx = EB[p + 2] | (EB[p + 3] << 8);
+            uint32_t to = EB[p + 4] | (EB[p + 5] << 8);
+            from = k == K_SREF ? to - EB[p + 1] : (uint32_t) (EB[p + 6] | (EB[p + 7] << 8));
+            tl = to - from;
+        }
+        uint32_t inc = tl;
+        const uint32_t special = __ballot_sync(0xffffffffu, k != K_LIT);
+        if (special == 0) {
+            inc = lane + 1;  // a row of plain literals
+        } else {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-        if ((int) lane >= d) inc += o;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((int) lane >= d) inc += o;
+            }
+        }
+        const int rel = (int) (base + inc - tl) - (int) skip;
+        uint32_t k0 = 0, k1 = 0;
+        if (k == K_LIT) {
+            if (rel >= 0 && rel < (int) nbytes) out8[rel] = EB[p];
+        } else if (isref) {
+            k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
+            k1 = (int) tl + rel > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
+        }
+        const bool emit = isref && k0 < k1;
+        const uint32_t em = __ballot_sync(0xffffffffu, emit);
+        if (emit) {
+            const uint32_t sidx = nseg + __popc(em & lt);
+            const uint32_t src_g = chunk_first + idx;
+            uint32_t sbase, per = 0;
+            if (src_g == g) {  // self reference (PiXiuStr.h:168-181): overlapping copies repeat with this period
+                uint32_t period = (uint32_t) ((int) t0 + rel) - from;
+                sbase = rec_base + from;
+                per = tl > period ? period : 0u;
+            } else {
+                if (src_g > g) atomicExch(err, 3u);
+                sbase = (src_g > g ? 0u : V.arena_off[src_g]) + from;
+            }
+            if (sidx < SEG_MAX) {
+                S.seg_base[sidx] = sbase;
+                S.seg_k0[sidx] = (uint16_t) k0;
+                S.seg_per[sidx] = (uint16_t) per;
+                S.seg_rel[sidx] = (uint16_t) (rel + (int) k0);
+                S.seg_len[sidx] = (uint16_t) (k1 - k0);
+            }
+        }
+        nseg += __popc(em);
+        base += __shfl_sync(0xffffffffu, inc, 31);
     }
-    uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    if (total < skip + nbytes) {
+    if (base < skip + nbytes || nseg > SEG_MAX) {
         if (lane == 0) atomicExch(err, 6u);
         return;
     }
-    // ---- 4. emit: literal bytes to the tile buffer, reference bytes to the pointer array ----
-    int rel = (int) (inc - sum) - (int) skip;  // tile-relative decoded offset at p0
-    for (uint32_t p = p0; p < p1; p++) {
-        uint8_t k = S.kind[p];
-        if (k == K_LIT) {
-            if (rel >= 0 && rel < (int) nbytes) {
-                S.out[rel] = S.enc[p];
-                atomicOr(&S.lit[rel >> 5], 1u << (rel & 31));
-            }
-            rel += 1;
-        } else if (k == K_SREF || k == K_BREF) {
-            uint32_t idx = S.enc[p + 2] | (S.enc[p + 3] << 8);
-            uint32_t to = S.enc[p + 4] | (S.enc[p + 5] << 8);
-            uint32_t from = k == K_SREF ? to - S.enc[p + 1] : (uint32_t) (S.enc[p + 6] | (S.enc[p + 7] << 8));
-            uint32_t tl = to - from;
-            uint32_t k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
-            uint32_t k1 = (int) tl + rel > (int) nbytes ? (uint32_t) ((int) nbytes - rel) : tl;
-            if (k0 < k1) {
-                uint32_t qi = 256;
-                if (k1 - k0 > 48) qi = atomicAdd(&S.qn, 1u);
-                if (qi < 256) S.queue[qi] = (uint16_t) p;
-                else emit_ref_ptrs(V, g, rec_base, t0, rel, idx, from, k0, k1, 1, 0, err);
-            }
-            rel += (int) tl;
-        }
-    }
     __syncwarp();
-    // long references: the whole warp writes each one (coalesced)
-    {
-        uint32_t qn = min(S.qn, 256u);
-        for (uint32_t qi = 0; qi < qn; qi++) {
-            uint32_t p = S.queue[qi];
-            uint32_t owner = p / strip;
-            uint32_t d = __shfl_sync(0xffffffffu, inc - sum, owner);
-            for (uint32_t q = owner * strip; q < p; q++) d += tok_dlen(S, q);
-            int r0 = (int) d - (int) skip;
-            uint8_t k = S.kind[p];
-            uint32_t idx = S.enc[p + 2] | (S.enc[p + 3] << 8);
-            uint32_t to = S.enc[p + 4] | (S.enc[p + 5] << 8);
-            uint32_t from = k == K_SREF ? to - S.enc[p + 1] : (uint32_t) (S.enc[p + 6] | (S.enc[p + 7] << 8));
-            uint32_t tl = to - from;
-            uint32_t k0 = r0 < 0 ? (uint32_t) (-r0) : 0u;
-            uint32_t k1 = (int) tl + r0 > (int) nbytes ? (uint32_t) ((int) nbytes - r0) : tl;
-            emit_ref_ptrs(V, g, rec_base, t0, r0, idx, from, k0, k1, 32, lane, err);
+    // ---- 4. per output byte: which segment covers it (markers at segment starts + running max), then the
+    //         literal bitmap word and the coalesced source pointers ----
+    uint16_t *marker = reinterpret_cast<uint16_t *>(S.encw);  // the encoded bytes are not needed any more
+    for (uint32_t j = lane; j < TILE / 2; j += 32) reinterpret_cast<uint32_t *>(marker)[j] = 0;
+    __syncwarp();
+    for (uint32_t sgi = lane; sgi < nseg; sgi += 32) marker[S.seg_rel[sgi]] = (uint16_t) (sgi + 1);
+    __syncwarp();
+    uint32_t *gptr = V.ptr + rec_base + t0;
+    uint32_t carry = 0;  // id+1 of the latest segment start seen so far
+    for (uint32_t j0 = 0; j0 < nbytes; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        uint32_t cur = j < nbytes ? marker[j] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, cur, d);
+            if ((int) lane >= d) cur = max(cur, o);
         }
+        cur = max(cur, carry);
+        carry = __shfl_sync(0xffffffffu, cur, 31);
+        bool isref = false;
+        if (cur && j < nbytes) {
+            const uint32_t sgi = cur - 1;
+            const uint32_t o = j - S.seg_rel[sgi];
+            if (o < S.seg_len[sgi]) {
+                isref = true;
+                uint32_t kk = S.seg_k0[sgi] + o, per = S.seg_per[sgi];
+                gptr[j] = S.seg_base[sgi] + (per ? kk % per : kk);
+            }
+        }
+        const uint32_t rm = __ballot_sync(0xffffffffu, isref);
+        const uint32_t valid = nbytes - j0 >= 32 ? 0xFFFFFFFFu : ((1u << (nbytes - j0)) - 1);
+        if (lane == 0) S.lit[j0 >> 5] = ~rm & valid;
     }
     __syncwarp();
     // ---- 5. store the tile's bytes (literal positions are final, the rest is filled by k_resolve)
@@ -238,15 +277,14 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
         uint8_t *dst = V.arena + rec_base + t0;
         uint32_t head = (uint32_t) ((4 - ((uintptr_t) dst & 3)) & 3);
         if (head > nbytes) head = nbytes;
-        if (lane < head) dst[lane] = S.out[lane];
+        if (lane < head) dst[lane] = out8[lane];
         uint32_t nwords = (nbytes - head) >> 2;
         uint32_t *dw = (uint32_t *) (dst + head);
-        for (uint32_t j = lane; j < nwords; j += 32) {
-            const uint8_t *sb = S.out + head + 4 * j;
-            dw[j] = (uint32_t) sb[0] | ((uint32_t) sb[1] << 8) | ((uint32_t) sb[2] << 16) | ((uint32_t) sb[3] << 24);
-        }
+        const uint32_t sh8 = 8 * head;
+        for (uint32_t j = lane; j < nwords; j += 32)
+            dw[j] = head ? __funnelshift_r(S.outw[j], S.outw[j + 1], sh8) : S.outw[j];
         uint32_t tail0 = head + 4 * nwords;
-        if (tail0 + lane < nbytes) dst[tail0 + lane] = S.out[tail0 + lane];
+        if (tail0 + lane < nbytes) dst[tail0 + lane] = out8[tail0 + lane];
         // bitmap: global bit position B0 = rec_base + t0 (zero-initialised map, OR-ed in)
         const uint32_t B0 = rec_base + t0, sh = B0 & 31;
         uint32_t *lm = V.litmap + (B0 >> 5);
@@ -259,31 +297,50 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
     }
 }
 
-// K11: chase every non-literal byte to its literal origin
+// K11: four arena bytes per thread; every non-literal byte chases its pointer chain to a literal
 __global__ void __launch_bounds__(256)
 k_resolve(uint32_t n, uint8_t *__restrict__ arena, uint32_t *__restrict__ ptr, const uint32_t *__restrict__ litmap,
           uint32_t *__restrict__ unfinished, uint32_t *__restrict__ err) {
-    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t i4 = (blockIdx.x * 256 + threadIdx.x) * 4;
     bool pending = false;
-    if (i < n && !((litmap[i >> 5] >> (i & 31)) & 1u)) {
-        uint32_t p = ptr[i];
-        bool done = false;
-        for (int h = 0; h < RESOLVE_HOPS; h++) {
-            if (p >= i) {  // sources always precede their byte in the arena: corrupt input
-                atomicExch(err, 7u);
-                done = true;
-                p = i;
-                break;
+    if (i4 < n) {
+        const uint32_t bits = (litmap[i4 >> 5] >> (i4 & 31)) & 0xFu;
+        if (bits != 0xFu) {
+            uint32_t word = *reinterpret_cast<const uint32_t *>(arena + i4);
+            uint32_t changed = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t i = i4 + b;
+                if (((bits >> b) & 1u) || i >= n) continue;
+                uint32_t p = ptr[i];
+                bool done = false;
+                for (int h = 0; h < RESOLVE_HOPS; h++) {
+                    if (p >= i) {  // sources always precede their byte in the arena: corrupt input
+                        atomicExch(err, 7u);
+                        done = true;
+                        p = i;
+                        break;
+                    }
+                    if ((litmap[p >> 5] >> (p & 31)) & 1u) {
+                        word = (word & ~(0xFFu << (8 * b))) | ((uint32_t) arena[p] << (8 * b));
+                        changed |= 1u << b;
+                        done = true;
+                        break;
+                    }
+                    p = ptr[p];
+                }
+                if (p != i) ptr[i] = p;  // the literal origin, or an ancestor further up the chain
+                pending |= !done;
             }
-            if ((litmap[p >> 5] >> (p & 31)) & 1u) {
-                arena[i] = arena[p];
-                done = true;
-                break;
+            if (changed) {
+                if (i4 + 3 < n) {
+                    *reinterpret_cast<uint32_t *>(arena + i4) = word;
+                } else {
+                    for (int b = 0; b < 4; b++)
+                        if ((changed >> b) & 1u) arena[i4 + b] = (uint8_t) (word >> (8 * b));
+                }
             }
-            p = ptr[p];
         }
-        if (p != i) ptr[i] = p;  // the literal origin, or an ancestor further up the chain
-        pending = !done;
     }
     if (__syncthreads_or(pending) && threadIdx.x == 0) atomicAdd(unfinished, 1u);
 }
@@ -374,7 +431,7 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     // resolve rounds: one is enough unless chains are deeper than RESOLVE_HOPS
     uint32_t h_ctr[2] = {0, 0};
     for (int round = 0; round < 40; round++) {
-        k_resolve<<<(unsigned) div_up<uint64_t>(arena_bytes, 256), 256, 0, st>>>((uint32_t) arena_bytes, arena, dec_ptr.p,
+        k_resolve<<<(unsigned) div_up<uint64_t>(div_up<uint64_t>(arena_bytes, 4), 256), 256, 0, st>>>((uint32_t) arena_bytes, arena, dec_ptr.p,
                                                                                dec_flags.p, dec_ctr.p + 1 + round, dec_ctr.p);
         nl++;
         PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
