@@ -32,14 +32,33 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // doc_len[r] = |esc(k)| + 2 [+ |esc(v)| + 2]; 0xFFFFFFFF marks an empty key (invalid)
 __global__ void __launch_bounds__(256)
 k_doc_len(uint32_t n, const uint8_t *__restrict__ keys, const int64_t *__restrict__ koff,
-          const uint8_t *__restrict__ vals, const int64_t *__restrict__ voff, uint32_t *__restrict__ doc_len) {
+          const uint8_t *__restrict__ vals, const int64_t *__restrict__ voff, uint32_t *__restrict__ doc_len,
+          uint32_t *__restrict__ present /* 256-bit set of the byte values seen (for the dense symbol map) */) {
     uint32_t r = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (r >= n) return;
     const int lane = lane_id();
     int64_t k0 = koff[r], k1 = koff[r + 1], v0 = voff[r], v1 = voff[r + 1];
     uint32_t c = 0;
-    for (int64_t i = k0 + lane; i < k1; i += 32) c += keys[i] == 251;
-    for (int64_t i = v0 + lane; i < v1; i += 32) c += vals[i] == 251;
+    uint32_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = k0 + lane; i < k1; i += 32) {
+        uint8_t b = keys[i];
+        c += b == 251;
+#pragma unroll
+        for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
+    }
+    for (int64_t i = v0 + lane; i < v1; i += 32) {
+        uint8_t b = vals[i];
+        c += b == 251;
+#pragma unroll
+        for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
+    }
+    if (present) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            uint32_t v = __reduce_or_sync(0xffffffffu, seen[w]);
+            if (lane == 0 && v) atomicOr(&present[w], v);
+        }
+    }
     c = warp_sum(c);
     if (lane == 0) {
         uint64_t len = (uint64_t) (k1 - k0) + c + 2 + (v1 > v0 ? (uint64_t) (v1 - v0) + 2 : 0);
@@ -118,27 +137,31 @@ k_write_docs(uint32_t n_new, uint32_t batch_first, uint32_t win_first, const uin
 // ---------------------------------------------------------------------------------
 // K2-K4: suffix array by prefix doubling
 // ---------------------------------------------------------------------------------
-// initial key = first 7 symbols, 9 bits each (byte+1; 0 from the record end on)
+// initial key = the first `nsym` symbols, `bits` bits each: symbol = 1 + rank of the byte among the byte
+// values present in the window (dense, order preserving), 0 from the record end on
 __global__ void __launch_bounds__(256)
-k_init_keys(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, uint32_t n, uint64_t *__restrict__ keys) {
+k_init_keys(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, uint32_t n, int nsym, int bits,
+            const uint8_t *__restrict__ symmap, uint64_t *__restrict__ keys) {
+    __shared__ uint8_t sm[256];
+    sm[threadIdx.x] = symmap[threadIdx.x];
+    __syncthreads();
     uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     uint32_t d = dist[i];
     uint64_t k = 0;
-#pragma unroll
-    for (int j = 0; j < 7; j++) k = (k << 9) | (uint64_t) (j < (int) d ? (uint32_t) text[i + j] + 1u : 0u);
+    for (int j = 0; j < nsym; j++) k = (k << bits) | (uint64_t) (j < (int) d ? (uint32_t) sm[text[i + j]] + 1u : 0u);
     keys[i] = k;
 }
 
 struct HeadFn {
     const uint64_t *keys;
     uint32_t n;
-    int initial;
+    uint64_t initial;  // mask of the last symbol slot in the round that follows the initial sort, else 0
     __device__ __forceinline__ bool operator()(uint32_t a) const {
         if (a == 0 || a >= n) return true;
         uint64_t k = keys[a];
         if (k != keys[a - 1]) return true;
-        return initial && (k & 0x1ff) == 0;  // a suffix that hit its record end is its own group
+        return initial && (k & initial) == 0;  // a suffix that hit its record end is its own group
     }
 };
 
@@ -154,7 +177,19 @@ k_round_keys(uint32_t A, const uint32_t *__restrict__ vals, const uint32_t *__re
 // ---------------------------------------------------------------------------------
 // K5: LCP (Kasai over 32-position segments; restarts cost one direct compare per segment)
 // ---------------------------------------------------------------------------------
-constexpr int LCP_SEG = 32;
+constexpr int LCP_SEG = 16;
+
+// 8 text bytes starting at an arbitrary address: two aligned 8-byte loads + funnel shift
+__device__ __forceinline__ uint64_t load8_unaligned(const uint8_t *__restrict__ p) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t) 7);
+    uint32_t sh = (uint32_t) (a & 7) * 8;
+    uint64_t lo = q[0];
+    if (sh == 0) return lo;
+    uint64_t hi = q[1];
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
 __global__ void __launch_bounds__(128)
 k_lcp(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const uint32_t *__restrict__ sa,
       const uint32_t *__restrict__ rank, uint32_t n, uint32_t *__restrict__ lcp) {
@@ -173,7 +208,16 @@ k_lcp(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const
         uint32_t p = sa[r - 1];
         uint32_t lim = min((uint32_t) dist[i], (uint32_t) dist[p]);
         if (h > lim) h = lim;
-        while (h < lim && text[i + h] == text[p + h]) h++;
+        // extend 8 bytes at a time (the text buffer has 16 bytes of slack past its end)
+        while (h < lim) {
+            uint64_t x = load8_unaligned(text + i + h) ^ load8_unaligned(text + p + h);
+            if (x) {
+                h += (uint32_t) (__ffsll((long long) x) - 1) >> 3;
+                break;
+            }
+            h += 8;
+        }
+        if (h > lim) h = lim;
         lcp[r] = h;
         if (h) h--;
     }
@@ -615,24 +659,36 @@ static void build_suffix_array(Store &S, uint32_t N) {
     int L = 0;
 
     Profiler *PF = S.prof.on ? &S.prof : nullptr;
+    // dense symbol map of the byte values present in the window (always 0, 2 and 251: the terminators)
+    uint8_t h_map[256];
+    int nsymbols = 0;
+    for (int b = 0; b < 256; b++) {
+        h_map[b] = (uint8_t) nsymbols;
+        if ((S.win_present[b >> 5] >> (b & 31)) & 1u) nsymbols++;
+    }
+    int bits = 1;
+    while ((1 << bits) <= nsymbols) bits++;       // symbols 1..nsymbols, 0 = past the record end
+    const int nsym = bits <= 7 ? 8 : 7;            // 56 bits (7 passes) up to 8-bit symbols, else 63 bits (8 passes)
+    E.symmap.reserve_discard(256);
+    PX_CUDA(cudaMemcpyAsync(E.symmap.p, h_map, 256, cudaMemcpyHostToDevice, st));
     S.prof.begin(PC_INIT_KEYS, st);
-    k_init_keys<<<div_up<uint32_t>(N, 256), 256, 0, st>>>(S.w_text.p, S.w_dist.p, N, E.keys0.p);
+    k_init_keys<<<div_up<uint32_t>(N, 256), 256, 0, st>>>(S.w_text.p, S.w_dist.p, N, nsym, bits, E.symmap.p, E.keys0.p);
     S.prof.end(st, 11.0 * N, 1);
     L++;
-    int cur = radix_sort_pairs<uint64_t>(E.keys0.p, E.keys1.p, E.vals0.p, E.vals1.p, N, 0, 63, true, E.rs, E.counters.p + 2, st, &L, PF);
+    int cur = radix_sort_pairs<uint64_t>(E.keys0.p, E.keys1.p, E.vals0.p, E.vals1.p, N, 0, nsym * bits, true, E.rs, E.counters.p + 2, st, &L, PF);
     uint64_t *skeys = cur ? E.keys1.p : E.keys0.p;
     uint32_t *svals = cur ? E.vals1.p : E.vals0.p;
     uint32_t *slot_cur = nullptr;  // nullptr: slot[a] = a (first round)
     uint32_t *slot_next = E.slot0.p;
     uint32_t A = N;
-    uint32_t h = 7;
+    uint32_t h = (uint32_t) nsym;
     const int kb = bits_for(N);
     bool initial = true;
     uint32_t *d_cnt = E.counters.p;
     uint32_t *sa = E.sa.p, *rank = E.rank.p, *gk = E.gk.p;
 
     while (true) {
-        HeadFn head{skeys, A, initial ? 1 : 0};
+        HeadFn head{skeys, A, initial ? ((1ull << bits) - 1) : 0ull};
         S.prof.begin(PC_RANK_SCAN, st);
         // (1) rank of every element = slot of its group head; write sa and rank
         {
@@ -1074,12 +1130,16 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     const auto t_begin = std::chrono::steady_clock::now();
     PX_CUDA(cudaEventRecord(ev0, st));
     doc_len.reserve_discard(nn);
+    es.counters.reserve_discard(16);
+    PX_CUDA(cudaMemsetAsync(es.counters.p + 8, 0, 8 * sizeof(uint32_t), st));
     prof.begin(PC_DOCS, st);
-    k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p);
+    k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p,
+                                                                                    es.counters.p + 8);
     prof.end(st, 0.0, 1);
     launches++;
     std::vector<uint32_t> h_doc_len(nn);
     PX_CUDA(cudaMemcpyAsync(h_doc_len.data(), doc_len.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(batch_present, es.counters.p + 8, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
     for (uint32_t i = 0; i < nn; i++) {
         if (h_doc_len[i] == 0xFFFFFFFFu) {
@@ -1105,6 +1165,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
             if (full) close_window();
         }
         if (!win_open) open_window();
+        for (int w8 = 0; w8 < 8; w8++) win_present[w8] |= batch_present[w8];
         int64_t lim = budget;
         if (ref_policy) {
             // candidates: what the remaining arena is expected to hold (+4% and one record); the exact cut is
@@ -1191,10 +1252,14 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
     const uint32_t nn = (uint32_t) n;
     PX_CUDA(cudaEventRecord(ev0, st));
     doc_len.reserve_discard(nn);
-    k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p);
+    es.counters.reserve_discard(16);
+    PX_CUDA(cudaMemsetAsync(es.counters.p + 8, 0, 8 * sizeof(uint32_t), st));
+    k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p,
+                                                                                    es.counters.p + 8);
     launches++;
     mg_doc_len.resize(nn);
     PX_CUDA(cudaMemcpyAsync(mg_doc_len.data(), doc_len.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(batch_present, es.counters.p + 8, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
     uint64_t batch_bytes = 0;
     for (uint32_t i = 0; i < nn; i++) {
@@ -1211,6 +1276,7 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
         mg_gbytes = 0;
         mg_h_gidx.clear();
     }
+    for (int w8 = 0; w8 < 8; w8++) win_present[w8] |= batch_present[w8];
     // local window = shard records + the whole batch
     const uint32_t first_new = win_R;
     uint64_t bytes = win_N;

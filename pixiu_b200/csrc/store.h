@@ -49,7 +49,7 @@ struct EncodeScratch {
     DevBuf<uint64_t> qoff;
     ScanWorkspace scanws;
     DevBuf<uint32_t> tree_a, tree_l;
-    DevBuf<uint8_t> flagp, flagc;
+    DevBuf<uint8_t> flagp, flagc, symmap;
     DevBuf<uint32_t> leafmask, splitmask, wordpre;
     PinnedBuf<uint32_t> h_leafmask, h_splitmask, h_wordpre;
     DevBuf<uint32_t> counters;  // [0] active count, [1] group count, [2] error flag, [3..] misc
@@ -93,6 +93,7 @@ struct Store {
     // arena state of the reference's suffix tree for the open window (MemPool::nth / used_num)
     uint32_t pool_nth = 1, pool_used = 5;
     double rho = 1.35;  // running estimate of suffix-tree nodes per window byte
+    uint32_t win_present[8] = {0}, batch_present[8] = {0};  // byte values present in the open window / last batch
 
     EncodeScratch es;
     std::unique_ptr<HostIndex> index;
