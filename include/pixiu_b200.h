@@ -112,6 +112,12 @@ int pixiu_record_location(pixiu_store *s, int64_t record, int64_t *chunk, int64_
  * load path of a serialised store.  Returns the chunk id or a negative error. */
 int64_t pixiu_import_chunk(pixiu_store *s, int64_t n, const uint8_t *enc, const int64_t *enc_off);
 
+/* Export one chunk in its wire format — the PiXiu-encoded records back to back plus offsets[count+1] — the
+ * inverse of pixiu_import_chunk (a chunk is self-contained: back references never leave it).  Pass out_cap = 0
+ * to query *count and *need; out_off must hold *count + 1 entries. */
+int pixiu_export_chunk(pixiu_store *s, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *count,
+                       int64_t *need);
+
 /* Decode every record of one chunk (tombstoned included) in idx order. */
 int pixiu_decode_chunk(pixiu_store *s, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *need);
 

@@ -411,6 +411,25 @@ int pixiu_profile_get(pixiu_store *h, int cls, const char **name, double *ms, do
 
 void *pixiu_stream(pixiu_store *h) { return h ? (void *) h->s.st : nullptr; }
 
+int pixiu_export_chunk(pixiu_store *h, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *count,
+                       int64_t *need) {
+    return guarded(h, [&](Store &S) -> int {
+        if (chunk < 0 || chunk >= (int64_t) S.n_chunks() || !count) return PIXIU_EINVAL;
+        const uint32_t g0 = S.chunk_first[chunk], n = S.chunk_count[chunk];
+        *count = n;
+        uint64_t total = 0;
+        for (uint32_t r = 0; r < n; r++) total += S.h_enc_len[g0 + r];
+        if (need) *need = (int64_t) total;
+        if ((int64_t) total > out_cap || !out || !out_off) return PIXIU_ENOSPC;
+        out_off[0] = 0;
+        for (uint32_t r = 0; r < n; r++) out_off[r + 1] = out_off[r] + S.h_enc_len[g0 + r];
+        // the records of a chunk are contiguous in the compressed arena
+        if (total) PX_CUDA(cudaMemcpyAsync(out, S.d_enc.p + S.h_enc_off[g0], total, cudaMemcpyDeviceToHost, S.st));
+        PX_CUDA(cudaStreamSynchronize(S.st));
+        return PIXIU_OK;
+    });
+}
+
 int pixiu_rotate(pixiu_store *h) {
     return guarded(h, [&](Store &S) -> int {
         if (S.win_open) S.close_window();

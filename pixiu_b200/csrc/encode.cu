@@ -175,6 +175,93 @@ k_round_keys(uint32_t A, const uint32_t *__restrict__ vals, const uint32_t *__re
 }
 
 // ---------------------------------------------------------------------------------
+// Segmented sort of the active groups by rank[i+h] (one launch instead of 5-6 radix passes): once no
+// group is larger than GS_MAX the groups are sorted independently — a warp per group of <= 32 members
+// (bitonic network over shuffles), a CTA per larger group (bitonic in shared memory).
+// ---------------------------------------------------------------------------------
+constexpr uint32_t GS_MAX = 2048;
+
+// per group: size; max size -> cnt[3]; ids of the groups with more than 32 members -> large[], count cnt[4]
+__global__ void __launch_bounds__(256)
+k_group_stats(const uint32_t *__restrict__ cnt_in, const uint32_t *__restrict__ goff, uint32_t *__restrict__ cnt,
+              uint32_t *__restrict__ large) {
+    const uint32_t G = cnt_in[1];
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    uint32_t size = g < G ? goff[g + 1] - goff[g] : 0u;
+    if (size > 32) large[atomicAdd(&cnt[4], 1u)] = g;
+    uint32_t m = __reduce_max_sync(0xffffffffu, size);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&cnt[3], m);
+}
+
+__global__ void __launch_bounds__(256)
+k_round_key2(uint32_t A, const uint32_t *__restrict__ vals, const uint32_t *__restrict__ rank, uint32_t h,
+             uint32_t *__restrict__ key2) {
+    uint32_t x = blockIdx.x * 256 + threadIdx.x;
+    if (x < A) key2[x] = rank[vals[x] + h];
+}
+
+// warp per group (size <= 32)
+__global__ void __launch_bounds__(256)
+k_group_sort_small(uint32_t G, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ key2,
+                   const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
+                   uint32_t *__restrict__ vals_out) {
+    const uint32_t g = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (g >= G) return;
+    const uint32_t off = goff[g], size = goff[g + 1] - off;
+    if (size > 32) return;
+    const uint32_t lane = lane_id();
+    uint64_t e = lane < size ? ((uint64_t) key2[off + lane] << 32) | vals[off + lane] : ~0ull;
+#pragma unroll
+    for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            uint64_t o = __shfl_xor_sync(0xffffffffu, e, j);
+            bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            e = (up == lower) ? (e < o ? e : o) : (e > o ? e : o);
+        }
+    }
+    if (lane < size) {
+        keys_out[off + lane] = ((uint64_t) g << kb) | (e >> 32);
+        vals_out[off + lane] = (uint32_t) e;
+    }
+}
+
+// CTA per group (32 < size <= GS_MAX)
+__global__ void __launch_bounds__(256)
+k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ key2,
+                   const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
+                   uint32_t *__restrict__ vals_out) {
+    __shared__ uint64_t sm[GS_MAX];
+    const uint32_t g = large[blockIdx.x];
+    const uint32_t off = goff[g], size = goff[g + 1] - off;
+    uint32_t n2 = 64;
+    while (n2 < size) n2 <<= 1;
+    for (uint32_t i = threadIdx.x; i < n2; i += 256)
+        sm[i] = i < size ? ((uint64_t) key2[off + i] << 32) | vals[off + i] : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < n2 / 2; t += 256) {
+                uint32_t i = 2 * t - (t & (j - 1));  // lower index of the pair (bit j clear)
+                uint32_t p = i + j;
+                uint64_t a = sm[i], b = sm[p];
+                bool up = (i & k) == 0;
+                if ((a > b) == up) {
+                    sm[i] = b;
+                    sm[p] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < size; i += 256) {
+        uint64_t e = sm[i];
+        keys_out[off + i] = ((uint64_t) g << kb) | (e >> 32);
+        vals_out[off + i] = (uint32_t) e;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // K5: LCP (Kasai over 32-position segments; restarts cost one direct compare per segment)
 // ---------------------------------------------------------------------------------
 constexpr int LCP_SEG = 16;
@@ -656,6 +743,9 @@ static void build_suffix_array(Store &S, uint32_t N) {
     E.rank.reserve_discard(N + 8);
     E.counters.reserve_discard(16);
     PX_CUDA(cudaMemsetAsync(E.counters.p, 0, 16 * sizeof(uint32_t), st));
+    E.goff.reserve_discard((size_t) N / 2 + 4);
+    E.glarge.reserve_discard((size_t) N / 32 + 4);
+    E.key2.reserve_discard(N);
     int L = 0;
 
     Profiler *PF = S.prof.on ? &S.prof : nullptr;
@@ -711,6 +801,7 @@ static void build_suffix_array(Store &S, uint32_t N) {
             uint32_t *sl_out = slot_next;
             uint32_t *vals_out = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
             uint32_t An = A;
+            uint32_t *goff = E.goff.p;
             device_scan<uint64_t>(
                 A,
                 [=] __device__(size_t a) -> uint64_t {
@@ -726,18 +817,24 @@ static void build_suffix_array(Store &S, uint32_t N) {
                         sl_out[dst] = sl ? sl[a] : (uint32_t) a;
                         vals_out[dst] = sv[a];
                         gk[dst] = hd ? g : g - 1;
+                        if (hd) goff[g] = dst;  // first member of surviving group g
                     }
                     if (a == An - 1) {
-                        d_cnt[0] = dst + (act ? 1u : 0u);
-                        d_cnt[1] = g + ((act && hd) ? 1u : 0u);
+                        uint32_t At = dst + (act ? 1u : 0u), Gt = g + ((act && hd) ? 1u : 0u);
+                        d_cnt[0] = At;
+                        d_cnt[1] = Gt;
+                        goff[Gt] = At;
                     }
                 },
                 OpSum(), 0ull, true, E.scanws, st);
             L += 1;
             svals = vals_out;  // compacted values (unsorted for the next key) live here now
         }
-        S.prof.end(st, 44.0 * A, 2);
-        uint32_t h_cnt[3];
+        // group sizes: largest group and the list of groups too big for one warp
+        k_group_stats<<<div_up<uint32_t>(A / 2 + 1, 256), 256, 0, st>>>(d_cnt, E.goff.p, d_cnt, E.glarge.p);
+        L++;
+        S.prof.end(st, 44.0 * A, 3);
+        uint32_t h_cnt[5];
         PX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         PX_CUDA(cudaStreamSynchronize(st));
         if (h_cnt[2]) throw std::runtime_error("radix sort look-back timed out");
@@ -745,7 +842,30 @@ static void build_suffix_array(Store &S, uint32_t N) {
         if (getenv("PIXIU_TRACE")) fprintf(stderr, "[sa] N=%u sorted_by=%u active=%u groups=%u\n", N, h, An, G);
         if (An == 0) break;
         if (h > 65535u) throw std::runtime_error("suffix array: groups left after h > 65535");
-        // (3) next keys: (group, rank[i+h]) and sort
+        const uint32_t gmax = h_cnt[3], nlarge = h_cnt[4];
+        PX_CUDA(cudaMemsetAsync(d_cnt + 3, 0, 2 * sizeof(uint32_t), st));
+        if (gmax <= GS_MAX && !getenv("PIXIU_NO_SEGSORT")) {
+            // (3a) every group fits a CTA: sort the groups independently by rank[i+h]
+            uint32_t *vout = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
+            S.prof.begin(PC_ROUND_KEYS, st);
+            k_round_key2<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, svals, rank, h, E.key2.p);
+            S.prof.end(st, 12.0 * An, 1);
+            S.prof.begin(PC_SEG_SORT, st);
+            k_group_sort_small<<<(unsigned) div_up<uint64_t>((uint64_t) G * 32, 256), 256, 0, st>>>(G, E.goff.p, E.key2.p, svals, kb,
+                                                                                              E.keys0.p, vout);
+            if (nlarge) k_group_sort_large<<<nlarge, 256, 0, st>>>(E.glarge.p, E.goff.p, E.key2.p, svals, kb, E.keys0.p, vout);
+            S.prof.end(st, 28.0 * An, nlarge ? 2 : 1);
+            L += nlarge ? 3 : 2;
+            skeys = E.keys0.p;
+            svals = vout;
+            slot_cur = slot_next;
+            slot_next = (slot_next == E.slot0.p) ? E.slot1.p : E.slot0.p;
+            A = An;
+            h *= 2;
+            initial = false;
+            continue;
+        }
+        // (3b) next keys: (group, rank[i+h]) and radix sort
         uint64_t *kin = E.keys0.p, *kalt = E.keys1.p;
         S.prof.begin(PC_ROUND_KEYS, st);
         k_round_keys<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, svals, gk, rank, h, kb, kin);

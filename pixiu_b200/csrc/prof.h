@@ -14,7 +14,8 @@ enum ProfClass {
     PC_SORT_HIST,    // k_rs_histogram + k_rs_scan_bins
     PC_SORT_PASS,    // k_rs_onesweep
     PC_RANK_SCAN,    // head/rank scan + compaction scan of a doubling round
-    PC_ROUND_KEYS,   // k_round_keys
+    PC_ROUND_KEYS,   // k_round_keys / k_round_key2
+    PC_SEG_SORT,     // k_group_sort_small / k_group_sort_large
     PC_LCP,          // k_lcp
     PC_TREE,         // k_tree_level
     PC_LPF,          // k_lpf
@@ -28,7 +29,7 @@ enum ProfClass {
 };
 
 inline const char *prof_class_name(int c) {
-    static const char *names[PC_COUNT] = {"docs", "init_keys", "sort_hist", "sort_pass", "rank_scan", "round_keys", "lcp",
+    static const char *names[PC_COUNT] = {"docs", "init_keys", "sort_hist", "sort_pass", "rank_scan", "round_keys", "seg_sort", "lcp",
                                           "tree", "lpf", "nodes", "flags", "emit", "tables", "decode", "lookup"};
     return c >= 0 && c < PC_COUNT ? names[c] : "?";
 }

@@ -47,6 +47,7 @@ struct EncodeScratch {
     DevBuf<uint64_t> keys0, keys1;
     DevBuf<uint32_t> vals0, vals1, slot0, slot1, gk, sa, rank, lcp, reach, lastnon, prevp, nextp, off;
     DevBuf<uint64_t> qoff;
+    DevBuf<uint32_t> goff, glarge, key2;  // segmented group sort: group offsets, list of big groups, rank[i+h]
     ScanWorkspace scanws;
     DevBuf<uint32_t> tree_a, tree_l;
     DevBuf<uint8_t> flagp, flagc, symmap;

@@ -48,7 +48,7 @@ EXPORTS = [
     "pixiu_getitem_batch", "pixiu_getitem_batch_dev", "pixiu_iter", "pixiu_encoded_view",
     "pixiu_record_location", "pixiu_import_chunk", "pixiu_decode_chunk", "pixiu_rotate",
     "pixiu_profile_enable", "pixiu_profile_get", "pixiu_stream",
-    "pixiu_mg_config", "pixiu_mg_setitem_begin", "pixiu_mg_setitem_mid", "pixiu_mg_setitem_end",
+    "pixiu_export_chunk", "pixiu_mg_config", "pixiu_mg_setitem_begin", "pixiu_mg_setitem_mid", "pixiu_mg_setitem_end",
 ]
 
 _lib = None
@@ -83,6 +83,7 @@ def load_library():
     L.pixiu_import_chunk.restype = C.c_int64
     L.pixiu_decode_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p]
     L.pixiu_rotate.argtypes = [C.c_void_p]
+    L.pixiu_export_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p, _i64p]
     L.pixiu_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.pixiu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), _i64p]
@@ -346,6 +347,18 @@ class PiXiuCtrl:
     def import_chunk(self, encs) -> int:
         ed, eo = encs if isinstance(encs, tuple) else _pack(encs)
         return self._check(self._L.pixiu_import_chunk(self._h, len(eo) - 1, _ptr(ed), _ptr(eo)))
+
+    def export_chunk(self, chunk: int):
+        """-> (enc u8[], off i64[n+1]): the chunk's wire format (feeds import_chunk of another store)"""
+        count, need = C.c_int64(0), C.c_int64(0)
+        rc = self._L.pixiu_export_chunk(self._h, chunk, None, 0, None, C.byref(count), C.byref(need))
+        if rc not in (OK, ENOSPC):
+            self._check(rc)
+        buf = np.zeros(max(need.value, 1), dtype=np.uint8)
+        off = np.zeros(count.value + 1, dtype=np.int64)
+        self._check(self._L.pixiu_export_chunk(self._h, chunk, _ptr(buf), buf.size, off.ctypes.data_as(_i64p),
+                                               C.byref(count), C.byref(need)))
+        return buf[:need.value], off
 
     def decode_chunk(self, chunk: int):
         n_off = 65536 + 1

@@ -339,3 +339,25 @@ def test_sharded_window_equals_unsharded_oracle(ctrl_mod, name, world):
             assert ctrl_mod.split_doc(buf[off[i]:off[i + 1]].tobytes()) == (k, latest[k])
     for s in stores:
         s.free_prop()
+
+
+def test_export_import_roundtrip(ctrl_mod):
+    """wire format: chunks exported from one store load into another and serve the same records"""
+    kd, ko, vd, vo = synth.gen_urls_kv(3000, seed=9)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    a = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=120000)
+    a.setitem_batch((kd, ko), (vd, vo))
+    nchunks = a.stats().chunks
+    assert nchunks >= 3
+    b = ctrl_mod.PiXiuCtrl()
+    for c in range(nchunks):
+        enc, off = a.export_chunk(c)
+        assert b.import_chunk((enc, off)) == c
+    assert b.stats().records == a.stats().records and b.stats().encoded_bytes == a.stats().encoded_bytes
+    buf, off, found = b.getitem_batch((kd, ko))
+    assert found.all()
+    for i in range(0, len(keys), 7):
+        assert ctrl_mod.split_doc(buf[off[i]:off[i + 1]].tobytes()) == (keys[i], vals[i])
+    assert not b.contains(b"http://absent")
+    a.free_prop()
+    b.free_prop()
