@@ -361,3 +361,45 @@ def test_export_import_roundtrip(ctrl_mod):
     assert not b.contains(b"http://absent")
     a.free_prop()
     b.free_prop()
+
+
+def test_api_edge_cases(ctrl_mod):
+    """empty store / empty batch, duplicates inside one batch (in-order semantics), key-only records,
+    keys that are prefixes of each other, binary keys full of 251 / 0 / 2, deleted keys"""
+    c = ctrl_mod.PiXiuCtrl()
+    # empty store (CritBitTree.cpp:154-196,:271-274: NULL / false / not found)
+    assert not c.contains(b"x") and c.getitem(b"x") is None and c.iter(b"") is None and c.delitem(b"x") == 1
+    rc, saved = c.setitem_batch([], [])
+    assert len(rc) == 0 and c.stats().records == 0
+    assert c.contains_batch([]).tolist() == [] and c.delitem_batch([]).tolist() == []
+    # duplicates inside one batch: later wins, rc tells which calls replaced
+    rc, _ = c.setitem_batch([b"k", b"k", b"j", b"k"], [b"v1", b"v2", b"w", b"v3"])
+    assert rc.tolist() == [0, 1, 0, 1]
+    assert ctrl_mod.split_doc(c.getitem(b"k").bytes()) == (b"k", b"v3")
+    assert c.stats().records == 4 and c.stats().live_records == 2
+    # key-only records (PiXiuCtrl.cpp:41-44) and keys that are prefixes of each other
+    rc, _ = c.setitem_batch([b"a", b"ab", b"abc", b"b"], [b"", b"1", b"", b"2"])
+    assert rc.tolist() == [0, 0, 0, 0]
+    assert c.getitem(b"a").bytes() == b"a\xfb\x00" and c.getitem(b"ab").bytes() == b"ab\xfb\x001\xfb\x02"
+    # iteration order is byte order on esc(key) 251 0: "abc" < "ab" < "a" (251 sorts above 'b' and 'c')
+    assert [ctrl_mod.split_doc(d)[0] for d in c.iter_docs(b"a")] == [b"abc", b"ab", b"a"]
+    assert [ctrl_mod.split_doc(d)[0] for d in c.iter_docs(b"")] == [b"abc", b"ab", b"a", b"b", b"j", b"k"]
+    assert c.iter_docs(b"zz") == [] and c.iter_docs(b"abcd") == []
+    # binary keys/values made of the special bytes, incl. the case the reference loses (bug B5)
+    bk = [bytes([251]), bytes([251, 251]), bytes([251, 0]), bytes([0]), bytes([2, 251, 0, 251]), b"a\xfb", b"a\xfb\xfb"]
+    bv = [bytes([0, 2, 251]) * 5, bytes([251]) * 9, b"", bytes([251, 0, 251, 2]), bytes([2]), b"x", bytes([251])]
+    rc, _ = c.setitem_batch(bk, bv)
+    assert rc.tolist() == [0] * len(bk)
+    buf, off, found = c.getitem_batch(bk)
+    assert found.all()
+    for i in range(len(bk)):
+        assert ctrl_mod.split_doc(buf[off[i]:off[i + 1]].tobytes()) == (bk[i], bv[i])
+        assert buf[off[i]:off[i + 1]].tobytes() == po.make_doc(bk[i], bv[i])
+    assert c.contains_batch([bytes([251, 251, 251]), bytes([251, 2]), b"a"]).tolist() == [False, False, True]
+    # delete, then the key is gone but the record bytes stay referencable
+    assert c.delitem_batch([b"ab", b"ab", bytes([251])]).tolist() == [0, 1, 0]
+    assert c.getitem(b"ab") is None and not c.contains(bytes([251]))
+    rc, _ = c.setitem_batch([b"ab"], [b"1"])  # re-insert after delete: a new key again
+    assert rc.tolist() == [0]
+    assert c.stats().live_records == len(c.iter_docs(b""))
+    c.free_prop()
