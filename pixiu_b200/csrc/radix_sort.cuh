@@ -18,7 +18,7 @@ namespace pixiu {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // keys per CTA
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
 constexpr uint32_t RS_FLAG_AGG = 1u << 30;
@@ -75,7 +75,7 @@ k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, con
     __shared__ uint32_t warp_hist[RS_WARPS][RS_BINS];  // per-warp digit counts, then exclusive warp prefixes
     __shared__ uint32_t digit_start[RS_BINS];          // first tile-local slot of each digit
     __shared__ uint32_t adj[RS_BINS];                  // global position of slot j of digit d = adj[d] + j
-    __shared__ uint32_t warp_tot[RS_WARPS];
+    __shared__ uint32_t warp_tot[RS_BINS / 32];
     __shared__ uint32_t s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
@@ -108,15 +108,19 @@ k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, con
         off[k] = (uint16_t) (c + __popc(m & lt_mask));
     }
     __syncthreads();
-    // digit `t`: exclusive prefix over the warps, tile total, tile-local digit start, decoupled look-back
+    // digit `t` (threads 0..255): exclusive prefix over the warps, tile total, tile-local digit start,
+    // decoupled look-back.  The other threads only take part in the barriers.
     {
         const int t = threadIdx.x;
+        const bool dig = t < RS_BINS;
         uint32_t run = 0;
+        if (dig) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            uint32_t c = warp_hist[w][t];
-            warp_hist[w][t] = run;
-            run += c;
+            for (int w = 0; w < RS_WARPS; w++) {
+                uint32_t c = warp_hist[w][t];
+                warp_hist[w][t] = run;
+                run += c;
+            }
         }
         // exclusive scan of `run` over the 256 digits
         uint32_t inc = run;
@@ -125,49 +129,51 @@ k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, con
             uint32_t o = __shfl_up_sync(0xffffffffu, inc, dd);
             if (lane >= dd) inc += o;
         }
-        if (lane == 31) warp_tot[warp] = inc;
+        if (dig && lane == 31) warp_tot[warp] = inc;
         __syncthreads();
-        uint32_t wpre = 0;
+        if (dig) {
+            uint32_t wpre = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) wpre += (w < warp) ? warp_tot[w] : 0u;
-        const uint32_t dstart = wpre + inc - run;
-        digit_start[t] = dstart;
+            for (int w = 0; w < RS_BINS / 32; w++) wpre += (w < warp) ? warp_tot[w] : 0u;
+            const uint32_t dstart = wpre + inc - run;
+            digit_start[t] = dstart;
 
-        uint32_t *mine = status + (size_t) tile * RS_BINS + t;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            st_relaxed_u32(mine, RS_FLAG_PREFIX | run);
-        } else {
-            st_relaxed_u32(mine, RS_FLAG_AGG | run);
-            // look back RS_LOOK predecessors at a time (independent relaxed loads overlap): the first wave
-            // of tiles runs in lock step and would otherwise walk hundreds of rows one round trip each
-            int64_t look = (int64_t) tile - 1;
-            uint32_t spins = 0;
-            bool done = false;
-            while (!done && look >= 0) {
-                uint32_t sv[RS_LOOK];
+            uint32_t *mine = status + (size_t) tile * RS_BINS + t;
+            uint32_t excl = 0;
+            if (tile == 0) {
+                st_relaxed_u32(mine, RS_FLAG_PREFIX | run);
+            } else {
+                st_relaxed_u32(mine, RS_FLAG_AGG | run);
+                // look back RS_LOOK predecessors at a time (independent relaxed loads overlap): the first wave
+                // of tiles runs in lock step and would otherwise walk hundreds of rows one round trip each
+                int64_t look = (int64_t) tile - 1;
+                uint32_t spins = 0;
+                bool done = false;
+                while (!done && look >= 0) {
+                    uint32_t sv[RS_LOOK];
 #pragma unroll
-                for (int b = 0; b < RS_LOOK; b++)
-                    sv[b] = look - b >= 0 ? ld_relaxed_u32(status + (size_t) (look - b) * RS_BINS + t) : RS_FLAG_PREFIX;
-                int used = 0;
+                    for (int b = 0; b < RS_LOOK; b++)
+                        sv[b] = look - b >= 0 ? ld_relaxed_u32(status + (size_t) (look - b) * RS_BINS + t) : RS_FLAG_PREFIX;
+                    int used = 0;
 #pragma unroll
-                for (int b = 0; b < RS_LOOK; b++) {
-                    if (done || used != b) continue;
-                    uint32_t flag = sv[b] & ~RS_VALUE_MASK;
-                    if (flag == 0) continue;  // not published yet: retry from here
-                    excl += sv[b] & RS_VALUE_MASK;
-                    used = b + 1;
-                    if (flag == RS_FLAG_PREFIX) done = true;
+                    for (int b = 0; b < RS_LOOK; b++) {
+                        if (done || used != b) continue;
+                        uint32_t flag = sv[b] & ~RS_VALUE_MASK;
+                        if (flag == 0) continue;  // not published yet: retry from here
+                        excl += sv[b] & RS_VALUE_MASK;
+                        used = b + 1;
+                        if (flag == RS_FLAG_PREFIX) done = true;
+                    }
+                    look -= used;
+                    if (used == 0 && ++spins > RS_SPIN_LIMIT) {
+                        atomicExch(err, 1u);
+                        break;
+                    }
                 }
-                look -= used;
-                if (used == 0 && ++spins > RS_SPIN_LIMIT) {
-                    atomicExch(err, 1u);
-                    break;
-                }
+                st_relaxed_u32(mine, RS_FLAG_PREFIX | (excl + run));
             }
-            st_relaxed_u32(mine, RS_FLAG_PREFIX | (excl + run));
+            adj[t] = bin_base[t] + excl - dstart;
         }
-        adj[t] = bin_base[t] + excl - dstart;
     }
     __syncthreads();
     // re-order the tile by digit in shared memory
