@@ -230,8 +230,16 @@ def run_ours(args, rank, world, local_rank):
     top = max((k for k in prof if prof[k]["launches"]), key=lambda k: prof[k]["ms"])
     tp = prof[top]
     ach = tp["bytes"] / 1e9 / (tp["ms"] / 1e3) if tp["ms"] else 0.0
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/
+    # r01_onesweep_12Mkeys_ncu_raw.csv): 150.06 MB read + 100.93 MB written per launch of 12 M keys, i.e.
+    # 0.871 x the algorithmic n x 24 B (L2 absorbs part of the scatter); scaled to this run's average launch.
+    NCU_TRAFFIC_OVER_ALGORITHMIC = {"sort_pass": (150.06e6 + 100.93e6) / (12e6 * 24)}
+    traffic = None
+    if top in NCU_TRAFFIC_OVER_ALGORITHMIC and tp["launches"]:
+        traffic = NCU_TRAFFIC_OVER_ALGORITHMIC[top] * tp["bytes"] / tp["launches"]
     roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "launches": tp["launches"],
+                "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": tp["bytes"] / max(tp["launches"], 1),
+                "launches": tp["launches"],
                 "avg_launch_ms": tp["ms"] / max(tp["launches"], 1), "share_of_step": tp["ms"] / tot_ms,
                 "classes_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}}
 

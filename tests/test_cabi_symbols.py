@@ -48,3 +48,16 @@ def test_generator_protocol():
     docs = [x.bytes() for x in it]
     assert [split_doc(d) for d in docs] == [(b"k", b"v"), (b"l", b"")]
     assert split_doc(b"\xfb\xfb\xfb\x00x\xfb\xfb\xfb\x02") == (b"\xfb", b"x\xfb")
+
+
+def test_fails_loudly_without_a_gpu():
+    """no CPU fallback: on a machine without a CUDA device the store cannot even be created"""
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pixiu_b200 import ctrl
+
+    with pytest.raises(ctrl.PiXiuError):
+        ctrl.PiXiuCtrl()
