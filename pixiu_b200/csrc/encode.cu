@@ -780,42 +780,34 @@ static void build_suffix_array(Store &S, uint32_t N) {
     while (true) {
         HeadFn head{skeys, A, initial ? ((1ull << bits) - 1) : 0ull};
         S.prof.begin(PC_RANK_SCAN, st);
-        // (1) rank of every element = slot of its group head; write sa and rank
-        {
-            const uint32_t *sl = slot_cur;
-            const uint32_t *sv = svals;
-            device_scan<uint32_t>(
-                A, [=] __device__(size_t a) -> uint32_t { return head((uint32_t) a) ? (uint32_t) a : 0u; },
-                [=] __device__(size_t a, uint32_t hp) {
-                    uint32_t v = sv[a];
-                    sa[sl ? sl[a] : (uint32_t) a] = v;
-                    rank[v] = sl ? sl[hp] : hp;
-                },
-                OpMax(), 0u, false, E.scanws, st);
-            L += 1;
-        }
-        // (2) keep the elements of groups larger than one; number the surviving groups
+        // (1)+(2) one pass, two scans: the inclusive MAX of "index+1 of the latest group head" gives every
+        // element the slot of its group head (its rank; written with sa), the exclusive SUM of
+        // (active, active head) compacts the members of groups larger than one and numbers those groups
         {
             const uint32_t *sl = slot_cur;
             const uint32_t *sv = svals;
             uint32_t *sl_out = slot_next;
             uint32_t *vals_out = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
-            uint32_t An = A;
+            const uint32_t An = A;
             uint32_t *goff = E.goff.p;
-            device_scan<uint64_t>(
+            device_scan_dual(
                 A,
-                [=] __device__(size_t a) -> uint64_t {
+                [=] __device__(size_t a, uint32_t &m, unsigned long long &sm) {
                     bool hd = head((uint32_t) a), hn = head((uint32_t) a + 1);
                     bool act = !(hd && hn);
-                    return act ? (1ull | ((uint64_t) hd << 32)) : 0ull;
+                    m = hd ? (uint32_t) a + 1u : 0u;
+                    sm = act ? (1ull | ((unsigned long long) hd << 32)) : 0ull;
                 },
-                [=] __device__(size_t a, uint64_t ex) {
-                    bool hd = head((uint32_t) a), hn = head((uint32_t) a + 1);
-                    bool act = !(hd && hn);
-                    uint32_t dst = (uint32_t) ex, g = (uint32_t) (ex >> 32);
+                [=] __device__(size_t a, uint32_t hp1, unsigned long long ex, uint32_t m, unsigned long long sm) {
+                    const uint32_t hp = hp1 - 1;  // index of the group head (element 0 is always a head)
+                    const uint32_t v = sv[a];
+                    sa[sl ? sl[a] : (uint32_t) a] = v;
+                    rank[v] = sl ? sl[hp] : hp;
+                    const bool act = sm & 1ull, hd = m != 0;
+                    const uint32_t dst = (uint32_t) ex, g = (uint32_t) (ex >> 32);
                     if (act) {
                         sl_out[dst] = sl ? sl[a] : (uint32_t) a;
-                        vals_out[dst] = sv[a];
+                        vals_out[dst] = v;
                         gk[dst] = hd ? g : g - 1;
                         if (hd) goff[g] = dst;  // first member of surviving group g
                     }
@@ -826,14 +818,14 @@ static void build_suffix_array(Store &S, uint32_t N) {
                         goff[Gt] = At;
                     }
                 },
-                OpSum(), 0ull, true, E.scanws, st);
+                E.scanws, st);
             L += 1;
             svals = vals_out;  // compacted values (unsorted for the next key) live here now
         }
         // group sizes: largest group and the list of groups too big for one warp
         k_group_stats<<<div_up<uint32_t>(A / 2 + 1, 256), 256, 0, st>>>(d_cnt, E.goff.p, d_cnt, E.glarge.p);
         L++;
-        S.prof.end(st, 44.0 * A, 3);
+        S.prof.end(st, 36.0 * A, 2);
         uint32_t h_cnt[5];
         PX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         PX_CUDA(cudaStreamSynchronize(st));

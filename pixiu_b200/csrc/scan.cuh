@@ -18,6 +18,19 @@ constexpr unsigned long long SCAN_FLAG_PREFIX = 2ull << 62;
 constexpr unsigned long long SCAN_VALUE_MASK = (1ull << 62) - 1;
 constexpr uint32_t SCAN_SPIN_LIMIT = 1u << 27;
 
+struct OpSum {
+    template <typename T>
+    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
+};
+struct OpMax {
+    template <typename T>
+    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; }
+};
+struct OpMin {
+    template <typename T>
+    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a < b ? a : b; }
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -123,28 +136,118 @@ k_scan_lookback(size_t n, InFn in, OutFn out, Op op, T identity, int exclusive, 
         pre = inc;
     }
 }
-#endif  // __CUDACC__
 
-struct OpSum {
-    template <typename T>
-    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
-};
-struct OpMax {
-    template <typename T>
-    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; }
-};
-struct OpMin {
-    template <typename T>
-    __host__ __device__ __forceinline__ T operator()(T a, T b) const { return a < b ? a : b; }
-};
+// Two scans over the same input pass: an inclusive MAX of a u32 and an exclusive SUM of a u64 (the round
+// finish of the suffix-array construction needs both from the same predicate).  in(i, m, s) produces the
+// two inputs, out(i, max_incl, sum_excl, m, s) consumes the results together with the element's own inputs.
+template <typename InFn, typename OutFn>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_dual(size_t n, InFn in, OutFn out, unsigned long long *__restrict__ status_m, unsigned long long *__restrict__ status_s,
+            uint32_t *__restrict__ ticket, uint32_t *__restrict__ err) {
+    __shared__ uint32_t sm_m[33];
+    __shared__ unsigned long long sm_s[33];
+    __shared__ uint32_t s_pm;
+    __shared__ unsigned long long s_ps;
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const size_t base = (size_t) tile * SCAN_TILE + (size_t) threadIdx.x * SCAN_ITEMS;
+    uint32_t vm[SCAN_ITEMS];
+    unsigned long long vs[SCAN_ITEMS];
+    uint32_t am = 0;
+    unsigned long long as = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        vm[k] = 0;
+        vs[k] = 0;
+        if (base + k < n) in(base + k, vm[k], vs[k]);
+        am = max(am, vm[k]);
+        as += vs[k];
+    }
+    uint32_t tot_m;
+    unsigned long long tot_s;
+    uint32_t pre_m = block_scan_exclusive(am, OpMax(), 0u, sm_m, &tot_m);
+    unsigned long long pre_s = block_scan_exclusive(as, OpSum(), 0ull, sm_s, &tot_s);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+        // warp 0 resolves the MAX prefix, warp 1 the SUM prefix (same look-back as k_scan_lookback)
+        unsigned long long *status = warp == 0 ? status_m : status_s;
+        const unsigned long long mine = warp == 0 ? (unsigned long long) tot_m : tot_s;
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed_u64(status, SCAN_FLAG_PREFIX | mine);
+        } else {
+            if (lane == 0) st_relaxed_u64(status + tile, SCAN_FLAG_AGG | mine);
+            int64_t look = (int64_t) tile - 1 - lane;
+            while (true) {
+                unsigned long long sv = SCAN_FLAG_PREFIX;  // before tile 0: identity (0 for both scans)
+                if (look >= 0) {
+                    uint32_t spins = 0;
+                    while (((sv = ld_relaxed_u64(status + look)) >> 62) == 0) {
+                        if (++spins > SCAN_SPIN_LIMIT) {
+                            atomicExch(err, 1u);
+                            sv = SCAN_FLAG_PREFIX;
+                            break;
+                        }
+                    }
+                }
+                const uint32_t pm = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                const int first = pm ? __ffs(pm) - 1 : 31;
+                unsigned long long contrib = lane <= first ? (sv & SCAN_VALUE_MASK) : 0ull;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    unsigned long long o = __shfl_xor_sync(0xffffffffu, contrib, d);
+                    contrib = warp == 0 ? (contrib > o ? contrib : o) : contrib + o;
+                }
+                excl = warp == 0 ? (excl > contrib ? excl : contrib) : excl + contrib;
+                if (pm) break;
+                look -= 32;
+            }
+            const unsigned long long incl = warp == 0 ? (excl > mine ? excl : mine) : excl + mine;
+            if (lane == 0) st_relaxed_u64(status + tile, SCAN_FLAG_PREFIX | incl);
+        }
+        if (lane == 0) {
+            if (warp == 0) s_pm = (uint32_t) excl;
+            else s_ps = excl;
+        }
+    }
+    __syncthreads();
+    pre_m = max(pre_m, s_pm);
+    pre_s += s_ps;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        pre_m = max(pre_m, vm[k]);
+        if (base + k < n) out(base + k, pre_m, pre_s, vm[k], vs[k]);
+        pre_s += vs[k];
+    }
+}
+#endif  // __CUDACC__
 
 // workspace shared by all scans of a store (status words + ticket + sticky error flag)
 struct ScanWorkspace {
-    DevBuf<unsigned long long> status;
+    DevBuf<unsigned long long> status, status2;
     DevBuf<uint32_t> ctl;  // [0] ticket, [1] error
 };
 
 #ifdef __CUDACC__
+template <typename InFn, typename OutFn>
+void device_scan_dual(size_t n, InFn in, OutFn out, ScanWorkspace &ws, cudaStream_t st) {
+    if (n == 0) return;
+    unsigned tiles = (unsigned) div_up<size_t>(n, SCAN_TILE);
+    ws.status.reserve_discard(tiles + 1);
+    ws.status2.reserve_discard(tiles + 1);
+    if (!ws.ctl.p) {
+        ws.ctl.reserve_discard(4);
+        PX_CUDA(cudaMemsetAsync(ws.ctl.p, 0, 4 * sizeof(uint32_t), st));
+    }
+    PX_CUDA(cudaMemsetAsync(ws.status.p, 0, (size_t) tiles * sizeof(unsigned long long), st));
+    PX_CUDA(cudaMemsetAsync(ws.status2.p, 0, (size_t) tiles * sizeof(unsigned long long), st));
+    PX_CUDA(cudaMemsetAsync(ws.ctl.p, 0, sizeof(uint32_t), st));
+    k_scan_dual<<<tiles, SCAN_THREADS, 0, st>>>(n, in, out, ws.status.p, ws.status2.p, ws.ctl.p, ws.ctl.p + 1);
+    PX_LAUNCH_CHECK();
+}
+
 template <typename T, typename Op, typename InFn, typename OutFn>
 void device_scan(size_t n, InFn in, OutFn out, Op op, T identity, bool exclusive, ScanWorkspace &ws, cudaStream_t st) {
     if (n == 0) return;
