@@ -11,6 +11,7 @@ namespace pixiu {
 Store::~Store() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev_nodes) cudaEventDestroy(ev_nodes);
     if (st) cudaStreamDestroy(st);
 }
 
@@ -20,13 +21,15 @@ void Store::init(const pixiu_config &c) {
     PX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     PX_CUDA(cudaEventCreate(&ev0));
     PX_CUDA(cudaEventCreate(&ev1));
+    PX_CUDA(cudaEventCreateWithFlags(&ev_nodes, cudaEventDisableTiming));
+    PX_CUDA(cudaFree(nullptr));  // make sure the primary context exists before the driver-API calls
+    d_enc.init(cfg.device, 256ull << 30);
     index.reset(new HostIndex());
 }
 
 void Store::grow_record_tables(size_t n_total, uint64_t enc_total, uint64_t tiles_total) {
     const size_t n_old = n_records();
-    // the compressed arena starts at 1 GiB and doubles: re-allocating GBs (cudaMalloc + copy + cudaFree) stalls ingest
-    d_enc.reserve_keep(std::max<uint64_t>(enc_total + 64, d_enc.cap ? 0 : (1ull << 30)), enc_bytes, st);
+    d_enc.ensure(enc_total + 4096);  // maps more physical memory behind the reserved range; nothing moves
     // record tables start at 1 M records / 4 M tiles (a few MB): every re-allocation is a cudaMalloc + copy +
     // stream sync + cudaFree, which stalls ingest for milliseconds
     const size_t rmin = d_enc_off.cap ? 0 : (1u << 20), tmin = d_tile_desc.cap ? 0 : (4u << 20);
@@ -297,7 +300,7 @@ int pixiu_encoded_view(pixiu_store *h, int64_t chunk, int64_t idx, uint8_t *out,
         uint32_t g = S.chunk_first[chunk] + (uint32_t) idx;
         uint32_t len = S.h_enc_len[g];
         if ((int64_t) len > out_cap) return PIXIU_ENOSPC;
-        PX_CUDA(cudaMemcpyAsync(out, S.d_enc.p + S.h_enc_off[g], len, cudaMemcpyDeviceToHost, S.st));
+        PX_CUDA(cudaMemcpyAsync(out, S.d_enc.ptr() + S.h_enc_off[g], len, cudaMemcpyDeviceToHost, S.st));
         PX_CUDA(cudaStreamSynchronize(S.st));
         return (int) len;
     });
@@ -424,7 +427,7 @@ int pixiu_export_chunk(pixiu_store *h, int64_t chunk, uint8_t *out, int64_t out_
         out_off[0] = 0;
         for (uint32_t r = 0; r < n; r++) out_off[r + 1] = out_off[r] + S.h_enc_len[g0 + r];
         // the records of a chunk are contiguous in the compressed arena
-        if (total) PX_CUDA(cudaMemcpyAsync(out, S.d_enc.p + S.h_enc_off[g0], total, cudaMemcpyDeviceToHost, S.st));
+        if (total) PX_CUDA(cudaMemcpyAsync(out, S.d_enc.ptr() + S.h_enc_off[g0], total, cudaMemcpyDeviceToHost, S.st));
         PX_CUDA(cudaStreamSynchronize(S.st));
         return PIXIU_OK;
     });

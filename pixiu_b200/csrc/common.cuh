@@ -1,5 +1,6 @@
 // Common host/device helpers for the pixiu_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -8,6 +9,7 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace pixiu {
 
@@ -66,6 +68,93 @@ struct DevBuf {
         }
         p = q;
         cap = want;
+    }
+};
+
+// Growable device arena without re-allocation: a large virtual range is reserved once and physical memory is
+// mapped behind it in 256 MiB steps (CUDA virtual memory management).  Growing never copies, never frees and
+// never moves the data, so pointers handed to kernels stay valid and ingest never stalls on a multi-GB realloc.
+struct VmArena {
+    // driver entry points are resolved through the runtime (cudaGetDriverEntryPoint): the library does not
+    // link libcuda, so it still loads (and reports its symbols) on a machine without a driver
+    struct Drv {
+        CUresult (*GetGran)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+        CUresult (*Reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+        CUresult (*Create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+        CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+        CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+        CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+        CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+        CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+        template <typename F>
+        static void get(const char *name, F &fn) {
+            void *p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            PX_CUDA(cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q));
+            if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error(std::string("driver entry point not found: ") + name);
+            fn = reinterpret_cast<F>(p);
+        }
+        void load() {
+            if (Reserve) return;
+            get("cuMemGetAllocationGranularity", GetGran);
+            get("cuMemAddressReserve", Reserve);
+            get("cuMemCreate", Create);
+            get("cuMemMap", Map);
+            get("cuMemSetAccess", SetAccess);
+            get("cuMemUnmap", Unmap);
+            get("cuMemRelease", Release);
+            get("cuMemAddressFree", AddressFree);
+        }
+    } drv;
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0, gran = 0;
+    int device = 0;
+    std::vector<CUmemGenericAllocationHandle> handles;
+    static constexpr size_t STEP = 256ull << 20;
+    VmArena() = default;
+    VmArena(const VmArena &) = delete;
+    VmArena &operator=(const VmArena &) = delete;
+    static void check(CUresult r, const char *what) {
+        if (r != CUDA_SUCCESS) throw std::runtime_error(std::string(what) + " failed with CUresult " + std::to_string((int) r));
+    }
+    uint8_t *ptr() const { return reinterpret_cast<uint8_t *>(base); }
+    CUmemAllocationProp prop() const {
+        CUmemAllocationProp p = {};
+        p.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        p.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        p.location.id = device;
+        return p;
+    }
+    void init(int dev, size_t reserve_bytes) {
+        device = dev;
+        drv.load();
+        CUmemAllocationProp p = prop();
+        check(drv.GetGran(&gran, &p, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED), "cuMemGetAllocationGranularity");
+        reserved = (reserve_bytes + STEP - 1) / STEP * STEP;
+        check(drv.Reserve(&base, reserved, 0, 0, 0), "cuMemAddressReserve");
+    }
+    // make bytes [0, n) usable
+    void ensure(size_t n) {
+        if (n <= mapped) return;
+        if (n > reserved) throw std::runtime_error("VmArena: reserved range exhausted");
+        CUmemAllocationProp p = prop();
+        CUmemAccessDesc acc = {};
+        acc.location = p.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        while (mapped < n) {
+            CUmemGenericAllocationHandle h;
+            check(drv.Create(&h, STEP, &p, 0), "cuMemCreate");
+            check(drv.Map(base + mapped, STEP, 0, h, 0), "cuMemMap");
+            check(drv.SetAccess(base + mapped, STEP, &acc, 1), "cuMemSetAccess");
+            handles.push_back(h);
+            mapped += STEP;
+        }
+    }
+    ~VmArena() {
+        if (!base) return;
+        if (mapped) drv.Unmap(base, mapped);
+        for (auto h : handles) drv.Release(h);
+        drv.AddressFree(base, reserved);
     }
 };
 

@@ -415,7 +415,7 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     dec_ctr.reserve_discard(64);
     PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));
     PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, (arena_bytes / 32 + 2) * sizeof(uint32_t), st));
-    DecodeView V{d_enc.p, d_enc_off.p, d_enc_len.p, d_dec_len.p, d_first.p, d_tile_base.p, d_tile_desc.p,
+    DecodeView V{d_enc.ptr(), d_enc_off.p, d_enc_len.p, d_dec_len.p, d_first.p, d_tile_base.p, d_tile_desc.p,
                  dec_aoff.p, arena, dec_ptr.p, dec_flags.p};
     const size_t smem = sizeof(WarpSmem) * DEC_WARPS;
     static bool attr_set = false;
@@ -554,7 +554,7 @@ int64_t Store::import_chunk(int64_t n, const uint8_t *enc, const int64_t *enc_of
         h_tile_base.push_back(tbase[r]);
         h_live.push_back(1);
     }
-    PX_CUDA(cudaMemcpyAsync(d_enc.p + enc_bytes, enc + enc_off[0], bytes, cudaMemcpyHostToDevice, st));
+    PX_CUDA(cudaMemcpyAsync(d_enc.ptr() + enc_bytes, enc + enc_off[0], bytes, cudaMemcpyHostToDevice, st));
     PX_CUDA(cudaMemcpyAsync(d_enc_off.p + g0, h_enc_off.data() + g0, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     PX_CUDA(cudaMemcpyAsync(d_enc_len.p + g0, h_enc_len.data() + g0, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     PX_CUDA(cudaMemcpyAsync(d_dec_len.p + g0, h_dec_len.data() + g0, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -565,6 +565,7 @@ int64_t Store::import_chunk(int64_t n, const uint8_t *enc, const int64_t *enc_of
     PX_CUDA(cudaStreamSynchronize(st));
     enc_bytes += bytes;
     n_tiles = tiles;
+    mirror_from = n_records();
     return (int64_t) chunk_first.size() - 1;
 }
 

@@ -741,8 +741,10 @@ static void build_suffix_array(Store &S, uint32_t N) {
     E.gk.reserve_discard(N);
     E.sa.reserve_discard(N);
     E.rank.reserve_discard(N + 8);
-    E.counters.reserve_discard(16);
-    PX_CUDA(cudaMemsetAsync(E.counters.p, 0, 16 * sizeof(uint32_t), st));
+    // [0] active count, [1] group count, [2] sticky error flag (cleared by flush_mirrors), [3] largest group,
+    // [4] number of big groups, [8..15] byte presence set of the batch
+    PX_CUDA(cudaMemsetAsync(E.counters.p, 0, 2 * sizeof(uint32_t), st));
+    PX_CUDA(cudaMemsetAsync(E.counters.p + 3, 0, 5 * sizeof(uint32_t), st));
     E.goff.reserve_discard((size_t) N / 2 + 4);
     E.glarge.reserve_discard((size_t) N / 32 + 4);
     E.key2.reserve_discard(N);
@@ -880,12 +882,11 @@ static void build_suffix_array(Store &S, uint32_t N) {
 // Replays the reference's arena allocations (MemPool::p_malloc, MemPool.cpp:7-37) for the leaf /
 // split events of the candidate records and returns how many of them fit before the rotation
 // trigger `nth >= 2048` (PiXiuCtrl.cpp:13).  Commits pool_nth/pool_used for the accepted ones.
-uint32_t Store::count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32_t s0, uint32_t N) {
+// (a) enqueue: word-level prefix of the arena blocks on the GPU and the copies of the masks to pinned memory
+void Store::count_nodes_enqueue(uint32_t s0, uint32_t N) {
     EncodeScratch &E = es;
-    (void) T;
     const uint32_t M = N - s0;
     const size_t words = (size_t) div_up<uint32_t>(M, 256) * 8;  // masks written by k_lpf<true>
-    auto t_a = std::chrono::steady_clock::now();
     // blocks per 32-position word (8 per leaf + 8 per split), exclusive prefix: the host then finds every
     // pool boundary by binary search instead of walking all words
     E.wordpre.reserve_discard(words + 1);
@@ -908,7 +909,16 @@ uint32_t Store::count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32
     PX_CUDA(cudaMemcpyAsync(E.h_leafmask.p, E.leafmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaMemcpyAsync(E.h_splitmask.p, E.splitmask.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaMemcpyAsync(E.h_wordpre.p, E.wordpre.p, (words + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaStreamSynchronize(st));
+    PX_CUDA(cudaEventRecord(ev_nodes, st));
+}
+
+// (b) replay on the host (while the GPU already runs phase B on the candidate superset): returns the number
+// of candidate records accepted
+uint32_t Store::count_nodes_and_cut(uint32_t first_new, uint32_t s0, uint32_t N) {
+    EncodeScratch &E = es;
+    (void) N;
+    auto t_a = std::chrono::steady_clock::now();
+    PX_CUDA(cudaEventSynchronize(ev_nodes));
     auto t_b = std::chrono::steady_clock::now();
     const uint32_t *lm = E.h_leafmask.p, *sm = E.h_splitmask.p, *wp = E.h_wordpre.p;
     constexpr uint32_t C = 65535;  // POOL_BLOCK_NUM (MemPool.h:6)
@@ -1065,20 +1075,10 @@ void Store::enc_phase_a(uint32_t first_new) {
     }
     prof.end(st, 18.0 * M, 1);
     L++;
-    // ---- reference rotation rule: keep only the records that fit the arena budget ----
-    if (cfg.rotate_policy == PIXIU_ROTATE_REFERENCE) {
-        uint32_t acc = count_nodes_and_cut(T, first_new, s0, N);
-        if (acc < n_new) {
-            n_new = acc;
-            R = first_new + acc;
-            N = h_win_rec_start[R];
-            M = N - s0;
-            win_R = R;
-            win_N = N;
-            h_win_rec_start.resize(R + 1);
-            gridM = div_up<uint32_t>(M, 256);
-        }
-    }
+    // reference rotation rule: the arena replay needs the node masks on the host; they are copied
+    // asynchronously and replayed while phase B already runs (apply_rotation_cut)
+    if (cfg.rotate_policy == PIXIU_ROTATE_REFERENCE) count_nodes_enqueue(s0, N);
+    (void) R;
     E.tree = T;
     ep_first_new = first_new;
     ep_s0 = s0;
@@ -1168,7 +1168,7 @@ uint32_t Store::enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const 
     uint32_t g_chunk_first = chunk_first.back();
     prof.begin(PC_EMIT, st);
     k_emit<<<gridM, 256, 0, st>>>(T, w_text.p, w_dist.p, w_recid.p, w_rec_start.p, E.rank.p, E.reach.p, E.flagc.p,
-                                  E.prevp.p, E.nextp.p, E.off.p, s0, N, cfg.strict251, d_enc.p + enc_bytes,
+                                  E.prevp.p, E.nextp.p, E.off.p, s0, N, cfg.strict251, d_enc.ptr() + enc_bytes,
                                   E.counters.p + 2, cand, runidx, gidx);
     prof.end(st, 20.0 * M, 1);
     prof.begin(PC_TABLES, st);
@@ -1189,15 +1189,7 @@ uint32_t Store::enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const 
     h_first.resize(old + n_new, g_chunk_first);
     h_tile_base.insert(h_tile_base.end(), tile_base.begin(), tile_base.end());
     h_live.resize(old + n_new, 1);
-    PX_CUDA(cudaMemcpyAsync(h_enc_off.data() + old, d_enc_off.p + old, n_new * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaMemcpyAsync(h_enc_len.data() + old, d_enc_len.p + old, n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaMemcpyAsync(h_dec_len.data() + old, d_dec_len.p + old, n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    uint32_t errflag = 0, scanerr = 0;
-    PX_CUDA(cudaMemcpyAsync(&errflag, E.counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaMemcpyAsync(&scanerr, E.scanws.ctl.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaStreamSynchronize(st));
-    if (scanerr) throw std::runtime_error("encode: scan look-back timed out");
-    if (errflag) throw std::runtime_error("encode: internal inconsistency (err=" + std::to_string(errflag) + ")");
+    // the host mirrors of the new records and the error flags are fetched once per batch (flush_mirrors)
     enc_bytes += enc_total;
     n_tiles += new_tiles;
     chunk_count.back() += n_new;
@@ -1205,9 +1197,44 @@ uint32_t Store::enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const 
     return n_new;
 }
 
+// Reference rotation rule: keep only the candidate records that fit the arena budget.  Phase B ran on the
+// whole candidate set; its per-position results for the accepted prefix do not depend on what follows
+// (flags are local, the run scans stop at separators, the output offsets are a prefix sum).
+void Store::apply_rotation_cut() {
+    if (cfg.rotate_policy != PIXIU_ROTATE_REFERENCE) return;
+    uint32_t acc = count_nodes_and_cut(ep_first_new, ep_s0, ep_N);
+    if (acc < ep_n_new) {
+        ep_n_new = acc;
+        win_R = ep_first_new + acc;
+        win_N = ep_N = h_win_rec_start[win_R];
+        h_win_rec_start.resize(win_R + 1);
+    }
+}
+
+// Host mirrors (encoded offset / length, decoded length) of the records emitted since the last flush, and the
+// device-side error flags: one copy and one synchronisation per batch instead of per window.
+void Store::flush_mirrors() {
+    EncodeScratch &E = es;
+    const size_t from = mirror_from, n = n_records() - from;
+    uint32_t errflag = 0, scanerr = 0;
+    if (n) {
+        PX_CUDA(cudaMemcpyAsync(h_enc_off.data() + from, d_enc_off.p + from, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaMemcpyAsync(h_enc_len.data() + from, d_enc_len.p + from, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaMemcpyAsync(h_dec_len.data() + from, d_dec_len.p + from, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (E.counters.p) PX_CUDA(cudaMemcpyAsync(&errflag, E.counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (E.scanws.ctl.p) PX_CUDA(cudaMemcpyAsync(&scanerr, E.scanws.ctl.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (E.counters.p) PX_CUDA(cudaMemsetAsync(E.counters.p + 2, 0, sizeof(uint32_t), st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    mirror_from = n_records();
+    if (scanerr) throw std::runtime_error("encode: scan look-back timed out");
+    if (errflag) throw std::runtime_error("encode: internal inconsistency (err=" + std::to_string(errflag) + ")");
+}
+
 uint32_t Store::encode_window_records(uint32_t first_new) {
     enc_phase_a(first_new);
     enc_phase_b();
+    apply_rotation_cut();
     return enc_phase_c(nullptr, nullptr, nullptr);
 }
 
@@ -1242,7 +1269,10 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     const auto t_begin = std::chrono::steady_clock::now();
     PX_CUDA(cudaEventRecord(ev0, st));
     doc_len.reserve_discard(nn);
-    es.counters.reserve_discard(16);
+    if (!es.counters.p) {
+        es.counters.reserve_discard(16);
+        PX_CUDA(cudaMemsetAsync(es.counters.p, 0, 16 * sizeof(uint32_t), st));
+    }
     PX_CUDA(cudaMemsetAsync(es.counters.p + 8, 0, 8 * sizeof(uint32_t), st));
     prof.begin(PC_DOCS, st);
     k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p,
@@ -1314,6 +1344,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         a += acc;
         if (acc < n_new) close_window();  // the arena budget was reached inside the candidates: rotate
     }
+    flush_mirrors();
     const auto t_gpu_done = std::chrono::steady_clock::now();
     PX_CUDA(cudaEventRecord(ev1, st));
     finish_index(nn, g_batch_first, h_keys, h_koff, h_voff, h_doc_len.data(), rc, saved);
@@ -1364,7 +1395,10 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
     const uint32_t nn = (uint32_t) n;
     PX_CUDA(cudaEventRecord(ev0, st));
     doc_len.reserve_discard(nn);
-    es.counters.reserve_discard(16);
+    if (!es.counters.p) {
+        es.counters.reserve_discard(16);
+        PX_CUDA(cudaMemsetAsync(es.counters.p, 0, 16 * sizeof(uint32_t), st));
+    }
     PX_CUDA(cudaMemsetAsync(es.counters.p + 8, 0, 8 * sizeof(uint32_t), st));
     k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p,
                                                                                     es.counters.p + 8);
@@ -1503,6 +1537,7 @@ int Store::mg_end(int32_t *rc, int32_t *saved) {
                                                           mg_d_voff, w_rec_start.p, w_text.p, w_dist.p, w_recid.p, lst.p);
         launches++;
     }
+    flush_mirrors();
     PX_CUDA(cudaEventRecord(ev1, st));
     mg_gR += nn;
     mg_gbytes += mg_batch_bytes;

@@ -443,7 +443,7 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     S.in_vals.reserve_discard(qbytes + 16);
     k_query_write<<<div_up<uint32_t>(nn, 256), 256, 0, st>>>(nn, S.in_keys.p, S.in_koff.p, d_qoff, S.in_vals.p);
     S.doc_off.reserve_discard(nn + 1);
-    ChaseView V{S.d_enc.p, S.d_enc_off.p, S.d_enc_len.p, S.d_dec_len.p, S.d_first.p, S.d_tile_base.p, S.d_tile_desc.p};
+    ChaseView V{S.d_enc.ptr(), S.d_enc_off.p, S.d_enc_len.p, S.d_dec_len.p, S.d_first.p, S.d_tile_base.p, S.d_tile_desc.p};
     k_lookup<<<div_up<uint32_t>(nn, 128), 128, 0, st>>>(nn, T, V, S.in_vals.p, d_qoff, S.doc_len.p, S.doc_off.p);
     PX_LAUNCH_CHECK();
     S.prof.end(st, 0.0, 4);

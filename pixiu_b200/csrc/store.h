@@ -64,7 +64,7 @@ struct EncodeScratch {
 struct Store {
     pixiu_config cfg{};
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_nodes = nullptr;
     std::string err;
     int64_t launches = 0;
     Profiler prof;
@@ -80,7 +80,7 @@ struct Store {
     int64_t raw_bytes = 0, doc_bytes = 0, live_records = 0;
 
     // ---- device store ----
-    DevBuf<uint8_t> d_enc;
+    VmArena d_enc;  // compressed arena: 256 GiB of address space, physical memory mapped as it fills
     DevBuf<uint64_t> d_enc_off;
     DevBuf<uint32_t> d_enc_len, d_dec_len, d_first, d_tile_base, d_tile_desc;
 
@@ -150,7 +150,11 @@ struct Store {
                  const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff, uint32_t **d_m, int64_t *count);
     int mg_mid(uint32_t **d_cand, int64_t *count);
     int mg_end(int32_t *rc, int32_t *saved);
-    uint32_t count_nodes_and_cut(const MinTree &T, uint32_t first_new, uint32_t s0, uint32_t N);
+    void count_nodes_enqueue(uint32_t s0, uint32_t N);
+    uint32_t count_nodes_and_cut(uint32_t first_new, uint32_t s0, uint32_t N);
+    void apply_rotation_cut();
+    void flush_mirrors();
+    size_t mirror_from = 0;  // first record whose host mirrors are not fetched yet
     // decode.cu
     void decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off);
     int64_t import_chunk(int64_t n, const uint8_t *enc, const int64_t *enc_off);
