@@ -46,8 +46,11 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region.  NVML in a thread (4 Hz): spawning
-    `nvidia-smi -lms 100` next to the run was measured to stall the CUDA driver calls of the timed loop."""
+    """SM clock / throttle reasons DURING the timed region, through NVML in a thread at 2 Hz.
+    Sampling is not free for a launch-heavy step (measured on this pool, scratch/nvml_cost.py: spawning
+    `nvidia-smi -lms 100` next to the run halves the throughput, NVML clock+reasons at 20 Hz costs 45 %,
+    at 4 Hz 14 %, one query kind at 4 Hz nothing measurable), so the rate is kept low and the two queries
+    alternate."""
 
     def __init__(self, index):
         self.index = index
@@ -68,16 +71,21 @@ class ClockSampler:
                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
 
             def loop():
+                k = 0
+                self._stop.wait(0.1)
                 while not self._stop.is_set():
                     try:
-                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                        for name, bit in bits.items():
-                            if r & bit:
-                                self.reasons.add(name)
+                        if k % 2 == 0:
+                            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        else:
+                            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                            for name, bit in bits.items():
+                                if r & bit:
+                                    self.reasons.add(name)
                     except Exception:
                         pass
-                    self._stop.wait(0.25)
+                    k += 1
+                    self._stop.wait(0.5)
 
             self.t = threading.Thread(target=loop, daemon=True)
             self.t.start()

@@ -418,11 +418,8 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     DecodeView V{d_enc.ptr(), d_enc_off.p, d_enc_len.p, d_dec_len.p, d_first.p, d_tile_base.p, d_tile_desc.p,
                  dec_aoff.p, arena, dec_ptr.p, dec_flags.p};
     const size_t smem = sizeof(WarpSmem) * DEC_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PX_CUDA(cudaFuncSetAttribute(k_token_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attr_set = true;
-    }
+    // (per device and cheap: no process-wide "already done" flag, a process may drive several GPUs)
+    PX_CUDA(cudaFuncSetAttribute(k_token_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     PX_CUDA(cudaEventRecord(ev0, st));
     prof.begin(PC_DECODE, st);
     k_token_scan<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(

@@ -200,9 +200,7 @@ template <typename KeyT>
 constexpr size_t rs_dyn_smem() { return (sizeof(KeyT) + sizeof(uint32_t)) * RS_TILE; }
 
 struct RadixSortTemp {
-    DevBuf<uint32_t> hist;     // [RS_MAX_PASSES][256]
-    DevBuf<uint32_t> status;   // [passes][tiles][256]
-    DevBuf<uint32_t> ticket;   // [passes] + err
+    DevBuf<uint32_t> status;   // [hist: 8 x 256][tickets: 8][status: passes x tiles x 256]
 };
 
 // Sorts n (key,value) pairs on bits [begin_bit, end_bit) ascending, stable.
@@ -217,31 +215,26 @@ int radix_sort_pairs(KeyT *k0, KeyT *k1, uint32_t *v0, uint32_t *v1, uint32_t n,
     int npass = (end_bit - begin_bit + 7) / 8;
     if (npass > RS_MAX_PASSES) throw std::runtime_error("radix_sort_pairs: too many passes");
     uint32_t tiles = div_up<uint32_t>(n, RS_TILE);
-    tmp.hist.reserve_discard(RS_MAX_PASSES * RS_BINS);
-    tmp.status.reserve_discard((size_t) npass * tiles * RS_BINS);
-    tmp.ticket.reserve_discard(RS_MAX_PASSES);
-    PX_CUDA(cudaMemsetAsync(tmp.hist.p, 0, RS_MAX_PASSES * RS_BINS * sizeof(uint32_t), st));
-    PX_CUDA(cudaMemsetAsync(tmp.status.p, 0, (size_t) npass * tiles * RS_BINS * sizeof(uint32_t), st));
-    PX_CUDA(cudaMemsetAsync(tmp.ticket.p, 0, RS_MAX_PASSES * sizeof(uint32_t), st));
+    // one buffer, one memset: [hist: 8 x 256][tickets: 8][status: npass x tiles x 256]
+    const size_t head_words = RS_MAX_PASSES * RS_BINS + RS_MAX_PASSES;
+    const size_t total_words = head_words + (size_t) npass * tiles * RS_BINS;
+    tmp.status.reserve_discard(total_words);
+    PX_CUDA(cudaMemsetAsync(tmp.status.p, 0, total_words * sizeof(uint32_t), st));
+    uint32_t *hist = tmp.status.p, *ticket = tmp.status.p + RS_MAX_PASSES * RS_BINS, *status = tmp.status.p + head_words;
     uint32_t hgrid = tiles < 148u * 8u ? tiles : 148u * 8u;
     if (prof) prof->begin(PC_SORT_HIST, st);
-    k_rs_histogram<KeyT><<<hgrid, RS_THREADS, 0, st>>>(k0, n, begin_bit, npass, tmp.hist.p);
-    k_rs_scan_bins<<<npass, RS_BINS, 0, st>>>(tmp.hist.p);
+    k_rs_histogram<KeyT><<<hgrid, RS_THREADS, 0, st>>>(k0, n, begin_bit, npass, hist);
+    k_rs_scan_bins<<<npass, RS_BINS, 0, st>>>(hist);
     if (prof) prof->end(st, (double) n * sizeof(KeyT), 2);
-    static bool attr_done = false;  // (one instantiation per KeyT; the attribute is per function)
-    if (!attr_done) {
-        PX_CUDA(cudaFuncSetAttribute(k_rs_onesweep<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rs_dyn_smem<KeyT>()));
-        attr_done = true;
-    }
+    PX_CUDA(cudaFuncSetAttribute(k_rs_onesweep<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rs_dyn_smem<KeyT>()));
     int cur = 0;
     for (int p = 0; p < npass; p++) {
         KeyT *ki = cur ? k1 : k0, *ko = cur ? k0 : k1;
         uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
         if (prof) prof->begin(PC_SORT_PASS, st);
         k_rs_onesweep<KeyT><<<tiles, RS_THREADS, rs_dyn_smem<KeyT>(), st>>>(ki, ko, (p == 0 && iota) ? nullptr : vi, vo, n,
-                                                          begin_bit + 8 * p, tmp.hist.p + p * RS_BINS,
-                                                          tmp.status.p + (size_t) p * tiles * RS_BINS,
-                                                          tmp.ticket.p + p, d_err);
+                                                          begin_bit + 8 * p, hist + p * RS_BINS,
+                                                          status + (size_t) p * tiles * RS_BINS, ticket + p, d_err);
         if (prof) prof->end(st, (double) n * (2.0 * sizeof(KeyT) + ((p == 0 && iota) ? 4.0 : 8.0)), 1);
         cur ^= 1;
     }

@@ -226,8 +226,8 @@ k_scan_dual(size_t n, InFn in, OutFn out, unsigned long long *__restrict__ statu
 
 // workspace shared by all scans of a store (status words + ticket + sticky error flag)
 struct ScanWorkspace {
-    DevBuf<unsigned long long> status, status2;
-    DevBuf<uint32_t> ctl;  // [0] ticket, [1] error
+    DevBuf<unsigned long long> status;  // [ticket word][status words ...]
+    DevBuf<uint32_t> ctl;               // [1] sticky error flag
 };
 
 #ifdef __CUDACC__
@@ -235,16 +235,15 @@ template <typename InFn, typename OutFn>
 void device_scan_dual(size_t n, InFn in, OutFn out, ScanWorkspace &ws, cudaStream_t st) {
     if (n == 0) return;
     unsigned tiles = (unsigned) div_up<size_t>(n, SCAN_TILE);
-    ws.status.reserve_discard(tiles + 1);
-    ws.status2.reserve_discard(tiles + 1);
+    // one buffer, one memset: [ticket word][status of scan 1: tiles][status of scan 2: tiles]
+    ws.status.reserve_discard(2 * (size_t) tiles + 2);
     if (!ws.ctl.p) {
         ws.ctl.reserve_discard(4);
         PX_CUDA(cudaMemsetAsync(ws.ctl.p, 0, 4 * sizeof(uint32_t), st));
     }
-    PX_CUDA(cudaMemsetAsync(ws.status.p, 0, (size_t) tiles * sizeof(unsigned long long), st));
-    PX_CUDA(cudaMemsetAsync(ws.status2.p, 0, (size_t) tiles * sizeof(unsigned long long), st));
-    PX_CUDA(cudaMemsetAsync(ws.ctl.p, 0, sizeof(uint32_t), st));
-    k_scan_dual<<<tiles, SCAN_THREADS, 0, st>>>(n, in, out, ws.status.p, ws.status2.p, ws.ctl.p, ws.ctl.p + 1);
+    PX_CUDA(cudaMemsetAsync(ws.status.p, 0, (2 * (size_t) tiles + 1) * sizeof(unsigned long long), st));
+    k_scan_dual<<<tiles, SCAN_THREADS, 0, st>>>(n, in, out, ws.status.p + 1, ws.status.p + 1 + tiles,
+                                                reinterpret_cast<uint32_t *>(ws.status.p), ws.ctl.p + 1);
     PX_LAUNCH_CHECK();
 }
 
@@ -252,15 +251,15 @@ template <typename T, typename Op, typename InFn, typename OutFn>
 void device_scan(size_t n, InFn in, OutFn out, Op op, T identity, bool exclusive, ScanWorkspace &ws, cudaStream_t st) {
     if (n == 0) return;
     unsigned tiles = (unsigned) div_up<size_t>(n, SCAN_TILE);
-    ws.status.reserve_discard(tiles + 1);
+    // one buffer, one memset: [ticket word][status: tiles]
+    ws.status.reserve_discard((size_t) tiles + 2);
     if (!ws.ctl.p) {
         ws.ctl.reserve_discard(4);
         PX_CUDA(cudaMemsetAsync(ws.ctl.p, 0, 4 * sizeof(uint32_t), st));
     }
-    PX_CUDA(cudaMemsetAsync(ws.status.p, 0, (size_t) tiles * sizeof(unsigned long long), st));
-    PX_CUDA(cudaMemsetAsync(ws.ctl.p, 0, sizeof(uint32_t), st));
-    k_scan_lookback<T><<<tiles, SCAN_THREADS, 0, st>>>(n, in, out, op, identity, exclusive ? 1 : 0, ws.status.p, ws.ctl.p,
-                                                      ws.ctl.p + 1);
+    PX_CUDA(cudaMemsetAsync(ws.status.p, 0, ((size_t) tiles + 1) * sizeof(unsigned long long), st));
+    k_scan_lookback<T><<<tiles, SCAN_THREADS, 0, st>>>(n, in, out, op, identity, exclusive ? 1 : 0, ws.status.p + 1,
+                                                      reinterpret_cast<uint32_t *>(ws.status.p), ws.ctl.p + 1);
     PX_LAUNCH_CHECK();
 }
 #endif
