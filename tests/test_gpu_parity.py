@@ -403,3 +403,29 @@ def test_api_edge_cases(ctrl_mod):
     assert rc.tolist() == [0]
     assert c.stats().live_records == len(c.iter_docs(b""))
     c.free_prop()
+
+
+def test_config1_full_parity_with_live_reference(ctrl_mod, ref):
+    """BASELINE config 1 in full: 10k URL keys x ~100 B values.  SET on the reference (as is, on the CPU) and
+    on the GPU path: same rc, same encoded bytes for every record; GET of every key: same decoded stream
+    (records this short never hit the reference decoder's bugs)."""
+    kd, ko, vd, vo = synth.gen_urls_kv(10000, seed=1)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    ref.reset()
+    r = ref.setitem_batch(keys, vals)
+    assert r["chunk"][-1] == 0
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_REFERENCE, strict251=True)
+    rc, saved = c.setitem_batch((kd, ko), (vd, vo))
+    assert rc.tolist() == r["rc"].tolist()
+    assert c.debug_pool_state() == (int(r["pools"][-1]), int(r["pool_used"][-1]))
+    enc, off = c.export_chunk(0)
+    assert np.diff(off).tolist() == r["enc_len"].tolist()
+    for i in range(0, len(keys), 37):
+        assert enc[off[i]:off[i + 1]].tobytes() == ref.encoded(i), f"record {i}"
+    buf, doff, found = c.getitem_batch((kd, ko))
+    assert found.all()
+    for i in range(0, len(keys), 53):
+        assert buf[doff[i]:doff[i + 1]].tobytes() == ref.getitem(keys[i]) == po.make_doc(keys[i], vals[i])
+    absent = [b"http://nope.qq.com/%d" % i for i in range(100)]
+    assert not c.contains_batch(absent).any() and not any(ref.contains(k) for k in absent)
+    c.free_prop()
