@@ -451,13 +451,52 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
         if (d != 0) {
             const uint32_t *A = T.a[0], *L = T.l[0];
             const uint32_t r = rank[s];
-            // nearest smaller text position above r: lcp = min L[j+1..r]
+            // nearest smaller text position above r: lcp = min L[j+1..r].  Most searches end within a few
+            // entries: a plain scan of up to LPF_FAST neighbours first, the block-min tree only for the rest
+            constexpr int LPF_FAST = 12;
             uint32_t l1 = L[r];
-            int64_t jl = l1 ? tree_search<true, false, true>(T, r, s, l1, 0) : -1;
+            int64_t jl = -1;
+            if (l1) {
+                uint32_t pos = r;
+                bool open = true;
+                for (int k = 0; k < LPF_FAST && pos > 0; k++) {
+                    pos--;
+                    if (A[pos] < s) {
+                        jl = pos;
+                        open = false;
+                        break;
+                    }
+                    l1 = min(l1, L[pos]);
+                    if (l1 == 0) {
+                        open = false;
+                        break;
+                    }
+                }
+                if (open) jl = pos > 0 ? tree_search<true, false, true>(T, pos, s, l1, 0) : -1;
+            }
             if (jl < 0) l1 = 0;
             // nearest smaller text position below r: lcp = min L[r+1..j]; ties with l1 matter for NODES
+            const int64_t floor2 = (NODES && l1 > 0) ? (int64_t) l1 - 1 : (int64_t) l1;
             uint32_t l2 = 0xFFFFFFFFu;
-            int64_t jr = tree_search<false, true, true>(T, r, s, l2, (NODES && l1 > 0) ? (int64_t) l1 - 1 : (int64_t) l1);
+            int64_t jr = n;
+            {
+                uint32_t pos = r;
+                bool open = true;
+                for (int k = 0; k < LPF_FAST && pos + 1 < n; k++) {
+                    pos++;
+                    l2 = min(l2, L[pos]);
+                    if (A[pos] < s) {
+                        jr = pos;
+                        open = false;
+                        break;
+                    }
+                    if ((int64_t) l2 <= floor2) {
+                        open = false;
+                        break;
+                    }
+                }
+                if (open) jr = pos + 1 < n ? tree_search<false, true, true>(T, pos, s, l2, floor2) : (int64_t) n;
+            }
             if (jr >= (int64_t) n) l2 = 0;
             best = max(l1, l2);
             if (NODES) {
