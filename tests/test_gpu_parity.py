@@ -429,3 +429,59 @@ def test_config1_full_parity_with_live_reference(ctrl_mod, ref):
     absent = [b"http://nope.qq.com/%d" % i for i in range(100)]
     assert not c.contains_batch(absent).any() and not any(ref.contains(k) for k in absent)
     c.free_prop()
+
+
+# --------------------------------------------------------------------------- size-independent properties at scale
+def _roundtrip_all(ctrl_mod, c, kd, ko, vd, vo):
+    """getitem of every key == esc(k) 251 0 esc(v) 251 2, checked vectorised for escape-free data"""
+    n = len(ko) - 1
+    buf, off, found = c.getitem_batch((kd, ko))
+    assert found.all()
+    klen, vlen = np.diff(ko), np.diff(vo)
+    assert np.array_equal(np.diff(off), klen + vlen + 4)
+    # key bytes, terminators and value bytes at their places
+    from pixiu_b200.synth import ragged_gather
+
+    assert np.array_equal(ragged_gather(buf, off[:-1], klen), kd)
+    assert np.array_equal(ragged_gather(buf, off[:-1] + klen + 2, vlen), vd)
+    t = off[:-1] + klen
+    assert (buf[t] == 251).all() and (buf[t + 1] == 0).all()
+    assert (buf[off[1:] - 2] == 251).all() and (buf[off[1:] - 1] == 2).all()
+
+
+def test_config3_style_deep_nesting_at_scale(ctrl_mod):
+    """100k x 1 KB records, each the previous one with one byte swept (nesting depth in the hundreds) plus
+    self-periodic runs: every record round-trips; the compressed store is a few percent of the input"""
+    kd, ko, vd, vo = synth.gen_nested(100000, seed=3)
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_REFERENCE)
+    rc, saved = c.setitem_batch((kd, ko), (vd, vo))
+    assert not rc.any()
+    st = c.stats()
+    assert st.records == 100000 and st.chunks >= 2
+    assert st.encoded_bytes < 0.06 * st.raw_bytes
+    assert int(saved.sum()) == st.doc_bytes - st.encoded_bytes
+    _roundtrip_all(ctrl_mod, c, kd, ko, vd, vo)
+    c.free_prop()
+
+
+def test_config4_style_lookup_at_scale(ctrl_mod):
+    """300k URL keys: 90 % present / 10 % absent queries in random order, then full round trip"""
+    n = 300000
+    kd, ko, vd, vo = synth.gen_urls_kv(n, seed=4, val_words=20)
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_REFERENCE)
+    rc, _ = c.setitem_batch((kd, ko), (vd, vo))
+    assert not rc.any() and c.stats().chunks >= 3
+    rng = np.random.default_rng(1)
+    keys = synth.unpack(kd, ko)
+    pick = rng.integers(0, n, size=90000)
+    q = [keys[i] for i in pick] + [b"http://absent.qq.com/%d" % i for i in range(10000)]
+    perm = rng.permutation(len(q))
+    found = c.contains_batch([q[i] for i in perm])
+    assert found.tolist() == (perm < 90000).tolist()
+    _roundtrip_all(ctrl_mod, c, kd, ko, vd, vo)
+    # delete a third, the rest stays reachable
+    dk = keys[::3]
+    assert not c.delitem_batch(dk).any()
+    f2 = c.contains_batch(keys[:3000])
+    assert f2.tolist() == [i % 3 != 0 for i in range(3000)]
+    c.free_prop()
