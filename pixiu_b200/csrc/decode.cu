@@ -42,12 +42,13 @@ struct DecodeView {
 };
 
 constexpr uint32_t SEG_MAX = (ENC_MAX + 8) / 6 + 2;  // a reference token takes at least 6 encoded bytes
+constexpr uint32_t ENC_WORDS = (ENC_MAX + 16) / 4;
 
-struct WarpSmem {
-    // encoded bytes (word aligned copy; byte p of the tile at enc8[a0 + p]) followed by the token kinds;
+struct alignas(16) WarpSmem {
+    // encoded bytes, re-aligned so that byte p of the tile is byte p of encw, followed by the token kinds;
     // after the row loop the same 4 KB hold the per-byte segment markers (u16 x TILE)
-    uint32_t encw[(ENC_MAX + 8) / 4];
-    uint8_t kind[ENC_MAX + 8];
+    uint32_t encw[ENC_WORDS];
+    uint32_t kindw[ENC_WORDS];
     uint32_t outw[TILE / 4];  // the tile's decoded bytes (literal positions); before that: the list of 251 positions
     uint32_t lit[TILE / 32];  // literal bitmap of the tile
     // reference segments clipped to the tile, in output order
@@ -57,34 +58,34 @@ struct WarpSmem {
     uint16_t seg_rel[SEG_MAX];   // tile-relative output position of byte k0
     uint16_t seg_len[SEG_MAX];
 };
-static_assert(sizeof(uint32_t) * ((ENC_MAX + 8) / 4) + (ENC_MAX + 8) >= sizeof(uint16_t) * TILE, "marker alias");
+static_assert(2 * sizeof(uint32_t) * ENC_WORDS >= sizeof(uint16_t) * TILE, "marker alias");
 
 // one 251 at tile position p that surely starts a token: walk its cluster (PiXiuStr.h:142-160 dispatch)
-__device__ __forceinline__ void walk_cluster(WarpSmem &S, const uint8_t *EB, uint32_t p, uint32_t ne, uint32_t *err) {
+__device__ __forceinline__ void walk_cluster(uint8_t *kind, const uint8_t *EB, uint32_t p, uint32_t ne, uint32_t *err) {
     uint32_t e = p;
     while (true) {
         if (e + 1 >= ne) {  // first half of an escape pair cut by the tile boundary
-            S.kind[e] = K_LIT;
+            kind[e] = K_LIT;
             break;
         }
         uint32_t nx = EB[e + 1];
         uint32_t tl;
         if (nx == 0 || nx == 251 || nx == 2) {
-            S.kind[e] = K_LIT;
-            S.kind[e + 1] = K_LIT;
+            kind[e] = K_LIT;
+            kind[e + 1] = K_LIT;
             tl = 2;
         } else if (nx == 1) {
-            S.kind[e] = K_BREF;
+            kind[e] = K_BREF;
             tl = 8;
         } else if (nx > 6) {
-            S.kind[e] = K_SREF;
+            kind[e] = K_SREF;
             tl = 6;
         } else {
             atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
             break;
         }
         if (tl > 2)
-            for (uint32_t q = e + 1; q < e + tl && q < ne; q++) S.kind[q] = K_COV;
+            for (uint32_t q = e + 1; q < e + tl && q < ne; q++) kind[q] = K_COV;
         e += tl;
         // the next 251 of the same cluster lies within 7 bytes of the last one seen
         uint32_t q = e;
@@ -94,6 +95,8 @@ __device__ __forceinline__ void walk_cluster(WarpSmem &S, const uint8_t *EB, uin
     }
 }
 
+// Every lane owns 4 consecutive bytes per step (128 per warp step): the warp-wide scans, ballots and loop
+// overheads are paid once per 128 bytes.
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
              uint32_t n_work, uint32_t *__restrict__ err) {
@@ -126,33 +129,47 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
         if (lane == 0) atomicExch(err, 4u);
         return;
     }
-    // ---- 1. stage the encoded bytes with aligned word loads (the arena has slack past its end) ----
+    // ---- 1. stage the encoded bytes re-aligned to words (the arena has slack past its end) ----
     const uint8_t *gsrc = encp + e0;
     const uint32_t a0 = (uint32_t) ((uintptr_t) gsrc & 3);
     const uint32_t *gw = reinterpret_cast<const uint32_t *>(gsrc - a0);
-    const uint32_t nw = (a0 + ne + 3) >> 2;
-    for (uint32_t j = lane; j < nw; j += 32) S.encw[j] = gw[j];
+    const uint32_t nw = ((ne + 3) >> 2) + 2;  // two extra words: token fields are read up to 7 bytes past a head
+    for (uint32_t j = lane; j < nw; j += 32) S.encw[j] = a0 ? __funnelshift_r(gw[j], gw[j + 1], 8 * a0) : gw[j];
     __syncwarp();
-    const uint8_t *EB = reinterpret_cast<const uint8_t *>(S.encw) + a0;
+    const uint8_t *EB = reinterpret_cast<const uint8_t *>(S.encw);
+    uint8_t *kind = reinterpret_cast<uint8_t *>(S.kindw);
     // ---- 2. token kinds.  Default: a 251 is "covered" until a walk proves it a head.  The 251 positions are
     //         compacted into a list (in outw) so that the cluster walks run 32 at a time ----
-    const uint32_t pstart = raw_first ? 1u : 0u;
     uint16_t *cands = reinterpret_cast<uint16_t *>(S.outw);
     uint32_t ncand = 0;
-    for (uint32_t r0 = 0; r0 < ne; r0 += 32) {
-        const uint32_t p = r0 + lane;
-        const bool is251 = p < ne && EB[p] == 251;
-        if (p < ne) S.kind[p] = is251 ? K_COV : K_LIT;
-        const uint32_t m = __ballot_sync(0xffffffffu, is251 && p >= pstart);
-        if (is251 && p >= pstart) {
-            uint32_t slot = ncand + __popc(m & lt);
-            if (slot < TILE / 2) cands[slot] = (uint16_t) p;
+    for (uint32_t r0 = 0; r0 < ne; r0 += 128) {
+        const uint32_t p = r0 + 4 * lane;
+        const uint32_t wd = p < ne ? S.encw[p >> 2] : 0u;
+        const uint32_t nval = p < ne ? min(ne - p, 4u) : 0u;
+        uint32_t m = __vcmpeq4(wd, 0xFBFBFBFBu);                      // 0xFF per byte that is 251
+        m &= nval >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nval)) - 1);
+        if (raw_first && p == 0) m &= ~0xFFu;                          // the raw first byte is a plain literal
+        if (p < ne) S.kindw[p >> 2] = m & 0x01010101u;                 // K_COV (1) for 251s, K_LIT (0) otherwise
+        uint32_t cnt = __popc(m) >> 3;
+        if (__ballot_sync(0xffffffffu, cnt != 0)) {
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((int) lane >= d) inc += o;
+            }
+            uint32_t slot = ncand + inc - cnt;
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++)
+                if ((m >> (8 * bb)) & 1u) {
+                    if (slot < TILE / 2) cands[slot] = (uint16_t) (p + bb);
+                    slot++;
+                }
+            ncand += __shfl_sync(0xffffffffu, inc, 31);
         }
-        ncand += __popc(m);
     }
     __syncwarp();
-    if (lane == 0 && raw_first) S.kind[0] = K_LIT;
-    __syncwarp();
+    const uint32_t pstart = raw_first ? 1u : 0u;
     if (ncand <= TILE / 2) {
         for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
             const uint32_t c = c0 + lane;
@@ -160,7 +177,7 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
                 const uint32_t p = cands[c];
                 // a 251 with no 251 among the 7 bytes before it surely starts a token
                 bool certain = c == 0 || (uint32_t) cands[c - 1] + 7 < p;
-                if (certain) walk_cluster(S, EB, p, ne, err);
+                if (certain) walk_cluster(kind, EB, p, ne, err);
             }
         }
     } else {  // 251-dense tile: scan positions directly
@@ -168,30 +185,47 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
             if (EB[p] != 251) continue;
             bool certain = true;
             for (uint32_t q = (p >= pstart + 7 ? p - 7 : pstart); q < p; q++) certain &= EB[q] != 251;
-            if (certain) walk_cluster(S, EB, p, ne, err);
+            if (certain) walk_cluster(kind, EB, p, ne, err);
         }
     }
     __syncwarp();
-    // ---- 3. rows of 32 encoded positions: decoded offsets by warp scan; literals go to the tile buffer,
-    //         references become segments (clipped to the tile, in output order) ----
+    // ---- 3. rows of 128 encoded positions: decoded offsets by one warp scan per row; literals go to the tile
+    //         buffer, references become segments (clipped to the tile, in output order) ----
     uint8_t *out8 = reinterpret_cast<uint8_t *>(S.outw);
     uint32_t base = 0;  // decoded bytes of the tokens before this row (counted from the first token's start)
     uint32_t nseg = 0;
-    for (uint32_t r0 = 0; r0 < ne; r0 += 32) {
-        const uint32_t p = r0 + lane;
-        const uint8_t k = p < ne ? S.kind[p] : (uint8_t) K_COV;
-        uint32_t idx = 0, from = 0, tl = k == K_LIT ? 1u : 0u;
-        const bool isref = k == K_SREF || k == K_BREF;
-        if (isref) {
-            idx = EB[p + 2] | (EB[p + 3] << 8);
-            uint32_t to = EB[p + 4] | (EB[p + 5] << 8);
-            from = k == K_SREF ? to - EB[p + 1] : (uint32_t) (EB[p + 6] | (EB[p + 7] << 8));
+    for (uint32_t r0 = 0; r0 < ne; r0 += 128) {
+        const uint32_t p = r0 + 4 * lane;
+        uint32_t kw = 0x01010101u, wd = 0;  // beyond the range: covered (no output)
+        if (p < ne) {
+            kw = S.kindw[p >> 2];
+            wd = S.encw[p >> 2];
+            const uint32_t nval = min(ne - p, 4u);
+            if (nval < 4) kw = (kw & ((1u << (8 * nval)) - 1)) | (0x01010101u << (8 * nval));  // past the end: covered
+        }
+        // at most one reference head among the lane's 4 bytes (a reference token is >= 6 bytes long)
+        int ri = -1;
+        uint32_t idx = 0, from = 0, tl = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t k = (kw >> (8 * i)) & 0xFFu;
+            if (k == K_SREF || k == K_BREF) ri = i;
+        }
+        if (ri >= 0) {
+            const uint32_t q = p + ri;
+            const uint32_t k = (kw >> (8 * ri)) & 0xFFu;
+            idx = EB[q + 2] | (EB[q + 3] << 8);
+            uint32_t to = EB[q + 4] | (EB[q + 5] << 8);
+            from = k == K_SREF ? to - EB[q + 1] : (uint32_t) (EB[q + 6] | (EB[q + 7] << 8));
             tl = to - from;
         }
-        uint32_t inc = tl;
-        const uint32_t special = __ballot_sync(0xffffffffu, k != K_LIT);
+        // decoded bytes produced by the lane's 4 positions
+        const uint32_t nlit = 4u - (__popc(__vcmpne4(kw, 0u)) >> 3);  // K_LIT is 0
+        uint32_t lane_sum = nlit + tl;
+        uint32_t inc = lane_sum;
+        const uint32_t special = __ballot_sync(0xffffffffu, kw != 0);
         if (special == 0) {
-            inc = lane + 1;  // a row of plain literals
+            inc = 4 * (lane + 1);  // a row of plain literals
         } else {
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -199,22 +233,31 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
                 if ((int) lane >= d) inc += o;
             }
         }
-        const int rel = (int) (base + inc - tl) - (int) skip;
+        int rel = (int) (base + inc - lane_sum) - (int) skip;
+        int seg_rel0 = 0;
         uint32_t k0 = 0, k1 = 0;
-        if (k == K_LIT) {
-            if (rel >= 0 && rel < (int) nbytes) out8[rel] = EB[p];
-        } else if (isref) {
-            k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
-            k1 = (int) tl + rel > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
+        bool emit = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t k = (kw >> (8 * i)) & 0xFFu;
+            if (k == K_LIT) {
+                if (rel >= 0 && rel < (int) nbytes) out8[rel] = (uint8_t) (wd >> (8 * i));
+                rel += 1;
+            } else if (i == ri) {
+                k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
+                k1 = (int) tl + rel > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
+                emit = k0 < k1;
+                seg_rel0 = rel;
+                rel += (int) tl;
+            }
         }
-        const bool emit = isref && k0 < k1;
         const uint32_t em = __ballot_sync(0xffffffffu, emit);
         if (emit) {
             const uint32_t sidx = nseg + __popc(em & lt);
             const uint32_t src_g = chunk_first + idx;
             uint32_t sbase, per = 0;
             if (src_g == g) {  // self reference (PiXiuStr.h:168-181): overlapping copies repeat with this period
-                uint32_t period = (uint32_t) ((int) t0 + rel) - from;
+                uint32_t period = (uint32_t) ((int) t0 + seg_rel0) - from;
                 sbase = rec_base + from;
                 per = tl > period ? period : 0u;
             } else {
@@ -225,7 +268,7 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
                 S.seg_base[sidx] = sbase;
                 S.seg_k0[sidx] = (uint16_t) k0;
                 S.seg_per[sidx] = (uint16_t) per;
-                S.seg_rel[sidx] = (uint16_t) (rel + (int) k0);
+                S.seg_rel[sidx] = (uint16_t) (seg_rel0 + (int) k0);
                 S.seg_len[sidx] = (uint16_t) (k1 - k0);
             }
         }
@@ -237,38 +280,54 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
         return;
     }
     __syncwarp();
-    // ---- 4. per output byte: which segment covers it (markers at segment starts + running max), then the
-    //         literal bitmap word and the coalesced source pointers ----
+    // ---- 4. per output byte (4 per lane): which segment covers it (markers at segment starts + running max),
+    //         then the literal bitmap and the coalesced source pointers ----
     uint16_t *marker = reinterpret_cast<uint16_t *>(S.encw);  // the encoded bytes are not needed any more
-    for (uint32_t j = lane; j < TILE / 2; j += 32) reinterpret_cast<uint32_t *>(marker)[j] = 0;
+    for (uint32_t j = lane; j < TILE / 2; j += 32) reinterpret_cast<uint32_t *>(marker)[j] = 0;  // spans encw + kindw
     __syncwarp();
     for (uint32_t sgi = lane; sgi < nseg; sgi += 32) marker[S.seg_rel[sgi]] = (uint16_t) (sgi + 1);
     __syncwarp();
     uint32_t *gptr = V.ptr + rec_base + t0;
     uint32_t carry = 0;  // id+1 of the latest segment start seen so far
-    for (uint32_t j0 = 0; j0 < nbytes; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        uint32_t cur = j < nbytes ? marker[j] : 0u;
+    for (uint32_t j0 = 0; j0 < nbytes; j0 += 128) {
+        const uint32_t j = j0 + 4 * lane;
+        uint2 mk = make_uint2(0u, 0u);
+        if (j < nbytes) mk = *reinterpret_cast<const uint2 *>(marker + j);  // 4 markers (beyond nbytes: zero)
+        const uint32_t m0 = mk.x & 0xFFFFu, m1 = mk.x >> 16, m2 = mk.y & 0xFFFFu, m3 = mk.y >> 16;
+        uint32_t lmax = max(max(m0, m1), max(m2, m3));
+        uint32_t inc = lmax;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, cur, d);
-            if ((int) lane >= d) cur = max(cur, o);
+            uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((int) lane >= d) inc = max(inc, o);
         }
+        uint32_t cur = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) cur = 0;
         cur = max(cur, carry);
-        carry = __shfl_sync(0xffffffffu, cur, 31);
-        bool isref = false;
-        if (cur && j < nbytes) {
-            const uint32_t sgi = cur - 1;
-            const uint32_t o = j - S.seg_rel[sgi];
-            if (o < S.seg_len[sgi]) {
-                isref = true;
-                uint32_t kk = S.seg_k0[sgi] + o, per = S.seg_per[sgi];
-                gptr[j] = S.seg_base[sgi] + (per ? kk % per : kk);
+        carry = max(carry, __shfl_sync(0xffffffffu, inc, 31));
+        uint32_t nib = 0;
+        const uint32_t mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (mm[i]) cur = mm[i];
+            const uint32_t jj = j + i;
+            bool isref = false;
+            if (cur && jj < nbytes) {
+                const uint32_t sgi = cur - 1;
+                const uint32_t o = jj - S.seg_rel[sgi];
+                if (o < S.seg_len[sgi]) {
+                    isref = true;
+                    uint32_t kk = S.seg_k0[sgi] + o, per = S.seg_per[sgi];
+                    gptr[jj] = S.seg_base[sgi] + (per ? kk % per : kk);
+                }
             }
+            if (jj < nbytes && !isref) nib |= 1u << i;
         }
-        const uint32_t rm = __ballot_sync(0xffffffffu, isref);
-        const uint32_t valid = nbytes - j0 >= 32 ? 0xFFFFFFFFu : ((1u << (nbytes - j0)) - 1);
-        if (lane == 0) S.lit[j0 >> 5] = ~rm & valid;
+        uint32_t v = nib << (4 * (lane & 7));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        if ((lane & 7) == 0) S.lit[(j0 >> 5) + (lane >> 3)] = v;
     }
     __syncwarp();
     // ---- 5. store the tile's bytes (literal positions are final, the rest is filled by k_resolve)
