@@ -41,62 +41,34 @@ struct DecodeView {
     uint32_t *litmap;           // per arena byte: 1 bit, set = literal
 };
 
-constexpr uint32_t SEG_MAX = (ENC_MAX + 8) / 6 + 2;  // a reference token takes at least 6 encoded bytes
+// every reference segment but the first and the last of a tile puts >= 7 decoded bytes into the tile
+constexpr uint32_t SEG_MAX = TILE / 7 + 4;
 constexpr uint32_t ENC_WORDS = (ENC_MAX + 16) / 4;
+constexpr uint32_t UB_WORDS = TILE / 32 + 6;  // bitmaps over the tile's output in word-aligned ("u") coordinates
+constexpr uint16_t CAND_HEAD = 0x8000;        // candidate flag: this 251 starts a reference token
 
 struct alignas(16) WarpSmem {
-    // encoded bytes, re-aligned so that byte p of the tile is byte p of encw, followed by the token kinds;
-    // after the row loop the same 4 KB hold the per-byte segment markers (u16 x TILE)
-    uint32_t encw[ENC_WORDS];
-    uint32_t kindw[ENC_WORDS];
-    uint32_t outw[TILE / 4];  // the tile's decoded bytes (literal positions); before that: the list of 251 positions
-    uint32_t lit[TILE / 32];  // literal bitmap of the tile
+    uint32_t encw[ENC_WORDS];       // encoded bytes, re-aligned: byte p of the tile's range is byte p of encw
+    uint16_t cands[ENC_MAX + 16];   // positions of the 251s, ascending (| CAND_HEAD)
     // reference segments clipped to the tile, in output order
-    uint32_t seg_base[SEG_MAX];  // arena position of the token's source byte 0
-    uint16_t seg_k0[SEG_MAX];    // first token byte inside the tile
-    uint16_t seg_per[SEG_MAX];   // period of a self-overlapping reference (0: none)
-    uint16_t seg_rel[SEG_MAX];   // tile-relative output position of byte k0
+    uint32_t seg_base[SEG_MAX];   // arena position of the token's source byte 0
+    uint16_t seg_k0[SEG_MAX];     // first token byte inside the tile
+    uint16_t seg_per[SEG_MAX];    // period of a self-overlapping reference (0: none)
+    uint16_t seg_rel[SEG_MAX];    // tile-relative output position of byte k0
     uint16_t seg_len[SEG_MAX];
+    uint16_t seg_delta[SEG_MAX];  // literals after the segment: encoded position = output position + delta (mod 2^16)
+    uint32_t startb[UB_WORDS];    // bit u: a segment starts at output byte u - mis
+    uint32_t lit[UB_WORDS];       // literal bitmap of the tile
+    uint16_t wprefix[UB_WORDS];   // segment starts before word w of startb
 };
-static_assert(2 * sizeof(uint32_t) * ENC_WORDS >= sizeof(uint16_t) * TILE, "marker alias");
 
-// one 251 at tile position p that surely starts a token: walk its cluster (PiXiuStr.h:142-160 dispatch)
-__device__ __forceinline__ void walk_cluster(uint8_t *kind, const uint8_t *EB, uint32_t p, uint32_t ne, uint32_t *err) {
-    uint32_t e = p;
-    while (true) {
-        if (e + 1 >= ne) {  // first half of an escape pair cut by the tile boundary
-            kind[e] = K_LIT;
-            break;
-        }
-        uint32_t nx = EB[e + 1];
-        uint32_t tl;
-        if (nx == 0 || nx == 251 || nx == 2) {
-            kind[e] = K_LIT;
-            kind[e + 1] = K_LIT;
-            tl = 2;
-        } else if (nx == 1) {
-            kind[e] = K_BREF;
-            tl = 8;
-        } else if (nx > 6) {
-            kind[e] = K_SREF;
-            tl = 6;
-        } else {
-            atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
-            break;
-        }
-        if (tl > 2)
-            for (uint32_t q = e + 1; q < e + tl && q < ne; q++) kind[q] = K_COV;
-        e += tl;
-        // the next 251 of the same cluster lies within 7 bytes of the last one seen
-        uint32_t q = e;
-        while (q < ne && q < e + 7 && EB[q] != 251) q++;
-        if (q >= ne || q >= e + 7) break;
-        e = q;
-    }
-}
-
-// Every lane owns 4 consecutive bytes per step (128 per warp step): the warp-wide scans, ballots and loop
-// overheads are paid once per 128 bytes.
+// K10: one warp per 2 KiB tile of decoded output.
+//   1. stage the tile's encoded bytes in shared memory
+//   2. list the 251s; walk each cluster of 251s from its first (certain) token head to classify reference heads
+//      (PiXiuStr.h:142-160 dispatch); a scan over the heads gives every reference's output position, because
+//      literals map 1:1:  out(p) = p + sum over earlier references (token bytes decoded - token bytes encoded)
+//   3. per output byte (4 per lane, aligned to the arena's words): inside a reference segment -> source pointer
+//      (coalesced), else the literal is copied straight from the staged bytes; literal bitmap for k_resolve
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
              uint32_t n_work, uint32_t *__restrict__ err) {
@@ -135,22 +107,21 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
     const uint32_t *gw = reinterpret_cast<const uint32_t *>(gsrc - a0);
     const uint32_t nw = ((ne + 3) >> 2) + 2;  // two extra words: token fields are read up to 7 bytes past a head
     for (uint32_t j = lane; j < nw; j += 32) S.encw[j] = a0 ? __funnelshift_r(gw[j], gw[j + 1], 8 * a0) : gw[j];
+    S.startb[lane] = 0;
+    S.startb[32 + lane] = 0;
+    if (lane < UB_WORDS - 64) S.startb[64 + lane] = 0;
     __syncwarp();
     const uint8_t *EB = reinterpret_cast<const uint8_t *>(S.encw);
-    uint8_t *kind = reinterpret_cast<uint8_t *>(S.kindw);
-    // ---- 2. token kinds.  Default: a 251 is "covered" until a walk proves it a head.  The 251 positions are
-    //         compacted into a list (in outw) so that the cluster walks run 32 at a time ----
-    uint16_t *cands = reinterpret_cast<uint16_t *>(S.outw);
+    // ---- 2a. positions of the 251s, 4 bytes per lane ----
     uint32_t ncand = 0;
     for (uint32_t r0 = 0; r0 < ne; r0 += 128) {
         const uint32_t p = r0 + 4 * lane;
         const uint32_t wd = p < ne ? S.encw[p >> 2] : 0u;
         const uint32_t nval = p < ne ? min(ne - p, 4u) : 0u;
-        uint32_t m = __vcmpeq4(wd, 0xFBFBFBFBu);                      // 0xFF per byte that is 251
+        uint32_t m = __vcmpeq4(wd, 0xFBFBFBFBu);  // 0xFF per byte that is 251
         m &= nval >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nval)) - 1);
-        if (raw_first && p == 0) m &= ~0xFFu;                          // the raw first byte is a plain literal
-        if (p < ne) S.kindw[p >> 2] = m & 0x01010101u;                 // K_COV (1) for 251s, K_LIT (0) otherwise
-        uint32_t cnt = __popc(m) >> 3;
+        if (raw_first && p == 0) m &= ~0xFFu;  // the raw first byte is a plain literal
+        const uint32_t cnt = __popc(m) >> 3;
         if (__ballot_sync(0xffffffffu, cnt != 0)) {
             uint32_t inc = cnt;
 #pragma unroll
@@ -161,103 +132,83 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
             uint32_t slot = ncand + inc - cnt;
 #pragma unroll
             for (int bb = 0; bb < 4; bb++)
-                if ((m >> (8 * bb)) & 1u) {
-                    if (slot < TILE / 2) cands[slot] = (uint16_t) (p + bb);
-                    slot++;
-                }
+                if ((m >> (8 * bb)) & 1u) S.cands[slot++] = (uint16_t) (p + bb);
             ncand += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
     __syncwarp();
-    const uint32_t pstart = raw_first ? 1u : 0u;
-    if (ncand <= TILE / 2) {
-        for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            if (c < ncand) {
-                const uint32_t p = cands[c];
-                // a 251 with no 251 among the 7 bytes before it surely starts a token
-                bool certain = c == 0 || (uint32_t) cands[c - 1] + 7 < p;
-                if (certain) walk_cluster(kind, EB, p, ne, err);
+    // ---- 2b. cluster walks, one lane per cluster: a 251 with no 251 among the 7 bytes before it surely starts
+    //          a token, and the next 251 of the same cluster lies within 7 bytes of the previous token's end ----
+    for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
+        uint32_t ci = c0 + lane;
+        if (ci >= ncand) continue;
+        uint32_t e = S.cands[ci] & 0xFFFu;
+        if (ci != 0 && (uint32_t) (S.cands[ci - 1] & 0xFFF) + 7 >= e) continue;
+        while (true) {
+            if (e + 1 >= ne) break;  // first half of an escape pair cut by the tile boundary: a literal
+            const uint32_t nx = EB[e + 1];
+            uint32_t tl;
+            if (nx == 0 || nx == 251 || nx == 2) {
+                tl = 2;
+            } else if (nx == 1) {
+                tl = 8;
+            } else if (nx > 6) {
+                tl = 6;
+            } else {
+                atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
+                break;
             }
-        }
-    } else {  // 251-dense tile: scan positions directly
-        for (uint32_t p = pstart + lane; p < ne; p += 32) {
-            if (EB[p] != 251) continue;
-            bool certain = true;
-            for (uint32_t q = (p >= pstart + 7 ? p - 7 : pstart); q < p; q++) certain &= EB[q] != 251;
-            if (certain) walk_cluster(kind, EB, p, ne, err);
+            if (tl > 2) S.cands[ci] = (uint16_t) (e | CAND_HEAD);
+            e += tl;
+            ci++;
+            while (ci < ncand && S.cands[ci] < e) ci++;  // 251s inside the token
+            if (ci >= ncand || (uint32_t) S.cands[ci] >= e + 7) break;
+            e = S.cands[ci] & 0xFFFu;
         }
     }
     __syncwarp();
-    // ---- 3. rows of 128 encoded positions: decoded offsets by one warp scan per row; literals go to the tile
-    //         buffer, references become segments (clipped to the tile, in output order) ----
-    uint8_t *out8 = reinterpret_cast<uint8_t *>(S.outw);
-    uint32_t base = 0;  // decoded bytes of the tokens before this row (counted from the first token's start)
+    // ---- 2c. reference heads in order -> segments.  D = sum over the references so far of (decoded - encoded)
+    //          token bytes; a token at encoded position p starts at output byte p + D - skip ----
+    const uint32_t mis = (uint32_t) ((uintptr_t) (V.arena + rec_base + t0) & 3);
     uint32_t nseg = 0;
-    for (uint32_t r0 = 0; r0 < ne; r0 += 128) {
-        const uint32_t p = r0 + 4 * lane;
-        uint32_t kw = 0x01010101u, wd = 0;  // beyond the range: covered (no output)
-        if (p < ne) {
-            kw = S.kindw[p >> 2];
-            wd = S.encw[p >> 2];
-            const uint32_t nval = min(ne - p, 4u);
-            if (nval < 4) kw = (kw & ((1u << (8 * nval)) - 1)) | (0x01010101u << (8 * nval));  // past the end: covered
-        }
-        // at most one reference head among the lane's 4 bytes (a reference token is >= 6 bytes long)
-        int ri = -1;
+    int D = 0;
+    for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const uint32_t cv = c < ncand ? S.cands[c] : 0u;
+        const bool head = (cv & CAND_HEAD) != 0;
+        if (__ballot_sync(0xffffffffu, head) == 0) continue;
+        const uint32_t p = cv & 0xFFF;
         uint32_t idx = 0, from = 0, tl = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t k = (kw >> (8 * i)) & 0xFFu;
-            if (k == K_SREF || k == K_BREF) ri = i;
-        }
-        if (ri >= 0) {
-            const uint32_t q = p + ri;
-            const uint32_t k = (kw >> (8 * ri)) & 0xFFu;
-            idx = EB[q + 2] | (EB[q + 3] << 8);
-            uint32_t to = EB[q + 4] | (EB[q + 5] << 8);
-            from = k == K_SREF ? to - EB[q + 1] : (uint32_t) (EB[q + 6] | (EB[q + 7] << 8));
+        int d = 0;
+        if (head) {
+            const bool big = EB[p + 1] == 1;
+            idx = EB[p + 2] | (EB[p + 3] << 8);
+            const uint32_t to = EB[p + 4] | (EB[p + 5] << 8);
+            from = big ? (uint32_t) (EB[p + 6] | (EB[p + 7] << 8)) : to - EB[p + 1];
+            if (to <= from || from > 0xFFFF) {
+                atomicExch(err, 5u);
+                from = to;
+            }
             tl = to - from;
+            d = (int) tl - (big ? 8 : 6);
         }
-        // decoded bytes produced by the lane's 4 positions
-        const uint32_t nlit = 4u - (__popc(__vcmpne4(kw, 0u)) >> 3);  // K_LIT is 0
-        uint32_t lane_sum = nlit + tl;
-        uint32_t inc = lane_sum;
-        const uint32_t special = __ballot_sync(0xffffffffu, kw != 0);
-        if (special == 0) {
-            inc = 4 * (lane + 1);  // a row of plain literals
-        } else {
+        int inc = d;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                if ((int) lane >= d) inc += o;
-            }
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, inc, dd);
+            if ((int) lane >= dd) inc += o;
         }
-        int rel = (int) (base + inc - lane_sum) - (int) skip;
-        int seg_rel0 = 0;
-        uint32_t k0 = 0, k1 = 0;
-        bool emit = false;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t k = (kw >> (8 * i)) & 0xFFu;
-            if (k == K_LIT) {
-                if (rel >= 0 && rel < (int) nbytes) out8[rel] = (uint8_t) (wd >> (8 * i));
-                rel += 1;
-            } else if (i == ri) {
-                k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
-                k1 = (int) tl + rel > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
-                emit = k0 < k1;
-                seg_rel0 = rel;
-                rel += (int) tl;
-            }
-        }
+        const int rel = (int) p + D + (inc - d) - (int) skip;  // output position of the token's first byte
+        const uint32_t k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
+        const uint32_t k1 = (int) tl + rel > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
+        const bool emit = head && k0 < k1;
         const uint32_t em = __ballot_sync(0xffffffffu, emit);
         if (emit) {
             const uint32_t sidx = nseg + __popc(em & lt);
             const uint32_t src_g = chunk_first + idx;
             uint32_t sbase, per = 0;
             if (src_g == g) {  // self reference (PiXiuStr.h:168-181): overlapping copies repeat with this period
-                uint32_t period = (uint32_t) ((int) t0 + seg_rel0) - from;
+                const uint32_t period = (uint32_t) ((int) t0 + rel) - from;
                 sbase = rec_base + from;
                 per = tl > period ? period : 0u;
             } else {
@@ -265,89 +216,120 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
                 sbase = (src_g > g ? 0u : V.arena_off[src_g]) + from;
             }
             if (sidx < SEG_MAX) {
+                const uint32_t srel = (uint32_t) (rel + (int) k0);
                 S.seg_base[sidx] = sbase;
                 S.seg_k0[sidx] = (uint16_t) k0;
                 S.seg_per[sidx] = (uint16_t) per;
-                S.seg_rel[sidx] = (uint16_t) (seg_rel0 + (int) k0);
+                S.seg_rel[sidx] = (uint16_t) srel;
                 S.seg_len[sidx] = (uint16_t) (k1 - k0);
+                S.seg_delta[sidx] = (uint16_t) ((int) skip - (D + inc));
+                atomicOr(&S.startb[(srel + mis) >> 5], 1u << ((srel + mis) & 31));
             }
         }
         nseg += __popc(em);
-        base += __shfl_sync(0xffffffffu, inc, 31);
+        D += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (base < skip + nbytes || nseg > SEG_MAX) {
+    if ((int) ne + D < (int) (skip + nbytes) || nseg > SEG_MAX) {
         if (lane == 0) atomicExch(err, 6u);
         return;
     }
     __syncwarp();
-    // ---- 4. per output byte (4 per lane): which segment covers it (markers at segment starts + running max),
-    //         then the literal bitmap and the coalesced source pointers ----
-    uint16_t *marker = reinterpret_cast<uint16_t *>(S.encw);  // the encoded bytes are not needed any more
-    for (uint32_t j = lane; j < TILE / 2; j += 32) reinterpret_cast<uint32_t *>(marker)[j] = 0;  // spans encw + kindw
-    __syncwarp();
-    for (uint32_t sgi = lane; sgi < nseg; sgi += 32) marker[S.seg_rel[sgi]] = (uint16_t) (sgi + 1);
-    __syncwarp();
-    uint32_t *gptr = V.ptr + rec_base + t0;
-    uint32_t carry = 0;  // id+1 of the latest segment start seen so far
-    for (uint32_t j0 = 0; j0 < nbytes; j0 += 128) {
-        const uint32_t j = j0 + 4 * lane;
-        uint2 mk = make_uint2(0u, 0u);
-        if (j < nbytes) mk = *reinterpret_cast<const uint2 *>(marker + j);  // 4 markers (beyond nbytes: zero)
-        const uint32_t m0 = mk.x & 0xFFFFu, m1 = mk.x >> 16, m2 = mk.y & 0xFFFFu, m3 = mk.y >> 16;
-        uint32_t lmax = max(max(m0, m1), max(m2, m3));
-        uint32_t inc = lmax;
+    // segment starts before each bitmap word (UB_WORDS <= 96: three words per lane)
+    {
+        const uint32_t c0 = __popc(S.startb[lane]);
+        const uint32_t c1 = __popc(S.startb[32 + lane]);
+        const uint32_t c2 = lane < UB_WORDS - 64 ? __popc(S.startb[64 + lane]) : 0u;
+        uint32_t i0 = c0, i1 = c1, i2 = c2;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-            if ((int) lane >= d) inc = max(inc, o);
+            uint32_t o0 = __shfl_up_sync(0xffffffffu, i0, d), o1 = __shfl_up_sync(0xffffffffu, i1, d),
+                     o2 = __shfl_up_sync(0xffffffffu, i2, d);
+            if ((int) lane >= d) i0 += o0, i1 += o1, i2 += o2;
         }
-        uint32_t cur = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) cur = 0;
-        cur = max(cur, carry);
-        carry = max(carry, __shfl_sync(0xffffffffu, inc, 31));
-        uint32_t nib = 0;
-        const uint32_t mm[4] = {m0, m1, m2, m3};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (mm[i]) cur = mm[i];
-            const uint32_t jj = j + i;
-            bool isref = false;
-            if (cur && jj < nbytes) {
-                const uint32_t sgi = cur - 1;
-                const uint32_t o = jj - S.seg_rel[sgi];
-                if (o < S.seg_len[sgi]) {
-                    isref = true;
-                    uint32_t kk = S.seg_k0[sgi] + o, per = S.seg_per[sgi];
-                    gptr[jj] = S.seg_base[sgi] + (per ? kk % per : kk);
+        const uint32_t t0s = __shfl_sync(0xffffffffu, i0, 31), t1s = __shfl_sync(0xffffffffu, i1, 31);
+        S.wprefix[lane] = (uint16_t) (i0 - c0);
+        S.wprefix[32 + lane] = (uint16_t) (t0s + i1 - c1);
+        if (lane < UB_WORDS - 64) S.wprefix[64 + lane] = (uint16_t) (t0s + t1s + i2 - c2);
+    }
+    __syncwarp();
+    // ---- 3. per output byte, 4 per lane.  u = output position + mis, so that u = 0 is an aligned arena word ----
+    const uint32_t nu = nbytes + mis;
+    uint8_t *dstu = V.arena + rec_base + t0 - mis;
+    uint32_t *gptru = V.ptr + rec_base + t0 - mis;
+    for (uint32_t u0 = 0; u0 < nu; u0 += 128) {
+        const uint32_t u = u0 + 4 * lane;
+        const uint32_t sw = S.startb[u >> 5], sh = u & 31;
+        uint32_t cnt = S.wprefix[u >> 5] + __popc(sw & ((1u << sh) - 1));
+        const uint32_t nibs = (sw >> sh) & 0xFu;
+        const uint32_t lo = u < mis ? mis - u : 0u;
+        const uint32_t hi = u + 4 <= nu ? 4u : (nu > u ? nu - u : 0u);
+        uint32_t litn = 0;
+        bool generic = hi != 0;
+        if (nibs == 0 && lo == 0 && hi == 4) {  // one segment (or none) governs all four bytes
+            const uint32_t jj = u - mis;
+            uint32_t q = jj;
+            bool all_lit = true;
+            generic = false;
+            if (cnt) {
+                const uint32_t sgi = cnt - 1;
+                const uint32_t o = jj - S.seg_rel[sgi], len = S.seg_len[sgi];
+                if (o + 4 <= len) {
+                    all_lit = false;
+                    const uint32_t kk = S.seg_k0[sgi] + o, per = S.seg_per[sgi], sb = S.seg_base[sgi];
+                    uint4 pv;
+                    if (per) pv = make_uint4(sb + kk % per, sb + (kk + 1) % per, sb + (kk + 2) % per, sb + (kk + 3) % per);
+                    else pv = make_uint4(sb + kk, sb + kk + 1, sb + kk + 2, sb + kk + 3);
+                    *reinterpret_cast<uint4 *>(gptru + u) = pv;
+                } else if (o >= len) {
+                    q = min((jj + S.seg_delta[sgi]) & 0xFFFFu, ENC_MAX);
+                } else {
+                    all_lit = false;
+                    generic = true;
                 }
             }
-            if (jj < nbytes && !isref) nib |= 1u << i;
+            if (all_lit) {
+                const uint32_t qa = q >> 2;
+                *reinterpret_cast<uint32_t *>(dstu + u) = __funnelshift_r(S.encw[qa], S.encw[qa + 1], 8 * (q & 3));
+                litn = 0xFu;
+            }
         }
-        uint32_t v = nib << (4 * (lane & 7));
+        if (generic) {
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                cnt += (nibs >> i) & 1u;
+                if (i < lo || i >= hi) continue;
+                const uint32_t jj = u + i - mis;
+                uint32_t q = jj;
+                bool isref = false;
+                if (cnt) {
+                    const uint32_t sgi = cnt - 1;
+                    const uint32_t o = jj - S.seg_rel[sgi];
+                    if (o < S.seg_len[sgi]) {
+                        isref = true;
+                        const uint32_t kk = S.seg_k0[sgi] + o, per = S.seg_per[sgi];
+                        gptru[u + i] = S.seg_base[sgi] + (per ? kk % per : kk);
+                    } else {
+                        q = min((jj + S.seg_delta[sgi]) & 0xFFFFu, ENC_MAX);
+                    }
+                }
+                if (!isref) {
+                    dstu[u + i] = EB[q];
+                    litn |= 1u << i;
+                }
+            }
+        }
+        uint32_t v = litn << (4 * (lane & 7));
         v |= __shfl_xor_sync(0xffffffffu, v, 1);
         v |= __shfl_xor_sync(0xffffffffu, v, 2);
         v |= __shfl_xor_sync(0xffffffffu, v, 4);
-        if ((lane & 7) == 0) S.lit[(j0 >> 5) + (lane >> 3)] = v;
+        if ((lane & 7) == 0) S.lit[(u0 >> 5) + (lane >> 3)] = v;
     }
     __syncwarp();
-    // ---- 5. store the tile's bytes (literal positions are final, the rest is filled by k_resolve)
-    //         and its slice of the literal bitmap; records are packed, so nothing is aligned ----
+    // ---- 4. the tile's slice of the literal bitmap (zero-initialised map, OR-ed in: tiles share words) ----
     {
-        uint8_t *dst = V.arena + rec_base + t0;
-        uint32_t head = (uint32_t) ((4 - ((uintptr_t) dst & 3)) & 3);
-        if (head > nbytes) head = nbytes;
-        if (lane < head) dst[lane] = out8[lane];
-        uint32_t nwords = (nbytes - head) >> 2;
-        uint32_t *dw = (uint32_t *) (dst + head);
-        const uint32_t sh8 = 8 * head;
-        for (uint32_t j = lane; j < nwords; j += 32)
-            dw[j] = head ? __funnelshift_r(S.outw[j], S.outw[j + 1], sh8) : S.outw[j];
-        uint32_t tail0 = head + 4 * nwords;
-        if (tail0 + lane < nbytes) dst[tail0 + lane] = out8[tail0 + lane];
-        // bitmap: global bit position B0 = rec_base + t0 (zero-initialised map, OR-ed in)
-        const uint32_t B0 = rec_base + t0, sh = B0 & 31;
+        const uint32_t B0 = rec_base + t0 - mis, sh = B0 & 31;
         uint32_t *lm = V.litmap + (B0 >> 5);
-        const uint32_t nsw = (nbytes + 31) / 32, ngw = (sh + nbytes + 31) / 32;
+        const uint32_t nsw = (nu + 31) / 32, ngw = (sh + nu + 31) / 32;
         for (uint32_t j = lane; j < ngw; j += 32) {
             uint32_t lo = j < nsw ? S.lit[j] : 0u, hi = (j > 0 && sh) ? S.lit[j - 1] : 0u;
             uint32_t v = sh ? ((lo << sh) | (hi >> (32 - sh))) : lo;
