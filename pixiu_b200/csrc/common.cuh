@@ -182,10 +182,16 @@ struct PinnedBuf {
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 
+// acquire-release fence at device scope (cheaper than the sequentially consistent __threadfence)
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// OR into a word with release semantics: the thread's earlier writes are visible before the bits are
+__device__ __forceinline__ void red_release_or_u32(uint32_t *p, uint32_t v) {
+    asm volatile("red.release.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

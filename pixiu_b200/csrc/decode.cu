@@ -2,21 +2,21 @@
 //
 // Replaces the recursive generator PXSGen::operator() (proj/PiXiuStr.h:110-198), which
 // re-scans the referenced record from its first byte for every back reference and bubbles
-// each byte through one coroutine per nesting level, by two dependency-free phases over a
-// flat *decoded arena* (the records of every touched chunk, back to back, u32-addressed):
-//   K10 k_token_scan   one warp per 2 KiB decode tile (tile descriptors make every tile
-//                      independently parsable): 251-dispatch of PiXiuStr.h:142-160 in parallel,
-//                      literal bytes go straight to the arena, every referenced byte gets a
-//                      source pointer (arena position; self-overlapping references are folded
-//                      onto their first period) and a literal bitmap is written;
-//   K11 k_resolve      every non-literal byte chases its pointer chain to a literal; chains
-//                      longer than RESOLVE_HOPS park their progress in the pointer array and the
-//                      kernel is re-run — concurrent shortening makes the remaining rounds
-//                      logarithmic in the nesting depth (deep chains, BASELINE config 3);
+// each byte through one coroutine per nesting level, by ONE data-flow kernel over a flat
+// *decoded arena* (the records of every touched chunk, back to back, u32-addressed):
+//   K10 k_decode_tiles one warp per 2 KiB decode tile (tile descriptors make every tile
+//                      independently parsable), tiles handed out by ticket in arena order:
+//                      251-dispatch of PiXiuStr.h:142-160 in parallel, literal bytes go straight
+//                      to the arena, every reference token becomes a segment (destination,
+//                      source, length; self-overlapping references keep their period) that is
+//                      copied as soon as its source bytes are final.  Finality is tracked per
+//                      byte in a bitmap (1 bit / byte), so the dependency depth is the nesting
+//                      depth of the bytes, not of tiles or records.
 //   K12 k_copy_records only when the caller's layout differs from the arena order.
-// No kernel ever waits on another thread's output, so there are no spin loops and no
-// ordering hazards: pointers only ever move to an ancestor on the same chain, and bytes are
-// only read from literal positions, which are final after K10.
+// Traffic per decoded byte: the encoded byte or the source byte read once, the byte written
+// once, 1/8 byte of bitmap - no per-byte pointer arrays.
+// Waiting is deadlock-free: a source always precedes its destination in the arena and tickets
+// follow arena order, so the tile owning a source is finished or held by a resident warp.
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -27,9 +27,19 @@
 namespace pixiu {
 
 constexpr int DEC_WARPS = 4;
-constexpr uint32_t ENC_MAX = TILE + 16;
-constexpr int RESOLVE_HOPS = 48;
-enum : uint8_t { K_LIT = 0, K_COV = 1, K_SREF = 2, K_BREF = 3 };
+constexpr uint32_t ENC_MAX = TILE + 16;           // encoded bytes a tile can span
+constexpr uint32_t STG_PAD = 16;                  // free bytes in front of the staged range (reads just before it stay in bounds)
+constexpr uint32_t STG_BYTES = STG_PAD + 16 + ENC_MAX + 16;  // pad + 16-byte alignment slack + range + token read-ahead
+constexpr uint32_t STG_WORDS = (STG_BYTES + 31) / 32 * 8;  // whole 32-byte bitmap words
+constexpr uint32_t BM_WORDS = 96;                 // bitmaps: three words per lane
+// every reference segment but the first and the last of a tile puts >= 7 decoded bytes into the tile
+constexpr uint32_t SEG_MAX = TILE / 7 + 4;
+// copy pieces: every reference segment is cut into pieces of at most 32 bytes (a piece is ready when one 32-bit
+// window of the "final" bitmap is all ones); periodic segments with a period >= 32 are also cut where they wrap
+constexpr uint32_t PIECE_MAX = SEG_MAX + 1 + 4 * (TILE / 32);
+constexpr uint32_t PIECE_ROWS = (PIECE_MAX + 31) / 32;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
+static_assert(STG_BYTES <= BM_WORDS * 32 && TILE + 4 <= (BM_WORDS - 1) * 32, "bitmaps too small");
 
 struct DecodeView {
     const uint8_t *enc;
@@ -37,46 +47,79 @@ struct DecodeView {
     const uint32_t *enc_len, *dec_len, *first, *tile_base, *tile_desc;
     const uint32_t *arena_off;  // per record: offset of its decoded bytes in the arena
     uint8_t *arena;
-    uint32_t *ptr;              // per arena byte: source position (non-literal bytes only)
-    uint32_t *litmap;           // per arena byte: 1 bit, set = literal
+    uint32_t *fin;              // per arena byte: 1 bit, set = the byte holds its final value
 };
 
-// every reference segment but the first and the last of a tile puts >= 7 decoded bytes into the tile
-constexpr uint32_t SEG_MAX = TILE / 7 + 4;
-constexpr uint32_t ENC_WORDS = (ENC_MAX + 16) / 4;
-constexpr uint32_t UB_WORDS = TILE / 32 + 6;  // bitmaps over the tile's output in word-aligned ("u") coordinates
-constexpr uint16_t CAND_HEAD = 0x8000;        // candidate flag: this 251 starts a reference token
+struct ParseSmem {                  // parse scratch
+    uint32_t b251[BM_WORDS];        // bit p: staged byte p is a 251 that can start a token
+    uint32_t cst[BM_WORDS];         // bit p: that 251 surely starts a token (no 251 among the 7 bytes before it)
+    uint32_t headb[BM_WORDS];       // bit p: a reference token starts at p
+    uint16_t heads[SEG_MAX + 8];    // staged positions of the reference heads, ascending
+};
 
 struct alignas(16) WarpSmem {
-    uint32_t encw[ENC_WORDS];       // encoded bytes, re-aligned: byte p of the tile's range is byte p of encw
-    uint16_t cands[ENC_MAX + 16];   // positions of the 251s, ascending (| CAND_HEAD)
-    // reference segments clipped to the tile, in output order
-    uint32_t seg_base[SEG_MAX];   // arena position of the token's source byte 0
-    uint16_t seg_k0[SEG_MAX];     // first token byte inside the tile
-    uint16_t seg_per[SEG_MAX];    // period of a self-overlapping reference (0: none)
-    uint16_t seg_rel[SEG_MAX];    // tile-relative output position of byte k0
-    uint16_t seg_len[SEG_MAX];
-    uint16_t seg_delta[SEG_MAX];  // literals after the segment: encoded position = output position + delta (mod 2^16)
-    uint32_t startb[UB_WORDS];    // bit u: a segment starts at output byte u - mis
-    uint32_t lit[UB_WORDS];       // literal bitmap of the tile
-    uint16_t wprefix[UB_WORDS];   // segment starts before word w of startb
+    uint32_t stg[STG_WORDS];        // staged encoded bytes: byte e0 + k of the record sits at staged position soff + k
+    ParseSmem ps;
+    uint32_t startb[BM_WORDS];      // bit u: a segment starts at output byte u - mis (word-aligned "u" coordinates)
+    uint32_t finw[BM_WORDS];        // bit u: output byte u - mis is a literal (final once phase 4 has stored it)
+    uint16_t wprefix[BM_WORDS];     // segment starts before word w of startb
+    // governors of the literal bytes: entry 0 governs the tile's start (the tail of a token that began in the
+    // previous tile, or empty), entries 1.. follow the start bits.  lo16: end of the segment (u); hi16: literals
+    // after it sit at staged position (u - mis) + this
+    uint32_t seg_ed[SEG_MAX + 1];
+    // copy pieces.  meta: u (12 bits) | (n - 1) << 12 (5 bits) | period << 17 (5 bits, 0 = plain copy) | phase << 22
+    uint32_t p_src[PIECE_MAX];      // arena position of the first source byte (periodic: of the period's byte 0)
+    uint32_t p_meta[PIECE_MAX];
+    uint32_t pend[PIECE_ROWS];      // per row of 32 pieces: lanes whose piece is not copied yet
 };
 
-// K10: one warp per 2 KiB tile of decoded output.
-//   1. stage the tile's encoded bytes in shared memory
-//   2. list the 251s; walk each cluster of 251s from its first (certain) token head to classify reference heads
-//      (PiXiuStr.h:142-160 dispatch); a scan over the heads gives every reference's output position, because
-//      literals map 1:1:  out(p) = p + sum over earlier references (token bytes decoded - token bytes encoded)
-//   3. per output byte (4 per lane, aligned to the arena's words): inside a reference segment -> source pointer
-//      (coalesced), else the literal is copied straight from the staged bytes; literal bitmap for k_resolve
+__device__ __forceinline__ uint32_t nib251(uint32_t w) {
+    return ((__vcmpeq4(w, 0xFBFBFBFBu) & 0x08040201u) * 0x01010101u) >> 24;
+}
+
+// publish the new bits of a tile's bitmap (finw, u coordinates) in the arena's bitmap (tiles share words: OR);
+// every lane looks after the global words lane, lane + 32 and lane + 64 of the tile's slice
+__device__ __forceinline__ void flush_word(const uint32_t *finw, uint32_t *lm, uint32_t sh, uint32_t ngw, uint32_t j, uint32_t &pub) {
+    if (j < ngw) {
+        const uint32_t lo = finw[j], hi = j > 0 ? finw[j - 1] : 0u;
+        const uint32_t v = sh ? ((lo << sh) | (hi >> (32 - sh))) : lo;
+        const uint32_t nv = v & ~pub;
+        if (nv) {
+            atomicOr(&lm[j], nv);
+            pub |= nv;
+        }
+    }
+}
+__device__ __forceinline__ void flush_final(const uint32_t *finw, uint32_t *lm, uint32_t sh, uint32_t ngw, uint32_t lane,
+                                            uint32_t &pub0, uint32_t &pub1, uint32_t &pub2) {
+    flush_word(finw, lm, sh, ngw, lane, pub0);
+    flush_word(finw, lm, sh, ngw, lane + 32, pub1);
+    flush_word(finw, lm, sh, ngw, lane + 64, pub2);
+}
+
+// K10: one warp per 2 KiB tile of decoded output, tiles taken by ticket in arena order.
+//   1. stage the tile's encoded bytes in shared memory (16-byte loads)
+//   2. bitmap of the 251s; a 251 with no 251 among the 7 bytes before it surely starts a token: one walk per such
+//      cluster start classifies the tokens of its cluster (PiXiuStr.h:142-160 dispatch) and marks reference heads
+//   3. heads in order -> segments: a scan of (decoded - encoded) token bytes gives every reference's output position,
+//      because literals map 1:1
+//   4. literal bytes: one aligned 32-bit store per output word straight from the staged bytes, then the literal bits
+//      of the tile are published in the arena's "final" bitmap
+//   5. reference segments: a segment is copied once its source range is final (sources always precede their
+//      destination in the arena, and tickets are handed out in arena order, so every source belongs to a tile that
+//      is finished or held by a resident warp: waiting cannot deadlock); copied ranges are published the same way
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
-             uint32_t n_work, uint32_t *__restrict__ err) {
+k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
+               uint32_t n_work, uint32_t *__restrict__ ctr) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
     const uint32_t lt = (1u << lane) - 1;
-    const uint32_t w = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t *err = ctr;
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(ctr + 1, 1u);
+    w = __shfl_sync(FULL, w, 0);
     if (w >= n_work) return;
     const uint32_t gt = work_tile[w], g = work_rec[w];
     const uint32_t t = gt - V.tile_base[g];
@@ -97,94 +140,149 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
         if (sk2 != 0 && sk2 != 0xFFFF) e_end += (encp[e_end + 1] == 1) ? 8u : 6u;
     }
     const uint32_t ne = e_end - e0;
+    const uint32_t mis = (uint32_t) ((uintptr_t) (V.arena + rec_base + t0) & 3);
+    const uint32_t nu = nbytes + mis;
+    const uint32_t B0 = rec_base + t0 - mis;  // arena position of u = 0
+    uint32_t pub0 = 0, pub1 = 0, pub2 = 0;  // bits of the tile already published (global words lane, lane+32, lane+64)
+    uint32_t *const lm = V.fin + (B0 >> 5);
+    const uint32_t fsh = B0 & 31, ngw = (fsh + nu + 31) / 32;
     if (ne > ENC_MAX || e_end > el) {
         if (lane == 0) atomicExch(err, 4u);
         return;
     }
-    // ---- 1. stage the encoded bytes re-aligned to words (the arena has slack past its end) ----
+    // ---- 1. stage the encoded bytes (the compressed arena has slack past its end) ----
     const uint8_t *gsrc = encp + e0;
-    const uint32_t a0 = (uint32_t) ((uintptr_t) gsrc & 3);
-    const uint32_t *gw = reinterpret_cast<const uint32_t *>(gsrc - a0);
-    const uint32_t nw = ((ne + 3) >> 2) + 2;  // two extra words: token fields are read up to 7 bytes past a head
-    for (uint32_t j = lane; j < nw; j += 32) S.encw[j] = a0 ? __funnelshift_r(gw[j], gw[j + 1], 8 * a0) : gw[j];
-    S.startb[lane] = 0;
-    S.startb[32 + lane] = 0;
-    if (lane < UB_WORDS - 64) S.startb[64 + lane] = 0;
-    __syncwarp();
-    const uint8_t *EB = reinterpret_cast<const uint8_t *>(S.encw);
-    // ---- 2a. positions of the 251s, 4 bytes per lane ----
-    uint32_t ncand = 0;
-    for (uint32_t r0 = 0; r0 < ne; r0 += 128) {
-        const uint32_t p = r0 + 4 * lane;
-        const uint32_t wd = p < ne ? S.encw[p >> 2] : 0u;
-        const uint32_t nval = p < ne ? min(ne - p, 4u) : 0u;
-        uint32_t m = __vcmpeq4(wd, 0xFBFBFBFBu);  // 0xFF per byte that is 251
-        m &= nval >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nval)) - 1);
-        if (raw_first && p == 0) m &= ~0xFFu;  // the raw first byte is a plain literal
-        const uint32_t cnt = __popc(m) >> 3;
-        if (__ballot_sync(0xffffffffu, cnt != 0)) {
-            uint32_t inc = cnt;
+    const uint32_t a16 = (uint32_t) ((uintptr_t) gsrc & 15);
+    const uint32_t soff = STG_PAD + a16, nstg = soff + ne;
+    {
+        const uint4 *g4 = reinterpret_cast<const uint4 *>(gsrc - a16);
+        uint4 *s4 = reinterpret_cast<uint4 *>(S.stg);
+        const uint32_t n16 = (a16 + ne + 8 + 15) >> 4;
+        for (uint32_t j = lane; j < n16; j += 32) s4[1 + j] = g4[j];
+        if (lane < 4) S.stg[lane] = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                if ((int) lane >= d) inc += o;
-            }
-            uint32_t slot = ncand + inc - cnt;
-#pragma unroll
-            for (int bb = 0; bb < 4; bb++)
-                if ((m >> (8 * bb)) & 1u) S.cands[slot++] = (uint16_t) (p + bb);
-            ncand += __shfl_sync(0xffffffffu, inc, 31);
+        for (int k = 0; k < 3; k++) {
+            S.ps.headb[lane + 32 * k] = 0;
+            S.startb[lane + 32 * k] = 0;
+            S.finw[lane + 32 * k] = 0;
         }
     }
     __syncwarp();
-    // ---- 2b. cluster walks, one lane per cluster: a 251 with no 251 among the 7 bytes before it surely starts
-    //          a token, and the next 251 of the same cluster lies within 7 bytes of the previous token's end ----
-    for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
-        uint32_t ci = c0 + lane;
-        if (ci >= ncand) continue;
-        uint32_t e = S.cands[ci] & 0xFFFu;
-        if (ci != 0 && (uint32_t) (S.cands[ci - 1] & 0xFFF) + 7 >= e) continue;
-        while (true) {
-            if (e + 1 >= ne) break;  // first half of an escape pair cut by the tile boundary: a literal
-            const uint32_t nx = EB[e + 1];
-            uint32_t tl;
-            if (nx == 0 || nx == 251 || nx == 2) {
-                tl = 2;
-            } else if (nx == 1) {
-                tl = 8;
-            } else if (nx > 6) {
-                tl = 6;
-            } else {
-                atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
-                break;
+    const uint8_t *SB = reinterpret_cast<const uint8_t *>(S.stg);
+    // ---- 2a. bitmap of the 251s (32 staged bytes per lane and step) ----
+    {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(S.stg);
+        const uint32_t lo = soff + (raw_first ? 1u : 0u);  // the raw first byte is a plain literal
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint32_t wi = lane + 32 * k, base = wi * 32;
+            uint32_t bits = 0;
+            if (base < nstg) {
+                const uint4 A = s4[2 * wi], B = s4[2 * wi + 1];
+                bits = nib251(A.x) | (nib251(A.y) << 4) | (nib251(A.z) << 8) | (nib251(A.w) << 12) | (nib251(B.x) << 16) |
+                       (nib251(B.y) << 20) | (nib251(B.z) << 24) | (nib251(B.w) << 28);
+                if (base < lo) bits &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
+                if (base + 32 > nstg) bits &= 0xFFFFFFFFu >> (base + 32 - nstg);
             }
-            if (tl > 2) S.cands[ci] = (uint16_t) (e | CAND_HEAD);
-            e += tl;
-            ci++;
-            while (ci < ncand && S.cands[ci] < e) ci++;  // 251s inside the token
-            if (ci >= ncand || (uint32_t) S.cands[ci] >= e + 7) break;
-            e = S.cands[ci] & 0xFFFu;
+            S.ps.b251[wi] = bits;
         }
     }
     __syncwarp();
-    // ---- 2c. reference heads in order -> segments.  D = sum over the references so far of (decoded - encoded)
-    //          token bytes; a token at encoded position p starts at output byte p + D - skip ----
-    const uint32_t mis = (uint32_t) ((uintptr_t) (V.arena + rec_base + t0) & 3);
-    uint32_t nseg = 0;
+    // ---- 2b. cluster starts, then one walk per cluster ----
+    uint32_t cs[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const uint32_t wi = lane + 32 * k;
+        const uint32_t b = S.ps.b251[wi], pb = wi ? S.ps.b251[wi - 1] : 0u;
+        unsigned long long y = (((unsigned long long) b << 32) | pb) << 1;
+        y |= y << 1;
+        y |= y << 2;
+        y |= y << 3;  // OR of the shifts 1..7
+        cs[k] = b & ~(uint32_t) (y >> 32);
+        S.ps.cst[wi] = cs[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uint32_t st = cs[k];
+        const uint32_t base = (lane + 32 * k) * 32;
+        while (st) {
+            uint32_t e = base + __ffs(st) - 1;
+            st &= st - 1;
+            while (true) {
+                if (e + 1 >= nstg) break;  // first half of an escape pair cut by the tile boundary: a literal
+                const uint32_t nx = SB[e + 1];
+                uint32_t tl;
+                if (nx == 0 || nx == 251 || nx == 2) {
+                    tl = 2;
+                } else if (nx == 1) {
+                    tl = 8;
+                } else if (nx > 6) {
+                    tl = 6;
+                } else {
+                    atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
+                    break;
+                }
+                if (tl > 2) atomicOr(&S.ps.headb[e >> 5], 1u << (e & 31));
+                e += tl;
+                if (e >= nstg) break;
+                // the next 251 of this cluster lies within 7 bytes of the token's end (further ones start their own)
+                const uint32_t wq = e >> 5, sh = e & 31;
+                const uint32_t x = __funnelshift_r(S.ps.b251[wq], S.ps.b251[wq + 1], sh) & 0x7Fu;
+                if (!x) break;
+                const uint32_t cx = __funnelshift_r(S.ps.cst[wq], S.ps.cst[wq + 1], sh);
+                const uint32_t f = __ffs(x) - 1;
+                if ((cx >> f) & 1u) break;  // that one is a cluster start: its own walk handles it
+                e += f;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- 2c. reference heads in ascending order (lane l owns bitmap words 3l .. 3l+2) ----
+    uint32_t nheads;
+    {
+        uint32_t h[3] = {S.ps.headb[3 * lane], S.ps.headb[3 * lane + 1], S.ps.headb[3 * lane + 2]};
+        const uint32_t cnt = __popc(h[0]) + __popc(h[1]) + __popc(h[2]);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if ((int) lane >= d) inc += o;
+        }
+        nheads = __shfl_sync(FULL, inc, 31);
+        if (nheads > SEG_MAX) {
+            if (lane == 0) atomicExch(err, 6u);
+            return;
+        }
+        uint32_t slot = inc - cnt;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint32_t hv = h[k];
+            while (hv) {
+                S.ps.heads[slot++] = (uint16_t) ((3 * lane + k) * 32 + __ffs(hv) - 1);
+                hv &= hv - 1;
+            }
+        }
+        if (lane == 0) S.seg_ed[0] = mis | (soff << 16);  // entry 0: literals of the tile's start map 1:1 onto the staged bytes
+    }
+    __syncwarp();
+    // ---- 3. heads -> segments.  D = sum over the references so far of (decoded - encoded) token bytes; a token
+    //         at staged position p starts at output byte (p - soff) + D - skip ----
+    uint32_t nseg = 0;  // governor entries 1..nseg
+    uint32_t npiece = 0;
     int D = 0;
-    for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
+    for (uint32_t c0 = 0; c0 < nheads; c0 += 32) {
         const uint32_t c = c0 + lane;
-        const uint32_t cv = c < ncand ? S.cands[c] : 0u;
-        const bool head = (cv & CAND_HEAD) != 0;
-        if (__ballot_sync(0xffffffffu, head) == 0) continue;
-        const uint32_t p = cv & 0xFFF;
-        uint32_t idx = 0, from = 0, tl = 0;
+        const bool head = c < nheads;
+        uint32_t p = 0, idx = 0, from = 0, tl = 0;
         int d = 0;
         if (head) {
-            const bool big = EB[p + 1] == 1;
-            idx = EB[p + 2] | (EB[p + 3] << 8);
-            const uint32_t to = EB[p + 4] | (EB[p + 5] << 8);
-            from = big ? (uint32_t) (EB[p + 6] | (EB[p + 7] << 8)) : to - EB[p + 1];
+            p = S.ps.heads[c];
+            const uint32_t b1 = SB[p + 1];
+            const bool big = b1 == 1;
+            idx = SB[p + 2] | (SB[p + 3] << 8);
+            const uint32_t to = SB[p + 4] | (SB[p + 5] << 8);
+            from = big ? (uint32_t) (SB[p + 6] | (SB[p + 7] << 8)) : to - b1;
             if (to <= from || from > 0xFFFF) {
                 atomicExch(err, 5u);
                 from = to;
@@ -195,195 +293,236 @@ k_token_scan(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_
         int inc = d;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
-            int o = __shfl_up_sync(0xffffffffu, inc, dd);
+            int o = __shfl_up_sync(FULL, inc, dd);
             if ((int) lane >= dd) inc += o;
         }
-        const int rel = (int) p + D + (inc - d) - (int) skip;  // output position of the token's first byte
+        const int rel = (int) (p - soff) + D + (inc - d) - (int) skip;  // output position of the token's first byte
         const uint32_t k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
         const uint32_t k1 = (int) tl + rel > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
         const bool emit = head && k0 < k1;
-        const uint32_t em = __ballot_sync(0xffffffffu, emit);
+        const bool initial = emit && rel < 0;  // the tail of a token that began in the previous tile (only the first head)
+        const uint32_t em = __ballot_sync(FULL, emit && !initial);
+        uint32_t sbase = 0, per = 0, ks = k0, us = 0, len = 0, np = 0;
         if (emit) {
-            const uint32_t sidx = nseg + __popc(em & lt);
+            const uint32_t sidx = initial ? 0u : 1u + nseg + __popc(em & lt);
             const uint32_t src_g = chunk_first + idx;
-            uint32_t sbase, per = 0;
             if (src_g == g) {  // self reference (PiXiuStr.h:168-181): overlapping copies repeat with this period
                 const uint32_t period = (uint32_t) ((int) t0 + rel) - from;
                 sbase = rec_base + from;
                 per = tl > period ? period : 0u;
+                if ((int) t0 + rel <= (int) from) atomicExch(err, 3u);
             } else {
                 if (src_g > g) atomicExch(err, 3u);
                 sbase = (src_g > g ? 0u : V.arena_off[src_g]) + from;
             }
-            if (sidx < SEG_MAX) {
-                const uint32_t srel = (uint32_t) (rel + (int) k0);
-                S.seg_base[sidx] = sbase;
-                S.seg_k0[sidx] = (uint16_t) k0;
-                S.seg_per[sidx] = (uint16_t) per;
-                S.seg_rel[sidx] = (uint16_t) srel;
-                S.seg_len[sidx] = (uint16_t) (k1 - k0);
-                S.seg_delta[sidx] = (uint16_t) ((int) skip - (D + inc));
-                atomicOr(&S.startb[(srel + mis) >> 5], 1u << ((srel + mis) & 31));
+            len = k1 - k0;
+            if (per) {
+                ks = k0 % per;
+                if (ks + len <= per) per = 0;  // this part does not wrap: a plain copy out of the first period
+            }
+            us = (uint32_t) (rel + (int) k0) + mis;
+            if (sidx <= SEG_MAX) {
+                S.seg_ed[sidx] = (us + len) | (((uint32_t) ((int) (soff + skip) - (D + inc)) & 0xFFFFu) << 16);
+                if (!initial) atomicOr(&S.startb[us >> 5], 1u << (us & 31));
+            }
+            // pieces of this segment: a short plain segment is one piece; longer ones are cut at the 32-byte
+            // boundaries of the SOURCE, so that a single word of the "final" bitmap decides whether a piece is ready
+            if (per != 0 && per < 32) {
+                np = (len + 31) >> 5;
+            } else if (per == 0) {
+                const uint32_t A = sbase + ks;
+                np = len <= 32 ? 1u : ((A + len - 1) >> 5) - (A >> 5) + 1;
+            } else {
+                for (uint32_t pos = ks, rem = len; rem; np++) {
+                    const uint32_t n = min(min(32u - ((sbase + pos) & 31u), per - pos), rem);
+                    pos = pos + n == per ? 0u : pos + n;
+                    rem -= n;
+                }
+            }
+        }
+        uint32_t pinc = np;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, pinc, dd);
+            if ((int) lane >= dd) pinc += o;
+        }
+        uint32_t slot = npiece + pinc - np;
+        if (np && slot + np <= PIECE_MAX) {
+            if (per != 0 && per < 32) {
+                for (uint32_t o = 0; o < len; o += 32, slot++) {
+                    S.p_src[slot] = sbase;
+                    S.p_meta[slot] = (us + o) | ((min(32u, len - o) - 1) << 12) | (per << 17) | (((ks + o) % per) << 22);
+                }
+            } else if (per == 0 && len <= 32) {
+                S.p_src[slot] = sbase + ks;
+                S.p_meta[slot] = us | ((len - 1) << 12);
+            } else {
+                const uint32_t wrap = per ? per : 0xFFFFFFFFu;
+                for (uint32_t pos = ks, o = 0; o < len; slot++) {
+                    const uint32_t n = min(min(32u - ((sbase + pos) & 31u), wrap - pos), len - o);
+                    S.p_src[slot] = sbase + pos;
+                    S.p_meta[slot] = (us + o) | ((n - 1) << 12);
+                    pos = pos + n == wrap ? 0u : pos + n;
+                    o += n;
+                }
             }
         }
         nseg += __popc(em);
-        D += __shfl_sync(0xffffffffu, inc, 31);
+        npiece += __shfl_sync(FULL, pinc, 31);
+        D += __shfl_sync(FULL, inc, 31);
     }
-    if ((int) ne + D < (int) (skip + nbytes) || nseg > SEG_MAX) {
+    if ((int) ne + D < (int) (skip + nbytes) || nseg > SEG_MAX || npiece > PIECE_MAX) {
         if (lane == 0) atomicExch(err, 6u);
         return;
     }
     __syncwarp();
-    // segment starts before each bitmap word (UB_WORDS <= 96: three words per lane)
-    {
-        const uint32_t c0 = __popc(S.startb[lane]);
-        const uint32_t c1 = __popc(S.startb[32 + lane]);
-        const uint32_t c2 = lane < UB_WORDS - 64 ? __popc(S.startb[64 + lane]) : 0u;
-        uint32_t i0 = c0, i1 = c1, i2 = c2;
+    {  // segment starts before each bitmap word
+        const uint32_t c0 = __popc(S.startb[3 * lane]), c1 = __popc(S.startb[3 * lane + 1]), c2 = __popc(S.startb[3 * lane + 2]);
+        uint32_t inc = c0 + c1 + c2;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o0 = __shfl_up_sync(0xffffffffu, i0, d), o1 = __shfl_up_sync(0xffffffffu, i1, d),
-                     o2 = __shfl_up_sync(0xffffffffu, i2, d);
-            if ((int) lane >= d) i0 += o0, i1 += o1, i2 += o2;
+            uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if ((int) lane >= d) inc += o;
         }
-        const uint32_t t0s = __shfl_sync(0xffffffffu, i0, 31), t1s = __shfl_sync(0xffffffffu, i1, 31);
-        S.wprefix[lane] = (uint16_t) (i0 - c0);
-        S.wprefix[32 + lane] = (uint16_t) (t0s + i1 - c1);
-        if (lane < UB_WORDS - 64) S.wprefix[64 + lane] = (uint16_t) (t0s + t1s + i2 - c2);
+        const uint32_t b = inc - (c0 + c1 + c2);
+        S.wprefix[3 * lane] = (uint16_t) b;
+        S.wprefix[3 * lane + 1] = (uint16_t) (b + c0);
+        S.wprefix[3 * lane + 2] = (uint16_t) (b + c0 + c1);
+        const uint32_t nrows0 = (npiece + 31) / 32;
+        if (lane < PIECE_ROWS) S.pend[lane] = lane < nrows0 ? (32 * (lane + 1) <= npiece ? 0xFFFFFFFFu : (1u << (npiece - 32 * lane)) - 1) : 0u;
     }
     __syncwarp();
-    // ---- 3. per output byte, 4 per lane.  u = output position + mis, so that u = 0 is an aligned arena word ----
-    const uint32_t nu = nbytes + mis;
-    uint8_t *dstu = V.arena + rec_base + t0 - mis;
-    uint32_t *gptru = V.ptr + rec_base + t0 - mis;
+    // ---- 4. literal bytes, one output word per lane and step.  The bytes of a word that belong to reference
+    //         segments are overwritten later by this warp's own copies, so interior words are stored whole ----
+    uint8_t *dstu = V.arena + B0;
     for (uint32_t u0 = 0; u0 < nu; u0 += 128) {
         const uint32_t u = u0 + 4 * lane;
-        const uint32_t sw = S.startb[u >> 5], sh = u & 31;
-        uint32_t cnt = S.wprefix[u >> 5] + __popc(sw & ((1u << sh) - 1));
-        const uint32_t nibs = (sw >> sh) & 0xFu;
-        const uint32_t lo = u < mis ? mis - u : 0u;
-        const uint32_t hi = u + 4 <= nu ? 4u : (nu > u ? nu - u : 0u);
-        uint32_t litn = 0;
-        bool generic = hi != 0;
-        if (nibs == 0 && lo == 0 && hi == 4) {  // one segment (or none) governs all four bytes
-            const uint32_t jj = u - mis;
-            uint32_t q = jj;
-            bool all_lit = true;
-            generic = false;
-            if (cnt) {
-                const uint32_t sgi = cnt - 1;
-                const uint32_t o = jj - S.seg_rel[sgi], len = S.seg_len[sgi];
-                if (o + 4 <= len) {
-                    all_lit = false;
-                    const uint32_t kk = S.seg_k0[sgi] + o, per = S.seg_per[sgi], sb = S.seg_base[sgi];
-                    uint4 pv;
-                    if (per) pv = make_uint4(sb + kk % per, sb + (kk + 1) % per, sb + (kk + 2) % per, sb + (kk + 3) % per);
-                    else pv = make_uint4(sb + kk, sb + kk + 1, sb + kk + 2, sb + kk + 3);
-                    *reinterpret_cast<uint4 *>(gptru + u) = pv;
-                } else if (o >= len) {
-                    q = min((jj + S.seg_delta[sgi]) & 0xFFFFu, ENC_MAX);
+        uint32_t m = 0;
+        if (u < nu) {
+            const uint32_t sw = S.startb[u >> 5], sh = u & 31;
+            const uint32_t gi = S.wprefix[u >> 5] + __popc(sw & ((1u << sh) - 1));  // governing entry of the word's first byte
+            const uint32_t nibs = (sw >> sh) & 0xFu;
+            const uint32_t ed = S.seg_ed[gi];
+            const uint32_t lo = max(u, ed & 0xFFFFu);
+            const uint32_t hi = min(nibs ? u + __ffs(nibs) - 1 : u + 4, nu);
+            if (lo < hi) {
+                m = ((1u << (hi - u)) - 1) & ~((1u << (lo - u)) - 1);
+                const uint32_t q = min((u - mis + (ed >> 16)) & 0xFFFFu, STG_BYTES - 8);
+                const uint32_t wv = __funnelshift_r(S.stg[q >> 2], S.stg[(q >> 2) + 1], 8 * (q & 3));
+                if (u >= mis && u + 4 <= nu) {
+                    *reinterpret_cast<uint32_t *>(dstu + u) = wv;
                 } else {
-                    all_lit = false;
-                    generic = true;
-                }
-            }
-            if (all_lit) {
-                const uint32_t qa = q >> 2;
-                *reinterpret_cast<uint32_t *>(dstu + u) = __funnelshift_r(S.encw[qa], S.encw[qa + 1], 8 * (q & 3));
-                litn = 0xFu;
-            }
-        }
-        if (generic) {
 #pragma unroll
-            for (uint32_t i = 0; i < 4; i++) {
-                cnt += (nibs >> i) & 1u;
-                if (i < lo || i >= hi) continue;
-                const uint32_t jj = u + i - mis;
-                uint32_t q = jj;
-                bool isref = false;
-                if (cnt) {
-                    const uint32_t sgi = cnt - 1;
-                    const uint32_t o = jj - S.seg_rel[sgi];
-                    if (o < S.seg_len[sgi]) {
-                        isref = true;
-                        const uint32_t kk = S.seg_k0[sgi] + o, per = S.seg_per[sgi];
-                        gptru[u + i] = S.seg_base[sgi] + (per ? kk % per : kk);
-                    } else {
-                        q = min((jj + S.seg_delta[sgi]) & 0xFFFFu, ENC_MAX);
-                    }
-                }
-                if (!isref) {
-                    dstu[u + i] = EB[q];
-                    litn |= 1u << i;
+                    for (int i = 0; i < 4; i++)
+                        if ((m >> i) & 1u) dstu[u + i] = (uint8_t) (wv >> (8 * i));
                 }
             }
         }
-        uint32_t v = litn << (4 * (lane & 7));
-        v |= __shfl_xor_sync(0xffffffffu, v, 1);
-        v |= __shfl_xor_sync(0xffffffffu, v, 2);
-        v |= __shfl_xor_sync(0xffffffffu, v, 4);
-        if ((lane & 7) == 0) S.lit[(u0 >> 5) + (lane >> 3)] = v;
+        uint32_t v = m << (4 * (lane & 7));
+        v |= __shfl_xor_sync(FULL, v, 1);
+        v |= __shfl_xor_sync(FULL, v, 2);
+        v |= __shfl_xor_sync(FULL, v, 4);
+        if ((lane & 7) == 0) S.finw[(u0 >> 5) + (lane >> 3)] = v;
     }
     __syncwarp();
-    // ---- 4. the tile's slice of the literal bitmap (zero-initialised map, OR-ed in: tiles share words) ----
-    {
-        const uint32_t B0 = rec_base + t0 - mis, sh = B0 & 31;
-        uint32_t *lm = V.litmap + (B0 >> 5);
-        const uint32_t nsw = (nu + 31) / 32, ngw = (sh + nu + 31) / 32;
-        for (uint32_t j = lane; j < ngw; j += 32) {
-            uint32_t lo = j < nsw ? S.lit[j] : 0u, hi = (j > 0 && sh) ? S.lit[j - 1] : 0u;
-            uint32_t v = sh ? ((lo << sh) | (hi >> (32 - sh))) : lo;
-            if (v) atomicOr(&lm[j], v);
-        }
-    }
-}
-
-// K11: four arena bytes per thread; every non-literal byte chases its pointer chain to a literal
-__global__ void __launch_bounds__(256)
-k_resolve(uint32_t n, uint8_t *__restrict__ arena, uint32_t *__restrict__ ptr, const uint32_t *__restrict__ litmap,
-          uint32_t *__restrict__ unfinished, uint32_t *__restrict__ err) {
-    const uint32_t i4 = (blockIdx.x * 256 + threadIdx.x) * 4;
-    bool pending = false;
-    if (i4 < n) {
-        const uint32_t bits = (litmap[i4 >> 5] >> (i4 & 31)) & 0xFu;
-        if (bits != 0xFu) {
-            uint32_t word = *reinterpret_cast<const uint32_t *>(arena + i4);
-            uint32_t changed = 0;
+    fence_gpu();
+    flush_final(S.finw, lm, fsh, ngw, lane, pub0, pub1, pub2);
+    // ---- 5. copy pieces, one per lane and row: poll the source window (acquire), copy arena -> arena with
+    //         aligned 32-bit stores where a whole word belongs to the piece, publish the piece's bits (release) ----
+    uint32_t remaining = npiece, spins = 0;
+    const uint32_t nrows = (npiece + 31) / 32;
+    while (remaining) {
+        uint32_t any = 0;
+        for (uint32_t row = 0; row < nrows; row++) {
+            const uint32_t pm = S.pend[row];
+            if (!pm) continue;
+            bool ready = false;
+            uint32_t meta = 0, a = 0;
+            if ((pm >> lane) & 1u) {
+                meta = S.p_meta[row * 32 + lane];
+                a = S.p_src[row * 32 + lane];
+                const uint32_t per = (meta >> 17) & 31u;
+                const uint32_t n = per ? per : ((meta >> 12) & 31u) + 1;
+                const uint32_t *fw = V.fin + (a >> 5);
+                const uint32_t bs = a & 31, need = 0xFFFFFFFFu >> (32 - n);
+                const uint32_t nlo = need << bs;
+                ready = (ld_acquire_u32(fw) & nlo) == nlo;
+                if (ready && bs + n > 32) {
+                    const uint32_t nhi = need >> (32 - bs);
+                    ready = (ld_acquire_u32(fw + 1) & nhi) == nhi;
+                }
+            }
+            if (ready) {
+                const uint32_t us = meta & 0xFFFu, n = ((meta >> 12) & 31u) + 1, per = (meta >> 17) & 31u;
+                uint8_t *dst = dstu + us;
+                if (per) {
+                    const uint32_t ph = meta >> 22;
+                    for (uint32_t j = 0; j < n; j += 4) {  // four loads in flight
+                        uint8_t bv[4];
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const uint32_t i = i4 + b;
-                if (((bits >> b) & 1u) || i >= n) continue;
-                uint32_t p = ptr[i];
-                bool done = false;
-                for (int h = 0; h < RESOLVE_HOPS; h++) {
-                    if (p >= i) {  // sources always precede their byte in the arena: corrupt input
-                        atomicExch(err, 7u);
-                        done = true;
-                        p = i;
-                        break;
+                        for (int i = 0; i < 4; i++) bv[i] = __ldcg(V.arena + a + (ph + j + i) % per);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            if (j + i < n) dst[j + i] = bv[i];
                     }
-                    if ((litmap[p >> 5] >> (p & 31)) & 1u) {
-                        word = (word & ~(0xFFu << (8 * b))) | ((uint32_t) arena[p] << (8 * b));
-                        changed |= 1u << b;
-                        done = true;
-                        break;
-                    }
-                    p = ptr[p];
-                }
-                if (p != i) ptr[i] = p;  // the literal origin, or an ancestor further up the chain
-                pending |= !done;
-            }
-            if (changed) {
-                if (i4 + 3 < n) {
-                    *reinterpret_cast<uint32_t *>(arena + i4) = word;
                 } else {
-                    for (int b = 0; b < 4; b++)
-                        if ((changed >> b) & 1u) arena[i4 + b] = (uint8_t) (word >> (8 * b));
+                    // destination word t holds piece bytes [4t - da, 4t - da + 4); its source bytes straddle the
+                    // aligned source words t + c and t + c + 1
+                    const uint32_t da = us & 3, sa = a & 3;
+                    const int delta = (int) sa - (int) da;
+                    const uint32_t sh = 8u * (uint32_t) (delta & 3);
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(V.arena + (a - sa)) + (delta < 0 ? -1 : 0);
+                    const uint32_t nsw = (sa + n + 3) >> 2;  // aligned source words the piece touches
+                    const int lastw = (int) nsw - 1 + (delta < 0 ? 1 : 0);  // last index (from wp) that may be read
+                    uint32_t *dw = reinterpret_cast<uint32_t *>(dst - da);
+                    const uint32_t ndw = (da + n + 3) >> 2;
+                    for (uint32_t t0w = 0; t0w < ndw; t0w += 4) {
+                        uint32_t wv[5];
+#pragma unroll
+                        for (int q = 0; q < 5; q++) {
+                            const int wi = (int) t0w + q;
+                            wv[q] = (wi <= lastw && !(delta < 0 && wi == 0)) ? __ldcg(wp + wi) : 0u;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t t = t0w + q;
+                            if (t < ndw) {
+                                const uint32_t x = __funnelshift_r(wv[q], wv[q + 1], sh);
+                                const int b0 = (int) (4 * t) - (int) da;  // piece byte of the word's first byte
+                                if (b0 >= 0 && b0 + 4 <= (int) n) {
+                                    dw[t] = x;
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 4; i++)
+                                        if (b0 + i >= 0 && b0 + i < (int) n) reinterpret_cast<uint8_t *>(dw + t)[i] = (uint8_t) (x >> (8 * i));
+                                }
+                            }
+                        }
+                    }
                 }
+                // publish: the copied bytes before their bits
+                const uint32_t B = B0 + us, bits = 0xFFFFFFFFu >> (32 - n), bs = B & 31;
+                red_release_or_u32(V.fin + (B >> 5), bits << bs);
+                if (bs + n > 32) red_release_or_u32(V.fin + (B >> 5) + 1, bits >> (32 - bs));
+            }
+            const uint32_t rb = __ballot_sync(FULL, ready);
+            if (rb) {
+                if (lane == 0) S.pend[row] = pm & ~rb;
+                remaining -= __popc(rb);
+                any = 1;
             }
         }
+        __syncwarp();
+        if (!any) {
+            if (++spins > SPIN_LIMIT || ld_relaxed_u32(err) != 0) {
+                if (lane == 0) atomicCAS(err, 0u, 8u);
+                return;
+            }
+            if (spins > 16) __nanosleep(spins > 256 ? 400 : 64);
+        } else {
+            spins = 0;
+        }
     }
-    if (__syncthreads_or(pending) && threadIdx.x == 0) atomicAdd(unfinished, 1u);
 }
 
 // K12: arena -> caller layout, one warp per requested record
@@ -422,7 +561,9 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     // direct mode: the request is exactly the arena order and the caller's layout is packed the same way
     bool direct = ((uintptr_t) d_out & 127) == 0;
     size_t ri = 0;
-    for (auto &cm : chunk_max)
+    std::vector<uint64_t> chunk_tiles;  // tiles per touched chunk
+    for (auto &cm : chunk_max) {
+        const size_t before = wt.size();
         for (uint32_t g = cm.first; g <= cm.second; g++) {
             if (direct) {
                 if (ri < recs.size() && recs[ri] == g && out_off[ri] == arena_bytes) ri++;
@@ -439,14 +580,35 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
             lo_g = std::min(lo_g, g);
             hi_g = std::max(hi_g, g);
         }
+        chunk_tiles.push_back(wt.size() - before);
+    }
     if (ri != recs.size()) direct = false;
     if (arena_bytes >= 0xFFFFFF00ull) throw std::runtime_error("decode: arena of one call exceeds 4 GiB; split the batch");
     if (!direct) dec_scratch.reserve_discard(arena_bytes + 256);  // same packed layout, private buffer
     const uint64_t n_work = wt.size();
+    if (chunk_tiles.size() > 1) {
+        // tiles of different chunks are independent (references are chunk-local): hand them out round-robin, so that
+        // as many dependency chains as there are chunks advance side by side; the order inside a chunk is kept
+        std::vector<uint32_t> wt2(n_work), wr2(n_work);
+        std::vector<uint64_t> cur(chunk_tiles.size()), end(chunk_tiles.size());
+        uint64_t acc = 0;
+        for (size_t c = 0; c < chunk_tiles.size(); c++) {
+            cur[c] = acc;
+            acc += chunk_tiles[c];
+            end[c] = acc;
+        }
+        uint64_t o = 0;
+        while (o < n_work)
+            for (size_t c = 0; c < chunk_tiles.size(); c++)
+                if (cur[c] < end[c]) {
+                    wt2[o] = wt[cur[c]];
+                    wr2[o++] = wr[cur[c]++];
+                }
+        wt.swap(wt2);
+        wr.swap(wr2);
+    }
     uint8_t *arena = direct ? d_out : dec_scratch.p;
-    dec_loc.reserve_discard(1);  // (unused in this scheme)
-    dec_flags.reserve_discard(arena_bytes / 32 + 64);        // literal bitmap
-    dec_ptr.reserve_discard(arena_bytes + 64);                // source pointers
+    dec_flags.reserve_discard(arena_bytes / 32 + 64);        // "final" bitmap
     dec_aoff.reserve_discard(NR + 1);
     PX_CUDA(cudaMemcpyAsync(dec_aoff.p + lo_g, aoff.data() + lo_g, (size_t) (hi_g - lo_g + 1) * sizeof(uint32_t),
                             cudaMemcpyHostToDevice, st));
@@ -454,29 +616,20 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     PX_CUDA(cudaMemcpyAsync(dec_work.p, wt.data(), n_work * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     PX_CUDA(cudaMemcpyAsync(dec_work.p + n_work, wr.data(), n_work * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     dec_ctr.reserve_discard(64);
-    PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));
+    PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));  // [0] error, [1] tile ticket
     PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, (arena_bytes / 32 + 2) * sizeof(uint32_t), st));
     DecodeView V{d_enc.ptr(), d_enc_off.p, d_enc_len.p, d_dec_len.p, d_first.p, d_tile_base.p, d_tile_desc.p,
-                 dec_aoff.p, arena, dec_ptr.p, dec_flags.p};
+                 dec_aoff.p, arena, dec_flags.p};
     const size_t smem = sizeof(WarpSmem) * DEC_WARPS;
     // (per device and cheap: no process-wide "already done" flag, a process may drive several GPUs)
-    PX_CUDA(cudaFuncSetAttribute(k_token_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    PX_CUDA(cudaFuncSetAttribute(k_decode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     PX_CUDA(cudaEventRecord(ev0, st));
     prof.begin(PC_DECODE, st);
-    k_token_scan<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(
+    k_decode_tiles<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(
         V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p);
     int nl = 1;
-    // resolve rounds: one is enough unless chains are deeper than RESOLVE_HOPS
     uint32_t h_ctr[2] = {0, 0};
-    for (int round = 0; round < 40; round++) {
-        k_resolve<<<(unsigned) div_up<uint64_t>(div_up<uint64_t>(arena_bytes, 4), 256), 256, 0, st>>>((uint32_t) arena_bytes, arena, dec_ptr.p,
-                                                                               dec_flags.p, dec_ctr.p + 1 + round, dec_ctr.p);
-        nl++;
-        PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        PX_CUDA(cudaMemcpyAsync(h_ctr + 1, dec_ctr.p + 1 + round, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        PX_CUDA(cudaStreamSynchronize(st));
-        if (h_ctr[0] || h_ctr[1] == 0) break;
-    }
+    PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (!direct) {
         // requested records -> caller layout
         DevBuf<uint32_t> &d_recs = dec_reqs;
@@ -498,7 +651,6 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     last_get_ms = ms;
     prof.collect();
     if (h_ctr[0]) throw std::runtime_error("decode: kernel reported error " + std::to_string(h_ctr[0]));
-    if (h_ctr[1]) throw std::runtime_error("decode: reference chains did not resolve");
 }
 
 // Host-side token walk of one encoded record: validates it, returns its decoded length and

@@ -102,12 +102,11 @@ struct Store {
     // ---- decode scratch ----
     DevBuf<uint8_t> dec_scratch;   // decoded arena when the caller's layout differs from arena order
     DevBuf<uint64_t> dec_loc;      // output offsets of the requested records
-    DevBuf<uint32_t> dec_flags;    // literal bitmap of the arena (1 bit per byte)
-    DevBuf<uint32_t> dec_ptr;      // source pointer of every non-literal arena byte
+    DevBuf<uint32_t> dec_flags;    // "final" bitmap of the arena (1 bit per byte)
     DevBuf<uint32_t> dec_aoff;     // per record: offset in the arena
     DevBuf<uint32_t> dec_reqs;     // requested record ids
     DevBuf<uint32_t> dec_work;     // work list: tile ids, then record ids
-    DevBuf<uint32_t> dec_ctr;      // [0] error, [1+r] unfinished CTAs of resolve round r
+    DevBuf<uint32_t> dec_ctr;      // [0] error, [1] tile ticket
 
     // ---- staging for batches ----
     DevBuf<uint8_t> in_keys, in_vals, out_stage;
