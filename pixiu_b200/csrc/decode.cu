@@ -39,6 +39,8 @@ constexpr uint32_t SEG_MAX = TILE / 7 + 4;
 constexpr uint32_t PIECE_MAX = SEG_MAX + 1 + 4 * (TILE / 32);
 constexpr uint32_t PIECE_ROWS = (PIECE_MAX + 31) / 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
+constexpr uint32_t GIVEUP_SPINS = 64;   // polls without any progress after which a tile hands its open pieces to k_resolve
+constexpr int RESOLVE_HOPS = 48;
 static_assert(STG_BYTES <= BM_WORDS * 32 && TILE + 4 <= (BM_WORDS - 1) * 32, "bitmaps too small");
 
 struct DecodeView {
@@ -48,6 +50,8 @@ struct DecodeView {
     const uint32_t *arena_off;  // per record: offset of its decoded bytes in the arena
     uint8_t *arena;
     uint32_t *fin;              // per arena byte: 1 bit, set = the byte holds its final value
+    uint32_t *gup;              // per arena byte: 1 bit, set = the byte was handed to k_resolve (its source is in ptr)
+    uint32_t *ptr;              // per arena byte: source position, written only for handed-over bytes
 };
 
 struct ParseSmem {                  // parse scratch
@@ -110,7 +114,7 @@ __device__ __forceinline__ void flush_final(const uint32_t *finw, uint32_t *lm, 
 //      is finished or held by a resident warp: waiting cannot deadlock); copied ranges are published the same way
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
-               uint32_t n_work, uint32_t *__restrict__ ctr) {
+               uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t giveup_spins) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -436,21 +440,47 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
         for (uint32_t row = 0; row < nrows; row++) {
             const uint32_t pm = S.pend[row];
             if (!pm) continue;
-            bool ready = false;
+            bool ready = false, giveup = false;
             uint32_t meta = 0, a = 0;
             if ((pm >> lane) & 1u) {
                 meta = S.p_meta[row * 32 + lane];
                 a = S.p_src[row * 32 + lane];
                 const uint32_t per = (meta >> 17) & 31u;
                 const uint32_t n = per ? per : ((meta >> 12) & 31u) + 1;
-                const uint32_t *fw = V.fin + (a >> 5);
-                const uint32_t bs = a & 31, need = 0xFFFFFFFFu >> (32 - n);
+                const uint32_t wi = a >> 5, bs = a & 31, need = 0xFFFFFFFFu >> (32 - n);
                 const uint32_t nlo = need << bs;
-                ready = (ld_acquire_u32(fw) & nlo) == nlo;
-                if (ready && bs + n > 32) {
-                    const uint32_t nhi = need >> (32 - bs);
-                    ready = (ld_acquire_u32(fw + 1) & nhi) == nhi;
+                uint32_t miss = nlo & ~ld_acquire_u32(V.fin + wi), mw = wi;
+                if (miss == 0 && bs + n > 32) {
+                    miss = (need >> (32 - bs)) & ~ld_acquire_u32(V.fin + wi + 1);
+                    mw = wi + 1;
                 }
+                ready = miss == 0;
+                // a missing byte that its own tile handed to k_resolve will not become final in this kernel
+                if (!ready) giveup = spins >= giveup_spins || (ld_relaxed_u32(V.gup + mw) & miss) != 0;
+            }
+            uint32_t gb = __ballot_sync(FULL, giveup);
+            if (gb) {
+                // hand the pieces over: per byte source pointers (self-overlapping references folded onto their first
+                // period), one coalesced row of pointers per piece
+                const uint32_t gmask = gb;
+                while (gb) {
+                    const int r = __ffs(gb) - 1;
+                    gb &= gb - 1;
+                    const uint32_t rm = __shfl_sync(FULL, meta, r), ra = __shfl_sync(FULL, a, r);
+                    const uint32_t n = ((rm >> 12) & 31u) + 1, per = (rm >> 17) & 31u;
+                    if (lane < n) V.ptr[B0 + (rm & 0xFFFu) + lane] = ra + (per ? ((rm >> 22) + lane) % per : lane);
+                }
+                if (giveup) {
+                    const uint32_t B = B0 + (meta & 0xFFFu), n = ((meta >> 12) & 31u) + 1;
+                    const uint32_t bits = 0xFFFFFFFFu >> (32 - n), bs = B & 31;
+                    atomicOr(V.gup + (B >> 5), bits << bs);
+                    if (bs + n > 32) atomicOr(V.gup + (B >> 5) + 1, bits >> (32 - bs));
+                }
+                if (lane == 0) atomicAdd(ctr + 2, (uint32_t) __popc(gmask));
+                remaining -= __popc(gmask);
+                any = 1;
+                if (lane == 0) S.pend[row] = pm & ~gmask;
+                __syncwarp();
             }
             if (ready) {
                 const uint32_t us = meta & 0xFFFu, n = ((meta >> 12) & 31u) + 1, per = (meta >> 17) & 31u;
@@ -507,7 +537,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
             }
             const uint32_t rb = __ballot_sync(FULL, ready);
             if (rb) {
-                if (lane == 0) S.pend[row] = pm & ~rb;
+                if (lane == 0) S.pend[row] &= ~rb;
                 remaining -= __popc(rb);
                 any = 1;
             }
@@ -523,6 +553,53 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
             spins = 0;
         }
     }
+}
+
+// K11 (only when K10 handed pieces over): a warp per 1 KiB of arena looks at its 32 words of the hand-over bitmap
+// and, for every word with bits set, resolves the 32 bytes one per lane: each handed-over byte chases its pointer
+// chain to a final byte.  Chains longer than RESOLVE_HOPS park their progress in the pointer array and the kernel is
+// re-run: concurrent shortening makes the remaining rounds logarithmic in the nesting depth.  Final bytes are only
+// read, never written, so no thread waits on another.
+__global__ void __launch_bounds__(256)
+k_resolve(uint32_t n, uint8_t *__restrict__ arena, uint32_t *__restrict__ ptr, const uint32_t *__restrict__ fin,
+          uint32_t *__restrict__ gup, uint32_t *__restrict__ unfinished, uint32_t *__restrict__ err) {
+    const uint32_t lane = lane_id();
+    const uint32_t w0 = ((blockIdx.x * 256 + threadIdx.x) >> 5) * 32;  // first bitmap word of the warp
+    const uint32_t nwords = (n + 31) >> 5;
+    bool pending = false;
+    const uint32_t mine = w0 + lane < nwords ? gup[w0 + lane] : 0u;
+    uint32_t todo = __ballot_sync(0xffffffffu, mine != 0);
+    while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t bits = __shfl_sync(0xffffffffu, mine, k);
+        const uint32_t i = (w0 + k) * 32 + lane;
+        bool done = true;
+        if ((bits >> lane) & 1u) {
+            uint32_t p = ptr[i];
+            done = false;
+            for (int h = 0; h < RESOLVE_HOPS; h++) {
+                if (p >= i) {  // sources always precede their byte in the arena: corrupt input
+                    atomicExch(err, 7u);
+                    done = true;
+                    p = i;
+                    break;
+                }
+                if ((fin[p >> 5] >> (p & 31)) & 1u) {
+                    arena[i] = arena[p];
+                    done = true;
+                    break;
+                }
+                p = ptr[p];
+            }
+            if (p != i) ptr[i] = p;  // the final origin, or an ancestor further up the chain
+            pending |= !done;
+        }
+        // bytes resolved for good leave the bitmap (later rounds skip them; chains through them end at ptr -> final)
+        const uint32_t still = __ballot_sync(0xffffffffu, !done);
+        if (lane == 0 && still != bits) gup[w0 + k] = still;
+    }
+    if (__syncthreads_or(pending) && threadIdx.x == 0) atomicAdd(unfinished, 1u);
 }
 
 // K12: arena -> caller layout, one warp per requested record
@@ -608,7 +685,9 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
         wr.swap(wr2);
     }
     uint8_t *arena = direct ? d_out : dec_scratch.p;
-    dec_flags.reserve_discard(arena_bytes / 32 + 64);        // "final" bitmap
+    const size_t bm_words = arena_bytes / 32 + 64;
+    dec_flags.reserve_discard(2 * bm_words);                  // "final" bitmap, then the "handed over" bitmap
+    dec_ptr.reserve_discard(arena_bytes + 64);                // source pointers (touched only for handed-over bytes)
     dec_aoff.reserve_discard(NR + 1);
     PX_CUDA(cudaMemcpyAsync(dec_aoff.p + lo_g, aoff.data() + lo_g, (size_t) (hi_g - lo_g + 1) * sizeof(uint32_t),
                             cudaMemcpyHostToDevice, st));
@@ -616,20 +695,38 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     PX_CUDA(cudaMemcpyAsync(dec_work.p, wt.data(), n_work * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     PX_CUDA(cudaMemcpyAsync(dec_work.p + n_work, wr.data(), n_work * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     dec_ctr.reserve_discard(64);
-    PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));  // [0] error, [1] tile ticket
-    PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, (arena_bytes / 32 + 2) * sizeof(uint32_t), st));
+    PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));  // [0] error, [1] tile ticket, [2] pieces handed over
+    PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, 2 * bm_words * sizeof(uint32_t), st));
     DecodeView V{d_enc.ptr(), d_enc_off.p, d_enc_len.p, d_dec_len.p, d_first.p, d_tile_base.p, d_tile_desc.p,
-                 dec_aoff.p, arena, dec_flags.p};
+                 dec_aoff.p, arena, dec_flags.p, dec_flags.p + bm_words, dec_ptr.p};
     const size_t smem = sizeof(WarpSmem) * DEC_WARPS;
     // (per device and cheap: no process-wide "already done" flag, a process may drive several GPUs)
     PX_CUDA(cudaFuncSetAttribute(k_decode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const char *gs = getenv("PIXIU_GIVEUP_SPINS");  // tuning knob
+    const uint32_t giveup_spins = gs ? (uint32_t) atoi(gs) : GIVEUP_SPINS;
     PX_CUDA(cudaEventRecord(ev0, st));
     prof.begin(PC_DECODE, st);
     k_decode_tiles<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(
-        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p);
+        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins);
     int nl = 1;
-    uint32_t h_ctr[2] = {0, 0};
-    PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    uint32_t h_ctr[4] = {0, 0, 0, 0};
+    PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    last_handed_over = h_ctr[2];
+    if (getenv("PIXIU_TRACE")) fprintf(stderr, "[decode] %llu tiles, %u pieces handed to k_resolve\n", (unsigned long long) n_work, h_ctr[2]);
+    if (h_ctr[0] == 0 && h_ctr[2] != 0) {
+        // deep reference chains: the pieces the data-flow pass handed over are resolved by pointer chasing
+        for (int round = 0; round < 40; round++) {
+            k_resolve<<<(unsigned) div_up<uint64_t>(div_up<uint64_t>(arena_bytes, 32), 256), 256, 0, st>>>(
+                (uint32_t) arena_bytes, arena, dec_ptr.p, V.fin, V.gup, dec_ctr.p + 3 + round, dec_ctr.p);
+            nl++;
+            PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PX_CUDA(cudaMemcpyAsync(h_ctr + 3, dec_ctr.p + 3 + round, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PX_CUDA(cudaStreamSynchronize(st));
+            if (h_ctr[0] || h_ctr[3] == 0) break;
+        }
+        if (h_ctr[0] == 0 && h_ctr[3] != 0) h_ctr[0] = 9;  // chains did not resolve
+    }
     if (!direct) {
         // requested records -> caller layout
         DevBuf<uint32_t> &d_recs = dec_reqs;

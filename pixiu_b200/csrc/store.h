@@ -102,11 +102,13 @@ struct Store {
     // ---- decode scratch ----
     DevBuf<uint8_t> dec_scratch;   // decoded arena when the caller's layout differs from arena order
     DevBuf<uint64_t> dec_loc;      // output offsets of the requested records
-    DevBuf<uint32_t> dec_flags;    // "final" bitmap of the arena (1 bit per byte)
+    DevBuf<uint32_t> dec_flags;    // "final" bitmap of the arena (1 bit per byte), then the "handed over" bitmap
+    DevBuf<uint32_t> dec_ptr;      // source pointer of every arena byte handed to k_resolve
+    uint64_t last_handed_over = 0; // pieces the last decode handed to k_resolve
     DevBuf<uint32_t> dec_aoff;     // per record: offset in the arena
     DevBuf<uint32_t> dec_reqs;     // requested record ids
     DevBuf<uint32_t> dec_work;     // work list: tile ids, then record ids
-    DevBuf<uint32_t> dec_ctr;      // [0] error, [1] tile ticket
+    DevBuf<uint32_t> dec_ctr;      // [0] error, [1] tile ticket, [2] pieces handed over, [3+r] unfinished CTAs of resolve round r
 
     // ---- staging for batches ----
     DevBuf<uint8_t> in_keys, in_vals, out_stage;
