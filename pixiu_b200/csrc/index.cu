@@ -184,181 +184,24 @@ HostIndex::DeviceView HostIndex::device_view(cudaStream_t st) {
             PX_CUDA(cudaMemcpyAsync(d_diff.p, diff_at.data(), ni * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
             PX_CUDA(cudaMemcpyAsync(d_mask.p, mask.data(), ni * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
         }
-        if (nl) PX_CUDA(cudaMemcpyAsync(d_leaf_rec.p, leaf_rec.data(), nl * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (nl) {
+            d_leaf_klen.reserve_discard(nl + 1);
+            d_leaf_koff.reserve_discard(nl + 1);
+            PX_CUDA(cudaMemcpyAsync(d_leaf_rec.p, leaf_rec.data(), nl * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            PX_CUDA(cudaMemcpyAsync(d_leaf_klen.p, leaf_klen.data(), nl * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            PX_CUDA(cudaMemcpyAsync(d_leaf_koff.p, leaf_koff.data(), nl * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        }
+        // the key arena only ever grows: upload what is new
+        if (arena.size() > keys_uploaded) {
+            d_keys.reserve_keep(arena.size() + 16, keys_uploaded, st);
+            PX_CUDA(cudaMemcpyAsync(d_keys.p + keys_uploaded, arena.data() + keys_uploaded, arena.size() - keys_uploaded,
+                                    cudaMemcpyHostToDevice, st));
+            keys_uploaded = arena.size();
+        }
         PX_CUDA(cudaStreamSynchronize(st));
         dirty = false;
     }
-    return DeviceView{d_child0.p, d_child1.p, d_diff.p, d_mask.p, d_leaf_rec.p, root, has_root ? 1 : 0};
-}
-
-// ---------------------------------------------------------------------------------
-// device: partial decode straight from the compressed store
-// ---------------------------------------------------------------------------------
-struct ChaseView {
-    const uint8_t *enc;
-    const uint64_t *enc_off;
-    const uint32_t *enc_len, *dec_len, *first, *tile_base, *tile_desc;
-};
-
-// byte reader over an encoded record that fetches aligned 16-byte blocks (one global load per 16 encoded
-// bytes instead of one per byte: the token walk is a chain of dependent loads)
-struct EncReader {
-    const uint8_t *base;
-    uint64_t blk_addr = ~0ull;
-    uint64_t lo = 0, hi = 0;
-    __device__ explicit EncReader(const uint8_t *b) : base(b) {}
-    __device__ __forceinline__ uint32_t get(uint32_t e) {
-        uint64_t a = (uint64_t) (uintptr_t) (base + e), ba = a & ~15ull;
-        if (ba != blk_addr) {
-            uint4 v = __ldg(reinterpret_cast<const uint4 *>(ba));
-            lo = (uint64_t) v.x | ((uint64_t) v.y << 32);
-            hi = (uint64_t) v.z | ((uint64_t) v.w << 32);
-            blk_addr = ba;
-        }
-        uint32_t o = (uint32_t) (a & 15);
-        return (uint32_t) (((o < 8 ? lo : hi) >> (8 * (o & 7))) & 0xff);
-    }
-};
-
-// decoded byte `o` of record g, following back references to a literal (iterative, no stack)
-__device__ int resolve_byte(const ChaseView &V, uint32_t g, uint32_t o) {
-    for (int hops = 0; hops < (1 << 20); hops++) {
-        if (o >= V.dec_len[g]) return -1;
-        uint32_t t = o / TILE;
-        uint32_t desc = V.tile_desc[V.tile_base[g] + t];
-        uint32_t e = desc & 0xffff, skip = desc >> 16;
-        EncReader enc(V.enc + V.enc_off[g]);
-        const uint32_t el = V.enc_len[g];
-        bool raw = skip == 0xFFFF;
-        uint32_t cur = t * TILE - (raw ? 0u : skip);
-        bool jumped = false;
-        while (e < el) {
-            uint32_t b = enc.get(e);
-            if (b != 251 || raw) {
-                if (cur == o) return b;
-                cur++;
-                e++;
-                raw = false;
-                continue;
-            }
-            uint32_t nx = enc.get(e + 1);
-            if (nx == 0 || nx == 251 || nx == 2) {
-                if (cur == o) return 251;
-                if (cur + 1 == o) return nx;
-                cur += 2;
-                e += 2;
-                continue;
-            }
-            uint32_t idx = enc.get(e + 2) | (enc.get(e + 3) << 8), to = enc.get(e + 4) | (enc.get(e + 5) << 8), from, adv;
-            if (nx == 1) {
-                from = enc.get(e + 6) | (enc.get(e + 7) << 8);
-                adv = 8;
-            } else {
-                from = to - nx;
-                adv = 6;
-            }
-            uint32_t tl = to - from;
-            if (o < cur + tl) {
-                uint32_t k = o - cur, sg = V.first[g] + idx;
-                if (sg == g) {
-                    uint32_t period = cur - from;
-                    o = from + (k % period);
-                } else {
-                    o = from + k;
-                    g = sg;
-                }
-                jumped = true;
-                break;
-            }
-            cur += tl;
-            e += adv;
-        }
-        if (!jumped) return -1;
-    }
-    return -1;
-}
-
-// decoded[g0][0..qlen) == q ?   Ranges are followed through back references with a small stack;
-// overlapping self references and stack overflow fall back to resolve_byte.
-__device__ bool compare_prefix(const ChaseView &V, uint32_t g0, const uint8_t *q, uint32_t qlen) {
-    if (V.dec_len[g0] < qlen) return false;
-    struct Item {
-        uint32_t g;
-        uint16_t a, b, qo;
-    };
-    constexpr int STACK = 24;
-    Item stack[STACK];
-    int sp = 0;
-    stack[sp++] = Item{g0, 0, (uint16_t) qlen, 0};
-    while (sp > 0) {
-        Item it = stack[--sp];
-        uint32_t t = it.a / TILE;
-        uint32_t desc = V.tile_desc[V.tile_base[it.g] + t];
-        uint32_t e = desc & 0xffff, skip = desc >> 16;
-        EncReader enc(V.enc + V.enc_off[it.g]);
-        const uint32_t el = V.enc_len[it.g];
-        bool raw = skip == 0xFFFF;
-        uint32_t cur = t * TILE - (raw ? 0u : skip);
-        uint32_t pos = it.a;
-        while (pos < it.b) {
-            if (e >= el) return false;
-            uint32_t b = enc.get(e);
-            if (b != 251 || raw) {
-                if (cur == pos) {
-                    if (b != q[it.qo + (pos - it.a)]) return false;
-                    pos++;
-                }
-                cur++;
-                e++;
-                raw = false;
-                continue;
-            }
-            uint32_t nx = enc.get(e + 1);
-            if (nx == 0 || nx == 251 || nx == 2) {
-                if (cur == pos) {
-                    if (q[it.qo + (pos - it.a)] != 251) return false;
-                    pos++;
-                }
-                cur++;
-                if (pos < it.b && cur == pos) {
-                    if (q[it.qo + (pos - it.a)] != nx) return false;
-                    pos++;
-                }
-                cur++;
-                e += 2;
-                continue;
-            }
-            uint32_t idx = enc.get(e + 2) | (enc.get(e + 3) << 8), to = enc.get(e + 4) | (enc.get(e + 5) << 8), from, adv;
-            if (nx == 1) {
-                from = enc.get(e + 6) | (enc.get(e + 7) << 8);
-                adv = 8;
-            } else {
-                from = to - nx;
-                adv = 6;
-            }
-            uint32_t tl = to - from;
-            if (cur + tl > pos) {
-                uint32_t hi = min((uint32_t) it.b, cur + tl);
-                uint32_t k0 = pos - cur, cnt = hi - pos;
-                uint32_t sg = V.first[it.g] + idx;
-                bool overlap = sg == it.g && from + k0 + cnt > cur;
-                if (overlap || sp >= STACK) {
-                    uint32_t period = cur - from;
-                    for (uint32_t x = 0; x < cnt; x++) {
-                        uint32_t so = sg == it.g ? from + ((k0 + x) % period) : from + k0 + x;
-                        if (resolve_byte(V, sg, so) != (int) q[it.qo + (pos - it.a) + x]) return false;
-                    }
-                } else {
-                    stack[sp++] = Item{sg, (uint16_t) (from + k0), (uint16_t) (from + k0 + cnt),
-                                       (uint16_t) (it.qo + (pos - it.a))};
-                }
-                pos = hi;
-            }
-            cur += tl;
-            e += adv;
-        }
-    }
-    return true;
+    return DeviceView{d_child0.p, d_child1.p, d_diff.p, d_mask.p, d_leaf_rec.p, d_leaf_klen.p, d_leaf_koff.p, d_keys.p, root, has_root ? 1 : 0};
 }
 
 // ---------------------------------------------------------------------------------
@@ -388,10 +231,12 @@ k_query_write(uint32_t n, const uint8_t *__restrict__ keys, const int64_t *__res
     o[1] = 0;
 }
 
-// one query per thread: level-by-level walk over the SoA nodes, then verification
+// one query per thread: level-by-level walk over the SoA nodes (find_best_match, CritBitTree.cpp:253-269), then
+// verification of the candidate leaf against its escaped key in the index's key arena (key_eq, PiXiuStr.cpp:129-143:
+// the key is the decoded prefix "esc(k) 251 0" of the record the leaf points to)
 __global__ void __launch_bounds__(128)
-k_lookup(uint32_t n, HostIndex::DeviceView T, ChaseView V, const uint8_t *__restrict__ q,
-         const uint64_t *__restrict__ qoff, const uint32_t *__restrict__ qlen, uint32_t *__restrict__ rec_out) {
+k_lookup(uint32_t n, HostIndex::DeviceView T, const uint8_t *__restrict__ q, const uint64_t *__restrict__ qoff,
+         const uint32_t *__restrict__ qlen, uint32_t *__restrict__ rec_out) {
     uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
     uint32_t res = 0xFFFFFFFFu;
@@ -405,8 +250,19 @@ k_lookup(uint32_t n, HostIndex::DeviceView T, ChaseView V, const uint8_t *__rest
             uint32_t dir = (1u + (T.mask[p] | b)) >> 8;
             p = dir ? T.child1[p] : T.child0[p];
         }
-        uint32_t g = T.leaf_rec[~p];
-        if (compare_prefix(V, g, key, kl)) res = g;
+        const uint32_t s = (uint32_t) ~p;
+        if (T.leaf_klen[s] == kl) {
+            const uint8_t *lk = T.keys + T.leaf_koff[s];
+            uint32_t j = 0;
+            // 8 bytes per step once both sides are 8-byte aligned relative to each other; bytes otherwise
+            if ((((uintptr_t) lk ^ (uintptr_t) key) & 7) == 0) {
+                while (j < kl && (((uintptr_t) (key + j)) & 7) && lk[j] == key[j]) j++;
+                if (j == kl || (((uintptr_t) (key + j)) & 7) == 0)
+                    while (j + 8 <= kl && *reinterpret_cast<const uint64_t *>(lk + j) == *reinterpret_cast<const uint64_t *>(key + j)) j += 8;
+            }
+            while (j < kl && lk[j] == key[j]) j++;
+            if (j == kl) res = T.leaf_rec[s];
+        }
     }
     rec_out[i] = res;
 }
@@ -443,8 +299,7 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     S.in_vals.reserve_discard(qbytes + 16);
     k_query_write<<<div_up<uint32_t>(nn, 256), 256, 0, st>>>(nn, S.in_keys.p, S.in_koff.p, d_qoff, S.in_vals.p);
     S.doc_off.reserve_discard(nn + 1);
-    ChaseView V{S.d_enc.ptr(), S.d_enc_off.p, S.d_enc_len.p, S.d_dec_len.p, S.d_first.p, S.d_tile_base.p, S.d_tile_desc.p};
-    k_lookup<<<div_up<uint32_t>(nn, 128), 128, 0, st>>>(nn, T, V, S.in_vals.p, d_qoff, S.doc_len.p, S.doc_off.p);
+    k_lookup<<<div_up<uint32_t>(nn, 128), 128, 0, st>>>(nn, T, S.in_vals.p, d_qoff, S.doc_len.p, S.doc_off.p);
     PX_LAUNCH_CHECK();
     S.prof.end(st, 0.0, 4);
     S.launches += 4;

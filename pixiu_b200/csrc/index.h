@@ -4,10 +4,11 @@
 //   inner node i : child[0][i], child[1][i] (>= 0 inner node, < 0 leaf ~slot), diff_at[i], mask[i]
 //   leaf slot s  : leaf_rec[s] = global record id; its escaped key (with the 251,0 terminator)
 //                  sits in a host key arena so inserts need no decode of stored records.
-// Device side: the same arrays mirrored as SoA for the batched level-synchronous walk
-// (find_best_match, CritBitTree.cpp:253-269); candidates are verified against the
-// decoded prefix of the stored record (key_eq / contains, PiXiuStr.cpp:129-143,
-// CritBitTree.cpp:154-178) straight from the compressed store.
+// Device side: the same arrays (and the key arena) mirrored as SoA for the batched level-synchronous
+// walk (find_best_match, CritBitTree.cpp:253-269); a candidate leaf is verified against its escaped
+// key in the arena, which is byte for byte the decoded prefix "esc(k) 251 0" of the record the leaf
+// points to (key_eq / contains, PiXiuStr.cpp:129-143, CritBitTree.cpp:154-178) - the reference decodes
+// that prefix from the compressed record instead, which costs a token walk per back-reference hop.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -34,7 +35,9 @@ class HostIndex {
         const int32_t *child0, *child1;
         const uint16_t *diff_at;
         const uint8_t *mask;
-        const uint32_t *leaf_rec;
+        const uint32_t *leaf_rec, *leaf_klen;
+        const uint64_t *leaf_koff;
+        const uint8_t *keys;  // escaped keys of the leaves
         int32_t root;
         int32_t has_root;
     };
@@ -55,7 +58,10 @@ class HostIndex {
     DevBuf<int32_t> d_child0, d_child1;
     DevBuf<uint16_t> d_diff;
     DevBuf<uint8_t> d_mask;
-    DevBuf<uint32_t> d_leaf_rec;
+    DevBuf<uint32_t> d_leaf_rec, d_leaf_klen;
+    DevBuf<uint64_t> d_leaf_koff;
+    DevBuf<uint8_t> d_keys;
+    size_t keys_uploaded = 0;
 
     int32_t new_leaf(const uint8_t *q, uint32_t qlen, uint32_t rec);
     int32_t new_inner();
