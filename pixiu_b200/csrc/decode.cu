@@ -35,8 +35,9 @@ constexpr uint32_t BM_WORDS = 96;                 // bitmaps: three words per la
 // every reference segment but the first and the last of a tile puts >= 7 decoded bytes into the tile
 constexpr uint32_t SEG_MAX = TILE / 7 + 4;
 // copy pieces: every reference segment is cut into pieces of at most 32 bytes (a piece is ready when one 32-bit
-// window of the "final" bitmap is all ones); periodic segments with a period >= 32 are also cut where they wrap
-constexpr uint32_t PIECE_MAX = SEG_MAX + 1 + 4 * (TILE / 32);
+// window of the "final" bitmap is all ones); periodic segments with a period >= 32 are also cut where they wrap.
+// A tile keeps at most PIECE_MAX pieces (typical tiles have ~80); the segments beyond that go straight to k_resolve.
+constexpr uint32_t PIECE_MAX = 256;
 constexpr uint32_t PIECE_ROWS = (PIECE_MAX + 31) / 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 constexpr uint32_t GIVEUP_SPINS = 64;   // polls without any progress after which a tile hands its open pieces to k_resolve
@@ -54,16 +55,24 @@ struct DecodeView {
     uint32_t *ptr;              // per arena byte: source position, written only for handed-over bytes
 };
 
-struct ParseSmem {                  // parse scratch
+struct ParseBits {                  // dead once the heads are listed: shares its storage with the pieces
     uint32_t b251[BM_WORDS];        // bit p: staged byte p is a 251 that can start a token
     uint32_t cst[BM_WORDS];         // bit p: that 251 surely starts a token (no 251 among the 7 bytes before it)
     uint32_t headb[BM_WORDS];       // bit p: a reference token starts at p
-    uint16_t heads[SEG_MAX + 8];    // staged positions of the reference heads, ascending
+};
+struct Pieces {
+    // meta: u (12 bits) | (n - 1) << 12 (5 bits) | period << 17 (5 bits, 0 = plain copy) | phase << 22
+    uint32_t src[PIECE_MAX];        // arena position of the first source byte (periodic: of the period's byte 0)
+    uint32_t meta[PIECE_MAX];
 };
 
 struct alignas(16) WarpSmem {
     uint32_t stg[STG_WORDS];        // staged encoded bytes: byte e0 + k of the record sits at staged position soff + k
-    ParseSmem ps;
+    union {
+        ParseBits ps;
+        Pieces pc;
+    };
+    uint16_t heads[SEG_MAX + 8];    // staged positions of the reference heads, ascending
     uint32_t startb[BM_WORDS];      // bit u: a segment starts at output byte u - mis (word-aligned "u" coordinates)
     uint32_t finw[BM_WORDS];        // bit u: output byte u - mis is a literal (final once phase 4 has stored it)
     uint16_t wprefix[BM_WORDS];     // segment starts before word w of startb
@@ -71,9 +80,6 @@ struct alignas(16) WarpSmem {
     // previous tile, or empty), entries 1.. follow the start bits.  lo16: end of the segment (u); hi16: literals
     // after it sit at staged position (u - mis) + this
     uint32_t seg_ed[SEG_MAX + 1];
-    // copy pieces.  meta: u (12 bits) | (n - 1) << 12 (5 bits) | period << 17 (5 bits, 0 = plain copy) | phase << 22
-    uint32_t p_src[PIECE_MAX];      // arena position of the first source byte (periodic: of the period's byte 0)
-    uint32_t p_meta[PIECE_MAX];
     uint32_t pend[PIECE_ROWS];      // per row of 32 pieces: lanes whose piece is not copied yet
 };
 
@@ -114,7 +120,7 @@ __device__ __forceinline__ void flush_final(const uint32_t *finw, uint32_t *lm, 
 //      is finished or held by a resident warp: waiting cannot deadlock); copied ranges are published the same way
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
-               uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t giveup_spins) {
+               uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t giveup_spins, uint32_t piece_cap) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -263,7 +269,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
         for (int k = 0; k < 3; k++) {
             uint32_t hv = h[k];
             while (hv) {
-                S.ps.heads[slot++] = (uint16_t) ((3 * lane + k) * 32 + __ffs(hv) - 1);
+                S.heads[slot++] = (uint16_t) ((3 * lane + k) * 32 + __ffs(hv) - 1);
                 hv &= hv - 1;
             }
         }
@@ -274,6 +280,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
     //         at staged position p starts at output byte (p - soff) + D - skip ----
     uint32_t nseg = 0;  // governor entries 1..nseg
     uint32_t npiece = 0;
+    bool full = false;  // the piece table is full: later segments are handed over
     int D = 0;
     for (uint32_t c0 = 0; c0 < nheads; c0 += 32) {
         const uint32_t c = c0 + lane;
@@ -281,7 +288,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
         uint32_t p = 0, idx = 0, from = 0, tl = 0;
         int d = 0;
         if (head) {
-            p = S.ps.heads[c];
+            p = S.heads[c];
             const uint32_t b1 = SB[p + 1];
             const bool big = b1 == 1;
             idx = SB[p + 2] | (SB[p + 3] << 8);
@@ -351,31 +358,46 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
             if ((int) lane >= dd) pinc += o;
         }
         uint32_t slot = npiece + pinc - np;
-        if (np && slot + np <= PIECE_MAX) {
+        const bool spill = np && (full || slot + np > piece_cap);  // (from the first spilling lane on, every later segment spills)
+        const uint32_t sb = __ballot_sync(FULL, spill);
+        if (spill) {
+            // no room: the whole segment goes to k_resolve (source pointers + hand-over bits)
+            const uint32_t B = B0 + us;
+            for (uint32_t j = 0; j < len; j++) V.ptr[B + j] = sbase + (per ? (ks + j) % per : ks + j);
+            for (uint32_t wj = B >> 5; wj <= (B + len - 1) >> 5; wj++) {
+                uint32_t bits = 0xFFFFFFFFu;
+                if (wj == B >> 5) bits <<= (B & 31);
+                if (wj == (B + len - 1) >> 5) bits &= 0xFFFFFFFFu >> (31 - ((B + len - 1) & 31));
+                atomicOr(V.gup + wj, bits);
+            }
+            atomicAdd(ctr + 2, 1u);
+        }
+        if (np && !spill) {
             if (per != 0 && per < 32) {
                 for (uint32_t o = 0; o < len; o += 32, slot++) {
-                    S.p_src[slot] = sbase;
-                    S.p_meta[slot] = (us + o) | ((min(32u, len - o) - 1) << 12) | (per << 17) | (((ks + o) % per) << 22);
+                    S.pc.src[slot] = sbase;
+                    S.pc.meta[slot] = (us + o) | ((min(32u, len - o) - 1) << 12) | (per << 17) | (((ks + o) % per) << 22);
                 }
             } else if (per == 0 && len <= 32) {
-                S.p_src[slot] = sbase + ks;
-                S.p_meta[slot] = us | ((len - 1) << 12);
+                S.pc.src[slot] = sbase + ks;
+                S.pc.meta[slot] = us | ((len - 1) << 12);
             } else {
                 const uint32_t wrap = per ? per : 0xFFFFFFFFu;
                 for (uint32_t pos = ks, o = 0; o < len; slot++) {
                     const uint32_t n = min(min(32u - ((sbase + pos) & 31u), wrap - pos), len - o);
-                    S.p_src[slot] = sbase + pos;
-                    S.p_meta[slot] = (us + o) | ((n - 1) << 12);
+                    S.pc.src[slot] = sbase + pos;
+                    S.pc.meta[slot] = (us + o) | ((n - 1) << 12);
                     pos = pos + n == wrap ? 0u : pos + n;
                     o += n;
                 }
             }
         }
         nseg += __popc(em);
-        npiece += __shfl_sync(FULL, pinc, 31);
+        npiece = sb ? __shfl_sync(FULL, slot, __ffs(sb) - 1) : npiece + __shfl_sync(FULL, pinc, 31);
+        if (sb) full = true;
         D += __shfl_sync(FULL, inc, 31);
     }
-    if ((int) ne + D < (int) (skip + nbytes) || nseg > SEG_MAX || npiece > PIECE_MAX) {
+    if ((int) ne + D < (int) (skip + nbytes) || nseg > SEG_MAX) {
         if (lane == 0) atomicExch(err, 6u);
         return;
     }
@@ -443,8 +465,8 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
             bool ready = false, giveup = false;
             uint32_t meta = 0, a = 0;
             if ((pm >> lane) & 1u) {
-                meta = S.p_meta[row * 32 + lane];
-                a = S.p_src[row * 32 + lane];
+                meta = S.pc.meta[row * 32 + lane];
+                a = S.pc.src[row * 32 + lane];
                 const uint32_t per = (meta >> 17) & 31u;
                 const uint32_t n = per ? per : ((meta >> 12) & 31u) + 1;
                 const uint32_t wi = a >> 5, bs = a & 31, need = 0xFFFFFFFFu >> (32 - n);
@@ -704,10 +726,12 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     PX_CUDA(cudaFuncSetAttribute(k_decode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     const char *gs = getenv("PIXIU_GIVEUP_SPINS");  // tuning knob
     const uint32_t giveup_spins = gs ? (uint32_t) atoi(gs) : GIVEUP_SPINS;
+    const char *pcs = getenv("PIXIU_PIECE_CAP");    // test knob: forces the spill path of the piece table
+    const uint32_t piece_cap = pcs ? std::min<uint32_t>((uint32_t) atoi(pcs), PIECE_MAX) : PIECE_MAX;
     PX_CUDA(cudaEventRecord(ev0, st));
     prof.begin(PC_DECODE, st);
     k_decode_tiles<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(
-        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins);
+        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins, piece_cap);
     int nl = 1;
     uint32_t h_ctr[4] = {0, 0, 0, 0};
     PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

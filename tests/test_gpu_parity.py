@@ -127,6 +127,38 @@ def test_setitem_nested_and_periodic_vs_oracle(ctrl_mod):
     c.free_prop()
 
 
+@pytest.mark.parametrize("knobs", [{"PIXIU_PIECE_CAP": "6"}, {"PIXIU_GIVEUP_SPINS": "0"},
+                                   {"PIXIU_PIECE_CAP": "40", "PIXIU_GIVEUP_SPINS": "2"}])
+def test_decode_handover_paths(ctrl_mod, knobs, monkeypatch):
+    """the decoder's data-flow pass hands pieces to the pointer-chasing pass when its piece table is full or when
+    sources stay unresolved (deep chains); both knobs force that on ordinary data: same bytes either way"""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    # HTML-like pages (many short references), nested records (long references, self-periodic runs), escapes
+    for gen in ("html", "nested", "esc"):
+        if gen == "html":
+            kd, ko, vd, vo = synth.gen_html_pages(24, seed=11, max_len=30000, mean_len=16000)
+        elif gen == "nested":
+            kd, ko, vd, vo = synth.gen_nested(1200, seed=5)
+        else:
+            rng = np.random.default_rng(9)
+            vals = []
+            for i in range(60):
+                base = rng.choice(np.array([250, 251, 252, 0, 1, 2, 65, 66], dtype=np.uint8), size=3000).tobytes()
+                vals.append(base if i % 3 else vals[-1][:1500] + base[:1500] if vals else base)
+            keys = [b"esc%04d" % i for i in range(len(vals))]
+            kd, ko = synth.pack(keys)
+            vd, vo = synth.pack(vals)
+        keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+        c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
+        c.setitem_batch((kd, ko), (vd, vo))
+        buf, off, found = c.getitem_batch((kd, ko))
+        assert found.all()
+        for i, (k, v) in enumerate(zip(keys, vals)):
+            assert buf[off[i]:off[i + 1]].tobytes() == po.make_doc(k, v), f"{gen} record {i}"
+        c.free_prop()
+
+
 def test_edge_records(ctrl_mod):
     """maximum lengths (PiXiuCtrl.cpp:121-174), key-only docs, long runs of 251, long periodic values"""
     recs = [
