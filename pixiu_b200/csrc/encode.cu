@@ -1278,23 +1278,20 @@ uint32_t Store::encode_window_records(uint32_t first_new) {
 }
 
 // index maintenance (host CritBit; in-order semantics of n sequential setitem calls) + rc / saved outputs
-void Store::finish_index(uint32_t nn, size_t g_batch_first, const uint8_t *h_keys, const int64_t *h_koff,
-                         const int64_t *h_voff, const uint32_t *h_doc_len, int32_t *rc, int32_t *saved) {
-    std::vector<uint8_t> q;
+void Store::finish_index(uint32_t nn, size_t g_batch_first, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *h_keys,
+                         const int64_t *h_koff, const int64_t *h_voff, const uint32_t *h_doc_len, int32_t *rc, int32_t *saved) {
+    std::vector<int64_t> old(nn);
+    index->insert_batch(*this, nn, d_keys, d_koff, h_keys, h_koff, (uint32_t) g_batch_first, old.data());
     for (uint32_t i = 0; i < nn; i++) {
-        const uint8_t *k = h_keys + h_koff[i];
-        size_t kl = (size_t) (h_koff[i + 1] - h_koff[i]);
-        escape_key(k, kl, q);
-        uint32_t g = (uint32_t) (g_batch_first + i);
-        int64_t old = index->set(q.data(), (uint32_t) q.size(), g);
-        if (old >= 0) {
-            h_live[old] = 0;
+        const uint32_t g = (uint32_t) (g_batch_first + i);
+        if (old[i] >= 0) {
+            h_live[old[i]] = 0;
             live_records--;
         }
         live_records++;
-        if (rc) rc[i] = old >= 0 ? PIXIU_CBT_SET_REPLACE : 0;
+        if (rc) rc[i] = old[i] >= 0 ? PIXIU_CBT_SET_REPLACE : 0;
         if (saved) saved[i] = (int32_t) h_doc_len[i] - (int32_t) h_enc_len[g];
-        raw_bytes += (int64_t) kl + (h_voff[i + 1] - h_voff[i]);
+        raw_bytes += (h_koff[i + 1] - h_koff[i]) + (h_voff[i + 1] - h_voff[i]);
         doc_bytes += h_doc_len[i];
     }
 }
@@ -1386,7 +1383,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     flush_mirrors();
     const auto t_gpu_done = std::chrono::steady_clock::now();
     PX_CUDA(cudaEventRecord(ev1, st));
-    finish_index(nn, g_batch_first, h_keys, h_koff, h_voff, h_doc_len.data(), rc, saved);
+    finish_index(nn, g_batch_first, d_keys, d_koff, h_keys, h_koff, h_voff, h_doc_len.data(), rc, saved);
     PX_CUDA(cudaEventSynchronize(ev1));
     float ms = 0;
     PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1580,7 +1577,7 @@ int Store::mg_end(int32_t *rc, int32_t *saved) {
     PX_CUDA(cudaEventRecord(ev1, st));
     mg_gR += nn;
     mg_gbytes += mg_batch_bytes;
-    finish_index(nn, g_batch_first, mg_h_keys.data(), mg_h_koff.data(), mg_h_voff.data(), mg_doc_len.data(), rc, saved);
+    finish_index(nn, g_batch_first, mg_d_keys, mg_d_koff, mg_h_keys.data(), mg_h_koff.data(), mg_h_voff.data(), mg_doc_len.data(), rc, saved);
     PX_CUDA(cudaEventSynchronize(ev1));
     float ms = 0;
     PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));

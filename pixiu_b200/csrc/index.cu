@@ -2,6 +2,7 @@
 #include "index.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "scan.cuh"
@@ -10,15 +11,21 @@
 namespace pixiu {
 
 void escape_key(const uint8_t *k, size_t n, std::vector<uint8_t> &out, bool terminator) {
-    out.clear();
-    out.reserve(n + 8);
-    for (size_t i = 0; i < n; i++) {
-        out.push_back(k[i]);
-        if (k[i] == 251) out.push_back(251);
+    if (!memchr(k, 251, n)) {  // nothing to double (every ASCII key)
+        out.resize(n + (terminator ? 2 : 0));
+        memcpy(out.data(), k, n);
+    } else {
+        out.clear();
+        out.reserve(2 * n + 2);
+        for (size_t i = 0; i < n; i++) {
+            out.push_back(k[i]);
+            if (k[i] == 251) out.push_back(251);
+        }
+        if (terminator) out.resize(out.size() + 2);
     }
     if (terminator) {
-        out.push_back(251);
-        out.push_back(0);
+        out[out.size() - 2] = 251;
+        out[out.size() - 1] = 0;
     }
 }
 
@@ -30,6 +37,7 @@ int32_t HostIndex::new_leaf(const uint8_t *q, uint32_t qlen, uint32_t rec) {
     if (!free_leaf.empty()) {
         s = free_leaf.back();
         free_leaf.pop_back();
+        dirty = true;  // a mirrored slot changes wholesale
     } else {
         s = (int32_t) leaf_rec.size();
         leaf_rec.push_back(0);
@@ -47,6 +55,7 @@ int32_t HostIndex::new_inner() {
     if (!free_inner.empty()) {
         int32_t s = free_inner.back();
         free_inner.pop_back();
+        dirty = true;  // a mirrored slot changes wholesale
         return s;
     }
     child[0].push_back(0);
@@ -65,15 +74,20 @@ int64_t HostIndex::get(const uint8_t *q, uint32_t qlen) const {
     return -1;
 }
 
-int64_t HostIndex::set(const uint8_t *q, uint32_t qlen, uint32_t rec) {
-    dirty = true;
+int64_t HostIndex::set(const uint8_t *q, uint32_t qlen, uint32_t rec) { return set_below(-1, 0, q, qlen, rec); }
+
+// CritBitTree::setitem restricted to the subtree hanging on the edge (top, tdir) (top < 0: the whole tree).  The
+// caller guarantees that the key's path from the root passes through that edge and that the new node belongs on
+// it or below it.
+int64_t HostIndex::set_below(int32_t top, int tdir, const uint8_t *q, uint32_t qlen, uint32_t rec) {
     if (!has_root) {
         root = ~new_leaf(q, qlen, rec);
         has_root = true;
         n_live = 1;
         return -1;
     }
-    int32_t p = root;
+    const int32_t start = top < 0 ? root : child[tdir][top];
+    int32_t p = start;
     while (p >= 0) p = child[dir_of(p, q, qlen)][p];
     int32_t s = ~p;
     const uint8_t *lk = arena.data() + leaf_koff[s];
@@ -82,6 +96,7 @@ int64_t HostIndex::set(const uint8_t *q, uint32_t qlen, uint32_t rec) {
     if (diff == qlen && diff == ll) {  // same key: repoint the leaf (replace(), CritBitTree.cpp:32-43)
         int64_t old = leaf_rec[s];
         leaf_rec[s] = rec;
+        note_leaf(s);
         return old;
     }
     // insert() (CritBitTree.cpp:45-92); reference bug B5 (record lost when the first difference
@@ -93,21 +108,32 @@ int64_t HostIndex::set(const uint8_t *q, uint32_t qlen, uint32_t rec) {
     mk |= mk >> 4;
     mk = (uint8_t) ((mk & ~(mk >> 1)) ^ 0xFF);
     int dir = (1 + (mk | b)) >> 8;
-    int32_t nl = new_leaf(q, qlen, rec);
-    int32_t ni = new_inner();
-    diff_at[ni] = (uint16_t) diff;
-    mask[ni] = mk;
-    child[dir][ni] = ~nl;
-    int32_t parent = -1, pdir = 0, cur = root;
+    int32_t parent = top, pdir = tdir, cur = start;
     while (cur >= 0) {
         if (diff_at[cur] > diff || (diff_at[cur] == diff && mask[cur] > mk)) break;
         pdir = dir_of(cur, q, qlen);
         parent = cur;
         cur = child[pdir][cur];
     }
-    child[1 - dir][ni] = cur;
-    if (parent < 0) root = ni;
-    else child[pdir][parent] = ni;
+    Probe pr{s, parent, cur, diff | ((uint32_t) mk << 16) | ((uint32_t) dir << 24) | ((uint32_t) pdir << 25)};
+    return splice(pr, q, qlen, rec);
+}
+
+// put the new leaf and its inner node on the edge (pr.parent, pdir) that currently holds pr.cur
+int64_t HostIndex::splice(const Probe &pr, const uint8_t *q, uint32_t qlen, uint32_t rec) {
+    const int dir = (pr.info >> 24) & 1, pdir = (pr.info >> 25) & 1;
+    int32_t nl = new_leaf(q, qlen, rec);
+    int32_t ni = new_inner();
+    diff_at[ni] = (uint16_t) (pr.info & 0xFFFF);
+    mask[ni] = (uint8_t) (pr.info >> 16);
+    child[dir][ni] = ~nl;
+    child[1 - dir][ni] = pr.cur;
+    if (pr.parent < 0) {
+        root = ni;
+    } else {
+        child[pdir][pr.parent] = ni;
+        note_child(pr.parent, pdir);
+    }
     n_live++;
     return -1;
 }
@@ -170,37 +196,77 @@ void HostIndex::iter(const uint8_t *prefix, uint32_t plen, std::vector<uint32_t>
     iter_rec(root, prefix, plen, false, harvest, stop, out);
 }
 
-HostIndex::DeviceView HostIndex::device_view(cudaStream_t st) {
-    if (dirty) {
-        size_t ni = diff_at.size(), nl = leaf_rec.size();
-        d_child0.reserve_discard(ni + 1);
-        d_child1.reserve_discard(ni + 1);
-        d_diff.reserve_discard(ni + 1);
-        d_mask.reserve_discard(ni + 1);
-        d_leaf_rec.reserve_discard(nl + 1);
-        if (ni) {
-            PX_CUDA(cudaMemcpyAsync(d_child0.p, child[0].data(), ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            PX_CUDA(cudaMemcpyAsync(d_child1.p, child[1].data(), ni * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            PX_CUDA(cudaMemcpyAsync(d_diff.p, diff_at.data(), ni * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-            PX_CUDA(cudaMemcpyAsync(d_mask.p, mask.data(), ni * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
-        }
-        if (nl) {
-            d_leaf_klen.reserve_discard(nl + 1);
-            d_leaf_koff.reserve_discard(nl + 1);
-            PX_CUDA(cudaMemcpyAsync(d_leaf_rec.p, leaf_rec.data(), nl * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-            PX_CUDA(cudaMemcpyAsync(d_leaf_klen.p, leaf_klen.data(), nl * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-            PX_CUDA(cudaMemcpyAsync(d_leaf_koff.p, leaf_koff.data(), nl * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        }
-        // the key arena only ever grows: upload what is new
-        if (arena.size() > keys_uploaded) {
-            d_keys.reserve_keep(arena.size() + 16, keys_uploaded, st);
-            PX_CUDA(cudaMemcpyAsync(d_keys.p + keys_uploaded, arena.data() + keys_uploaded, arena.size() - keys_uploaded,
-                                    cudaMemcpyHostToDevice, st));
-            keys_uploaded = arena.size();
-        }
-        PX_CUDA(cudaStreamSynchronize(st));
-        dirty = false;
+__global__ void __launch_bounds__(256)
+k_apply_index_mods(uint32_t n_child, uint32_t n_leaf, const int32_t *__restrict__ mods, int32_t *__restrict__ child0,
+                   int32_t *__restrict__ child1, uint32_t *__restrict__ leaf_rec) {
+    // mods: n_child pairs (node * 2 + dir, value), then n_leaf pairs (slot, record id)
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n_child) {
+        int32_t k = mods[2 * i], v = mods[2 * i + 1];
+        ((k & 1) ? child1 : child0)[k >> 1] = v;
+    } else if (i < n_child + n_leaf) {
+        leaf_rec[mods[2 * i]] = (uint32_t) mods[2 * i + 1];
     }
+}
+
+HostIndex::DeviceView HostIndex::device_view(cudaStream_t st) {
+    const size_t ni = diff_at.size(), nl = leaf_rec.size();
+    if (dirty) {
+        synced_inner = synced_leaf = 0;
+        mod_child.clear();
+        mod_leaf.clear();
+    }
+    if (ni > synced_inner) {  // appended inner nodes
+        const size_t a = synced_inner, c = ni - a;
+        d_child0.reserve_keep(ni + 1, a, st);
+        d_child1.reserve_keep(ni + 1, a, st);
+        d_diff.reserve_keep(ni + 1, a, st);
+        d_mask.reserve_keep(ni + 1, a, st);
+        PX_CUDA(cudaMemcpyAsync(d_child0.p + a, child[0].data() + a, c * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        PX_CUDA(cudaMemcpyAsync(d_child1.p + a, child[1].data() + a, c * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        PX_CUDA(cudaMemcpyAsync(d_diff.p + a, diff_at.data() + a, c * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        PX_CUDA(cudaMemcpyAsync(d_mask.p + a, mask.data() + a, c * sizeof(uint8_t), cudaMemcpyHostToDevice, st));
+    }
+    if (nl > synced_leaf) {  // appended leaves
+        const size_t a = synced_leaf, c = nl - a;
+        d_leaf_rec.reserve_keep(nl + 1, a, st);
+        d_leaf_klen.reserve_keep(nl + 1, a, st);
+        d_leaf_koff.reserve_keep(nl + 1, a, st);
+        PX_CUDA(cudaMemcpyAsync(d_leaf_rec.p + a, leaf_rec.data() + a, c * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        PX_CUDA(cudaMemcpyAsync(d_leaf_klen.p + a, leaf_klen.data() + a, c * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        PX_CUDA(cudaMemcpyAsync(d_leaf_koff.p + a, leaf_koff.data() + a, c * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    }
+    // the key arena only ever grows: upload what is new
+    if (arena.size() > keys_uploaded) {
+        d_keys.reserve_keep(arena.size() + 16, keys_uploaded, st);
+        PX_CUDA(cudaMemcpyAsync(d_keys.p + keys_uploaded, arena.data() + keys_uploaded, arena.size() - keys_uploaded,
+                                cudaMemcpyHostToDevice, st));
+        keys_uploaded = arena.size();
+    }
+    // scattered changes of entries that were already mirrored
+    const size_t nc = mod_child.size(), nm = mod_leaf.size();
+    if (nc + nm) {
+        std::vector<int32_t> pairs(2 * (nc + nm));
+        for (size_t i = 0; i < nc; i++) {
+            pairs[2 * i] = mod_child[i];
+            pairs[2 * i + 1] = child[mod_child[i] & 1][mod_child[i] >> 1];
+        }
+        for (size_t i = 0; i < nm; i++) {
+            pairs[2 * (nc + i)] = mod_leaf[i];
+            pairs[2 * (nc + i) + 1] = (int32_t) leaf_rec[mod_leaf[i]];
+        }
+        d_mod.reserve_discard(pairs.size());
+        PX_CUDA(cudaMemcpyAsync(d_mod.p, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        k_apply_index_mods<<<(unsigned) div_up<size_t>(nc + nm, 256), 256, 0, st>>>((uint32_t) nc, (uint32_t) nm, d_mod.p, d_child0.p,
+                                                                                   d_child1.p, d_leaf_rec.p);
+        PX_CUDA(cudaStreamSynchronize(st));  // pairs is a local
+        mod_child.clear();
+        mod_leaf.clear();
+    }
+    PX_CUDA(cudaStreamSynchronize(st));
+    synced_inner = ni;
+    synced_leaf = nl;
+    dirty = false;
     return DeviceView{d_child0.p, d_child1.p, d_diff.p, d_mask.p, d_leaf_rec.p, d_leaf_klen.p, d_leaf_koff.p, d_keys.p, root, has_root ? 1 : 0};
 }
 
@@ -265,6 +331,156 @@ k_lookup(uint32_t n, HostIndex::DeviceView T, const uint8_t *__restrict__ q, con
         }
     }
     rec_out[i] = res;
+}
+
+// one key per thread: the two read-only walks of CritBitTree::setitem (best-match leaf and critical position,
+// CritBitTree.cpp:13-30,:45-66; then the edge where the new node belongs, :67-81)
+__global__ void __launch_bounds__(128)
+k_insert_probe(uint32_t n, HostIndex::DeviceView T, const uint8_t *__restrict__ q, const uint64_t *__restrict__ qoff,
+               const uint32_t *__restrict__ qlen, HostIndex::Probe *__restrict__ out) {
+    uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *key = q + qoff[i];
+    const uint32_t kl = qlen[i];
+    int32_t p = T.root;
+    while (p >= 0) {
+        uint32_t da = T.diff_at[p];
+        uint32_t b = da < kl ? key[da] : 0u;
+        p = ((1u + (T.mask[p] | b)) >> 8) ? T.child1[p] : T.child0[p];
+    }
+    const uint32_t s = (uint32_t) ~p;
+    const uint8_t *lk = T.keys + T.leaf_koff[s];
+    const uint32_t ll = T.leaf_klen[s], m = min(ll, kl);
+    uint32_t diff = 0;
+    while (diff < m && lk[diff] == key[diff]) diff++;
+    HostIndex::Probe r;
+    r.leaf = (int32_t) s;
+    if (diff == kl && diff == ll) {
+        r.parent = -1;
+        r.cur = 0;
+        r.info = 1u << 26;
+        out[i] = r;
+        return;
+    }
+    const uint32_t a = diff < ll ? lk[diff] : 0u, b = diff < kl ? key[diff] : 0u;
+    uint32_t mk = a ^ b;
+    mk |= mk >> 1;
+    mk |= mk >> 2;
+    mk |= mk >> 4;
+    mk = ((mk & ~(mk >> 1)) ^ 0xFFu) & 0xFFu;
+    const uint32_t dir = (1u + (mk | b)) >> 8;
+    int32_t parent = -1, cur = T.root;
+    uint32_t pdir = 0;
+    while (cur >= 0) {
+        const uint32_t da = T.diff_at[cur], cm = T.mask[cur];
+        if (da > diff || (da == diff && cm > mk)) break;
+        const uint32_t kb = da < kl ? key[da] : 0u;
+        pdir = (1u + (cm | kb)) >> 8;
+        parent = cur;
+        cur = pdir ? T.child1[cur] : T.child0[cur];
+    }
+    r.parent = parent;
+    r.cur = cur;
+    r.info = diff | (mk << 16) | (dir << 24) | (pdir << 25);
+    out[i] = r;
+}
+
+void HostIndex::insert_batch(Store &S, uint32_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *h_keys,
+                             const int64_t *h_koff, uint32_t first_rec, int64_t *old_out) {
+    cudaStream_t st = S.st;
+    std::vector<uint8_t> q;
+    uint32_t a = 0;
+    const bool trace = getenv("PIXIU_TRACE") != nullptr;
+    double t_probe = 0, t_apply = 0, t_sync = 0;
+    bool reserved = false;
+    uint64_t n_fallback = 0, n_rounds = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    while (a < n) {
+        // while the tree is small (or the rest of the batch is), plain host inserts; afterwards sub-batches of
+        // at most a quarter of the tree, so that few keys of a sub-batch meet on the same edge
+        const size_t live = n_live;
+        uint32_t b;
+        bool probe = live >= 4096 && n - a >= 1024;
+        if (!probe) {
+            b = (uint32_t) std::min<uint64_t>(n, (uint64_t) a + (live < 4096 ? 4096 : n - a));
+            for (uint32_t i = a; i < b; i++) {
+                escape_key(h_keys + h_koff[i], (size_t) (h_koff[i + 1] - h_koff[i]), q);
+                old_out[i] = set(q.data(), (uint32_t) q.size(), first_rec + i);
+            }
+            a = b;
+            continue;
+        }
+        b = (uint32_t) std::min<uint64_t>(n, (uint64_t) a + live / 4);
+        const uint32_t m = b - a;
+        const auto t0 = now();
+        if (!reserved) {
+            // one growth step for the whole batch instead of one per sub-batch (cudaMalloc/cudaFree synchronise)
+            const size_t rest = n - a, ni = diff_at.size() + rest + 1, nl = leaf_rec.size() + rest + 1;
+            const size_t kb = arena.size() + (size_t) (h_koff[n] - h_koff[a]) + 4 * rest + 64;  // room for doubled 251s is taken on demand
+            if (dirty) device_view(st);
+            d_child0.reserve_keep(ni, synced_inner, st);
+            d_child1.reserve_keep(ni, synced_inner, st);
+            d_diff.reserve_keep(ni, synced_inner, st);
+            d_mask.reserve_keep(ni, synced_inner, st);
+            d_leaf_rec.reserve_keep(nl, synced_leaf, st);
+            d_leaf_klen.reserve_keep(nl, synced_leaf, st);
+            d_leaf_koff.reserve_keep(nl, synced_leaf, st);
+            d_keys.reserve_keep(kb, keys_uploaded, st);
+            reserved = true;
+        }
+        DeviceView T = device_view(st);
+        t_sync += std::chrono::duration<double, std::milli>(now() - t0).count();
+        S.prof.begin(PC_LOOKUP, st);
+        d_qlen.reserve_discard(m + 1);
+        d_qoff.reserve_discard((size_t) m + 2);
+        uint32_t *ql = d_qlen.p;
+        uint64_t *qo = d_qoff.p;
+        k_query_len<<<div_up<uint32_t>(m, 256), 256, 0, st>>>(m, d_keys, d_koff + a, ql);
+        device_scan<uint64_t>(
+            (size_t) m + 1, [=] __device__(size_t i) -> uint64_t { return i < m ? (uint64_t) ql[i] : 0ull; },
+            [=] __device__(size_t i, uint64_t v) { qo[i] = v; }, OpSum(), 0ull, true, S.es.scanws, st);
+        uint64_t qbytes = 0;
+        PX_CUDA(cudaMemcpyAsync(&qbytes, qo + m, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaStreamSynchronize(st));
+        d_q.reserve_discard(qbytes + 16);
+        k_query_write<<<div_up<uint32_t>(m, 256), 256, 0, st>>>(m, d_keys, d_koff + a, qo, d_q.p);
+        d_probe.reserve_discard(m);
+        k_insert_probe<<<div_up<uint32_t>(m, 128), 128, 0, st>>>(m, T, d_q.p, qo, ql, d_probe.p);
+        PX_LAUNCH_CHECK();
+        S.prof.end(st, 0.0, 4);
+        S.launches += 4;
+        h_probe.resize(m);
+        PX_CUDA(cudaMemcpyAsync(h_probe.data(), d_probe.p, (size_t) m * sizeof(Probe), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaStreamSynchronize(st));
+        const auto t1 = now();
+        for (uint32_t i = 0; i < m; i++) {
+            const Probe &pr = h_probe[i];
+            escape_key(h_keys + h_koff[a + i], (size_t) (h_koff[a + i + 1] - h_koff[a + i]), q);
+            const uint32_t rec = first_rec + a + i;
+            if (pr.info & (1u << 26)) {  // the key exists: repoint its leaf (replace(), CritBitTree.cpp:32-43)
+                old_out[a + i] = leaf_rec[pr.leaf];
+                leaf_rec[pr.leaf] = rec;
+                note_leaf(pr.leaf);
+                continue;
+            }
+            const int pdir = (pr.info >> 25) & 1;
+            const int32_t now = pr.parent < 0 ? root : child[pdir][pr.parent];
+            if (now == pr.cur) old_out[a + i] = splice(pr, q.data(), (uint32_t) q.size(), rec);
+            else {
+                // the edge changed within this sub-batch (earlier keys were spliced onto it): the key still reaches
+                // this edge, so only the few new nodes below it are walked again
+                old_out[a + i] = set_below(pr.parent, pdir, q.data(), (uint32_t) q.size(), rec);
+                n_fallback++;
+            }
+        }
+        t_probe += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t_apply += std::chrono::duration<double, std::milli>(now() - t1).count();
+        n_rounds++;
+        a = b;
+    }
+    if (trace)
+        fprintf(stderr, "[index] %u keys: %llu probe rounds %.1f ms (mirror sync %.1f ms), host splices %.1f ms, %llu keys re-walked below their edge\n", n,
+                (unsigned long long) n_rounds, t_probe, t_sync, t_apply, (unsigned long long) n_fallback);
 }
 
 void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, std::vector<uint32_t> &rec_out) {

@@ -20,6 +20,8 @@ namespace pixiu {
 // esc(k) 251 0   (PiXiuStr_init_key, proj/PiXiuStr.cpp:12-14)
 void escape_key(const uint8_t *k, size_t n, std::vector<uint8_t> &out, bool terminator = true);
 
+struct Store;
+
 class HostIndex {
    public:
     // returns the record id that was replaced, or -1 when the key is new (CritBitTree.cpp:13-105)
@@ -41,7 +43,22 @@ class HostIndex {
         int32_t root;
         int32_t has_root;
     };
-    DeviceView device_view(cudaStream_t st);  // uploads when dirty
+    DeviceView device_view(cudaStream_t st);  // brings the mirror up to date (appended ranges + scattered changes)
+
+    // Batched insert (the batch form of CritBitTree::setitem, CritBitTree.cpp:13-105): the GPU finds, for every
+    // key, its best-match leaf, the critical position against that leaf and the edge the new node goes on (two
+    // read-only walks per key); the host then splices in batch order, O(1) per key.  Splices on distinct edges
+    // commute; a key whose edge was already changed in this batch takes the ordinary set().  d_keys/d_koff: the
+    // raw keys on the device (koff indexed [0, n]); h_keys/h_koff the same on the host.  old_out[i] = record id
+    // that key i replaced, or -1.
+    void insert_batch(Store &S, uint32_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *h_keys,
+                      const int64_t *h_koff, uint32_t first_rec, int64_t *old_out);
+    struct Probe {
+        int32_t leaf;     // best-match leaf slot
+        int32_t parent;   // node above the new inner node (-1: the root edge)
+        int32_t cur;      // what hangs on that edge now (>= 0 inner node, < 0 leaf ~slot)
+        uint32_t info;    // diff_at (16) | mask << 16 (8) | dir << 24 | pdir << 25 | exists << 26
+    };
 
    private:
     std::vector<int32_t> child[2];
@@ -54,7 +71,24 @@ class HostIndex {
     int32_t root = 0;
     bool has_root = false;
     size_t n_live = 0;
-    bool dirty = true;
+    bool dirty = true;            // the device mirror needs a full upload
+    size_t synced_inner = 0, synced_leaf = 0;   // entries of the mirror that are current (up to scattered changes)
+    std::vector<int32_t> mod_child;             // changed child pointers of mirrored nodes: node * 2 + dir
+    std::vector<int32_t> mod_leaf;              // mirrored leaves whose record id changed
+    DevBuf<int32_t> d_mod;
+    DevBuf<Probe> d_probe;
+    DevBuf<uint8_t> d_q;          // escaped keys of a sub-batch
+    DevBuf<uint64_t> d_qoff;
+    DevBuf<uint32_t> d_qlen;
+    std::vector<Probe> h_probe;
+    void note_child(int32_t node, int dir) {
+        if ((size_t) node < synced_inner) mod_child.push_back(node * 2 + dir);
+    }
+    void note_leaf(int32_t slot) {
+        if ((size_t) slot < synced_leaf) mod_leaf.push_back(slot);
+    }
+    int64_t splice(const Probe &pr, const uint8_t *q, uint32_t qlen, uint32_t rec);
+    int64_t set_below(int32_t top, int tdir, const uint8_t *q, uint32_t qlen, uint32_t rec);
     DevBuf<int32_t> d_child0, d_child1;
     DevBuf<uint16_t> d_diff;
     DevBuf<uint8_t> d_mask;

@@ -517,3 +517,50 @@ def test_config4_style_lookup_at_scale(ctrl_mod):
     f2 = c.contains_batch(keys[:3000])
     assert f2.tolist() == [i % 3 != 0 for i in range(3000)]
     c.free_prop()
+
+
+def test_batched_index_insert_with_conflicts(ctrl_mod):
+    """the batched CritBit insert (GPU probes + host splices) against a dict: monotone ids (most keys of a
+    sub-batch meet on the same edges), keys that replace stored ones, duplicates inside one batch, deletes followed
+    by re-inserts (slot reuse), binary keys with 251s, and prefix iteration order afterwards"""
+    rng = np.random.default_rng(12)
+    model = {}
+
+    def put(keys, tag):
+        vals = [b"v%s_%d" % (tag, i) for i in range(len(keys))]
+        rc, _ = c.setitem_batch(keys, vals)
+        want = []
+        for k, v in zip(keys, vals):
+            want.append(1 if k in model else 0)
+            model[k] = v
+        assert rc.tolist() == want, tag
+
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=4 << 20)
+    base = [b"http://h%d.example.com/a/%08d.htm" % (i % 7, 1000 + 3 * i) for i in range(20000)]   # monotone ids
+    put(base, b"a")
+    mixed = ([b"http://h%d.example.com/a/%08d.htm" % (i % 7, 1000 + 3 * i + 1) for i in range(9000)]   # neighbours of stored keys
+             + [base[i] for i in rng.integers(0, len(base), 4000)]                                     # replace stored keys
+             + [bytes([251, 250, i % 256, 251, (i >> 8) % 256]) + b"bin" for i in range(3000)])       # 251-heavy keys
+    mixed += [mixed[i] for i in rng.integers(0, len(mixed), 3000)]                                       # duplicates in the batch
+    order = rng.permutation(len(mixed))
+    put([mixed[i] for i in order], b"b")
+    # deletes, then re-inserts and fresh keys in one batch (leaf / inner slots are reused)
+    gone = [base[i] for i in range(0, len(base), 5)]
+    assert not c.delitem_batch(gone).any()
+    for k in gone:
+        del model[k]
+    put(gone[::2] + [b"http://h9.example.com/z/%07d" % i for i in range(6000)], b"c")
+    keys = list(model)
+    probe = keys + gone[1::2]
+    found = c.contains_batch(probe)
+    assert found.tolist() == [k in model for k in probe]
+    sample = [keys[i] for i in rng.integers(0, len(keys), 3000)]
+    buf, off, f = c.getitem_batch(sample)
+    assert f.all()
+    for i, k in enumerate(sample):
+        assert buf[off[i]:off[i + 1]].tobytes() == po.make_doc(k, model[k])
+    got = [ctrl_mod.split_doc(d)[0] for d in c.iter_docs(b"http://h3.")]
+    esc = lambda k: k.replace(b"\xfb", b"\xfb\xfb") + b"\xfb\x00"
+    want = sorted((k for k in model if k.startswith(b"http://h3.")), key=esc)
+    assert got == want
+    c.free_prop()
