@@ -425,7 +425,7 @@ void HostIndex::insert_batch(Store &S, uint32_t n, const uint8_t *d_keys, const 
             d_leaf_rec.reserve_keep(nl, synced_leaf, st);
             d_leaf_klen.reserve_keep(nl, synced_leaf, st);
             d_leaf_koff.reserve_keep(nl, synced_leaf, st);
-            d_keys.reserve_keep(kb, keys_uploaded, st);
+            this->d_keys.reserve_keep(kb, keys_uploaded, st);
             reserved = true;
         }
         DeviceView T = device_view(st);
