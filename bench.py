@@ -329,6 +329,124 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_getitem(args, rank, world, local_rank):
+    """BASELINE config[2] (C3): batched getitem decode of N records x 1 KB with deeply nested back references
+    (or `--workload c2`: the HTML pages).  One step = lookup + decode of EVERY stored record of this rank.
+      value : GB/s of (encoded bytes read + decoded bytes written), whole pixiu_getitem_batch_dev call timed with
+              CUDA events on the store's stream (keys are host inputs, the decoded output stays in HBM)
+      e2e   : pixiu_getitem_batch into a pinned HOST buffer (key H2D, decoded bytes D2H inside the timed region)
+      roofline : the decode kernels alone (k_decode_tiles [+ k_resolve rounds]), algorithmic bytes / event time
+    Multi-GPU: every rank holds its own records (partition by key), no collective."""
+    import torch
+
+    from pixiu_b200 import ctrl, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "c2":
+        kd, ko, vd, vo = gen_corpus(args.pages, 2 + rank)
+        wl = f"C2 decode: {args.pages} synthetic HTML-like pages x <=60KB per GPU, batched getitem of every record"
+    else:
+        kd, ko, vd, vo = synth.gen_nested(args.records, seed=3 + rank)
+        wl = (f"C3: {args.records} records x 1 KB per GPU, record r = record r-1 with one swept byte mutated "
+              f"(deeply nested back references) + self-periodic runs, batched getitem of every record")
+    n = len(ko) - 1
+    raw = int(ko[-1] + vo[-1])
+    c = ctrl.PiXiuCtrl(device=local_rank, rotate_policy=ctrl.ROTATE_REFERENCE)
+    rcs, _ = c.setitem_batch((kd, ko), (vd, vo))
+    st = c.stats()
+    ext = torch.cuda.ExternalStream(c.stream(), device=dev)
+    cap = int(st.doc_bytes + 64)
+    out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    hout = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    hout_np = hout.numpy()
+    alg = float(st.encoded_bytes + st.doc_bytes)
+
+    def step_dev():
+        return c.getitem_batch_dev((kd, ko), out.data_ptr(), cap)
+
+    def step_host():
+        return c.getitem_batch((kd, ko), out=hout_np)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    for _ in range(args.warmup):
+        off, found = step_dev()
+    assert found.all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = c.stats().kernel_launches
+    dev_ms, dev_wall = timed(step_dev, args.steps)
+    launches = c.stats().kernel_launches - l0
+    clocks = sampler.stop()
+    step_host()
+    e2e_ms, e2e_wall = timed(step_host, args.steps)
+    # decode kernels alone
+    c.profile_enable(True)
+    step_dev()
+    prof = c.profile()
+    c.profile_enable(False)
+    s = c.stats()
+    pd = prof["decode"]
+    peak, peak_kind = measured_peak()
+    ach = pd["bytes"] / 1e9 / (pd["ms"] / 1e3)
+    # bit-exact round trip of every record against the inputs (escape-free synthetic data)
+    hb = out[: int(off[-1])].cpu().numpy()
+    klen, vlen = np.diff(ko), np.diff(vo)
+    ok = bool(np.array_equal(np.diff(off), klen + vlen + 4)
+              and np.array_equal(synth.ragged_gather(hb, off[:-1], klen), kd)
+              and np.array_equal(synth.ragged_gather(hb, off[:-1] + klen + 2, vlen), vd))
+    if not ok:
+        raise SystemExit("getitem bench: decoded records differ from the inputs")
+    if rank == 0:
+        line = {"metric": "getitem_decode_throughput", "value": alg * world * args.steps / (dev_ms / 1e3) / 1e9, "unit": "GB/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": wl, "records_per_gpu": n, "raw_bytes_per_gpu": raw, "decoded_bytes_per_gpu": int(st.doc_bytes),
+                           "encoded_bytes_per_gpu": int(st.encoded_bytes), "chunks": int(st.chunks),
+                           "bytes_counted": "encoded read + decoded written (SURVEY 8d)",
+                           "l2": "decoded output (>= 1 GB) exceeds the 126 MB L2; no explicit flush"},
+                "wall_ms_per_step": dev_wall / args.steps,
+                "e2e": {"value": alg * world * args.steps / (e2e_ms / 1e3) / 1e9, "unit": "GB/s",
+                        "h2d_bytes_per_step": int(kd.nbytes + ko.nbytes), "d2h_bytes_per_step": int(off[-1]) + 9 * n,
+                        "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "k_decode_tiles(+k_resolve)", "achieved": ach, "peak": peak,
+                             "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": pd["bytes"], "avg_launch_ms": pd["ms"],
+                             "launches": pd["launches"], "lookup_ms": s.last_lookup_gpu_ms},
+                "roundtrip_all_records_ok": ok, "clocks": clocks, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    c.free_prop()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_sharded(args, rank, world, local_rank):
     """BASELINE config 5 style: ONE extended window sharded by record over the GPUs; every batch goes to
     all ranks, match lengths are MAX-reduced and leftmost candidates MIN-reduced by NCCL."""
@@ -406,10 +524,12 @@ def main():
     ap.add_argument("--ref-pages", type=int, default=150, help="bounded sample for the CPU reference leg")
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--mode", default="partition", choices=["partition", "shard"],
+    ap.add_argument("--mode", default="partition", choices=["partition", "shard", "getitem"],
                     help="partition: one store per GPU, corpus partitioned by key (default, weak scaling); "
                          "shard: one extended window sharded over the GPUs with NCCL reduces (config 5 style)")
     ap.add_argument("--batch-pages", type=int, default=256)
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3"], help="--mode getitem: which corpus to decode")
+    ap.add_argument("--records", type=int, default=1_000_000, help="--mode getitem --workload c3: records per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -418,6 +538,8 @@ def main():
         run_reference(args, rank, world)
     elif args.mode == "shard":
         run_sharded(args, rank, world, local_rank)
+    elif args.mode == "getitem":
+        run_getitem(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 
