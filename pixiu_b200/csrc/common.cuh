@@ -193,6 +193,9 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 __device__ __forceinline__ void red_release_or_u32(uint32_t *p, uint32_t v) {
     asm volatile("red.release.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_or_u32(uint32_t *p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -201,6 +204,13 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// poll of a flag word whose set bits license later (control-dependent, L2-coherent) loads of other data: the
+// "memory" clobber keeps the compiler from moving those loads above the poll
+__device__ __forceinline__ uint32_t ld_poll_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {

@@ -120,7 +120,8 @@ __device__ __forceinline__ void flush_final(const uint32_t *finw, uint32_t *lm, 
 //      is finished or held by a resident warp: waiting cannot deadlock); copied ranges are published the same way
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
-               uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t giveup_spins, uint32_t piece_cap) {
+               uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t giveup_spins, uint32_t piece_cap,
+               uint32_t sleep_after, uint32_t sleep_ns) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -455,30 +456,52 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
     flush_final(S.finw, lm, fsh, ngw, lane, pub0, pub1, pub2);
     // ---- 5. copy pieces, one per lane and row: poll the source window (acquire), copy arena -> arena with
     //         aligned 32-bit stores where a whole word belongs to the piece, publish the piece's bits (release) ----
+    // bytes of a piece already copied: a piece does not wait for its whole source window, it copies whatever has
+    // become final and keeps the rest pending, so the critical path is the nesting depth of BYTES (a window that
+    // slides from record to record would otherwise chain every record to its predecessor).  The literal phase is
+    // over: the masks take seg_ed's storage, the per-row "copied in this sweep" masks the head list's.
+    // One sweep = every row polls its sources (relaxed loads; the bytes are then read with L2-coherent loads that are
+    // control-dependent on the poll) and copies what it can; ONE fence; every row publishes its bits.  A fence per
+    // row and direction (MEMBAR.ALL.GPU, microseconds under load) made a dependency hop cost ~6 us.
+    static_assert(SEG_MAX + 1 >= PIECE_MAX, "done masks do not fit in seg_ed");
+    uint32_t *const pdone = S.seg_ed;
+    uint32_t *const cop = reinterpret_cast<uint32_t *>(S.heads);
+    for (uint32_t k = lane; k < npiece; k += 32) pdone[k] = 0;
+    if (lane < PIECE_ROWS) cop[lane] = 0;
+    __syncwarp();
     uint32_t remaining = npiece, spins = 0;
     const uint32_t nrows = (npiece + 31) / 32;
     while (remaining) {
-        uint32_t any = 0;
+        uint32_t any = 0, anycopy = 0;
         for (uint32_t row = 0; row < nrows; row++) {
             const uint32_t pm = S.pend[row];
             if (!pm) continue;
-            bool ready = false, giveup = false;
-            uint32_t meta = 0, a = 0;
+            bool ready = false, giveup = false, part = false;
+            uint32_t meta = 0, a = 0, dn = 0, avail = 0, need = 0;
             if ((pm >> lane) & 1u) {
                 meta = S.pc.meta[row * 32 + lane];
                 a = S.pc.src[row * 32 + lane];
                 const uint32_t per = (meta >> 17) & 31u;
                 const uint32_t n = per ? per : ((meta >> 12) & 31u) + 1;
-                const uint32_t wi = a >> 5, bs = a & 31, need = 0xFFFFFFFFu >> (32 - n);
-                const uint32_t nlo = need << bs;
-                uint32_t miss = nlo & ~ld_acquire_u32(V.fin + wi), mw = wi;
-                if (miss == 0 && bs + n > 32) {
-                    miss = (need >> (32 - bs)) & ~ld_acquire_u32(V.fin + wi + 1);
-                    mw = wi + 1;
+                const uint32_t wi = a >> 5, bs = a & 31;
+                need = 0xFFFFFFFFu >> (32 - n);
+                uint32_t have = ld_poll_u32(V.fin + wi) >> bs;
+                if (bs + n > 32) have |= ld_poll_u32(V.fin + wi + 1) << (32 - bs);
+                have &= need;
+                if (per) {
+                    ready = have == need;  // short periods are copied in one go
+                } else {
+                    dn = pdone[row * 32 + lane];
+                    avail = have & ~dn;
+                    ready = avail == need;
+                    part = !ready && avail != 0;
                 }
-                ready = miss == 0;
                 // a missing byte that its own tile handed to k_resolve will not become final in this kernel
-                if (!ready) giveup = spins >= giveup_spins || (ld_relaxed_u32(V.gup + mw) & miss) != 0;
+                if (!ready && !part && (spins & 7u) == 7u) {
+                    const uint32_t miss = need & ~have;
+                    giveup = spins >= giveup_spins || (ld_relaxed_u32(V.gup + wi) & (miss << bs)) != 0 ||
+                             (bs + n > 32 && (ld_relaxed_u32(V.gup + wi + 1) & (miss >> (32 - bs))) != 0);
+                }
             }
             uint32_t gb = __ballot_sync(FULL, giveup);
             if (gb) {
@@ -494,15 +517,34 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                 }
                 if (giveup) {
                     const uint32_t B = B0 + (meta & 0xFFFu), n = ((meta >> 12) & 31u) + 1;
-                    const uint32_t bits = 0xFFFFFFFFu >> (32 - n), bs = B & 31;
+                    const uint32_t bits = (0xFFFFFFFFu >> (32 - n)) & ~dn, bs = B & 31;  // the bytes still open
                     atomicOr(V.gup + (B >> 5), bits << bs);
-                    if (bs + n > 32) atomicOr(V.gup + (B >> 5) + 1, bits >> (32 - bs));
+                    if (bs + n > 32 && (bits >> (32 - bs))) atomicOr(V.gup + (B >> 5) + 1, bits >> (32 - bs));
                 }
                 if (lane == 0) atomicAdd(ctr + 2, (uint32_t) __popc(gmask));
                 remaining -= __popc(gmask);
                 any = 1;
                 if (lane == 0) S.pend[row] = pm & ~gmask;
                 __syncwarp();
+            }
+            if (part) {
+                // some source bytes are final: copy those, keep the rest pending
+                uint8_t *dst = dstu + (meta & 0xFFFu);
+                for (uint32_t m = avail; m;) {
+                    uint32_t jj[4];
+                    uint8_t bv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        jj[i] = m ? __ffs(m) - 1 : 32u;
+                        m &= m - 1;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) bv[i] = jj[i] < 32 ? __ldcg(V.arena + a + jj[i]) : (uint8_t) 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (jj[i] < 32) dst[jj[i]] = bv[i];
+                }
+                pdone[row * 32 + lane] = dn | avail;
             }
             if (ready) {
                 const uint32_t us = meta & 0xFFFu, n = ((meta >> 12) & 31u) + 1, per = (meta >> 17) & 31u;
@@ -552,17 +594,37 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                         }
                     }
                 }
-                // publish: the copied bytes before their bits
-                const uint32_t B = B0 + us, bits = 0xFFFFFFFFu >> (32 - n), bs = B & 31;
-                red_release_or_u32(V.fin + (B >> 5), bits << bs);
-                if (bs + n > 32) red_release_or_u32(V.fin + (B >> 5) + 1, bits >> (32 - bs));
+                pdone[row * 32 + lane] = 0xFFFFFFFFu >> (32 - n);
             }
-            const uint32_t rb = __ballot_sync(FULL, ready);
-            if (rb) {
-                if (lane == 0) S.pend[row] &= ~rb;
-                remaining -= __popc(rb);
-                any = 1;
+            const uint32_t cb = __ballot_sync(FULL, ready || part);
+            if (lane == 0) cop[row] = cb;
+            anycopy |= cb;
+        }
+        if (anycopy) {
+            // release side: every lane's copied bytes before the bits of any row
+            __syncwarp();
+            fence_gpu();
+            for (uint32_t row = 0; row < nrows; row++) {
+                const uint32_t cb = cop[row];
+                if (!cb) continue;
+                bool fin = false;
+                if ((cb >> lane) & 1u) {
+                    const uint32_t meta = S.pc.meta[row * 32 + lane], dn = pdone[row * 32 + lane];
+                    const uint32_t n = ((meta >> 12) & 31u) + 1;
+                    const uint32_t B = B0 + (meta & 0xFFFu), bs = B & 31;
+                    red_relaxed_or_u32(V.fin + (B >> 5), dn << bs);  // (bits published earlier are simply set again)
+                    if (bs && (dn >> (32 - bs))) red_relaxed_or_u32(V.fin + (B >> 5) + 1, dn >> (32 - bs));
+                    fin = dn == (0xFFFFFFFFu >> (32 - n));
+                }
+                const uint32_t fb = __ballot_sync(FULL, fin);
+                __syncwarp();
+                if (lane == 0) {
+                    if (fb) S.pend[row] &= ~fb;
+                    cop[row] = 0;
+                }
+                remaining -= __popc(fb);
             }
+            any = 1;
         }
         __syncwarp();
         if (!any) {
@@ -570,7 +632,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                 if (lane == 0) atomicCAS(err, 0u, 8u);
                 return;
             }
-            if (spins > 16) __nanosleep(spins > 256 ? 400 : 64);
+            if (spins > sleep_after) __nanosleep(spins > 256 ? 400 : sleep_ns);
         } else {
             spins = 0;
         }
@@ -728,10 +790,12 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     const uint32_t giveup_spins = gs ? (uint32_t) atoi(gs) : GIVEUP_SPINS;
     const char *pcs = getenv("PIXIU_PIECE_CAP");    // test knob: forces the spill path of the piece table
     const uint32_t piece_cap = pcs ? std::min<uint32_t>((uint32_t) atoi(pcs), PIECE_MAX) : PIECE_MAX;
+    const char *sa_ = getenv("PIXIU_SLEEP_AFTER"), *sn_ = getenv("PIXIU_SLEEP_NS");  // tuning knobs of the poll back-off
+    const uint32_t sleep_after = sa_ ? (uint32_t) atoi(sa_) : 16u, sleep_ns = sn_ ? (uint32_t) atoi(sn_) : 64u;
     PX_CUDA(cudaEventRecord(ev0, st));
     prof.begin(PC_DECODE, st);
     k_decode_tiles<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(
-        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins, piece_cap);
+        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins, piece_cap, sleep_after, sleep_ns);
     int nl = 1;
     uint32_t h_ctr[4] = {0, 0, 0, 0};
     PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
