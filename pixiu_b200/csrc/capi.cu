@@ -1,6 +1,7 @@
 // C ABI (include/pixiu_b200.h) over the Store: argument checking, staging of host batches,
 // error translation.  No compute happens here.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "index.h"
@@ -133,9 +134,13 @@ int getitem_common(Store &S, int64_t n, const uint8_t *keys, const int64_t *key_
                    int64_t *out_off, uint8_t *found, int64_t *need, bool dev) {
     if (n < 0 || (n && (!keys || !offsets_ok(n, key_off))) || !out_off) return PIXIU_EINVAL;
     std::vector<uint32_t> rec;
+    const auto t0 = std::chrono::steady_clock::now();
     pixiu::lookup_batch(S, n, keys, key_off, rec);
+    const auto t1 = std::chrono::steady_clock::now();
     std::vector<uint32_t> recs;
     std::vector<uint64_t> offs(1, 0);
+    recs.reserve((size_t) n);
+    offs.reserve((size_t) n + 1);
     out_off[0] = 0;
     for (int64_t i = 0; i < n; i++) {
         bool f = rec[i] != 0xFFFFFFFFu;
@@ -146,7 +151,13 @@ int getitem_common(Store &S, int64_t n, const uint8_t *keys, const int64_t *key_
         }
         out_off[i + 1] = (int64_t) offs.back();
     }
-    return decode_to(S, recs, offs, out, out_cap, dev, need);
+    const auto t2 = std::chrono::steady_clock::now();
+    const int r = decode_to(S, recs, offs, out, out_cap, dev, need);
+    if (getenv("PIXIU_TRACE"))
+        fprintf(stderr, "[getitem] n=%lld lookup %.3f ms, lists %.3f ms, decode_to %.3f ms\n", (long long) n,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count());
+    return r;
 }
 }  // namespace
 

@@ -18,6 +18,7 @@
 // Waiting is deadlock-free: a source always precedes its destination in the arena and tickets
 // follow arena order, so the tile owning a source is finished or held by a resident warp.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <map>
 
@@ -87,6 +88,13 @@ __device__ __forceinline__ uint32_t nib251(uint32_t w) {
     return ((__vcmpeq4(w, 0xFBFBFBFBu) & 0x08040201u) * 0x01010101u) >> 24;
 }
 
+__device__ __forceinline__ uint32_t nibnz(uint32_t w) {  // 4-bit mask of the nonzero bytes of w
+    return ((__vcmpne4(w, 0u) & 0x08040201u) * 0x01010101u) >> 24;
+}
+__device__ __forceinline__ uint32_t bytemask4(uint32_t m) {  // 4-bit mask -> 0xFF per selected byte
+    return (((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+}
+
 // publish the new bits of a tile's bitmap (finw, u coordinates) in the arena's bitmap (tiles share words: OR);
 // every lane looks after the global words lane, lane + 32 and lane + 64 of the tile's slice
 __device__ __forceinline__ void flush_word(const uint32_t *finw, uint32_t *lm, uint32_t sh, uint32_t ngw, uint32_t j, uint32_t &pub) {
@@ -118,7 +126,7 @@ __device__ __forceinline__ void flush_final(const uint32_t *finw, uint32_t *lm, 
 //   5. reference segments: a segment is copied once its source range is final (sources always precede their
 //      destination in the arena, and tickets are handed out in arena order, so every source belongs to a tile that
 //      is finished or held by a resident warp: waiting cannot deadlock); copied ranges are published the same way
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__(DEC_WARPS * 32, 8)
 k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
                uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t giveup_spins, uint32_t piece_cap,
                uint32_t sleep_after, uint32_t sleep_ns) {
@@ -419,12 +427,13 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
         if (lane < PIECE_ROWS) S.pend[lane] = lane < nrows0 ? (32 * (lane + 1) <= npiece ? 0xFFFFFFFFu : (1u << (npiece - 32 * lane)) - 1) : 0u;
     }
     __syncwarp();
-    // ---- 4. literal bytes, one output word per lane and step.  The bytes of a word that belong to reference
-    //         segments are overwritten later by this warp's own copies, so interior words are stored whole ----
+    // ---- 4. literal bytes, one output word per lane and step.  Bytes of a word that belong to reference segments
+    //         are stored as zero (= "not final yet", see phase 5); only ZERO-valued literals need a bit in the bitmap ----
     uint8_t *dstu = V.arena + B0;
+    uint32_t anyz = 0;
     for (uint32_t u0 = 0; u0 < nu; u0 += 128) {
         const uint32_t u = u0 + 4 * lane;
-        uint32_t m = 0;
+        uint32_t zm = 0;
         if (u < nu) {
             const uint32_t sw = S.startb[u >> 5], sh = u & 31;
             const uint32_t gi = S.wprefix[u >> 5] + __popc(sw & ((1u << sh) - 1));  // governing entry of the word's first byte
@@ -433,9 +442,10 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
             const uint32_t lo = max(u, ed & 0xFFFFu);
             const uint32_t hi = min(nibs ? u + __ffs(nibs) - 1 : u + 4, nu);
             if (lo < hi) {
-                m = ((1u << (hi - u)) - 1) & ~((1u << (lo - u)) - 1);
+                const uint32_t m = ((1u << (hi - u)) - 1) & ~((1u << (lo - u)) - 1);
                 const uint32_t q = min((u - mis + (ed >> 16)) & 0xFFFFu, STG_BYTES - 8);
-                const uint32_t wv = __funnelshift_r(S.stg[q >> 2], S.stg[(q >> 2) + 1], 8 * (q & 3));
+                const uint32_t wv = __funnelshift_r(S.stg[q >> 2], S.stg[(q >> 2) + 1], 8 * (q & 3)) & bytemask4(m);
+                zm = m & ~nibnz(wv);
                 if (u >= mis && u + 4 <= nu) {
                     *reinterpret_cast<uint32_t *>(dstu + u) = wv;
                 } else {
@@ -445,69 +455,154 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                 }
             }
         }
-        uint32_t v = m << (4 * (lane & 7));
+        uint32_t v = zm << (4 * (lane & 7));
         v |= __shfl_xor_sync(FULL, v, 1);
         v |= __shfl_xor_sync(FULL, v, 2);
         v |= __shfl_xor_sync(FULL, v, 4);
         if ((lane & 7) == 0) S.finw[(u0 >> 5) + (lane >> 3)] = v;
+        anyz |= __ballot_sync(FULL, zm != 0);
     }
     __syncwarp();
-    fence_gpu();
-    flush_final(S.finw, lm, fsh, ngw, lane, pub0, pub1, pub2);
-    // ---- 5. copy pieces, one per lane and row: poll the source window (acquire), copy arena -> arena with
-    //         aligned 32-bit stores where a whole word belongs to the piece, publish the piece's bits (release) ----
-    // bytes of a piece already copied: a piece does not wait for its whole source window, it copies whatever has
-    // become final and keeps the rest pending, so the critical path is the nesting depth of BYTES (a window that
-    // slides from record to record would otherwise chain every record to its predecessor).  The literal phase is
-    // over: the masks take seg_ed's storage, the per-row "copied in this sweep" masks the head list's.
-    // One sweep = every row polls its sources (relaxed loads; the bytes are then read with L2-coherent loads that are
-    // control-dependent on the poll) and copies what it can; ONE fence; every row publishes its bits.  A fence per
-    // row and direction (MEMBAR.ALL.GPU, microseconds under load) made a dependency hop cost ~6 us.
+    if (anyz) flush_final(S.finw, lm, fsh, ngw, lane, pub0, pub1, pub2);
+    // ---- 5. copy pieces, one per lane and row.  Finality travels IN BAND: the arena starts zeroed and a byte is only
+    //         ever stored with its final value, so a nonzero byte is final the moment it is visible; a final byte
+    //         whose value is zero is announced by its bit in V.fin (the bit IS the value, the byte itself needs no
+    //         store).  A piece loads its source words (L2-coherent relaxed loads), copies the bytes that are final,
+    //         remembers them in its done mask and retries the rest: no flag round trip, no fence, and the critical
+    //         path is the nesting depth of BYTES (measured before: flag + MEMBAR.ALL.GPU per hop ~ 5 us).  The
+    //         literal phase is over: the done masks take seg_ed's storage. ----
     static_assert(SEG_MAX + 1 >= PIECE_MAX, "done masks do not fit in seg_ed");
     uint32_t *const pdone = S.seg_ed;
-    uint32_t *const cop = reinterpret_cast<uint32_t *>(S.heads);
     for (uint32_t k = lane; k < npiece; k += 32) pdone[k] = 0;
-    if (lane < PIECE_ROWS) cop[lane] = 0;
     __syncwarp();
-    uint32_t remaining = npiece, spins = 0;
+    uint32_t remaining = npiece, spins = 0, sweep = 3;  // (the first sweep examines every piece)
     const uint32_t nrows = (npiece + 31) / 32;
-    while (remaining) {
-        uint32_t any = 0, anycopy = 0;
+    for (; remaining; sweep++) {
+        uint32_t any = 0;
         for (uint32_t row = 0; row < nrows; row++) {
             const uint32_t pm = S.pend[row];
             if (!pm) continue;
-            bool ready = false, giveup = false, part = false;
-            uint32_t meta = 0, a = 0, dn = 0, avail = 0, need = 0;
+            bool giveup = false, complete = false;
+            uint32_t meta = 0, a = 0, dn = 0, avail = 0;
             if ((pm >> lane) & 1u) {
-                meta = S.pc.meta[row * 32 + lane];
-                a = S.pc.src[row * 32 + lane];
-                const uint32_t per = (meta >> 17) & 31u;
-                const uint32_t n = per ? per : ((meta >> 12) & 31u) + 1;
-                const uint32_t wi = a >> 5, bs = a & 31;
-                need = 0xFFFFFFFFu >> (32 - n);
-                uint32_t have = ld_poll_u32(V.fin + wi) >> bs;
-                if (bs + n > 32) have |= ld_poll_u32(V.fin + wi + 1) << (32 - bs);
-                have &= need;
-                if (per) {
-                    ready = have == need;  // short periods are copied in one go
-                } else {
-                    dn = pdone[row * 32 + lane];
-                    avail = have & ~dn;
-                    ready = avail == need;
-                    part = !ready && avail != 0;
+                const uint32_t slot = row * 32 + lane;
+                meta = S.pc.meta[slot];
+                a = S.pc.src[slot];
+                const uint32_t per = (meta >> 17) & 31u, np = ((meta >> 12) & 31u) + 1, us = meta & 0xFFFu;
+                const uint32_t n = per ? per : np;  // source bytes
+                const uint32_t need = 0xFFFFFFFFu >> (32 - n);
+                dn = per ? 0u : pdone[slot];
+                uint32_t seen = 0;  // source bytes found final in this sweep
+                // a waiting piece costs one load per sweep: the source byte behind its first open byte; the whole
+                // window is examined when that byte has arrived (and every fourth sweep, for bytes out of order and
+                // for zero-valued ones).  Sweeps are what a dependency hop costs, and 32 warps per SM share the issue
+                // slots: the full examination of every piece in every sweep made a hop ~12 us.
+                bool look = (sweep & 3u) == 3u;
+                if (!look) {
+                    const uint32_t pj = a + __ffs(need & ~dn) - 1;
+                    const uint32_t w0 = ld_poll_u32(reinterpret_cast<const uint32_t *>(V.arena + (pj & ~3u)));
+                    look = ((w0 >> (8 * (pj & 3))) & 0xFFu) != 0;
+                }
+                if (look) {
+                    const uint32_t sa = a & 3, nsw = (sa + n + 3) >> 2;  // aligned source words (<= 9)
+                    const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(V.arena + (a - sa));
+                    uint32_t sw[10];
+#pragma unroll
+                    for (int q = 0; q < 5; q++) sw[q] = (uint32_t) q < nsw ? ld_poll_u32(wp0 + q) : 0u;
+#pragma unroll
+                    for (int q = 5; q < 10; q++) sw[q] = 0;
+                    if (nsw > 5) {
+#pragma unroll
+                        for (int q = 5; q < 9; q++) sw[q] = (uint32_t) q < nsw ? ld_poll_u32(wp0 + q) : 0u;
+                    }
+                    unsigned long long nzm = 0;
+#pragma unroll
+                    for (int q = 0; q < 5; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
+                    if (nsw > 5) {
+#pragma unroll
+                        for (int q = 5; q < 9; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
+                    }
+                    const uint32_t nz = (uint32_t) (nzm >> sa) & need;  // source bytes seen nonzero: final
+                    uint32_t zf = 0;  // source bytes that are final zeros
+                    const uint32_t zc = need & ~nz & ~dn;
+                    if (zc) {
+                        const uint32_t wi = a >> 5, bs = a & 31;
+                        uint32_t bits = ld_relaxed_u32(V.fin + wi) >> bs;
+                        if (bs + n > 32) bits |= ld_relaxed_u32(V.fin + wi + 1) << (32 - bs);
+                        zf = zc & bits;
+                    }
+                    seen = nz | zf;
+                    avail = seen & ~dn;
+                    if (per) avail = avail == need ? need : 0u;  // short periods are copied in one go
+                    uint32_t zout = 0;  // copied bytes whose value is zero (destination coordinates of the piece)
+                    if (avail && per) {
+                        uint8_t *dst = dstu + us;
+                        const uint32_t ph = meta >> 22;
+                        for (uint32_t j = 0; j < np; j += 4) {  // four loads in flight
+                            uint8_t bv[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) bv[i] = __ldcg(V.arena + a + (ph + j + i) % per);
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                if (j + i < np) {
+                                    dst[j + i] = bv[i];
+                                    if (bv[i] == 0) zout |= 1u << (j + i);
+                                }
+                        }
+                        dn = 0xFFFFFFFFu >> (32 - np);
+                        complete = true;
+                    } else if (avail) {
+                        // destination word t holds piece bytes [4t - da, 4t - da + 4); its source bytes straddle the
+                        // aligned source words t + c and t + c + 1 (c = -1 when the source sits further left in its word)
+                        const uint32_t da = us & 3;
+                        const int delta = (int) sa - (int) da;
+                        const uint32_t sh = 8u * (uint32_t) (delta & 3);
+                        if (delta < 0) {
+#pragma unroll
+                            for (int q = 9; q > 0; q--) sw[q] = sw[q - 1];
+                            sw[0] = 0;
+                        }
+                        uint32_t *dw = reinterpret_cast<uint32_t *>(dstu + us - da);
+                        const unsigned long long am = (unsigned long long) avail << da;  // bytes to store, word coordinates
+                        const uint32_t ndw = (da + n + 3) >> 2;
+#pragma unroll
+                        for (int t = 0; t < 9; t++) {
+                            const uint32_t vm = (uint32_t) (am >> (4 * t)) & 0xFu;
+                            if ((uint32_t) t < ndw && vm) {
+                                const uint32_t x = __funnelshift_r(sw[t], sw[t + 1], sh);
+                                if (vm == 0xFu) {
+                                    dw[t] = x;
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 4; i++)
+                                        if ((vm >> i) & 1u) reinterpret_cast<uint8_t *>(dw + t)[i] = (uint8_t) (x >> (8 * i));
+                                }
+                            }
+                        }
+                        zout = zf;
+                        dn |= avail;
+                        pdone[slot] = dn;
+                        complete = dn == need;
+                    }
+                    if (zout) {  // announce the zero-valued bytes just copied
+                        const uint32_t B = B0 + us, bs = B & 31;
+                        red_relaxed_or_u32(V.fin + (B >> 5), zout << bs);
+                        if (bs && (zout >> (32 - bs))) red_relaxed_or_u32(V.fin + (B >> 5) + 1, zout >> (32 - bs));
+                    }
                 }
                 // a missing byte that its own tile handed to k_resolve will not become final in this kernel
-                if (!ready && !part && (spins & 7u) == 7u) {
-                    const uint32_t miss = need & ~have;
+                if (!avail && (spins & 7u) == 7u) {
+                    const uint32_t miss = need & ~seen & ~dn;
+                    const uint32_t wi = a >> 5, bs = a & 31;
                     giveup = spins >= giveup_spins || (ld_relaxed_u32(V.gup + wi) & (miss << bs)) != 0 ||
                              (bs + n > 32 && (ld_relaxed_u32(V.gup + wi + 1) & (miss >> (32 - bs))) != 0);
                 }
             }
             uint32_t gb = __ballot_sync(FULL, giveup);
+            const uint32_t gmask = gb;
             if (gb) {
                 // hand the pieces over: per byte source pointers (self-overlapping references folded onto their first
                 // period), one coalesced row of pointers per piece
-                const uint32_t gmask = gb;
                 while (gb) {
                     const int r = __ffs(gb) - 1;
                     gb &= gb - 1;
@@ -524,107 +619,14 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                 if (lane == 0) atomicAdd(ctr + 2, (uint32_t) __popc(gmask));
                 remaining -= __popc(gmask);
                 any = 1;
-                if (lane == 0) S.pend[row] = pm & ~gmask;
+            }
+            const uint32_t cb = __ballot_sync(FULL, complete);
+            if (__ballot_sync(FULL, avail != 0)) any = 1;
+            if (cb | gmask) {
+                if (lane == 0) S.pend[row] = pm & ~(cb | gmask);
+                remaining -= __popc(cb);
                 __syncwarp();
             }
-            if (part) {
-                // some source bytes are final: copy those, keep the rest pending
-                uint8_t *dst = dstu + (meta & 0xFFFu);
-                for (uint32_t m = avail; m;) {
-                    uint32_t jj[4];
-                    uint8_t bv[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        jj[i] = m ? __ffs(m) - 1 : 32u;
-                        m &= m - 1;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) bv[i] = jj[i] < 32 ? __ldcg(V.arena + a + jj[i]) : (uint8_t) 0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (jj[i] < 32) dst[jj[i]] = bv[i];
-                }
-                pdone[row * 32 + lane] = dn | avail;
-            }
-            if (ready) {
-                const uint32_t us = meta & 0xFFFu, n = ((meta >> 12) & 31u) + 1, per = (meta >> 17) & 31u;
-                uint8_t *dst = dstu + us;
-                if (per) {
-                    const uint32_t ph = meta >> 22;
-                    for (uint32_t j = 0; j < n; j += 4) {  // four loads in flight
-                        uint8_t bv[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) bv[i] = __ldcg(V.arena + a + (ph + j + i) % per);
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            if (j + i < n) dst[j + i] = bv[i];
-                    }
-                } else {
-                    // destination word t holds piece bytes [4t - da, 4t - da + 4); its source bytes straddle the
-                    // aligned source words t + c and t + c + 1
-                    const uint32_t da = us & 3, sa = a & 3;
-                    const int delta = (int) sa - (int) da;
-                    const uint32_t sh = 8u * (uint32_t) (delta & 3);
-                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(V.arena + (a - sa)) + (delta < 0 ? -1 : 0);
-                    const uint32_t nsw = (sa + n + 3) >> 2;  // aligned source words the piece touches
-                    const int lastw = (int) nsw - 1 + (delta < 0 ? 1 : 0);  // last index (from wp) that may be read
-                    uint32_t *dw = reinterpret_cast<uint32_t *>(dst - da);
-                    const uint32_t ndw = (da + n + 3) >> 2;
-                    for (uint32_t t0w = 0; t0w < ndw; t0w += 4) {
-                        uint32_t wv[5];
-#pragma unroll
-                        for (int q = 0; q < 5; q++) {
-                            const int wi = (int) t0w + q;
-                            wv[q] = (wi <= lastw && !(delta < 0 && wi == 0)) ? __ldcg(wp + wi) : 0u;
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const uint32_t t = t0w + q;
-                            if (t < ndw) {
-                                const uint32_t x = __funnelshift_r(wv[q], wv[q + 1], sh);
-                                const int b0 = (int) (4 * t) - (int) da;  // piece byte of the word's first byte
-                                if (b0 >= 0 && b0 + 4 <= (int) n) {
-                                    dw[t] = x;
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 4; i++)
-                                        if (b0 + i >= 0 && b0 + i < (int) n) reinterpret_cast<uint8_t *>(dw + t)[i] = (uint8_t) (x >> (8 * i));
-                                }
-                            }
-                        }
-                    }
-                }
-                pdone[row * 32 + lane] = 0xFFFFFFFFu >> (32 - n);
-            }
-            const uint32_t cb = __ballot_sync(FULL, ready || part);
-            if (lane == 0) cop[row] = cb;
-            anycopy |= cb;
-        }
-        if (anycopy) {
-            // release side: every lane's copied bytes before the bits of any row
-            __syncwarp();
-            fence_gpu();
-            for (uint32_t row = 0; row < nrows; row++) {
-                const uint32_t cb = cop[row];
-                if (!cb) continue;
-                bool fin = false;
-                if ((cb >> lane) & 1u) {
-                    const uint32_t meta = S.pc.meta[row * 32 + lane], dn = pdone[row * 32 + lane];
-                    const uint32_t n = ((meta >> 12) & 31u) + 1;
-                    const uint32_t B = B0 + (meta & 0xFFFu), bs = B & 31;
-                    red_relaxed_or_u32(V.fin + (B >> 5), dn << bs);  // (bits published earlier are simply set again)
-                    if (bs && (dn >> (32 - bs))) red_relaxed_or_u32(V.fin + (B >> 5) + 1, dn >> (32 - bs));
-                    fin = dn == (0xFFFFFFFFu >> (32 - n));
-                }
-                const uint32_t fb = __ballot_sync(FULL, fin);
-                __syncwarp();
-                if (lane == 0) {
-                    if (fb) S.pend[row] &= ~fb;
-                    cop[row] = 0;
-                }
-                remaining -= __popc(fb);
-            }
-            any = 1;
         }
         __syncwarp();
         if (!any) {
@@ -669,8 +671,9 @@ k_resolve(uint32_t n, uint8_t *__restrict__ arena, uint32_t *__restrict__ ptr, c
                     p = i;
                     break;
                 }
-                if ((fin[p >> 5] >> (p & 31)) & 1u) {
-                    arena[i] = arena[p];
+                const uint8_t bv = __ldcg(arena + p);  // final = nonzero, or a zero announced in the bitmap
+                if (bv != 0 || ((fin[p >> 5] >> (p & 31)) & 1u)) {
+                    arena[i] = bv;
                     done = true;
                     break;
                 }
@@ -705,6 +708,7 @@ k_copy_records(uint32_t n, const uint32_t *__restrict__ recs, const uint64_t *__
 // ---------------------------------------------------------------------------------
 void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off) {
     if (recs.empty()) return;
+    const auto t_h0 = std::chrono::steady_clock::now();
     // per touched chunk: records [first, max requested] form the arena
     std::map<uint32_t, uint32_t> chunk_max;  // chunk first record -> max requested record
     for (uint32_t g : recs) {
@@ -792,8 +796,12 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     const uint32_t piece_cap = pcs ? std::min<uint32_t>((uint32_t) atoi(pcs), PIECE_MAX) : PIECE_MAX;
     const char *sa_ = getenv("PIXIU_SLEEP_AFTER"), *sn_ = getenv("PIXIU_SLEEP_NS");  // tuning knobs of the poll back-off
     const uint32_t sleep_after = sa_ ? (uint32_t) atoi(sa_) : 16u, sleep_ns = sn_ ? (uint32_t) atoi(sn_) : 64u;
+    if (getenv("PIXIU_TRACE"))
+        fprintf(stderr, "[decode] host work list %.3f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count());
     PX_CUDA(cudaEventRecord(ev0, st));
     prof.begin(PC_DECODE, st);
+    PX_CUDA(cudaMemsetAsync(arena, 0, arena_bytes, st));  // zero = "not final yet" (k_decode_tiles, phase 5): timed with the kernel
     k_decode_tiles<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(
         V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins, piece_cap, sleep_after, sleep_ns);
     int nl = 1;
