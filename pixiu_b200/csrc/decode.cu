@@ -703,6 +703,64 @@ k_copy_records(uint32_t n, const uint32_t *__restrict__ recs, const uint64_t *__
     for (uint32_t j = lane_id(); j < len; j += 32) dst[j] = src[j];
 }
 
+
+// Work list of a decode call, built on the device.  The host describes the touched chunks (a few hundred ranges at
+// most); everything per record or per tile is derived here from the record tables already resident in HBM.
+struct DecRange {
+    uint32_t first, last;      // records [first, last] of one chunk form a contiguous part of the arena
+    uint32_t tile_lo, ntiles;  // their decode tiles (global tile ids are consecutive inside a chunk)
+    uint32_t rec_cum, tile_cum;  // records / tiles of the ranges before this one
+    uint32_t arena_base, pad;
+};
+
+// arena offset of every record of the ranges
+__global__ void __launch_bounds__(256)
+k_dec_aoff(uint32_t n_rec, uint32_t n_ranges, const DecRange *__restrict__ R, const uint64_t *__restrict__ dec_prefix,
+           uint32_t *__restrict__ aoff) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_rec) return;
+    uint32_t lo = 0, hi = n_ranges;  // last range with rec_cum <= i
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (R[mid].rec_cum <= i) lo = mid;
+        else hi = mid;
+    }
+    const DecRange r = R[lo];
+    const uint32_t g = r.first + (i - r.rec_cum);
+    aoff[g] = r.arena_base + (uint32_t) (dec_prefix[g] - dec_prefix[r.first]);
+}
+
+// (tile, record) of every work item.  Tiles of one chunk keep their order (the data-flow argument needs it); chunks
+// are interleaved round-robin, so that as many dependency chains as there are chunks advance side by side: the
+// k-th tile of range c goes to position sum_c' min(ntiles_c', k) + #{c' < c : ntiles_c' > k}.
+__global__ void __launch_bounds__(256)
+k_dec_work(uint32_t n_work, uint32_t n_ranges, const DecRange *__restrict__ R, const uint32_t *__restrict__ tile_base,
+           uint32_t *__restrict__ work_tile, uint32_t *__restrict__ work_rec) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n_work) return;
+    uint32_t lo = 0, hi = n_ranges;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (R[mid].tile_cum <= j) lo = mid;
+        else hi = mid;
+    }
+    const DecRange r = R[lo];
+    const uint32_t k = j - r.tile_cum, gt = r.tile_lo + k;
+    uint32_t pos = 0;
+    for (uint32_t c = 0; c < n_ranges; c++) {
+        const uint32_t nt = R[c].ntiles;
+        pos += min(nt, k) + ((c < lo && nt > k) ? 1u : 0u);
+    }
+    uint32_t a = r.first, b = r.last + 1;  // last record with tile_base <= gt
+    while (b - a > 1) {
+        const uint32_t mid = (a + b) >> 1;
+        if (tile_base[mid] <= gt) a = mid;
+        else b = mid;
+    }
+    work_tile[pos] = gt;
+    work_rec[pos] = a;
+}
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
@@ -711,77 +769,70 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
     const auto t_h0 = std::chrono::steady_clock::now();
     // per touched chunk: records [first, max requested] form the arena
     std::map<uint32_t, uint32_t> chunk_max;  // chunk first record -> max requested record
-    for (uint32_t g : recs) {
-        uint32_t f = h_first[g];
-        auto it = chunk_max.find(f);
-        if (it == chunk_max.end()) chunk_max[f] = g;
-        else it->second = std::max(it->second, g);
+    {
+        uint32_t last_f = 0xFFFFFFFFu, *last_max = nullptr;
+        for (uint32_t g : recs) {
+            const uint32_t f = h_first[g];
+            if (f != last_f) {
+                auto it = chunk_max.find(f);
+                if (it == chunk_max.end()) it = chunk_max.emplace(f, g).first;
+                last_f = f;
+                last_max = &it->second;
+            }
+            if (g > *last_max) *last_max = g;
+        }
     }
     const size_t NR = n_records();
-    std::vector<uint32_t> aoff(NR, 0);
-    std::vector<uint32_t> wt, wr;
-    uint64_t arena_bytes = 0;
-    uint32_t lo_g = 0xFFFFFFFFu, hi_g = 0;
+    // running sum of the decoded lengths (host and device copies grow with the store)
+    if (h_dec_prefix.empty()) h_dec_prefix.push_back(0);
+    while (h_dec_prefix.size() < NR + 1) h_dec_prefix.push_back(h_dec_prefix.back() + h_dec_len[h_dec_prefix.size() - 1]);
+    if (dec_prefix_synced < NR + 1) {
+        d_dec_prefix.reserve_keep(NR + 1, dec_prefix_synced, st);
+        PX_CUDA(cudaMemcpyAsync(d_dec_prefix.p + dec_prefix_synced, h_dec_prefix.data() + dec_prefix_synced,
+                                (NR + 1 - dec_prefix_synced) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        dec_prefix_synced = NR + 1;
+    }
+    std::vector<DecRange> ranges;
+    ranges.reserve(chunk_max.size());
+    uint64_t arena_bytes = 0, n_work = 0, n_rec = 0;
     double alg_bytes = 0;
-    // direct mode: the request is exactly the arena order and the caller's layout is packed the same way
-    bool direct = ((uintptr_t) d_out & 127) == 0;
-    size_t ri = 0;
-    std::vector<uint64_t> chunk_tiles;  // tiles per touched chunk
     for (auto &cm : chunk_max) {
-        const size_t before = wt.size();
-        for (uint32_t g = cm.first; g <= cm.second; g++) {
-            if (direct) {
-                if (ri < recs.size() && recs[ri] == g && out_off[ri] == arena_bytes) ri++;
-                else direct = false;
-            }
-            aoff[g] = (uint32_t) arena_bytes;
-            uint32_t nt = div_up<uint32_t>(h_dec_len[g], TILE);
-            for (uint32_t t = 0; t < nt; t++) {
-                wt.push_back(h_tile_base[g] + t);
-                wr.push_back(g);
-            }
-            arena_bytes += h_dec_len[g];
-            alg_bytes += (double) h_enc_len[g] + h_dec_len[g];
-            lo_g = std::min(lo_g, g);
-            hi_g = std::max(hi_g, g);
-        }
-        chunk_tiles.push_back(wt.size() - before);
+        const uint32_t f = cm.first, m = cm.second;
+        const uint32_t tile_lo = h_tile_base[f], tile_hi = h_tile_base[m] + div_up<uint32_t>(h_dec_len[m], TILE);
+        if (arena_bytes >= 0xFFFFFF00ull) break;
+        ranges.push_back(DecRange{f, m, tile_lo, tile_hi - tile_lo, (uint32_t) n_rec, (uint32_t) n_work, (uint32_t) arena_bytes, 0u});
+        arena_bytes += h_dec_prefix[m + 1] - h_dec_prefix[f];
+        n_work += tile_hi - tile_lo;
+        n_rec += m - f + 1;
+        alg_bytes += (double) (h_enc_off[m] + h_enc_len[m] - h_enc_off[f]) + (double) (h_dec_prefix[m + 1] - h_dec_prefix[f]);
     }
-    if (ri != recs.size()) direct = false;
     if (arena_bytes >= 0xFFFFFF00ull) throw std::runtime_error("decode: arena of one call exceeds 4 GiB; split the batch");
-    if (!direct) dec_scratch.reserve_discard(arena_bytes + 256);  // same packed layout, private buffer
-    const uint64_t n_work = wt.size();
-    if (chunk_tiles.size() > 1) {
-        // tiles of different chunks are independent (references are chunk-local): hand them out round-robin, so that
-        // as many dependency chains as there are chunks advance side by side; the order inside a chunk is kept
-        std::vector<uint32_t> wt2(n_work), wr2(n_work);
-        std::vector<uint64_t> cur(chunk_tiles.size()), end(chunk_tiles.size());
-        uint64_t acc = 0;
-        for (size_t c = 0; c < chunk_tiles.size(); c++) {
-            cur[c] = acc;
-            acc += chunk_tiles[c];
-            end[c] = acc;
+    // direct mode: the request is exactly the arena order and the caller's layout is packed the same way
+    bool direct = ((uintptr_t) d_out & 127) == 0 && recs.size() == n_rec;
+    if (direct) {
+        size_t ri = 0;
+        for (const DecRange &r : ranges) {
+            const uint64_t base = (uint64_t) r.arena_base - h_dec_prefix[r.first];
+            for (uint32_t g = r.first; g <= r.last && direct; g++, ri++)
+                direct = recs[ri] == g && out_off[ri] == base + h_dec_prefix[g];
+            if (!direct) break;
         }
-        uint64_t o = 0;
-        while (o < n_work)
-            for (size_t c = 0; c < chunk_tiles.size(); c++)
-                if (cur[c] < end[c]) {
-                    wt2[o] = wt[cur[c]];
-                    wr2[o++] = wr[cur[c]++];
-                }
-        wt.swap(wt2);
-        wr.swap(wr2);
     }
+    if (!direct) dec_scratch.reserve_discard(arena_bytes + 256);  // same packed layout, private buffer
     uint8_t *arena = direct ? d_out : dec_scratch.p;
     const size_t bm_words = arena_bytes / 32 + 64;
-    dec_flags.reserve_discard(2 * bm_words);                  // "final" bitmap, then the "handed over" bitmap
+    dec_flags.reserve_discard(2 * bm_words);                  // zero-byte bitmap, then the "handed over" bitmap
     dec_ptr.reserve_discard(arena_bytes + 64);                // source pointers (touched only for handed-over bytes)
     dec_aoff.reserve_discard(NR + 1);
-    PX_CUDA(cudaMemcpyAsync(dec_aoff.p + lo_g, aoff.data() + lo_g, (size_t) (hi_g - lo_g + 1) * sizeof(uint32_t),
-                            cudaMemcpyHostToDevice, st));
     dec_work.reserve_discard(2 * n_work + 2);
-    PX_CUDA(cudaMemcpyAsync(dec_work.p, wt.data(), n_work * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    PX_CUDA(cudaMemcpyAsync(dec_work.p + n_work, wr.data(), n_work * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    dec_ranges.reserve_discard(ranges.size() * sizeof(DecRange) / sizeof(uint32_t) + 8);
+    DecRange *d_ranges = reinterpret_cast<DecRange *>(dec_ranges.p);
+    PX_CUDA(cudaMemcpyAsync(d_ranges, ranges.data(), ranges.size() * sizeof(DecRange), cudaMemcpyHostToDevice, st));
+    k_dec_aoff<<<(unsigned) div_up<uint64_t>(n_rec, 256), 256, 0, st>>>((uint32_t) n_rec, (uint32_t) ranges.size(), d_ranges,
+                                                                        d_dec_prefix.p, dec_aoff.p);
+    k_dec_work<<<(unsigned) div_up<uint64_t>(n_work, 256), 256, 0, st>>>((uint32_t) n_work, (uint32_t) ranges.size(), d_ranges,
+                                                                         d_tile_base.p, dec_work.p, dec_work.p + n_work);
+    launches += 2;
     dec_ctr.reserve_discard(64);
     PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));  // [0] error, [1] tile ticket, [2] pieces handed over
     PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, 2 * bm_words * sizeof(uint32_t), st));

@@ -107,7 +107,11 @@ struct Store {
     uint64_t last_handed_over = 0; // pieces the last decode handed to k_resolve
     DevBuf<uint32_t> dec_aoff;     // per record: offset in the arena
     DevBuf<uint32_t> dec_reqs;     // requested record ids
-    DevBuf<uint32_t> dec_work;     // work list: tile ids, then record ids
+    DevBuf<uint32_t> dec_work;     // work list: tile ids, then record ids (built by k_dec_work)
+    DevBuf<uint32_t> dec_ranges;   // touched chunk ranges of the call (DecRange[], decode.cu)
+    std::vector<uint64_t> h_dec_prefix;  // running sum of h_dec_len (NR + 1 entries, extended lazily)
+    DevBuf<uint64_t> d_dec_prefix;
+    size_t dec_prefix_synced = 0;
     DevBuf<uint32_t> dec_ctr;      // [0] error, [1] tile ticket, [2] pieces handed over, [3+r] unfinished CTAs of resolve round r
 
     // ---- staging for batches ----
