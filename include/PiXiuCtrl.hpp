@@ -150,6 +150,10 @@ struct PiXiuCtrl {
         return g;
     }
 
+    // PiXiuCtrl.cpp:88-114, by chunk id instead of `PiXiuChunk *&` (set config.auto_reinsert = 1 before init_prop for
+    // the reference's trigger).  Returns the number of records moved or a negative PIXIU_E* code.
+    int64_t reinsert(int64_t chunk) { return pixiu_reinsert_chunk(store, chunk); }
+
     // ---- batched forms (packed data + int64 offsets), in-order semantics of n single calls ----
     int setitem_batch(int64_t n, const uint8_t *keys, const int64_t *key_off, const uint8_t *vals,
                       const int64_t *val_off, int32_t *rc, int32_t *saved = nullptr) {

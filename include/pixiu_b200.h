@@ -12,6 +12,7 @@
  *   PiXiuCtrl::getitem    (PiXiuCtrl.cpp:59-61)  -> pixiu_getitem_batch   (drained PXSGen streams)
  *   PiXiuCtrl::delitem    (PiXiuCtrl.cpp:63-69)  -> pixiu_delitem_batch
  *   PiXiuCtrl::iter       (PiXiuCtrl.cpp:71-75)  -> pixiu_iter
+ *   PiXiuCtrl::reinsert   (PiXiuCtrl.cpp:88-114) -> pixiu_reinsert_chunk (+ pixiu_config.auto_reinsert for the trigger)
  *   ctrl.st.cbt_chunk->getitem(i)->{len,data} (main.cpp:67) -> pixiu_encoded_view
  *
  * Conventions: plain pointers and sizes; inputs are borrowed; outputs go to caller
@@ -53,7 +54,8 @@ typedef struct pixiu_config {
     int32_t rotate_policy;   /* PIXIU_ROTATE_* */
     int64_t window_bytes;    /* for PIXIU_ROTATE_BYTES */
     int32_t strict251;       /* 1: reproduce reference bug B1 (run of 251 -> ambiguous FB FB form) */
-    int32_t reserved;
+    int32_t auto_reinsert;   /* 1: the reference's compaction trigger (PiXiuCtrl.cpp:7-8,:26-29,:64-67): a closed chunk
+                                with < 50 % live records is re-inserted before the next setitem batch / delitem */
 } pixiu_config;
 
 typedef struct pixiu_stats {
@@ -68,6 +70,8 @@ typedef struct pixiu_stats {
     double last_setitem_gpu_ms; /* device time of the last setitem batch (CUDA events) */
     double last_getitem_gpu_ms;
     double last_lookup_gpu_ms;
+    int64_t reinserted_records; /* records moved by pixiu_reinsert_chunk / the auto_reinsert trigger so far */
+    int64_t reclaimable_bytes;  /* encoded bytes of dropped chunks (still resident; freed by export + import) */
 } pixiu_stats;
 
 void pixiu_default_config(pixiu_config *cfg);
@@ -106,6 +110,14 @@ int pixiu_iter(pixiu_store *s, const uint8_t *prefix, int64_t prefix_len, uint8_
 int pixiu_encoded_view(pixiu_store *s, int64_t chunk, int64_t idx, uint8_t *out, int64_t out_cap);
 /* (chunk, idx) of the i-th record ever inserted */
 int pixiu_record_location(pixiu_store *s, int64_t record, int64_t *chunk, int64_t *idx);
+
+/* PiXiuCtrl::reinsert (PiXiuCtrl.cpp:88-114): decode the live records of a CLOSED chunk, insert them again through
+ * the setitem path (they compress against the open window and replace themselves in the index) and drop the chunk.
+ * Works for chunks of any size (the reference dereferences NULL slots of non-full chunks, bug B4).  Returns the
+ * number of records moved or a negative error. */
+int64_t pixiu_reinsert_chunk(pixiu_store *s, int64_t chunk);
+/* records ever stored in the chunk, records still live, and whether it was dropped by a re-insertion */
+int pixiu_chunk_info(pixiu_store *s, int64_t chunk, int64_t *total, int64_t *live, int32_t *dropped);
 
 /* Import one pre-encoded chunk (array of PiXiu-encoded records, e.g. produced by the
  * reference) as a new closed chunk and index its keys; used by parity tests and as the

@@ -159,6 +159,92 @@ int getitem_common(Store &S, int64_t n, const uint8_t *keys, const int64_t *key_
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count());
     return r;
 }
+
+// PiXiuCtrl::reinsert (PiXiuCtrl.cpp:88-114): the live records of a closed chunk are decoded (GPU), inserted again
+// through the ordinary setitem path (they compress against the open window and replace themselves in the index,
+// which tombstones the old copies) and the chunk is dropped.  Unlike the reference (bug B4: it walks all 65,535 slots
+// and dereferences the NULL ones) this works for chunks of any size.  Returns the number of records moved.
+int64_t reinsert_chunk(Store &S, int64_t c) {
+    if (c < 0 || c >= (int64_t) S.n_chunks()) return PIXIU_EINVAL;
+    if (S.win_open && c == (int64_t) S.n_chunks() - 1) return PIXIU_EINVAL;  // never the open chunk (PiXiuCtrl.cpp:26)
+    if (S.chunk_dropped.size() < S.n_chunks()) S.chunk_dropped.resize(S.n_chunks(), 0);
+    if (S.chunk_dropped[c]) return 0;
+    std::vector<uint32_t> recs;
+    std::vector<uint64_t> offs(1, 0);
+    const uint32_t g0 = S.chunk_first[c], cnt = S.chunk_count[c];
+    for (uint32_t r = 0; r < cnt; r++)
+        if (S.h_live[g0 + r]) {
+            recs.push_back(g0 + r);
+            offs.push_back(offs.back() + S.h_dec_len[g0 + r]);
+        }
+    const int64_t n = (int64_t) recs.size();
+    if (n) {
+        std::vector<uint8_t> docs(offs.back() + 1);
+        int d = decode_to(S, recs, offs, docs.data(), (int64_t) docs.size(), false, nullptr);
+        if (d != PIXIU_OK) return d;
+        // doc = esc(k) 251 0 [esc(v) 251 2]  ->  raw key, raw value
+        std::vector<uint8_t> keys, vals;
+        std::vector<int64_t> koff(1, 0), voff(1, 0);
+        keys.reserve(docs.size());
+        vals.reserve(docs.size());
+        for (int64_t i = 0; i < n; i++) {
+            const uint8_t *p = docs.data() + offs[i];
+            const uint32_t len = (uint32_t) (offs[i + 1] - offs[i]);
+            bool in_val = false, closed = false;
+            for (uint32_t k = 0; k < len;) {
+                if (p[k] != 251) {
+                    (in_val ? vals : keys).push_back(p[k++]);
+                    continue;
+                }
+                if (k + 1 >= len) return PIXIU_ECORRUPT;
+                const uint8_t nx = p[k + 1];
+                if (nx == 251) (in_val ? vals : keys).push_back(251);
+                else if (nx == 0 && !in_val) in_val = true;
+                else if (nx == 2 && in_val) closed = true;
+                else return PIXIU_ECORRUPT;
+                k += 2;
+            }
+            if (!in_val || (closed != ((int64_t) vals.size() > voff.back()))) return PIXIU_ECORRUPT;
+            koff.push_back((int64_t) keys.size());
+            voff.push_back((int64_t) vals.size());
+        }
+        keys.push_back(0);
+        vals.push_back(0);
+        std::vector<int32_t> rc((size_t) n);
+        stage(S, n, keys.data(), koff.data(), S.in_keys, S.in_koff);
+        stage(S, n, vals.data(), voff.data(), S.in_vals, S.in_voff);
+        const int64_t raw0 = S.raw_bytes, doc0 = S.doc_bytes;
+        int r = S.setitem_batch(n, S.in_keys.p, S.in_koff.p, S.in_vals.p, S.in_voff.p, keys.data(), koff.data(), voff.data(),
+                                rc.data(), nullptr);
+        if (r != PIXIU_OK) return r;
+        S.raw_bytes = raw0;  // moved, not added
+        S.doc_bytes = doc0;
+        for (int64_t i = 0; i < n; i++)
+            if (rc[i] != PIXIU_CBT_SET_REPLACE) {
+                S.err = "reinsert: a live record did not replace itself";
+                return PIXIU_EINTERNAL;
+            }
+    }
+    if (S.chunk_dropped.size() < S.n_chunks()) S.chunk_dropped.resize(S.n_chunks(), 0);
+    S.chunk_dropped[c] = 1;
+    S.reinserted_records += n;
+    const uint32_t gl = g0 + cnt - 1;
+    if (cnt) S.reclaimable_bytes += (int64_t) (S.h_enc_off[gl] + S.h_enc_len[gl] - S.h_enc_off[g0]);
+    if (S.reinsert_candidate == c) S.reinsert_candidate = -1;
+    return n;
+}
+
+// the reference's trigger (PiXiuCtrl.cpp:7-8,:26-29,:64-67): a chunk that a tombstone left below 0.8 x 65,535 live
+// records is remembered; it is re-inserted as soon as it is not the open chunk and less than half of it is live
+int64_t maybe_reinsert(Store &S) {
+    const int64_t c = S.reinsert_candidate;
+    if (c < 0 || c >= (int64_t) S.n_chunks()) return 0;
+    if (S.win_open && c == (int64_t) S.n_chunks() - 1) return 0;
+    if (c < (int64_t) S.chunk_dropped.size() && S.chunk_dropped[c]) return 0;
+    const uint32_t live = c < (int64_t) S.chunk_live.size() ? S.chunk_live[c] : 0;
+    if (!(live < 0.5 * S.chunk_count[c])) return 0;
+    return reinsert_chunk(S, c);
+}
 }  // namespace
 
 extern "C" {
@@ -198,6 +284,24 @@ void pixiu_destroy(pixiu_store *h) {
 
 const char *pixiu_last_error(const pixiu_store *h) { return h ? h->s.err.c_str() : "null store"; }
 
+int64_t pixiu_reinsert_chunk(pixiu_store *h, int64_t chunk) {
+    int64_t moved = 0;
+    int rc = guarded(h, [&](Store &S) -> int {
+        moved = reinsert_chunk(S, chunk);
+        return moved < 0 ? (int) moved : PIXIU_OK;
+    });
+    return rc == PIXIU_OK ? moved : rc;
+}
+
+int pixiu_chunk_info(pixiu_store *h, int64_t chunk, int64_t *total, int64_t *live, int32_t *dropped) {
+    if (!h || chunk < 0 || chunk >= (int64_t) h->s.n_chunks()) return PIXIU_EINVAL;
+    Store &S = h->s;
+    if (total) *total = S.chunk_count[chunk];
+    if (live) *live = chunk < (int64_t) S.chunk_live.size() ? S.chunk_live[chunk] : 0;
+    if (dropped) *dropped = chunk < (int64_t) S.chunk_dropped.size() ? S.chunk_dropped[chunk] : 0;
+    return PIXIU_OK;
+}
+
 int pixiu_get_stats(pixiu_store *h, pixiu_stats *o) {
     if (!h || !o) return PIXIU_EINVAL;
     Store &S = h->s;
@@ -212,6 +316,8 @@ int pixiu_get_stats(pixiu_store *h, pixiu_stats *o) {
     o->last_setitem_gpu_ms = S.last_set_ms;
     o->last_getitem_gpu_ms = S.last_get_ms;
     o->last_lookup_gpu_ms = S.last_lookup_ms;
+    o->reinserted_records = S.reinserted_records;
+    o->reclaimable_bytes = S.reclaimable_bytes;
     return PIXIU_OK;
 }
 
@@ -221,6 +327,10 @@ int pixiu_setitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const in
         if (n < 0 || (n && (!keys || !offsets_ok(n, key_off) || !offsets_ok(n, val_off)))) return PIXIU_EINVAL;
         if (n == 0) return PIXIU_OK;
         if (val_off[n] > val_off[0] && !vals) return PIXIU_EINVAL;
+        if (S.cfg.auto_reinsert) {
+            int64_t m = maybe_reinsert(S);
+            if (m < 0) return (int) m;
+        }
         stage(S, n, keys, key_off, S.in_keys, S.in_koff);
         stage(S, n, vals, val_off, S.in_vals, S.in_voff);
         return S.setitem_batch(n, S.in_keys.p, S.in_koff.p, S.in_vals.p, S.in_voff.p, keys, key_off, val_off, rc, saved);
@@ -238,6 +348,10 @@ int pixiu_setitem_batch_dev(pixiu_store *h, int64_t n, const uint8_t *d_keys, co
         PX_CUDA(cudaMemcpyAsync(voff.data(), d_val_off, (size_t) (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, S.st));
         PX_CUDA(cudaStreamSynchronize(S.st));
         if (koff[0] != 0 || voff[0] != 0 || !offsets_ok(n, koff.data()) || !offsets_ok(n, voff.data())) return PIXIU_EINVAL;
+        if (S.cfg.auto_reinsert) {
+            int64_t m = maybe_reinsert(S);
+            if (m < 0) return (int) m;
+        }
         std::vector<uint8_t> hk((size_t) koff[n] + 1);
         PX_CUDA(cudaMemcpyAsync(hk.data(), d_keys, (size_t) koff[n], cudaMemcpyDeviceToHost, S.st));
         PX_CUDA(cudaStreamSynchronize(S.st));
@@ -261,11 +375,13 @@ int pixiu_delitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const in
         std::vector<uint8_t> q;
         for (int64_t i = 0; i < n; i++) {
             pixiu::escape_key(keys + key_off[i], (size_t) (key_off[i + 1] - key_off[i]), q);
-            int64_t r = S.index->del(q.data(), (uint32_t) q.size());
-            if (r >= 0) {
-                S.h_live[r] = 0;  // tombstone: bytes stay, later records may reference them (PiXiuStr.cpp:178-187)
-                S.live_records--;
+            // (PiXiuCtrl::delitem, PiXiuCtrl.cpp:63-69: the compaction trigger is looked at before every delete)
+            if (S.cfg.auto_reinsert) {
+                int64_t m = maybe_reinsert(S);
+                if (m < 0) return (int) m;
             }
+            int64_t r = S.index->del(q.data(), (uint32_t) q.size());
+            if (r >= 0) S.tombstone((uint32_t) r);
             if (rc) rc[i] = r >= 0 ? 0 : PIXIU_CBT_DEL_NOT_FOUND;
         }
         return PIXIU_OK;
@@ -365,11 +481,8 @@ int64_t pixiu_import_chunk(pixiu_store *h, int64_t n, const uint8_t *enc, const 
             while (k + 1 < len && !(p[k] == 251 && p[k + 1] == 0)) k += (p[k] == 251) ? 2 : 1;
             if (k + 1 >= len) return PIXIU_ECORRUPT;
             int64_t old = S.index->set(p, k + 2, recs[r]);
-            if (old >= 0) {
-                S.h_live[old] = 0;
-                S.live_records--;
-            }
-            S.live_records++;
+            if (old >= 0) S.tombstone((uint32_t) old);
+            S.note_live(recs[r]);
             S.doc_bytes += len;
         }
         return PIXIU_OK;
@@ -389,6 +502,10 @@ int pixiu_mg_setitem_begin(pixiu_store *h, int64_t n, const uint8_t *keys, const
     return guarded(h, [&](Store &S) -> int {
         if (n <= 0 || !keys || !offsets_ok(n, key_off) || !offsets_ok(n, val_off) || !d_m || !count) return PIXIU_EINVAL;
         if (val_off[n] > val_off[0] && !vals) return PIXIU_EINVAL;
+        if (S.cfg.auto_reinsert) {
+            int64_t m = maybe_reinsert(S);
+            if (m < 0) return (int) m;
+        }
         stage(S, n, keys, key_off, S.in_keys, S.in_koff);
         stage(S, n, vals, val_off, S.in_vals, S.in_voff);
         return S.mg_begin(n, S.in_keys.p, S.in_koff.p, S.in_vals.p, S.in_voff.p, keys, key_off, val_off, d_m, count);

@@ -1284,11 +1284,8 @@ void Store::finish_index(uint32_t nn, size_t g_batch_first, const uint8_t *d_key
     index->insert_batch(*this, nn, d_keys, d_koff, h_keys, h_koff, (uint32_t) g_batch_first, old.data());
     for (uint32_t i = 0; i < nn; i++) {
         const uint32_t g = (uint32_t) (g_batch_first + i);
-        if (old[i] >= 0) {
-            h_live[old[i]] = 0;
-            live_records--;
-        }
-        live_records++;
+        if (old[i] >= 0) tombstone((uint32_t) old[i]);
+        note_live(g);
         if (rc) rc[i] = old[i] >= 0 ? PIXIU_CBT_SET_REPLACE : 0;
         if (saved) saved[i] = (int32_t) h_doc_len[i] - (int32_t) h_enc_len[g];
         raw_bytes += (h_koff[i + 1] - h_koff[i]) + (h_voff[i + 1] - h_voff[i]);

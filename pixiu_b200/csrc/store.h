@@ -16,6 +16,7 @@
 //                                   rec_start u32[R+1]
 //   index mirror:                   CritBit nodes as SoA (child0/child1 i32, diff_at u16, mask u8)
 #pragma once
+#include <algorithm>
 #include <memory>
 #include <string>
 #include <vector>
@@ -78,6 +79,28 @@ struct Store {
     std::vector<uint32_t> chunk_count;  // records in chunk c
     uint64_t enc_bytes = 0, n_tiles = 0;
     int64_t raw_bytes = 0, doc_bytes = 0, live_records = 0;
+    // occupancy per chunk and the reference's compaction trigger (PiXiuStr.cpp:178-187, PiXiuCtrl.cpp:7-8,:26-29)
+    std::vector<uint32_t> chunk_live;    // live (not tombstoned) records of chunk c
+    std::vector<uint8_t> chunk_dropped;  // chunk c was re-inserted: none of its records is live or reachable
+    int64_t reinsert_candidate = -1;     // Glob_Reinsert_Chunk
+    int64_t reinserted_records = 0, reclaimable_bytes = 0;
+    size_t chunk_of(uint32_t g) const {
+        return (size_t) (std::upper_bound(chunk_first.begin(), chunk_first.end(), g) - chunk_first.begin()) - 1;
+    }
+    void note_live(uint32_t g) {
+        const size_t c = chunk_of(g);
+        if (chunk_live.size() <= c) chunk_live.resize(c + 1, 0);
+        chunk_live[c]++;
+        live_records++;
+    }
+    void tombstone(uint32_t g) {  // PiXiuChunk::delitem (PiXiuStr.cpp:178-187): the bytes stay, later records may reference them
+        h_live[g] = 0;
+        live_records--;
+        const size_t c = chunk_of(g);
+        if (chunk_live.size() <= c) chunk_live.resize(c + 1, 0);
+        chunk_live[c]--;
+        if (chunk_live[c] < 0.8 * MAX_CHUNK_RECS) reinsert_candidate = (int64_t) c;
+    }
 
     // ---- device store ----
     VmArena d_enc;  // compressed arena: 256 GiB of address space, physical memory mapped as it fills

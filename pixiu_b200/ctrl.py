@@ -31,7 +31,7 @@ ROTATE_REFERENCE, ROTATE_BYTES, ROTATE_RECORDS = 0, 1, 2
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("rotate_policy", C.c_int32), ("window_bytes", C.c_int64),
-                ("strict251", C.c_int32), ("reserved", C.c_int32)]
+                ("strict251", C.c_int32), ("auto_reinsert", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -39,7 +39,8 @@ class Stats(C.Structure):
                 ("raw_bytes", C.c_int64), ("doc_bytes", C.c_int64), ("encoded_bytes", C.c_int64),
                 ("window_bytes", C.c_int64), ("kernel_launches", C.c_int64),
                 ("last_setitem_gpu_ms", C.c_double), ("last_getitem_gpu_ms", C.c_double),
-                ("last_lookup_gpu_ms", C.c_double)]
+                ("last_lookup_gpu_ms", C.c_double),
+                ("reinserted_records", C.c_int64), ("reclaimable_bytes", C.c_int64)]
 
 
 EXPORTS = [
@@ -48,6 +49,7 @@ EXPORTS = [
     "pixiu_getitem_batch", "pixiu_getitem_batch_dev", "pixiu_iter", "pixiu_encoded_view",
     "pixiu_record_location", "pixiu_import_chunk", "pixiu_decode_chunk", "pixiu_rotate",
     "pixiu_profile_enable", "pixiu_profile_get", "pixiu_stream",
+    "pixiu_reinsert_chunk", "pixiu_chunk_info",
     "pixiu_export_chunk", "pixiu_mg_config", "pixiu_mg_setitem_begin", "pixiu_mg_setitem_mid", "pixiu_mg_setitem_end",
 ]
 
@@ -83,6 +85,9 @@ def load_library():
     L.pixiu_import_chunk.restype = C.c_int64
     L.pixiu_decode_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p]
     L.pixiu_rotate.argtypes = [C.c_void_p]
+    L.pixiu_reinsert_chunk.argtypes = [C.c_void_p, C.c_int64]
+    L.pixiu_reinsert_chunk.restype = C.c_int64
+    L.pixiu_chunk_info.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p, _i32p]
     L.pixiu_export_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p, _i64p]
     L.pixiu_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.pixiu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
@@ -201,9 +206,9 @@ class PiXiuCtrl:
     """Drop-in for the reference's ``struct PiXiuCtrl`` — same methods, plus ``*_batch``."""
 
     def __init__(self, device: int = 0, rotate_policy: int = ROTATE_REFERENCE, window_bytes: int = 12_500_000,
-                 strict251: bool = False):
+                 strict251: bool = False, auto_reinsert: bool = False):
         self._L = load_library()
-        self._cfg = Config(device, rotate_policy, window_bytes, int(strict251), 0)
+        self._cfg = Config(device, rotate_policy, window_bytes, int(strict251), int(auto_reinsert))
         self._h = None
         self.init_prop()
 
@@ -343,6 +348,17 @@ class PiXiuCtrl:
         c, i = C.c_int64(), C.c_int64()
         self._check(self._L.pixiu_record_location(self._h, record, C.byref(c), C.byref(i)))
         return c.value, i.value
+
+    def reinsert(self, chunk: int) -> int:
+        """PiXiuCtrl::reinsert (PiXiuCtrl.cpp:88-114): move the live records of a closed chunk into the open window
+        and drop the chunk; returns the number of records moved"""
+        return self._check(self._L.pixiu_reinsert_chunk(self._h, chunk))
+
+    def chunk_info(self, chunk: int):
+        """-> (records ever stored in the chunk, live records, dropped by a re-insertion)"""
+        t, l, d = C.c_int64(), C.c_int64(), C.c_int32()
+        self._check(self._L.pixiu_chunk_info(self._h, chunk, C.byref(t), C.byref(l), C.byref(d)))
+        return t.value, l.value, bool(d.value)
 
     def import_chunk(self, encs) -> int:
         ed, eo = encs if isinstance(encs, tuple) else _pack(encs)

@@ -564,3 +564,85 @@ def test_batched_index_insert_with_conflicts(ctrl_mod):
     want = sorted((k for k in model if k.startswith(b"http://h3.")), key=esc)
     assert got == want
     c.free_prop()
+
+
+# --------------------------------------------------------------------------- compaction (PiXiuCtrl::reinsert)
+def test_reinsert_chunk_moves_live_records(ctrl_mod):
+    """explicit pixiu_reinsert_chunk on a partially deleted, non-full chunk (the reference crashes there, bug B4):
+    every live key keeps its document, the old chunk ends with no live record, moved records sit in the open chunk"""
+    rng = np.random.default_rng(5)
+    keys = [b"http://c%d.example.org/p/%06d" % (i % 5, i) for i in range(6000)]
+    vals = [bytes(rng.integers(97, 123, size=int(rng.integers(20, 400))).astype(np.uint8)) + b"<div class=x>" * int(rng.integers(0, 6))
+            for _ in keys]
+    vals[7] = b""                                  # key-only record
+    vals[11] = bytes([251, 0, 251, 2, 251, 251]) * 9    # escapes in the value
+    keys[13] = bytes([251, 251, 0, 7]) + keys[13]
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=400_000)
+    assert not c.setitem_batch(keys, vals)[0].any()
+    st0 = c.stats()
+    assert st0.chunks >= 3
+    total0, live0, dropped0 = c.chunk_info(0)
+    assert live0 == total0 and not dropped0
+    first_chunk = [i for i in range(len(keys)) if c.record_location(i)[0] == 0]
+    gone = set(first_chunk[::3] + first_chunk[1::3])            # two thirds of chunk 0
+    assert not c.delitem_batch([keys[i] for i in sorted(gone)]).any()
+    assert c.chunk_info(0)[1] == total0 - len(gone)
+    with pytest.raises(ctrl_mod.PiXiuError):
+        c.reinsert(st0.chunks - 1)                              # never the open chunk (PiXiuCtrl.cpp:26)
+    moved = c.reinsert(0)
+    assert moved == total0 - len(gone)
+    assert c.chunk_info(0) == (total0, 0, True)
+    assert c.reinsert(0) == 0                                   # idempotent
+    st1 = c.stats()
+    assert st1.live_records == len(keys) - len(gone) and st1.records == st0.records + moved
+    assert st1.reinserted_records == moved and st1.reclaimable_bytes > 0
+    buf, off, found = c.getitem_batch(keys)
+    assert found.tolist() == [i not in gone for i in range(len(keys))]
+    for i in range(len(keys)):
+        if i not in gone:
+            assert buf[off[i]:off[i + 1]].tobytes() == po.make_doc(keys[i], vals[i]), i
+    # iteration order and content unchanged
+    got = [ctrl_mod.split_doc(d)[0] for d in c.iter_docs(b"http://c3.")]
+    esc = lambda k: k.replace(b"\xfb", b"\xfb\xfb") + b"\xfb\x00"
+    assert got == sorted((keys[i] for i in range(len(keys)) if i not in gone and keys[i].startswith(b"http://c3.")), key=esc)
+    c.free_prop()
+
+
+def test_auto_reinsert_matches_live_reference(ctrl_mod, ref):
+    """the reference's own trigger on a FULL chunk (65,535 records; its reinsert only works there): after more than
+    half of chunk 0 is deleted, the next call re-inserts the survivors.  Same return codes, same survivors, and the
+    re-inserted records are byte-identical to the reference's (same order, same window)."""
+    n0 = 65535 + 40
+    keys = [b"k%07d" % i for i in range(n0)]
+    vals = [b"v%05d-%s" % (i % 977, b"abcdefghij"[: 1 + i % 9]) for i in range(n0)]
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_REFERENCE, strict251=True, auto_reinsert=True)
+    rc, _ = c.setitem_batch(keys, vals)
+    ref.reset()
+    r = ref.setitem_batch(keys, vals)
+    assert rc.tolist() == r["rc"].tolist()
+    assert c.stats().chunks == 2 and c.chunk_info(0)[0] == 65535
+    kill = [keys[i] for i in range(0, 65535, 2)] + [keys[i] for i in range(1, 2000, 2)]     # 33,768 of chunk 0
+    # (a delitem batch looks at the trigger before every delete, like n single calls)
+    assert not c.delitem_batch(kill).any()
+    assert all(ref.delitem(k) == 0 for k in kill)
+    survivors = sorted(set(keys) - set(kill))
+    total, live, dropped = c.chunk_info(0)
+    assert dropped and live == 0, (total, live, dropped)
+    extra_k, extra_v = b"k-after", b"v-after"
+    assert c.setitem(extra_k, extra_v) == ref.setitem(extra_k, extra_v) == 0
+    info = ref.last_info()
+    st = c.stats()
+    ch, idx = c.record_location(st.records - 1)
+    assert idx == info["idx"], (idx, info)
+    for i in range(0, idx + 1, 97):
+        assert c.encoded(ch, i) == ref.encoded(i), i
+    assert c.encoded(ch, idx) == ref.encoded(idx)
+    found = c.contains_batch(keys)
+    alive = set(survivors)
+    assert found.tolist() == [k in alive for k in keys]
+    sample = survivors[::211]
+    buf, off, f = c.getitem_batch(sample)
+    assert f.all()
+    for i, k in enumerate(sample):
+        assert buf[off[i]:off[i + 1]].tobytes() == ref.getitem(k) == po.make_doc(k, vals[keys.index(k)])
+    c.free_prop()
