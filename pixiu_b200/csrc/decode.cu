@@ -515,74 +515,122 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
 #pragma unroll
                         for (int q = 5; q < 9; q++) sw[q] = (uint32_t) q < nsw ? ld_poll_u32(wp0 + q) : 0u;
                     }
-                    unsigned long long nzm = 0;
+                    // fast path (the common case): nothing copied yet and no zero among the source bytes, i.e. the whole
+                    // piece is final -> straight word copy.  (w - 0x01010101) & ~w & 0x80808080 flags zero bytes; bytes
+                    // outside [sa, sa + n) are forced nonzero.
+                    bool fast = false;
+                    if (!per && dn == 0) {
+                        const uint32_t end = sa + n, L = (end - 1) >> 2, e8 = 8 * (end & 3);
+                        const uint32_t mlo = (1u << (8 * sa)) - 1, mhi = e8 ? 0xFFFFFFFFu << e8 : 0u;
+                        uint32_t z = 0;
 #pragma unroll
-                    for (int q = 0; q < 5; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
-                    if (nsw > 5) {
-#pragma unroll
-                        for (int q = 5; q < 9; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
+                        for (int q = 0; q < 9; q++) {
+                            uint32_t w = sw[q];
+                            if (q == 0) w |= mlo;
+                            if ((uint32_t) q == L) w |= mhi;
+                            if ((uint32_t) q > L) w = 0xFFFFFFFFu;
+                            z |= (w - 0x01010101u) & ~w & 0x80808080u;
+                        }
+                        fast = z == 0;
                     }
-                    const uint32_t nz = (uint32_t) (nzm >> sa) & need;  // source bytes seen nonzero: final
-                    uint32_t zf = 0;  // source bytes that are final zeros
-                    const uint32_t zc = need & ~nz & ~dn;
-                    if (zc) {
-                        const uint32_t wi = a >> 5, bs = a & 31;
-                        uint32_t bits = ld_relaxed_u32(V.fin + wi) >> bs;
-                        if (bs + n > 32) bits |= ld_relaxed_u32(V.fin + wi + 1) << (32 - bs);
-                        zf = zc & bits;
-                    }
-                    seen = nz | zf;
-                    avail = seen & ~dn;
-                    if (per) avail = avail == need ? need : 0u;  // short periods are copied in one go
                     uint32_t zout = 0;  // copied bytes whose value is zero (destination coordinates of the piece)
-                    if (avail && per) {
+                    if (fast) {
                         uint8_t *dst = dstu + us;
-                        const uint32_t ph = meta >> 22;
-                        for (uint32_t j = 0; j < np; j += 4) {  // four loads in flight
-                            uint8_t bv[4];
+                        const uint32_t hbe = min((4u - (us & 3)) & 3u, n);  // head bytes up to a destination word boundary
+                        const uint32_t x0 = __funnelshift_r(sw[0], sw[1], 8 * sa);
 #pragma unroll
-                            for (int i = 0; i < 4; i++) bv[i] = __ldcg(V.arena + a + (ph + j + i) % per);
+                        for (int i = 0; i < 3; i++)
+                            if ((uint32_t) i < hbe) dst[i] = (uint8_t) (x0 >> (8 * i));
+                        const uint32_t rem = n - hbe, m = rem >> 2, tb = rem & 3, so = sa + hbe;
+                        const uint32_t sh = 8 * (so & 3);
+                        if (so >> 2) {  // (0 or 1)
 #pragma unroll
-                            for (int i = 0; i < 4; i++)
-                                if (j + i < np) {
-                                    dst[j + i] = bv[i];
-                                    if (bv[i] == 0) zout |= 1u << (j + i);
-                                }
+                            for (int q = 0; q < 9; q++) sw[q] = sw[q + 1];
                         }
-                        dn = 0xFFFFFFFFu >> (32 - np);
-                        complete = true;
-                    } else if (avail) {
-                        // destination word t holds piece bytes [4t - da, 4t - da + 4); its source bytes straddle the
-                        // aligned source words t + c and t + c + 1 (c = -1 when the source sits further left in its word)
-                        const uint32_t da = us & 3;
-                        const int delta = (int) sa - (int) da;
-                        const uint32_t sh = 8u * (uint32_t) (delta & 3);
-                        if (delta < 0) {
-#pragma unroll
-                            for (int q = 9; q > 0; q--) sw[q] = sw[q - 1];
-                            sw[0] = 0;
-                        }
-                        uint32_t *dw = reinterpret_cast<uint32_t *>(dstu + us - da);
-                        const unsigned long long am = (unsigned long long) avail << da;  // bytes to store, word coordinates
-                        const uint32_t ndw = (da + n + 3) >> 2;
+                        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + hbe);
+                        uint32_t xt = 0;
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
-                            const uint32_t vm = (uint32_t) (am >> (4 * t)) & 0xFu;
-                            if ((uint32_t) t < ndw && vm) {
-                                const uint32_t x = __funnelshift_r(sw[t], sw[t + 1], sh);
-                                if (vm == 0xFu) {
-                                    dw[t] = x;
-                                } else {
+                            const uint32_t x = __funnelshift_r(sw[t], sw[t + 1], sh);
+                            if ((uint32_t) t < m) dw[t] = x;
+                            if ((uint32_t) t == m) xt = x;
+                        }
 #pragma unroll
-                                    for (int i = 0; i < 4; i++)
-                                        if ((vm >> i) & 1u) reinterpret_cast<uint8_t *>(dw + t)[i] = (uint8_t) (x >> (8 * i));
+                        for (int i = 0; i < 3; i++)
+                            if ((uint32_t) i < tb) reinterpret_cast<uint8_t *>(dw + m)[i] = (uint8_t) (xt >> (8 * i));
+                        avail = need;
+                        seen = need;
+                        dn = need;
+                        complete = true;
+                    } else {
+                        unsigned long long nzm = 0;
+#pragma unroll
+                        for (int q = 0; q < 5; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
+                        if (nsw > 5) {
+#pragma unroll
+                            for (int q = 5; q < 9; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
+                        }
+                        const uint32_t nz = (uint32_t) (nzm >> sa) & need;  // source bytes seen nonzero: final
+                        uint32_t zf = 0;  // source bytes that are final zeros
+                        const uint32_t zc = need & ~nz & ~dn;
+                        if (zc) {
+                            const uint32_t wi = a >> 5, bs = a & 31;
+                            uint32_t bits = ld_relaxed_u32(V.fin + wi) >> bs;
+                            if (bs + n > 32) bits |= ld_relaxed_u32(V.fin + wi + 1) << (32 - bs);
+                            zf = zc & bits;
+                        }
+                        seen = nz | zf;
+                        avail = seen & ~dn;
+                        if (per) avail = avail == need ? need : 0u;  // short periods are copied in one go
+                        if (avail && per) {
+                            uint8_t *dst = dstu + us;
+                            const uint32_t ph = meta >> 22;
+                            for (uint32_t j = 0; j < np; j += 4) {  // four loads in flight
+                                uint8_t bv[4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++) bv[i] = __ldcg(V.arena + a + (ph + j + i) % per);
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                    if (j + i < np) {
+                                        dst[j + i] = bv[i];
+                                        if (bv[i] == 0) zout |= 1u << (j + i);
+                                    }
+                            }
+                            dn = 0xFFFFFFFFu >> (32 - np);
+                            complete = true;
+                        } else if (avail) {
+                            // destination word t holds piece bytes [4t - da, 4t - da + 4); its source bytes straddle the
+                            // aligned source words t + c and t + c + 1 (c = -1 when the source sits further left in its word)
+                            const uint32_t da = us & 3;
+                            const int delta = (int) sa - (int) da;
+                            const uint32_t sh = 8u * (uint32_t) (delta & 3);
+                            if (delta < 0) {
+#pragma unroll
+                                for (int q = 9; q > 0; q--) sw[q] = sw[q - 1];
+                                sw[0] = 0;
+                            }
+                            uint32_t *dw = reinterpret_cast<uint32_t *>(dstu + us - da);
+                            const unsigned long long am = (unsigned long long) avail << da;  // bytes to store, word coordinates
+                            const uint32_t ndw = (da + n + 3) >> 2;
+#pragma unroll
+                            for (int t = 0; t < 9; t++) {
+                                const uint32_t vm = (uint32_t) (am >> (4 * t)) & 0xFu;
+                                if ((uint32_t) t < ndw && vm) {
+                                    const uint32_t x = __funnelshift_r(sw[t], sw[t + 1], sh);
+                                    if (vm == 0xFu) {
+                                        dw[t] = x;
+                                    } else {
+#pragma unroll
+                                        for (int i = 0; i < 4; i++)
+                                            if ((vm >> i) & 1u) reinterpret_cast<uint8_t *>(dw + t)[i] = (uint8_t) (x >> (8 * i));
+                                    }
                                 }
                             }
+                            zout = zf;
+                            dn |= avail;
+                            pdone[slot] = dn;
+                            complete = dn == need;
                         }
-                        zout = zf;
-                        dn |= avail;
-                        pdone[slot] = dn;
-                        complete = dn == need;
                     }
                     if (zout) {  // announce the zero-valued bytes just copied
                         const uint32_t B = B0 + us, bs = B & 31;
