@@ -52,8 +52,9 @@ class ClockSampler:
     at 4 Hz 14 %, one query kind at 4 Hz nothing measurable), so the rate is kept low and the two queries
     alternate."""
 
-    def __init__(self, index):
+    def __init__(self, index, first_delay=0.1, period=0.5):
         self.index = index
+        self.first_delay, self.period = first_delay, period
         self.sm, self.reasons, self.mx = [], set(), None
         self._stop = threading.Event()
         self.t = None
@@ -72,7 +73,7 @@ class ClockSampler:
 
             def loop():
                 k = 0
-                self._stop.wait(0.1)
+                self._stop.wait(self.first_delay)
                 while not self._stop.is_set():
                     try:
                         if k % 2 == 0:
@@ -85,7 +86,7 @@ class ClockSampler:
                     except Exception:
                         pass
                     k += 1
-                    self._stop.wait(0.5)
+                    self._stop.wait(self.period)
 
             self.t = threading.Thread(target=loop, daemon=True)
             self.t.start()
@@ -403,7 +404,7 @@ def run_getitem(args, rank, world, local_rank):
     for _ in range(args.warmup):
         off, found = step_dev()
     assert found.all()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, first_delay=0.002, period=0.01)  # a step is milliseconds of kernel time, not launch-bound
     sampler.start()
     l0 = c.stats().kernel_launches
     dev_ms, dev_wall = timed(step_dev, args.steps)
@@ -420,6 +421,12 @@ def run_getitem(args, rank, world, local_rank):
     pd = prof["decode"]
     peak, peak_kind = measured_peak()
     ach = pd["bytes"] / 1e9 / (pd["ms"] / 1e3)
+    # DRAM traffic of k_decode_tiles over its algorithmic bytes from the committed `ncu --set full` captures
+    # (profiles/r01_decode_tiles_c2_3000pages_ncu_raw.csv: 135.2 MB read + 77.9 MB written for 196.6 MB;
+    #  profiles/r01_decode_tiles_c3_1Mrecords_ncu_raw.csv: 724.9 MB + 1,008.4 MB for 1,056.3 MB - deep chains re-read
+    #  decoded sources that have left the L2), plus the arena memset (the decoded bytes written once more)
+    ncu_ratio = {"c2": (135.17 + 77.93) / 196.57, "c3": (724.9 + 1008.4) / 1056.3}[args.workload]
+    traffic = ncu_ratio * pd["bytes"] + float(st.doc_bytes)
     # bit-exact round trip of every record against the inputs (escape-free synthetic data)
     hb = out[: int(off[-1])].cpu().numpy()
     klen, vlen = np.diff(ko), np.diff(vo)
@@ -442,7 +449,7 @@ def run_getitem(args, rank, world, local_rank):
                         "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_decode_tiles(+k_resolve)", "achieved": ach, "peak": peak,
-                             "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                              "algorithmic_bytes_per_launch": pd["bytes"], "avg_launch_ms": pd["ms"],
                              "launches": pd["launches"], "lookup_ms": s.last_lookup_gpu_ms},
                 "roundtrip_all_records_ok": ok, "clocks": clocks, "cpu_baseline": None}
