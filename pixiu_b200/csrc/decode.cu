@@ -812,12 +812,70 @@ k_dec_work(uint32_t n_work, uint32_t n_ranges, const DecRange *__restrict__ R, c
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+// The arena of one decode pass is addressed with 32 bits.  A request whose touched chunks decode to more than
+// DEC_ARENA_LIMIT bytes is split by chunk (chunks are self-contained) into passes that each stay below it.
 void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off) {
+    if (recs.empty()) return;
+    const char *lim_env = getenv("PIXIU_DEC_ARENA_LIMIT");  // test knob
+    const uint64_t LIMIT = lim_env ? (uint64_t) atoll(lim_env) : (7ull << 29);  // 3.5 GiB
+    // arena bytes per touched chunk: records [first, max requested]
+    std::map<uint32_t, uint32_t> cmax;
+    uint32_t last_f = 0xFFFFFFFFu, *last_max = nullptr;
+    for (uint32_t g : recs) {
+        const uint32_t f = h_first[g];
+        if (f != last_f) {
+            auto it = cmax.find(f);
+            if (it == cmax.end()) it = cmax.emplace(f, g).first;
+            last_f = f;
+            last_max = &it->second;
+        }
+        if (g > *last_max) *last_max = g;
+    }
+    if (h_dec_prefix.empty()) h_dec_prefix.push_back(0);
+    while (h_dec_prefix.size() < n_records() + 1) h_dec_prefix.push_back(h_dec_prefix.back() + h_dec_len[h_dec_prefix.size() - 1]);
+    uint64_t total = 0;
+    for (auto &cm : cmax) total += h_dec_prefix[cm.second + 1] - h_dec_prefix[cm.first];
+    if (total <= LIMIT) {
+        decode_pass(recs, d_out, out_off, &cmax);
+        return;
+    }
+    std::map<uint32_t, uint32_t> group_of;  // chunk first record -> pass
+    uint32_t ng = 0;
+    uint64_t acc = 0;
+    for (auto &cm : cmax) {
+        const uint64_t b = h_dec_prefix[cm.second + 1] - h_dec_prefix[cm.first];
+        if (acc && acc + b > LIMIT) {
+            ng++;
+            acc = 0;
+        }
+        group_of[cm.first] = ng;
+        acc += b;
+    }
+    ng++;
+    std::vector<std::vector<uint32_t>> grecs(ng);
+    std::vector<std::vector<uint64_t>> goffs(ng);
+    for (size_t i = 0; i < recs.size(); i++) {
+        const uint32_t gi = group_of[h_first[recs[i]]];
+        grecs[gi].push_back(recs[i]);
+        goffs[gi].push_back(out_off[i]);
+    }
+    double ms_sum = 0;
+    for (uint32_t gi = 0; gi < ng; gi++) {
+        goffs[gi].push_back(0);  // (only the first recs.size() entries are read; keeps the "n + 1" shape)
+        decode_pass(grecs[gi], d_out, goffs[gi], nullptr);
+        ms_sum += last_get_ms;
+    }
+    last_get_ms = ms_sum;
+}
+
+void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off,
+                        const std::map<uint32_t, uint32_t> *known_max) {
     if (recs.empty()) return;
     const auto t_h0 = std::chrono::steady_clock::now();
     // per touched chunk: records [first, max requested] form the arena
-    std::map<uint32_t, uint32_t> chunk_max;  // chunk first record -> max requested record
-    {
+    std::map<uint32_t, uint32_t> own_max;  // chunk first record -> max requested record
+    if (!known_max) {
+        std::map<uint32_t, uint32_t> &chunk_max = own_max;
         uint32_t last_f = 0xFFFFFFFFu, *last_max = nullptr;
         for (uint32_t g : recs) {
             const uint32_t f = h_first[g];
@@ -830,6 +888,7 @@ void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, co
             if (g > *last_max) *last_max = g;
         }
     }
+    const std::map<uint32_t, uint32_t> &chunk_max = known_max ? *known_max : own_max;
     const size_t NR = n_records();
     // running sum of the decoded lengths (host and device copies grow with the store)
     if (h_dec_prefix.empty()) h_dec_prefix.push_back(0);

@@ -17,6 +17,7 @@
 //   index mirror:                   CritBit nodes as SoA (child0/child1 i32, diff_at u16, mask u8)
 #pragma once
 #include <algorithm>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -186,6 +187,8 @@ struct Store {
     size_t mirror_from = 0;  // first record whose host mirrors are not fetched yet
     // decode.cu
     void decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off);
+    void decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off,
+                     const std::map<uint32_t, uint32_t> *known_max);
     int64_t import_chunk(int64_t n, const uint8_t *enc, const int64_t *enc_off);
 };
 

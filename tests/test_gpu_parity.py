@@ -191,6 +191,56 @@ def test_edge_records(ctrl_mod):
     c.free_prop()
 
 
+def test_decode_request_split_into_passes(ctrl_mod, monkeypatch):
+    """a request whose touched chunks decode to more than the 32-bit arena of one pass is split by chunk; the knob
+    shrinks the limit so that a small store needs many passes (shuffled request, device and host outputs)"""
+    kd, ko, vd, vo = synth.gen_html_pages(60, seed=4, max_len=20000, mean_len=9000)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=60_000)
+    c.setitem_batch((kd, ko), (vd, vo))
+    assert c.stats().chunks >= 8
+    monkeypatch.setenv("PIXIU_DEC_ARENA_LIMIT", "150000")
+    order = [int(i) for i in np.random.default_rng(3).permutation(len(keys))]
+    for req in (list(range(len(keys))), order, order[:17]):
+        buf, off, found = c.getitem_batch([keys[i] for i in req])
+        assert found.all()
+        for j, i in enumerate(req):
+            assert buf[off[j]:off[j + 1]].tobytes() == po.make_doc(keys[i], vals[i]), (len(req), i)
+    c.free_prop()
+
+
+def test_decode_zero_bytes_travel_through_the_bitmap(ctrl_mod):
+    """the decoder recognises a final byte by being nonzero; zero-valued bytes are announced in a bitmap instead.
+    Values that are mostly zeros: long zero runs (period-1 self references whose source is a zero), zero runs copied
+    from record to record, and a swept single-byte mutation over zero-filled records (chains of zero bytes that can
+    only resolve through the bitmap)"""
+    rng = np.random.default_rng(21)
+    keys, vals = [], []
+    base = np.zeros(1500, dtype=np.uint8)
+    base[rng.integers(0, 1500, size=40)] = rng.integers(1, 250, size=40).astype(np.uint8)
+    cur = base.copy()
+    for r in range(900):
+        cur = cur.copy()
+        cur[(13 * r) % 1500] = 0 if r % 3 else int(rng.integers(1, 250))
+        keys.append(b"z%05d" % r)
+        vals.append(cur.tobytes())
+    keys += [b"allzero", b"zero-then-text", bytes([0, 0, 0]) + b"key-with-zeros"]
+    vals += [bytes(40000), bytes(3000) + b"tail" * 50 + bytes(3000), bytes(5000)]
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
+    assert not c.setitem_batch(keys, vals)[0].any()
+    assert c.stats().encoded_bytes < 0.2 * c.stats().doc_bytes
+    buf, off, found = c.getitem_batch(keys)
+    assert found.all()
+    for i, (k, v) in enumerate(zip(keys, vals)):
+        assert buf[off[i]:off[i + 1]].tobytes() == po.make_doc(k, v), i
+    # a partial request (the arena then holds records that were not asked for) in shuffled order
+    pick = [int(x) for x in rng.permutation(len(keys))[:200]]
+    buf, off, found = c.getitem_batch([keys[i] for i in pick])
+    for j, i in enumerate(pick):
+        assert buf[off[j]:off[j + 1]].tobytes() == po.make_doc(keys[i], vals[i]), i
+    c.free_prop()
+
+
 # --------------------------------------------------------------------------- decode
 @pytest.mark.parametrize("name", GOLDEN)
 def test_import_and_decode_chunk(ctrl_mod, name):
