@@ -433,7 +433,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
     uint32_t anyz = 0;
     for (uint32_t u0 = 0; u0 < nu; u0 += 128) {
         const uint32_t u = u0 + 4 * lane;
-        uint32_t zm = 0;
+        uint32_t m = 0, wv = 0, hz = 0;
         if (u < nu) {
             const uint32_t sw = S.startb[u >> 5], sh = u & 31;
             const uint32_t gi = S.wprefix[u >> 5] + __popc(sw & ((1u << sh) - 1));  // governing entry of the word's first byte
@@ -442,10 +442,11 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
             const uint32_t lo = max(u, ed & 0xFFFFu);
             const uint32_t hi = min(nibs ? u + __ffs(nibs) - 1 : u + 4, nu);
             if (lo < hi) {
-                const uint32_t m = ((1u << (hi - u)) - 1) & ~((1u << (lo - u)) - 1);
+                m = ((1u << (hi - u)) - 1) & ~((1u << (lo - u)) - 1);
+                const uint32_t bm = bytemask4(m);
                 const uint32_t q = min((u - mis + (ed >> 16)) & 0xFFFFu, STG_BYTES - 8);
-                const uint32_t wv = __funnelshift_r(S.stg[q >> 2], S.stg[(q >> 2) + 1], 8 * (q & 3)) & bytemask4(m);
-                zm = m & ~nibnz(wv);
+                wv = __funnelshift_r(S.stg[q >> 2], S.stg[(q >> 2) + 1], 8 * (q & 3)) & bm;
+                hz = (wv - 0x01010101u) & ~wv & 0x80808080u & bm;  // (superset of) the zero-valued literal bytes
                 if (u >= mis && u + 4 <= nu) {
                     *reinterpret_cast<uint32_t *>(dstu + u) = wv;
                 } else {
@@ -455,12 +456,14 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                 }
             }
         }
-        uint32_t v = zm << (4 * (lane & 7));
-        v |= __shfl_xor_sync(FULL, v, 1);
-        v |= __shfl_xor_sync(FULL, v, 2);
-        v |= __shfl_xor_sync(FULL, v, 4);
-        if ((lane & 7) == 0) S.finw[(u0 >> 5) + (lane >> 3)] = v;
-        anyz |= __ballot_sync(FULL, zm != 0);
+        if (__any_sync(FULL, hz != 0)) {  // rare: text has no zero bytes beyond the key terminator
+            uint32_t v = (m & ~nibnz(wv)) << (4 * (lane & 7));
+            v |= __shfl_xor_sync(FULL, v, 1);
+            v |= __shfl_xor_sync(FULL, v, 2);
+            v |= __shfl_xor_sync(FULL, v, 4);
+            if ((lane & 7) == 0) S.finw[(u0 >> 5) + (lane >> 3)] = v;
+            anyz = 1;
+        }
     }
     __syncwarp();
     if (anyz) flush_final(S.finw, lm, fsh, ngw, lane, pub0, pub1, pub2);
