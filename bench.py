@@ -459,6 +459,136 @@ def run_getitem(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_lookup(args, rank, world, local_rank):
+    """BASELINE config[3] (C4): batched contains over N URL keys with ~200-byte values (10 M keys = a ~2 GB compressed
+    corpus); the query batch is N keys, 90 % present / 10 % absent, in random order.  One step = one batch.
+      value : M keys/s, queries already packed in HBM (pixiu_contains_batch_dev), CUDA events on the store's stream
+      e2e   : pixiu_contains_batch with HOST buffers (query H2D and found[] D2H inside the timed region)
+      roofline : k_query_len/write + k_lookup, algorithmic bytes per query = q_len + depth x 7 + q_len"""
+    import torch
+
+    from pixiu_b200 import ctrl, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.keys
+    kd, ko, vd, vo = synth.gen_urls_kv(n, seed=4 + rank, val_words=20)
+    c = ctrl.PiXiuCtrl(device=local_rank, rotate_policy=ctrl.ROTATE_REFERENCE)
+    t0 = time.perf_counter()
+    rcs, _ = c.setitem_batch((kd, ko), (vd, vo))
+    set_s = time.perf_counter() - t0
+    st = c.stats()
+    # queries
+    rng = np.random.default_rng(40 + rank)
+    n_abs = n // 10
+    n_pre = n - n_abs
+    pick = rng.integers(0, n, size=n_pre)
+    ad, ao = synth.pack([b"http://absent.qq.com/a/%d.htm" % i for i in range(n_abs)])
+    klen = np.diff(ko)
+    all_d = np.concatenate([kd, ad])
+    starts = np.concatenate([ko[:-1][pick], ko[-1] + ao[:-1]])
+    lens = np.concatenate([klen[pick], np.diff(ao)])
+    perm = rng.permutation(n)
+    qd = synth.ragged_gather(all_d, starts[perm], lens[perm])
+    qo = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens[perm], out=qo[1:])
+    expect = perm < n_pre
+    d_qd, d_qo = torch.from_numpy(qd).to(dev), torch.from_numpy(qo).to(dev)
+    d_found = torch.zeros(n, dtype=torch.uint8, device=dev)
+    p_qd, p_qo = torch.from_numpy(qd).pin_memory(), torch.from_numpy(qo).pin_memory()
+    found_h = np.zeros(n, dtype=np.uint8)
+    ext = torch.cuda.ExternalStream(c.stream(), device=dev)
+
+    def step_dev():
+        c.contains_batch_dev(d_qd.data_ptr(), d_qo.data_ptr(), n, d_found.data_ptr())
+
+    def step_host():
+        c._check(c._L.pixiu_contains_batch(c._h, n, p_qd.data_ptr(), p_qo.data_ptr(), found_h.ctypes.data_as(ctrl._u8p)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    for _ in range(args.warmup):
+        step_dev()
+    if not np.array_equal(d_found.cpu().numpy().astype(bool), expect):
+        raise SystemExit("lookup bench: found[] differs from the expected presence of the queries")
+    sampler = ClockSampler(local_rank, first_delay=0.002, period=0.01)
+    sampler.start()
+    l0 = c.stats().kernel_launches
+    dev_ms, dev_wall = timed(step_dev, args.steps)
+    launches = c.stats().kernel_launches - l0
+    clocks = sampler.stop()
+    step_host()
+    if not np.array_equal(found_h.astype(bool), expect):
+        raise SystemExit("lookup bench: host-path found[] differs")
+    e2e_ms, e2e_wall = timed(step_host, args.steps)
+    c.profile_enable(True)
+    step_dev()
+    pl = c.profile()["lookup"]
+    c.profile_enable(False)
+    # mean depth of the walks on a sample (host index)
+    samp = np.arange(0, n, max(n // 20000, 1))
+    sd = synth.ragged_gather(qd, qo[:-1][samp], np.diff(qo)[samp])
+    so = np.zeros(len(samp) + 1, dtype=np.int64)
+    np.cumsum(np.diff(qo)[samp], out=so[1:])
+    depth = c.debug_index_depth((sd, so))
+    mean_depth = float(depth.mean())
+    alg = pl["bytes"] + n * mean_depth * 7.0
+    peak, peak_kind = measured_peak()
+    ach = alg / 1e9 / (pl["ms"] / 1e3)
+    if rank == 0:
+        line = {"metric": "contains_lookup_throughput", "value": n * world * args.steps / (dev_ms / 1e3) / 1e6, "unit": "Mkeys/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"C4: {n} URL keys x ~200 B values per GPU stored ({st.chunks} chunks, {st.encoded_bytes / 1e9:.2f} GB "
+                                       f"compressed), batched contains of {n} keys, 90 % present / 10 % absent, random order",
+                           "keys_per_gpu": n, "query_bytes": int(qd.nbytes), "mean_walk_depth": mean_depth,
+                           "max_walk_depth_in_sample": int(depth.max()), "stored_over_raw": st.encoded_bytes / max(st.raw_bytes, 1),
+                           "setitem_seconds_incl_index": set_s, "setitem_mb_s": st.raw_bytes / set_s / 1e6,
+                           "setitem_gpu_ms": st.last_setitem_gpu_ms,
+                           "setitem_note": "one cold call of the process (first allocations included); wall = GPU encode + CritBit insert",
+                           "l2": "index (nodes + key arena) and queries exceed the 126 MB L2 at 10 M keys; no explicit flush"},
+                "wall_ms_per_step": dev_wall / args.steps,
+                "e2e": {"value": n * world * args.steps / (e2e_ms / 1e3) / 1e6, "unit": "Mkeys/s",
+                        "h2d_bytes_per_step": int(qd.nbytes + qo.nbytes), "d2h_bytes_per_step": int(n),
+                        "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "k_query_len + scan + k_query_write + k_lookup", "achieved": ach, "peak": peak,
+                             "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg, "avg_launch_ms": pl["ms"], "launches": pl["launches"],
+                             "sector_granular_gbs": (pl["bytes"] + n * mean_depth * 32.0) / 1e9 / (pl["ms"] / 1e3),
+                             "bytes_model": "2 x escaped query bytes + depth x 7 B per query (SURVEY 8d); sector-granular: depth x 32 B"},
+                "found_matches_expected": True, "clocks": clocks, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    c.free_prop()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_sharded(args, rank, world, local_rank):
     """BASELINE config 5 style: ONE extended window sharded by record over the GPUs; every batch goes to
     all ranks, match lengths are MAX-reduced and leftmost candidates MIN-reduced by NCCL."""
@@ -536,11 +666,12 @@ def main():
     ap.add_argument("--ref-pages", type=int, default=150, help="bounded sample for the CPU reference leg")
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--mode", default="partition", choices=["partition", "shard", "getitem"],
+    ap.add_argument("--mode", default="partition", choices=["partition", "shard", "getitem", "lookup"],
                     help="partition: one store per GPU, corpus partitioned by key (default, weak scaling); "
                          "shard: one extended window sharded over the GPUs with NCCL reduces (config 5 style)")
     ap.add_argument("--batch-pages", type=int, default=256)
     ap.add_argument("--workload", default="c3", choices=["c2", "c3"], help="--mode getitem: which corpus to decode")
+    ap.add_argument("--keys", type=int, default=10_000_000, help="--mode lookup: keys stored and queried per GPU")
     ap.add_argument("--records", type=int, default=1_000_000, help="--mode getitem --workload c3: records per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -552,6 +683,8 @@ def main():
         run_sharded(args, rank, world, local_rank)
     elif args.mode == "getitem":
         run_getitem(args, rank, world, local_rank)
+    elif args.mode == "lookup":
+        run_lookup(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -90,6 +90,8 @@ int pixiu_setitem_batch_dev(pixiu_store *s, int64_t n, const uint8_t *d_keys, co
                             const uint8_t *d_vals, const int64_t *d_val_off, int32_t *rc, int32_t *saved);
 
 int pixiu_contains_batch(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off, uint8_t *found);
+/* same with DEVICE pointers: keys/key_off (key_off[0] == 0) already in HBM, found[] written on the device */
+int pixiu_contains_batch_dev(pixiu_store *s, int64_t n, const uint8_t *d_keys, const int64_t *d_key_off, uint8_t *d_found);
 int pixiu_delitem_batch(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off, int32_t *rc);
 
 /* Decoded records `esc(k) 251 0 [esc(v) 251 2]` (what draining PXSGen yields, README.md:157)

@@ -14,6 +14,8 @@ int64_t pixiu_debug_window_array(pixiu_store *s, const char *name, void *out, in
 int pixiu_debug_memcpy(void *dst, const void *src, int64_t bytes, int kind);
 /* MemPool::nth / used_num the reference would show for the open window (PIXIU_ROTATE_REFERENCE only) */
 int pixiu_debug_pool_state(pixiu_store *s, int32_t *nth, int32_t *used);
+/* inner nodes visited by each key's CritBit walk (host index; feeds the algorithmic-bytes figure of the lookup bench) */
+int pixiu_debug_index_depth(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off, int32_t *depth);
 #ifdef __cplusplus
 }
 #endif

@@ -369,6 +369,22 @@ int pixiu_contains_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const i
     });
 }
 
+int pixiu_contains_batch_dev(pixiu_store *h, int64_t n, const uint8_t *d_keys, const int64_t *d_key_off, uint8_t *d_found) {
+    return guarded(h, [&](Store &S) -> int {
+        if (n < 0 || n > 0x7fffffff || (n && (!d_keys || !d_key_off || !d_found))) return PIXIU_EINVAL;
+        pixiu::contains_batch_dev(S, n, d_keys, d_key_off, d_found);
+        return PIXIU_OK;
+    });
+}
+
+int pixiu_debug_index_depth(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, int32_t *depth) {
+    return guarded(h, [&](Store &S) -> int {
+        if (n < 0 || (n && (!keys || !offsets_ok(n, key_off) || !depth))) return PIXIU_EINVAL;
+        pixiu::index_depths(S, n, keys, key_off, depth);
+        return PIXIU_OK;
+    });
+}
+
 int pixiu_delitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, int32_t *rc) {
     return guarded(h, [&](Store &S) -> int {
         if (n < 0 || (n && (!keys || !offsets_ok(n, key_off)))) return PIXIU_EINVAL;

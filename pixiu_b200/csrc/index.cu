@@ -74,6 +74,16 @@ int64_t HostIndex::get(const uint8_t *q, uint32_t qlen) const {
     return -1;
 }
 
+int32_t HostIndex::depth(const uint8_t *q, uint32_t qlen) const {
+    if (!has_root) return 0;
+    int32_t p = root, d = 0;
+    while (p >= 0) {
+        p = child[dir_of(p, q, qlen)][p];
+        d++;
+    }
+    return d;
+}
+
 int64_t HostIndex::set(const uint8_t *q, uint32_t qlen, uint32_t rec) { return set_below(-1, 0, q, qlen, rec); }
 
 // CritBitTree::setitem restricted to the subtree hanging on the edge (top, tdir) (top < 0: the whole tree).  The
@@ -483,18 +493,10 @@ void HostIndex::insert_batch(Store &S, uint32_t n, const uint8_t *d_keys, const 
                 (unsigned long long) n_rounds, t_probe, t_sync, t_apply, (unsigned long long) n_fallback);
 }
 
-void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, std::vector<uint32_t> &rec_out) {
-    rec_out.assign((size_t) n, 0xFFFFFFFFu);
-    if (n == 0) return;
+// the walk itself: d_keys/d_koff are the packed raw keys on the device (koff[0] == 0); the record id of every key
+// (0xFFFFFFFF = absent) is left in S.doc_off on the device
+void lookup_core(Store &S, uint32_t nn, const uint8_t *d_keys, const int64_t *d_koff) {
     cudaStream_t st = S.st;
-    const uint32_t nn = (uint32_t) n;
-    const int64_t kbytes = h_koff[n] - h_koff[0];
-    S.in_keys.reserve_discard((size_t) kbytes + 16);
-    S.in_koff.reserve_discard(nn + 1);
-    std::vector<int64_t> rel(nn + 1);
-    for (uint32_t i = 0; i <= nn; i++) rel[i] = h_koff[i] - h_koff[0];
-    PX_CUDA(cudaMemcpyAsync(S.in_keys.p, h_keys + h_koff[0], (size_t) kbytes, cudaMemcpyHostToDevice, st));
-    PX_CUDA(cudaMemcpyAsync(S.in_koff.p, rel.data(), (nn + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     HostIndex::DeviceView T = S.index->device_view(st);
     PX_CUDA(cudaEventRecord(S.ev0, st));
     S.prof.begin(PC_LOOKUP, st);
@@ -502,7 +504,7 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     DevBuf<uint64_t> &qoff = S.es.qoff;
     qoff.reserve_discard((size_t) nn + 2);
     uint64_t *d_qoff = qoff.p;
-    k_query_len<<<div_up<uint32_t>(nn, 256), 256, 0, st>>>(nn, S.in_keys.p, S.in_koff.p, S.doc_len.p);
+    k_query_len<<<div_up<uint32_t>(nn, 256), 256, 0, st>>>(nn, d_keys, d_koff, S.doc_len.p);
     {
         const uint32_t *ql = S.doc_len.p;
         device_scan<uint64_t>(
@@ -513,19 +515,68 @@ void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_k
     PX_CUDA(cudaMemcpyAsync(&qbytes, d_qoff + nn, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
     S.in_vals.reserve_discard(qbytes + 16);
-    k_query_write<<<div_up<uint32_t>(nn, 256), 256, 0, st>>>(nn, S.in_keys.p, S.in_koff.p, d_qoff, S.in_vals.p);
+    k_query_write<<<div_up<uint32_t>(nn, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_qoff, S.in_vals.p);
     S.doc_off.reserve_discard(nn + 1);
     k_lookup<<<div_up<uint32_t>(nn, 128), 128, 0, st>>>(nn, T, S.in_vals.p, d_qoff, S.doc_len.p, S.doc_off.p);
     PX_LAUNCH_CHECK();
-    S.prof.end(st, 0.0, 4);
+    S.last_lookup_qbytes = qbytes;
+    S.prof.end(st, 2.0 * (double) qbytes, 4);  // escaped query read for the walk and for the verification (+ depth x 7 B: bench.py)
     S.launches += 4;
     PX_CUDA(cudaEventRecord(S.ev1, st));
-    PX_CUDA(cudaMemcpyAsync(rec_out.data(), S.doc_off.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaStreamSynchronize(st));
+}
+
+static void lookup_finish(Store &S) {
+    PX_CUDA(cudaStreamSynchronize(S.st));
     float ms = 0;
     PX_CUDA(cudaEventElapsedTime(&ms, S.ev0, S.ev1));
     S.last_lookup_ms = ms;
     S.prof.collect();
+}
+
+void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, std::vector<uint32_t> &rec_out) {
+    rec_out.assign((size_t) n, 0xFFFFFFFFu);
+    if (n == 0) return;
+    cudaStream_t st = S.st;
+    const uint32_t nn = (uint32_t) n;
+    const int64_t kbytes = h_koff[n] - h_koff[0];
+    S.in_keys.reserve_discard((size_t) kbytes + 16);
+    S.in_koff.reserve_discard(nn + 1);
+    PX_CUDA(cudaMemcpyAsync(S.in_keys.p, h_keys + h_koff[0], (size_t) kbytes, cudaMemcpyHostToDevice, st));
+    if (h_koff[0] == 0) {
+        PX_CUDA(cudaMemcpyAsync(S.in_koff.p, h_koff, (nn + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    } else {
+        std::vector<int64_t> rel(nn + 1);
+        for (uint32_t i = 0; i <= nn; i++) rel[i] = h_koff[i] - h_koff[0];
+        PX_CUDA(cudaMemcpyAsync(S.in_koff.p, rel.data(), (nn + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        PX_CUDA(cudaStreamSynchronize(st));
+    }
+    lookup_core(S, nn, S.in_keys.p, S.in_koff.p);
+    PX_CUDA(cudaMemcpyAsync(rec_out.data(), S.doc_off.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    lookup_finish(S);
+}
+
+__global__ void __launch_bounds__(256) k_found(uint32_t n, const uint32_t *__restrict__ rec, uint8_t *__restrict__ found) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) found[i] = rec[i] != 0xFFFFFFFFu;
+}
+
+// contains for keys already resident in HBM: found[] is written on the device
+void contains_batch_dev(Store &S, int64_t n, const uint8_t *d_keys, const int64_t *d_koff, uint8_t *d_found) {
+    if (n == 0) return;
+    const uint32_t nn = (uint32_t) n;
+    lookup_core(S, nn, d_keys, d_koff);
+    k_found<<<div_up<uint32_t>(nn, 256), 256, 0, S.st>>>(nn, S.doc_off.p, d_found);
+    S.launches++;
+    lookup_finish(S);
+}
+
+// depth of the leaf each (raw) key's walk ends in: inner nodes visited (measurement only)
+void index_depths(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, int32_t *out) {
+    std::vector<uint8_t> q;
+    for (int64_t i = 0; i < n; i++) {
+        escape_key(h_keys + h_koff[i], (size_t) (h_koff[i + 1] - h_koff[i]), q);
+        out[i] = S.index->depth(q.data(), (uint32_t) q.size());
+    }
 }
 
 }  // namespace pixiu

@@ -27,6 +27,7 @@ class HostIndex {
     // returns the record id that was replaced, or -1 when the key is new (CritBitTree.cpp:13-105)
     int64_t set(const uint8_t *q, uint32_t qlen, uint32_t rec);
     int64_t get(const uint8_t *q, uint32_t qlen) const;  // record id or -1
+    int32_t depth(const uint8_t *q, uint32_t qlen) const;  // inner nodes on the key's walk
     int64_t del(const uint8_t *q, uint32_t qlen);        // record id or -1 (CritBitTree.cpp:107-152)
     // record ids of all keys starting with the escaped prefix, ascending key order (CritBitTree.h:55-157)
     void iter(const uint8_t *prefix, uint32_t plen, std::vector<uint32_t> &out) const;
@@ -111,5 +112,7 @@ struct Store;
 // GPU batched lookup: escapes the n packed keys on the device, walks the SoA tree and verifies the
 // candidates against the compressed store.  rec_out[i] = record id or 0xFFFFFFFF.
 void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, std::vector<uint32_t> &rec_out);
+void contains_batch_dev(Store &S, int64_t n, const uint8_t *d_keys, const int64_t *d_koff, uint8_t *d_found);
+void index_depths(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, int32_t *out);
 
 }  // namespace pixiu

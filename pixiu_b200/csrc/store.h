@@ -71,6 +71,7 @@ struct Store {
     int64_t launches = 0;
     Profiler prof;
     double last_set_ms = 0, last_get_ms = 0, last_lookup_ms = 0;
+    uint64_t last_lookup_qbytes = 0;  // escaped query bytes of the last lookup
 
     // ---- record tables (host mirrors) ----
     std::vector<uint64_t> h_enc_off;

@@ -45,7 +45,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "pixiu_default_config", "pixiu_create", "pixiu_destroy", "pixiu_last_error", "pixiu_get_stats",
-    "pixiu_setitem_batch", "pixiu_setitem_batch_dev", "pixiu_contains_batch", "pixiu_delitem_batch",
+    "pixiu_setitem_batch", "pixiu_setitem_batch_dev", "pixiu_contains_batch", "pixiu_contains_batch_dev", "pixiu_delitem_batch",
     "pixiu_getitem_batch", "pixiu_getitem_batch_dev", "pixiu_iter", "pixiu_encoded_view",
     "pixiu_record_location", "pixiu_import_chunk", "pixiu_decode_chunk", "pixiu_rotate",
     "pixiu_profile_enable", "pixiu_profile_get", "pixiu_stream",
@@ -75,6 +75,8 @@ def load_library():
     L.pixiu_setitem_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32p, _i32p]
     L.pixiu_setitem_batch_dev.argtypes = L.pixiu_setitem_batch.argtypes
     L.pixiu_contains_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, _u8p]
+    L.pixiu_contains_batch_dev.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pixiu_debug_index_depth.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, _i32p]
     L.pixiu_delitem_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, _i32p]
     L.pixiu_getitem_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p, _u8p, _i64p]
     L.pixiu_getitem_batch_dev.argtypes = L.pixiu_getitem_batch.argtypes
@@ -262,6 +264,17 @@ class PiXiuCtrl:
         found = np.zeros(max(n, 1), dtype=np.uint8)
         self._check(self._L.pixiu_contains_batch(self._h, n, _ptr(kd), _ptr(ko), found.ctypes.data_as(_u8p)))
         return found[:n].astype(bool)
+
+    def contains_batch_dev(self, d_keys: int, d_koff: int, n: int, d_found: int):
+        """device pointers (ints): packed keys + int64 offsets in HBM, found u8[n] written on the device"""
+        self._check(self._L.pixiu_contains_batch_dev(self._h, n, d_keys, d_koff, d_found))
+
+    def debug_index_depth(self, keys):
+        kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
+        n = len(ko) - 1
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        self._check(self._L.pixiu_debug_index_depth(self._h, n, _ptr(kd), _ptr(ko), out.ctypes.data_as(_i32p)))
+        return out[:n]
 
     def delitem_batch(self, keys):
         kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
