@@ -41,6 +41,8 @@ class HostIndex {
         const uint32_t *leaf_rec, *leaf_klen;
         const uint64_t *leaf_koff;
         const uint8_t *keys;  // escaped keys of the leaves
+        const uint4 *leaves;  // packed leaves {key offset lo, hi, key length, record id}
+        const int4 *nodes;    // packed inner nodes {child0, child1, diff_at | mask << 16, 0}: what the lookup walks read
         int32_t root;
         int32_t has_root;
     };
@@ -96,6 +98,8 @@ class HostIndex {
     DevBuf<uint32_t> d_leaf_rec, d_leaf_klen;
     DevBuf<uint64_t> d_leaf_koff;
     DevBuf<uint8_t> d_keys;
+    DevBuf<int4> d_nodes;
+    DevBuf<uint4> d_leaves;
     size_t keys_uploaded = 0;
 
     int32_t new_leaf(const uint8_t *q, uint32_t qlen, uint32_t rec);
