@@ -696,3 +696,31 @@ def test_auto_reinsert_matches_live_reference(ctrl_mod, ref):
     for i, k in enumerate(sample):
         assert buf[off[i]:off[i + 1]].tobytes() == ref.getitem(k) == po.make_doc(k, vals[keys.index(k)])
     c.free_prop()
+
+
+def test_contains_with_device_resident_queries(ctrl_mod):
+    """pixiu_contains_batch_dev (queries and found[] in HBM) answers like the host-buffer entry point, including
+    absent keys, keys with escapes, tombstoned keys and an empty store"""
+    import torch
+
+    def ask(c, keys):
+        kd, ko = synth.pack(keys)
+        d_k = torch.from_numpy(np.concatenate([kd, np.zeros(8, dtype=np.uint8)])).cuda()
+        d_o = torch.from_numpy(ko).cuda()
+        d_f = torch.full((len(keys),), 7, dtype=torch.uint8, device="cuda")
+        c.contains_batch_dev(d_k.data_ptr(), d_o.data_ptr(), len(keys), d_f.data_ptr())
+        return d_f.cpu().numpy().astype(bool)
+
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=200_000)
+    probe = [b"a", bytes([251, 0, 251]), b"http://x/%d" % 5]
+    assert not ask(c, probe).any()                                  # empty store
+    keys = [b"http://x/%d" % i for i in range(5000)] + [bytes([251, i % 256, 251, 251, 0]) + b"k%d" % i for i in range(300)]
+    vals = [b"v%d" % i * (1 + i % 7) for i in range(len(keys))]
+    c.setitem_batch(keys, vals)
+    c.delitem_batch(keys[::5])
+    q = keys[::3] + [b"http://x/%d" % i for i in range(5000, 5400)] + [bytes([251, 7, 251, 251, 0]) + b"k7x"]
+    got = ask(c, q)
+    want = c.contains_batch(q)
+    alive = set(keys) - set(keys[::5])
+    assert got.tolist() == want.tolist() == [k in alive for k in q]
+    c.free_prop()
