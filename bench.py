@@ -215,12 +215,15 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(args.warmup):
         step_dev()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # NVML queries take a driver-wide lock: with one sampler per rank the ranks of a launch-bound step slow each other
+    # down, so only rank 0 (whose line is printed) samples its GPU
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     st0 = c.stats()
     dev_ms, dev_wall_ms = timed(step_dev, args.steps)
     st1 = c.stats()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     launches_per_step = (st1.kernel_launches - st0.kernel_launches) // max(args.steps, 1)
     ratio = (st1.encoded_bytes - st0.encoded_bytes) / max(st1.raw_bytes - st0.raw_bytes, 1)
     chunks_per_step = (st1.chunks - st0.chunks) / max(args.steps, 1)
@@ -404,12 +407,14 @@ def run_getitem(args, rank, world, local_rank):
     for _ in range(args.warmup):
         off, found = step_dev()
     assert found.all()
-    sampler = ClockSampler(local_rank, first_delay=0.002, period=0.01)  # a step is milliseconds of kernel time, not launch-bound
-    sampler.start()
+    # (a step is milliseconds of kernel time, not launch-bound: fast sampling; rank 0 only, NVML takes a driver-wide lock)
+    sampler = ClockSampler(local_rank, first_delay=0.002, period=0.01) if rank == 0 else None
+    if sampler:
+        sampler.start()
     l0 = c.stats().kernel_launches
     dev_ms, dev_wall = timed(step_dev, args.steps)
     launches = c.stats().kernel_launches - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     step_host()
     e2e_ms, e2e_wall = timed(step_host, args.steps)
     # decode kernels alone
@@ -536,12 +541,13 @@ def run_lookup(args, rank, world, local_rank):
         step_dev()
     if not np.array_equal(d_found.cpu().numpy().astype(bool), expect):
         raise SystemExit("lookup bench: found[] differs from the expected presence of the queries")
-    sampler = ClockSampler(local_rank, first_delay=0.002, period=0.01)
-    sampler.start()
+    sampler = ClockSampler(local_rank, first_delay=0.002, period=0.01) if rank == 0 else None
+    if sampler:
+        sampler.start()
     l0 = c.stats().kernel_launches
     dev_ms, dev_wall = timed(step_dev, args.steps)
     launches = c.stats().kernel_launches - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     step_host()
     if not np.array_equal(found_h.astype(bool), expect):
         raise SystemExit("lookup bench: host-path found[] differs")
