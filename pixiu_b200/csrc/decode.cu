@@ -819,6 +819,7 @@ k_dec_work(uint32_t n_work, uint32_t n_ranges, const DecRange *__restrict__ R, c
 // DEC_ARENA_LIMIT bytes is split by chunk (chunks are self-contained) into passes that each stay below it.
 void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off) {
     if (recs.empty()) return;
+    if (mirror_from < n_records()) flush_mirrors();  // the running sum below is built from the host mirrors
     const char *lim_env = getenv("PIXIU_DEC_ARENA_LIMIT");  // test knob
     const uint64_t LIMIT = lim_env ? (uint64_t) atoll(lim_env) : (7ull << 29);  // 3.5 GiB
     // arena bytes per touched chunk: records [first, max requested]
