@@ -502,7 +502,11 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                 // slots: the full examination of every piece in every sweep made a hop ~12 us.
                 bool look = (sweep & 3u) == 3u;
                 if (!look) {
-                    const uint32_t pj = a + __ffs(need & ~dn) - 1;
+                    // (first open byte on even sweeps, last one on odd sweeps: looking at the first byte only makes a
+                    // byte wait for everything left of it in its piece, and with a source window that slides from
+                    // record to record that running maximum chains every record to its predecessor)
+                    const uint32_t open = need & ~dn;
+                    const uint32_t pj = a + ((sweep & 1u) ? 31u - (uint32_t) __clz(open) : (uint32_t) __ffs(open) - 1u);
                     const uint32_t w0 = ld_poll_u32(reinterpret_cast<const uint32_t *>(V.arena + (pj & ~3u)));
                     look = ((w0 >> (8 * (pj & 3))) & 0xFFu) != 0;
                 }
