@@ -183,6 +183,11 @@ struct PinnedBuf {
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 
 // acquire-release fence at device scope (cheaper than the sequentially consistent __threadfence)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+    return v;
+}
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     uint32_t v;

@@ -129,7 +129,7 @@ __device__ __forceinline__ void flush_final(const uint32_t *finw, uint32_t *lm, 
 __global__ void __launch_bounds__(DEC_WARPS * 32, 8)
 k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
                uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t giveup_spins, uint32_t piece_cap,
-               uint32_t sleep_after, uint32_t sleep_ns) {
+               uint32_t sleep_after, uint32_t sleep_ns, unsigned long long *__restrict__ trace) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -140,6 +140,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
     if (lane == 0) w = atomicAdd(ctr + 1, 1u);
     w = __shfl_sync(FULL, w, 0);
     if (w >= n_work) return;
+    if (trace && lane == 0) trace[4 * (size_t) w] = globaltimer_ns();
     const uint32_t gt = work_tile[w], g = work_rec[w];
     const uint32_t t = gt - V.tile_base[g];
     const uint32_t dl = V.dec_len[g], el = V.enc_len[g];
@@ -467,6 +468,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
     }
     __syncwarp();
     if (anyz) flush_final(S.finw, lm, fsh, ngw, lane, pub0, pub1, pub2);
+    if (trace && lane == 0) trace[4 * (size_t) w + 1] = globaltimer_ns();
     // ---- 5. copy pieces, one per lane and row.  Finality travels IN BAND: the arena starts zeroed and a byte is only
     //         ever stored with its final value, so a nonzero byte is final the moment it is visible; a final byte
     //         whose value is zero is announced by its bit in V.fin (the bit IS the value, the byte itself needs no
@@ -693,6 +695,10 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
         } else {
             spins = 0;
         }
+    }
+    if (trace && lane == 0) {  // measurement aid (PIXIU_DEC_TRACE_FILE): entry, end of the literal phase, done, sweeps
+        trace[4 * (size_t) w + 2] = globaltimer_ns();
+        trace[4 * (size_t) w + 3] = sweep;
     }
 }
 
@@ -965,16 +971,36 @@ void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const
     if (getenv("PIXIU_TRACE"))
         fprintf(stderr, "[decode] host work list %.3f ms\n",
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count());
+    unsigned long long *d_trace = nullptr;
+    const char *trace_file = getenv("PIXIU_DEC_TRACE_FILE");  // measurement aid: per-tile entry / parsed / done times + sweeps
+    if (trace_file) {
+        PX_CUDA(cudaMalloc(&d_trace, 4 * n_work * sizeof(unsigned long long)));
+        PX_CUDA(cudaMemsetAsync(d_trace, 0, 4 * n_work * sizeof(unsigned long long), st));
+    }
     PX_CUDA(cudaEventRecord(ev0, st));
     prof.begin(PC_DECODE, st);
     PX_CUDA(cudaMemsetAsync(arena, 0, arena_bytes, st));  // zero = "not final yet" (k_decode_tiles, phase 5): timed with the kernel
     k_decode_tiles<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(
-        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins, piece_cap, sleep_after, sleep_ns);
+        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins, piece_cap, sleep_after, sleep_ns, d_trace);
     int nl = 1;
     uint32_t h_ctr[4] = {0, 0, 0, 0};
     PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
     last_handed_over = h_ctr[2];
+    if (d_trace) {  // file: u64 n_work, u32 record[n_work] (ticket order), u64 {entry, parsed, done (ns), sweeps}[n_work]
+        std::vector<unsigned long long> ht(4 * n_work);
+        std::vector<uint32_t> hr(n_work);
+        PX_CUDA(cudaMemcpy(ht.data(), d_trace, ht.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        PX_CUDA(cudaMemcpy(hr.data(), dec_work.p + n_work, n_work * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(trace_file, "wb")) {
+            const unsigned long long nw = n_work;
+            fwrite(&nw, 8, 1, f);
+            fwrite(hr.data(), 4, n_work, f);
+            fwrite(ht.data(), 8, ht.size(), f);
+            fclose(f);
+        }
+        cudaFree(d_trace);
+    }
     if (getenv("PIXIU_TRACE")) fprintf(stderr, "[decode] %llu tiles, %u pieces handed to k_resolve\n", (unsigned long long) n_work, h_ctr[2]);
     if (h_ctr[0] == 0 && h_ctr[2] != 0) {
         // deep reference chains: the pieces the data-flow pass handed over are resolved by pointer chasing
