@@ -164,6 +164,8 @@ struct Store {
     void enc_phase_b();
     uint32_t enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const uint16_t *gidx);
     uint32_t ep_first_new = 0, ep_s0 = 0, ep_N = 0, ep_n_new = 0;  // state shared by the phases
+    bool ep_emitted = false;  // k_emit already ran for the candidates (enc_emit_all)
+    void enc_emit_all();
     void finish_index(uint32_t nn, size_t g_batch_first, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *h_keys,
                       const int64_t *h_koff, const int64_t *h_voff,
                       const uint32_t *h_doc_len, int32_t *rc, int32_t *saved);
