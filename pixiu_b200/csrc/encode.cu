@@ -310,6 +310,76 @@ k_lcp(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const
     }
 }
 
+// K5a/K5b: the same LCP array in two passes that keep the random accesses inside the L2.
+// Kasai's walk (k_lcp above) visits the text in order and, per position, touches sa[rank-1], dist[p], text[p+h] and
+// lcp[r] at random in ~200 MB of arrays: six 32-byte DRAM sectors per position (ncu: 2.6 GB read for 214 MB of
+// algorithmic bytes).  Here pass a walks the SUFFIX ARRAY in order - sa and lcp stream, only text and dist (40 MB,
+// L2-resident) are touched at random - and compares neighbours from scratch, but only up to LCP_CAP bytes; the few
+// positions whose match is longer are marked in a bitmap and pass b finishes them in text order with Kasai's carry
+// (matches of consecutive text positions shrink by at most one), so long repeats still cost O(length), not O(length^2).
+constexpr uint32_t LCP_CAP = 64;
+
+__global__ void __launch_bounds__(256)
+k_lcp_sa(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const uint32_t *__restrict__ sa, uint32_t n,
+         uint32_t *__restrict__ lcp, uint32_t *__restrict__ longmap) {
+    const uint32_t r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= n) return;
+    uint32_t h = 0;
+    if (r > 0) {
+        const uint32_t a = __ldcs(sa + r), b = __ldcs(sa + r - 1);
+        const uint32_t lim = min((uint32_t) dist[a], (uint32_t) dist[b]);
+        const uint32_t stop = min(lim, LCP_CAP);
+        bool diff = false;
+        while (h < stop) {
+            const uint64_t x = load8_unaligned(text + a + h) ^ load8_unaligned(text + b + h);
+            if (x) {
+                h += (uint32_t) (__ffsll((long long) x) - 1) >> 3;
+                diff = true;
+                break;
+            }
+            h += 8;
+        }
+        if (h > lim) h = lim;
+        if (!diff && h >= LCP_CAP && lim > LCP_CAP) {  // the match may go on: finished by k_lcp_long
+            h = LCP_CAP;
+            atomicOr(longmap + (a >> 5), 1u << (a & 31));
+        }
+    }
+    __stcs(lcp + r, h);
+}
+
+__global__ void __launch_bounds__(128)
+k_lcp_long(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const uint32_t *__restrict__ sa,
+           const uint32_t *__restrict__ rank, const uint32_t *__restrict__ longmap, uint32_t n, uint32_t *__restrict__ lcp) {
+    // one thread per 32 text positions (one word of the bitmap); words without a long match cost one load
+    const uint32_t w = blockIdx.x * 128 + threadIdx.x;
+    if ((uint64_t) w * 32 >= n) return;
+    uint32_t bits = longmap[w];
+    uint32_t h = 0, prev = 0xFFFFFFFFu;
+    while (bits) {
+        const uint32_t k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const uint32_t i = w * 32 + k;
+        const uint32_t r = rank[i];
+        const uint32_t p = sa[r - 1];  // (r > 0: position i was marked by a comparison with its predecessor)
+        const uint32_t lim = min((uint32_t) dist[i], (uint32_t) dist[p]);
+        // Kasai: the match of position i is at least the match of i - 1 minus one (when i - 1 was long as well)
+        h = (prev + 1 == i && h > LCP_CAP) ? h - 1 : LCP_CAP;
+        if (h > lim) h = lim;
+        while (h < lim) {
+            const uint64_t x = load8_unaligned(text + i + h) ^ load8_unaligned(text + p + h);
+            if (x) {
+                h += (uint32_t) (__ffsll((long long) x) - 1) >> 3;
+                break;
+            }
+            h += 8;
+        }
+        if (h > lim) h = lim;
+        lcp[r] = h;
+        prev = i;
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // block-min trees over sa and lcp
 // ---------------------------------------------------------------------------------
@@ -1057,9 +1127,18 @@ void Store::enc_phase_a(uint32_t first_new) {
     // ---- LCP + trees ----
     E.lcp.reserve_discard(N);
     prof.begin(PC_LCP, st);
-    k_lcp<<<div_up<uint32_t>(div_up<uint32_t>(N, LCP_SEG), 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, N, E.lcp.p);
-    prof.end(st, 16.0 * N, 1);
-    L++;
+    if (getenv("PIXIU_LCP_KASAI")) {  // (knob: the one-pass Kasai walk, for A/B measurements)
+        k_lcp<<<div_up<uint32_t>(div_up<uint32_t>(N, LCP_SEG), 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, N, E.lcp.p);
+        L++;
+    } else {
+        const uint32_t words = div_up<uint32_t>(N, 32);
+        E.longmap.reserve_discard(words + 1);
+        PX_CUDA(cudaMemsetAsync(E.longmap.p, 0, (size_t) words * sizeof(uint32_t), st));
+        k_lcp_sa<<<div_up<uint32_t>(N, 256), 256, 0, st>>>(w_text.p, w_dist.p, E.sa.p, N, E.lcp.p, E.longmap.p);
+        k_lcp_long<<<div_up<uint32_t>(words, 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, E.longmap.p, N, E.lcp.p);
+        L += 2;
+    }
+    prof.end(st, 16.0 * N, 2);
     MinTree T{};
     {
         size_t total = 0;

@@ -53,7 +53,7 @@ struct EncodeScratch {
     ScanWorkspace scanws;
     DevBuf<uint32_t> tree_a, tree_l;
     DevBuf<uint8_t> flagp, flagc, symmap;
-    DevBuf<uint32_t> leafmask, splitmask, wordpre;
+    DevBuf<uint32_t> leafmask, splitmask, wordpre, longmap;
     PinnedBuf<uint32_t> h_leafmask, h_splitmask, h_wordpre;
     DevBuf<uint32_t> counters;  // [0] active count, [1] group count, [2] error flag, [3..] misc
     RadixSortTemp rs;
