@@ -1085,6 +1085,39 @@ uint32_t Store::count_nodes_and_cut(uint32_t first_new, uint32_t s0, uint32_t N)
             // first word whose end exceeds the room left: everything before it fits as a whole
             uint64_t limit = Pk + (C - used);
             uint32_t lo = k >> 5, hi = (kb - 1) >> 5;  // find the smallest w in [lo, hi] with blocks up to end of w > limit
+            {
+                // the answer lies about (room / average blocks per word) words ahead: bracket it by galloping from
+                // that guess instead of bisecting the whole record (a 40 KB page spans ~1,300 words and six pools)
+                auto over = [&](uint32_t w) { return P(std::min<uint32_t>((w + 1) << 5, kb)) > limit; };
+                const uint64_t span_blocks = Pend - Pk;
+                const uint32_t span_words = hi - lo + 1;
+                uint32_t g = lo + (uint32_t) std::min<uint64_t>((uint64_t) (C - used) * span_words / (span_blocks ? span_blocks : 1), hi - lo);
+                if (over(g)) {
+                    hi = g;
+                    uint32_t step = 1;
+                    while (hi > lo) {  // walk down until a word that is not over: the answer is in (that word, hi]
+                        const uint32_t c = hi - lo > step ? hi - step : lo;
+                        if (!over(c)) {
+                            lo = c + 1;
+                            break;
+                        }
+                        hi = c;
+                        step <<= 1;
+                    }
+                } else {
+                    lo = g + 1;
+                    uint32_t step = 1;
+                    while (lo < hi) {  // walk up until a word that is over: the answer is in [lo, that word]
+                        const uint32_t c = hi - lo > step ? lo + step : hi;
+                        if (over(c)) {
+                            hi = c;
+                            break;
+                        }
+                        lo = c + 1;
+                        step <<= 1;
+                    }
+                }
+            }
             while (lo < hi) {
                 uint32_t mid = (lo + hi) >> 1;
                 uint32_t wend = std::min<uint32_t>((mid + 1) << 5, kb);
