@@ -11,6 +11,7 @@
 // reach(s) = s+M(s);  byte i is PASS iff i is a value of reach;  the pointer of a run ending at j
 // is the end of the leftmost occurrence of D[s*(j)..j],  s*(j) = min{s : reach(s) > j}.
 #include <algorithm>
+#include <cmath>
 #include <chrono>
 #include <cstring>
 
@@ -1141,7 +1142,12 @@ uint32_t Store::count_nodes_and_cut(uint32_t first_new, uint32_t s0, uint32_t N)
     }
     // running estimate of nodes per byte (drives the next candidate selection only; the cut is exact)
     uint32_t bytes = h_win_rec_start[first_new + accepted] - s0;
-    if (bytes > (2u << 20)) rho = std::max(0.02, (double) node_blocks / 8.0 / (double) bytes);
+    if (bytes > (2u << 20)) {
+        const double rho_new = std::max(0.02, (double) node_blocks / 8.0 / (double) bytes);
+        // how far the previous estimate was off (decaying maximum): sizes the slack of the next candidate selection
+        rho_err = std::max(0.7 * rho_err, std::fabs(rho_new / rho - 1.0));
+        rho = rho_new;
+    }
     return accepted;
 }
 
@@ -1479,7 +1485,10 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
             // candidates: what the remaining arena is expected to hold (+4% and one record); the exact cut is
             // found by count_nodes_and_cut.  At least a quarter of the window so re-sorting stays geometric.
             double blocks_left = (2048.0 - pool_nth) * 65535.0 + (65535.0 - pool_used);
-            double est = blocks_left / (8.0 * rho) * 1.04 + 70000.0;
+            // slack over the estimate: candidates the cut then drops were sorted for nothing, a shortfall costs a second
+            // pass over the window.  1 % .. 4 %, three times the recent error of the estimate, plus one large record
+            const double slack = 1.0 + std::min(0.04, std::max(0.01, 3.0 * rho_err));
+            double est = blocks_left / (8.0 * rho) * slack + 70000.0;
             lim = std::min<int64_t>(hard_cap, (int64_t) win_N + (int64_t) std::max<double>(est, (double) win_N / 4));
         }
         // records [a, b) go into the open window

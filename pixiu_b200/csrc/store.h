@@ -119,6 +119,7 @@ struct Store {
     // arena state of the reference's suffix tree for the open window (MemPool::nth / used_num)
     uint32_t pool_nth = 1, pool_used = 5;
     double rho = 1.35;  // running estimate of suffix-tree nodes per window byte
+    double rho_err = 0.02;  // recent relative error of that estimate
     uint32_t win_present[8] = {0}, batch_present[8] = {0};  // byte values present in the open window / last batch
 
     EncodeScratch es;
