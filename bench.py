@@ -1,22 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — batched setitem (compress-on-insert) throughput on BASELINE.json config[1]:
-10k synthetic HTML-like pages x <=60 KB ASCII with URL keys (~400 MB raw) on 1 x B200.
+"""bench.py — BASELINE.json's metric on a B200: batched setitem MB/s of raw input (config[1], C2) as the headline
+line, with the second half of the metric — batched getitem decode GB/s (config[2], C3) and batched contains lookup
+(config[3], C4) — as sub-records of the same JSON line, each with its own e2e / roofline / cpu_baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode all|setitem|getitem|lookup|shard]
 
-One step = one pass of the hot path (PiXiuCtrl::setitem for every record, in order) over the
-whole corpus, starting from a freshly rotated window.  Prints ONE JSON line (rank 0).
+One step of the headline = one pass of the hot path (PiXiuCtrl::setitem for every record, in order) over the whole
+C2 corpus (10k synthetic HTML-like pages x <= 60 KB, URL keys, ~356 MB raw), starting from a freshly rotated window.
+Prints ONE JSON line (rank 0).
 
- value : raw-input MB/s, inputs already resident in HBM (pixiu_setitem_batch_dev), CUDA events
- e2e   : same through pixiu_setitem_batch with pinned HOST buffers (H2D of keys/values and
-         D2H of rc/saved inside the timed region)
- roofline     : dominant kernel class, algorithmic bytes / CUDA-event time vs measured HBM peak
+ value : raw-input MB/s, inputs already resident in HBM (pixiu_setitem_batch_dev), CUDA events on the store's stream
+ e2e   : the same through pixiu_setitem_batch with pinned HOST buffers (H2D of keys/values and D2H of rc/saved inside
+         the timed region)
+ roofline     : dominant kernel class, algorithmic bytes / CUDA-event time vs the measured HBM copy bandwidth
  cpu_baseline : the unmodified reference (oracle/_ref) on this box's host cores, bounded sample
- getitem      : (extra) batched getitem decode of every record, GB/s of encoded+decoded bytes
+ getitem_c2   : batched getitem decode of every C2 record just stored (GB/s of encoded + decoded bytes)
+ getitem_c3   : C3 = 1 M records x 1 KB with deeply nested back references: batched getitem of every record
+ lookup_c4    : C4 = 10 M URL keys x ~200 B values (~2 GB compressed): batched contains of 10 M keys, 90 % present
+ sharded      : (N > 1 only) BASELINE config 5 style: ONE extended window sharded over the N GPUs, every batch replicated,
+                ncclAllReduce(MAX) of the match lengths and ncclAllReduce(MIN) of the leftmost candidates issued inside
+                libpixiu_b200.so -> strong scaling, with the bytes and the stream time of both collectives
 
-N > 1: one process per GPU (torchrun); the corpus is partitioned by key, every rank ingests its
-own pages into its own store (no data-path collective: the reference window is ~12.5 MB, a
-shard never needs another shard's text) -> weak scaling.
+N > 1: one process per GPU (torchrun).  The headline and the read-side sub-records partition the work by key (every
+rank owns its records in its own store; the reference window is ~12.5 MB, a shard never needs another shard's text):
+no data-path collective, weak scaling.  The `sharded` sub-record is the mode with a real exchange step.
 """
 import argparse
 import json
@@ -151,11 +158,97 @@ def ref_all_cores(pages_per_proc, procs):
             "seconds": sec, "stored_over_raw_on_sample": sum(r[2] for r in res) / raw}
 
 
+
+
+def _pool_map(fn, jobs, procs):
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        return pool.map(fn, jobs)
+
+
+# ---- CPU legs of the read side: the reference's getitem / contains (PiXiuCtrl.cpp:55-61) on a bounded sample ----
+def _ref_getitem_worker(job):
+    """one reference instance: ingest `records` C3-style records (untimed), then time getitem + drain of every record
+    (PXSGen::operator(), PiXiuStr.h:129-198).  The reference decoder has bugs B1/B2 (SURVEY 8c): its output is NOT
+    checked, only timed."""
+    records, seed = job
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as po
+    from pixiu_b200 import synth
+
+    kd, ko, vd, vo = synth.gen_nested(records, seed=seed)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    if po.ref_available():
+        ref = po.Ref()
+        r = ref.setitem_batch(keys, vals)
+        g = ref.getitem_batch(keys)
+        ref.close()
+        return int(r["enc_len"].sum()), int(g["bytes"]), float(g["seconds"]), "reference"
+    st = po.OracleStore(strict251=True)
+    enc = 0
+    for k, v in zip(keys, vals):
+        st.setitem(k, v)
+    t0 = time.perf_counter()
+    dec = sum(len(st.getitem(k)) for k in keys)
+    return enc, dec, time.perf_counter() - t0, "port"
+
+
+def cpu_getitem_c3(records, procs):
+    res = _pool_map(_ref_getitem_worker, [(records, 1003 + i) for i in range(procs)], procs)
+    alg = sum(r[0] + r[1] for r in res)
+    sec = max(r[2] for r in res)
+    return {"value": alg / sec / 1e9, "unit": "GB/s", "cores": procs, "kind": res[0][3], "seconds": sec,
+            "decoded_mb_s": sum(r[1] for r in res) / sec / 1e6,
+            "sample": f"{procs} independent single-threaded instances, each ingests {records} records of the C3 generator "
+                      f"(untimed) and then drains getitem of every one of them (timed; output unchecked: reference "
+                      f"decoder bugs B1/B2); aggregate = (encoded + decoded bytes) / slowest instance"}
+
+
+def _ref_contains_worker(job):
+    keys_n, seed = job
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as po
+    from pixiu_b200 import synth
+
+    kd, ko, vd, vo = synth.gen_urls_kv(keys_n, seed=seed, val_words=20)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    rng = np.random.default_rng(seed)
+    n_abs = keys_n // 10
+    q = [keys[i] for i in rng.integers(0, keys_n, size=keys_n - n_abs)] + [b"http://absent.qq.com/a/%d.htm" % i for i in range(n_abs)]
+    q = [q[i] for i in rng.permutation(len(q))]
+    if po.ref_available():
+        ref = po.Ref()
+        ref.setitem_batch(keys, vals)
+        c = ref.contains_batch(q)
+        ref.close()
+        return len(q), float(c["seconds"]), int(c["found"].sum()), "reference"
+    st = po.OracleStore(strict251=True)
+    for k, v in zip(keys, vals):
+        st.setitem(k, v)
+    t0 = time.perf_counter()
+    f = sum(st.contains(k) for k in q)
+    return len(q), time.perf_counter() - t0, f, "port"
+
+
+def cpu_contains_c4(keys_n, procs):
+    res = _pool_map(_ref_contains_worker, [(keys_n, 1004 + i) for i in range(procs)], procs)
+    tot = sum(r[0] for r in res)
+    sec = max(r[1] for r in res)
+    return {"value": tot / sec / 1e6, "unit": "Mkeys/s", "cores": procs, "kind": res[0][3], "seconds": sec,
+            "found_fraction": sum(r[2] for r in res) / tot,
+            "sample": f"{procs} independent single-threaded instances, each ingests {keys_n} C4-style records (untimed) and "
+                      f"then answers contains for {keys_n} keys, 90 % present / 10 % absent, random order (timed); a "
+                      f"{keys_n}-key tree is shallower than the 10 M-key one, which favours the CPU; aggregate = keys / slowest instance"}
+
+
 # ------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """the reference's own CPU implementation (unmodified, compiled into oracle/_ref) on ALL host cores: one
     single-threaded instance per core on its own pages (the reference is not re-entrant; partition by key is also how
-    the GPU arm scales).  One step = every instance ingests --ref-pages pages; value = total raw bytes / slowest instance."""
+    the GPU arm scales).  One step = every instance ingests --ref-pages pages; value = total raw bytes / slowest instance.
+    The read-side legs (getitem C3, contains C4) are timed once each and reported as sub-records."""
     if rank != 0:
         return
     procs = args.ref_procs or (os.cpu_count() or 1)
@@ -174,39 +267,90 @@ def run_reference(args, rank, world):
                                    f"bounded sample: {procs} instances x {args.ref_pages} pages per step)"},
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.mode == "all" and not args.no_read_side:
+        g = cpu_getitem_c3(args.ref_records, procs)
+        line["getitem_c3"] = {"metric": "getitem_decode_throughput", "value": g["value"], "unit": "GB/s", "cpu_baseline": g,
+                              "e2e": {"value": g["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        k = cpu_contains_c4(args.ref_keys, procs)
+        line["lookup_c4"] = {"metric": "contains_lookup_throughput", "value": k["value"], "unit": "Mkeys/s", "cpu_baseline": k,
+                             "e2e": {"value": k["value"], "unit": "Mkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
-    import torch
+class Env:
+    """process-wide plumbing of the GPU arm: device, optional NCCL process group, barrier, timed loop"""
 
+    def __init__(self, rank, world, local_rank):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        self.torch, self.rank, self.world, self.local_rank = torch, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def ext_stream(self, c):
+        return self.torch.cuda.ExternalStream(c.stream(), device=self.dev)
+
+    def timed(self, ext, fn, steps):
+        """K steps bracketed by barrier + synchronize, CUDA events on the store's stream, MAX over ranks"""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall * 1e3], dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def reference_full_corpus_ratio(pages):
+    """stored/raw of the UNMODIFIED reference over the full C2 corpus, from the committed fixture
+    (tests/golden/c2_full_enc_len.npz, made by tests/golden/make_c2_full.py); None when it does not apply"""
+    p = os.path.join(ROOT, "tests", "golden", "c2_full_enc_len.npz")
+    if pages != 10000 or not os.path.exists(p):
+        return None
+    g = np.load(p)
+    return float(g["enc_len"].astype(np.int64).sum()) / float(g["raw_bytes"])
+
+
+def bench_setitem(args, env):
+    """headline: C2 batched setitem; returns the fields of the main JSON line (rank 0) and the corpus for getitem_c2"""
+    torch = env.torch
     from pixiu_b200 import ctrl, synth
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    rank, world, dev = env.rank, env.world, env.dev
     kd, ko, vd, vo = gen_corpus(args.pages, 2 + rank)
     n = len(ko) - 1
     raw = int(ko[-1] + vo[-1])
-    dev = torch.device("cuda", local_rank)
     t_kd, t_ko, t_vd, t_vo = (torch.from_numpy(a) for a in (kd, ko, vd, vo))
     d_kd, d_ko, d_vd, d_vo = (t.to(dev) for t in (t_kd, t_ko, t_vd, t_vo))
     p_kd, p_ko, p_vd, p_vo = (t.pin_memory() for t in (t_kd, t_ko, t_vd, t_vo))
     policy = {"reference": ctrl.ROTATE_REFERENCE, "bytes": ctrl.ROTATE_BYTES, "records": ctrl.ROTATE_RECORDS}[args.window]
-    c = ctrl.PiXiuCtrl(device=local_rank, rotate_policy=policy, window_bytes=args.window_bytes)
-    ext = torch.cuda.ExternalStream(c.stream(), device=dev)
+    c = ctrl.PiXiuCtrl(device=env.local_rank, rotate_policy=policy, window_bytes=args.window_bytes)
+    ext = env.ext_stream(c)
 
     def step_dev():
         c.rotate()
@@ -214,39 +358,22 @@ def run_ours(args, rank, world, local_rank):
 
     def step_host():
         c.rotate()
-        L = c._L
         rc = np.zeros(n, dtype=np.int32)
         saved = np.zeros(n, dtype=np.int32)
-        r = L.pixiu_setitem_batch(c._h, n, p_kd.data_ptr(), p_ko.data_ptr(), p_vd.data_ptr(), p_vo.data_ptr(),
-                                  rc.ctypes.data_as(ctrl._i32p), saved.ctypes.data_as(ctrl._i32p))
+        r = c._L.pixiu_setitem_batch(c._h, n, p_kd.data_ptr(), p_ko.data_ptr(), p_vd.data_ptr(), p_vo.data_ptr(),
+                                     rc.ctypes.data_as(ctrl._i32p), saved.ctypes.data_as(ctrl._i32p))
         c._check(r)
         return rc, saved
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(ext)
-        for _ in range(steps):
-            fn()
-        e1.record(ext)
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = max(e0.elapsed_time(e1), 0.0)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1])
 
     for _ in range(args.warmup):
         step_dev()
     # NVML queries take a driver-wide lock: with one sampler per rank the ranks of a launch-bound step slow each other
     # down, so only rank 0 (whose line is printed) samples its GPU
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(env.local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     st0 = c.stats()
-    dev_ms, dev_wall_ms = timed(step_dev, args.steps)
+    dev_ms, dev_wall_ms = env.timed(ext, step_dev, args.steps)
     st1 = c.stats()
     clocks = sampler.stop() if sampler else None
     launches_per_step = (st1.kernel_launches - st0.kernel_launches) // max(args.steps, 1)
@@ -255,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(min(args.warmup, 1)):
         step_host()
-    e2e_ms, e2e_wall_ms = timed(step_host, args.steps)
+    e2e_ms, e2e_wall_ms = env.timed(ext, step_host, args.steps)
 
     # ---- roofline: per-kernel-class CUDA-event timing of one extra (untimed) step ----
     c.profile_enable(True)
@@ -267,52 +394,38 @@ def run_ours(args, rank, world, local_rank):
     top = max((k for k in prof if prof[k]["launches"]), key=lambda k: prof[k]["ms"])
     tp = prof[top]
     ach = tp["bytes"] / 1e9 / (tp["ms"] / 1e3) if tp["ms"] else 0.0
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/
-    # r01_onesweep_12Mkeys_ncu_raw.csv): 150.06 MB read + 100.93 MB written per launch of 12 M keys, i.e.
-    # 0.871 x the algorithmic n x 24 B (L2 absorbs part of the scatter); scaled to this run's average launch.
-    NCU_TRAFFIC_OVER_ALGORITHMIC = {"sort_pass": (150.06e6 + 100.93e6) / (12e6 * 24)}
     traffic = None
     if top in NCU_TRAFFIC_OVER_ALGORITHMIC and tp["launches"]:
-        traffic = NCU_TRAFFIC_OVER_ALGORITHMIC[top] * tp["bytes"] / tp["launches"]
+        traffic = NCU_TRAFFIC_OVER_ALGORITHMIC[top][0] * tp["bytes"] / tp["launches"]
     roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": tp["bytes"] / max(tp["launches"], 1),
-                "launches": tp["launches"],
+                "frac": ach / peak, "traffic": traffic,
+                "traffic_source": (NCU_TRAFFIC_OVER_ALGORITHMIC[top][1] + " (ratio of a committed ncu capture x this run's "
+                                   "algorithmic bytes per launch; not measured in this run)") if traffic else None,
+                "algorithmic_bytes_per_launch": tp["bytes"] / max(tp["launches"], 1), "launches": tp["launches"],
                 "avg_launch_ms": tp["ms"] / max(tp["launches"], 1), "share_of_step": tp["ms"] / tot_ms,
                 "classes_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}}
 
-    # ---- extra: batched getitem decode of everything just stored (device output) ----
+    # ---- getitem_c2: batched getitem decode of everything just stored (device output), every record checked ----
     getitem = None
     try:
-        out = torch.empty(int(raw + 8 * n + 64), dtype=torch.uint8, device=dev)
-        c.getitem_batch_dev((kd, ko), out.data_ptr(), out.numel())  # warm
-        torch.cuda.synchronize()
-        tg0 = time.perf_counter()
-        off, found = c.getitem_batch_dev((kd, ko), out.data_ptr(), out.numel())
-        call_ms = (time.perf_counter() - tg0) * 1e3     # whole call: key upload, lookup, work list, decode (it returns synchronised)
-        s = c.stats()
-        c.profile_enable(True)
-        c.getitem_batch_dev((kd, ko), out.data_ptr(), out.numel())
-        pd = c.profile()["decode"]
-        c.profile_enable(False)
-        gbs = pd["bytes"] / 1e9 / (pd["ms"] / 1e3)
-        getitem = {"decode_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "decode_ms": pd["ms"], "records": int(found.sum()),
-                   "decoded_bytes": int(off[-1]), "lookup_ms": s.last_lookup_gpu_ms, "whole_call_ms": call_ms,
-                   "whole_call_gbs": pd["bytes"] / 1e9 / (call_ms / 1e3),
-                   "bytes_counted": "encoded read + decoded written; decode_* = decode kernels + arena memset (CUDA events), "
-                                    "whole_call_* = pixiu_getitem_batch_dev wall time; `bench.py --mode getitem` is the full line"}
-        # bit-exact round trip of a sample against the inputs
-        from pixiu_b200.ctrl import split_doc
-        hb = out[: int(off[-1])].cpu().numpy()
-        keys, vals = synth.unpack(kd, ko), None
-        vb = vd.tobytes()
-        for i in list(range(0, n, max(n // 64, 1))):
-            k, v = split_doc(hb[off[i]:off[i + 1]].tobytes())
-            assert k == keys[i] and v == vb[vo[i]:vo[i + 1]], f"round trip mismatch at record {i}"
-        getitem["roundtrip_sample_ok"] = True
+        getitem = getitem_measure(args, env, c, (kd, ko, vd, vo), "c2", steps=max(3, min(args.steps, 10)), cpu=None)
     except Exception as e:  # the headline metric stands on its own
         getitem = {"error": repr(e)}
+    st_end = c.stats()
+    c.free_prop()
+    del d_kd, d_ko, d_vd, d_vo
 
-    # ---- CPU baseline: the reference on a bounded sample, every host core busy (rank 0, N=1 only) ----
+    # ---- the reference-exact ratio: strict251 reproduces the reference's bytes (bug B1 included) ----
+    strict_ratio = None
+    try:
+        cs = ctrl.PiXiuCtrl(device=env.local_rank, rotate_policy=policy, window_bytes=args.window_bytes, strict251=True)
+        cs.setitem_batch((kd, ko), (vd, vo))
+        ss = cs.stats()
+        strict_ratio = ss.encoded_bytes / max(ss.raw_bytes, 1)
+        cs.free_prop()
+    except Exception as e:
+        strict_ratio = repr(e)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         procs = args.ref_procs or (os.cpu_count() or 1)
@@ -323,69 +436,69 @@ def run_ours(args, rank, world, local_rank):
                                   "stored_over_raw_on_sample": one[2] / one[0]}
         cpu["host_cores"] = os.cpu_count()
 
-    if rank == 0:
-        total_raw = raw * world
-        line = {
-            "metric": METRIC, "value": total_raw * args.steps / (dev_ms / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2: {args.pages} synthetic HTML-like pages x <=60KB (bytes 33..126), URL keys, batched setitem, per GPU",
-                       "raw_bytes_per_gpu": raw, "records_per_gpu": n, "window_policy": args.window,
-                       "windows_per_step": chunks_per_step, "stored_over_raw": ratio,
-                       "l2": "inputs (~400 MB) and per-window scratch (~0.9 GB) exceed the 126 MB L2; no explicit flush",
-                       "partitioning": "by key across ranks, no collective"},
-            "wall_ms_per_step": dev_wall_ms / args.steps,
-            "e2e": {"value": total_raw * args.steps / (e2e_ms / 1e3) / 1e6, "unit": UNIT,
-                    "h2d_bytes_per_step": int(kd.nbytes + ko.nbytes + vd.nbytes + vo.nbytes), "d2h_bytes_per_step": int(8 * n),
-                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall_ms / args.steps},
-            "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roofline, "cpu_baseline": cpu, "getitem": getitem, "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
-    c.free_prop()
-    if dist is not None:
-        dist.destroy_process_group()
+    total_raw = raw * world
+    line = {
+        "metric": METRIC, "value": total_raw * args.steps / (dev_ms / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"C2: {args.pages} synthetic HTML-like pages x <=60KB (bytes 33..126), URL keys, batched setitem, per GPU",
+                   "raw_bytes_per_gpu": raw, "records_per_gpu": n, "window_policy": args.window,
+                   "windows_per_step": chunks_per_step, "stored_over_raw": ratio,
+                   "stored_over_raw_strict251": strict_ratio,
+                   "stored_over_raw_reference_full_corpus": reference_full_corpus_ratio(args.pages) if rank == 0 else None,
+                   "ratio_note": "default mode writes a run of exactly 251 bytes in the 8-byte form (+2 B per such run; the "
+                                 "reference's 6-byte form FB FB.. is undecodable, bug B1); strict251 reproduces the reference's "
+                                 "bytes; *_reference_full_corpus is the unmodified reference over the same 10,000 pages "
+                                 "(tests/golden/c2_full_enc_len.npz)",
+                   "steps_note": "every step re-inserts the same keys: after the first pass each record takes the index's "
+                                 "REPLACE path and tombstones its previous copy; nothing is reclaimed between steps (the "
+                                 f"store grows by ~{(st1.encoded_bytes - st0.encoded_bytes) / max(args.steps, 1) / 1e6:.0f} MB per step)",
+                   "l2": "inputs (~400 MB) and per-window scratch (~0.9 GB) exceed the 126 MB L2; no explicit flush",
+                   "partitioning": "by key across ranks, no collective"},
+        "wall_ms_per_step": dev_wall_ms / args.steps,
+        "e2e": {"value": total_raw * args.steps / (e2e_ms / 1e3) / 1e6, "unit": UNIT,
+                "h2d_bytes_per_step": int(kd.nbytes + ko.nbytes + vd.nbytes + vo.nbytes), "d2h_bytes_per_step": int(8 * n),
+                "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall_ms / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": roofline, "cpu_baseline": cpu, "getitem_c2": getitem,
+        "index_memory": {"key_arena_bytes": int(st_end.index_key_arena_bytes), "host_bytes": int(st_end.index_host_bytes),
+                         "device_bytes": int(st_end.index_device_bytes), "table_device_bytes": int(st_end.table_device_bytes),
+                         "note": "held beside the compressed store (pixiu_stats.index_*): the index keeps esc(k) 251 0 of every "
+                                 "leaf instead of decoding the record to verify a key"},
+        "clocks": clocks,
+    }
+    return line
 
 
-def run_getitem(args, rank, world, local_rank):
-    """BASELINE config[2] (C3): batched getitem decode of N records x 1 KB with deeply nested back references
-    (or `--workload c2`: the HTML pages).  One step = lookup + decode of EVERY stored record of this rank.
-      value : GB/s of (encoded bytes read + decoded bytes written), whole pixiu_getitem_batch_dev call timed with
-              CUDA events on the store's stream (keys are host inputs, the decoded output stays in HBM)
+# DRAM traffic over algorithmic bytes of the dominant kernels, from the committed `ncu --set full` captures under profiles/
+NCU_TRAFFIC_OVER_ALGORITHMIC = {
+    # k_rs_onesweep: 150.06 MB read + 100.93 MB written per launch of 12 M keys vs n x 24 B (L2 absorbs part of the scatter)
+    "sort_pass": ((150.06e6 + 100.93e6) / (12e6 * 24), "profiles/r01_onesweep_12Mkeys_ncu_raw.csv"),
+}
+NCU_DECODE_TRAFFIC = {  # filled from this round's captures of the decode kernel (see profiles/README.md)
+    "c2": None, "c3": None,
+}
+
+
+def getitem_measure(args, env, c, corpus, workload, steps, cpu):
+    """batched getitem of EVERY record of `corpus` already stored in `c`; returns a sub-record
+      value : GB/s of (encoded bytes read + decoded bytes written), whole pixiu_getitem_batch_dev call timed with CUDA
+              events on the store's stream (keys are host inputs, the decoded output stays in HBM)
       e2e   : pixiu_getitem_batch into a pinned HOST buffer (key H2D, decoded bytes D2H inside the timed region)
-      roofline : the decode kernels alone (k_decode_tiles [+ k_resolve rounds]), algorithmic bytes / event time
-    Multi-GPU: every rank holds its own records (partition by key), no collective."""
-    import torch
+      roofline : the decode kernels alone, algorithmic bytes / event time"""
+    torch = env.torch
+    from pixiu_b200 import synth
 
-    from pixiu_b200 import ctrl, synth
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
-    if args.workload == "c2":
-        kd, ko, vd, vo = gen_corpus(args.pages, 2 + rank)
-        wl = f"C2 decode: {args.pages} synthetic HTML-like pages x <=60KB per GPU, batched getitem of every record"
-    else:
-        kd, ko, vd, vo = synth.gen_nested(args.records, seed=3 + rank)
-        wl = (f"C3: {args.records} records x 1 KB per GPU, record r = record r-1 with one swept byte mutated "
-              f"(deeply nested back references) + self-periodic runs, batched getitem of every record")
+    kd, ko, vd, vo = corpus
     n = len(ko) - 1
-    raw = int(ko[-1] + vo[-1])
-    c = ctrl.PiXiuCtrl(device=local_rank, rotate_policy=ctrl.ROTATE_REFERENCE)
-    rcs, _ = c.setitem_batch((kd, ko), (vd, vo))
     st = c.stats()
-    ext = torch.cuda.ExternalStream(c.stream(), device=dev)
-    cap = int(st.doc_bytes + 64)
-    out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    ext = env.ext_stream(c)
+    # decoded docs of the LIVE copies of the corpus' records: key + value + 4 terminator bytes each (escape-free data)
+    dec_bytes = int(ko[-1] + vo[-1] + 4 * n)
+    cap = dec_bytes + 64
+    out = torch.empty(cap, dtype=torch.uint8, device=env.dev)
     hout = torch.empty(cap, dtype=torch.uint8).pin_memory()
     hout_np = hout.numpy()
-    alg = float(st.encoded_bytes + st.doc_bytes)
 
     def step_dev():
         return c.getitem_batch_dev((kd, ko), out.data_ptr(), cap)
@@ -393,112 +506,99 @@ def run_getitem(args, rank, world, local_rank):
     def step_host():
         return c.getitem_batch((kd, ko), out=hout_np)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(ext)
-        for _ in range(steps):
-            fn()
-        e1.record(ext)
-        barrier()
-        wall = time.perf_counter() - t0
-        t = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1])
-
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3) if workload != "c2" else 3):
         off, found = step_dev()
     assert found.all()
-    # (a step is milliseconds of kernel time, not launch-bound: fast sampling; rank 0 only, NVML takes a driver-wide lock)
-    sampler = ClockSampler(local_rank, first_delay=0.002, period=0.01) if rank == 0 else None
+    sampler = ClockSampler(env.local_rank, first_delay=0.002, period=0.01) if env.rank == 0 else None
     if sampler:
         sampler.start()
     l0 = c.stats().kernel_launches
-    dev_ms, dev_wall = timed(step_dev, args.steps)
+    dev_ms, dev_wall = env.timed(ext, step_dev, steps)
     launches = c.stats().kernel_launches - l0
     clocks = sampler.stop() if sampler else None
     step_host()
-    e2e_ms, e2e_wall = timed(step_host, args.steps)
-    # decode kernels alone
+    e2e_ms, e2e_wall = env.timed(ext, step_host, steps)
     c.profile_enable(True)
     step_dev()
-    prof = c.profile()
+    pd = c.profile()["decode"]
     c.profile_enable(False)
     s = c.stats()
-    pd = prof["decode"]
     peak, peak_kind = measured_peak()
-    ach = pd["bytes"] / 1e9 / (pd["ms"] / 1e3)
-    # DRAM traffic of k_decode_tiles over its algorithmic bytes from the committed `ncu --set full` captures
-    # (profiles/r01_decode_tiles_c2_3000pages_ncu_raw.csv: 135.2 MB read + 77.9 MB written for 196.6 MB;
-    #  profiles/r01_decode_tiles_c3_1Mrecords_ncu_raw.csv: 724.9 MB + 1,008.4 MB for 1,056.3 MB - deep chains re-read
-    #  decoded sources that have left the L2), plus the arena memset (the decoded bytes written once more)
-    ncu_ratio = {"c2": (135.17 + 77.93) / 196.57, "c3": (724.9 + 1008.4) / 1056.3}[args.workload]
-    traffic = ncu_ratio * pd["bytes"] + float(st.doc_bytes)
-    # bit-exact round trip of every record against the inputs (escape-free synthetic data)
+    alg = float(pd["bytes"])                      # encoded bytes of the decoded ranges + decoded bytes
+    ach = alg / 1e9 / (pd["ms"] / 1e3)
+    ncu = NCU_DECODE_TRAFFIC.get(workload)
+    # bit-exact round trip of EVERY record against the inputs (escape-free synthetic data)
     hb = out[: int(off[-1])].cpu().numpy()
     klen, vlen = np.diff(ko), np.diff(vo)
     ok = bool(np.array_equal(np.diff(off), klen + vlen + 4)
               and np.array_equal(synth.ragged_gather(hb, off[:-1], klen), kd)
               and np.array_equal(synth.ragged_gather(hb, off[:-1] + klen + 2, vlen), vd))
     if not ok:
-        raise SystemExit("getitem bench: decoded records differ from the inputs")
-    if rank == 0:
-        line = {"metric": "getitem_decode_throughput", "value": alg * world * args.steps / (dev_ms / 1e3) / 1e9, "unit": "GB/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": wl, "records_per_gpu": n, "raw_bytes_per_gpu": raw, "decoded_bytes_per_gpu": int(st.doc_bytes),
-                           "encoded_bytes_per_gpu": int(st.encoded_bytes), "chunks": int(st.chunks),
-                           "bytes_counted": "encoded read + decoded written (SURVEY 8d)",
-                           "l2": "decoded output (>= 1 GB) exceeds the 126 MB L2; no explicit flush"},
-                "wall_ms_per_step": dev_wall / args.steps,
-                "e2e": {"value": alg * world * args.steps / (e2e_ms / 1e3) / 1e9, "unit": "GB/s",
-                        "h2d_bytes_per_step": int(kd.nbytes + ko.nbytes), "d2h_bytes_per_step": int(off[-1]) + 9 * n,
-                        "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_decode_tiles(+k_resolve)", "achieved": ach, "peak": peak,
-                             "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                             "algorithmic_bytes_per_launch": pd["bytes"], "avg_launch_ms": pd["ms"],
-                             "launches": pd["launches"], "lookup_ms": s.last_lookup_gpu_ms},
-                "roundtrip_all_records_ok": ok, "clocks": clocks, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        raise SystemExit(f"getitem bench ({workload}): decoded records differ from the inputs")
+    world = env.world
+    return {"metric": "getitem_decode_throughput", "value": alg * world * steps / (dev_ms / 1e3) / 1e9, "unit": "GB/s",
+            "n_gpus": world, "steps": steps, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
+            "config": {"workload": workload, "records_per_gpu": n, "decoded_bytes_per_gpu": dec_bytes,
+                       "algorithmic_bytes_per_gpu": alg, "chunks": int(st.chunks),
+                       "bytes_counted": "encoded read + decoded written (SURVEY 8d)",
+                       "l2": "decoded output (>= 350 MB) exceeds the 126 MB L2; no explicit flush"},
+            "wall_ms_per_step": dev_wall / steps,
+            "e2e": {"value": alg * world * steps / (e2e_ms / 1e3) / 1e9, "unit": "GB/s",
+                    "h2d_bytes_per_step": int(kd.nbytes + ko.nbytes), "d2h_bytes_per_step": int(off[-1]) + 9 * n,
+                    "ms_per_step": e2e_ms / steps, "wall_ms_per_step": e2e_wall / steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "decode kernels (k_decode_tiles ...)", "achieved": ach, "peak": peak,
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": (ncu[0] * alg) if ncu else None, "traffic_source": ncu[1] if ncu else None,
+                         "algorithmic_bytes_per_launch": alg, "avg_launch_ms": pd["ms"], "launches": pd["launches"],
+                         "lookup_ms": s.last_lookup_gpu_ms},
+            "roundtrip_all_records_ok": ok, "clocks": clocks, "cpu_baseline": cpu}
+
+
+def bench_getitem(args, env, workload):
+    """BASELINE config[2] (C3): 1 M records x 1 KB with deeply nested back references (or the C2 pages): setitem of the
+    corpus (untimed), then getitem_measure; the CPU leg runs the reference's getitem on a bounded sample (rank 0, N=1)"""
+    from pixiu_b200 import ctrl, synth
+
+    if workload == "c2":
+        corpus = gen_corpus(args.pages, 2 + env.rank)
+        wl = f"C2 decode: {args.pages} synthetic HTML-like pages x <=60KB per GPU, batched getitem of every record"
+    else:
+        corpus = synth.gen_nested(args.records, seed=3 + env.rank)
+        wl = (f"C3: {args.records} records x 1 KB per GPU, record r = record r-1 with one swept byte mutated "
+              f"(deeply nested back references) + self-periodic runs, batched getitem of every record")
+    c = ctrl.PiXiuCtrl(device=env.local_rank, rotate_policy=ctrl.ROTATE_REFERENCE)
+    c.setitem_batch((corpus[0], corpus[1]), (corpus[2], corpus[3]))
+    cpu = None
+    if env.rank == 0 and env.world == 1 and not args.no_cpu and workload == "c3":
+        cpu = cpu_getitem_c3(args.ref_records, args.ref_procs or (os.cpu_count() or 1))
+    rec = getitem_measure(args, env, c, corpus, workload, steps=args.steps, cpu=cpu)
+    rec["config"]["workload"] = wl
+    st = c.stats()
+    rec["config"]["encoded_bytes_per_gpu"] = int(st.encoded_bytes)
+    rec["config"]["stored_over_raw"] = st.encoded_bytes / max(st.raw_bytes, 1)
     c.free_prop()
-    if dist is not None:
-        dist.destroy_process_group()
+    return rec
 
 
-def run_lookup(args, rank, world, local_rank):
+def bench_lookup(args, env):
     """BASELINE config[3] (C4): batched contains over N URL keys with ~200-byte values (10 M keys = a ~2 GB compressed
     corpus); the query batch is N keys, 90 % present / 10 % absent, in random order.  One step = one batch.
       value : M keys/s, queries already packed in HBM (pixiu_contains_batch_dev), CUDA events on the store's stream
       e2e   : pixiu_contains_batch with HOST buffers (query H2D and found[] D2H inside the timed region)
       roofline : k_query_len/write + k_lookup, algorithmic bytes per query = q_len + depth x 7 + q_len"""
-    import torch
-
+    torch = env.torch
     from pixiu_b200 import ctrl, synth
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, dev = env.rank, env.world, env.dev
     n = args.keys
     kd, ko, vd, vo = synth.gen_urls_kv(n, seed=4 + rank, val_words=20)
-    c = ctrl.PiXiuCtrl(device=local_rank, rotate_policy=ctrl.ROTATE_REFERENCE)
+    c = ctrl.PiXiuCtrl(device=env.local_rank, rotate_policy=ctrl.ROTATE_REFERENCE)
     t0 = time.perf_counter()
-    rcs, _ = c.setitem_batch((kd, ko), (vd, vo))
+    c.setitem_batch((kd, ko), (vd, vo))
     set_s = time.perf_counter() - t0
     st = c.stats()
+    del vd
     # queries
     rng = np.random.default_rng(40 + rank)
     n_abs = n // 10
@@ -518,7 +618,7 @@ def run_lookup(args, rank, world, local_rank):
     d_found = torch.zeros(n, dtype=torch.uint8, device=dev)
     p_qd, p_qo = torch.from_numpy(qd).pin_memory(), torch.from_numpy(qo).pin_memory()
     found_h = np.zeros(n, dtype=np.uint8)
-    ext = torch.cuda.ExternalStream(c.stream(), device=dev)
+    ext = env.ext_stream(c)
 
     def step_dev():
         c.contains_batch_dev(d_qd.data_ptr(), d_qo.data_ptr(), n, d_found.data_ptr())
@@ -526,41 +626,21 @@ def run_lookup(args, rank, world, local_rank):
     def step_host():
         c._check(c._L.pixiu_contains_batch(c._h, n, p_qd.data_ptr(), p_qo.data_ptr(), found_h.ctypes.data_as(ctrl._u8p)))
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(ext)
-        for _ in range(steps):
-            fn()
-        e1.record(ext)
-        barrier()
-        wall = time.perf_counter() - t0
-        t = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1])
-
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         step_dev()
     if not np.array_equal(d_found.cpu().numpy().astype(bool), expect):
         raise SystemExit("lookup bench: found[] differs from the expected presence of the queries")
-    sampler = ClockSampler(local_rank, first_delay=0.002, period=0.01) if rank == 0 else None
+    sampler = ClockSampler(env.local_rank, first_delay=0.002, period=0.01) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = c.stats().kernel_launches
-    dev_ms, dev_wall = timed(step_dev, args.steps)
+    dev_ms, dev_wall = env.timed(ext, step_dev, args.steps)
     launches = c.stats().kernel_launches - l0
     clocks = sampler.stop() if sampler else None
     step_host()
     if not np.array_equal(found_h.astype(bool), expect):
         raise SystemExit("lookup bench: host-path found[] differs")
-    e2e_ms, e2e_wall = timed(step_host, args.steps)
+    e2e_ms, e2e_wall = env.timed(ext, step_host, args.steps)
     c.profile_enable(True)
     step_dev()
     pl = c.profile()["lookup"]
@@ -575,48 +655,47 @@ def run_lookup(args, rank, world, local_rank):
     alg = pl["bytes"] + n * mean_depth * 7.0
     peak, peak_kind = measured_peak()
     ach = alg / 1e9 / (pl["ms"] / 1e3)
-    if rank == 0:
-        line = {"metric": "contains_lookup_throughput", "value": n * world * args.steps / (dev_ms / 1e3) / 1e6, "unit": "Mkeys/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"C4: {n} URL keys x ~200 B values per GPU stored ({st.chunks} chunks, {st.encoded_bytes / 1e9:.2f} GB "
-                                       f"compressed), batched contains of {n} keys, 90 % present / 10 % absent, random order",
-                           "keys_per_gpu": n, "query_bytes": int(qd.nbytes), "mean_walk_depth": mean_depth,
-                           "max_walk_depth_in_sample": int(depth.max()), "stored_over_raw": st.encoded_bytes / max(st.raw_bytes, 1),
-                           "setitem_seconds_incl_index": set_s, "setitem_mb_s": st.raw_bytes / set_s / 1e6,
-                           "setitem_gpu_ms": st.last_setitem_gpu_ms,
-                           "setitem_note": "one cold call of the process (first allocations included); wall = GPU encode + CritBit insert",
-                           "l2": "index (nodes + key arena) and queries exceed the 126 MB L2 at 10 M keys; no explicit flush"},
-                "wall_ms_per_step": dev_wall / args.steps,
-                "e2e": {"value": n * world * args.steps / (e2e_ms / 1e3) / 1e6, "unit": "Mkeys/s",
-                        "h2d_bytes_per_step": int(qd.nbytes + qo.nbytes), "d2h_bytes_per_step": int(n),
-                        "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_query_len + scan + k_query_write + k_lookup", "achieved": ach, "peak": peak,
-                             "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                             "algorithmic_bytes_per_launch": alg, "avg_launch_ms": pl["ms"], "launches": pl["launches"],
-                             "sector_granular_gbs": (pl["bytes"] + n * mean_depth * 32.0) / 1e9 / (pl["ms"] / 1e3),
-                             "bytes_model": "2 x escaped query bytes + depth x 7 B per query (SURVEY 8d); sector-granular: depth x 32 B"},
-                "found_matches_expected": True, "clocks": clocks, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+    st2 = c.stats()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_contains_c4(args.ref_keys, args.ref_procs or (os.cpu_count() or 1))
+    rec = {"metric": "contains_lookup_throughput", "value": n * world * args.steps / (dev_ms / 1e3) / 1e6, "unit": "Mkeys/s",
+           "n_gpus": world, "steps": args.steps, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "config": {"workload": f"C4: {n} URL keys x ~200 B values per GPU stored ({st.chunks} chunks, {st.encoded_bytes / 1e9:.2f} GB "
+                                  f"compressed), batched contains of {n} keys, 90 % present / 10 % absent, random order",
+                      "keys_per_gpu": n, "query_bytes": int(qd.nbytes), "mean_walk_depth": mean_depth,
+                      "max_walk_depth_in_sample": int(depth.max()), "stored_over_raw": st.encoded_bytes / max(st.raw_bytes, 1),
+                      "index_key_arena_bytes": int(st2.index_key_arena_bytes), "index_device_bytes": int(st2.index_device_bytes),
+                      "index_host_bytes": int(st2.index_host_bytes),
+                      "stored_plus_index_over_raw": (st.encoded_bytes + st2.index_device_bytes) / max(st.raw_bytes, 1),
+                      "setitem_seconds_incl_index": set_s, "setitem_mb_s": st.raw_bytes / set_s / 1e6,
+                      "setitem_gpu_ms": st.last_setitem_gpu_ms,
+                      "setitem_note": "one cold call of the process (first allocations included); wall = GPU encode + CritBit insert",
+                      "l2": "index (nodes + key arena) and queries exceed the 126 MB L2 at 10 M keys; no explicit flush"},
+           "wall_ms_per_step": dev_wall / args.steps,
+           "e2e": {"value": n * world * args.steps / (e2e_ms / 1e3) / 1e6, "unit": "Mkeys/s",
+                   "h2d_bytes_per_step": int(qd.nbytes + qo.nbytes), "d2h_bytes_per_step": int(n),
+                   "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "kernel": "k_query_len + scan + k_query_write + k_lookup", "achieved": ach, "peak": peak,
+                        "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "algorithmic_bytes_per_launch": alg, "avg_launch_ms": pl["ms"], "launches": pl["launches"],
+                        "sector_granular_gbs": (pl["bytes"] + n * mean_depth * 32.0) / 1e9 / (pl["ms"] / 1e3),
+                        "bytes_model": "2 x escaped query bytes + depth x 7 B per query (SURVEY 8d); sector-granular: depth x 32 B"},
+           "found_matches_expected": True, "clocks": clocks, "cpu_baseline": cpu}
     c.free_prop()
-    if dist is not None:
-        dist.destroy_process_group()
+    return rec
 
 
-def run_sharded(args, rank, world, local_rank):
-    """BASELINE config 5 style: ONE extended window sharded by record over the GPUs; every batch goes to
-    all ranks, match lengths are MAX-reduced and leftmost candidates MIN-reduced by NCCL."""
-    import torch
-    import torch.distributed as dist
+def bench_sharded(args, env):
+    """BASELINE config 5 style: ONE extended window sharded by record over the GPUs; every batch goes to all ranks;
+    match lengths are MAX-reduced and leftmost candidates MIN-reduced by ncclAllReduce inside libpixiu_b200.so
+    (pixiu_mg_setitem_batch).  Total work is fixed as N grows: strong scaling."""
+    torch = env.torch
+    from pixiu_b200 import ctrl, multigpu, shard
 
-    from pixiu_b200 import ctrl, multigpu, shard, synth
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    kd, ko, vd, vo = gen_corpus(args.pages, 2)          # the same corpus on every rank
+    rank, world = env.rank, env.world
+    kd, ko, vd, vo = gen_corpus(args.shard_pages, 2)          # the same corpus on every rank
     n = len(ko) - 1
     raw = int(ko[-1] + vo[-1])
     bp = args.batch_pages
@@ -625,48 +704,52 @@ def run_sharded(args, rank, world, local_rank):
         idx = np.arange(a, min(n, a + bp))
         batches.append((shard.take_packed(kd, ko, idx), shard.take_packed(vd, vo, idx)))
 
-    def one_pass():
-        c = ctrl.PiXiuCtrl(device=local_rank, rotate_policy=ctrl.ROTATE_BYTES, window_bytes=args.window_bytes)
-        c.mg_config(rank, world)
-        torch.cuda.synchronize()
+    def one_pass(k):
+        c = ctrl.PiXiuCtrl(device=env.local_rank, rotate_policy=ctrl.ROTATE_BYTES, window_bytes=args.shard_window_bytes)
         if world > 1:
-            dist.barrier()
+            multigpu.init_comm_torch(c)       # bootstrap only: the 128-byte NCCL id travels over the process group
+        else:
+            c.mg_comm_init(0, 1, c.mg_unique_id())
+        env.barrier()
         t0 = time.perf_counter()
         for kb, vb in batches:
-            if world > 1:
-                multigpu.setitem_sharded(c, kb, vb, device=dev)
-            else:
-                c.mg_setitem_begin(kb, vb)
-                c.mg_setitem_mid()
-                c.mg_setitem_end()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+            c.mg_setitem_batch(kb, vb)
+        env.barrier()
         dt = time.perf_counter() - t0
-        st = c.stats()
-        out = (dt, st.encoded_bytes / max(st.raw_bytes, 1), st.chunks, st.kernel_launches)
+        st, ms = c.stats(), c.mg_stats()
+        out = dict(sec=dt, ratio=st.encoded_bytes / max(st.raw_bytes, 1), chunks=int(st.chunks), launches=int(st.kernel_launches),
+                   max_ms=ms.max_reduce_ms, min_ms=ms.min_reduce_ms, max_bytes=int(ms.max_reduce_bytes),
+                   min_bytes=int(ms.min_reduce_bytes), nccl=int(ms.nccl_version))
         c.free_prop()
         return out
 
-    for _ in range(args.warmup):
-        one_pass()
-    res = [one_pass() for _ in range(args.steps)]
-    t = torch.tensor([sum(r[0] for r in res)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        sec = float(t) / args.steps
-        print(json.dumps({
-            "metric": METRIC, "value": raw / sec / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C5 style: {args.pages} synthetic HTML-like pages, ONE window sharded over {world} GPU(s), "
-                                   f"{args.window_bytes} window bytes per GPU, batches of {bp} pages replicated to all ranks",
-                       "mode": "sharded window + NCCL all_reduce(MAX) of M / all_reduce(MIN) of leftmost candidates",
-                       "raw_bytes": raw, "stored_over_raw": res[-1][1], "chunks": res[-1][2]},
-            "gpu_launches": int(res[-1][3]), "collectives_per_step": 2 * len(batches) if world > 1 else 0}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    for k in range(min(args.warmup, 1)):
+        one_pass(-1 - k)
+    steps = max(1, min(args.steps, 3))
+    res = [one_pass(k) for k in range(steps)]
+    t = torch.tensor([sum(r["sec"] for r in res), sum(r["max_ms"] for r in res), sum(r["min_ms"] for r in res)],
+                     dtype=torch.float64, device=env.dev)
+    if env.dist is not None:
+        env.dist.all_reduce(t, op=env.dist.ReduceOp.MAX)
+    sec = float(t[0]) / steps
+    last = res[-1]
+    return {"metric": METRIC, "value": raw / sec / 1e6, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "timing": "wall clock around the pass, bracketed by barrier + synchronize, MAX over ranks (each batch ends "
+                      "synchronised: rc/saved are returned to the host)",
+            "config": {"workload": f"C5 style: {args.shard_pages} synthetic HTML-like pages ({raw / 1e6:.0f} MB raw), ONE window sharded "
+                                   f"over {world} GPU(s), {args.shard_window_bytes} window bytes per GPU, batches of {bp} pages "
+                                   f"replicated to all ranks",
+                       "mode": "sharded window + ncclAllReduce(MAX) of M / ncclAllReduce(MIN) of leftmost candidates, issued by "
+                               "libpixiu_b200.so on the store's stream",
+                       "raw_bytes": raw, "stored_over_raw": last["ratio"], "chunks": last["chunks"], "batches_per_step": len(batches)},
+            "gpu_launches": last["launches"],
+            "collectives": {"per_step": 2 * len(batches) if world > 1 else 0, "nccl_version": last["nccl"],
+                            "max_reduce_bytes_per_step": last["max_bytes"], "min_reduce_bytes_per_step": last["min_bytes"],
+                            "max_reduce_ms_per_step": float(t[1]) / steps, "min_reduce_ms_per_step": float(t[2]) / steps,
+                            "share_of_step": (float(t[1]) + float(t[2])) / steps / (sec * 1e3),
+                            "note": "stream time between the events around each ncclAllReduce (MAX over ranks): includes "
+                                    "waiting for the slowest rank's phase"}}
 
 
 def main():
@@ -679,30 +762,54 @@ def main():
     ap.add_argument("--window", default="reference", choices=["reference", "bytes", "records"])
     ap.add_argument("--window-bytes", type=int, default=12_500_000)
     ap.add_argument("--ref-pages", type=int, default=100, help="bounded sample for the CPU reference leg: pages per instance")
+    ap.add_argument("--ref-records", type=int, default=5000, help="CPU getitem leg: C3 records per instance")
+    ap.add_argument("--ref-keys", type=int, default=30000, help="CPU contains leg: C4 keys per instance")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference instances run side by side (0 = one per host core)")
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--mode", default="partition", choices=["partition", "shard", "getitem", "lookup"],
-                    help="partition: one store per GPU, corpus partitioned by key (default, weak scaling); "
-                         "shard: one extended window sharded over the GPUs with NCCL reduces (config 5 style)")
+    ap.add_argument("--no-read-side", action="store_true", help="mode all: skip the getitem_c3 / lookup_c4 sub-records")
+    ap.add_argument("--mode", default="all", choices=["all", "setitem", "partition", "shard", "getitem", "lookup"],
+                    help="all: headline setitem line + getitem_c3 / lookup_c4 (and, N > 1, sharded) sub-records; "
+                         "setitem (= partition): the headline alone; getitem / lookup / shard: that record as the line")
     ap.add_argument("--batch-pages", type=int, default=256)
+    ap.add_argument("--shard-pages", type=int, default=3000, help="sharded mode: pages of the corpus (same on every rank)")
+    ap.add_argument("--shard-window-bytes", type=int, default=64_000_000, help="sharded mode: window bytes per GPU")
     ap.add_argument("--workload", default="c3", choices=["c2", "c3"], help="--mode getitem: which corpus to decode")
-    ap.add_argument("--keys", type=int, default=10_000_000, help="--mode lookup: keys stored and queried per GPU")
-    ap.add_argument("--records", type=int, default=1_000_000, help="--mode getitem --workload c3: records per GPU")
+    ap.add_argument("--keys", type=int, default=10_000_000, help="lookup: keys stored and queried per GPU")
+    ap.add_argument("--records", type=int, default=1_000_000, help="getitem c3: records per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
-    elif args.mode == "shard":
-        run_sharded(args, rank, world, local_rank)
+        return
+    env = Env(rank, world, local_rank)
+    base = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "vs_baseline": None, "dtype": "u8", "data": "synthetic"}
+    if args.mode == "shard":
+        line = dict(base, **bench_sharded(args, env))
     elif args.mode == "getitem":
-        run_getitem(args, rank, world, local_rank)
+        line = dict(base, **bench_getitem(args, env, args.workload))
     elif args.mode == "lookup":
-        run_lookup(args, rank, world, local_rank)
+        line = dict(base, **bench_lookup(args, env))
     else:
-        run_ours(args, rank, world, local_rank)
+        line = bench_setitem(args, env)
+        if args.mode == "all" and not args.no_read_side:
+            for name, fn in (("getitem_c3", lambda: bench_getitem(args, env, "c3")), ("lookup_c4", lambda: bench_lookup(args, env))):
+                try:
+                    line[name] = fn()
+                except SystemExit as e:   # a failed parity check of a sub-record must be visible, not fatal to the headline
+                    line[name] = {"error": str(e)}
+                except Exception as e:
+                    line[name] = {"error": repr(e)}
+        if args.mode == "all" and world > 1:
+            try:
+                line["sharded"] = bench_sharded(args, env)
+            except Exception as e:
+                line["sharded"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    env.close()
 
 
 if __name__ == "__main__":

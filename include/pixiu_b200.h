@@ -40,6 +40,7 @@ typedef struct pixiu_store pixiu_store;
 #define PIXIU_ENOSPC (-4)      /* caller buffer too small; required size reported */
 #define PIXIU_ECORRUPT (-5)    /* malformed encoded record */
 #define PIXIU_EINTERNAL (-6)
+#define PIXIU_EPOISONED (-7)   /* an earlier update failed half way (CUDA error, ...): the store refuses further calls; destroy it */
 
 #define PIXIU_CBT_SET_REPLACE 1   /* data_struct/CritBitTree.h:7 */
 #define PIXIU_CBT_DEL_NOT_FOUND 1 /* data_struct/CritBitTree.h:8 */
@@ -72,6 +73,12 @@ typedef struct pixiu_stats {
     double last_lookup_gpu_ms;
     int64_t reinserted_records; /* records moved by pixiu_reinsert_chunk / the auto_reinsert trigger so far */
     int64_t reclaimable_bytes;  /* encoded bytes of dropped chunks (still resident; freed by export + import) */
+    /* memory the CritBit index holds BESIDE the compressed store (the reference verifies a key by decoding the record,
+     * CritBitTree.cpp:154-178; this index keeps esc(k) 251 0 of every leaf instead - these bytes are the price) */
+    int64_t index_key_arena_bytes; /* escaped keys of the leaves (one copy on the host, one in HBM) */
+    int64_t index_host_bytes;      /* host arrays: nodes, leaves, key arena */
+    int64_t index_device_bytes;    /* their device mirror (allocated capacity) */
+    int64_t table_device_bytes;    /* record tables + decode tile descriptors in HBM (allocated capacity) */
 } pixiu_stats;
 
 void pixiu_default_config(pixiu_config *cfg);
@@ -148,6 +155,30 @@ int pixiu_mg_setitem_begin(pixiu_store *s, int64_t n, const uint8_t *keys, const
                            const int64_t *val_off, uint32_t **d_m, int64_t *count);
 int pixiu_mg_setitem_mid(pixiu_store *s, uint32_t **d_cand, int64_t *count);
 int pixiu_mg_setitem_end(pixiu_store *s, int32_t *rc, int32_t *saved);
+
+/* The same three phases with the two collectives issued INSIDE the library: ncclAllReduce(MAX) / ncclAllReduce(MIN) on
+ * the store's own stream, no host synchronisation between a phase and its collective, no PyTorch.  NCCL is bound at
+ * run time (libnccl.so.2, or the path in PIXIU_NCCL_LIB; a copy already loaded by the process is shared).
+ *   rank 0:      pixiu_mg_unique_id(s, id)  -> broadcast the 128 bytes to the other ranks by any means
+ *   every rank:  pixiu_mg_comm_init(s, rank, world, id)   (collective: ncclCommInitRank; implies pixiu_mg_config)
+ *   every rank:  pixiu_mg_setitem_batch(s, <the same batch>)   (collective)
+ * Replaces the single window of SuffixTree::setitem (SuffixTree.cpp:291-304) for BASELINE config 5. */
+#define PIXIU_NCCL_UNIQUE_ID_BYTES 128
+int pixiu_mg_unique_id(pixiu_store *s, uint8_t *id /* [PIXIU_NCCL_UNIQUE_ID_BYTES] */);
+int pixiu_mg_comm_init(pixiu_store *s, int rank, int world, const uint8_t *id);
+int pixiu_mg_setitem_batch(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off, const uint8_t *vals,
+                           const int64_t *val_off, int32_t *rc, int32_t *saved);
+typedef struct pixiu_mg_stats {
+    int32_t rank, world;
+    int32_t nccl_version;       /* ncclGetVersion, 0 when the collectives are played by the caller */
+    int32_t pad;
+    int64_t batches;            /* pixiu_mg_setitem_batch calls so far */
+    int64_t max_reduce_bytes;   /* payload of the MAX all-reduces so far (4 B per batch position) */
+    int64_t min_reduce_bytes;   /* payload of the MIN all-reduces so far (4 B per long run) */
+    double max_reduce_ms;       /* their time on the store's stream (CUDA events; includes waiting for the slowest rank) */
+    double min_reduce_ms;
+} pixiu_mg_stats;
+int pixiu_mg_get_stats(pixiu_store *s, pixiu_mg_stats *out);
 
 /* Per-kernel-class device timing (CUDA events on the store's stream), for the roofline report.
  * enable(1) resets the counters; get() returns 1 once cls is past the last class. `bytes` are the

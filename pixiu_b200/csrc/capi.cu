@@ -10,6 +10,7 @@
 namespace pixiu {
 
 Store::~Store() {
+    if (mg_comm) mg_comm_free(mg_comm);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (ev_nodes) cudaEventDestroy(ev_nodes);
@@ -73,19 +74,46 @@ struct pixiu_store {
 };
 
 namespace {
+// what an entry point does to the store decides when it may run (see Store::dirty / poisoned, and the multi-GPU
+// phases, which keep a half-encoded batch between calls):
+//   G_READ    lookups / decodes / exports: refused while a multi-GPU batch is between its phases (they would reuse its
+//             scratch) and on a poisoned store
+//   G_INDEX   delitem: the same (it changes the replicated index only)
+//   G_PLAIN   single-GPU setitem / import / rotate / reinsert: also refused once the store is a multi-GPU shard
+//             (they would desynchronise the global record numbering of the ranks)
+//   G_MG      the multi-GPU phases themselves
+enum GuardKind { G_READ = 0, G_INDEX = 1, G_PLAIN = 2, G_MG = 3 };
+
 template <typename F>
-int guarded(pixiu_store *h, F &&f) {
+int guarded(pixiu_store *h, F &&f, GuardKind kind = G_READ) {
     if (!h) return PIXIU_EINVAL;
-    try {
-        cudaSetDevice(h->s.cfg.device);
-        return f(h->s);
-    } catch (const pixiu::CudaError &e) {
-        h->s.err = e.what();
-        return PIXIU_ECUDA;
-    } catch (const std::exception &e) {
-        h->s.err = e.what();
-        return PIXIU_EINTERNAL;
+    Store &S = h->s;
+    if (S.poisoned) {
+        if (S.err.rfind("store poisoned", 0) != 0) S.err = "store poisoned by an earlier failed update: " + S.err;
+        return PIXIU_EPOISONED;
     }
+    if (kind != G_MG && S.mg_pending) {
+        S.err = "a multi-GPU setitem batch is between its phases (pixiu_mg_setitem_begin without _end)";
+        return PIXIU_EINVAL;
+    }
+    if (kind == G_PLAIN && S.mg_world > 0) {
+        S.err = "store is a multi-GPU window shard (pixiu_mg_config): use the pixiu_mg_* entry points to change it";
+        return PIXIU_EINVAL;
+    }
+    int rc;
+    try {
+        cudaSetDevice(S.cfg.device);
+        rc = f(S);
+    } catch (const pixiu::CudaError &e) {
+        S.err = e.what();
+        rc = PIXIU_ECUDA;
+    } catch (const std::exception &e) {
+        S.err = e.what();
+        rc = PIXIU_EINTERNAL;
+    }
+    if (rc < 0 && S.dirty) S.poisoned = true;  // the update stopped half way: nothing may run on this state
+    if (rc >= 0) S.dirty = S.mg_pending != 0;  // (a multi-GPU batch between its phases is a half-built window)
+    return rc;
 }
 
 // stage a packed host batch on the device: returns rebased offsets on the device
@@ -169,6 +197,9 @@ int64_t reinsert_chunk(Store &S, int64_t c) {
     if (S.win_open && c == (int64_t) S.n_chunks() - 1) return PIXIU_EINVAL;  // never the open chunk (PiXiuCtrl.cpp:26)
     if (S.chunk_dropped.size() < S.n_chunks()) S.chunk_dropped.resize(S.n_chunks(), 0);
     if (S.chunk_dropped[c]) return 0;
+    // the tombstones of the moved records make c the candidate again: another chunk that was waiting for its
+    // compaction must not be forgotten (the reference saves and restores Glob_Reinsert_Chunk, PiXiuCtrl.cpp:90,:112)
+    const int64_t saved_candidate = S.reinsert_candidate;
     std::vector<uint32_t> recs;
     std::vector<uint64_t> offs(1, 0);
     const uint32_t g0 = S.chunk_first[c], cnt = S.chunk_count[c];
@@ -230,13 +261,14 @@ int64_t reinsert_chunk(Store &S, int64_t c) {
     S.reinserted_records += n;
     const uint32_t gl = g0 + cnt - 1;
     if (cnt) S.reclaimable_bytes += (int64_t) (S.h_enc_off[gl] + S.h_enc_len[gl] - S.h_enc_off[g0]);
-    if (S.reinsert_candidate == c) S.reinsert_candidate = -1;
+    S.reinsert_candidate = saved_candidate == c ? -1 : saved_candidate;
     return n;
 }
 
 // the reference's trigger (PiXiuCtrl.cpp:7-8,:26-29,:64-67): a chunk that a tombstone left below 0.8 x 65,535 live
 // records is remembered; it is re-inserted as soon as it is not the open chunk and less than half of it is live
 int64_t maybe_reinsert(Store &S) {
+    if (S.mg_world > 0) return 0;  // (a multi-GPU shard is only changed through the pixiu_mg_* phases)
     const int64_t c = S.reinsert_candidate;
     if (c < 0 || c >= (int64_t) S.n_chunks()) return 0;
     if (S.win_open && c == (int64_t) S.n_chunks() - 1) return 0;
@@ -289,7 +321,7 @@ int64_t pixiu_reinsert_chunk(pixiu_store *h, int64_t chunk) {
     int rc = guarded(h, [&](Store &S) -> int {
         moved = reinsert_chunk(S, chunk);
         return moved < 0 ? (int) moved : PIXIU_OK;
-    });
+    }, G_PLAIN);
     return rc == PIXIU_OK ? moved : rc;
 }
 
@@ -318,6 +350,11 @@ int pixiu_get_stats(pixiu_store *h, pixiu_stats *o) {
     o->last_lookup_gpu_ms = S.last_lookup_ms;
     o->reinserted_records = S.reinserted_records;
     o->reclaimable_bytes = S.reclaimable_bytes;
+    o->index_key_arena_bytes = (int64_t) S.index->key_arena_bytes();
+    o->index_host_bytes = (int64_t) S.index->host_bytes();
+    o->index_device_bytes = (int64_t) S.index->device_bytes();
+    o->table_device_bytes = (int64_t) (S.d_enc_off.cap * 8 + (S.d_enc_len.cap + S.d_dec_len.cap + S.d_first.cap + S.d_tile_base.cap +
+                                                               S.d_tile_desc.cap) * 4);
     return PIXIU_OK;
 }
 
@@ -334,7 +371,7 @@ int pixiu_setitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const in
         stage(S, n, keys, key_off, S.in_keys, S.in_koff);
         stage(S, n, vals, val_off, S.in_vals, S.in_voff);
         return S.setitem_batch(n, S.in_keys.p, S.in_koff.p, S.in_vals.p, S.in_voff.p, keys, key_off, val_off, rc, saved);
-    });
+    }, G_PLAIN);
 }
 
 int pixiu_setitem_batch_dev(pixiu_store *h, int64_t n, const uint8_t *d_keys, const int64_t *d_key_off,
@@ -356,7 +393,7 @@ int pixiu_setitem_batch_dev(pixiu_store *h, int64_t n, const uint8_t *d_keys, co
         PX_CUDA(cudaMemcpyAsync(hk.data(), d_keys, (size_t) koff[n], cudaMemcpyDeviceToHost, S.st));
         PX_CUDA(cudaStreamSynchronize(S.st));
         return S.setitem_batch(n, d_keys, d_key_off, d_vals, d_val_off, hk.data(), koff.data(), voff.data(), rc, saved);
-    });
+    }, G_PLAIN);
 }
 
 int pixiu_contains_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, uint8_t *found) {
@@ -401,7 +438,7 @@ int pixiu_delitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const in
             if (rc) rc[i] = r >= 0 ? 0 : PIXIU_CBT_DEL_NOT_FOUND;
         }
         return PIXIU_OK;
-    });
+    }, G_INDEX);
 }
 
 int pixiu_getitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, uint8_t *out,
@@ -502,7 +539,7 @@ int64_t pixiu_import_chunk(pixiu_store *h, int64_t n, const uint8_t *enc, const 
             S.doc_bytes += len;
         }
         return PIXIU_OK;
-    });
+    }, G_PLAIN);
     return rc == PIXIU_OK ? chunk_id : rc;
 }
 
@@ -518,25 +555,57 @@ int pixiu_mg_setitem_begin(pixiu_store *h, int64_t n, const uint8_t *keys, const
     return guarded(h, [&](Store &S) -> int {
         if (n <= 0 || !keys || !offsets_ok(n, key_off) || !offsets_ok(n, val_off) || !d_m || !count) return PIXIU_EINVAL;
         if (val_off[n] > val_off[0] && !vals) return PIXIU_EINVAL;
-        if (S.cfg.auto_reinsert) {
-            int64_t m = maybe_reinsert(S);
-            if (m < 0) return (int) m;
-        }
-        stage(S, n, keys, key_off, S.in_keys, S.in_koff);
-        stage(S, n, vals, val_off, S.in_vals, S.in_voff);
-        return S.mg_begin(n, S.in_keys.p, S.in_koff.p, S.in_vals.p, S.in_voff.p, keys, key_off, val_off, d_m, count);
-    });
+        stage(S, n, keys, key_off, S.mg_in_keys, S.mg_in_koff);
+        stage(S, n, vals, val_off, S.mg_in_vals, S.mg_in_voff);
+        return S.mg_begin(n, S.mg_in_keys.p, S.mg_in_koff.p, S.mg_in_vals.p, S.mg_in_voff.p, keys, key_off, val_off, d_m, count);
+    }, G_MG);
 }
 
 int pixiu_mg_setitem_mid(pixiu_store *h, uint32_t **d_cand, int64_t *count) {
     return guarded(h, [&](Store &S) -> int {
         if (!d_cand || !count) return PIXIU_EINVAL;
         return S.mg_mid(d_cand, count);
-    });
+    }, G_MG);
 }
 
 int pixiu_mg_setitem_end(pixiu_store *h, int32_t *rc, int32_t *saved) {
-    return guarded(h, [&](Store &S) -> int { return S.mg_end(rc, saved); });
+    return guarded(h, [&](Store &S) -> int { return S.mg_end(rc, saved); }, G_MG);
+}
+
+int pixiu_mg_unique_id(pixiu_store *h, uint8_t *id) {
+    if (!id) return PIXIU_EINVAL;
+    std::string e;
+    const int r = pixiu::mg_unique_id(id, e);
+    if (r != PIXIU_OK) {
+        if (h) h->s.err = e;
+        else fprintf(stderr, "pixiu_mg_unique_id: %s\n", e.c_str());
+    }
+    return r;
+}
+
+int pixiu_mg_comm_init(pixiu_store *h, int rank, int world, const uint8_t *id) {
+    return guarded(h, [&](Store &S) -> int {
+        if (!id) return PIXIU_EINVAL;
+        return pixiu::mg_comm_init(S, rank, world, id);
+    }, G_MG);
+}
+
+int pixiu_mg_setitem_batch(pixiu_store *h, int64_t n, const uint8_t *keys, const int64_t *key_off, const uint8_t *vals,
+                           const int64_t *val_off, int32_t *rc, int32_t *saved) {
+    return guarded(h, [&](Store &S) -> int {
+        if (n <= 0 || !keys || !offsets_ok(n, key_off) || !offsets_ok(n, val_off)) return PIXIU_EINVAL;
+        if (val_off[n] > val_off[0] && !vals) return PIXIU_EINVAL;
+        stage(S, n, keys, key_off, S.mg_in_keys, S.mg_in_koff);
+        stage(S, n, vals, val_off, S.mg_in_vals, S.mg_in_voff);
+        return pixiu::mg_setitem_nccl(S, n, S.mg_in_keys.p, S.mg_in_koff.p, S.mg_in_vals.p, S.mg_in_voff.p, keys, key_off,
+                                      val_off, rc, saved);
+    }, G_MG);
+}
+
+int pixiu_mg_get_stats(pixiu_store *h, pixiu_mg_stats *o) {
+    if (!h || !o) return PIXIU_EINVAL;
+    pixiu::mg_comm_stats(h->s, o);
+    return PIXIU_OK;
 }
 
 int pixiu_profile_enable(pixiu_store *h, int on) {
@@ -581,7 +650,7 @@ int pixiu_rotate(pixiu_store *h) {
     return guarded(h, [&](Store &S) -> int {
         if (S.win_open) S.close_window();
         return PIXIU_OK;
-    });
+    }, G_PLAIN);
 }
 
 }  // extern "C"

@@ -1118,6 +1118,7 @@ int64_t Store::import_chunk(int64_t n, const uint8_t *enc, const int64_t *enc_of
     }
     const size_t g0 = n_records();
     const uint64_t bytes = (uint64_t) (enc_off[n] - enc_off[0]);
+    dirty = true;  // validation is over: from here on the record tables change
     grow_record_tables(g0 + n, enc_bytes + bytes, tiles);
     chunk_first.push_back((uint32_t) g0);
     chunk_count.push_back((uint32_t) n);

@@ -1471,6 +1471,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     const size_t g_batch_first = n_records();
     const bool ref_policy = cfg.rotate_policy == PIXIU_ROTATE_REFERENCE;
     uint32_t a = 0;
+    dirty = true;  // from here on the window, the record tables and the index change: a failure poisons the store
     while (a < nn) {
         if (win_open) {
             bool full = win_R >= MAX_CHUNK_RECS;
@@ -1560,7 +1561,8 @@ k_apply_m(const uint32_t *__restrict__ in, uint32_t s0, uint32_t m, uint32_t *__
 }
 
 int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals, const int64_t *d_voff,
-                    const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff, uint32_t **d_m, int64_t *count) {
+                    const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff, uint32_t **d_m, int64_t *count,
+                    bool sync) {
     if (mg_world < 1 || mg_pending) return PIXIU_EINVAL;
     if (n <= 0 || n > (int64_t) MAX_CHUNK_RECS) return PIXIU_EINVAL;  // a batch must fit one chunk
     if (cfg.rotate_policy == PIXIU_ROTATE_REFERENCE) {
@@ -1590,7 +1592,14 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
     }
     // rotation is decided from global counters only, so every rank takes the same decision
     const uint64_t byte_budget = cfg.rotate_policy == PIXIU_ROTATE_BYTES ? (uint64_t) cfg.window_bytes * mg_world : ~0ull;
-    if (win_open && (mg_gR + nn > MAX_CHUNK_RECS || (mg_gbytes && mg_gbytes + batch_bytes > byte_budget))) close_window();
+    const bool rotate = win_open && (mg_gR + nn > MAX_CHUNK_RECS || (mg_gbytes && mg_gbytes + batch_bytes > byte_budget));
+    // the sort's look-back words carry 30-bit counts (checked before anything changes)
+    if ((rotate || !win_open ? 0ull : (uint64_t) win_N) + batch_bytes >= (1ull << 30) - (1ull << 17)) {
+        err = "multi-GPU setitem: shard + batch exceed 2^30 window positions";
+        return PIXIU_EINVAL;
+    }
+    dirty = true;
+    if (rotate) close_window();
     if (!win_open) {
         open_window();
         mg_gR = 0;
@@ -1606,7 +1615,6 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
         h_win_rec_start.push_back((uint32_t) bytes);
         mg_h_gidx.push_back((uint16_t) (mg_gR + i));
     }
-    if (bytes >= (1ull << 30) - (1ull << 17)) return PIXIU_EINVAL;
     const uint32_t newN = (uint32_t) bytes;
     w_text.reserve_keep(newN + 16, win_N, st);
     w_dist.reserve_keep(newN + 16, win_N, st);
@@ -1625,7 +1633,7 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
     es.mg_m.reserve_discard(m + 1);
     k_extract_m<<<div_up<uint32_t>(m, 256), 256, 0, st>>>(es.reach.p, ep_s0, m, es.mg_m.p);
     launches++;
-    PX_CUDA(cudaStreamSynchronize(st));
+    if (sync) PX_CUDA(cudaStreamSynchronize(st));
     // keep what the later phases need
     mg_d_keys = d_keys;
     mg_d_koff = d_koff;
@@ -1645,7 +1653,7 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
     return PIXIU_OK;
 }
 
-int Store::mg_mid(uint32_t **d_cand, int64_t *count) {
+int Store::mg_mid(uint32_t **d_cand, int64_t *count, bool sync) {
     if (mg_pending != 1) return PIXIU_EINVAL;
     EncodeScratch &E = es;
     const uint32_t s0 = ep_s0, N = ep_N, m = N - s0;
@@ -1676,7 +1684,7 @@ int Store::mg_mid(uint32_t **d_cand, int64_t *count) {
                                                              cfg.strict251, E.mg_cand.p);
         launches++;
     }
-    PX_CUDA(cudaStreamSynchronize(st));
+    if (sync) PX_CUDA(cudaStreamSynchronize(st));
     mg_pending = 2;
     *d_cand = E.mg_cand.p;
     *count = nruns;

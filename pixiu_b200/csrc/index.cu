@@ -174,36 +174,46 @@ int64_t HostIndex::del(const uint8_t *q, uint32_t qlen) {
     return rec;
 }
 
-void HostIndex::iter_rec(int32_t p, const uint8_t *pre, uint32_t plen, bool include_all, bool &harvest, bool &stop,
-                         std::vector<uint32_t> &out) const {
-    if (stop) return;
-    if (p < 0) {
-        int32_t s = ~p;
-        if (!harvest) {
-            if (leaf_klen[s] < plen || memcmp(arena.data() + leaf_koff[s], pre, plen) != 0) {
-                stop = true;  // CBTGHelper yields NULL and CBTGen stops (CritBitTree.h:76-79,:145-147)
-                return;
-            }
-            harvest = true;
-        }
-        out.push_back(leaf_rec[s]);
-        return;
-    }
-    if (!include_all && diff_at[p] >= plen) include_all = true;
-    if (include_all) {
-        iter_rec(child[0][p], pre, plen, true, harvest, stop, out);
-        iter_rec(child[1][p], pre, plen, true, harvest, stop, out);
-    } else {
-        iter_rec(child[dir_of(p, pre, plen)][p], pre, plen, false, harvest, stop, out);
-    }
-}
-
+// In-order walk below the prefix (CBTGen / CBTGHelper, CritBitTree.h:55-157) with an explicit stack: the depth of a
+// CritBit tree is bounded only by the key bits (keys a, aa, aaa, ... chain one node per key), so recursion could
+// overflow the host stack on ~100k chained keys.
 void HostIndex::iter(const uint8_t *prefix, uint32_t plen, std::vector<uint32_t> &out) const {
     out.clear();
     if (!has_root) return;
-    bool harvest = false, stop = false;
-    // explicit stack would be safer for 65k-byte keys; tree depth is bounded by key bits
-    iter_rec(root, prefix, plen, false, harvest, stop, out);
+    bool harvest = false;
+    std::vector<std::pair<int32_t, bool>> stack;  // (node or ~leaf, whole subtree lies below the prefix)
+    stack.emplace_back(root, false);
+    while (!stack.empty()) {
+        const int32_t p = stack.back().first;
+        bool include_all = stack.back().second;
+        stack.pop_back();
+        if (p < 0) {
+            const int32_t s = ~p;
+            if (!harvest) {
+                // CBTGHelper yields NULL and CBTGen stops (CritBitTree.h:76-79,:145-147)
+                if (leaf_klen[s] < plen || memcmp(arena.data() + leaf_koff[s], prefix, plen) != 0) return;
+                harvest = true;
+            }
+            out.push_back(leaf_rec[s]);
+            continue;
+        }
+        if (!include_all && diff_at[p] >= plen) include_all = true;
+        if (include_all) {
+            stack.emplace_back(child[1][p], true);  // (popped after the whole left subtree)
+            stack.emplace_back(child[0][p], true);
+        } else {
+            stack.emplace_back(child[dir_of(p, prefix, plen)][p], false);
+        }
+    }
+}
+
+size_t HostIndex::host_bytes() const {
+    return child[0].capacity() * 8 + diff_at.capacity() * 2 + mask.capacity() + leaf_rec.capacity() * 4 + leaf_klen.capacity() * 4 +
+           leaf_koff.capacity() * 8 + arena.capacity();
+}
+size_t HostIndex::device_bytes() const {
+    return d_child0.cap * 4 + d_child1.cap * 4 + d_diff.cap * 2 + d_mask.cap + d_leaf_rec.cap * 4 + d_leaf_klen.cap * 4 +
+           d_leaf_koff.cap * 8 + d_keys.cap + d_nodes.cap * 16 + d_leaves.cap * 16;
 }
 
 // packed copy of the inner nodes for the walks: {child0, child1, diff_at | mask << 16, 0} - one 16-byte load (one

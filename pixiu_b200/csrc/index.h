@@ -32,6 +32,11 @@ class HostIndex {
     // record ids of all keys starting with the escaped prefix, ascending key order (CritBitTree.h:55-157)
     void iter(const uint8_t *prefix, uint32_t plen, std::vector<uint32_t> &out) const;
     size_t size() const { return n_live; }
+    // memory the index holds beside the compressed store: host arrays (nodes, leaves, escaped-key arena) and their
+    // device mirror (SoA + packed walk copy + key arena)
+    size_t host_bytes() const;
+    size_t device_bytes() const;
+    size_t key_arena_bytes() const { return arena.size(); }
 
     // ---- device mirror ----
     struct DeviceView {
@@ -108,8 +113,6 @@ class HostIndex {
         uint8_t b = qlen > diff_at[node] ? q[diff_at[node]] : 0;
         return (1 + (mask[node] | b)) >> 8;
     }
-    void iter_rec(int32_t p, const uint8_t *pre, uint32_t plen, bool include_all, bool &harvest, bool &stop,
-                  std::vector<uint32_t> &out) const;
 };
 
 struct Store;

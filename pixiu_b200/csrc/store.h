@@ -44,6 +44,8 @@ struct MinTree {
 };
 
 class HostIndex;  // CritBit (index.cu)
+struct MgComm;    // NCCL communicator + collective statistics of a multi-GPU shard (mgcomm.cu)
+void mg_comm_free(MgComm *c);
 
 struct EncodeScratch {
     DevBuf<uint64_t> keys0, keys1;
@@ -68,6 +70,11 @@ struct Store {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_nodes = nullptr;
     std::string err;
+    // A mutating call that fails after its first change (CUDA error, sticky scan time-out, late argument error) leaves
+    // records that are not indexed, or a half-built window: `dirty` is raised at the first change of such a call and
+    // lowered when it completes; a call that ends with `dirty` still raised poisons the store, and every later entry
+    // point answers PIXIU_EPOISONED instead of running on that state.
+    bool dirty = false, poisoned = false;
     int64_t launches = 0;
     Profiler prof;
     double last_set_ms = 0, last_get_ms = 0, last_lookup_ms = 0;
@@ -143,6 +150,9 @@ struct Store {
     // ---- staging for batches ----
     DevBuf<uint8_t> in_keys, in_vals, out_stage;
     DevBuf<int64_t> in_koff, in_voff;
+    // the multi-GPU phases keep their batch across calls: own staging, never touched by lookups (which reuse in_*)
+    DevBuf<uint8_t> mg_in_keys, mg_in_vals;
+    DevBuf<int64_t> mg_in_koff, mg_in_voff;
     DevBuf<uint32_t> doc_len, doc_off;
 
     Store() = default;
@@ -172,6 +182,7 @@ struct Store {
                       const uint32_t *h_doc_len, int32_t *rc, int32_t *saved);
     // multi-GPU extended window (encode.cu, "Multi-GPU extended window")
     int mg_rank = 0, mg_world = 0, mg_pending = 0;
+    MgComm *mg_comm = nullptr;   // set by pixiu_mg_comm_init: the collectives run inside the library (mgcomm.cu)
     uint32_t mg_gR = 0;          // records of the open chunk over all ranks
     uint64_t mg_gbytes = 0, mg_batch_bytes = 0;
     std::vector<uint16_t> mg_h_gidx;  // chunk index of every local window record
@@ -181,8 +192,10 @@ struct Store {
     const uint8_t *mg_d_keys = nullptr, *mg_d_vals = nullptr;
     const int64_t *mg_d_koff = nullptr, *mg_d_voff = nullptr;
     int mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals, const int64_t *d_voff,
-                 const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff, uint32_t **d_m, int64_t *count);
-    int mg_mid(uint32_t **d_cand, int64_t *count);
+                 const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff, uint32_t **d_m, int64_t *count,
+                 bool sync = true);
+    // (sync: the caller issues the collective from another stream / library, so the phase ends synchronised)
+    int mg_mid(uint32_t **d_cand, int64_t *count, bool sync = true);
     int mg_end(int32_t *rc, int32_t *saved);
     void count_nodes_enqueue(uint32_t s0, uint32_t N);
     uint32_t count_nodes_and_cut(uint32_t first_new, uint32_t s0, uint32_t N);
@@ -195,5 +208,13 @@ struct Store {
                      const std::map<uint32_t, uint32_t> *known_max);
     int64_t import_chunk(int64_t n, const uint8_t *enc, const int64_t *enc_off);
 };
+
+// mgcomm.cu
+int mg_unique_id(uint8_t *id, std::string &err);
+int mg_comm_init(Store &S, int rank, int world, const uint8_t *id);
+int mg_setitem_nccl(Store &S, int64_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *d_vals,
+                    const int64_t *d_voff, const uint8_t *h_keys, const int64_t *h_koff, const int64_t *h_voff,
+                    int32_t *rc, int32_t *saved);
+void mg_comm_stats(const Store &S, pixiu_mg_stats *o);
 
 }  // namespace pixiu

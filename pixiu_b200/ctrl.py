@@ -23,7 +23,8 @@ _u32p = C.POINTER(C.c_uint32)
 _i64p = C.POINTER(C.c_int64)
 _u64p = C.POINTER(C.c_uint64)
 
-OK, EINVAL, ETOOLONG, ECUDA, ENOSPC, ECORRUPT, EINTERNAL = 0, -1, -2, -3, -4, -5, -6
+OK, EINVAL, ETOOLONG, ECUDA, ENOSPC, ECORRUPT, EINTERNAL, EPOISONED = 0, -1, -2, -3, -4, -5, -6, -7
+NCCL_UNIQUE_ID_BYTES = 128
 CBT_SET_REPLACE = 1
 CBT_DEL_NOT_FOUND = 1
 ROTATE_REFERENCE, ROTATE_BYTES, ROTATE_RECORDS = 0, 1, 2
@@ -40,7 +41,15 @@ class Stats(C.Structure):
                 ("window_bytes", C.c_int64), ("kernel_launches", C.c_int64),
                 ("last_setitem_gpu_ms", C.c_double), ("last_getitem_gpu_ms", C.c_double),
                 ("last_lookup_gpu_ms", C.c_double),
-                ("reinserted_records", C.c_int64), ("reclaimable_bytes", C.c_int64)]
+                ("reinserted_records", C.c_int64), ("reclaimable_bytes", C.c_int64),
+                ("index_key_arena_bytes", C.c_int64), ("index_host_bytes", C.c_int64), ("index_device_bytes", C.c_int64),
+                ("table_device_bytes", C.c_int64)]
+
+
+class MgStats(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("nccl_version", C.c_int32), ("pad", C.c_int32),
+                ("batches", C.c_int64), ("max_reduce_bytes", C.c_int64), ("min_reduce_bytes", C.c_int64),
+                ("max_reduce_ms", C.c_double), ("min_reduce_ms", C.c_double)]
 
 
 EXPORTS = [
@@ -51,6 +60,7 @@ EXPORTS = [
     "pixiu_profile_enable", "pixiu_profile_get", "pixiu_stream",
     "pixiu_reinsert_chunk", "pixiu_chunk_info",
     "pixiu_export_chunk", "pixiu_mg_config", "pixiu_mg_setitem_begin", "pixiu_mg_setitem_mid", "pixiu_mg_setitem_end",
+    "pixiu_mg_unique_id", "pixiu_mg_comm_init", "pixiu_mg_setitem_batch", "pixiu_mg_get_stats",
 ]
 
 _lib = None
@@ -64,6 +74,17 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")
+    if "PIXIU_NCCL_LIB" not in os.environ:
+        # multi-GPU mode binds NCCL at run time: prefer the copy PyTorch bundles (a torchrun process has it loaded
+        # anyway, and two NCCL copies in one process are best avoided); the system libnccl.so.2 is the fallback
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl") if importlib.util.find_spec("nvidia") else None
+        for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["PIXIU_NCCL_LIB"] = cand
+                break
     L = C.CDLL(LIB_PATH)
     L.pixiu_default_config.argtypes = [C.POINTER(Config)]
     L.pixiu_create.argtypes = [C.POINTER(Config)]
@@ -101,6 +122,10 @@ def load_library():
                                          C.POINTER(C.c_void_p), _i64p]
     L.pixiu_mg_setitem_mid.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _i64p]
     L.pixiu_mg_setitem_end.argtypes = [C.c_void_p, _i32p, _i32p]
+    L.pixiu_mg_unique_id.argtypes = [C.c_void_p, C.c_void_p]
+    L.pixiu_mg_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.pixiu_mg_setitem_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32p, _i32p]
+    L.pixiu_mg_get_stats.argtypes = [C.c_void_p, C.POINTER(MgStats)]
     # test hooks
     L.pixiu_debug_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     L.pixiu_debug_sort_pairs.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
@@ -425,6 +450,34 @@ class PiXiuCtrl:
         saved = np.zeros(self._mg_n, dtype=np.int32)
         self._check(self._L.pixiu_mg_setitem_end(self._h, rc.ctypes.data_as(_i32p), saved.ctypes.data_as(_i32p)))
         return rc, saved
+
+    # -- the same with the collectives inside the library (NCCL on the store's stream; pixiu_b200/csrc/mgcomm.cu) --
+    def mg_unique_id(self) -> bytes:
+        """rank 0: a fresh ncclUniqueId (128 bytes) to hand to every rank's mg_comm_init"""
+        buf = (C.c_uint8 * NCCL_UNIQUE_ID_BYTES)()
+        self._check(self._L.pixiu_mg_unique_id(self._h, buf))
+        return bytes(buf)
+
+    def mg_comm_init(self, rank: int, world: int, unique_id: bytes):
+        assert len(unique_id) == NCCL_UNIQUE_ID_BYTES
+        buf = (C.c_uint8 * NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self._L.pixiu_mg_comm_init(self._h, rank, world, buf))
+
+    def mg_setitem_batch(self, keys, vals):
+        """one replicated batch through the sharded window (collective call: every rank, same batch)"""
+        kd, ko = keys if isinstance(keys, tuple) else _pack(keys)
+        vd, vo = vals if isinstance(vals, tuple) else _pack(vals)
+        n = len(ko) - 1
+        rc = np.zeros(n, dtype=np.int32)
+        saved = np.zeros(n, dtype=np.int32)
+        self._check(self._L.pixiu_mg_setitem_batch(self._h, n, _ptr(kd), _ptr(ko), _ptr(vd), _ptr(vo),
+                                                   rc.ctypes.data_as(_i32p), saved.ctypes.data_as(_i32p)))
+        return rc, saved
+
+    def mg_stats(self) -> MgStats:
+        st = MgStats()
+        self._check(self._L.pixiu_mg_get_stats(self._h, C.byref(st)))
+        return st
 
     def profile_enable(self, on: bool = True):
         self._check(self._L.pixiu_profile_enable(self._h, int(on)))

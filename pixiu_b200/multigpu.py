@@ -1,45 +1,54 @@
-"""Multi-GPU extended-window setitem: the two collectives between the C-ABI phases.
+"""Multi-GPU extended-window setitem (BASELINE config 5): rendezvous helpers.
 
-`setitem_sharded(ctrl, keys, vals)` runs one batch through `pixiu_mg_setitem_{begin,mid,end}` and
-issues `all_reduce(MAX)` on the per-position match lengths and `all_reduce(MIN)` on the per-run
-(idx << 16 | to) candidates with torch.distributed (NCCL over NVLink on the GPUs).  The device
-buffers handed out by the library are wrapped as torch tensors without a copy.
+The data plane is inside libpixiu_b200.so: `pixiu_mg_setitem_batch` runs the three encode phases and issues
+`ncclAllReduce(MAX)` on the per-position match lengths and `ncclAllReduce(MIN)` on the per-run
+(idx << 16 | to) candidates on the store's own CUDA stream (pixiu_b200/csrc/mgcomm.cu).  What is left for the
+host program is the usual NCCL bootstrap: rank 0 creates a 128-byte unique id and every rank receives it.  Two
+ways are offered; neither touches the data path:
+
+  init_comm_file(ctrl, rank, world, path)    a file on a shared filesystem (no other dependency)
+  init_comm_torch(ctrl)                      a torch.distributed broadcast, for programs launched by torchrun
 """
 from __future__ import annotations
 
-import torch
-import torch.distributed as dist
+import os
+import time
+
+from .ctrl import NCCL_UNIQUE_ID_BYTES
 
 
-class _DevArray:
-    """__cuda_array_interface__ view of `count` uint32 at a raw device pointer"""
+def init_comm_file(c, rank: int, world: int, path: str, timeout_s: float = 120.0):
+    if rank == 0:
+        uid = c.mg_unique_id()
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(uid)
+        os.replace(tmp, path)
+    else:
+        t0 = time.time()
+        while not (os.path.exists(path) and os.path.getsize(path) == NCCL_UNIQUE_ID_BYTES):
+            if time.time() - t0 > timeout_s:
+                raise TimeoutError(f"no NCCL unique id at {path}")
+            time.sleep(0.01)
+        uid = open(path, "rb").read()
+    c.mg_comm_init(rank, world, uid)
 
-    def __init__(self, ptr: int, count: int):
-        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<u4", "data": (ptr, False), "version": 2}
+
+def init_comm_torch(c, group=None):
+    """bootstrap only: the unique id travels through an existing torch.distributed group (any backend)"""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.zeros(NCCL_UNIQUE_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(c.mg_unique_id()), dtype=torch.uint8).clone()
+    t = t.to(dev)
+    dist.broadcast(t, src=0, group=group)
+    c.mg_comm_init(rank, world, bytes(t.cpu().numpy().tobytes()))
 
 
-def wrap_u32(ptr: int, count: int, device) -> torch.Tensor:
-    # int32 view: torch has no uint32 collectives; MAX on match lengths (< 65536) is sign-safe, MIN on
-    # candidates is made sign-safe by the caller-side bias below
-    return torch.as_tensor(_DevArray(ptr, count), device=device).view(torch.int32)
-
-
-def setitem_sharded(c, keys, vals, device=None, group=None):
+def setitem_sharded(c, keys, vals):
     """one replicated batch through the sharded window; returns (rc, saved) like setitem_batch"""
-    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    p, cnt = c.mg_setitem_begin(keys, vals)
-    if cnt:
-        m = wrap_u32(p, cnt, device)
-        torch.cuda.synchronize(device)
-        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
-        torch.cuda.synchronize(device)
-    p, cnt = c.mg_setitem_mid()
-    if cnt:
-        cand = wrap_u32(p, cnt, device)
-        torch.cuda.synchronize(device)
-        # unsigned MIN through a signed collective: flip the top bit, reduce, flip back
-        cand ^= -0x80000000
-        dist.all_reduce(cand, op=dist.ReduceOp.MIN, group=group)
-        cand ^= -0x80000000
-        torch.cuda.synchronize(device)
-    return c.mg_setitem_end()
+    return c.mg_setitem_batch(keys, vals)

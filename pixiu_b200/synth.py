@@ -86,45 +86,97 @@ def _vocab(rng: Rng, n_words: int) -> list[bytes]:
 _HOSTS = [b"news", b"sports", b"ent", b"finance", b"tech", b"auto"]
 
 
-def _urls(rng: Rng, n: int) -> list[bytes]:
-    """unique keys http://{host}.qq.com/a/{yyyymmdd}/{6 digits}.htm"""
+def _urls_packed(rng: Rng, n: int) -> tuple[np.ndarray, np.ndarray]:
+    """unique keys http://{host}.qq.com/a/{yyyymmdd}/{6 or 8 digits}.htm, packed (vectorised: 10 M keys in seconds)"""
     host = rng.below(n, len(_HOSTS))
     day = rng.below(n, 28) + 1
     month = rng.below(n, 12) + 1
-    # the 6-digit serial is a permutation-like function of i => keys are unique
-    serial = (np.arange(n, dtype=np.int64) * 7919 + 104729) % 1000000 if n <= 1000000 else None
-    out = []
-    for i in range(n):
-        s = serial[i] if serial is not None else i
-        if serial is not None:
-            out.append(b"http://%s.qq.com/a/2016%02d%02d/%06d.htm" % (_HOSTS[host[i]], month[i], day[i], s))
-        else:
-            out.append(b"http://%s.qq.com/a/2016%02d%02d/%08d.htm" % (_HOSTS[host[i]], month[i], day[i], s))
-    return out
+    # the serial is a permutation-like function of i => keys are unique
+    if n <= 1000000:
+        serial, nd = (np.arange(n, dtype=np.int64) * 7919 + 104729) % 1000000, 6
+    else:
+        serial, nd = np.arange(n, dtype=np.int64), 8
+    hl = np.array([len(h) for h in _HOSTS], dtype=np.int64)[host]
+    tail_len = len(b".qq.com/a/2016") + 4 + 1 + nd + len(b".htm")
+    klen = 7 + hl + tail_len
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(klen, out=off[1:])
+    out = np.empty(int(off[-1]), dtype=np.uint8)
+    hpool, hoff = pack(_HOSTS)
+    # fixed-width tail of every key
+    tail = np.empty((n, tail_len), dtype=np.uint8)
+    pre = np.frombuffer(b".qq.com/a/2016", dtype=np.uint8)
+    tail[:, :len(pre)] = pre
+    c = len(pre)
+    tail[:, c] = 48 + month // 10
+    tail[:, c + 1] = 48 + month % 10
+    tail[:, c + 2] = 48 + day // 10
+    tail[:, c + 3] = 48 + day % 10
+    tail[:, c + 4] = ord("/")
+    sv = serial.copy()
+    for d in range(nd - 1, -1, -1):
+        tail[:, c + 5 + d] = 48 + sv % 10
+        sv //= 10
+    tail[:, c + 5 + nd:] = np.frombuffer(b".htm", dtype=np.uint8)
+    head = np.frombuffer(b"http://", dtype=np.uint8)
+    base = off[:-1]
+    for j in range(7):
+        out[base + j] = head[j]
+    for h in range(len(_HOSTS)):
+        sel = np.nonzero(host == h)[0]
+        if len(sel):
+            for j in range(len(_HOSTS[h])):
+                out[base[sel] + 7 + j] = _HOSTS[h][j]
+    tb = base + 7 + hl
+    for j in range(tail_len):
+        out[tb + j] = tail[:, j]
+    return out, off
+
+
+def _urls(rng: Rng, n: int) -> list[bytes]:
+    return unpack(*_urls_packed(rng, n))
 
 
 def gen_urls_kv(n: int = 10000, seed: int = 1, val_words: int = 12):
     """C1 (and C4 with n=10M, val_words≈28): URL keys, `<title>` + words values."""
     rng = Rng(seed)
     vocab = _vocab(rng, 2000)
-    keys = _urls(rng, n)
+    kd, ko = _urls_packed(rng, n)
     vpool, voff = pack(vocab)
     vlen = np.diff(voff)
-    w = rng.below(n * val_words, len(vocab)).reshape(n, val_words)
     head = np.frombuffer(b"<title>", dtype=np.uint8)
     # value i = "<title>" + words joined by single spaces
     sp = np.frombuffer(b" ", dtype=np.uint8)
     pool = np.concatenate([vpool, head, sp])
     h_at, s_at = len(vpool), len(vpool) + len(head)
-    starts = np.empty((n, 2 * val_words), dtype=np.int64)
-    lens = np.empty((n, 2 * val_words), dtype=np.int64)
-    starts[:, 0], lens[:, 0] = h_at, len(head)
-    starts[:, 1::2], lens[:, 1::2] = voff[w], vlen[w]
-    starts[:, 2::2], lens[:, 2::2] = s_at, 1
-    vals = ragged_gather(pool, starts.ravel(), lens.ravel())
+    ctr0 = rng.ctr
+    rng.ctr += n * val_words
+
+    def rows(r0, r1):  # the values of records [r0, r1): the random stream is counter-based, so blocks are independent
+        m = r1 - r0
+        u = splitmix64(np.arange(ctr0 + r0 * val_words, ctr0 + r1 * val_words, dtype=np.uint64), seed)
+        w = ((u >> np.uint64(11)).astype(np.int64) % len(vocab)).reshape(m, val_words)
+        starts = np.empty((m, 2 * val_words), dtype=np.int64)
+        lens = np.empty((m, 2 * val_words), dtype=np.int64)
+        starts[:, 0], lens[:, 0] = h_at, len(head)
+        starts[:, 1::2], lens[:, 1::2] = voff[w], vlen[w]
+        starts[:, 2::2], lens[:, 2::2] = s_at, 1
+        return ragged_gather(pool, starts.ravel(), lens.ravel()), lens.sum(axis=1)
+
+    B = 250000
+    blocks = [(a, min(n, a + B)) for a in range(0, n, B)]
+    if len(blocks) > 1:  # (numpy releases the GIL inside its loops: the 10 M-record corpus of C4 builds on all cores)
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+
+        with ThreadPoolExecutor(max_workers=min(len(blocks), os.cpu_count() or 1)) as ex:
+            parts = list(ex.map(lambda ab: rows(*ab), blocks))
+    else:
+        parts = [rows(*ab) for ab in blocks]
+    vals = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, dtype=np.uint8)
     val_off = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(lens.sum(axis=1), out=val_off[1:])
-    kd, ko = pack(keys)
+    if parts:
+        np.cumsum(np.concatenate([p[1] for p in parts]), out=val_off[1:])
     return kd, ko, vals, val_off
 
 
@@ -217,13 +269,24 @@ def gen_nested(n: int = 1000000, seed: int = 3, rec_len: int = 1000, sprinkle: b
     letters = (65 + rng.below(n + 1, 26)).astype(np.uint8)
     inv13 = pow(13, -1, rec_len)
     p = np.arange(rec_len, dtype=np.int64)
-    first_mut = 1 + (p * inv13) % rec_len          # first record index mutating position p
+    first_mut = (1 + (p * inv13) % rec_len).astype(np.int32)          # first record index mutating position p
     vals = np.empty((n, rec_len), dtype=np.uint8)
     B = 16384
-    for r0 in range(0, n, B):
-        r = np.arange(r0, min(n, r0 + B), dtype=np.int64)[:, None]
+
+    def block(r0):
+        r = np.arange(r0, min(n, r0 + B), dtype=np.int32)[:, None]
         last = r - ((r - first_mut[None, :]) % rec_len)     # latest mutation of p at or before r
         vals[r0:r0 + len(r)] = np.where(last >= 1, letters[np.maximum(last, 0)], base[None, :])
+
+    if n > 4 * B:  # (numpy releases the GIL inside its loops)
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+            list(ex.map(block, range(0, n, B)))
+    else:
+        for r0 in range(0, n, B):
+            block(r0)
     if sprinkle:
         rows = np.arange(0, n, 16)
         per = 1 + rng.below(len(rows), 9)
@@ -233,7 +296,12 @@ def gen_nested(n: int = 1000000, seed: int = 3, rec_len: int = 1000, sprinkle: b
             a, P, L = int(at[j]), int(per[j]), int(ln[j])
             seg = vals[r, a:a + P].copy()
             vals[r, a:a + L] = np.tile(seg, L // P + 1)[:L]
-    keys = [b"key%09d" % i for i in range(n)]
-    kd, ko = pack(keys)
+    kd = np.empty((n, 12), dtype=np.uint8)
+    kd[:, :3] = np.frombuffer(b"key", dtype=np.uint8)
+    iv = np.arange(n, dtype=np.int64)
+    for d in range(8, -1, -1):
+        kd[:, 3 + d] = 48 + iv % 10
+        iv //= 10
+    kd, ko = kd.reshape(-1), np.arange(n + 1, dtype=np.int64) * 12
     val_off = np.arange(n + 1, dtype=np.int64) * rec_len
     return kd, ko, vals.reshape(-1), val_off
