@@ -724,3 +724,61 @@ def test_contains_with_device_resident_queries(ctrl_mod):
     alive = set(keys) - set(keys[::5])
     assert got.tolist() == want.tolist() == [k in alive for k in q]
     c.free_prop()
+
+
+# --------------------------------------------------------------------------- full-corpus pin (BASELINE config[1])
+def test_c2_full_corpus_matches_reference_fixture(ctrl_mod):
+    """All 10,000 pages of the headline workload (bench.py's corpus) through setitem: every record lands in the same
+    window (chunk) at the same idx as in the UNMODIFIED reference, with the same encoded length and the same bytes
+    (CRC32) - i.e. the compression ratio README.md:53 quotes is identical, and so is every rotation point
+    (PiXiuCtrl.cpp:13-17).  Fixture: tests/golden/c2_full_enc_len.npz (tests/golden/make_c2_full.py, ~8 min of the
+    reference on one core)."""
+    import os
+    import zlib
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_full_enc_len.npz"))
+    kd, ko, vd, vo = synth.gen_html_pages(int(g["pages"]), seed=int(g["seed"]))
+    n = len(ko) - 1
+    assert int(ko[-1] + vo[-1]) == int(g["raw_bytes"])
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_REFERENCE, strict251=True)
+    rc, saved = c.setitem_batch((kd, ko), (vd, vo))
+    assert not rc.any()
+    st = c.stats()
+    assert st.chunks == int(g["chunk"][-1]) + 1
+    enc_len = (np.diff(ko) + np.diff(vo) + 4 - saved).astype(np.int64)   # escape-free corpus: doc = k + v + 4
+    assert np.array_equal(enc_len, g["enc_len"].astype(np.int64))
+    assert st.encoded_bytes == int(g["enc_len"].astype(np.int64).sum())
+    r = 0
+    for ch in range(st.chunks):
+        enc, off = c.export_chunk(ch)
+        cnt = len(off) - 1
+        assert np.array_equal(g["chunk"][r:r + cnt], np.full(cnt, ch)) and np.array_equal(g["idx"][r:r + cnt], np.arange(cnt))
+        b = enc.tobytes()
+        crc = np.array([zlib.crc32(b[off[i]:off[i + 1]]) for i in range(cnt)], dtype=np.uint32)
+        assert np.array_equal(crc, g["crc32"][r:r + cnt]), f"window {ch}: encoded bytes differ from the reference"
+        r += cnt
+    assert r == n
+    c.free_prop()
+
+
+# --------------------------------------------------------------------------- guards (ADVICE round 1)
+def test_mg_phase_guards_and_shard_is_not_a_plain_store(ctrl_mod):
+    """while a multi-GPU batch is between its phases every other entry point is refused (they would reuse its
+    scratch); a shard refuses plain setitem / import / rotate / reinsert altogether"""
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
+    c.mg_config(0, 1)
+    keys, vals = [b"alpha", b"beta"], [b"x" * 40, b"y" * 40]
+    c.mg_setitem_begin(keys, vals)
+    for call in (lambda: c.contains(b"alpha"), lambda: c.getitem(b"alpha"), lambda: c.delitem(b"alpha"),
+                 lambda: c.setitem(b"k", b"v"), lambda: c.rotate(), lambda: c.iter_docs(b"")):
+        with pytest.raises(ctrl_mod.PiXiuError) as e:
+            call()
+        assert e.value.code == ctrl_mod.EINVAL
+    c.mg_setitem_mid()
+    rc, _ = c.mg_setitem_end()
+    assert not rc.any()
+    assert c.contains(b"alpha") and c.delitem(b"beta") == 0          # reads and deletes are fine between batches
+    for call in (lambda: c.setitem(b"k", b"v"), lambda: c.rotate(), lambda: c.reinsert(0)):
+        with pytest.raises(ctrl_mod.PiXiuError):
+            call()
+    c.free_prop()
