@@ -16,6 +16,11 @@ int pixiu_debug_memcpy(void *dst, const void *src, int64_t bytes, int kind);
 int pixiu_debug_pool_state(pixiu_store *s, int32_t *nth, int32_t *used);
 /* inner nodes visited by each key's CritBit walk (host index; feeds the algorithmic-bytes figure of the lookup bench) */
 int pixiu_debug_index_depth(pixiu_store *s, int64_t n, const uint8_t *keys, const int64_t *key_off, int32_t *depth);
+/* change a tuning / test knob of a live store ("dec_arena_limit", "piece_cap", "sleep_after", "sleep_ns", "trace", ...;
+ * the environment variables PIXIU_<NAME> set the same knobs when the store is created) */
+int pixiu_debug_set_knob(pixiu_store *s, const char *name, int64_t value);
+/* pending (polled) pieces and drain passes of the last decode call */
+int pixiu_debug_decode_counters(pixiu_store *s, int64_t *pending_pieces, int64_t *drains);
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ Store::~Store() {
 
 void Store::init(const pixiu_config &c) {
     cfg = c;
+    knobs.from_env();
     PX_CUDA(cudaSetDevice(cfg.device));
     PX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     PX_CUDA(cudaEventCreate(&ev0));
@@ -181,7 +182,7 @@ int getitem_common(Store &S, int64_t n, const uint8_t *keys, const int64_t *key_
     }
     const auto t2 = std::chrono::steady_clock::now();
     const int r = decode_to(S, recs, offs, out, out_cap, dev, need);
-    if (getenv("PIXIU_TRACE"))
+    if (S.knobs.trace)
         fprintf(stderr, "[getitem] n=%lld lookup %.3f ms, lists %.3f ms, decode_to %.3f ms\n", (long long) n,
                 std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count());
@@ -693,6 +694,20 @@ int pixiu_debug_sort_pairs(int device, uint64_t *keys, uint32_t *vals, int64_t n
 int pixiu_debug_memcpy(void *dst, const void *src, int64_t bytes, int kind) {
     cudaError_t e = cudaMemcpy(dst, src, (size_t) bytes, kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice);
     return e == cudaSuccess ? PIXIU_OK : PIXIU_ECUDA;
+}
+
+// change a tuning / test knob of a live store (Knobs::set, store.h); returns PIXIU_EINVAL for an unknown name
+int pixiu_debug_set_knob(pixiu_store *h, const char *name, int64_t value) {
+    if (!h || !name) return PIXIU_EINVAL;
+    return h->s.knobs.set(name, value) ? PIXIU_OK : PIXIU_EINVAL;
+}
+
+// pending (polled) pieces and drain passes of the last decode call
+int pixiu_debug_decode_counters(pixiu_store *h, int64_t *pending_pieces, int64_t *drains) {
+    if (!h) return PIXIU_EINVAL;
+    if (pending_pieces) *pending_pieces = (int64_t) h->s.last_pending_pieces;
+    if (drains) *drains = (int64_t) h->s.last_drains;
+    return PIXIU_OK;
 }
 
 // arena state the reference's suffix tree would have for the open window (MemPool::nth, used_num)

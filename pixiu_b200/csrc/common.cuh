@@ -31,6 +31,12 @@ struct CudaError : std::runtime_error {
 template <typename T>
 static inline T div_up(T a, T b) { return (a + b - 1) / b; }
 
+// PIXIU_TRACE, looked at once per process (allocation / phase trace lines on stderr)
+static inline bool trace_on() {
+    static const bool on = getenv("PIXIU_TRACE") != nullptr;
+    return on;
+}
+
 // Growable device array (capacity doubling).  HBM is 180 GB: slack is cheap, realloc is not.
 template <typename T>
 struct DevBuf {
@@ -50,7 +56,7 @@ struct DevBuf {
         if (n <= cap) return;
         release();
         size_t want = n + n / 4 + 256;
-        if (getenv("PIXIU_TRACE")) fprintf(stderr, "[mem] alloc %zu bytes\n", want * sizeof(T));
+        if (trace_on()) fprintf(stderr, "[mem] alloc %zu bytes\n", want * sizeof(T));
         PX_CUDA(cudaMalloc(&p, want * sizeof(T)));
         cap = want;
     }
@@ -59,7 +65,7 @@ struct DevBuf {
         if (n <= cap) return;
         size_t want = std::max<size_t>(2 * cap, n + n / 2 + 256);
         T *q = nullptr;
-        if (getenv("PIXIU_TRACE")) fprintf(stderr, "[mem] grow %zu -> %zu bytes (keep %zu)\n", cap * sizeof(T), want * sizeof(T), keep * sizeof(T));
+        if (trace_on()) fprintf(stderr, "[mem] grow %zu -> %zu bytes (keep %zu)\n", cap * sizeof(T), want * sizeof(T), keep * sizeof(T));
         PX_CUDA(cudaMalloc(&q, want * sizeof(T)));
         if (p && keep) PX_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
         if (p) {

@@ -1,22 +1,30 @@
 // getitem hot path: batched decode of PiXiu-encoded records.
 //
-// Replaces the recursive generator PXSGen::operator() (proj/PiXiuStr.h:110-198), which
-// re-scans the referenced record from its first byte for every back reference and bubbles
-// each byte through one coroutine per nesting level, by ONE data-flow kernel over a flat
-// *decoded arena* (the records of every touched chunk, back to back, u32-addressed):
-//   K10 k_decode_tiles one warp per 2 KiB decode tile (tile descriptors make every tile
-//                      independently parsable), tiles handed out by ticket in arena order:
-//                      251-dispatch of PiXiuStr.h:142-160 in parallel, literal bytes go straight
-//                      to the arena, every reference token becomes a segment (destination,
-//                      source, length; self-overlapping references keep their period) that is
-//                      copied as soon as its source bytes are final.  Finality is tracked per
-//                      byte in a bitmap (1 bit / byte), so the dependency depth is the nesting
-//                      depth of the bytes, not of tiles or records.
-//   K12 k_copy_records only when the caller's layout differs from the arena order.
-// Traffic per decoded byte: the encoded byte or the source byte read once, the byte written
-// once, 1/8 byte of bitmap - no per-byte pointer arrays.
-// Waiting is deadlock-free: a source always precedes its destination in the arena and tickets
-// follow arena order, so the tile owning a source is finished or held by a resident warp.
+// Replaces the recursive generator PXSGen::operator() (proj/PiXiuStr.h:110-198), which re-scans the referenced
+// record from its first byte for every back reference and bubbles each byte through one coroutine per nesting
+// level, by ONE data-flow kernel over a flat *decoded arena* (the records of every touched chunk, back to back,
+// u32-addressed):
+//   K10 k_decode_tiles  one warp per 2 KiB decode tile (tile descriptors make every tile independently parsable),
+//                       tiles handed out by ticket in arena order.  The 251-dispatch of PiXiuStr.h:142-160 runs in
+//                       parallel over the staged encoded bytes; then ONE LANE PER TOKEN writes the literal run in
+//                       front of its reference and the reference itself, every byte exactly once:
+//                         - a reference whose source lies below the chunk's *retired watermark* (everything below it
+//                           is final: the common case, sources of the leftmost-occurrence rule lie far back) is
+//                           copied straight away, no polling;
+//                         - any other reference stays zero and becomes *pending pieces* that copy as soon as
+//                           their source bytes are final.  Finality travels IN BAND: a nonzero byte is final the
+//                           moment it is visible, a final byte whose value is zero is announced in a 1-bit-per-byte
+//                           bitmap that stays all-zero between calls (the words a call dirties are listed and
+//                           cleared again), so the dependency depth is the nesting depth of BYTES.
+//                       No memset of the arena: a tile zeroes ITSELF as it starts (the L2 merges those stores with
+//                       the final bytes that follow) and announces it; a polling tile first makes sure that every
+//                       earlier tile of its chunk has done so (a per-chunk in-order watermark; a second one marks
+//                       the retired prefix).
+//   K12 k_copy_records  only when the caller's layout differs from the arena order.
+// Traffic per decoded byte: the encoded byte or the source byte read once, the byte written once (pending bytes
+// twice, which the L2 absorbs).
+// Waiting is deadlock-free: a source always precedes its destination in the arena and tickets follow arena order,
+// so every tile a warp waits for is finished or held by a resident warp.
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -28,288 +36,692 @@
 namespace pixiu {
 
 constexpr int DEC_WARPS = 4;
+#ifndef PIXIU_DEC_MINB
+#define PIXIU_DEC_MINB 8     // resident CTAs per SM the decode kernel is compiled for (register budget 65536 / (128 x this))
+#endif
 constexpr uint32_t ENC_MAX = TILE + 16;           // encoded bytes a tile can span
 constexpr uint32_t STG_PAD = 16;                  // free bytes in front of the staged range (reads just before it stay in bounds)
 constexpr uint32_t STG_BYTES = STG_PAD + 16 + ENC_MAX + 16;  // pad + 16-byte alignment slack + range + token read-ahead
 constexpr uint32_t STG_WORDS = (STG_BYTES + 31) / 32 * 8;  // whole 32-byte bitmap words
 constexpr uint32_t BM_WORDS = 96;                 // bitmaps: three words per lane
-// every reference segment but the first and the last of a tile puts >= 7 decoded bytes into the tile
+// every reference token but the first and the last of a tile puts >= 7 decoded bytes into the tile
 constexpr uint32_t SEG_MAX = TILE / 7 + 4;
-// copy pieces: every reference segment is cut into pieces of at most 32 bytes (a piece is ready when one 32-bit
-// window of the "final" bitmap is all ones); periodic segments with a period >= 32 are also cut where they wrap.
-// A tile keeps at most PIECE_MAX pieces (typical tiles have ~80); the segments beyond that go straight to k_resolve.
-constexpr uint32_t PIECE_MAX = 256;
-constexpr uint32_t PIECE_ROWS = (PIECE_MAX + 31) / 32;
+// pending pieces: a reference whose source is not retired yet is cut into pieces of at most 32 bytes at the 32-byte
+// boundaries of the SOURCE (periodic ones also where they wrap).  A tile keeps at most PEND_MAX of them; when the
+// table is full the warp first drains it (copies them), then goes on.
+constexpr uint32_t PEND_MAX = 128;
+constexpr uint32_t PEND_ROWS = PEND_MAX / 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
-constexpr uint32_t GIVEUP_SPINS = 64;   // polls without any progress after which a tile hands its open pieces to k_resolve
-constexpr int RESOLVE_HOPS = 48;
+constexpr uint32_t LANE_RUN_MAX = 64;             // literal runs up to this length are copied by their lane, longer ones by the warp
 static_assert(STG_BYTES <= BM_WORDS * 32 && TILE + 4 <= (BM_WORDS - 1) * 32, "bitmaps too small");
+
+// the touched part of one chunk: records [first, last] form a contiguous part of the arena
+struct DecRange {
+    uint32_t first, last;      // records
+    uint32_t tile_lo, ntiles;  // their decode tiles (global tile ids are consecutive inside a chunk)
+    uint32_t rec_cum, tile_cum;  // records / tiles of the ranges before this one
+    uint32_t arena_base, pad;
+};
+
+// per range: two HINTS about its tiles, (index << 32) | arena offset relative to arena_base, only ever raised
+// (atomicMax): tiles [0, index) have reached the level and the offset is where the last of them ends.  Producers
+// only publish their own state (DecodeView::ts); whoever needs a watermark scans the states from the hint on, 32 at a
+// time, and raises the hint for the next one (no in-order hand-over between producers, no Dekker fences).
+struct DecSync {
+    unsigned long long zeroed;    // level 1: those tiles have zeroed themselves, their bytes may be polled in band
+    unsigned long long retired;   // level 2: those tiles are complete, every byte below the offset is final
+};
+
+// one work item = one tile, everything the decode kernel needs to start in ONE 48-byte read (k_dec_work derives it
+// from the record tables, so that the tile's warp does not walk a chain of dependent table loads)
+struct alignas(16) TileJob {
+    uint64_t enc_pos;       // offset in the compressed arena of the first staged byte
+    uint32_t rec_base;      // arena offset of the tile's record
+    uint32_t g;             // the record
+    uint32_t t0_nbytes;     // first decoded byte of the tile in its record (lo16), decoded bytes of the tile (hi16)
+    uint32_t ne_skip;       // staged encoded bytes (lo16); bytes of the first token to skip (hi16; 0xFFFF: raw first byte)
+    uint32_t chunk_first;   // global id of record 0 of the chunk (back references carry chunk-local indices)
+    uint32_t range;         // index of the DecRange
+    uint32_t sidx;          // index of the tile's state / end entry
+    uint32_t kidx;          // index of the tile inside its range
+    uint32_t pad0, pad1;
+};
+static_assert(sizeof(TileJob) == 48, "TileJob layout");
 
 struct DecodeView {
     const uint8_t *enc;
-    const uint64_t *enc_off;
-    const uint32_t *enc_len, *dec_len, *first, *tile_base, *tile_desc;
+    const TileJob *jobs;        // in ticket order
     const uint32_t *arena_off;  // per record: offset of its decoded bytes in the arena
+    const DecRange *ranges;
     uint8_t *arena;
-    uint32_t *fin;              // per arena byte: 1 bit, set = the byte holds its final value
-    uint32_t *gup;              // per arena byte: 1 bit, set = the byte was handed to k_resolve (its source is in ptr)
-    uint32_t *ptr;              // per arena byte: source position, written only for handed-over bytes
+    uint32_t *fin;              // per arena byte: 1 bit, set = the byte is final AND its value is zero
+    uint32_t *dirty;            // words of `fin` this call has set bits in (cleared again by k_fin_clean)
+    uint32_t dirty_cap;
+    unsigned long long *ts;     // per tile (range.tile_cum + index in range): (end offset relative to the range) << 2 |
+                                // state, 0 = not started, 1 = zeroed, 2 = complete
+    DecSync *sync;              // per range
 };
 
-struct ParseBits {                  // dead once the heads are listed: shares its storage with the pieces
+// what the out-of-line helpers need (passed by value: a reference to the kernel's parameter block would force a copy
+// of it into local memory)
+struct PubCtx {
+    uint8_t *arena;
+    uint32_t *fin, *dirty, *ctr;
+    uint32_t dirty_cap;
+};
+
+// counters of a decode call (dec_ctr)
+enum { DC_ERR = 0, DC_TICKET = 1, DC_DIRTY = 2, DC_PENDING = 3, DC_DRAINS = 4, DC_WAITS = 5 };
+
+struct ParseBits {                  // dead once the heads are listed: shares its storage with the pending pieces
     uint32_t b251[BM_WORDS];        // bit p: staged byte p is a 251 that can start a token
     uint32_t cst[BM_WORDS];         // bit p: that 251 surely starts a token (no 251 among the 7 bytes before it)
-    uint32_t headb[BM_WORDS];       // bit p: a reference token starts at p
+    uint16_t cl[SEG_MAX + 8];       // staged positions of those cluster starts, ascending
 };
-struct Pieces {
+struct Pending {
     // meta: u (12 bits) | (n - 1) << 12 (5 bits) | period << 17 (5 bits, 0 = plain copy) | phase << 22
-    uint32_t src[PIECE_MAX];        // arena position of the first source byte (periodic: of the period's byte 0)
-    uint32_t meta[PIECE_MAX];
+    uint32_t src[PEND_MAX];         // arena position of the first source byte (periodic: of the period's byte 0)
+    uint32_t meta[PEND_MAX];
+    uint32_t done[PEND_MAX];        // bytes of the piece already copied
 };
 
 struct alignas(16) WarpSmem {
     uint32_t stg[STG_WORDS];        // staged encoded bytes: byte e0 + k of the record sits at staged position soff + k
     union {
         ParseBits ps;
-        Pieces pc;
+        Pending pc;
     };
+    uint32_t zbm[BM_WORDS];         // bit p: staged byte p is zero (only valid when the tile's staged bytes hold a zero)
     uint16_t heads[SEG_MAX + 8];    // staged positions of the reference heads, ascending
-    uint32_t startb[BM_WORDS];      // bit u: a segment starts at output byte u - mis (word-aligned "u" coordinates)
-    uint32_t finw[BM_WORDS];        // bit u: output byte u - mis is a literal (final once phase 4 has stored it)
-    uint16_t wprefix[BM_WORDS];     // segment starts before word w of startb
-    // governors of the literal bytes: entry 0 governs the tile's start (the tail of a token that began in the
-    // previous tile, or empty), entries 1.. follow the start bits.  lo16: end of the segment (u); hi16: literals
-    // after it sit at staged position (u - mis) + this
-    uint32_t seg_ed[SEG_MAX + 1];
-    uint32_t pend[PIECE_ROWS];      // per row of 32 pieces: lanes whose piece is not copied yet
+    uint32_t pend[PEND_ROWS];       // per row of 32 pieces: lanes whose piece is not copied yet
 };
 
 __device__ __forceinline__ uint32_t nib251(uint32_t w) {
     return ((__vcmpeq4(w, 0xFBFBFBFBu) & 0x08040201u) * 0x01010101u) >> 24;
 }
-
+__device__ __forceinline__ uint32_t nibz(uint32_t w) {   // 4-bit mask of the zero bytes of w
+    return ((__vcmpeq4(w, 0u) & 0x08040201u) * 0x01010101u) >> 24;
+}
 __device__ __forceinline__ uint32_t nibnz(uint32_t w) {  // 4-bit mask of the nonzero bytes of w
     return ((__vcmpne4(w, 0u) & 0x08040201u) * 0x01010101u) >> 24;
 }
-__device__ __forceinline__ uint32_t bytemask4(uint32_t m) {  // 4-bit mask -> 0xFF per selected byte
-    return (((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+__device__ __forceinline__ uint32_t haszero(uint32_t w) { return (w - 0x01010101u) & ~w & 0x80808080u; }
+
+__device__ __forceinline__ uint32_t atom_relaxed_or_u32(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.relaxed.gpu.global.or.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+// stores that other warps poll: strong (relaxed, device scope) so that the poll and the store are both morally
+// strong operations; a byte is only ever stored with its final value or with zero ("not final yet")
+__device__ __forceinline__ void st_pub_u8(uint8_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v));
+}
+__device__ __forceinline__ void st_pub_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v));
+}
+__device__ __forceinline__ void st_pub_v4(uint4 *p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
-// publish the new bits of a tile's bitmap (finw, u coordinates) in the arena's bitmap (tiles share words: OR);
-// every lane looks after the global words lane, lane + 32 and lane + 64 of the tile's slice
-__device__ __forceinline__ void flush_word(const uint32_t *finw, uint32_t *lm, uint32_t sh, uint32_t ngw, uint32_t j, uint32_t &pub) {
-    if (j < ngw) {
-        const uint32_t lo = finw[j], hi = j > 0 ? finw[j - 1] : 0u;
-        const uint32_t v = sh ? ((lo << sh) | (hi >> (32 - sh))) : lo;
-        const uint32_t nv = v & ~pub;
-        if (nv) {
-            atomicOr(&lm[j], nv);
-            pub |= nv;
+// announce final bytes whose value is zero: bit j of `zmask` = arena byte B + j (j < 32)
+__device__ __noinline__ void publish_zeros(PubCtx P, uint32_t B, uint32_t zmask) {
+    const uint32_t bs = B & 31;
+    uint32_t wi = B >> 5, bits = zmask << bs;
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        if (bits) {
+            if (atom_relaxed_or_u32(P.fin + wi, bits) == 0) {  // first bit in this word: remember it for the clean-up
+                const uint32_t k = atomicAdd(P.ctr + DC_DIRTY, 1u);
+                if (k < P.dirty_cap) P.dirty[k] = wi;
+            }
         }
+        bits = bs ? zmask >> (32 - bs) : 0u;
+        wi++;
     }
 }
-__device__ __forceinline__ void flush_final(const uint32_t *finw, uint32_t *lm, uint32_t sh, uint32_t ngw, uint32_t lane,
-                                            uint32_t &pub0, uint32_t &pub1, uint32_t &pub2) {
-    flush_word(finw, lm, sh, ngw, lane, pub0);
-    flush_word(finw, lm, sh, ngw, lane + 32, pub1);
-    flush_word(finw, lm, sh, ngw, lane + 64, pub2);
+
+// One lane writes n (1..32) bytes at dst from a source given as nine aligned 32-bit words: byte j of the source is
+// byte sa + j of w0..w8.  Head bytes up to a word boundary of the destination, whole words, tail bytes.  ONE copy of
+// this code serves the literal runs, the retired references and the pending pieces (the kernel's working set has to
+// fit the instruction cache: the first version inlined it five times and stalled on instruction fetch).
+__device__ __noinline__ void put_bytes(uint8_t *dst, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                       uint32_t w6, uint32_t w7, uint32_t w8, uint32_t sa, uint32_t n) {
+    uint32_t sw[10] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, 0u};
+    const uint32_t hbe = min((4u - ((uint32_t) (uintptr_t) dst & 3u)) & 3u, n);  // head bytes up to a destination word boundary
+    const uint32_t x0 = __funnelshift_r(sw[0], sw[1], 8 * sa);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        if ((uint32_t) i < hbe) st_pub_u8(dst + i, (x0 >> (8 * i)) & 0xFFu);
+    const uint32_t rem = n - hbe, m = rem >> 2, tb = rem & 3, so = sa + hbe;
+    const uint32_t sh = 8 * (so & 3);
+    if (so >> 2) {  // (0 or 1)
+#pragma unroll
+        for (int q = 0; q < 9; q++) sw[q] = sw[q + 1];
+    }
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + hbe);
+    uint32_t xt = 0;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+        const uint32_t x = __funnelshift_r(sw[t], sw[t + 1], sh);
+        if ((uint32_t) t < m) st_pub_u32(dw + t, x);
+        if ((uint32_t) t == m) xt = x;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        if ((uint32_t) i < tb) st_pub_u8(reinterpret_cast<uint8_t *>(dw + m) + i, (xt >> (8 * i)) & 0xFFu);
+}
+
+// exact mask of the zero bytes among source bytes [sa, sa + n) of the aligned words sw (n <= 32)
+__device__ __forceinline__ uint32_t zero_mask(const uint32_t (&sw)[9], uint32_t sa, uint32_t n) {
+    unsigned long long zm = 0;
+#pragma unroll
+    for (int q = 0; q < 9; q++) zm |= (unsigned long long) nibz(sw[q]) << (4 * q);
+    return (uint32_t) (zm >> sa) & (0xFFFFFFFFu >> (32 - n));
+}
+
+// The whole warp writes n bytes at arena + B from staged bytes (from_arena = false: src is a staged position) or from
+// final arena bytes (src is an arena position).  Lane l looks after the destination words l, l + 32, ... of the span.
+__device__ __noinline__ void warp_put(PubCtx P, const uint32_t *stg, bool from_arena, uint32_t B, uint32_t src, uint32_t n) {
+    const uint32_t lane = lane_id();
+    const uint32_t da = B & 3u, span = da + n;   // destination words cover [B - da, B - da + span)
+    uint8_t *base = P.arena + (B - da);
+#pragma unroll 1
+    for (uint32_t o = 4 * lane; o < span; o += 128) {
+        const int j0 = (int) o - (int) da;         // piece byte held by the word's byte 0 (< 0 in the first word when da > 0)
+        const uint32_t lo = j0 < 0 ? (uint32_t) (-j0) : 0u;
+        // source bytes from piece byte max(j0, 0) on: two aligned words and a funnel shift, moved up to byte `lo`
+        const uint32_t s = src + (uint32_t) (j0 + (int) lo);
+        uint32_t x;
+        if (from_arena) {
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(P.arena + (s & ~3u));
+            x = __funnelshift_r(__ldcg(wp), __ldcg(wp + 1), 8 * (s & 3));
+        } else {
+            x = __funnelshift_r(stg[s >> 2], stg[(s >> 2) + 1], 8 * (s & 3));
+        }
+        x <<= 8 * lo;
+        const uint32_t hi = min(4u, (uint32_t) ((int) n - j0));
+        if (lo == 0 && hi == 4) {
+            st_pub_u32(reinterpret_cast<uint32_t *>(base + o), x);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if ((uint32_t) i >= lo && (uint32_t) i < hi) st_pub_u8(base + o + i, (x >> (8 * i)) & 0xFFu);
+        }
+        const uint32_t zb = nibz(x) & ((1u << hi) - 1) & ~((1u << lo) - 1);
+        if (zb) publish_zeros(P, (B - da) + o, zb);
+    }
+}
+
+// The whole warp zeroes arena bytes [B, B + n): byte stores up to a 16-byte boundary, 16-byte stores, byte stores.
+__device__ __forceinline__ void warp_zero(uint8_t *arena, uint32_t B, uint32_t n, uint32_t lane) {
+    const uint32_t hb = min((16u - (B & 15u)) & 15u, n);
+    if (lane < hb) st_pub_u8(arena + B + lane, 0u);
+    const uint32_t body = (n - hb) >> 4, tb = (n - hb) & 15u;
+    uint4 *b4 = reinterpret_cast<uint4 *>(arena + B + hb);
+#pragma unroll 1
+    for (uint32_t j = lane; j < body; j += 32) st_pub_v4(b4 + j, make_uint4(0u, 0u, 0u, 0u));
+    if (lane < tb) st_pub_u8(arena + B + hb + 16 * body + lane, 0u);
+}
+
+// How far have the tiles of a range reached `level`?  Scans the states from the range's hint on, 32 per step, up to
+// tile `limit` and for at most `max_steps` steps; raises the hint; returns (index << 32) | end offset of tile index - 1.
+// The caller fences afterwards (acquire side of the producers' fence + state store).
+__device__ __noinline__ unsigned long long scan_mark(const unsigned long long *ts, unsigned long long *hint, uint32_t limit,
+                                                     uint32_t level, uint32_t max_steps) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = lane_id();
+    unsigned long long h = 0;
+    if (lane == 0) h = ld_relaxed_u64(hint);
+    h = __shfl_sync(FULL, h, 0);
+    uint32_t idx = (uint32_t) (h >> 32), bytes = (uint32_t) h;
+    const uint32_t idx0 = idx;
+    for (uint32_t step = 0; step < max_steps && idx < limit; step++) {
+        const unsigned long long v = idx + lane < limit ? ld_relaxed_u64(ts + idx + lane) : 0ull;
+        const uint32_t ready = __ballot_sync(FULL, ((uint32_t) v & 3u) >= level);
+        const uint32_t n = ready == FULL ? 32u : (uint32_t) __ffs(~ready) - 1u;  // leading tiles that reached the level
+        if (n == 0) break;
+        bytes = __shfl_sync(FULL, (uint32_t) (v >> 2), n - 1);
+        idx += n;
+        if (n < 32) break;
+    }
+    h = ((unsigned long long) idx << 32) | bytes;
+    if (idx > idx0 && lane == 0) atomicMax(hint, h);
+    return h;
+}
+
+// Copy the pending pieces of a tile: one piece per lane and row, sweeping until all are done.  A piece loads its
+// source words (L2-coherent relaxed loads), copies the bytes that are final (nonzero, or zero and announced in the
+// bitmap), remembers them in its done mask and retries the rest: no flag round trip, no fence, and the critical path
+// is the nesting depth of BYTES.  Returns the number of sweeps, or 0xFFFFFFFF on a time-out / foreign error.
+__device__ __noinline__ uint32_t drain_pending(WarpSmem &S, PubCtx P, uint32_t B0, uint32_t npiece, uint32_t sleep_after,
+                                               uint32_t sleep_ns) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = lane_id();
+    uint8_t *const dstu = P.arena + B0;
+    const uint32_t nrows = (npiece + 31) / 32;
+    if (lane < PEND_ROWS)
+        S.pend[lane] = lane < nrows ? (32 * (lane + 1) <= npiece ? 0xFFFFFFFFu : (1u << (npiece - 32 * lane)) - 1) : 0u;
+    for (uint32_t k = lane; k < npiece; k += 32) S.pc.done[k] = 0;
+    __syncwarp();
+    uint32_t remaining = npiece, spins = 0, sweep = 3;  // (the first sweep examines every piece)
+    for (; remaining; sweep++) {
+        uint32_t any = 0;
+#pragma unroll 1
+        for (uint32_t row = 0; row < nrows; row++) {
+            const uint32_t pm = S.pend[row];
+            if (!pm) continue;
+            bool complete = false;
+            uint32_t avail = 0;
+            if ((pm >> lane) & 1u) {
+                const uint32_t slot = row * 32 + lane;
+                const uint32_t meta = S.pc.meta[slot], a = S.pc.src[slot];
+                const uint32_t per = (meta >> 17) & 31u, np = ((meta >> 12) & 31u) + 1, us = meta & 0xFFFu;
+                const uint32_t n = per ? per : np;  // source bytes
+                const uint32_t need = 0xFFFFFFFFu >> (32 - n);
+                uint32_t dn = per ? 0u : S.pc.done[slot];
+                // a waiting piece costs one load per sweep: the source byte behind its first open byte (its last one on
+                // odd sweeps: looking at the first byte only makes a byte wait for everything left of it in its piece,
+                // and with a source window that slides from record to record that running maximum chains every record
+                // to its predecessor); the whole window is examined when that byte has arrived and every fourth sweep
+                // (bytes out of order, zero-valued ones)
+                bool look = (sweep & 3u) == 3u;
+                if (!look) {
+                    const uint32_t open = need & ~dn;
+                    const uint32_t pj = a + ((sweep & 1u) ? 31u - (uint32_t) __clz(open) : (uint32_t) __ffs(open) - 1u);
+                    const uint32_t w0 = ld_poll_u32(reinterpret_cast<const uint32_t *>(P.arena + (pj & ~3u)));
+                    look = ((w0 >> (8 * (pj & 3))) & 0xFFu) != 0;
+                }
+                if (look) {
+                    const uint32_t sa = a & 3, nsw = (sa + n + 3) >> 2;  // aligned source words (<= 9)
+                    const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(P.arena + (a - sa));
+                    uint32_t sw[9];
+#pragma unroll
+                    for (int q = 0; q < 9; q++) sw[q] = (uint32_t) q < nsw ? ld_poll_u32(wp0 + q) : 0u;
+                    unsigned long long nzm = 0;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
+                    const uint32_t nz = (uint32_t) (nzm >> sa) & need;  // source bytes seen nonzero: final
+                    uint32_t zf = 0;  // source bytes that are final zeros
+                    const uint32_t zc = need & ~nz & ~dn;
+                    if (zc) {
+                        const uint32_t wi = a >> 5, bs = a & 31;
+                        uint32_t bits = ld_relaxed_u32(P.fin + wi) >> bs;
+                        if (bs + n > 32) bits |= ld_relaxed_u32(P.fin + wi + 1) << (32 - bs);
+                        zf = zc & bits;
+                    }
+                    avail = (nz | zf) & ~dn;
+                    uint32_t zout = 0;  // copied bytes whose value is zero (destination coordinates of the piece)
+                    if (per) {
+                        avail = avail == need ? need : 0u;  // short periods are copied in one go
+                        if (avail) {
+                            uint8_t *dst = dstu + us;
+                            const uint32_t ph = meta >> 22;
+#pragma unroll 1
+                            for (uint32_t j = 0; j < np; j += 4) {  // four loads in flight (the period is final: plain L2 loads)
+                                uint32_t bv[4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++) bv[i] = __ldcg(P.arena + a + (ph + j + i) % per);
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                    if (j + i < np) {
+                                        st_pub_u8(dst + j + i, bv[i]);
+                                        if (bv[i] == 0) zout |= 1u << (j + i);
+                                    }
+                            }
+                            complete = true;
+                        }
+                    } else if (avail == need && dn == 0) {
+                        // the common case: the whole piece is final -> straight copy
+                        put_bytes(dstu + us, sw[0], sw[1], sw[2], sw[3], sw[4], sw[5], sw[6], sw[7], sw[8], sa, n);
+                        zout = zf;
+                        complete = true;
+                    } else if (avail) {
+                        // destination word t holds piece bytes [4t - da, 4t - da + 4); its source bytes straddle the
+                        // aligned source words t + c and t + c + 1 (c = -1 when the source sits further left in its word)
+                        const uint32_t da = us & 3;
+                        const int delta = (int) sa - (int) da;
+                        const uint32_t sh = 8u * (uint32_t) (delta & 3);
+                        uint32_t prev = 0;
+                        uint32_t *dw = reinterpret_cast<uint32_t *>(dstu + us - da);
+                        const unsigned long long am = (unsigned long long) avail << da;  // bytes to store, word coordinates
+                        const uint32_t ndw = (da + n + 3) >> 2;
+#pragma unroll
+                        for (int t = 0; t < 9; t++) {
+                            // (delta < 0: word t straddles source words t - 1 and t)
+                            const uint32_t lo_w = delta < 0 ? prev : sw[t], hi_w = delta < 0 ? sw[t] : (t < 8 ? sw[t + 1] : 0u);
+                            prev = sw[t];
+                            const uint32_t vm = (uint32_t) (am >> (4 * t)) & 0xFu;
+                            if ((uint32_t) t < ndw && vm) {
+                                const uint32_t x = __funnelshift_r(lo_w, hi_w, sh);
+                                if (vm == 0xFu) {
+                                    st_pub_u32(dw + t, x);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 4; i++)
+                                        if ((vm >> i) & 1u) st_pub_u8(reinterpret_cast<uint8_t *>(dw + t) + i, (x >> (8 * i)) & 0xFFu);
+                                }
+                            }
+                        }
+                        zout = zf & avail;
+                        dn |= avail;
+                        S.pc.done[slot] = dn;
+                        complete = dn == need;
+                    }
+                    if (zout) publish_zeros(P, B0 + us, zout);
+                }
+            }
+            const uint32_t cb = __ballot_sync(FULL, complete);
+            if (__ballot_sync(FULL, avail != 0)) any = 1;
+            if (cb) {
+                if (lane == 0) S.pend[row] = pm & ~cb;
+                remaining -= __popc(cb);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        if (!any) {
+            if (++spins > SPIN_LIMIT || ld_relaxed_u32(P.ctr + DC_ERR) != 0) {
+                if (lane == 0) atomicCAS(P.ctr + DC_ERR, 0u, 8u);
+                return 0xFFFFFFFFu;
+            }
+            if (spins > sleep_after) __nanosleep(spins > 256 ? 400 : sleep_ns);
+        } else {
+            spins = 0;
+        }
+    }
+    return sweep - 3;
 }
 
 // K10: one warp per 2 KiB tile of decoded output, tiles taken by ticket in arena order.
+//   0. the tile zeroes itself; after the parse it announces "zeroed" (in-order watermark wl)
 //   1. stage the tile's encoded bytes in shared memory (16-byte loads)
-//   2. bitmap of the 251s; a 251 with no 251 among the 7 bytes before it surely starts a token: one walk per such
-//      cluster start classifies the tokens of its cluster (PiXiuStr.h:142-160 dispatch) and marks reference heads
-//   3. heads in order -> segments: a scan of (decoded - encoded) token bytes gives every reference's output position,
-//      because literals map 1:1
-//   4. literal bytes: one aligned 32-bit store per output word straight from the staged bytes, then the literal bits
-//      of the tile are published in the arena's "final" bitmap
-//   5. reference segments: a segment is copied once its source range is final (sources always precede their
-//      destination in the arena, and tickets are handed out in arena order, so every source belongs to a tile that
-//      is finished or held by a resident warp: waiting cannot deadlock); copied ranges are published the same way
-__global__ void __launch_bounds__(DEC_WARPS * 32, 8)
-k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint32_t *__restrict__ work_rec,
-               uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t giveup_spins, uint32_t piece_cap,
-               uint32_t sleep_after, uint32_t sleep_ns, unsigned long long *__restrict__ trace) {
+//   2. bitmap of the 251s; a 251 with no 251 among the 7 bytes before it surely starts a token: these cluster starts
+//      are listed, and one lane per cluster walks its tokens (PiXiuStr.h:142-160 dispatch) and counts / lists the
+//      reference heads (a cluster is almost always a single token)
+//   3. heads in order, 32 per round, one lane per reference token: a scan of (decoded - encoded) token bytes gives its
+//      output position (literals map 1:1); the lane writes the literal run in front of its token from the staged
+//      bytes, then the token: copied from the arena when its source is retired, else it becomes pending pieces
+//   4. the literal run behind the last token
+//   5. pending pieces (drain_pending), once every earlier tile of the chunk has announced "zeroed"
+//   6. the tile announces "complete" (in-order watermark wm = retired prefix of the chunk)
+__global__ void __launch_bounds__(DEC_WARPS * 32, PIXIU_DEC_MINB)
+k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t piece_cap, uint32_t sleep_after,
+               uint32_t sleep_ns, unsigned long long *__restrict__ trace) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
-    const uint32_t lt = (1u << lane) - 1;
     const uint32_t FULL = 0xffffffffu;
-    uint32_t *err = ctr;
+    uint32_t *err = ctr + DC_ERR;
+    const PubCtx P{V.arena, V.fin, V.dirty, ctr, V.dirty_cap};
+    // persistent warps: every warp takes tiles by ticket until none is left
+#pragma unroll 1
+    for (;;) {
+    __syncwarp();
     uint32_t w = 0;
-    if (lane == 0) w = atomicAdd(ctr + 1, 1u);
+    if (lane == 0) w = atomicAdd(ctr + DC_TICKET, 1u);
     w = __shfl_sync(FULL, w, 0);
     if (w >= n_work) return;
     if (trace && lane == 0) trace[4 * (size_t) w] = globaltimer_ns();
-    const uint32_t gt = work_tile[w], g = work_rec[w];
-    const uint32_t t = gt - V.tile_base[g];
-    const uint32_t dl = V.dec_len[g], el = V.enc_len[g];
-    const uint32_t t0 = t * TILE, t1 = min(dl, t0 + TILE), nbytes = t1 - t0;
-    const uint32_t rec_base = V.arena_off[g], chunk_first = V.first[g];
-    const uint8_t *encp = V.enc + V.enc_off[g];
-    uint32_t desc = V.tile_desc[gt];
-    const uint32_t e0 = desc & 0xffff;
-    uint32_t skip = desc >> 16;
+    // ---- the job: three 16-byte reads ----
+    const uint4 j0 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w)), j1 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w) + 1);
+    const uint4 j2 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w) + 2);
+    const uint8_t *gsrc = V.enc + (((uint64_t) j0.y << 32) | j0.x);
+    const uint32_t rec_base = j0.z, g = j0.w;
+    const uint32_t t0 = j1.x & 0xFFFFu, nbytes = j1.x >> 16;
+    const uint32_t ne = j1.y & 0xFFFFu;
+    uint32_t skip = j1.y >> 16;
     const bool raw_first = skip == 0xFFFF;  // first enc byte is the 2nd half of an escape pair
     if (raw_first) skip = 0;
-    uint32_t e_end = el;
-    if (t1 < dl) {
-        uint32_t d2 = V.tile_desc[gt + 1];
-        e_end = d2 & 0xffff;
-        uint32_t sk2 = d2 >> 16;
-        if (sk2 != 0 && sk2 != 0xFFFF) e_end += (encp[e_end + 1] == 1) ? 8u : 6u;
-    }
-    const uint32_t ne = e_end - e0;
+    const uint32_t chunk_first = j1.z, sidx = j2.x, kidx = j2.y;
+    const DecRange rg = V.ranges[j1.w];
+    DecSync *const sy = V.sync + j1.w;
     const uint32_t mis = (uint32_t) ((uintptr_t) (V.arena + rec_base + t0) & 3);
-    const uint32_t nu = nbytes + mis;
-    const uint32_t B0 = rec_base + t0 - mis;  // arena position of u = 0
-    uint32_t pub0 = 0, pub1 = 0, pub2 = 0;  // bits of the tile already published (global words lane, lane+32, lane+64)
-    uint32_t *const lm = V.fin + (B0 >> 5);
-    const uint32_t fsh = B0 & 31, ngw = (fsh + nu + 31) / 32;
-    if (ne > ENC_MAX || e_end > el) {
+    const uint32_t B0 = rec_base + t0 - mis;  // arena position of u = 0 (word aligned); u = output byte + mis
+    uint8_t *const dstu = V.arena + B0;
+    const uint32_t tile_rel = rec_base + t0 - rg.arena_base;  // start of the tile relative to its range
+    // the retired prefix of the chunk as this tile starts (everything below is final: references into it are copied
+    // without polling); the fence is the acquire side of the producers' "fence, then state" (nothing of this tile is in
+    // flight yet, so it is cheap here)
+    const unsigned long long *const rts = V.ts + rg.tile_cum;
+    const uint32_t wm = (uint32_t) scan_mark(rts, &sy->retired, kidx, 2u, 2u) + rg.arena_base;   // absolute arena offset
+    fence_gpu();
+    bool failed = false;
+    if (ne > ENC_MAX) {   // (k_dec_work flags an inconsistent descriptor this way)
         if (lane == 0) atomicExch(err, 4u);
-        return;
+        failed = true;
     }
+    // ---- 0. the tile zeroes itself ("not final yet" for every byte), so that other tiles may poll its bytes in band
+    //         long before its literals are written; the stores drain while the tile is staged and parsed, and the
+    //         L2 merges them with the final bytes that follow (no second trip to DRAM) ----
+    warp_zero(V.arena, rec_base + t0, nbytes, lane);
     // ---- 1. stage the encoded bytes (the compressed arena has slack past its end) ----
-    const uint8_t *gsrc = encp + e0;
     const uint32_t a16 = (uint32_t) ((uintptr_t) gsrc & 15);
     const uint32_t soff = STG_PAD + a16, nstg = soff + ne;
-    {
+    uint32_t nheads = 0;
+    if (!failed) {
         const uint4 *g4 = reinterpret_cast<const uint4 *>(gsrc - a16);
         uint4 *s4 = reinterpret_cast<uint4 *>(S.stg);
         const uint32_t n16 = (a16 + ne + 8 + 15) >> 4;
+#pragma unroll 1
         for (uint32_t j = lane; j < n16; j += 32) s4[1 + j] = g4[j];
         if (lane < 4) S.stg[lane] = 0;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            S.ps.headb[lane + 32 * k] = 0;
-            S.startb[lane + 32 * k] = 0;
-            S.finw[lane + 32 * k] = 0;
-        }
+        __syncwarp();
     }
-    __syncwarp();
     const uint8_t *SB = reinterpret_cast<const uint8_t *>(S.stg);
-    // ---- 2a. bitmap of the 251s (32 staged bytes per lane and step) ----
-    {
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(S.stg);
-        const uint32_t lo = soff + (raw_first ? 1u : 0u);  // the raw first byte is a plain literal
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const uint32_t wi = lane + 32 * k, base = wi * 32;
-            uint32_t bits = 0;
-            if (base < nstg) {
-                const uint4 A = s4[2 * wi], B = s4[2 * wi + 1];
-                bits = nib251(A.x) | (nib251(A.y) << 4) | (nib251(A.z) << 8) | (nib251(A.w) << 12) | (nib251(B.x) << 16) |
-                       (nib251(B.y) << 20) | (nib251(B.z) << 24) | (nib251(B.w) << 28);
-                if (base < lo) bits &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
-                if (base + 32 > nstg) bits &= 0xFFFFFFFFu >> (base + 32 - nstg);
-            }
-            S.ps.b251[wi] = bits;
-        }
-    }
-    __syncwarp();
-    // ---- 2b. cluster starts, then one walk per cluster ----
-    uint32_t cs[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const uint32_t wi = lane + 32 * k;
-        const uint32_t b = S.ps.b251[wi], pb = wi ? S.ps.b251[wi - 1] : 0u;
-        unsigned long long y = (((unsigned long long) b << 32) | pb) << 1;
-        y |= y << 1;
-        y |= y << 2;
-        y |= y << 3;  // OR of the shifts 1..7
-        cs[k] = b & ~(uint32_t) (y >> 32);
-        S.ps.cst[wi] = cs[k];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        uint32_t st = cs[k];
-        const uint32_t base = (lane + 32 * k) * 32;
-        while (st) {
-            uint32_t e = base + __ffs(st) - 1;
-            st &= st - 1;
-            while (true) {
-                if (e + 1 >= nstg) break;  // first half of an escape pair cut by the tile boundary: a literal
-                const uint32_t nx = SB[e + 1];
-                uint32_t tl;
-                if (nx == 0 || nx == 251 || nx == 2) {
-                    tl = 2;
-                } else if (nx == 1) {
-                    tl = 8;
-                } else if (nx > 6) {
-                    tl = 6;
-                } else {
-                    atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
-                    break;
+    if (!failed) {
+        // ---- 2a. bitmap of the 251s and of the zero bytes (32 staged bytes per lane and step) ----
+        {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(S.stg);
+            const uint32_t lo = soff + (raw_first ? 1u : 0u);  // the raw first byte is a plain literal
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                const uint32_t wi = lane + 32 * k, base = wi * 32;
+                uint32_t bits = 0, zb = 0;
+                if (base < nstg) {
+                    const uint4 A = s4[2 * wi], B = s4[2 * wi + 1];
+                    bits = nib251(A.x) | (nib251(A.y) << 4) | (nib251(A.z) << 8) | (nib251(A.w) << 12) | (nib251(B.x) << 16) |
+                           (nib251(B.y) << 20) | (nib251(B.z) << 24) | (nib251(B.w) << 28);
+                    if (base < lo) bits &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
+                    if (base + 32 > nstg) bits &= 0xFFFFFFFFu >> (base + 32 - nstg);
+                    if (haszero(A.x) | haszero(A.y) | haszero(A.z) | haszero(A.w) | haszero(B.x) | haszero(B.y) | haszero(B.z) |
+                        haszero(B.w)) {
+                        zb = nibz(A.x) | (nibz(A.y) << 4) | (nibz(A.z) << 8) | (nibz(A.w) << 12) | (nibz(B.x) << 16) |
+                             (nibz(B.y) << 20) | (nibz(B.z) << 24) | (nibz(B.w) << 28);
+                        if (base < soff) zb &= (soff - base >= 32) ? 0u : (0xFFFFFFFFu << (soff - base));
+                        if (base + 32 > nstg) zb &= 0xFFFFFFFFu >> (base + 32 - nstg);
+                    }
                 }
-                if (tl > 2) atomicOr(&S.ps.headb[e >> 5], 1u << (e & 31));
-                e += tl;
-                if (e >= nstg) break;
-                // the next 251 of this cluster lies within 7 bytes of the token's end (further ones start their own)
-                const uint32_t wq = e >> 5, sh = e & 31;
-                const uint32_t x = __funnelshift_r(S.ps.b251[wq], S.ps.b251[wq + 1], sh) & 0x7Fu;
-                if (!x) break;
-                const uint32_t cx = __funnelshift_r(S.ps.cst[wq], S.ps.cst[wq + 1], sh);
-                const uint32_t f = __ffs(x) - 1;
-                if ((cx >> f) & 1u) break;  // that one is a cluster start: its own walk handles it
-                e += f;
+                S.ps.b251[wi] = bits;
+                S.zbm[wi] = zb;
             }
         }
-    }
-    __syncwarp();
-    // ---- 2c. reference heads in ascending order (lane l owns bitmap words 3l .. 3l+2) ----
-    uint32_t nheads;
-    {
-        uint32_t h[3] = {S.ps.headb[3 * lane], S.ps.headb[3 * lane + 1], S.ps.headb[3 * lane + 2]};
-        const uint32_t cnt = __popc(h[0]) + __popc(h[1]) + __popc(h[2]);
-        uint32_t inc = cnt;
+        __syncwarp();
+        // ---- 2b. cluster starts (lane l owns the consecutive bitmap words 3l .. 3l+2), listed in ascending order ----
+        uint32_t ncl;
+        {
+            uint32_t cs[3], cnt = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, inc, d);
-            if ((int) lane >= d) inc += o;
+            for (int k = 0; k < 3; k++) {
+                const uint32_t wi = 3 * lane + k;
+                const uint32_t b = S.ps.b251[wi], pb = wi ? S.ps.b251[wi - 1] : 0u;
+                unsigned long long y = (((unsigned long long) b << 32) | pb) << 1;
+                y |= y << 1;
+                y |= y << 2;
+                y |= y << 3;  // OR of the shifts 1..7
+                cs[k] = b & ~(uint32_t) (y >> 32);
+                cnt += __popc(cs[k]);
+            }
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, inc, d);
+                if ((int) lane >= d) inc += o;
+            }
+            ncl = __shfl_sync(FULL, inc, 31);
+            __syncwarp();
+            uint32_t slot = inc - cnt;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                S.ps.cst[3 * lane + k] = cs[k];
+                uint32_t hv = cs[k];
+                while (hv) {
+                    if (slot < SEG_MAX + 8) S.ps.cl[slot] = (uint16_t) ((3 * lane + k) * 32 + __ffs(hv) - 1);
+                    slot++;
+                    hv &= hv - 1;
+                }
+            }
+            if (ncl > SEG_MAX + 8) {   // (cluster starts are >= 8 bytes apart: cannot happen on a tile of <= 2064 bytes)
+                if (lane == 0) atomicExch(err, 6u);
+                failed = true;
+                ncl = 0;
+            }
         }
-        nheads = __shfl_sync(FULL, inc, 31);
+        __syncwarp();
+        // ---- 2c. one lane per cluster: walk its tokens, count the reference heads (pass 0), list them (pass 1) ----
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < ncl; c0 += 32) {
+            const bool has = c0 + lane < ncl;
+            const uint32_t e_first = has ? S.ps.cl[c0 + lane] : 0u;
+            uint32_t nh = 0, h0 = 0, hbase = 0;
+            bool again = false;   // (a cluster with more than one reference head is walked a second time to list them)
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                uint32_t e = e_first, k = 0;
+                while (has && (pass == 0 || again)) {
+                    if (e + 1 >= nstg) break;  // first half of an escape pair cut by the tile boundary: a literal
+                    const uint32_t nx = SB[e + 1];
+                    uint32_t tl;
+                    if (nx == 0 || nx == 251 || nx == 2) {
+                        tl = 2;
+                    } else if (nx == 1) {
+                        tl = 8;
+                    } else if (nx > 6) {
+                        tl = 6;
+                    } else {
+                        atomicExch(err, 5u);  // 3..6: invalid (assert(false), PiXiuStr.h:193)
+                        break;
+                    }
+                    if (tl > 2) {
+                        if (pass && hbase + k < SEG_MAX + 8) S.heads[hbase + k] = (uint16_t) e;
+                        if (k == 0) h0 = e;
+                        k++;
+                    }
+                    e += tl;
+                    if (e >= nstg) break;
+                    // the next 251 of this cluster lies within 7 bytes of the token's end (further ones start their own)
+                    const uint32_t wq = e >> 5, sh = e & 31;
+                    const uint32_t x = __funnelshift_r(S.ps.b251[wq], S.ps.b251[wq + 1], sh) & 0x7Fu;
+                    if (!x) break;
+                    const uint32_t cx = __funnelshift_r(S.ps.cst[wq], S.ps.cst[wq + 1], sh);
+                    const uint32_t f = __ffs(x) - 1;
+                    if ((cx >> f) & 1u) break;  // that one is a cluster start: its own walk handles it
+                    e += f;
+                }
+                if (pass == 0) {
+                    nh = k;
+                    uint32_t inc = nh;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        uint32_t o = __shfl_up_sync(FULL, inc, d);
+                        if ((int) lane >= d) inc += o;
+                    }
+                    hbase = nheads + inc - nh;
+                    nheads += __shfl_sync(FULL, inc, 31);
+                    if (nh == 1 && hbase < SEG_MAX + 8) S.heads[hbase] = (uint16_t) h0;
+                    again = nh > 1;
+                    if (!__any_sync(FULL, again)) break;
+                }
+            }
+        }
         if (nheads > SEG_MAX) {
             if (lane == 0) atomicExch(err, 6u);
-            return;
+            failed = true;
+            nheads = 0;
         }
-        uint32_t slot = inc - cnt;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            uint32_t hv = h[k];
-            while (hv) {
-                S.heads[slot++] = (uint16_t) ((3 * lane + k) * 32 + __ffs(hv) - 1);
-                hv &= hv - 1;
-            }
-        }
-        if (lane == 0) S.seg_ed[0] = mis | (soff << 16);  // entry 0: literals of the tile's start map 1:1 onto the staged bytes
+        __syncwarp();   // (from here on ParseBits is dead: its storage holds the pending pieces)
+    }
+    // the tile announces "zeroed" (state 1)
+    const unsigned long long my_end = (unsigned long long) (tile_rel + nbytes) << 2;
+    if (lane == 0) {
+        fence_gpu();                                        // the zeroes are visible before the state is
+        st_relaxed_u64(V.ts + sidx, my_end | 1ull);
     }
     __syncwarp();
-    // ---- 3. heads -> segments.  D = sum over the references so far of (decoded - encoded) token bytes; a token
-    //         at staged position p starts at output byte (p - soff) + D - skip ----
-    uint32_t nseg = 0;  // governor entries 1..nseg
-    uint32_t npiece = 0;
-    bool full = false;  // the piece table is full: later segments are handed over
-    int D = 0;
-    for (uint32_t c0 = 0; c0 < nheads; c0 += 32) {
+    // ---- 3. rounds of 32 reference tokens, one lane each ----
+    uint32_t npiece = 0;        // pending pieces in the table
+    bool lit_ok = false;        // every earlier tile of the chunk has zeroed itself: in-band polling is valid
+    uint32_t sweeps = 0;
+    int D = 0;                  // sum of (decoded - encoded) bytes of the reference tokens so far
+    int carry_out = 0;          // output position where the previous token ended (literals before the first one start at 0)
+    uint32_t carry_stg = soff;  // staged position behind the previous token
+
+    // wait until in-band polling is valid, then copy the pending pieces
+    auto drain = [&]() -> bool {
+        if (!npiece) return true;
+        if (!lit_ok) {
+            // (every earlier tile zeroed itself within microseconds of its start: this wait is over before it begins,
+            //  except right behind a tile that was held up)
+            uint32_t spins = 0;
+            bool ok = true;
+            while ((uint32_t) (scan_mark(rts, &sy->zeroed, kidx, 1u, 8u) >> 32) < kidx) {
+                if (++spins > SPIN_LIMIT || ld_relaxed_u32(err) != 0) {
+                    if (lane == 0) atomicCAS(err, 0u, 8u);
+                    ok = false;
+                    break;
+                }
+                __nanosleep(spins > 16 ? 1000 : 100);
+            }
+            if (spins && lane == 0) atomicAdd(ctr + DC_WAITS, 1u);
+            fence_gpu();  // (acquire side: the zeroes of the earlier tiles are visible to the polls below)
+            __syncwarp();
+            if (!ok) return false;
+            lit_ok = true;
+        }
+        if (lane == 0) {
+            atomicAdd(ctr + DC_PENDING, npiece);
+            atomicAdd(ctr + DC_DRAINS, 1u);
+        }
+        const uint32_t sw = drain_pending(S, P, B0, npiece, sleep_after, sleep_ns);
+        npiece = 0;
+        sweeps += sw;
+        return sw != 0xFFFFFFFFu;
+    };
+
+    // arena offset of the source record of this lane's token, fetched one round ahead (a dependent L2 round trip
+    // that would otherwise sit in the middle of every round)
+    auto source_base = [&](uint32_t c) -> uint32_t {
+        if (c >= nheads) return 0u;
+        const uint32_t p2 = S.heads[c] + 2u;
+        const uint32_t src_g = chunk_first + (__funnelshift_r(S.stg[p2 >> 2], S.stg[(p2 >> 2) + 1], 8 * (p2 & 3)) & 0xFFFFu);
+        return src_g < g ? V.arena_off[src_g] : 0u;
+    };
+    uint32_t aoff_cur = failed ? 0u : source_base(lane);
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < nheads && !failed; c0 += 32) {
         const uint32_t c = c0 + lane;
         const bool head = c < nheads;
-        uint32_t p = 0, idx = 0, from = 0, tl = 0;
+        const uint32_t aoff_next = source_base(c + 32);
+        uint32_t p = 0, idx = 0, from = 0, tl = 0, elen = 0;
         int d = 0;
         if (head) {
             p = S.heads[c];
-            const uint32_t b1 = SB[p + 1];
+            // the token's eight bytes: two unaligned 32-bit reads of the staged words
+            const uint32_t wq = p >> 2, sh = 8 * (p & 3);
+            const uint32_t a0 = S.stg[wq], a1 = S.stg[wq + 1], a2 = S.stg[wq + 2];
+            const uint32_t f0 = __funnelshift_r(a0, a1, sh), f1 = __funnelshift_r(a1, a2, sh);
+            const uint32_t b1 = (f0 >> 8) & 0xFFu;
             const bool big = b1 == 1;
-            idx = SB[p + 2] | (SB[p + 3] << 8);
-            const uint32_t to = SB[p + 4] | (SB[p + 5] << 8);
-            from = big ? (uint32_t) (SB[p + 6] | (SB[p + 7] << 8)) : to - b1;
+            idx = f0 >> 16;
+            const uint32_t to = f1 & 0xFFFFu;
+            from = big ? f1 >> 16 : to - b1;
             if (to <= from || from > 0xFFFF) {
                 atomicExch(err, 5u);
                 from = to;
             }
             tl = to - from;
-            d = (int) tl - (big ? 8 : 6);
+            elen = big ? 8u : 6u;
+            d = (int) tl - (int) elen;
         }
         int inc = d;
 #pragma unroll
@@ -318,14 +730,27 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
             if ((int) lane >= dd) inc += o;
         }
         const int rel = (int) (p - soff) + D + (inc - d) - (int) skip;  // output position of the token's first byte
+        const int end_out = rel + (int) tl;
+        const uint32_t end_stg = p + elen;
+        int pe_out = __shfl_up_sync(FULL, end_out, 1);
+        uint32_t pe_stg = __shfl_up_sync(FULL, end_stg, 1);
+        if (lane == 0) {
+            pe_out = carry_out;
+            pe_stg = carry_stg;
+        }
+        // the literal run in front of the token: output [lo, hi), staged bytes from pe_stg + (lo - pe_out)
+        const int lo = max(pe_out, 0), hi = min(rel, (int) nbytes);
+        const uint32_t rn = (head && hi > lo) ? (uint32_t) (hi - lo) : 0u;
+        const uint32_t rsrc = pe_stg + (uint32_t) (lo - pe_out);
+        const uint32_t ru = (uint32_t) lo + mis;
+        const bool rlong = rn > LANE_RUN_MAX;
+        // the token itself
         const uint32_t k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
-        const uint32_t k1 = (int) tl + rel > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
+        const uint32_t k1 = end_out > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
         const bool emit = head && k0 < k1;
-        const bool initial = emit && rel < 0;  // the tail of a token that began in the previous tile (only the first head)
-        const uint32_t em = __ballot_sync(FULL, emit && !initial);
-        uint32_t sbase = 0, per = 0, ks = k0, us = 0, len = 0, np = 0;
+        uint32_t sbase = 0, per = 0, ks = k0, us = 0, len = 0;
+        bool fast = false;
         if (emit) {
-            const uint32_t sidx = initial ? 0u : 1u + nseg + __popc(em & lt);
             const uint32_t src_g = chunk_first + idx;
             if (src_g == g) {  // self reference (PiXiuStr.h:168-181): overlapping copies repeat with this period
                 const uint32_t period = (uint32_t) ((int) t0 + rel) - from;
@@ -334,7 +759,7 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                 if ((int) t0 + rel <= (int) from) atomicExch(err, 3u);
             } else {
                 if (src_g > g) atomicExch(err, 3u);
-                sbase = (src_g > g ? 0u : V.arena_off[src_g]) + from;
+                sbase = aoff_cur + from;
             }
             len = k1 - k0;
             if (per) {
@@ -342,412 +767,187 @@ k_decode_tiles(DecodeView V, const uint32_t *__restrict__ work_tile, const uint3
                 if (ks + len <= per) per = 0;  // this part does not wrap: a plain copy out of the first period
             }
             us = (uint32_t) (rel + (int) k0) + mis;
-            if (sidx <= SEG_MAX) {
-                S.seg_ed[sidx] = (us + len) | (((uint32_t) ((int) (soff + skip) - (D + inc)) & 0xFFFFu) << 16);
-                if (!initial) atomicOr(&S.startb[us >> 5], 1u << (us & 31));
-            }
-            // pieces of this segment: a short plain segment is one piece; longer ones are cut at the 32-byte
-            // boundaries of the SOURCE, so that a single word of the "final" bitmap decides whether a piece is ready
-            if (per != 0 && per < 32) {
-                np = (len + 31) >> 5;
-            } else if (per == 0) {
-                const uint32_t A = sbase + ks;
-                np = len <= 32 ? 1u : ((A + len - 1) >> 5) - (A >> 5) + 1;
+            fast = per == 0 && sbase + ks + len <= wm;   // the source is retired: final, no polling
+        }
+        // ---- 3a. up to three items per lane, each at most 32 bytes: the run's first and second half from the staged bytes,
+        //          the token from the arena when its source is retired.  (Tokens whose source is not retired stay zero =
+        //          "not final yet" and become pending pieces below.) ----
+#pragma unroll 1
+        for (int it = 0; it < 3; it++) {
+            uint32_t n, q, u;
+            if (it < 2) {
+                n = (rlong || rn <= 32u * it) ? 0u : min(rn - 32u * it, 32u);
+                q = rsrc + 32u * it;
+                u = ru + 32u * it;
             } else {
-                for (uint32_t pos = ks, rem = len; rem; np++) {
-                    const uint32_t n = min(min(32u - ((sbase + pos) & 31u), per - pos), rem);
-                    pos = pos + n == per ? 0u : pos + n;
-                    rem -= n;
-                }
+                n = (emit && fast && len <= 32) ? len : 0u;
+                q = sbase + ks;
+                u = us;
             }
-        }
-        uint32_t pinc = np;
+            if (!__any_sync(FULL, n != 0)) continue;
+            if (n) {
+                const uint32_t sa = q & 3, nsw = (sa + n + 3) >> 2;
+                uint32_t sw[9];
+                uint32_t zb;
+                if (it < 2) {
 #pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, pinc, dd);
-            if ((int) lane >= dd) pinc += o;
-        }
-        uint32_t slot = npiece + pinc - np;
-        const bool spill = np && (full || slot + np > piece_cap);  // (from the first spilling lane on, every later segment spills)
-        const uint32_t sb = __ballot_sync(FULL, spill);
-        if (spill) {
-            // no room: the whole segment goes to k_resolve (source pointers + hand-over bits)
-            const uint32_t B = B0 + us;
-            for (uint32_t j = 0; j < len; j++) V.ptr[B + j] = sbase + (per ? (ks + j) % per : ks + j);
-            for (uint32_t wj = B >> 5; wj <= (B + len - 1) >> 5; wj++) {
-                uint32_t bits = 0xFFFFFFFFu;
-                if (wj == B >> 5) bits <<= (B & 31);
-                if (wj == (B + len - 1) >> 5) bits &= 0xFFFFFFFFu >> (31 - ((B + len - 1) & 31));
-                atomicOr(V.gup + wj, bits);
-            }
-            atomicAdd(ctr + 2, 1u);
-        }
-        if (np && !spill) {
-            if (per != 0 && per < 32) {
-                for (uint32_t o = 0; o < len; o += 32, slot++) {
-                    S.pc.src[slot] = sbase;
-                    S.pc.meta[slot] = (us + o) | ((min(32u, len - o) - 1) << 12) | (per << 17) | (((ks + o) % per) << 22);
-                }
-            } else if (per == 0 && len <= 32) {
-                S.pc.src[slot] = sbase + ks;
-                S.pc.meta[slot] = us | ((len - 1) << 12);
-            } else {
-                const uint32_t wrap = per ? per : 0xFFFFFFFFu;
-                for (uint32_t pos = ks, o = 0; o < len; slot++) {
-                    const uint32_t n = min(min(32u - ((sbase + pos) & 31u), wrap - pos), len - o);
-                    S.pc.src[slot] = sbase + pos;
-                    S.pc.meta[slot] = (us + o) | ((n - 1) << 12);
-                    pos = pos + n == wrap ? 0u : pos + n;
-                    o += n;
-                }
-            }
-        }
-        nseg += __popc(em);
-        npiece = sb ? __shfl_sync(FULL, slot, __ffs(sb) - 1) : npiece + __shfl_sync(FULL, pinc, 31);
-        if (sb) full = true;
-        D += __shfl_sync(FULL, inc, 31);
-    }
-    if ((int) ne + D < (int) (skip + nbytes) || nseg > SEG_MAX) {
-        if (lane == 0) atomicExch(err, 6u);
-        return;
-    }
-    __syncwarp();
-    {  // segment starts before each bitmap word
-        const uint32_t c0 = __popc(S.startb[3 * lane]), c1 = __popc(S.startb[3 * lane + 1]), c2 = __popc(S.startb[3 * lane + 2]);
-        uint32_t inc = c0 + c1 + c2;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, inc, d);
-            if ((int) lane >= d) inc += o;
-        }
-        const uint32_t b = inc - (c0 + c1 + c2);
-        S.wprefix[3 * lane] = (uint16_t) b;
-        S.wprefix[3 * lane + 1] = (uint16_t) (b + c0);
-        S.wprefix[3 * lane + 2] = (uint16_t) (b + c0 + c1);
-        const uint32_t nrows0 = (npiece + 31) / 32;
-        if (lane < PIECE_ROWS) S.pend[lane] = lane < nrows0 ? (32 * (lane + 1) <= npiece ? 0xFFFFFFFFu : (1u << (npiece - 32 * lane)) - 1) : 0u;
-    }
-    __syncwarp();
-    // ---- 4. literal bytes, one output word per lane and step.  Bytes of a word that belong to reference segments
-    //         are stored as zero (= "not final yet", see phase 5); only ZERO-valued literals need a bit in the bitmap ----
-    uint8_t *dstu = V.arena + B0;
-    uint32_t anyz = 0;
-    for (uint32_t u0 = 0; u0 < nu; u0 += 128) {
-        const uint32_t u = u0 + 4 * lane;
-        uint32_t m = 0, wv = 0, hz = 0;
-        if (u < nu) {
-            const uint32_t sw = S.startb[u >> 5], sh = u & 31;
-            const uint32_t gi = S.wprefix[u >> 5] + __popc(sw & ((1u << sh) - 1));  // governing entry of the word's first byte
-            const uint32_t nibs = (sw >> sh) & 0xFu;
-            const uint32_t ed = S.seg_ed[gi];
-            const uint32_t lo = max(u, ed & 0xFFFFu);
-            const uint32_t hi = min(nibs ? u + __ffs(nibs) - 1 : u + 4, nu);
-            if (lo < hi) {
-                m = ((1u << (hi - u)) - 1) & ~((1u << (lo - u)) - 1);
-                const uint32_t bm = bytemask4(m);
-                const uint32_t q = min((u - mis + (ed >> 16)) & 0xFFFFu, STG_BYTES - 8);
-                wv = __funnelshift_r(S.stg[q >> 2], S.stg[(q >> 2) + 1], 8 * (q & 3)) & bm;
-                hz = (wv - 0x01010101u) & ~wv & 0x80808080u & bm;  // (superset of) the zero-valued literal bytes
-                if (u >= mis && u + 4 <= nu) {
-                    *reinterpret_cast<uint32_t *>(dstu + u) = wv;
+                    for (int i = 0; i < 9; i++) sw[i] = S.stg[(q >> 2) + i];   // (reads past the run stay inside the warp's shared memory)
+                    // zero-valued literals are announced in the bitmap: the staged zero bits, restricted to the run
+                    zb = __funnelshift_r(S.zbm[q >> 5], S.zbm[(q >> 5) + 1], q & 31) & (0xFFFFFFFFu >> (32 - n));
                 } else {
+                    const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(V.arena + (q - sa));
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if ((m >> i) & 1u) dstu[u + i] = (uint8_t) (wv >> (8 * i));
+                    for (int i = 0; i < 9; i++) sw[i] = (uint32_t) i < nsw ? __ldcg(wp0 + i) : 0xFFFFFFFFu;
+                    // (exact test: the bytes around the range are forced nonzero first)
+                    const uint32_t end = sa + n, L = (end - 1) >> 2, e8 = 8 * (end & 3);
+                    uint32_t z = haszero(sw[0] | ((1u << (8 * sa)) - 1));
+#pragma unroll
+                    for (int i = 1; i < 9; i++) z |= haszero(sw[i]);
+                    // (the last word's bytes behind the range: re-test it with them forced nonzero)
+                    zb = 0;
+                    if (z) {
+                        uint32_t tmp[9];
+#pragma unroll
+                        for (int i = 0; i < 9; i++) tmp[i] = sw[i];
+                        (void) L;
+                        (void) e8;
+                        zb = zero_mask(tmp, sa, n);
+                    }
                 }
+                put_bytes(dstu + u, sw[0], sw[1], sw[2], sw[3], sw[4], sw[5], sw[6], sw[7], sw[8], sa, n);
+                if (zb) publish_zeros(P, B0 + u, zb);
             }
         }
-        if (__any_sync(FULL, hz != 0)) {  // rare: text has no zero bytes beyond the key terminator
-            uint32_t v = (m & ~nibnz(wv)) << (4 * (lane & 7));
-            v |= __shfl_xor_sync(FULL, v, 1);
-            v |= __shfl_xor_sync(FULL, v, 2);
-            v |= __shfl_xor_sync(FULL, v, 4);
-            if ((lane & 7) == 0) S.finw[(u0 >> 5) + (lane >> 3)] = v;
-            anyz = 1;
-        }
-    }
-    __syncwarp();
-    if (anyz) flush_final(S.finw, lm, fsh, ngw, lane, pub0, pub1, pub2);
-    if (trace && lane == 0) trace[4 * (size_t) w + 1] = globaltimer_ns();
-    // ---- 5. copy pieces, one per lane and row.  Finality travels IN BAND: the arena starts zeroed and a byte is only
-    //         ever stored with its final value, so a nonzero byte is final the moment it is visible; a final byte
-    //         whose value is zero is announced by its bit in V.fin (the bit IS the value, the byte itself needs no
-    //         store).  A piece loads its source words (L2-coherent relaxed loads), copies the bytes that are final,
-    //         remembers them in its done mask and retries the rest: no flag round trip, no fence, and the critical
-    //         path is the nesting depth of BYTES (measured before: flag + MEMBAR.ALL.GPU per hop ~ 5 us).  The
-    //         literal phase is over: the done masks take seg_ed's storage. ----
-    static_assert(SEG_MAX + 1 >= PIECE_MAX, "done masks do not fit in seg_ed");
-    uint32_t *const pdone = S.seg_ed;
-    for (uint32_t k = lane; k < npiece; k += 32) pdone[k] = 0;
-    __syncwarp();
-    uint32_t remaining = npiece, spins = 0, sweep = 3;  // (the first sweep examines every piece)
-    const uint32_t nrows = (npiece + 31) / 32;
-    for (; remaining; sweep++) {
-        uint32_t any = 0;
-        for (uint32_t row = 0; row < nrows; row++) {
-            const uint32_t pm = S.pend[row];
-            if (!pm) continue;
-            bool giveup = false, complete = false;
-            uint32_t meta = 0, a = 0, dn = 0, avail = 0;
-            if ((pm >> lane) & 1u) {
-                const uint32_t slot = row * 32 + lane;
-                meta = S.pc.meta[slot];
-                a = S.pc.src[slot];
-                const uint32_t per = (meta >> 17) & 31u, np = ((meta >> 12) & 31u) + 1, us = meta & 0xFFFu;
-                const uint32_t n = per ? per : np;  // source bytes
-                const uint32_t need = 0xFFFFFFFFu >> (32 - n);
-                dn = per ? 0u : pdone[slot];
-                uint32_t seen = 0;  // source bytes found final in this sweep
-                // a waiting piece costs one load per sweep: the source byte behind its first open byte; the whole
-                // window is examined when that byte has arrived (and every fourth sweep, for bytes out of order and
-                // for zero-valued ones).  Sweeps are what a dependency hop costs, and 32 warps per SM share the issue
-                // slots: the full examination of every piece in every sweep made a hop ~12 us.
-                bool look = (sweep & 3u) == 3u;
-                if (!look) {
-                    // (first open byte on even sweeps, last one on odd sweeps: looking at the first byte only makes a
-                    // byte wait for everything left of it in its piece, and with a source window that slides from
-                    // record to record that running maximum chains every record to its predecessor)
-                    const uint32_t open = need & ~dn;
-                    const uint32_t pj = a + ((sweep & 1u) ? 31u - (uint32_t) __clz(open) : (uint32_t) __ffs(open) - 1u);
-                    const uint32_t w0 = ld_poll_u32(reinterpret_cast<const uint32_t *>(V.arena + (pj & ~3u)));
-                    look = ((w0 >> (8 * (pj & 3))) & 0xFFu) != 0;
-                }
-                if (look) {
-                    const uint32_t sa = a & 3, nsw = (sa + n + 3) >> 2;  // aligned source words (<= 9)
-                    const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(V.arena + (a - sa));
-                    uint32_t sw[10];
-#pragma unroll
-                    for (int q = 0; q < 5; q++) sw[q] = (uint32_t) q < nsw ? ld_poll_u32(wp0 + q) : 0u;
-#pragma unroll
-                    for (int q = 5; q < 10; q++) sw[q] = 0;
-                    if (nsw > 5) {
-#pragma unroll
-                        for (int q = 5; q < 9; q++) sw[q] = (uint32_t) q < nsw ? ld_poll_u32(wp0 + q) : 0u;
-                    }
-                    // fast path (the common case): nothing copied yet and no zero among the source bytes, i.e. the whole
-                    // piece is final -> straight word copy.  (w - 0x01010101) & ~w & 0x80808080 flags zero bytes; bytes
-                    // outside [sa, sa + n) are forced nonzero.
-                    bool fast = false;
-                    if (!per && dn == 0) {
-                        const uint32_t end = sa + n, L = (end - 1) >> 2, e8 = 8 * (end & 3);
-                        const uint32_t mlo = (1u << (8 * sa)) - 1, mhi = e8 ? 0xFFFFFFFFu << e8 : 0u;
-                        uint32_t z = 0;
-#pragma unroll
-                        for (int q = 0; q < 9; q++) {
-                            uint32_t w = sw[q];
-                            if (q == 0) w |= mlo;
-                            if ((uint32_t) q == L) w |= mhi;
-                            if ((uint32_t) q > L) w = 0xFFFFFFFFu;
-                            z |= (w - 0x01010101u) & ~w & 0x80808080u;
-                        }
-                        fast = z == 0;
-                    }
-                    uint32_t zout = 0;  // copied bytes whose value is zero (destination coordinates of the piece)
-                    if (fast) {
-                        uint8_t *dst = dstu + us;
-                        const uint32_t hbe = min((4u - (us & 3)) & 3u, n);  // head bytes up to a destination word boundary
-                        const uint32_t x0 = __funnelshift_r(sw[0], sw[1], 8 * sa);
-#pragma unroll
-                        for (int i = 0; i < 3; i++)
-                            if ((uint32_t) i < hbe) dst[i] = (uint8_t) (x0 >> (8 * i));
-                        const uint32_t rem = n - hbe, m = rem >> 2, tb = rem & 3, so = sa + hbe;
-                        const uint32_t sh = 8 * (so & 3);
-                        if (so >> 2) {  // (0 or 1)
-#pragma unroll
-                            for (int q = 0; q < 9; q++) sw[q] = sw[q + 1];
-                        }
-                        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + hbe);
-                        uint32_t xt = 0;
-#pragma unroll
-                        for (int t = 0; t < 9; t++) {
-                            const uint32_t x = __funnelshift_r(sw[t], sw[t + 1], sh);
-                            if ((uint32_t) t < m) dw[t] = x;
-                            if ((uint32_t) t == m) xt = x;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 3; i++)
-                            if ((uint32_t) i < tb) reinterpret_cast<uint8_t *>(dw + m)[i] = (uint8_t) (xt >> (8 * i));
-                        avail = need;
-                        seen = need;
-                        dn = need;
-                        complete = true;
-                    } else {
-                        unsigned long long nzm = 0;
-#pragma unroll
-                        for (int q = 0; q < 5; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
-                        if (nsw > 5) {
-#pragma unroll
-                            for (int q = 5; q < 9; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
-                        }
-                        const uint32_t nz = (uint32_t) (nzm >> sa) & need;  // source bytes seen nonzero: final
-                        uint32_t zf = 0;  // source bytes that are final zeros
-                        const uint32_t zc = need & ~nz & ~dn;
-                        if (zc) {
-                            const uint32_t wi = a >> 5, bs = a & 31;
-                            uint32_t bits = ld_relaxed_u32(V.fin + wi) >> bs;
-                            if (bs + n > 32) bits |= ld_relaxed_u32(V.fin + wi + 1) << (32 - bs);
-                            zf = zc & bits;
-                        }
-                        seen = nz | zf;
-                        avail = seen & ~dn;
-                        if (per) avail = avail == need ? need : 0u;  // short periods are copied in one go
-                        if (avail && per) {
-                            uint8_t *dst = dstu + us;
-                            const uint32_t ph = meta >> 22;
-                            for (uint32_t j = 0; j < np; j += 4) {  // four loads in flight
-                                uint8_t bv[4];
-#pragma unroll
-                                for (int i = 0; i < 4; i++) bv[i] = __ldcg(V.arena + a + (ph + j + i) % per);
-#pragma unroll
-                                for (int i = 0; i < 4; i++)
-                                    if (j + i < np) {
-                                        dst[j + i] = bv[i];
-                                        if (bv[i] == 0) zout |= 1u << (j + i);
-                                    }
-                            }
-                            dn = 0xFFFFFFFFu >> (32 - np);
-                            complete = true;
-                        } else if (avail) {
-                            // destination word t holds piece bytes [4t - da, 4t - da + 4); its source bytes straddle the
-                            // aligned source words t + c and t + c + 1 (c = -1 when the source sits further left in its word)
-                            const uint32_t da = us & 3;
-                            const int delta = (int) sa - (int) da;
-                            const uint32_t sh = 8u * (uint32_t) (delta & 3);
-                            if (delta < 0) {
-#pragma unroll
-                                for (int q = 9; q > 0; q--) sw[q] = sw[q - 1];
-                                sw[0] = 0;
-                            }
-                            uint32_t *dw = reinterpret_cast<uint32_t *>(dstu + us - da);
-                            const unsigned long long am = (unsigned long long) avail << da;  // bytes to store, word coordinates
-                            const uint32_t ndw = (da + n + 3) >> 2;
-#pragma unroll
-                            for (int t = 0; t < 9; t++) {
-                                const uint32_t vm = (uint32_t) (am >> (4 * t)) & 0xFu;
-                                if ((uint32_t) t < ndw && vm) {
-                                    const uint32_t x = __funnelshift_r(sw[t], sw[t + 1], sh);
-                                    if (vm == 0xFu) {
-                                        dw[t] = x;
-                                    } else {
-#pragma unroll
-                                        for (int i = 0; i < 4; i++)
-                                            if ((vm >> i) & 1u) reinterpret_cast<uint8_t *>(dw + t)[i] = (uint8_t) (x >> (8 * i));
-                                    }
-                                }
-                            }
-                            zout = zf;
-                            dn |= avail;
-                            pdone[slot] = dn;
-                            complete = dn == need;
-                        }
-                    }
-                    if (zout) {  // announce the zero-valued bytes just copied
-                        const uint32_t B = B0 + us, bs = B & 31;
-                        red_relaxed_or_u32(V.fin + (B >> 5), zout << bs);
-                        if (bs && (zout >> (32 - bs))) red_relaxed_or_u32(V.fin + (B >> 5) + 1, zout >> (32 - bs));
-                    }
-                }
-                // a missing byte that its own tile handed to k_resolve will not become final in this kernel
-                if (!avail && (spins & 7u) == 7u) {
-                    const uint32_t miss = need & ~seen & ~dn;
-                    const uint32_t wi = a >> 5, bs = a & 31;
-                    giveup = spins >= giveup_spins || (ld_relaxed_u32(V.gup + wi) & (miss << bs)) != 0 ||
-                             (bs + n > 32 && (ld_relaxed_u32(V.gup + wi + 1) & (miss >> (32 - bs))) != 0);
-                }
-            }
-            uint32_t gb = __ballot_sync(FULL, giveup);
-            const uint32_t gmask = gb;
-            if (gb) {
-                // hand the pieces over: per byte source pointers (self-overlapping references folded onto their first
-                // period), one coalesced row of pointers per piece
-                while (gb) {
-                    const int r = __ffs(gb) - 1;
-                    gb &= gb - 1;
-                    const uint32_t rm = __shfl_sync(FULL, meta, r), ra = __shfl_sync(FULL, a, r);
-                    const uint32_t n = ((rm >> 12) & 31u) + 1, per = (rm >> 17) & 31u;
-                    if (lane < n) V.ptr[B0 + (rm & 0xFFFu) + lane] = ra + (per ? ((rm >> 22) + lane) % per : lane);
-                }
-                if (giveup) {
-                    const uint32_t B = B0 + (meta & 0xFFFu), n = ((meta >> 12) & 31u) + 1;
-                    const uint32_t bits = (0xFFFFFFFFu >> (32 - n)) & ~dn, bs = B & 31;  // the bytes still open
-                    atomicOr(V.gup + (B >> 5), bits << bs);
-                    if (bs + n > 32 && (bits >> (32 - bs))) atomicOr(V.gup + (B >> 5) + 1, bits >> (32 - bs));
-                }
-                if (lane == 0) atomicAdd(ctr + 2, (uint32_t) __popc(gmask));
-                remaining -= __popc(gmask);
-                any = 1;
-            }
-            const uint32_t cb = __ballot_sync(FULL, complete);
-            if (__ballot_sync(FULL, avail != 0)) any = 1;
-            if (cb | gmask) {
-                if (lane == 0) S.pend[row] = pm & ~(cb | gmask);
-                remaining -= __popc(cb);
-                __syncwarp();
+        // ---- 3b. long runs and long retired tokens: the whole warp copies ----
+        {
+            const bool tlong = emit && fast && len > 32;
+            uint32_t lm = __ballot_sync(FULL, rlong), tm = __ballot_sync(FULL, tlong);
+            while (lm | tm) {
+                const bool tok = lm == 0;
+                const uint32_t mm = tok ? tm : lm;
+                const int r = __ffs(mm) - 1;
+                if (tok) tm &= tm - 1;
+                else lm &= lm - 1;
+                warp_put(P, S.stg, tok, B0 + __shfl_sync(FULL, tok ? us : ru, r), __shfl_sync(FULL, tok ? sbase + ks : rsrc, r),
+                         __shfl_sync(FULL, tok ? len : rn, r));
             }
         }
         __syncwarp();
-        if (!any) {
-            if (++spins > SPIN_LIMIT || ld_relaxed_u32(err) != 0) {
-                if (lane == 0) atomicCAS(err, 0u, 8u);
-                return;
+        // ---- 3c. pending pieces of the tokens whose source is not retired: cut at the 32-byte boundaries of the SOURCE
+        //          (periods >= 32 also where they wrap).  Plain tokens of up to 32 bytes give one or two pieces and are
+        //          entered by their own lanes; the rest token by token ----
+        {
+            const bool pend = emit && !fast;
+            const bool simple = pend && per == 0 && len <= 32;
+            const uint32_t A = sbase + ks;
+            const uint32_t np = simple ? ((A + len - 1) >> 5) - (A >> 5) + 1 : 0u;   // 1 or 2
+            uint32_t pinc = np;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, pinc, dd);
+                if ((int) lane >= dd) pinc += o;
             }
-            if (spins > sleep_after) __nanosleep(spins > 256 ? 400 : sleep_ns);
-        } else {
-            spins = 0;
+            const uint32_t tot = __shfl_sync(FULL, pinc, 31);
+            if (tot) {
+                if (npiece + tot > piece_cap) {
+                    if (!drain()) failed = true;
+                }
+                if (!failed && tot <= piece_cap) {
+                    if (np) {
+                        const uint32_t slot = npiece + pinc - np, cut = ((A >> 5) + 1) << 5;  // first 32-byte boundary behind A
+                        const uint32_t n0 = np == 2 ? cut - A : len;
+                        S.pc.src[slot] = A;
+                        S.pc.meta[slot] = us | ((n0 - 1) << 12);
+                        if (np == 2) {
+                            S.pc.src[slot + 1] = cut;
+                            S.pc.meta[slot + 1] = (us + n0) | ((len - n0 - 1) << 12);
+                        }
+                    }
+                    npiece += tot;
+                }
+            }
+            // (with a tiny piece_cap - a test knob - even the simple tokens of one round may not fit: one by one then)
+            uint32_t pm = __ballot_sync(FULL, pend && (!simple || tot > piece_cap));
+            __syncwarp();
+            while (pm && !failed) {
+                const int r = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t tsb = __shfl_sync(FULL, sbase, r), tper = __shfl_sync(FULL, per, r), tks = __shfl_sync(FULL, ks, r);
+                const uint32_t tus = __shfl_sync(FULL, us, r), tlen = __shfl_sync(FULL, len, r);
+                // the token's pieces one after the other (all lanes walk, lane 0 writes)
+                const bool shortp = tper != 0 && tper < 32;
+                const uint32_t wrap = tper ? tper : 0xFFFFFFFFu;
+#pragma unroll 1
+                for (uint32_t pos = tks, o = 0; o < tlen;) {
+                    if (npiece == piece_cap) {
+                        if (!drain()) {
+                            failed = true;
+                            break;
+                        }
+                    }
+                    uint32_t n;
+                    if (shortp) {
+                        // short period: a piece covers 32 destination bytes and reads the whole first period
+                        n = min(32u, tlen - o);
+                        if (lane == 0) {
+                            S.pc.src[npiece] = tsb;
+                            S.pc.meta[npiece] = (tus + o) | ((n - 1) << 12) | (tper << 17) | (((tks + o) % tper) << 22);
+                        }
+                    } else {
+                        n = min(min(32u - ((tsb + pos) & 31u), wrap - pos), tlen - o);
+                        if (lane == 0) {
+                            S.pc.src[npiece] = tsb + pos;
+                            S.pc.meta[npiece] = (tus + o) | ((n - 1) << 12);
+                        }
+                        pos = pos + n == wrap ? 0u : pos + n;
+                    }
+                    npiece++;
+                    o += n;
+                    __syncwarp();
+                }
+            }
         }
+        // carries for the next round
+        aoff_cur = aoff_next;
+        const uint32_t last = min(nheads - c0, 32u) - 1;
+        carry_out = __shfl_sync(FULL, end_out, last);
+        carry_stg = __shfl_sync(FULL, end_stg, last);
+        D += __shfl_sync(FULL, inc, last);
+    }
+    if (!failed) {
+        if ((int) ne + D < (int) (skip + nbytes)) {
+            if (lane == 0) atomicExch(err, 6u);
+            failed = true;
+        }
+    }
+    // ---- 4. the literal run behind the last token ----
+    if (!failed) {
+        const int lo = max(carry_out, 0);
+        if (lo < (int) nbytes) warp_put(P, S.stg, false, B0 + (uint32_t) lo + mis, carry_stg + (uint32_t) (lo - carry_out), nbytes - (uint32_t) lo);
+    }
+    if (trace && lane == 0) trace[4 * (size_t) w + 1] = globaltimer_ns();
+    // ---- 5. pending pieces ----
+    __syncwarp();
+    if (npiece != 0 && !failed) drain();
+    // ---- 6. "complete" (a failed tile announces itself too: the error flag is what the host reads, and waiting tiles
+    //         must not hang) ----
+    __syncwarp();
+    if (lane == 0) {
+        fence_gpu();                                        // the tile's bytes are visible before its state is
+        st_relaxed_u64(V.ts + sidx, my_end | 2ull);
     }
     if (trace && lane == 0) {  // measurement aid (PIXIU_DEC_TRACE_FILE): entry, end of the literal phase, done, sweeps
         trace[4 * (size_t) w + 2] = globaltimer_ns();
-        trace[4 * (size_t) w + 3] = sweep;
+        trace[4 * (size_t) w + 3] = sweeps;
     }
+    }  // next ticket
 }
 
-// K11 (only when K10 handed pieces over): a warp per 1 KiB of arena looks at its 32 words of the hand-over bitmap
-// and, for every word with bits set, resolves the 32 bytes one per lane: each handed-over byte chases its pointer
-// chain to a final byte.  Chains longer than RESOLVE_HOPS park their progress in the pointer array and the kernel is
-// re-run: concurrent shortening makes the remaining rounds logarithmic in the nesting depth.  Final bytes are only
-// read, never written, so no thread waits on another.
+// clears the words of the zero-byte bitmap a decode call has set bits in (the bitmap stays all-zero between calls)
 __global__ void __launch_bounds__(256)
-k_resolve(uint32_t n, uint8_t *__restrict__ arena, uint32_t *__restrict__ ptr, const uint32_t *__restrict__ fin,
-          uint32_t *__restrict__ gup, uint32_t *__restrict__ unfinished, uint32_t *__restrict__ err) {
-    const uint32_t lane = lane_id();
-    const uint32_t w0 = ((blockIdx.x * 256 + threadIdx.x) >> 5) * 32;  // first bitmap word of the warp
-    const uint32_t nwords = (n + 31) >> 5;
-    bool pending = false;
-    const uint32_t mine = w0 + lane < nwords ? gup[w0 + lane] : 0u;
-    uint32_t todo = __ballot_sync(0xffffffffu, mine != 0);
-    while (todo) {
-        const int k = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t bits = __shfl_sync(0xffffffffu, mine, k);
-        const uint32_t i = (w0 + k) * 32 + lane;
-        bool done = true;
-        if ((bits >> lane) & 1u) {
-            uint32_t p = ptr[i];
-            done = false;
-            for (int h = 0; h < RESOLVE_HOPS; h++) {
-                if (p >= i) {  // sources always precede their byte in the arena: corrupt input
-                    atomicExch(err, 7u);
-                    done = true;
-                    p = i;
-                    break;
-                }
-                const uint8_t bv = __ldcg(arena + p);  // final = nonzero, or a zero announced in the bitmap
-                if (bv != 0 || ((fin[p >> 5] >> (p & 31)) & 1u)) {
-                    arena[i] = bv;
-                    done = true;
-                    break;
-                }
-                p = ptr[p];
-            }
-            if (p != i) ptr[i] = p;  // the final origin, or an ancestor further up the chain
-            pending |= !done;
-        }
-        // bytes resolved for good leave the bitmap (later rounds skip them; chains through them end at ptr -> final)
-        const uint32_t still = __ballot_sync(0xffffffffu, !done);
-        if (lane == 0 && still != bits) gup[w0 + k] = still;
-    }
-    if (__syncthreads_or(pending) && threadIdx.x == 0) atomicAdd(unfinished, 1u);
+k_fin_clean(uint32_t *__restrict__ fin, const uint32_t *__restrict__ dirty, const uint32_t *__restrict__ ctr, uint32_t cap) {
+    const uint32_t n = min(ctr[DC_DIRTY], cap);
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) fin[dirty[i]] = 0;
 }
 
 // K12: arena -> caller layout, one warp per requested record
@@ -767,13 +967,6 @@ k_copy_records(uint32_t n, const uint32_t *__restrict__ recs, const uint64_t *__
 
 // Work list of a decode call, built on the device.  The host describes the touched chunks (a few hundred ranges at
 // most); everything per record or per tile is derived here from the record tables already resident in HBM.
-struct DecRange {
-    uint32_t first, last;      // records [first, last] of one chunk form a contiguous part of the arena
-    uint32_t tile_lo, ntiles;  // their decode tiles (global tile ids are consecutive inside a chunk)
-    uint32_t rec_cum, tile_cum;  // records / tiles of the ranges before this one
-    uint32_t arena_base, pad;
-};
-
 // arena offset of every record of the ranges
 __global__ void __launch_bounds__(256)
 k_dec_aoff(uint32_t n_rec, uint32_t n_ranges, const DecRange *__restrict__ R, const uint64_t *__restrict__ dec_prefix,
@@ -791,12 +984,14 @@ k_dec_aoff(uint32_t n_rec, uint32_t n_ranges, const DecRange *__restrict__ R, co
     aoff[g] = r.arena_base + (uint32_t) (dec_prefix[g] - dec_prefix[r.first]);
 }
 
-// (tile, record) of every work item.  Tiles of one chunk keep their order (the data-flow argument needs it); chunks
-// are interleaved round-robin, so that as many dependency chains as there are chunks advance side by side: the
-// k-th tile of range c goes to position sum_c' min(ntiles_c', k) + #{c' < c : ntiles_c' > k}.
+// One TileJob per work item.  Tiles of one chunk keep their order (the data-flow argument needs it); chunks are
+// interleaved round-robin, so that as many dependency chains as there are chunks advance side by side: the k-th tile
+// of range c goes to position sum_c' min(ntiles_c', k) + #{c' < c : ntiles_c' > k}.
 __global__ void __launch_bounds__(256)
 k_dec_work(uint32_t n_work, uint32_t n_ranges, const DecRange *__restrict__ R, const uint32_t *__restrict__ tile_base,
-           uint32_t *__restrict__ work_tile, uint32_t *__restrict__ work_rec) {
+           const uint32_t *__restrict__ tile_desc, const uint64_t *__restrict__ enc_off, const uint32_t *__restrict__ enc_len,
+           const uint32_t *__restrict__ dec_len, const uint32_t *__restrict__ first, const uint32_t *__restrict__ aoff,
+           const uint8_t *__restrict__ enc, TileJob *__restrict__ jobs) {
     const uint32_t j = blockIdx.x * 256 + threadIdx.x;
     if (j >= n_work) return;
     uint32_t lo = 0, hi = n_ranges;
@@ -818,8 +1013,32 @@ k_dec_work(uint32_t n_work, uint32_t n_ranges, const DecRange *__restrict__ R, c
         if (tile_base[mid] <= gt) a = mid;
         else b = mid;
     }
-    work_tile[pos] = gt;
-    work_rec[pos] = a;
+    const uint32_t g = a, t = gt - tile_base[g];
+    const uint32_t dl = dec_len[g], el = enc_len[g];
+    const uint32_t t0 = t * TILE, t1 = min(dl, t0 + TILE);
+    const uint32_t desc = tile_desc[gt];
+    const uint32_t e0 = desc & 0xffff;
+    uint32_t e_end = el;
+    if (t1 < dl) {
+        const uint32_t d2 = tile_desc[gt + 1];
+        e_end = d2 & 0xffff;
+        const uint32_t sk2 = d2 >> 16;
+        if (sk2 != 0 && sk2 != 0xFFFF) e_end += (enc[enc_off[g] + e_end + 1] == 1) ? 8u : 6u;
+    }
+    uint32_t ne = e_end - e0;
+    if (e_end > el || e_end < e0 || ne > ENC_MAX) ne = 0xFFFFu;  // inconsistent descriptor: the tile's warp reports it
+    TileJob J;
+    J.enc_pos = enc_off[g] + e0;
+    J.rec_base = aoff[g];
+    J.g = g;
+    J.t0_nbytes = t0 | ((t1 - t0) << 16);
+    J.ne_skip = ne | (desc & 0xFFFF0000u);
+    J.chunk_first = first[g];
+    J.range = lo;
+    J.sidx = j;            // (= tile_cum + k: states are kept in range-major order)
+    J.kidx = k;
+    J.pad0 = J.pad1 = 0;
+    jobs[pos] = J;
 }
 
 // ---------------------------------------------------------------------------------
@@ -830,8 +1049,7 @@ k_dec_work(uint32_t n_work, uint32_t n_ranges, const DecRange *__restrict__ R, c
 void Store::decode_records(const std::vector<uint32_t> &recs, uint8_t *d_out, const std::vector<uint64_t> &out_off) {
     if (recs.empty()) return;
     if (mirror_from < n_records()) flush_mirrors();  // the running sum below is built from the host mirrors
-    const char *lim_env = getenv("PIXIU_DEC_ARENA_LIMIT");  // test knob
-    const uint64_t LIMIT = lim_env ? (uint64_t) atoll(lim_env) : (7ull << 29);  // 3.5 GiB
+    const uint64_t LIMIT = knobs.dec_arena_limit;  // 3.5 GiB unless the test knob says otherwise
     // arena bytes per touched chunk: records [first, max requested]
     std::map<uint32_t, uint32_t> cmax;
     uint32_t last_f = 0xFFFFFFFFu, *last_max = nullptr;
@@ -941,80 +1159,63 @@ void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const
     }
     if (!direct) dec_scratch.reserve_discard(arena_bytes + 256);  // same packed layout, private buffer
     uint8_t *arena = direct ? d_out : dec_scratch.p;
+    // zero-byte bitmap: all-zero between calls (a (re)allocation zeroes it once; a call clears the words it dirtied)
     const size_t bm_words = arena_bytes / 32 + 64;
-    dec_flags.reserve_discard(2 * bm_words);                  // zero-byte bitmap, then the "handed over" bitmap
-    dec_ptr.reserve_discard(arena_bytes + 64);                // source pointers (touched only for handed-over bytes)
+    if (bm_words > dec_flags.cap) {
+        dec_flags.reserve_discard(bm_words);
+        PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, dec_flags.cap * sizeof(uint32_t), st));
+    }
+    const size_t dirty_cap = std::max<size_t>(arena_bytes / 128, 4096);
+    dec_dirty.reserve_discard(dirty_cap);
     dec_aoff.reserve_discard(NR + 1);
-    dec_work.reserve_discard(2 * n_work + 2);
+    dec_work.reserve_discard((n_work + 1) * (sizeof(TileJob) / sizeof(uint32_t)));
+    // per-tile states (+ end offsets) and the per-range hints: one buffer, zeroed per call (8 B per 2 KiB tile)
+    const size_t sync_words = 2 * n_work + 4 * ranges.size() + 8;
+    dec_sync.reserve_discard(sync_words);
+    PX_CUDA(cudaMemsetAsync(dec_sync.p, 0, sync_words * sizeof(uint32_t), st));
     dec_ranges.reserve_discard(ranges.size() * sizeof(DecRange) / sizeof(uint32_t) + 8);
     DecRange *d_ranges = reinterpret_cast<DecRange *>(dec_ranges.p);
     PX_CUDA(cudaMemcpyAsync(d_ranges, ranges.data(), ranges.size() * sizeof(DecRange), cudaMemcpyHostToDevice, st));
     k_dec_aoff<<<(unsigned) div_up<uint64_t>(n_rec, 256), 256, 0, st>>>((uint32_t) n_rec, (uint32_t) ranges.size(), d_ranges,
                                                                         d_dec_prefix.p, dec_aoff.p);
-    k_dec_work<<<(unsigned) div_up<uint64_t>(n_work, 256), 256, 0, st>>>((uint32_t) n_work, (uint32_t) ranges.size(), d_ranges,
-                                                                         d_tile_base.p, dec_work.p, dec_work.p + n_work);
+    TileJob *d_jobs = reinterpret_cast<TileJob *>(dec_work.p);
+    k_dec_work<<<(unsigned) div_up<uint64_t>(n_work, 256), 256, 0, st>>>(
+        (uint32_t) n_work, (uint32_t) ranges.size(), d_ranges, d_tile_base.p, d_tile_desc.p, d_enc_off.p, d_enc_len.p, d_dec_len.p,
+        d_first.p, dec_aoff.p, d_enc.ptr(), d_jobs);
     launches += 2;
     dec_ctr.reserve_discard(64);
-    PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));  // [0] error, [1] tile ticket, [2] pieces handed over
-    PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, 2 * bm_words * sizeof(uint32_t), st));
-    DecodeView V{d_enc.ptr(), d_enc_off.p, d_enc_len.p, d_dec_len.p, d_first.p, d_tile_base.p, d_tile_desc.p,
-                 dec_aoff.p, arena, dec_flags.p, dec_flags.p + bm_words, dec_ptr.p};
+    PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));
+    DecodeView V{d_enc.ptr(), d_jobs, dec_aoff.p, d_ranges, arena, dec_flags.p, dec_dirty.p, (uint32_t) dirty_cap,
+                 reinterpret_cast<unsigned long long *>(dec_sync.p), reinterpret_cast<DecSync *>(dec_sync.p + 2 * n_work + (2 * n_work % 4))};
     const size_t smem = sizeof(WarpSmem) * DEC_WARPS;
     // (per device and cheap: no process-wide "already done" flag, a process may drive several GPUs)
     PX_CUDA(cudaFuncSetAttribute(k_decode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    const char *gs = getenv("PIXIU_GIVEUP_SPINS");  // tuning knob
-    const uint32_t giveup_spins = gs ? (uint32_t) atoi(gs) : GIVEUP_SPINS;
-    const char *pcs = getenv("PIXIU_PIECE_CAP");    // test knob: forces the spill path of the piece table
-    const uint32_t piece_cap = pcs ? std::min<uint32_t>((uint32_t) atoi(pcs), PIECE_MAX) : PIECE_MAX;
-    const char *sa_ = getenv("PIXIU_SLEEP_AFTER"), *sn_ = getenv("PIXIU_SLEEP_NS");  // tuning knobs of the poll back-off
-    const uint32_t sleep_after = sa_ ? (uint32_t) atoi(sa_) : 16u, sleep_ns = sn_ ? (uint32_t) atoi(sn_) : 64u;
-    if (getenv("PIXIU_TRACE"))
+    const uint32_t piece_cap = std::min<uint32_t>(std::max<uint32_t>(knobs.piece_cap, 1u), PEND_MAX);
+    if (knobs.trace)
         fprintf(stderr, "[decode] host work list %.3f ms\n",
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h0).count());
     unsigned long long *d_trace = nullptr;
-    const char *trace_file = getenv("PIXIU_DEC_TRACE_FILE");  // measurement aid: per-tile entry / parsed / done times + sweeps
+    const char *trace_file = knobs.dec_trace_file.empty() ? nullptr : knobs.dec_trace_file.c_str();  // measurement aid
     if (trace_file) {
         PX_CUDA(cudaMalloc(&d_trace, 4 * n_work * sizeof(unsigned long long)));
         PX_CUDA(cudaMemsetAsync(d_trace, 0, 4 * n_work * sizeof(unsigned long long), st));
     }
     PX_CUDA(cudaEventRecord(ev0, st));
     prof.begin(PC_DECODE, st);
-    PX_CUDA(cudaMemsetAsync(arena, 0, arena_bytes, st));  // zero = "not final yet" (k_decode_tiles, phase 5): timed with the kernel
-    k_decode_tiles<<<(unsigned) div_up<uint64_t>(n_work, DEC_WARPS), DEC_WARPS * 32, smem, st>>>(
-        V, dec_work.p, dec_work.p + n_work, (uint32_t) n_work, dec_ctr.p, giveup_spins, piece_cap, sleep_after, sleep_ns, d_trace);
-    int nl = 1;
-    uint32_t h_ctr[4] = {0, 0, 0, 0};
-    PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaStreamSynchronize(st));
-    last_handed_over = h_ctr[2];
-    if (d_trace) {  // file: u64 n_work, u32 record[n_work] (ticket order), u64 {entry, parsed, done (ns), sweeps}[n_work]
-        std::vector<unsigned long long> ht(4 * n_work);
-        std::vector<uint32_t> hr(n_work);
-        PX_CUDA(cudaMemcpy(ht.data(), d_trace, ht.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        PX_CUDA(cudaMemcpy(hr.data(), dec_work.p + n_work, n_work * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        if (FILE *f = fopen(trace_file, "wb")) {
-            const unsigned long long nw = n_work;
-            fwrite(&nw, 8, 1, f);
-            fwrite(hr.data(), 4, n_work, f);
-            fwrite(ht.data(), 8, ht.size(), f);
-            fclose(f);
-        }
-        cudaFree(d_trace);
+    if (!dec_sms) {
+        int dev = 0, sms = 0;
+        PX_CUDA(cudaGetDevice(&dev));
+        PX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        dec_sms = (uint32_t) sms;
     }
-    if (getenv("PIXIU_TRACE")) fprintf(stderr, "[decode] %llu tiles, %u pieces handed to k_resolve\n", (unsigned long long) n_work, h_ctr[2]);
-    if (h_ctr[0] == 0 && h_ctr[2] != 0) {
-        // deep reference chains: the pieces the data-flow pass handed over are resolved by pointer chasing
-        for (int round = 0; round < 40; round++) {
-            k_resolve<<<(unsigned) div_up<uint64_t>(div_up<uint64_t>(arena_bytes, 32), 256), 256, 0, st>>>(
-                (uint32_t) arena_bytes, arena, dec_ptr.p, V.fin, V.gup, dec_ctr.p + 3 + round, dec_ctr.p);
-            nl++;
-            PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            PX_CUDA(cudaMemcpyAsync(h_ctr + 3, dec_ctr.p + 3 + round, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            PX_CUDA(cudaStreamSynchronize(st));
-            if (h_ctr[0] || h_ctr[3] == 0) break;
-        }
-        if (h_ctr[0] == 0 && h_ctr[3] != 0) h_ctr[0] = 9;  // chains did not resolve
-    }
+    // persistent warps: one CTA slot per resident CTA of every SM (148 x 8 on a B200), fewer for small calls
+    const unsigned dec_grid = (unsigned) std::min<uint64_t>(div_up<uint64_t>(n_work, DEC_WARPS), (uint64_t) dec_sms * PIXIU_DEC_MINB);
+    k_decode_tiles<<<dec_grid, DEC_WARPS * 32, smem, st>>>(
+        V, (uint32_t) n_work, dec_ctr.p, piece_cap, knobs.sleep_after, knobs.sleep_ns, d_trace);
+    k_fin_clean<<<64, 256, 0, st>>>(dec_flags.p, dec_dirty.p, dec_ctr.p, (uint32_t) dirty_cap);
+    int nl = 2;
+    uint32_t h_ctr[8] = {0};
+    PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (!direct) {
         // requested records -> caller layout
         DevBuf<uint32_t> &d_recs = dec_reqs;
@@ -1035,7 +1236,36 @@ void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const
     PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     last_get_ms = ms;
     prof.collect();
-    if (h_ctr[0]) throw std::runtime_error("decode: kernel reported error " + std::to_string(h_ctr[0]));
+    last_pending_pieces = h_ctr[DC_PENDING];
+    last_drains = h_ctr[DC_DRAINS];
+    if (h_ctr[DC_DIRTY] > dirty_cap)  // more dirty words than the list holds (zero-heavy data): clear the whole bitmap
+        PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, dec_flags.cap * sizeof(uint32_t), st));
+    if (d_trace) {  // file: u64 n_work, u32 record[n_work] (ticket order), u64 {entry, parsed, done (ns), sweeps}[n_work]
+        std::vector<unsigned long long> ht(4 * n_work);
+        std::vector<uint32_t> hr(n_work);
+        PX_CUDA(cudaMemcpy(ht.data(), d_trace, ht.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        {
+            std::vector<TileJob> hj(n_work);
+            PX_CUDA(cudaMemcpy(hj.data(), d_jobs, n_work * sizeof(TileJob), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n_work; i++) hr[i] = hj[i].g;
+        }
+        if (FILE *f = fopen(trace_file, "wb")) {
+            const unsigned long long nw = n_work;
+            fwrite(&nw, 8, 1, f);
+            fwrite(hr.data(), 4, n_work, f);
+            fwrite(ht.data(), 8, ht.size(), f);
+            fclose(f);
+        }
+        cudaFree(d_trace);
+    }
+    if (knobs.trace)
+        fprintf(stderr, "[decode] %llu tiles, %u pending pieces in %u drains, %u tiles waited for the literal watermark, %u dirty bitmap words\n",
+                (unsigned long long) n_work, h_ctr[DC_PENDING], h_ctr[DC_DRAINS], h_ctr[DC_WAITS], h_ctr[DC_DIRTY]);
+    if (h_ctr[DC_ERR]) {
+        // (the bitmap may hold bits of tiles that never finished)
+        PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, dec_flags.cap * sizeof(uint32_t), st));
+        throw std::runtime_error("decode: kernel reported error " + std::to_string(h_ctr[DC_ERR]));
+    }
 }
 
 // Host-side token walk of one encoded record: validates it, returns its decoded length and

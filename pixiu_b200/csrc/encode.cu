@@ -943,12 +943,12 @@ static void build_suffix_array(Store &S, uint32_t N) {
         PX_CUDA(cudaStreamSynchronize(st));
         if (h_cnt[2]) throw std::runtime_error("radix sort look-back timed out");
         uint32_t An = h_cnt[0], G = h_cnt[1];
-        if (getenv("PIXIU_TRACE")) fprintf(stderr, "[sa] N=%u sorted_by=%u active=%u groups=%u\n", N, h, An, G);
+        if (S.knobs.trace) fprintf(stderr, "[sa] N=%u sorted_by=%u active=%u groups=%u\n", N, h, An, G);
         if (An == 0) break;
         if (h > 65535u) throw std::runtime_error("suffix array: groups left after h > 65535");
         const uint32_t gmax = h_cnt[3], nlarge = h_cnt[4];
         PX_CUDA(cudaMemsetAsync(d_cnt + 3, 0, 2 * sizeof(uint32_t), st));
-        if (gmax <= GS_MAX && !getenv("PIXIU_NO_SEGSORT")) {
+        if (gmax <= GS_MAX && !S.knobs.no_segsort) {
             // (3a) every group fits a CTA: sort the groups independently by rank[i+h]
             uint32_t *vout = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
             S.prof.begin(PC_ROUND_KEYS, st);
@@ -1134,7 +1134,7 @@ uint32_t Store::count_nodes_and_cut(uint32_t first_new, uint32_t s0, uint32_t N)
         pool_nth = nth;
         pool_used = used;
     }
-    if (getenv("PIXIU_TRACE")) {
+    if (knobs.trace) {
         auto t_c = std::chrono::steady_clock::now();
         fprintf(stderr, "[rot] cand=%u accepted=%u nth=%u wait+d2h=%.3f ms replay=%.3f ms rho=%.3f\n", win_R - first_new, accepted,
                 pool_nth, std::chrono::duration<double, std::milli>(t_b - t_a).count(),
@@ -1166,7 +1166,7 @@ void Store::enc_phase_a(uint32_t first_new) {
     // ---- LCP + trees ----
     E.lcp.reserve_discard(N);
     prof.begin(PC_LCP, st);
-    if (getenv("PIXIU_LCP_KASAI")) {  // (knob: the one-pass Kasai walk, for A/B measurements)
+    if (knobs.lcp_kasai) {  // (knob: the one-pass Kasai walk, for A/B measurements)
         k_lcp<<<div_up<uint32_t>(div_up<uint32_t>(N, LCP_SEG), 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, N, E.lcp.p);
         L++;
     } else {
@@ -1411,7 +1411,7 @@ void Store::enc_emit_all() {
 uint32_t Store::encode_window_records(uint32_t first_new) {
     enc_phase_a(first_new);
     enc_phase_b();
-    if (!getenv("PIXIU_NO_SPEC_EMIT")) enc_emit_all();  // (knob: A/B measurement)
+    if (!knobs.no_spec_emit) enc_emit_all();  // (knob: A/B measurement)
     apply_rotation_cut();
     return enc_phase_c(nullptr, nullptr, nullptr);
 }
@@ -1529,7 +1529,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     last_set_ms = ms;
     prof.collect();
-    if (getenv("PIXIU_TRACE")) {
+    if (knobs.trace) {
         const auto t_end = std::chrono::steady_clock::now();
         fprintf(stderr, "[setitem] n=%u encode(wall)=%.3f ms index=%.3f ms gpu(events)=%.3f ms\n", nn,
                 std::chrono::duration<double, std::milli>(t_gpu_done - t_begin).count(),

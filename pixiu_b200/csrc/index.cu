@@ -437,7 +437,7 @@ void HostIndex::insert_batch(Store &S, uint32_t n, const uint8_t *d_keys, const 
     cudaStream_t st = S.st;
     std::vector<uint8_t> q;
     uint32_t a = 0;
-    const bool trace = getenv("PIXIU_TRACE") != nullptr;
+    const bool trace = S.knobs.trace;
     double t_probe = 0, t_apply = 0, t_sync = 0;
     bool reserved = false;
     uint64_t n_fallback = 0, n_rounds = 0;

@@ -65,8 +65,49 @@ struct EncodeScratch {
     DevBuf<uint16_t> gidx;
 };
 
+// Tuning / test knobs: read from the environment ONCE, when the store is created (never on a hot path); tests change
+// them afterwards through pixiu_debug_set_knob.
+struct Knobs {
+    bool trace = false;            // PIXIU_TRACE: phase trace lines on stderr
+    bool lcp_kasai = false;        // PIXIU_LCP_KASAI: the one-pass Kasai walk (A/B measurements)
+    bool no_spec_emit = false;     // PIXIU_NO_SPEC_EMIT: emit after the rotation cut instead of beside it (A/B)
+    bool no_segsort = false;       // PIXIU_NO_SEGSORT: radix sort only (A/B)
+    uint64_t dec_arena_limit = 7ull << 29;  // PIXIU_DEC_ARENA_LIMIT: decoded bytes of one decode pass (3.5 GiB)
+    uint32_t piece_cap = 0xFFFFFFFFu;       // PIXIU_PIECE_CAP: pending pieces a decode tile keeps before it drains them
+    uint32_t sleep_after = 16, sleep_ns = 64;  // PIXIU_SLEEP_AFTER / _NS: back-off of the decoder's polls
+    std::string dec_trace_file;    // PIXIU_DEC_TRACE_FILE: per-tile timestamps of a decode call
+    void from_env() {
+        auto num = [](const char *n, uint64_t dflt) -> uint64_t {
+            const char *v = getenv(n);
+            return v ? (uint64_t) atoll(v) : dflt;
+        };
+        trace = getenv("PIXIU_TRACE") != nullptr;
+        lcp_kasai = getenv("PIXIU_LCP_KASAI") != nullptr;
+        no_spec_emit = getenv("PIXIU_NO_SPEC_EMIT") != nullptr;
+        no_segsort = getenv("PIXIU_NO_SEGSORT") != nullptr;
+        dec_arena_limit = num("PIXIU_DEC_ARENA_LIMIT", dec_arena_limit);
+        piece_cap = (uint32_t) num("PIXIU_PIECE_CAP", piece_cap);
+        sleep_after = (uint32_t) num("PIXIU_SLEEP_AFTER", sleep_after);
+        sleep_ns = (uint32_t) num("PIXIU_SLEEP_NS", sleep_ns);
+        if (const char *f = getenv("PIXIU_DEC_TRACE_FILE")) dec_trace_file = f;
+    }
+    bool set(const std::string &name, int64_t v) {
+        if (name == "dec_arena_limit") dec_arena_limit = (uint64_t) v;
+        else if (name == "piece_cap") piece_cap = (uint32_t) v;
+        else if (name == "sleep_after") sleep_after = (uint32_t) v;
+        else if (name == "sleep_ns") sleep_ns = (uint32_t) v;
+        else if (name == "trace") trace = v != 0;
+        else if (name == "lcp_kasai") lcp_kasai = v != 0;
+        else if (name == "no_spec_emit") no_spec_emit = v != 0;
+        else if (name == "no_segsort") no_segsort = v != 0;
+        else return false;
+        return true;
+    }
+};
+
 struct Store {
     pixiu_config cfg{};
+    Knobs knobs;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_nodes = nullptr;
     std::string err;
@@ -135,17 +176,19 @@ struct Store {
     // ---- decode scratch ----
     DevBuf<uint8_t> dec_scratch;   // decoded arena when the caller's layout differs from arena order
     DevBuf<uint64_t> dec_loc;      // output offsets of the requested records
-    DevBuf<uint32_t> dec_flags;    // "final" bitmap of the arena (1 bit per byte), then the "handed over" bitmap
-    DevBuf<uint32_t> dec_ptr;      // source pointer of every arena byte handed to k_resolve
-    uint64_t last_handed_over = 0; // pieces the last decode handed to k_resolve
+    DevBuf<uint32_t> dec_flags;    // zero-byte bitmap of the arena (1 bit per byte; all-zero between calls)
+    DevBuf<uint32_t> dec_dirty;    // words of that bitmap the running call has set bits in
+    DevBuf<uint32_t> dec_sync;     // per tile: state, end offset; per range: the two in-order watermarks (zeroed per call)
+    uint32_t dec_sms = 0;          // SM count of the store's device (grid of the persistent decode kernel)
+    uint64_t last_pending_pieces = 0, last_drains = 0;  // pending (polled) pieces of the last decode and its drain passes
     DevBuf<uint32_t> dec_aoff;     // per record: offset in the arena
     DevBuf<uint32_t> dec_reqs;     // requested record ids
-    DevBuf<uint32_t> dec_work;     // work list: tile ids, then record ids (built by k_dec_work)
+    DevBuf<uint32_t> dec_work;     // work list: tile ids, record ids, range ids (built by k_dec_work)
     DevBuf<uint32_t> dec_ranges;   // touched chunk ranges of the call (DecRange[], decode.cu)
     std::vector<uint64_t> h_dec_prefix;  // running sum of h_dec_len (NR + 1 entries, extended lazily)
     DevBuf<uint64_t> d_dec_prefix;
     size_t dec_prefix_synced = 0;
-    DevBuf<uint32_t> dec_ctr;      // [0] error, [1] tile ticket, [2] pieces handed over, [3+r] unfinished CTAs of resolve round r
+    DevBuf<uint32_t> dec_ctr;      // counters of a decode call (enum DC_* in decode.cu)
 
     // ---- staging for batches ----
     DevBuf<uint8_t> in_keys, in_vals, out_stage;

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpixiu_b200.so")
+LIB_PATH = os.environ.get("PIXIU_B200_LIB") or os.path.join(HERE, "libpixiu_b200.so")   # (override: A/B builds)
 
 _u8p = C.POINTER(C.c_uint8)
 _i32p = C.POINTER(C.c_int32)
@@ -132,6 +132,8 @@ def load_library():
     L.pixiu_debug_window_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
     L.pixiu_debug_window_array.restype = C.c_int64
     L.pixiu_debug_pool_state.argtypes = [C.c_void_p, _i32p, _i32p]
+    L.pixiu_debug_set_knob.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    L.pixiu_debug_decode_counters.argtypes = [C.c_void_p, _i64p, _i64p]
     _lib = L
     return L
 
@@ -500,6 +502,16 @@ class PiXiuCtrl:
 
     def rotate(self):
         self._check(self._L.pixiu_rotate(self._h))
+
+    def debug_set_knob(self, name: str, value: int):
+        """tuning / test knob of a live store (Knobs::set in csrc/store.h)"""
+        self._check(self._L.pixiu_debug_set_knob(self._h, name.encode(), int(value)))
+
+    def debug_decode_counters(self):
+        """-> (pending pieces, drain passes) of the last decode call"""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._L.pixiu_debug_decode_counters(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def debug_pool_state(self):
         nth, used = C.c_int32(), C.c_int32()

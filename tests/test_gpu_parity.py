@@ -127,13 +127,10 @@ def test_setitem_nested_and_periodic_vs_oracle(ctrl_mod):
     c.free_prop()
 
 
-@pytest.mark.parametrize("knobs", [{"PIXIU_PIECE_CAP": "6"}, {"PIXIU_GIVEUP_SPINS": "0"},
-                                   {"PIXIU_PIECE_CAP": "40", "PIXIU_GIVEUP_SPINS": "2"}])
-def test_decode_handover_paths(ctrl_mod, knobs, monkeypatch):
-    """the decoder's data-flow pass hands pieces to the pointer-chasing pass when its piece table is full or when
-    sources stay unresolved (deep chains); both knobs force that on ordinary data: same bytes either way"""
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
+@pytest.mark.parametrize("piece_cap", [1, 6, 40])
+def test_decode_pending_table_drains(ctrl_mod, piece_cap):
+    """a decode tile keeps the references whose sources are not retired yet as pending pieces; when the table is full it
+    first copies them (drains), then goes on.  A tiny table forces that on ordinary data: same bytes either way"""
     # HTML-like pages (many short references), nested records (long references, self-periodic runs), escapes
     for gen in ("html", "nested", "esc"):
         if gen == "html":
@@ -152,10 +149,14 @@ def test_decode_handover_paths(ctrl_mod, knobs, monkeypatch):
         keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
         c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
         c.setitem_batch((kd, ko), (vd, vo))
+        c.debug_set_knob("piece_cap", piece_cap)
         buf, off, found = c.getitem_batch((kd, ko))
         assert found.all()
         for i, (k, v) in enumerate(zip(keys, vals)):
             assert buf[off[i]:off[i + 1]].tobytes() == po.make_doc(k, v), f"{gen} record {i}"
+        pieces, drains = c.debug_decode_counters()
+        if gen == "nested":
+            assert pieces > 0 and drains > 0
         c.free_prop()
 
 
@@ -191,7 +192,7 @@ def test_edge_records(ctrl_mod):
     c.free_prop()
 
 
-def test_decode_request_split_into_passes(ctrl_mod, monkeypatch):
+def test_decode_request_split_into_passes(ctrl_mod):
     """a request whose touched chunks decode to more than the 32-bit arena of one pass is split by chunk; the knob
     shrinks the limit so that a small store needs many passes (shuffled request, device and host outputs)"""
     kd, ko, vd, vo = synth.gen_html_pages(60, seed=4, max_len=20000, mean_len=9000)
@@ -199,7 +200,7 @@ def test_decode_request_split_into_passes(ctrl_mod, monkeypatch):
     c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=60_000)
     c.setitem_batch((kd, ko), (vd, vo))
     assert c.stats().chunks >= 8
-    monkeypatch.setenv("PIXIU_DEC_ARENA_LIMIT", "150000")
+    c.debug_set_knob("dec_arena_limit", 150000)
     order = [int(i) for i in np.random.default_rng(3).permutation(len(keys))]
     for req in (list(range(len(keys))), order, order[:17]):
         buf, off, found = c.getitem_batch([keys[i] for i in req])
