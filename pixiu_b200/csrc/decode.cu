@@ -2,29 +2,30 @@
 //
 // Replaces the recursive generator PXSGen::operator() (proj/PiXiuStr.h:110-198), which re-scans the referenced
 // record from its first byte for every back reference and bubbles each byte through one coroutine per nesting
-// level, by ONE data-flow kernel over a flat *decoded arena* (the records of every touched chunk, back to back,
-// u32-addressed):
-//   K10 k_decode_tiles  one warp per 2 KiB decode tile (tile descriptors make every tile independently parsable),
-//                       tiles handed out by ticket in arena order.  The 251-dispatch of PiXiuStr.h:142-160 runs in
-//                       parallel over the staged encoded bytes; then ONE LANE PER TOKEN writes the literal run in
-//                       front of its reference and the reference itself, every byte exactly once:
-//                         - a reference whose source lies below the chunk's *retired watermark* (everything below it
-//                           is final: the common case, sources of the leftmost-occurrence rule lie far back) is
-//                           copied straight away, no polling;
-//                         - any other reference stays zero and becomes *pending pieces* that copy as soon as
-//                           their source bytes are final.  Finality travels IN BAND: a nonzero byte is final the
-//                           moment it is visible, a final byte whose value is zero is announced in a 1-bit-per-byte
-//                           bitmap that stays all-zero between calls (the words a call dirties are listed and
-//                           cleared again), so the dependency depth is the nesting depth of BYTES.
-//                       No memset of the arena: a tile zeroes ITSELF as it starts (the L2 merges those stores with
-//                       the final bytes that follow) and announces it; a polling tile first makes sure that every
-//                       earlier tile of its chunk has done so (a per-chunk in-order watermark; a second one marks
-//                       the retired prefix).
-//   K12 k_copy_records  only when the caller's layout differs from the arena order.
-// Traffic per decoded byte: the encoded byte or the source byte read once, the byte written once (pending bytes
-// twice, which the L2 absorbs).
-// Waiting is deadlock-free: a source always precedes its destination in the arena and tickets follow arena order,
-// so every tile a warp waits for is finished or held by a resident warp.
+// level, by TWO kernels over a flat *decoded arena* (the records of every touched chunk, back to back,
+// u32-addressed), one warp per 2 KiB decode tile (tile descriptors make every tile independently parsable):
+//   K10 k_decode_literals  no dependencies, pure throughput.  The 251-dispatch of PiXiuStr.h:142-160 runs in parallel
+//                          over the staged encoded bytes (bitmap of the 251s, one lane per token cluster), a scan of
+//                          (decoded - encoded) token bytes places every reference token, and the tile is then written
+//                          ONCE, each lane assembling a 64-byte strip of output words straight from the staged bytes:
+//                          literal bytes with their value, reference bytes as zero = "not final yet".  Every reference
+//                          token leaves copy *pieces* of at most 32 bytes (destination, source, length; self-overlapping
+//                          references keep their period) in a packed table in HBM.
+//   K11 k_decode_copies    the data flow: tiles by ticket in arena order, one lane per piece, a piece copies as soon as
+//                          its source bytes are final.  Finality travels IN BAND: a nonzero byte is final the moment it is
+//                          visible; a final byte whose value is zero is announced in a 1-bit-per-byte bitmap that stays
+//                          all-zero between calls (the words a call dirties are listed and cleared again).  The dependency
+//                          depth is the nesting depth of BYTES, not of tiles or records; there is no flag, no fence and no
+//                          memset of the arena.
+//   K12 k_copy_records     only when the caller's layout differs from the arena order.
+// Why two kernels: a single data-flow kernel that parses, places and copies (the first version of this round, ~6,000
+// SASS instructions of mostly straight-line code with warps in every phase at once) saturated the GPC instruction cache
+// (ncu: gcc__cache_requests_type_instruction 93 % of peak, stall_no_inst the top stall) long before any data path.  Split
+// this way each kernel is a compact loop nest, and the polling kernel is a few hundred instructions.
+// Traffic per decoded byte: the encoded byte read once, the byte written once (reference bytes twice), 8 bytes of
+// piece table written and read per reference token, the source bytes of every reference read once.
+// Waiting (K11) is deadlock-free: a source always precedes its destination in the arena and tickets follow arena
+// order, so every byte a warp waits for belongs to a tile that is finished or held by a resident warp.
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -37,7 +38,7 @@ namespace pixiu {
 
 constexpr int DEC_WARPS = 4;
 #ifndef PIXIU_DEC_MINB
-#define PIXIU_DEC_MINB 8     // resident CTAs per SM the decode kernel is compiled for (register budget 65536 / (128 x this))
+#define PIXIU_DEC_MINB 7     // resident CTAs per SM the decode kernels are compiled for (register budget 65536 / (128 x this))
 #endif
 constexpr uint32_t ENC_MAX = TILE + 16;           // encoded bytes a tile can span
 constexpr uint32_t STG_PAD = 16;                  // free bytes in front of the staged range (reads just before it stay in bounds)
@@ -46,13 +47,18 @@ constexpr uint32_t STG_WORDS = (STG_BYTES + 31) / 32 * 8;  // whole 32-byte bitm
 constexpr uint32_t BM_WORDS = 96;                 // bitmaps: three words per lane
 // every reference token but the first and the last of a tile puts >= 7 decoded bytes into the tile
 constexpr uint32_t SEG_MAX = TILE / 7 + 4;
-// pending pieces: a reference whose source is not retired yet is cut into pieces of at most 32 bytes at the 32-byte
-// boundaries of the SOURCE (periodic ones also where they wrap).  A tile keeps at most PEND_MAX of them; when the
-// table is full the warp first drains it (copies them), then goes on.
+constexpr uint32_t TOK_MAX = SEG_MAX + 8;         // token table entries of a tile (+ sentinel)
+// copy pieces of a tile: one per reference token of up to 32 bytes, one per 32 bytes of a longer one
+constexpr uint32_t PIECE_BUF = SEG_MAX + TILE / 32 + 8;
+// K11 copies the pieces of a tile in batches of at most PEND_MAX (four rows of 32 lanes)
 constexpr uint32_t PEND_MAX = 128;
 constexpr uint32_t PEND_ROWS = PEND_MAX / 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
-constexpr uint32_t LANE_RUN_MAX = 64;             // literal runs up to this length are copied by their lane, longer ones by the warp
+constexpr uint32_t STRIP = 64;                    // output bytes a lane assembles
+// plain references of UNIT_MIN bytes or more are copied by the whole warp, UNIT_BYTES at a time, one destination word
+// per lane (a "unit"); everything else by one lane per piece of at most 32 bytes
+constexpr uint32_t UNIT_MIN = 64, UNIT_BYTES = 120;
+constexpr uint32_t META_UNIT = 0x80000000u;       // piece meta: the piece is a unit, (n - 1) takes bits 12..18
 static_assert(STG_BYTES <= BM_WORDS * 32 && TILE + 4 <= (BM_WORDS - 1) * 32, "bitmaps too small");
 
 // the touched part of one chunk: records [first, last] form a contiguous part of the arena
@@ -63,17 +69,8 @@ struct DecRange {
     uint32_t arena_base, pad;
 };
 
-// per range: two HINTS about its tiles, (index << 32) | arena offset relative to arena_base, only ever raised
-// (atomicMax): tiles [0, index) have reached the level and the offset is where the last of them ends.  Producers
-// only publish their own state (DecodeView::ts); whoever needs a watermark scans the states from the hint on, 32 at a
-// time, and raises the hint for the next one (no in-order hand-over between producers, no Dekker fences).
-struct DecSync {
-    unsigned long long zeroed;    // level 1: those tiles have zeroed themselves, their bytes may be polled in band
-    unsigned long long retired;   // level 2: those tiles are complete, every byte below the offset is final
-};
-
-// one work item = one tile, everything the decode kernel needs to start in ONE 48-byte read (k_dec_work derives it
-// from the record tables, so that the tile's warp does not walk a chain of dependent table loads)
+// one work item = one tile, everything its warp needs to start in ONE 48-byte read (k_dec_work derives it from the
+// record tables, so that the warp does not walk a chain of dependent table loads)
 struct alignas(16) TileJob {
     uint64_t enc_pos;       // offset in the compressed arena of the first staged byte
     uint32_t rec_base;      // arena offset of the tile's record
@@ -82,9 +79,7 @@ struct alignas(16) TileJob {
     uint32_t ne_skip;       // staged encoded bytes (lo16); bytes of the first token to skip (hi16; 0xFFFF: raw first byte)
     uint32_t chunk_first;   // global id of record 0 of the chunk (back references carry chunk-local indices)
     uint32_t range;         // index of the DecRange
-    uint32_t sidx;          // index of the tile's state / end entry
-    uint32_t kidx;          // index of the tile inside its range
-    uint32_t pad0, pad1;
+    uint32_t pad0, pad1, pad2, pad3;
 };
 static_assert(sizeof(TileJob) == 48, "TileJob layout");
 
@@ -92,14 +87,13 @@ struct DecodeView {
     const uint8_t *enc;
     const TileJob *jobs;        // in ticket order
     const uint32_t *arena_off;  // per record: offset of its decoded bytes in the arena
-    const DecRange *ranges;
     uint8_t *arena;
     uint32_t *fin;              // per arena byte: 1 bit, set = the byte is final AND its value is zero
     uint32_t *dirty;            // words of `fin` this call has set bits in (cleared again by k_fin_clean)
     uint32_t dirty_cap;
-    unsigned long long *ts;     // per tile (range.tile_cum + index in range): (end offset relative to the range) << 2 |
-                                // state, 0 = not started, 1 = zeroed, 2 = complete
-    DecSync *sync;              // per range
+    uint2 *pieces;              // packed piece table: {source arena position, meta}
+    uint32_t pieces_cap;
+    uint2 *phead;               // per tile (ticket order): {first piece, number of pieces}
 };
 
 // what the out-of-line helpers need (passed by value: a reference to the kernel's parameter block would force a copy
@@ -111,12 +105,19 @@ struct PubCtx {
 };
 
 // counters of a decode call (dec_ctr)
-enum { DC_ERR = 0, DC_TICKET = 1, DC_DIRTY = 2, DC_PENDING = 3, DC_DRAINS = 4, DC_WAITS = 5 };
+enum { DC_ERR = 0, DC_TICKET = 1, DC_DIRTY = 2, DC_PIECES = 3, DC_TICKET2 = 4, DC_SWEEPS = 5 };
 
-struct ParseBits {                  // dead once the heads are listed: shares its storage with the pending pieces
+struct ParseBits {                  // dead once the heads are listed: shares its storage with the token table
     uint32_t b251[BM_WORDS];        // bit p: staged byte p is a 251 that can start a token
     uint32_t cst[BM_WORDS];         // bit p: that 251 surely starts a token (no 251 among the 7 bytes before it)
     uint16_t cl[SEG_MAX + 8];       // staged positions of those cluster starts, ascending
+};
+// reference tokens of a tile in output order, in "u" coordinates (u = output byte of the tile + misalignment of the
+// tile's first byte, so that u = 0 is a word boundary of the arena); entry nt is a sentinel
+struct TokTab {
+    int16_t ts[TOK_MAX];            // first output byte of token i (clipped to the tile)
+    int16_t te[TOK_MAX];            // one past its last output byte (clipped)
+    int16_t dl[TOK_MAX];            // the literals in front of token i: staged position = u + dl[i]
 };
 struct Pending {
     // meta: u (12 bits) | (n - 1) << 12 (5 bits) | period << 17 (5 bits, 0 = plain copy) | phase << 22
@@ -125,15 +126,20 @@ struct Pending {
     uint32_t done[PEND_MAX];        // bytes of the piece already copied
 };
 
-struct alignas(16) WarpSmem {
+struct alignas(16) WarpSmem {       // K10
     uint32_t stg[STG_WORDS];        // staged encoded bytes: byte e0 + k of the record sits at staged position soff + k
     union {
         ParseBits ps;
-        Pending pc;
+        TokTab tt;
     };
-    uint32_t zbm[BM_WORDS];         // bit p: staged byte p is zero (only valid when the tile's staged bytes hold a zero)
     uint16_t heads[SEG_MAX + 8];    // staged positions of the reference heads, ascending
+    uint2 piece[PIECE_BUF];         // the tile's copy pieces, flushed to the packed table at the end
+    uint16_t first_tok[TILE / STRIP + 4];  // per strip: the token that governs its first byte
+};
+struct alignas(16) CopySmem {       // K11
+    Pending pc;
     uint32_t pend[PEND_ROWS];       // per row of 32 pieces: lanes whose piece is not copied yet
+    uint32_t upend[PEND_ROWS];      // per row: slots that hold a unit (copied by the whole warp) not finished yet
 };
 
 __device__ __forceinline__ uint32_t nib251(uint32_t w) {
@@ -145,7 +151,6 @@ __device__ __forceinline__ uint32_t nibz(uint32_t w) {   // 4-bit mask of the ze
 __device__ __forceinline__ uint32_t nibnz(uint32_t w) {  // 4-bit mask of the nonzero bytes of w
     return ((__vcmpne4(w, 0u) & 0x08040201u) * 0x01010101u) >> 24;
 }
-__device__ __forceinline__ uint32_t haszero(uint32_t w) { return (w - 0x01010101u) & ~w & 0x80808080u; }
 
 __device__ __forceinline__ uint32_t atom_relaxed_or_u32(uint32_t *p, uint32_t v) {
     uint32_t old;
@@ -153,15 +158,12 @@ __device__ __forceinline__ uint32_t atom_relaxed_or_u32(uint32_t *p, uint32_t v)
     return old;
 }
 // stores that other warps poll: strong (relaxed, device scope) so that the poll and the store are both morally
-// strong operations; a byte is only ever stored with its final value or with zero ("not final yet")
+// strong operations; a byte is only ever stored with its final value (K10 has left zero = "not final yet")
 __device__ __forceinline__ void st_pub_u8(uint8_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v));
 }
 __device__ __forceinline__ void st_pub_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v));
-}
-__device__ __forceinline__ void st_pub_v4(uint4 *p, uint4 v) {
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
 // announce final bytes whose value is zero: bit j of `zmask` = arena byte B + j (j < 32)
@@ -212,105 +214,59 @@ __device__ __noinline__ void put_bytes(uint8_t *dst, uint32_t w0, uint32_t w1, u
         if ((uint32_t) i < tb) st_pub_u8(reinterpret_cast<uint8_t *>(dw + m) + i, (xt >> (8 * i)) & 0xFFu);
 }
 
-// exact mask of the zero bytes among source bytes [sa, sa + n) of the aligned words sw (n <= 32)
-__device__ __forceinline__ uint32_t zero_mask(const uint32_t (&sw)[9], uint32_t sa, uint32_t n) {
-    unsigned long long zm = 0;
-#pragma unroll
-    for (int q = 0; q < 9; q++) zm |= (unsigned long long) nibz(sw[q]) << (4 * q);
-    return (uint32_t) (zm >> sa) & (0xFFFFFFFFu >> (32 - n));
-}
-
-// The whole warp writes n bytes at arena + B from staged bytes (from_arena = false: src is a staged position) or from
-// final arena bytes (src is an arena position).  Lane l looks after the destination words l, l + 32, ... of the span.
-__device__ __noinline__ void warp_put(PubCtx P, const uint32_t *stg, bool from_arena, uint32_t B, uint32_t src, uint32_t n) {
-    const uint32_t lane = lane_id();
-    const uint32_t da = B & 3u, span = da + n;   // destination words cover [B - da, B - da + span)
-    uint8_t *base = P.arena + (B - da);
-#pragma unroll 1
-    for (uint32_t o = 4 * lane; o < span; o += 128) {
-        const int j0 = (int) o - (int) da;         // piece byte held by the word's byte 0 (< 0 in the first word when da > 0)
-        const uint32_t lo = j0 < 0 ? (uint32_t) (-j0) : 0u;
-        // source bytes from piece byte max(j0, 0) on: two aligned words and a funnel shift, moved up to byte `lo`
-        const uint32_t s = src + (uint32_t) (j0 + (int) lo);
-        uint32_t x;
-        if (from_arena) {
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(P.arena + (s & ~3u));
-            x = __funnelshift_r(__ldcg(wp), __ldcg(wp + 1), 8 * (s & 3));
-        } else {
-            x = __funnelshift_r(stg[s >> 2], stg[(s >> 2) + 1], 8 * (s & 3));
-        }
-        x <<= 8 * lo;
-        const uint32_t hi = min(4u, (uint32_t) ((int) n - j0));
-        if (lo == 0 && hi == 4) {
-            st_pub_u32(reinterpret_cast<uint32_t *>(base + o), x);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if ((uint32_t) i >= lo && (uint32_t) i < hi) st_pub_u8(base + o + i, (x >> (8 * i)) & 0xFFu);
-        }
-        const uint32_t zb = nibz(x) & ((1u << hi) - 1) & ~((1u << lo) - 1);
-        if (zb) publish_zeros(P, (B - da) + o, zb);
-    }
-}
-
-// The whole warp zeroes arena bytes [B, B + n): byte stores up to a 16-byte boundary, 16-byte stores, byte stores.
-__device__ __forceinline__ void warp_zero(uint8_t *arena, uint32_t B, uint32_t n, uint32_t lane) {
-    const uint32_t hb = min((16u - (B & 15u)) & 15u, n);
-    if (lane < hb) st_pub_u8(arena + B + lane, 0u);
-    const uint32_t body = (n - hb) >> 4, tb = (n - hb) & 15u;
-    uint4 *b4 = reinterpret_cast<uint4 *>(arena + B + hb);
-#pragma unroll 1
-    for (uint32_t j = lane; j < body; j += 32) st_pub_v4(b4 + j, make_uint4(0u, 0u, 0u, 0u));
-    if (lane < tb) st_pub_u8(arena + B + hb + 16 * body + lane, 0u);
-}
-
-// How far have the tiles of a range reached `level`?  Scans the states from the range's hint on, 32 per step, up to
-// tile `limit` and for at most `max_steps` steps; raises the hint; returns (index << 32) | end offset of tile index - 1.
-// The caller fences afterwards (acquire side of the producers' fence + state store).
-__device__ __noinline__ unsigned long long scan_mark(const unsigned long long *ts, unsigned long long *hint, uint32_t limit,
-                                                     uint32_t level, uint32_t max_steps) {
-    const uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = lane_id();
-    unsigned long long h = 0;
-    if (lane == 0) h = ld_relaxed_u64(hint);
-    h = __shfl_sync(FULL, h, 0);
-    uint32_t idx = (uint32_t) (h >> 32), bytes = (uint32_t) h;
-    const uint32_t idx0 = idx;
-    for (uint32_t step = 0; step < max_steps && idx < limit; step++) {
-        const unsigned long long v = idx + lane < limit ? ld_relaxed_u64(ts + idx + lane) : 0ull;
-        const uint32_t ready = __ballot_sync(FULL, ((uint32_t) v & 3u) >= level);
-        const uint32_t n = ready == FULL ? 32u : (uint32_t) __ffs(~ready) - 1u;  // leading tiles that reached the level
-        if (n == 0) break;
-        bytes = __shfl_sync(FULL, (uint32_t) (v >> 2), n - 1);
-        idx += n;
-        if (n < 32) break;
-    }
-    h = ((unsigned long long) idx << 32) | bytes;
-    if (idx > idx0 && lane == 0) atomicMax(hint, h);
-    return h;
-}
-
 // Copy the pending pieces of a tile: one piece per lane and row, sweeping until all are done.  A piece loads its
 // source words (L2-coherent relaxed loads), copies the bytes that are final (nonzero, or zero and announced in the
 // bitmap), remembers them in its done mask and retries the rest: no flag round trip, no fence, and the critical path
 // is the nesting depth of BYTES.  Returns the number of sweeps, or 0xFFFFFFFF on a time-out / foreign error.
-__device__ __noinline__ uint32_t drain_pending(WarpSmem &S, PubCtx P, uint32_t B0, uint32_t npiece, uint32_t sleep_after,
-                                               uint32_t sleep_ns) {
+__device__ __noinline__ uint32_t drain_pending(CopySmem &S, PubCtx P, uint32_t B0, uint32_t npiece, uint32_t sleep_after,
+                                               uint32_t sleep_ns, uint32_t sweep_gap) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = lane_id();
     uint8_t *const dstu = P.arena + B0;
     const uint32_t nrows = (npiece + 31) / 32;
-    if (lane < PEND_ROWS)
-        S.pend[lane] = lane < nrows ? (32 * (lane + 1) <= npiece ? 0xFFFFFFFFu : (1u << (npiece - 32 * lane)) - 1) : 0u;
-    for (uint32_t k = lane; k < npiece; k += 32) S.pc.done[k] = 0;
+    uint32_t remaining = 0, uremaining = 0;
+    for (uint32_t row = 0; row < PEND_ROWS; row++) {   // which slots are lane pieces, which are units
+        const uint32_t k = row * 32 + lane;
+        const bool valid = k < npiece, unit = valid && (S.pc.meta[k] & META_UNIT);
+        if (valid) S.pc.done[k] = 0;
+        const uint32_t vm = __ballot_sync(FULL, valid && !unit), um = __ballot_sync(FULL, unit);
+        if (lane == 0) {
+            S.pend[row] = vm;
+            S.upend[row] = um;
+        }
+        remaining += __popc(vm);
+        uremaining += __popc(um);
+    }
     __syncwarp();
-    uint32_t remaining = npiece, spins = 0, sweep = 3;  // (the first sweep examines every piece)
-    for (; remaining; sweep++) {
+    uint32_t spins = 0, sweep = 3;  // (the first sweep examines every piece)
+    for (; remaining | uremaining; sweep++) {
         uint32_t any = 0;
+        // A waiting piece costs one load per sweep: the source byte behind its first open byte (its last one on odd
+        // sweeps: looking at the first byte only makes a byte wait for everything left of it in its piece, and with a
+        // source window that slides from record to record that running maximum chains every record to its predecessor);
+        // the whole window is examined when that byte has arrived and every fourth sweep (bytes out of order,
+        // zero-valued ones).  The polls of all rows are issued before any of them is consumed: one L2 round trip per
+        // sweep, not one per row (the sweep period is what a dependency hop costs).
+        uint32_t pollw[PEND_ROWS];
+        const bool full_look = (sweep & 3u) == 3u;
+#pragma unroll
+        for (uint32_t row = 0; row < PEND_ROWS; row++) {
+            pollw[row] = 1u;
+            if (!full_look && row < nrows && ((S.pend[row] >> lane) & 1u)) {
+                const uint32_t slot = row * 32 + lane;
+                const uint32_t meta = S.pc.meta[slot], a = S.pc.src[slot];
+                const uint32_t per = (meta >> 17) & 31u, n = per ? per : ((meta >> 12) & 31u) + 1;
+                const uint32_t open = (0xFFFFFFFFu >> (32 - n)) & ~(per ? 0u : S.pc.done[slot]);
+                const uint32_t pj = a + ((sweep & 1u) ? 31u - (uint32_t) __clz(open) : (uint32_t) __ffs(open) - 1u);
+                pollw[row] = (ld_poll_u32(reinterpret_cast<const uint32_t *>(P.arena + (pj & ~3u))) >> (8 * (pj & 3))) & 0xFFu;
+            }
+        }
+        static_assert(PEND_ROWS == 4, "row select below");
 #pragma unroll 1
         for (uint32_t row = 0; row < nrows; row++) {
             const uint32_t pm = S.pend[row];
             if (!pm) continue;
+            const uint32_t pw = row == 0 ? pollw[0] : row == 1 ? pollw[1] : row == 2 ? pollw[2] : pollw[3];
             bool complete = false;
             uint32_t avail = 0;
             if ((pm >> lane) & 1u) {
@@ -320,28 +276,35 @@ __device__ __noinline__ uint32_t drain_pending(WarpSmem &S, PubCtx P, uint32_t B
                 const uint32_t n = per ? per : np;  // source bytes
                 const uint32_t need = 0xFFFFFFFFu >> (32 - n);
                 uint32_t dn = per ? 0u : S.pc.done[slot];
-                // a waiting piece costs one load per sweep: the source byte behind its first open byte (its last one on
-                // odd sweeps: looking at the first byte only makes a byte wait for everything left of it in its piece,
-                // and with a source window that slides from record to record that running maximum chains every record
-                // to its predecessor); the whole window is examined when that byte has arrived and every fourth sweep
-                // (bytes out of order, zero-valued ones)
-                bool look = (sweep & 3u) == 3u;
-                if (!look) {
-                    const uint32_t open = need & ~dn;
-                    const uint32_t pj = a + ((sweep & 1u) ? 31u - (uint32_t) __clz(open) : (uint32_t) __ffs(open) - 1u);
-                    const uint32_t w0 = ld_poll_u32(reinterpret_cast<const uint32_t *>(P.arena + (pj & ~3u)));
-                    look = ((w0 >> (8 * (pj & 3))) & 0xFFu) != 0;
-                }
+                const bool look = full_look || pw != 0;
                 if (look) {
                     const uint32_t sa = a & 3, nsw = (sa + n + 3) >> 2;  // aligned source words (<= 9)
                     const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(P.arena + (a - sa));
                     uint32_t sw[9];
 #pragma unroll
                     for (int q = 0; q < 9; q++) sw[q] = (uint32_t) q < nsw ? ld_poll_u32(wp0 + q) : 0u;
-                    unsigned long long nzm = 0;
+                    // source bytes seen nonzero are final.  The common case - every byte of the range nonzero - is settled by
+                    // a cheap zero-byte test over the words (bytes outside the range forced nonzero); the exact mask only
+                    // when some byte is still zero
+                    uint32_t nz = need;
+                    {
+                        const uint32_t end = sa + n, L = (end - 1) >> 2, e8 = 8 * (end & 3);
+                        uint32_t z = 0;
 #pragma unroll
-                    for (int q = 0; q < 9; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
-                    const uint32_t nz = (uint32_t) (nzm >> sa) & need;  // source bytes seen nonzero: final
+                        for (int q = 0; q < 9; q++) {
+                            uint32_t w = sw[q];
+                            if (q == 0) w |= (1u << (8 * sa)) - 1;
+                            if ((uint32_t) q == L && e8) w |= 0xFFFFFFFFu << e8;
+                            if ((uint32_t) q > L) w = 0xFFFFFFFFu;
+                            z |= (w - 0x01010101u) & ~w & 0x80808080u;
+                        }
+                        if (z) {
+                            unsigned long long nzm = 0;
+#pragma unroll
+                            for (int q = 0; q < 9; q++) nzm |= (unsigned long long) nibnz(sw[q]) << (4 * q);
+                            nz = (uint32_t) (nzm >> sa) & need;
+                        }
+                    }
                     uint32_t zf = 0;  // source bytes that are final zeros
                     const uint32_t zc = need & ~nz & ~dn;
                     if (zc) {
@@ -419,6 +382,65 @@ __device__ __noinline__ uint32_t drain_pending(WarpSmem &S, PubCtx P, uint32_t B
                 __syncwarp();
             }
         }
+        // ---- units: the whole warp, one destination word per lane; a word is stored as soon as its source bytes are
+        //      final (progress per word, not per unit: a long reference into a region that is itself being copied
+        //      follows it word by word).  The units are examined one after the other, each a little later than the one
+        //      before: sampling them all at once (loads of several units in flight together) was measured and needs
+        //      more sweeps - on deep chains the sweeps, not the load latency, are what costs ----
+        if (uremaining) {
+#pragma unroll 1
+            for (uint32_t row = 0; row < nrows; row++) {
+                uint32_t um = S.upend[row];
+#pragma unroll 1
+                while (um) {
+                    const uint32_t slot = row * 32 + (uint32_t) __ffs(um) - 1u;
+                    um &= um - 1;
+                    const uint32_t meta = S.pc.meta[slot], A = S.pc.src[slot], dn = S.pc.done[slot];
+                    const uint32_t B = B0 + (meta & 0xFFFu), n = ((meta >> 12) & 0x7Fu) + 1;
+                    const uint32_t da = B & 3u, nw = (da + n + 3) >> 2;   // destination words (<= 31)
+                    bool ready = false;
+                    if (lane < nw && !((dn >> lane) & 1u)) {
+                        const int j0 = 4 * (int) lane - (int) da;      // unit byte held by the word's byte 0 (< 0 in word 0 when da > 0)
+                        const uint32_t lo = j0 < 0 ? (uint32_t) (-j0) : 0u, hi = min(4u, (uint32_t) ((int) n - j0));
+                        const uint32_t sp = A + (uint32_t) (j0 + (int) lo);   // source position of the first valid byte
+                        const uint32_t *wp = reinterpret_cast<const uint32_t *>(P.arena + (sp & ~3u));
+                        const uint32_t w0 = ld_poll_u32(wp), w1 = ((sp & 3u) + (hi - lo) > 4u) ? ld_poll_u32(wp + 1) : 0u;
+                        const uint32_t x = __funnelshift_r(w0, w1, 8 * (sp & 3u)) << (8 * lo);
+                        const uint32_t vb = ((1u << hi) - 1) & ~((1u << lo) - 1);      // valid bytes of the word (4 bits)
+                        const uint32_t zb = nibz(x) & vb;                                 // valid bytes that read zero
+                        ready = zb == 0;
+                        if (!ready) {   // zero: final only if announced in the bitmap (bits of source bytes sp ...)
+                            const uint32_t wi = sp >> 5, bs = sp & 31;
+                            uint32_t bits = ld_relaxed_u32(P.fin + wi) >> bs;
+                            if (bs > 28) bits |= ld_relaxed_u32(P.fin + wi + 1) << (32 - bs);
+                            ready = (((zb >> lo) & ~bits) & 0xFu) == 0;
+                        }
+                        if (ready) {
+                            uint8_t *d = P.arena + (B - da) + 4 * lane;
+                            if (vb == 0xFu) {
+                                st_pub_u32(reinterpret_cast<uint32_t *>(d), x);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; i++)
+                                    if ((vb >> i) & 1u) st_pub_u8(d + i, (x >> (8 * i)) & 0xFFu);
+                            }
+                            if (zb) publish_zeros(P, (B - da) + 4 * lane, zb);
+                        }
+                    }
+                    const uint32_t rb = __ballot_sync(FULL, ready);
+                    if (rb) {
+                        any = 1;
+                        const uint32_t nd = dn | rb;
+                        if (nd == (nw >= 32 ? 0xFFFFFFFFu : (1u << nw) - 1)) {
+                            if (lane == 0) S.upend[row] &= ~(1u << (slot & 31));
+                            uremaining--;
+                        } else if (lane == 0) {
+                            S.pc.done[slot] = nd;
+                        }
+                    }
+                }
+            }
+        }
         __syncwarp();
         if (!any) {
             if (++spins > SPIN_LIMIT || ld_relaxed_u32(P.ctr + DC_ERR) != 0) {
@@ -428,44 +450,48 @@ __device__ __noinline__ uint32_t drain_pending(WarpSmem &S, PubCtx P, uint32_t B
             if (spins > sleep_after) __nanosleep(spins > 256 ? 400 : sleep_ns);
         } else {
             spins = 0;
+            if (sweep_gap && (remaining | uremaining)) __nanosleep(sweep_gap);
         }
     }
     return sweep - 3;
 }
 
-// K10: one warp per 2 KiB tile of decoded output, tiles taken by ticket in arena order.
-//   0. the tile zeroes itself; after the parse it announces "zeroed" (in-order watermark wl)
+
+// K10: one warp per 2 KiB tile of decoded output; no waiting anywhere.
 //   1. stage the tile's encoded bytes in shared memory (16-byte loads)
 //   2. bitmap of the 251s; a 251 with no 251 among the 7 bytes before it surely starts a token: these cluster starts
 //      are listed, and one lane per cluster walks its tokens (PiXiuStr.h:142-160 dispatch) and counts / lists the
 //      reference heads (a cluster is almost always a single token)
 //   3. heads in order, 32 per round, one lane per reference token: a scan of (decoded - encoded) token bytes gives its
-//      output position (literals map 1:1); the lane writes the literal run in front of its token from the staged
-//      bytes, then the token: copied from the arena when its source is retired, else it becomes pending pieces
-//   4. the literal run behind the last token
-//   5. pending pieces (drain_pending), once every earlier tile of the chunk has announced "zeroed"
-//   6. the tile announces "complete" (in-order watermark wm = retired prefix of the chunk)
+//      output position (literals map 1:1); the lane enters the token in the tile's token table and its copy pieces
+//      (<= 32 bytes each) in the piece buffer
+//   4. the tile is written once: every lane assembles a 64-byte strip word by word, walking the token table from the
+//      token that governs the strip's first byte - literal bytes come straight from the staged bytes (one unaligned
+//      32-bit read per word and run), reference bytes are zero; zero-valued literals are announced in the bitmap
+//   5. the pieces go to the packed table (one atomic add per tile)
 __global__ void __launch_bounds__(DEC_WARPS * 32, PIXIU_DEC_MINB)
-k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t piece_cap, uint32_t sleep_after,
-               uint32_t sleep_ns, unsigned long long *__restrict__ trace) {
+k_decode_literals(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
     const uint32_t FULL = 0xffffffffu;
     uint32_t *err = ctr + DC_ERR;
     const PubCtx P{V.arena, V.fin, V.dirty, ctr, V.dirty_cap};
-    // persistent warps: every warp takes tiles by ticket until none is left
+    // persistent warps: every warp takes tiles by ticket, TICKETS at a time (nothing here waits on another tile, so the
+    // order does not matter and one atomic serves several tiles), until none is left
+    constexpr uint32_t TICKETS = 4;
+    uint32_t w = 0, w_end = 0;
 #pragma unroll 1
-    for (;;) {
+    for (;; w++) {
     __syncwarp();
-    uint32_t w = 0;
-    if (lane == 0) w = atomicAdd(ctr + DC_TICKET, 1u);
-    w = __shfl_sync(FULL, w, 0);
+    if (w == w_end) {
+        if (lane == 0) w = atomicAdd(ctr + DC_TICKET, TICKETS);
+        w = __shfl_sync(FULL, w, 0);
+        w_end = w + TICKETS;
+    }
     if (w >= n_work) return;
-    if (trace && lane == 0) trace[4 * (size_t) w] = globaltimer_ns();
-    // ---- the job: three 16-byte reads ----
+    // ---- the job: two 16-byte reads ----
     const uint4 j0 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w)), j1 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w) + 1);
-    const uint4 j2 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w) + 2);
     const uint8_t *gsrc = V.enc + (((uint64_t) j0.y << 32) | j0.x);
     const uint32_t rec_base = j0.z, g = j0.w;
     const uint32_t t0 = j1.x & 0xFFFFu, nbytes = j1.x >> 16;
@@ -473,28 +499,15 @@ k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32
     uint32_t skip = j1.y >> 16;
     const bool raw_first = skip == 0xFFFF;  // first enc byte is the 2nd half of an escape pair
     if (raw_first) skip = 0;
-    const uint32_t chunk_first = j1.z, sidx = j2.x, kidx = j2.y;
-    const DecRange rg = V.ranges[j1.w];
-    DecSync *const sy = V.sync + j1.w;
-    const uint32_t mis = (uint32_t) ((uintptr_t) (V.arena + rec_base + t0) & 3);
-    const uint32_t B0 = rec_base + t0 - mis;  // arena position of u = 0 (word aligned); u = output byte + mis
-    uint8_t *const dstu = V.arena + B0;
-    const uint32_t tile_rel = rec_base + t0 - rg.arena_base;  // start of the tile relative to its range
-    // the retired prefix of the chunk as this tile starts (everything below is final: references into it are copied
-    // without polling); the fence is the acquire side of the producers' "fence, then state" (nothing of this tile is in
-    // flight yet, so it is cheap here)
-    const unsigned long long *const rts = V.ts + rg.tile_cum;
-    const uint32_t wm = (uint32_t) scan_mark(rts, &sy->retired, kidx, 2u, 2u) + rg.arena_base;   // absolute arena offset
-    fence_gpu();
+    const uint32_t chunk_first = j1.z;
+    const uint32_t mis = (rec_base + t0) & 3u;   // (the arena itself is at least 16-byte aligned)
+    const uint32_t B0 = rec_base + t0 - mis;     // arena position of u = 0 (word aligned); u = output byte + mis
+    const uint32_t nu = nbytes + mis;
     bool failed = false;
     if (ne > ENC_MAX) {   // (k_dec_work flags an inconsistent descriptor this way)
         if (lane == 0) atomicExch(err, 4u);
         failed = true;
     }
-    // ---- 0. the tile zeroes itself ("not final yet" for every byte), so that other tiles may poll its bytes in band
-    //         long before its literals are written; the stores drain while the tile is staged and parsed, and the
-    //         L2 merges them with the final bytes that follow (no second trip to DRAM) ----
-    warp_zero(V.arena, rec_base + t0, nbytes, lane);
     // ---- 1. stage the encoded bytes (the compressed arena has slack past its end) ----
     const uint32_t a16 = (uint32_t) ((uintptr_t) gsrc & 15);
     const uint32_t soff = STG_PAD + a16, nstg = soff + ne;
@@ -510,30 +523,22 @@ k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32
     }
     const uint8_t *SB = reinterpret_cast<const uint8_t *>(S.stg);
     if (!failed) {
-        // ---- 2a. bitmap of the 251s and of the zero bytes (32 staged bytes per lane and step) ----
+        // ---- 2a. bitmap of the 251s (32 staged bytes per lane and step) ----
         {
             const uint4 *s4 = reinterpret_cast<const uint4 *>(S.stg);
             const uint32_t lo = soff + (raw_first ? 1u : 0u);  // the raw first byte is a plain literal
 #pragma unroll 1
             for (int k = 0; k < 3; k++) {
                 const uint32_t wi = lane + 32 * k, base = wi * 32;
-                uint32_t bits = 0, zb = 0;
+                uint32_t bits = 0;
                 if (base < nstg) {
                     const uint4 A = s4[2 * wi], B = s4[2 * wi + 1];
                     bits = nib251(A.x) | (nib251(A.y) << 4) | (nib251(A.z) << 8) | (nib251(A.w) << 12) | (nib251(B.x) << 16) |
                            (nib251(B.y) << 20) | (nib251(B.z) << 24) | (nib251(B.w) << 28);
                     if (base < lo) bits &= (lo - base >= 32) ? 0u : (0xFFFFFFFFu << (lo - base));
                     if (base + 32 > nstg) bits &= 0xFFFFFFFFu >> (base + 32 - nstg);
-                    if (haszero(A.x) | haszero(A.y) | haszero(A.z) | haszero(A.w) | haszero(B.x) | haszero(B.y) | haszero(B.z) |
-                        haszero(B.w)) {
-                        zb = nibz(A.x) | (nibz(A.y) << 4) | (nibz(A.z) << 8) | (nibz(A.w) << 12) | (nibz(B.x) << 16) |
-                             (nibz(B.y) << 20) | (nibz(B.z) << 24) | (nibz(B.w) << 28);
-                        if (base < soff) zb &= (soff - base >= 32) ? 0u : (0xFFFFFFFFu << (soff - base));
-                        if (base + 32 > nstg) zb &= 0xFFFFFFFFu >> (base + 32 - nstg);
-                    }
                 }
                 S.ps.b251[wi] = bits;
-                S.zbm[wi] = zb;
             }
         }
         __syncwarp();
@@ -641,53 +646,13 @@ k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32
         }
         __syncwarp();   // (from here on ParseBits is dead: its storage holds the pending pieces)
     }
-    // the tile announces "zeroed" (state 1)
-    const unsigned long long my_end = (unsigned long long) (tile_rel + nbytes) << 2;
-    if (lane == 0) {
-        fence_gpu();                                        // the zeroes are visible before the state is
-        st_relaxed_u64(V.ts + sidx, my_end | 1ull);
-    }
-    __syncwarp();
     // ---- 3. rounds of 32 reference tokens, one lane each ----
-    uint32_t npiece = 0;        // pending pieces in the table
-    bool lit_ok = false;        // every earlier tile of the chunk has zeroed itself: in-band polling is valid
-    uint32_t sweeps = 0;
+    uint32_t npiece = 0;        // pieces in the buffer
     int D = 0;                  // sum of (decoded - encoded) bytes of the reference tokens so far
     int carry_out = 0;          // output position where the previous token ended (literals before the first one start at 0)
     uint32_t carry_stg = soff;  // staged position behind the previous token
-
-    // wait until in-band polling is valid, then copy the pending pieces
-    auto drain = [&]() -> bool {
-        if (!npiece) return true;
-        if (!lit_ok) {
-            // (every earlier tile zeroed itself within microseconds of its start: this wait is over before it begins,
-            //  except right behind a tile that was held up)
-            uint32_t spins = 0;
-            bool ok = true;
-            while ((uint32_t) (scan_mark(rts, &sy->zeroed, kidx, 1u, 8u) >> 32) < kidx) {
-                if (++spins > SPIN_LIMIT || ld_relaxed_u32(err) != 0) {
-                    if (lane == 0) atomicCAS(err, 0u, 8u);
-                    ok = false;
-                    break;
-                }
-                __nanosleep(spins > 16 ? 1000 : 100);
-            }
-            if (spins && lane == 0) atomicAdd(ctr + DC_WAITS, 1u);
-            fence_gpu();  // (acquire side: the zeroes of the earlier tiles are visible to the polls below)
-            __syncwarp();
-            if (!ok) return false;
-            lit_ok = true;
-        }
-        if (lane == 0) {
-            atomicAdd(ctr + DC_PENDING, npiece);
-            atomicAdd(ctr + DC_DRAINS, 1u);
-        }
-        const uint32_t sw = drain_pending(S, P, B0, npiece, sleep_after, sleep_ns);
-        npiece = 0;
-        sweeps += sw;
-        return sw != 0xFFFFFFFFu;
-    };
-
+    const uint32_t nstrips = (nu + STRIP - 1) / STRIP;
+    for (uint32_t s = lane; s < nstrips; s += 32) S.first_tok[s] = (uint16_t) nheads;   // (the sentinel governs what no token claims)
     // arena offset of the source record of this lane's token, fetched one round ahead (a dependent L2 round trip
     // that would otherwise sit in the middle of every round)
     auto source_base = [&](uint32_t c) -> uint32_t {
@@ -697,6 +662,7 @@ k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32
         return src_g < g ? V.arena_off[src_g] : 0u;
     };
     uint32_t aoff_cur = failed ? 0u : source_base(lane);
+    __syncwarp();
 #pragma unroll 1
     for (uint32_t c0 = 0; c0 < nheads && !failed; c0 += 32) {
         const uint32_t c = c0 + lane;
@@ -738,18 +704,22 @@ k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32
             pe_out = carry_out;
             pe_stg = carry_stg;
         }
-        // the literal run in front of the token: output [lo, hi), staged bytes from pe_stg + (lo - pe_out)
-        const int lo = max(pe_out, 0), hi = min(rel, (int) nbytes);
-        const uint32_t rn = (head && hi > lo) ? (uint32_t) (hi - lo) : 0u;
-        const uint32_t rsrc = pe_stg + (uint32_t) (lo - pe_out);
-        const uint32_t ru = (uint32_t) lo + mis;
-        const bool rlong = rn > LANE_RUN_MAX;
-        // the token itself
+        // the token in the tile: output bytes [k0, k1) of it
         const uint32_t k0 = rel < 0 ? (uint32_t) (-rel) : 0u;
         const uint32_t k1 = end_out > (int) nbytes ? (uint32_t) max((int) nbytes - rel, 0) : tl;
         const bool emit = head && k0 < k1;
+        // ---- token table (every head, also one that puts nothing into the tile) and the strips it governs ----
+        if (head) {
+            const int us0 = min(max(rel, 0), (int) nbytes) + (int) mis, ue0 = min(max(end_out, 0), (int) nbytes) + (int) mis;
+            S.tt.ts[c] = (int16_t) us0;
+            S.tt.te[c] = (int16_t) ue0;
+            S.tt.dl[c] = (int16_t) ((int) pe_stg - pe_out - (int) mis);
+            // token c governs the positions [end of token c - 1, end of token c): the strips that start in there
+            const int gov0 = c == 0 ? 0 : min(max(pe_out, 0), (int) nbytes) + (int) mis;
+            for (uint32_t s = ((uint32_t) gov0 + STRIP - 1) / STRIP; s * STRIP < (uint32_t) ue0; s++) S.first_tok[s] = (uint16_t) c;
+        }
+        // ---- copy pieces ----
         uint32_t sbase = 0, per = 0, ks = k0, us = 0, len = 0;
-        bool fast = false;
         if (emit) {
             const uint32_t src_g = chunk_first + idx;
             if (src_g == g) {  // self reference (PiXiuStr.h:168-181): overlapping copies repeat with this period
@@ -767,80 +737,18 @@ k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32
                 if (ks + len <= per) per = 0;  // this part does not wrap: a plain copy out of the first period
             }
             us = (uint32_t) (rel + (int) k0) + mis;
-            fast = per == 0 && sbase + ks + len <= wm;   // the source is retired: final, no polling
         }
-        // ---- 3a. up to three items per lane, each at most 32 bytes: the run's first and second half from the staged bytes,
-        //          the token from the arena when its source is retired.  (Tokens whose source is not retired stay zero =
-        //          "not final yet" and become pending pieces below.) ----
-#pragma unroll 1
-        for (int it = 0; it < 3; it++) {
-            uint32_t n, q, u;
-            if (it < 2) {
-                n = (rlong || rn <= 32u * it) ? 0u : min(rn - 32u * it, 32u);
-                q = rsrc + 32u * it;
-                u = ru + 32u * it;
-            } else {
-                n = (emit && fast && len <= 32) ? len : 0u;
-                q = sbase + ks;
-                u = us;
-            }
-            if (!__any_sync(FULL, n != 0)) continue;
-            if (n) {
-                const uint32_t sa = q & 3, nsw = (sa + n + 3) >> 2;
-                uint32_t sw[9];
-                uint32_t zb;
-                if (it < 2) {
-#pragma unroll
-                    for (int i = 0; i < 9; i++) sw[i] = S.stg[(q >> 2) + i];   // (reads past the run stay inside the warp's shared memory)
-                    // zero-valued literals are announced in the bitmap: the staged zero bits, restricted to the run
-                    zb = __funnelshift_r(S.zbm[q >> 5], S.zbm[(q >> 5) + 1], q & 31) & (0xFFFFFFFFu >> (32 - n));
-                } else {
-                    const uint32_t *wp0 = reinterpret_cast<const uint32_t *>(V.arena + (q - sa));
-#pragma unroll
-                    for (int i = 0; i < 9; i++) sw[i] = (uint32_t) i < nsw ? __ldcg(wp0 + i) : 0xFFFFFFFFu;
-                    // (exact test: the bytes around the range are forced nonzero first)
-                    const uint32_t end = sa + n, L = (end - 1) >> 2, e8 = 8 * (end & 3);
-                    uint32_t z = haszero(sw[0] | ((1u << (8 * sa)) - 1));
-#pragma unroll
-                    for (int i = 1; i < 9; i++) z |= haszero(sw[i]);
-                    // (the last word's bytes behind the range: re-test it with them forced nonzero)
-                    zb = 0;
-                    if (z) {
-                        uint32_t tmp[9];
-#pragma unroll
-                        for (int i = 0; i < 9; i++) tmp[i] = sw[i];
-                        (void) L;
-                        (void) e8;
-                        zb = zero_mask(tmp, sa, n);
-                    }
+        {
+            // pieces of a token: 32 destination bytes each (a period >= 32 that wraps: also cut where it wraps)
+            const bool wrapper = emit && per >= 32, units = emit && per == 0 && len >= UNIT_MIN;
+            uint32_t np = !emit || wrapper ? 0u : units ? (len + UNIT_BYTES - 1) / UNIT_BYTES : (len + 31) >> 5;
+            if (wrapper) {
+                for (uint32_t pos = ks, o = 0; o < len; np++) {
+                    const uint32_t n = min(min(32u, per - pos), len - o);
+                    pos = pos + n == per ? 0u : pos + n;
+                    o += n;
                 }
-                put_bytes(dstu + u, sw[0], sw[1], sw[2], sw[3], sw[4], sw[5], sw[6], sw[7], sw[8], sa, n);
-                if (zb) publish_zeros(P, B0 + u, zb);
             }
-        }
-        // ---- 3b. long runs and long retired tokens: the whole warp copies ----
-        {
-            const bool tlong = emit && fast && len > 32;
-            uint32_t lm = __ballot_sync(FULL, rlong), tm = __ballot_sync(FULL, tlong);
-            while (lm | tm) {
-                const bool tok = lm == 0;
-                const uint32_t mm = tok ? tm : lm;
-                const int r = __ffs(mm) - 1;
-                if (tok) tm &= tm - 1;
-                else lm &= lm - 1;
-                warp_put(P, S.stg, tok, B0 + __shfl_sync(FULL, tok ? us : ru, r), __shfl_sync(FULL, tok ? sbase + ks : rsrc, r),
-                         __shfl_sync(FULL, tok ? len : rn, r));
-            }
-        }
-        __syncwarp();
-        // ---- 3c. pending pieces of the tokens whose source is not retired: cut at the 32-byte boundaries of the SOURCE
-        //          (periods >= 32 also where they wrap).  Plain tokens of up to 32 bytes give one or two pieces and are
-        //          entered by their own lanes; the rest token by token ----
-        {
-            const bool pend = emit && !fast;
-            const bool simple = pend && per == 0 && len <= 32;
-            const uint32_t A = sbase + ks;
-            const uint32_t np = simple ? ((A + len - 1) >> 5) - (A >> 5) + 1 : 0u;   // 1 or 2
             uint32_t pinc = np;
 #pragma unroll
             for (int dd = 1; dd < 32; dd <<= 1) {
@@ -848,63 +756,31 @@ k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32
                 if ((int) lane >= dd) pinc += o;
             }
             const uint32_t tot = __shfl_sync(FULL, pinc, 31);
-            if (tot) {
-                if (npiece + tot > piece_cap) {
-                    if (!drain()) failed = true;
-                }
-                if (!failed && tot <= piece_cap) {
-                    if (np) {
-                        const uint32_t slot = npiece + pinc - np, cut = ((A >> 5) + 1) << 5;  // first 32-byte boundary behind A
-                        const uint32_t n0 = np == 2 ? cut - A : len;
-                        S.pc.src[slot] = A;
-                        S.pc.meta[slot] = us | ((n0 - 1) << 12);
-                        if (np == 2) {
-                            S.pc.src[slot + 1] = cut;
-                            S.pc.meta[slot + 1] = (us + n0) | ((len - n0 - 1) << 12);
-                        }
+            if (npiece + tot > PIECE_BUF) {
+                if (lane == 0) atomicExch(err, 6u);
+                failed = true;
+            } else {
+                uint32_t slot = npiece + pinc - np;
+                if (wrapper) {
+                    for (uint32_t pos = ks, o = 0; o < len; slot++) {
+                        const uint32_t n = min(min(32u, per - pos), len - o);
+                        S.piece[slot] = make_uint2(sbase + pos, (us + o) | ((n - 1) << 12));
+                        pos = pos + n == per ? 0u : pos + n;
+                        o += n;
                     }
-                    npiece += tot;
-                }
-            }
-            // (with a tiny piece_cap - a test knob - even the simple tokens of one round may not fit: one by one then)
-            uint32_t pm = __ballot_sync(FULL, pend && (!simple || tot > piece_cap));
-            __syncwarp();
-            while (pm && !failed) {
-                const int r = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const uint32_t tsb = __shfl_sync(FULL, sbase, r), tper = __shfl_sync(FULL, per, r), tks = __shfl_sync(FULL, ks, r);
-                const uint32_t tus = __shfl_sync(FULL, us, r), tlen = __shfl_sync(FULL, len, r);
-                // the token's pieces one after the other (all lanes walk, lane 0 writes)
-                const bool shortp = tper != 0 && tper < 32;
-                const uint32_t wrap = tper ? tper : 0xFFFFFFFFu;
-#pragma unroll 1
-                for (uint32_t pos = tks, o = 0; o < tlen;) {
-                    if (npiece == piece_cap) {
-                        if (!drain()) {
-                            failed = true;
-                            break;
-                        }
+                } else if (units) {
+                    for (uint32_t o = 0; o < len; o += UNIT_BYTES, slot++) {
+                        const uint32_t n = min(UNIT_BYTES, len - o);
+                        S.piece[slot] = make_uint2(sbase + ks + o, (us + o) | ((n - 1) << 12) | META_UNIT);
                     }
-                    uint32_t n;
-                    if (shortp) {
-                        // short period: a piece covers 32 destination bytes and reads the whole first period
-                        n = min(32u, tlen - o);
-                        if (lane == 0) {
-                            S.pc.src[npiece] = tsb;
-                            S.pc.meta[npiece] = (tus + o) | ((n - 1) << 12) | (tper << 17) | (((tks + o) % tper) << 22);
-                        }
-                    } else {
-                        n = min(min(32u - ((tsb + pos) & 31u), wrap - pos), tlen - o);
-                        if (lane == 0) {
-                            S.pc.src[npiece] = tsb + pos;
-                            S.pc.meta[npiece] = (tus + o) | ((n - 1) << 12);
-                        }
-                        pos = pos + n == wrap ? 0u : pos + n;
+                } else {
+                    for (uint32_t o = 0; o < len; o += 32, slot++) {
+                        const uint32_t n = min(32u, len - o);
+                        S.piece[slot] = per ? make_uint2(sbase, (us + o) | ((n - 1) << 12) | (per << 17) | (((ks + o) % per) << 22))
+                                            : make_uint2(sbase + ks + o, (us + o) | ((n - 1) << 12));
                     }
-                    npiece++;
-                    o += n;
-                    __syncwarp();
                 }
+                npiece += tot;
             }
         }
         // carries for the next round
@@ -920,27 +796,111 @@ k_decode_tiles(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32
             failed = true;
         }
     }
-    // ---- 4. the literal run behind the last token ----
+    if (lane == 0) {   // sentinel: behind the last token everything is literal
+        S.tt.ts[nheads] = (int16_t) nu;
+        S.tt.te[nheads] = (int16_t) nu;
+        S.tt.dl[nheads] = (int16_t) ((int) carry_stg - carry_out - (int) mis);
+    }
+    __syncwarp();
+    // ---- 4. the tile is written once, a 64-byte strip per lane ----
     if (!failed) {
-        const int lo = max(carry_out, 0);
-        if (lo < (int) nbytes) warp_put(P, S.stg, false, B0 + (uint32_t) lo + mis, carry_stg + (uint32_t) (lo - carry_out), nbytes - (uint32_t) lo);
+        uint8_t *const dstu = V.arena + B0;
+#pragma unroll 1
+        for (uint32_t s = lane; s < nstrips; s += 32) {
+            uint32_t i = S.first_tok[s];
+            int ts_i = S.tt.ts[i], te_i = S.tt.te[i], dl_i = S.tt.dl[i];
+            const int s_end = (int) min((s + 1) * STRIP, nu);
+#pragma unroll 1
+            for (int pos = (int) (s * STRIP); pos < s_end; pos += 4) {
+                const int lo = max(pos, (int) mis), end = min(pos + 4, s_end);   // bytes [lo, end) of this word belong to the tile
+                uint32_t x = 0, lit = 0;   // the word; its literal bytes (0xFF each)
+                int cur = lo;
+                while (true) {
+                    if (cur < ts_i) {   // literals in front of token i: bytes [cur, min(ts_i, end))
+                        const int se = min(ts_i, end);
+                        const uint32_t m = (0xFFFFFFFFu >> (32 - 8 * (se - pos))) & (0xFFFFFFFFu << (8 * (cur - pos)));
+                        const uint32_t q = (uint32_t) (pos + dl_i);
+                        x |= __funnelshift_r(S.stg[q >> 2], S.stg[(q >> 2) + 1], 8 * (q & 3)) & m;
+                        lit |= m;
+                        cur = se;
+                    }
+                    if (cur < te_i) cur = min(te_i, end);   // bytes of token i: zero = "not final yet"
+                    if (cur >= end) break;
+                    i++;
+                    ts_i = S.tt.ts[i];
+                    te_i = S.tt.te[i];
+                    dl_i = S.tt.dl[i];
+                }
+                if (lo == pos && end == pos + 4) {
+                    *reinterpret_cast<uint32_t *>(dstu + pos) = x;
+                } else {
+                    for (int k = lo; k < end; k++) dstu[k] = (uint8_t) (x >> (8 * (k - pos)));
+                }
+                const uint32_t zb = nibz(x | ~lit);   // zero-valued literal bytes are final: announce them
+                if (zb) publish_zeros(P, B0 + (uint32_t) pos, zb);
+            }
+        }
     }
-    if (trace && lane == 0) trace[4 * (size_t) w + 1] = globaltimer_ns();
-    // ---- 5. pending pieces ----
-    __syncwarp();
-    if (npiece != 0 && !failed) drain();
-    // ---- 6. "complete" (a failed tile announces itself too: the error flag is what the host reads, and waiting tiles
-    //         must not hang) ----
-    __syncwarp();
+    // ---- 5. the pieces go to the packed table ----
+    uint32_t pbase = 0;
     if (lane == 0) {
-        fence_gpu();                                        // the tile's bytes are visible before its state is
-        st_relaxed_u64(V.ts + sidx, my_end | 2ull);
+        pbase = failed ? 0u : atomicAdd(ctr + DC_PIECES, npiece);
+        if (!failed && pbase + npiece > V.pieces_cap) {
+            atomicExch(err, 10u);
+            failed = true;
+        }
+        V.phead[w] = make_uint2(pbase, failed ? 0u : npiece);
     }
-    if (trace && lane == 0) {  // measurement aid (PIXIU_DEC_TRACE_FILE): entry, end of the literal phase, done, sweeps
-        trace[4 * (size_t) w + 2] = globaltimer_ns();
-        trace[4 * (size_t) w + 3] = sweeps;
-    }
+    pbase = __shfl_sync(FULL, pbase, 0);
+    failed = __shfl_sync(FULL, (int) failed, 0) != 0;
+    if (!failed)
+        for (uint32_t k = lane; k < npiece; k += 32) V.pieces[pbase + k] = S.piece[k];
     }  // next ticket
+}
+
+// K11: the data flow.  Tiles by ticket in arena order; the pieces of a tile are copied in batches of up to 128 (one lane
+// per piece and row, see drain_pending); K10 has written every literal and zeroed every reference byte of the whole
+// arena before this kernel starts, so polling needs no flag.
+__global__ void __launch_bounds__(DEC_WARPS * 32, 8)
+k_decode_copies(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint32_t piece_cap, uint32_t sleep_after,
+                uint32_t sleep_ns, uint32_t sweep_gap, unsigned long long *__restrict__ trace) {
+    __shared__ CopySmem smem[DEC_WARPS];
+    CopySmem &S = smem[threadIdx.x >> 5];
+    const uint32_t lane = lane_id();
+    const uint32_t FULL = 0xffffffffu;
+    const PubCtx P{V.arena, V.fin, V.dirty, ctr, V.dirty_cap};
+#pragma unroll 1
+    for (;;) {
+        __syncwarp();
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(ctr + DC_TICKET2, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= n_work) return;
+        if (trace && lane == 0) trace[4 * (size_t) w] = globaltimer_ns();
+        const uint2 ph = V.phead[w];
+        const uint4 j0 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w)), j1 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w) + 1);
+        const uint32_t at = j0.z + (j1.x & 0xFFFFu);   // arena position of the tile's first byte
+        const uint32_t B0 = at - (at & 3u);
+        uint32_t sweeps = 0;
+#pragma unroll 1
+        for (uint32_t b0 = 0; b0 < ph.y; b0 += piece_cap) {
+            const uint32_t n = min(piece_cap, ph.y - b0);
+            for (uint32_t k = lane; k < n; k += 32) {
+                const uint2 r = V.pieces[ph.x + b0 + k];
+                S.pc.src[k] = r.x;
+                S.pc.meta[k] = r.y;
+            }
+            __syncwarp();
+            const uint32_t sw = drain_pending(S, P, B0, n, sleep_after, sleep_ns, sweep_gap);
+            if (sw == 0xFFFFFFFFu) return;   // (time-out or foreign error: the flag is set)
+            sweeps += sw;
+        }
+        if (trace && lane == 0) {  // measurement aid (PIXIU_DEC_TRACE_FILE): entry, -, done, sweeps
+            trace[4 * (size_t) w + 1] = trace[4 * (size_t) w];
+            trace[4 * (size_t) w + 2] = globaltimer_ns();
+            trace[4 * (size_t) w + 3] = sweeps;
+        }
+    }
 }
 
 // clears the words of the zero-byte bitmap a decode call has set bits in (the bitmap stays all-zero between calls)
@@ -1035,9 +995,7 @@ k_dec_work(uint32_t n_work, uint32_t n_ranges, const DecRange *__restrict__ R, c
     J.ne_skip = ne | (desc & 0xFFFF0000u);
     J.chunk_first = first[g];
     J.range = lo;
-    J.sidx = j;            // (= tile_cum + k: states are kept in range-major order)
-    J.kidx = k;
-    J.pad0 = J.pad1 = 0;
+    J.pad0 = J.pad1 = J.pad2 = J.pad3 = 0;
     jobs[pos] = J;
 }
 
@@ -1169,10 +1127,13 @@ void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const
     dec_dirty.reserve_discard(dirty_cap);
     dec_aoff.reserve_discard(NR + 1);
     dec_work.reserve_discard((n_work + 1) * (sizeof(TileJob) / sizeof(uint32_t)));
-    // per-tile states (+ end offsets) and the per-range hints: one buffer, zeroed per call (8 B per 2 KiB tile)
-    const size_t sync_words = 2 * n_work + 4 * ranges.size() + 8;
-    dec_sync.reserve_discard(sync_words);
-    PX_CUDA(cudaMemsetAsync(dec_sync.p, 0, sync_words * sizeof(uint32_t), st));
+    // piece table: one piece per reference token (a token is >= 6 encoded bytes) plus one per 32 decoded bytes of the long
+    // ones, plus slack per tile; 8 B per piece, and 8 B per tile for the table's directory
+    uint64_t enc_span = 0;
+    for (const DecRange &r : ranges) enc_span += h_enc_off[r.last] + h_enc_len[r.last] - h_enc_off[r.first];
+    const uint64_t pieces_cap = std::min<uint64_t>(enc_span / 6 + arena_bytes / 32 + 2 * n_work + 64, 0xFFFFFF00ull);
+    dec_pieces.reserve_discard(pieces_cap);
+    dec_phead.reserve_discard(n_work + 1);
     dec_ranges.reserve_discard(ranges.size() * sizeof(DecRange) / sizeof(uint32_t) + 8);
     DecRange *d_ranges = reinterpret_cast<DecRange *>(dec_ranges.p);
     PX_CUDA(cudaMemcpyAsync(d_ranges, ranges.data(), ranges.size() * sizeof(DecRange), cudaMemcpyHostToDevice, st));
@@ -1185,11 +1146,11 @@ void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const
     launches += 2;
     dec_ctr.reserve_discard(64);
     PX_CUDA(cudaMemsetAsync(dec_ctr.p, 0, 64 * sizeof(uint32_t), st));
-    DecodeView V{d_enc.ptr(), d_jobs, dec_aoff.p, d_ranges, arena, dec_flags.p, dec_dirty.p, (uint32_t) dirty_cap,
-                 reinterpret_cast<unsigned long long *>(dec_sync.p), reinterpret_cast<DecSync *>(dec_sync.p + 2 * n_work + (2 * n_work % 4))};
+    DecodeView V{d_enc.ptr(), d_jobs, dec_aoff.p, arena, dec_flags.p, dec_dirty.p, (uint32_t) dirty_cap,
+                 reinterpret_cast<uint2 *>(dec_pieces.p), (uint32_t) pieces_cap, reinterpret_cast<uint2 *>(dec_phead.p)};
     const size_t smem = sizeof(WarpSmem) * DEC_WARPS;
     // (per device and cheap: no process-wide "already done" flag, a process may drive several GPUs)
-    PX_CUDA(cudaFuncSetAttribute(k_decode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    PX_CUDA(cudaFuncSetAttribute(k_decode_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     const uint32_t piece_cap = std::min<uint32_t>(std::max<uint32_t>(knobs.piece_cap, 1u), PEND_MAX);
     if (knobs.trace)
         fprintf(stderr, "[decode] host work list %.3f ms\n",
@@ -1208,12 +1169,18 @@ void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const
         PX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         dec_sms = (uint32_t) sms;
     }
-    // persistent warps: one CTA slot per resident CTA of every SM (148 x 8 on a B200), fewer for small calls
-    const unsigned dec_grid = (unsigned) std::min<uint64_t>(div_up<uint64_t>(n_work, DEC_WARPS), (uint64_t) dec_sms * PIXIU_DEC_MINB);
-    k_decode_tiles<<<dec_grid, DEC_WARPS * 32, smem, st>>>(
-        V, (uint32_t) n_work, dec_ctr.p, piece_cap, knobs.sleep_after, knobs.sleep_ns, d_trace);
+    // persistent warps: one CTA per resident CTA slot of every SM, fewer for small calls
+    const uint64_t ctas = div_up<uint64_t>(n_work, DEC_WARPS);
+    prof.begin(PC_DECODE_LIT, st);
+    k_decode_literals<<<(unsigned) std::min<uint64_t>(ctas, (uint64_t) dec_sms * PIXIU_DEC_MINB), DEC_WARPS * 32, smem, st>>>(
+        V, (uint32_t) n_work, dec_ctr.p);
+    prof.end(st, alg_bytes, 1);
+    prof.begin(PC_DECODE_COPY, st);
+    k_decode_copies<<<(unsigned) std::min<uint64_t>(ctas, (uint64_t) dec_sms * std::min<uint32_t>(std::max<uint32_t>(knobs.copy_ctas, 1u), 8u)), DEC_WARPS * 32, 0, st>>>(
+        V, (uint32_t) n_work, dec_ctr.p, piece_cap, knobs.sleep_after, knobs.sleep_ns, knobs.sweep_gap, d_trace);
+    prof.end(st, 0.0, 1);
     k_fin_clean<<<64, 256, 0, st>>>(dec_flags.p, dec_dirty.p, dec_ctr.p, (uint32_t) dirty_cap);
-    int nl = 2;
+    int nl = 3;
     uint32_t h_ctr[8] = {0};
     PX_CUDA(cudaMemcpyAsync(h_ctr, dec_ctr.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (!direct) {
@@ -1236,8 +1203,8 @@ void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const
     PX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     last_get_ms = ms;
     prof.collect();
-    last_pending_pieces = h_ctr[DC_PENDING];
-    last_drains = h_ctr[DC_DRAINS];
+    last_pending_pieces = h_ctr[DC_PIECES];
+    last_drains = h_ctr[DC_SWEEPS];
     if (h_ctr[DC_DIRTY] > dirty_cap)  // more dirty words than the list holds (zero-heavy data): clear the whole bitmap
         PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, dec_flags.cap * sizeof(uint32_t), st));
     if (d_trace) {  // file: u64 n_work, u32 record[n_work] (ticket order), u64 {entry, parsed, done (ns), sweeps}[n_work]
@@ -1259,8 +1226,8 @@ void Store::decode_pass(const std::vector<uint32_t> &recs, uint8_t *d_out, const
         cudaFree(d_trace);
     }
     if (knobs.trace)
-        fprintf(stderr, "[decode] %llu tiles, %u pending pieces in %u drains, %u tiles waited for the literal watermark, %u dirty bitmap words\n",
-                (unsigned long long) n_work, h_ctr[DC_PENDING], h_ctr[DC_DRAINS], h_ctr[DC_WAITS], h_ctr[DC_DIRTY]);
+        fprintf(stderr, "[decode] %llu tiles, %u copy pieces, %u dirty bitmap words\n", (unsigned long long) n_work, h_ctr[DC_PIECES],
+                h_ctr[DC_DIRTY]);
     if (h_ctr[DC_ERR]) {
         // (the bitmap may hold bits of tiles that never finished)
         PX_CUDA(cudaMemsetAsync(dec_flags.p, 0, dec_flags.cap * sizeof(uint32_t), st));

@@ -23,14 +23,16 @@ enum ProfClass {
     PC_FLAGS,        // k_flag_scatter, k_pair_rule, run/offset scans
     PC_EMIT,         // k_emit
     PC_TABLES,       // k_record_tables, k_tile_desc
-    PC_DECODE,       // k_decode_tiles
+    PC_DECODE,       // the decode kernels together (k_decode_literals, k_decode_copies, k_fin_clean [, k_copy_records])
+    PC_DECODE_LIT,   // k_decode_literals alone
+    PC_DECODE_COPY,  // k_decode_copies alone
     PC_LOOKUP,       // k_query_*, k_lookup
     PC_COUNT
 };
 
 inline const char *prof_class_name(int c) {
     static const char *names[PC_COUNT] = {"docs", "init_keys", "sort_hist", "sort_pass", "rank_scan", "round_keys", "seg_sort", "lcp",
-                                          "tree", "lpf", "nodes", "flags", "emit", "tables", "decode", "lookup"};
+                                          "tree", "lpf", "nodes", "flags", "emit", "tables", "decode", "decode_lit", "decode_copy", "lookup"};
     return c >= 0 && c < PC_COUNT ? names[c] : "?";
 }
 
@@ -41,6 +43,7 @@ struct Profiler {
         int cls;
         double bytes;
         int launches;
+        bool open;
     };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> pool;
@@ -59,13 +62,18 @@ struct Profiler {
     }
     void begin(int cls, cudaStream_t st) {
         if (!on) return;
-        Span s{get(), get(), cls, 0, 0};
+        Span s{get(), get(), cls, 0, 0, true};
         cudaEventRecord(s.a, st);
         spans.push_back(s);
     }
     void end(cudaStream_t st, double nbytes, int nlaunch) {
-        if (!on || spans.empty()) return;
-        Span &s = spans.back();
+        if (!on) return;
+        // (spans nest: an end closes the innermost span that is still open)
+        int k = (int) spans.size() - 1;
+        while (k >= 0 && !spans[k].open) k--;
+        if (k < 0) return;
+        Span &s = spans[k];
+        s.open = false;
         s.bytes = nbytes;
         s.launches = nlaunch;
         cudaEventRecord(s.b, st);

@@ -75,6 +75,8 @@ struct Knobs {
     uint64_t dec_arena_limit = 7ull << 29;  // PIXIU_DEC_ARENA_LIMIT: decoded bytes of one decode pass (3.5 GiB)
     uint32_t piece_cap = 0xFFFFFFFFu;       // PIXIU_PIECE_CAP: pending pieces a decode tile keeps before it drains them
     uint32_t sleep_after = 16, sleep_ns = 64;  // PIXIU_SLEEP_AFTER / _NS: back-off of the decoder's polls
+    uint32_t copy_ctas = 8;        // PIXIU_COPY_CTAS: resident CTAs per SM of the copy kernel (persistent warps)
+    uint32_t sweep_gap = 0;        // PIXIU_SWEEP_GAP: ns a decode warp sleeps between two sweeps over its open pieces
     std::string dec_trace_file;    // PIXIU_DEC_TRACE_FILE: per-tile timestamps of a decode call
     void from_env() {
         auto num = [](const char *n, uint64_t dflt) -> uint64_t {
@@ -89,6 +91,8 @@ struct Knobs {
         piece_cap = (uint32_t) num("PIXIU_PIECE_CAP", piece_cap);
         sleep_after = (uint32_t) num("PIXIU_SLEEP_AFTER", sleep_after);
         sleep_ns = (uint32_t) num("PIXIU_SLEEP_NS", sleep_ns);
+        sweep_gap = (uint32_t) num("PIXIU_SWEEP_GAP", sweep_gap);
+        copy_ctas = (uint32_t) num("PIXIU_COPY_CTAS", copy_ctas);
         if (const char *f = getenv("PIXIU_DEC_TRACE_FILE")) dec_trace_file = f;
     }
     bool set(const std::string &name, int64_t v) {
@@ -96,6 +100,8 @@ struct Knobs {
         else if (name == "piece_cap") piece_cap = (uint32_t) v;
         else if (name == "sleep_after") sleep_after = (uint32_t) v;
         else if (name == "sleep_ns") sleep_ns = (uint32_t) v;
+        else if (name == "sweep_gap") sweep_gap = (uint32_t) v;
+        else if (name == "copy_ctas") copy_ctas = (uint32_t) v;
         else if (name == "trace") trace = v != 0;
         else if (name == "lcp_kasai") lcp_kasai = v != 0;
         else if (name == "no_spec_emit") no_spec_emit = v != 0;
@@ -178,9 +184,10 @@ struct Store {
     DevBuf<uint64_t> dec_loc;      // output offsets of the requested records
     DevBuf<uint32_t> dec_flags;    // zero-byte bitmap of the arena (1 bit per byte; all-zero between calls)
     DevBuf<uint32_t> dec_dirty;    // words of that bitmap the running call has set bits in
-    DevBuf<uint32_t> dec_sync;     // per tile: state, end offset; per range: the two in-order watermarks (zeroed per call)
+    DevBuf<uint64_t> dec_pieces;   // packed table of copy pieces {source, meta} written by K10, read by K11
+    DevBuf<uint64_t> dec_phead;    // per tile: {first piece, pieces}
     uint32_t dec_sms = 0;          // SM count of the store's device (grid of the persistent decode kernel)
-    uint64_t last_pending_pieces = 0, last_drains = 0;  // pending (polled) pieces of the last decode and its drain passes
+    uint64_t last_pending_pieces = 0, last_drains = 0;  // copy pieces of the last decode (and spare counter)
     DevBuf<uint32_t> dec_aoff;     // per record: offset in the arena
     DevBuf<uint32_t> dec_reqs;     // requested record ids
     DevBuf<uint32_t> dec_work;     // work list: tile ids, record ids, range ids (built by k_dec_work)

@@ -25,10 +25,12 @@ out = torch.empty(cap, dtype=torch.uint8, device="cuda")
 for rep in range(3):
     c.profile_enable(True)
     c.getitem_batch_dev((kd, ko), out.data_ptr(), cap)
-    pd = c.profile()["decode"]
+    pr = c.profile()
+    pd = pr["decode"]
     c.profile_enable(False)
     pieces, drains = c.debug_decode_counters()
-    print(f"call {rep}: decode {pd['ms']:.3f} ms, {pd['bytes'] / 1e6 / pd['ms']:.1f} GB/s, pending pieces {pieces}, drains {drains}")
+    print(f"call {rep}: decode {pd['ms']:.3f} ms (literals {pr['decode_lit']['ms']:.3f} + copies {pr['decode_copy']['ms']:.3f}), "
+          f"{pd['bytes'] / 1e6 / pd['ms']:.1f} GB/s, {pieces} copy pieces")
 if trace:
     raw = open("/tmp/dectrace.bin", "rb").read()
     nw = int(np.frombuffer(raw[:8], dtype=np.uint64)[0])

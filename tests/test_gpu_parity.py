@@ -128,9 +128,9 @@ def test_setitem_nested_and_periodic_vs_oracle(ctrl_mod):
 
 
 @pytest.mark.parametrize("piece_cap", [1, 6, 40])
-def test_decode_pending_table_drains(ctrl_mod, piece_cap):
-    """a decode tile keeps the references whose sources are not retired yet as pending pieces; when the table is full it
-    first copies them (drains), then goes on.  A tiny table forces that on ordinary data: same bytes either way"""
+def test_decode_piece_batches(ctrl_mod, piece_cap):
+    """the copy kernel takes the pieces of a tile in batches (128 by default); tiny batches force the multi-batch path
+    (a piece may then wait for a piece of an earlier batch of its own tile): same bytes either way"""
     # HTML-like pages (many short references), nested records (long references, self-periodic runs), escapes
     for gen in ("html", "nested", "esc"):
         if gen == "html":
@@ -154,9 +154,8 @@ def test_decode_pending_table_drains(ctrl_mod, piece_cap):
         assert found.all()
         for i, (k, v) in enumerate(zip(keys, vals)):
             assert buf[off[i]:off[i + 1]].tobytes() == po.make_doc(k, v), f"{gen} record {i}"
-        pieces, drains = c.debug_decode_counters()
-        if gen == "nested":
-            assert pieces > 0 and drains > 0
+        pieces, _ = c.debug_decode_counters()
+        assert pieces > 0
         c.free_prop()
 
 
