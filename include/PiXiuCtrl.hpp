@@ -150,6 +150,19 @@ struct PiXiuCtrl {
         return g;
     }
 
+    // encoded length of the record stored last - what the reference's REPL reads through
+    // `ctrl.st.cbt_chunk->getitem(ctrl.st.local_chunk.used_num - 1)->len` to print the bytes saved (main.cpp:67)
+    int last_encoded_len(void) {
+        pixiu_stats st;
+        int64_t chunk = 0, idx = 0;
+        if (pixiu_get_stats(store, &st) != PIXIU_OK || st.records == 0) return -1;
+        if (pixiu_record_location(store, st.records - 1, &chunk, &idx) != PIXIU_OK) return -1;
+        uint8_t *buf = (uint8_t *) malloc(65536);
+        const int n = pixiu_encoded_view(store, chunk, idx, buf, 65536);
+        free(buf);
+        return n;
+    }
+
     // PiXiuCtrl.cpp:88-114, by chunk id instead of `PiXiuChunk *&` (set config.auto_reinsert = 1 before init_prop for
     // the reference's trigger).  Returns the number of records moved or a negative PIXIU_E* code.
     int64_t reinsert(int64_t chunk) { return pixiu_reinsert_chunk(store, chunk); }

@@ -139,6 +139,14 @@ int64_t pixiu_import_chunk(pixiu_store *s, int64_t n, const uint8_t *enc, const 
 int pixiu_export_chunk(pixiu_store *s, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *count,
                        int64_t *need);
 
+/* The CritBit index in its wire format (flat SoA node arrays, leaf -> record ids, escaped keys; compacted, leaves in key
+ * order).  Together with pixiu_export_chunk of every chunk this is the whole store: load the chunks with
+ * pixiu_import_chunk_raw (no indexing, no decode) in the same order into a fresh store, then pixiu_import_index -
+ * lookups work at once, nothing is rebuilt.  Pass out_cap = 0 to query *need. */
+int pixiu_export_index(pixiu_store *s, uint8_t *out, int64_t out_cap, int64_t *need);
+int64_t pixiu_import_chunk_raw(pixiu_store *s, int64_t n, const uint8_t *enc, const int64_t *enc_off);
+int pixiu_import_index(pixiu_store *s, const uint8_t *blob, int64_t size);
+
 /* Decode every record of one chunk (tombstoned included) in idx order. */
 int pixiu_decode_chunk(pixiu_store *s, int64_t chunk, uint8_t *out, int64_t out_cap, int64_t *out_off, int64_t *need);
 

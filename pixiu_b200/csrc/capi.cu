@@ -463,7 +463,7 @@ int pixiu_iter(pixiu_store *h, const uint8_t *prefix, int64_t prefix_len, uint8_
         std::vector<uint8_t> q;
         pixiu::escape_key(prefix, (size_t) prefix_len, q, false);
         std::vector<uint32_t> recs;
-        S.index->iter(q.data(), (uint32_t) q.size(), recs);
+        pixiu::iter_prefix(S, q.data(), (uint32_t) q.size(), recs);   // the walk runs on the device (k_iter_prefix)
         *count = (int64_t) recs.size();
         std::vector<uint64_t> offs(1, 0);
         for (uint32_t g : recs) offs.push_back(offs.back() + S.h_dec_len[g]);
@@ -542,6 +542,49 @@ int64_t pixiu_import_chunk(pixiu_store *h, int64_t n, const uint8_t *enc, const 
         return PIXIU_OK;
     }, G_PLAIN);
     return rc == PIXIU_OK ? chunk_id : rc;
+}
+
+int64_t pixiu_import_chunk_raw(pixiu_store *h, int64_t n, const uint8_t *enc, const int64_t *enc_off) {
+    int64_t chunk_id = -1;
+    int rc = guarded(h, [&](Store &S) -> int {
+        if (!enc || !offsets_ok(n, enc_off)) return PIXIU_EINVAL;
+        const size_t g0 = S.n_records();
+        int64_t c = S.import_chunk(n, enc, enc_off);
+        if (c < 0) return (int) c;
+        chunk_id = c;
+        for (size_t g = g0; g < S.n_records(); g++) {   // nothing is live until an index says so
+            S.h_live[g] = 0;
+            S.doc_bytes += S.h_dec_len[g];
+        }
+        return PIXIU_OK;
+    }, G_PLAIN);
+    return rc == PIXIU_OK ? chunk_id : rc;
+}
+
+int pixiu_export_index(pixiu_store *h, uint8_t *out, int64_t out_cap, int64_t *need) {
+    return guarded(h, [&](Store &S) -> int {
+        std::vector<uint8_t> blob;
+        S.index->save(blob);
+        if (need) *need = (int64_t) blob.size();
+        if ((int64_t) blob.size() > out_cap || !out) return PIXIU_ENOSPC;
+        memcpy(out, blob.data(), blob.size());
+        return PIXIU_OK;
+    });
+}
+
+int pixiu_import_index(pixiu_store *h, const uint8_t *blob, int64_t size) {
+    return guarded(h, [&](Store &S) -> int {
+        if (!blob || size <= 0 || S.index->size() != 0) return PIXIU_EINVAL;
+        std::vector<uint32_t> live;
+        if (!S.index->load(blob, (size_t) size, (uint32_t) S.n_records(), live)) return PIXIU_ECORRUPT;
+        S.dirty = true;
+        for (uint32_t g : live) {
+            if (S.h_live[g]) return PIXIU_ECORRUPT;   // two leaves on one record
+            S.h_live[g] = 1;
+            S.note_live(g);
+        }
+        return PIXIU_OK;
+    }, G_PLAIN);
 }
 
 int pixiu_mg_config(pixiu_store *h, int rank, int world) {

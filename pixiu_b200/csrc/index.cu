@@ -207,6 +207,136 @@ void HostIndex::iter(const uint8_t *prefix, uint32_t plen, std::vector<uint32_t>
     }
 }
 
+// ---- wire format: "PXCB" u32 version | u64 n_inner, n_leaf, arena_bytes | i32 root, has_root | arrays ----
+namespace {
+template <typename T>
+void put_vec(std::vector<uint8_t> &out, const std::vector<T> &v) {
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(v.data());
+    out.insert(out.end(), p, p + v.size() * sizeof(T));
+}
+template <typename T>
+bool get_vec(const uint8_t *&p, const uint8_t *end, size_t n, std::vector<T> &v) {
+    if ((size_t) (end - p) < n * sizeof(T)) return false;
+    v.resize(n);
+    if (n) memcpy(v.data(), p, n * sizeof(T));
+    p += n * sizeof(T);
+    return true;
+}
+}  // namespace
+
+void HostIndex::save(std::vector<uint8_t> &out) const {
+    // free slots are compacted away: the saved tree only holds what is reachable
+    std::vector<int32_t> inner_map(diff_at.size(), -1), leaf_map(leaf_rec.size(), -1);
+    std::vector<int32_t> order_inner, order_leaf, stack;
+    if (has_root) stack.push_back(root);
+    while (!stack.empty()) {
+        const int32_t p = stack.back();
+        stack.pop_back();
+        if (p < 0) {
+            leaf_map[~p] = (int32_t) order_leaf.size();
+            order_leaf.push_back(~p);
+        } else {
+            inner_map[p] = (int32_t) order_inner.size();
+            order_inner.push_back(p);
+            stack.push_back(child[1][p]);
+            stack.push_back(child[0][p]);
+        }
+    }
+    auto remap = [&](int32_t c) { return c < 0 ? ~leaf_map[~c] : inner_map[c]; };
+    const uint64_t ni = order_inner.size(), nl = order_leaf.size();
+    std::vector<int32_t> c0(ni), c1(ni);
+    std::vector<uint16_t> da(ni);
+    std::vector<uint8_t> mk(ni), ar;
+    std::vector<uint32_t> lr(nl), lk(nl);
+    std::vector<uint64_t> lo(nl);
+    for (uint64_t i = 0; i < ni; i++) {
+        const int32_t p = order_inner[i];
+        c0[i] = remap(child[0][p]);
+        c1[i] = remap(child[1][p]);
+        da[i] = diff_at[p];
+        mk[i] = mask[p];
+    }
+    for (uint64_t i = 0; i < nl; i++) {   // (DFS order = key order: the saved arena is sorted by key)
+        const int32_t s = order_leaf[i];
+        lr[i] = leaf_rec[s];
+        lk[i] = leaf_klen[s];
+        lo[i] = ar.size();
+        ar.insert(ar.end(), arena.begin() + (ptrdiff_t) leaf_koff[s], arena.begin() + (ptrdiff_t) (leaf_koff[s] + leaf_klen[s]));
+    }
+    const uint64_t ab = ar.size();
+    const uint32_t magic = 0x42435850u, version = 1;
+    const int32_t r = has_root ? remap(root) : 0, hr = has_root ? 1 : 0;
+    out.clear();
+    auto put = [&](const void *p, size_t n) { out.insert(out.end(), (const uint8_t *) p, (const uint8_t *) p + n); };
+    put(&magic, 4);
+    put(&version, 4);
+    put(&ni, 8);
+    put(&nl, 8);
+    put(&ab, 8);
+    put(&r, 4);
+    put(&hr, 4);
+    put_vec(out, c0);
+    put_vec(out, c1);
+    put_vec(out, da);
+    put_vec(out, mk);
+    put_vec(out, lr);
+    put_vec(out, lk);
+    put_vec(out, lo);
+    put_vec(out, ar);
+}
+
+bool HostIndex::load(const uint8_t *blob, size_t size, uint32_t n_records, std::vector<uint32_t> &live_out) {
+    const uint8_t *p = blob, *end = blob + size;
+    if (size < 40) return false;
+    uint32_t magic, version;
+    uint64_t ni, nl, ab;
+    int32_t r, hr;
+    memcpy(&magic, p, 4);
+    memcpy(&version, p + 4, 4);
+    memcpy(&ni, p + 8, 8);
+    memcpy(&nl, p + 16, 8);
+    memcpy(&ab, p + 24, 8);
+    memcpy(&r, p + 32, 4);
+    memcpy(&hr, p + 36, 4);
+    p += 40;
+    if (magic != 0x42435850u || version != 1 || ni > 0x7fffffffull || nl > 0x7fffffffull || (nl && ni + 1 != nl) || (hr != 0) != (nl != 0))
+        return false;
+    std::vector<int32_t> c0, c1;
+    std::vector<uint16_t> da;
+    std::vector<uint8_t> mk, ar;
+    std::vector<uint32_t> lr, lk;
+    std::vector<uint64_t> lo;
+    if (!get_vec(p, end, ni, c0) || !get_vec(p, end, ni, c1) || !get_vec(p, end, ni, da) || !get_vec(p, end, ni, mk) ||
+        !get_vec(p, end, nl, lr) || !get_vec(p, end, nl, lk) || !get_vec(p, end, nl, lo) || !get_vec(p, end, ab, ar) || p != end)
+        return false;
+    auto child_ok = [&](int32_t c) { return c < 0 ? (uint64_t) ~c < nl : (uint64_t) c < ni; };
+    for (uint64_t i = 0; i < ni; i++)
+        if (!child_ok(c0[i]) || !child_ok(c1[i])) return false;
+    for (uint64_t i = 0; i < nl; i++)
+        if (lr[i] >= n_records || lo[i] + lk[i] > ab || lk[i] < 2) return false;
+    if (hr && !child_ok(r)) return false;
+    child[0].swap(c0);
+    child[1].swap(c1);
+    diff_at.swap(da);
+    mask.swap(mk);
+    leaf_rec.swap(lr);
+    leaf_klen.swap(lk);
+    leaf_koff.swap(lo);
+    arena.swap(ar);
+    free_inner.clear();
+    free_leaf.clear();
+    root = r;
+    has_root = hr != 0;
+    n_live = nl;
+    dirty = true;
+    synced_inner = synced_leaf = 0;
+    keys_uploaded = 0;
+    mod_child.clear();
+    mod_leaf.clear();
+    live_out = leaf_rec;
+    return true;
+}
+
 size_t HostIndex::host_bytes() const {
     return child[0].capacity() * 8 + diff_at.capacity() * 2 + mask.capacity() + leaf_rec.capacity() * 4 + leaf_klen.capacity() * 4 +
            leaf_koff.capacity() * 8 + arena.capacity();
@@ -605,6 +735,131 @@ void contains_batch_dev(Store &S, int64_t n, const uint8_t *d_keys, const int64_
     k_found<<<div_up<uint32_t>(nn, 256), 256, 0, S.st>>>(nn, S.doc_off.p, d_found);
     S.launches++;
     lookup_finish(S);
+}
+
+// iter(prefix) on the device (replaces the coroutine walk of CBTGen / CBTGHelper, CritBitTree.h:55-157): one CTA.
+//   1. thread 0 walks from the root along the prefix's bits until the critical position of a node lies behind the
+//      prefix (from there on the whole subtree qualifies) or a leaf is reached;
+//   2. the subtree is unfolded level by level in ORDER: the frontier (inner nodes and leaves, left to right) is
+//      rewritten with every inner node replaced by its two children (a block-wide scan gives the positions), until it
+//      holds leaves only - their order is the ascending byte order of esc(key) 251 0 (the tree order, Appendix A.20);
+//   3. the first leaf must start with the prefix (keys the walk never compared; CritBitTree.h:76-79), else the result
+//      is empty; the leaves' record ids are the output.
+// out[0] = number of records, out[1 ...] = record ids in key order; buf0 / buf1 hold at least (inner + leaves) entries.
+constexpr int ITER_THREADS = 512;
+__global__ void __launch_bounds__(ITER_THREADS)
+k_iter_prefix(HostIndex::DeviceView T, const uint8_t *__restrict__ prefix, uint32_t plen, int32_t *__restrict__ buf0,
+              int32_t *__restrict__ buf1, uint32_t *__restrict__ out) {
+    __shared__ uint32_t wsum[ITER_THREADS / 32];
+    __shared__ uint32_t s_n, s_inner, s_ok;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        uint32_t n = 0;
+        if (T.has_root) {
+            int32_t p = T.root;
+            while (p >= 0) {
+                const int4 nd = __ldg(T.nodes + p);
+                const uint32_t da = (uint32_t) nd.z & 0xFFFFu;
+                if (da >= plen) break;
+                p = ((1u + ((((uint32_t) nd.z >> 16) & 0xFFu) | prefix[da])) >> 8) ? nd.y : nd.x;
+            }
+            buf0[0] = p;
+            n = 1;
+        }
+        s_n = n;
+        s_inner = 1;
+    }
+    __syncthreads();
+    int32_t *cur = buf0, *nxt = buf1;
+    uint32_t n = s_n;
+    while (n && s_inner) {
+        __syncthreads();
+        if (tid == 0) s_inner = 0;
+        __syncthreads();
+        uint32_t base = 0;
+        bool any_inner = false;
+        for (uint32_t i0 = 0; i0 < n; i0 += ITER_THREADS) {
+            const uint32_t i = i0 + tid;
+            const int32_t e = i < n ? cur[i] : -1;
+            const bool inner = i < n && e >= 0;
+            const uint32_t cnt = i < n ? (inner ? 2u : 1u) : 0u;
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((int) lane >= d) inc += o;
+            }
+            if (lane == 31) wsum[wid] = inc;
+            __syncthreads();
+            uint32_t woff = 0, total = 0;
+#pragma unroll
+            for (int k = 0; k < ITER_THREADS / 32; k++) {
+                const uint32_t v = wsum[k];
+                if ((uint32_t) k < wid) woff += v;
+                total += v;
+            }
+            const uint32_t pos = base + woff + inc - cnt;
+            if (inner) {
+                const int4 nd = __ldg(T.nodes + e);
+                nxt[pos] = nd.x;
+                nxt[pos + 1] = nd.y;
+                if (nd.x >= 0 || nd.y >= 0) any_inner = true;
+            } else if (i < n) {
+                nxt[pos] = e;
+            }
+            base += total;
+            __syncthreads();
+        }
+        if (any_inner) s_inner = 1;   // (benign race: every writer stores 1)
+        n = base;
+        int32_t *t = cur;
+        cur = nxt;
+        nxt = t;
+        __syncthreads();
+    }
+    // the entries of `cur` are leaves now
+    if (tid == 0) {
+        uint32_t ok = 0;
+        if (n) {
+            const uint4 lf = __ldg(T.leaves + (uint32_t) ~cur[0]);
+            if (lf.z >= plen) {
+                const uint8_t *lk = T.keys + (((uint64_t) lf.y << 32) | lf.x);
+                uint32_t j = 0;
+                while (j < plen && lk[j] == prefix[j]) j++;
+                ok = j == plen;
+            }
+        }
+        s_ok = ok;
+        out[0] = ok ? n : 0u;
+    }
+    __syncthreads();
+    if (s_ok)
+        for (uint32_t i = tid; i < n; i += ITER_THREADS) out[1 + i] = __ldg(T.leaves + (uint32_t) ~cur[i]).w;
+}
+
+// record ids of all live keys starting with the escaped prefix, ascending key order - walked on the device
+void iter_prefix(Store &S, const uint8_t *h_prefix, uint32_t plen, std::vector<uint32_t> &out) {
+    out.clear();
+    if (S.index->size() == 0) return;
+    cudaStream_t st = S.st;
+    HostIndex::DeviceView T = S.index->device_view(st);
+    const size_t cap = S.index->size() * 2 + 64;   // leaves + inner nodes
+    S.iter_buf.reserve_discard(3 * cap + 64);
+    S.in_keys.reserve_discard((size_t) plen + 16);
+    if (plen) PX_CUDA(cudaMemcpyAsync(S.in_keys.p, h_prefix, plen, cudaMemcpyHostToDevice, st));
+    int32_t *b0 = reinterpret_cast<int32_t *>(S.iter_buf.p), *b1 = b0 + cap;
+    uint32_t *o = S.iter_buf.p + 2 * cap;
+    k_iter_prefix<<<1, ITER_THREADS, 0, st>>>(T, S.in_keys.p, plen, b0, b1, o);
+    PX_LAUNCH_CHECK();
+    S.launches++;
+    uint32_t n = 0;
+    PX_CUDA(cudaMemcpyAsync(&n, o, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    out.resize(n);
+    if (n) {
+        PX_CUDA(cudaMemcpyAsync(out.data(), o + 1, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaStreamSynchronize(st));
+    }
 }
 
 // depth of the leaf each (raw) key's walk ends in: inner nodes visited (measurement only)

@@ -37,6 +37,11 @@ class HostIndex {
     size_t host_bytes() const;
     size_t device_bytes() const;
     size_t key_arena_bytes() const { return arena.size(); }
+    // wire format of the whole tree (flat SoA arrays, leaf -> record ids, escaped-key arena): the index of a store
+    // whose chunks were exported with pixiu_export_chunk; load() replaces the tree (the device mirror is rebuilt on
+    // the next lookup).  live_out: the record ids the leaves point to.
+    void save(std::vector<uint8_t> &out) const;
+    bool load(const uint8_t *blob, size_t size, uint32_t n_records, std::vector<uint32_t> &live_out);
 
     // ---- device mirror ----
     struct DeviceView {
@@ -121,5 +126,7 @@ struct Store;
 void lookup_batch(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, std::vector<uint32_t> &rec_out);
 void contains_batch_dev(Store &S, int64_t n, const uint8_t *d_keys, const int64_t *d_koff, uint8_t *d_found);
 void index_depths(Store &S, int64_t n, const uint8_t *h_keys, const int64_t *h_koff, int32_t *out);
+// iter(prefix) walked on the device (k_iter_prefix): record ids in ascending key order
+void iter_prefix(Store &S, const uint8_t *h_prefix, uint32_t plen, std::vector<uint32_t> &out);
 
 }  // namespace pixiu

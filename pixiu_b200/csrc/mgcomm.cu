@@ -115,6 +115,22 @@ int mg_comm_init(Store &S, int rank, int world, const uint8_t *id) {
     }
     for (auto &e : c->ev) PX_CUDA(cudaEventCreate(&e));
     if (A.GetVersion) A.GetVersion(&c->version);
+    // NCCL connects its channels lazily, on the first collective of a communicator (hundreds of milliseconds): do
+    // that here, with one all-reduce of each kind and of a typical size, instead of inside the first batch
+    if (world > 1) {
+        DevBuf<uint32_t> tmp;
+        const size_t n_max = 4u << 20, n_min = 64u << 10;
+        tmp.reserve_discard(n_max);
+        PX_CUDA(cudaMemsetAsync(tmp.p, 0, n_max * sizeof(uint32_t), S.st));
+        ncclResult_t r1 = A.AllReduce(tmp.p, tmp.p, n_max, ncclUint32, ncclMax, c->comm, S.st);
+        ncclResult_t r2 = A.AllReduce(tmp.p, tmp.p, n_min, ncclUint32, ncclMin, c->comm, S.st);
+        PX_CUDA(cudaStreamSynchronize(S.st));
+        if (r1 != ncclSuccess || r2 != ncclSuccess) {
+            S.err = std::string("NCCL warm-up all-reduce: ") + A.GetErrorString(r1 != ncclSuccess ? r1 : r2);
+            delete c;
+            return PIXIU_ECUDA;
+        }
+    }
     S.mg_comm = c;
     S.mg_rank = rank;
     S.mg_world = world;

@@ -204,6 +204,7 @@ struct Store {
     DevBuf<uint8_t> mg_in_keys, mg_in_vals;
     DevBuf<int64_t> mg_in_koff, mg_in_voff;
     DevBuf<uint32_t> doc_len, doc_off;
+    DevBuf<uint32_t> iter_buf;     // frontier ping-pong buffers + output of the device-side prefix walk
 
     Store() = default;
     ~Store();

@@ -61,6 +61,7 @@ EXPORTS = [
     "pixiu_reinsert_chunk", "pixiu_chunk_info",
     "pixiu_export_chunk", "pixiu_mg_config", "pixiu_mg_setitem_begin", "pixiu_mg_setitem_mid", "pixiu_mg_setitem_end",
     "pixiu_mg_unique_id", "pixiu_mg_comm_init", "pixiu_mg_setitem_batch", "pixiu_mg_get_stats",
+    "pixiu_export_index", "pixiu_import_chunk_raw", "pixiu_import_index",
 ]
 
 _lib = None
@@ -112,6 +113,10 @@ def load_library():
     L.pixiu_reinsert_chunk.restype = C.c_int64
     L.pixiu_chunk_info.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p, _i32p]
     L.pixiu_export_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p, _i64p]
+    L.pixiu_export_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, _i64p]
+    L.pixiu_import_chunk_raw.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.pixiu_import_chunk_raw.restype = C.c_int64
+    L.pixiu_import_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.pixiu_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.pixiu_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), _i64p]
@@ -403,6 +408,25 @@ class PiXiuCtrl:
     def import_chunk(self, encs) -> int:
         ed, eo = encs if isinstance(encs, tuple) else _pack(encs)
         return self._check(self._L.pixiu_import_chunk(self._h, len(eo) - 1, _ptr(ed), _ptr(eo)))
+
+    def import_chunk_raw(self, encs) -> int:
+        """a chunk's records without indexing them (the index follows with import_index)"""
+        ed, eo = encs if isinstance(encs, tuple) else _pack(encs)
+        return self._check(self._L.pixiu_import_chunk_raw(self._h, len(eo) - 1, _ptr(ed), _ptr(eo)))
+
+    def export_index(self) -> np.ndarray:
+        """the CritBit index in its wire format (feeds import_index of a store holding the same chunks)"""
+        need = C.c_int64(0)
+        rc = self._L.pixiu_export_index(self._h, None, 0, C.byref(need))
+        if rc not in (OK, ENOSPC):
+            self._check(rc)
+        buf = np.zeros(max(need.value, 1), dtype=np.uint8)
+        self._check(self._L.pixiu_export_index(self._h, _ptr(buf), buf.size, C.byref(need)))
+        return buf[:need.value]
+
+    def import_index(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._check(self._L.pixiu_import_index(self._h, _ptr(blob), blob.size))
 
     def export_chunk(self, chunk: int):
         """-> (enc u8[], off i64[n+1]): the chunk's wire format (feeds import_chunk of another store)"""

@@ -445,6 +445,42 @@ def test_export_import_roundtrip(ctrl_mod):
     b.free_prop()
 
 
+def test_export_import_with_index_blob(ctrl_mod):
+    """the whole store in its wire format: chunks + the serialised CritBit SoA; the copy serves lookups, getitem, iter
+    and deletes without rebuilding anything (no decode on import, no per-key insert)"""
+    kd, ko, vd, vo = synth.gen_urls_kv(4000, seed=12)
+    keys, vals = synth.unpack(kd, ko), synth.unpack(vd, vo)
+    a = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=150000)
+    a.setitem_batch((kd, ko), (vd, vo))
+    a.setitem_batch(keys[:300], vals[300:600])          # replaced records: tombstones in the exported chunks
+    dead = keys[1000:1100]
+    assert not a.delitem_batch(dead).any()
+    b = ctrl_mod.PiXiuCtrl()
+    for c in range(a.stats().chunks):
+        b.import_chunk_raw(a.export_chunk(c))
+    assert not b.contains(keys[5])                       # nothing is indexed yet
+    b.import_index(a.export_index())
+    sa, sb = a.stats(), b.stats()
+    assert (sb.records, sb.live_records, sb.encoded_bytes) == (sa.records, sa.live_records, sa.encoded_bytes)
+    latest = dict(zip(keys, vals))
+    latest.update(zip(keys[:300], vals[300:600]))
+    buf, off, found = b.getitem_batch((kd, ko))
+    for i, k in enumerate(keys):
+        assert bool(found[i]) == (k not in dead), i
+        if found[i]:
+            assert ctrl_mod.split_doc(buf[off[i]:off[i + 1]].tobytes()) == (k, latest[k])
+    assert [ctrl_mod.split_doc(d)[0] for d in b.iter_docs(b"http://news")] == sorted(k for k in latest if k.startswith(b"http://news") and k not in dead)
+    assert b.delitem(keys[7]) == 0 and not b.contains(keys[7]) and b.setitem(b"new-key", b"v") == 0 and b.contains(b"new-key")
+    with pytest.raises(ctrl_mod.PiXiuError):             # a corrupt blob is refused
+        c = ctrl_mod.PiXiuCtrl()
+        c.import_chunk_raw(a.export_chunk(0))
+        blob = a.export_index().copy()
+        blob[40:48] = 255
+        c.import_index(blob)
+    a.free_prop()
+    b.free_prop()
+
+
 def test_api_edge_cases(ctrl_mod):
     """empty store / empty batch, duplicates inside one batch (in-order semantics), key-only records,
     keys that are prefixes of each other, binary keys full of 251 / 0 / 2, deleted keys"""
