@@ -134,7 +134,7 @@ struct alignas(16) WarpSmem {       // K10
     };
     uint16_t heads[SEG_MAX + 8];    // staged positions of the reference heads, ascending
     uint2 piece[PIECE_BUF];         // the tile's copy pieces, flushed to the packed table at the end
-    uint16_t first_tok[TILE / STRIP + 4];  // per strip: the token that governs its first byte
+    uint16_t first_tok[TILE / STRIP + 4];  // per strip: the token that governs its first byte (u <= 2062: 33 strips)
 };
 struct alignas(16) CopySmem {       // K11
     Pending pc;
@@ -500,8 +500,8 @@ k_decode_literals(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr) {
     const bool raw_first = skip == 0xFFFF;  // first enc byte is the 2nd half of an escape pair
     if (raw_first) skip = 0;
     const uint32_t chunk_first = j1.z;
-    const uint32_t mis = (rec_base + t0) & 3u;   // (the arena itself is at least 16-byte aligned)
-    const uint32_t B0 = rec_base + t0 - mis;     // arena position of u = 0 (word aligned); u = output byte + mis
+    const uint32_t mis = (rec_base + t0) & 15u;  // (the arena itself is at least 16-byte aligned)
+    const uint32_t B0 = rec_base + t0 - mis;     // arena position of u = 0 (16-byte aligned); u = output byte + mis
     const uint32_t nu = nbytes + mis;
     bool failed = false;
     if (ne > ENC_MAX) {   // (k_dec_work flags an inconsistent descriptor this way)
@@ -802,7 +802,7 @@ k_decode_literals(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr) {
         S.tt.dl[nheads] = (int16_t) ((int) carry_stg - carry_out - (int) mis);
     }
     __syncwarp();
-    // ---- 4. the tile is written once, a 64-byte strip per lane ----
+    // ---- 4. the tile is written once, a 64-byte strip per lane, 16 bytes (one store) at a time ----
     if (!failed) {
         uint8_t *const dstu = V.arena + B0;
 #pragma unroll 1
@@ -811,17 +811,23 @@ k_decode_literals(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr) {
             int ts_i = S.tt.ts[i], te_i = S.tt.te[i], dl_i = S.tt.dl[i];
             const int s_end = (int) min((s + 1) * STRIP, nu);
 #pragma unroll 1
-            for (int pos = (int) (s * STRIP); pos < s_end; pos += 4) {
-                const int lo = max(pos, (int) mis), end = min(pos + 4, s_end);   // bytes [lo, end) of this word belong to the tile
-                uint32_t x = 0, lit = 0;   // the word; its literal bytes (0xFF each)
+            for (int pos = (int) (s * STRIP); pos < s_end; pos += 16) {
+                const int lo = max(pos, (int) mis), end = min(pos + 16, s_end);   // bytes [lo, end) of this group belong to the tile
+                uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;   // the group's four words
+                uint32_t lit = 0;                          // its literal bytes (one bit each)
                 int cur = lo;
                 while (true) {
-                    if (cur < ts_i) {   // literals in front of token i: bytes [cur, min(ts_i, end))
+                    if (cur < ts_i) {   // literals in front of token i: bytes [cur, min(ts_i, end)), staged at u + dl_i
                         const int se = min(ts_i, end);
-                        const uint32_t m = (0xFFFFFFFFu >> (32 - 8 * (se - pos))) & (0xFFFFFFFFu << (8 * (cur - pos)));
-                        const uint32_t q = (uint32_t) (pos + dl_i);
-                        x |= __funnelshift_r(S.stg[q >> 2], S.stg[(q >> 2) + 1], 8 * (q & 3)) & m;
-                        lit |= m;
+                        const uint32_t bm = (0xFFFFu >> (16 - (se - pos))) & (0xFFFFu << (cur - pos));
+                        const uint32_t q = (uint32_t) (pos + dl_i), wq = q >> 2, sh = 8 * (q & 3);
+                        const uint32_t a0 = S.stg[wq], a1 = S.stg[wq + 1], a2 = S.stg[wq + 2], a3 = S.stg[wq + 3], a4 = S.stg[wq + 4];
+                        // (nibble -> byte mask: 0xF -> 0xFFFFFFFF, 0x3 -> 0x0000FFFF, ...)
+                        x0 |= __funnelshift_r(a0, a1, sh) & ((((bm & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                        x1 |= __funnelshift_r(a1, a2, sh) & (((((bm >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                        x2 |= __funnelshift_r(a2, a3, sh) & (((((bm >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                        x3 |= __funnelshift_r(a3, a4, sh) & (((((bm >> 12) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                        lit |= bm;
                         cur = se;
                     }
                     if (cur < te_i) cur = min(te_i, end);   // bytes of token i: zero = "not final yet"
@@ -831,12 +837,16 @@ k_decode_literals(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr) {
                     te_i = S.tt.te[i];
                     dl_i = S.tt.dl[i];
                 }
-                if (lo == pos && end == pos + 4) {
-                    *reinterpret_cast<uint32_t *>(dstu + pos) = x;
+                if (lo == pos && end == pos + 16) {
+                    *reinterpret_cast<uint4 *>(dstu + pos) = make_uint4(x0, x1, x2, x3);
                 } else {
-                    for (int k = lo; k < end; k++) dstu[k] = (uint8_t) (x >> (8 * (k - pos)));
+                    for (int k = lo; k < end; k++) {
+                        const uint32_t xw = (k - pos) < 4 ? x0 : (k - pos) < 8 ? x1 : (k - pos) < 12 ? x2 : x3;
+                        dstu[k] = (uint8_t) (xw >> (8 * ((k - pos) & 3)));
+                    }
                 }
-                const uint32_t zb = nibz(x | ~lit);   // zero-valued literal bytes are final: announce them
+                // zero-valued literal bytes are final: announce them
+                const uint32_t zb = (nibz(x0) | (nibz(x1) << 4) | (nibz(x2) << 8) | (nibz(x3) << 12)) & lit;
                 if (zb) publish_zeros(P, B0 + (uint32_t) pos, zb);
             }
         }
@@ -880,7 +890,7 @@ k_decode_copies(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr, uint3
         const uint2 ph = V.phead[w];
         const uint4 j0 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w)), j1 = __ldg(reinterpret_cast<const uint4 *>(V.jobs + w) + 1);
         const uint32_t at = j0.z + (j1.x & 0xFFFFu);   // arena position of the tile's first byte
-        const uint32_t B0 = at - (at & 3u);
+        const uint32_t B0 = at - (at & 15u);
         uint32_t sweeps = 0;
 #pragma unroll 1
         for (uint32_t b0 = 0; b0 < ph.y; b0 += piece_cap) {

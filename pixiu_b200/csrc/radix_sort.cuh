@@ -17,7 +17,13 @@ namespace pixiu {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 8;
+#ifndef PIXIU_RS_ITEMS
+#define PIXIU_RS_ITEMS 8
+#endif
+#ifndef PIXIU_RS_MINB
+#define PIXIU_RS_MINB 5
+#endif
+constexpr int RS_ITEMS = PIXIU_RS_ITEMS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // keys per CTA
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
@@ -65,7 +71,7 @@ static __global__ void __launch_bounds__(RS_BINS) k_rs_scan_bins(uint32_t *hist)
 // Dynamic shared memory: RS_TILE keys + RS_TILE values (the tile is re-ordered by digit in shared
 // memory so that the global stores of one digit are consecutive: coalesced 128-byte runs on average).
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS, 5)
+__global__ void __launch_bounds__(RS_THREADS, PIXIU_RS_MINB)
 k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const uint32_t *__restrict__ vals_in,
               uint32_t *__restrict__ vals_out, uint32_t n, int shift, const uint32_t *__restrict__ bin_base,
               uint32_t *__restrict__ status, uint32_t *__restrict__ ticket, uint32_t *__restrict__ err) {
