@@ -699,10 +699,51 @@ def bench_sharded(args, env):
     match lengths are MAX-reduced and leftmost candidates MIN-reduced by ncclAllReduce inside libpixiu_b200.so
     (pixiu_mg_setitem_batch).  Total work is fixed as N grows: strong scaling."""
     torch = env.torch
-    from pixiu_b200 import ctrl, multigpu, shard
+    from pixiu_b200 import ctrl, multigpu, shard, synth
 
     rank, world = env.rank, env.world
-    kd, ko, vd, vo = gen_corpus(args.shard_pages, 2)          # the same corpus on every rank
+    # The same corpus on every rank.  Large corpora (BASELINE config 5: 8 GB = ~200k pages) are generated in 8 parts,
+    # each by one rank, and broadcast: the page generator is single-threaded Python/numpy (~1 min per GB).
+    PARTS = 8
+    if world > 1 and args.shard_pages >= 16 * PARTS:
+        per = args.shard_pages // PARTS
+        parts = [None] * PARTS
+        for p in range(PARTS):
+            if p % world == rank:
+                a = synth.gen_html_pages(per if p < PARTS - 1 else args.shard_pages - per * (PARTS - 1), seed=500 + p)
+                # (keys are only unique inside one generator call: tag them with the part)
+                tag = np.frombuffer(b"/p%d" % p, dtype=np.uint8)
+                klen = np.diff(a[1]) + len(tag)
+                ko2 = np.zeros(len(klen) + 1, dtype=np.int64)
+                np.cumsum(klen, out=ko2[1:])
+                kd2 = np.empty(int(ko2[-1]), dtype=np.uint8)
+                src_idx = synth.ragged_gather(np.arange(len(a[0]), dtype=np.int64), a[1][:-1], np.diff(a[1]))
+                pos = np.repeat(ko2[:-1], np.diff(a[1])) + (np.arange(len(a[0])) - np.repeat(a[1][:-1], np.diff(a[1])))
+                kd2[pos] = a[0][src_idx]
+                for j in range(len(tag)):
+                    kd2[ko2[1:] - len(tag) + j] = tag[j]
+                parts[p] = (kd2, ko2, a[2], a[3])
+        for p in range(PARTS):
+            owner = p % world
+            hdr = torch.zeros(4, dtype=torch.int64, device=env.dev)
+            if owner == rank:
+                hdr = torch.tensor([len(x) for x in parts[p]], dtype=torch.int64, device=env.dev)
+            env.dist.broadcast(hdr, src=owner)
+            out = []
+            for j, (n_el, dt) in enumerate(zip(hdr.tolist(), (torch.uint8, torch.int64, torch.uint8, torch.int64))):
+                t = torch.from_numpy(parts[p][j]).to(env.dev) if owner == rank else torch.empty(n_el, dtype=dt, device=env.dev)
+                env.dist.broadcast(t, src=owner)
+                out.append(t.cpu().numpy())
+                del t
+            parts[p] = tuple(out)
+        kd = np.concatenate([x[0] for x in parts])
+        vd = np.concatenate([x[2] for x in parts])
+        ko = np.concatenate([[0]] + [x[1][1:] + off for x, off in zip(parts, np.cumsum([0] + [int(x[1][-1]) for x in parts[:-1]]))]).astype(np.int64)
+        vo = np.concatenate([[0]] + [x[3][1:] + off for x, off in zip(parts, np.cumsum([0] + [int(x[3][-1]) for x in parts[:-1]]))]).astype(np.int64)
+        del parts
+        torch.cuda.empty_cache()
+    else:
+        kd, ko, vd, vo = gen_corpus(args.shard_pages, 2)
     n = len(ko) - 1
     raw = int(ko[-1] + vo[-1])
     bp = args.batch_pages

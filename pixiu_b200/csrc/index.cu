@@ -7,6 +7,7 @@
 
 #include "scan.cuh"
 #include "store.h"
+#include "mintree.cuh"
 
 namespace pixiu {
 
@@ -562,6 +563,340 @@ k_insert_probe(uint32_t n, HostIndex::DeviceView T, const uint8_t *__restrict__ 
     out[i] = r;
 }
 
+// ---------------------------------------------------------------------------------
+// Bulk build of the tree on the GPU: when a batch is at least as large as the tree, the tree is not
+// spliced key by key on the host (CritBitTree::setitem, CritBitTree.cpp:13-105: 0.35 us per key, serial) but rebuilt
+// from ALL keys - the live leaves and the batch - on the device:
+//   1. LSD radix sort of the keys by their bytes, 8 bytes per round from the last chunk to the first (the existing
+//      onesweep sort; stable, so equal keys keep their order: tree first, then the batch in insertion order);
+//   2. equal neighbours: the last of a group survives, every batch element whose key was there before it replaces its
+//      predecessor (in-order semantics of n setitem calls: rc = CBT_SET_REPLACE and the old record is tombstoned);
+//   3. critical position of every pair of neighbouring distinct keys (first differing byte, highest differing bit);
+//   4. the tree over the sorted leaves is the Cartesian tree of those positions (the pair with the smallest position
+//      splits a range: it is unique there): nearest smaller position to the left and to the right of every pair
+//      (block-min tree search), the parent is the nearer-in-value of the two, children are set by their parents' slots;
+//   5. the flat arrays come back to the host mirror in one copy; the leaves are in key order.
+// ---------------------------------------------------------------------------------
+constexpr uint32_t BULK_MAX_KEY = 248;   // escaped key bytes the radix rounds cover (longer keys: the host path)
+
+// 8 key bytes [8c, 8c + 8) of entry perm[j], big endian, zero padded: the radix key of round c
+__global__ void __launch_bounds__(256)
+k_bulk_chunk(uint32_t n, const uint32_t *__restrict__ perm, const uint64_t *__restrict__ eoff, const uint32_t *__restrict__ elen,
+             const uint8_t *__restrict__ keys, uint32_t c, uint64_t *__restrict__ out) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t e = perm ? perm[j] : j;
+    const uint8_t *k = keys + eoff[e];
+    const uint32_t len = elen[e];
+    uint64_t v = 0;
+#pragma unroll
+    for (uint32_t b = 0; b < 8; b++) {
+        const uint32_t p = 8 * c + b;
+        v = (v << 8) | (p < len ? (uint64_t) k[p] : 0ull);
+    }
+    out[j] = v;
+}
+
+// neighbours in sorted order: dup[j] = same key as j - 1; crit[j] = (first differing byte << 8) | mask otherwise
+__global__ void __launch_bounds__(256)
+k_bulk_adjacent(uint32_t n, const uint32_t *__restrict__ perm, const uint64_t *__restrict__ eoff, const uint32_t *__restrict__ elen,
+                const uint8_t *__restrict__ keys, uint8_t *__restrict__ dup, uint32_t *__restrict__ crit) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    if (j == 0) {
+        dup[0] = 0;
+        crit[0] = 0;
+        return;
+    }
+    const uint32_t a = perm[j - 1], b = perm[j];
+    const uint8_t *ka = keys + eoff[a], *kb = keys + eoff[b];
+    const uint32_t la = elen[a], lb = elen[b], m = min(la, lb);
+    uint32_t d = 0;
+    while (d < m && ka[d] == kb[d]) d++;
+    if (d == la && d == lb) {
+        dup[j] = 1;
+        crit[j] = 0;
+        return;
+    }
+    // (keys end with 251,0 and are prefix free: d < m)
+    uint32_t x = (uint32_t) (ka[d] ^ kb[d]);
+    x |= x >> 1;
+    x |= x >> 2;
+    x |= x >> 4;
+    const uint32_t mk = ((x & ~(x >> 1)) ^ 0xFFu) & 0xFFu;
+    dup[j] = 0;
+    crit[j] = (d << 8) | mk;
+}
+
+// survivors -> leaves (key order), replaced predecessors -> old_out, crit of unique pair (u - 1, u) -> cu[u - 1]
+__global__ void __launch_bounds__(256)
+k_bulk_leaves(uint32_t n, uint32_t n_old, const uint32_t *__restrict__ perm, const uint8_t *__restrict__ dup,
+              const uint32_t *__restrict__ crit, const uint32_t *__restrict__ uidx /* exclusive count of group heads */,
+              const uint64_t *__restrict__ eoff, const uint32_t *__restrict__ elen, const uint32_t *__restrict__ erec,
+              uint64_t *__restrict__ leaf_koff, uint32_t *__restrict__ leaf_klen, uint32_t *__restrict__ leaf_rec,
+              uint32_t *__restrict__ cu, long long *__restrict__ old_out) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t e = perm[j];
+    const uint32_t u = uidx[j] + (dup[j] ? 0u : 1u) - 1u;   // index of this element's group among the unique keys
+    if (dup[j] && e >= n_old) old_out[e - n_old] = (long long) erec[perm[j - 1]];   // it replaces its predecessor
+    if (!dup[j] && u > 0) cu[u - 1] = crit[j];
+    if (j + 1 == n || !dup[j + 1]) {   // the last of its group survives
+        leaf_koff[u] = eoff[e];
+        leaf_klen[u] = elen[e];
+        leaf_rec[u] = erec[e];
+    }
+}
+
+// inner node i sits between leaves i and i + 1; its parent is the nearer in value of the nearest smaller positions to
+// its left and right; a side without inner nodes holds the leaf
+__global__ void __launch_bounds__(256)
+k_bulk_tree(uint32_t ni, MinTree T, const uint32_t *__restrict__ cu, int32_t *__restrict__ child0, int32_t *__restrict__ child1,
+            uint16_t *__restrict__ diff_at, uint8_t *__restrict__ mask, int32_t *__restrict__ root) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= ni) return;
+    const uint32_t c = cu[i];
+    uint32_t acc = 0xFFFFFFFFu;
+    const int64_t L = i > 0 ? tree_search<true, false, true>(T, i, c, acc, -1) : -1;
+    const int64_t R = i + 1 < ni ? tree_search<false, false, true>(T, i, c, acc, -1) : (int64_t) ni;
+    diff_at[i] = (uint16_t) (c >> 8);
+    mask[i] = (uint8_t) (c & 0xFFu);
+    if (L == (int64_t) i - 1) child0[i] = ~(int32_t) i;          // no inner node between L and i: leaf i
+    if (R == (int64_t) i + 1) child1[i] = ~(int32_t) (i + 1);    // ... leaf i + 1
+    if (L < 0 && R >= (int64_t) ni) {
+        *root = (int32_t) i;
+    } else {
+        const int64_t p = L < 0 ? R : (R >= (int64_t) ni ? L : (cu[L] > cu[R] ? L : R));
+        if ((int64_t) i < p) child0[p] = (int32_t) i;
+        else child1[p] = (int32_t) i;
+    }
+}
+
+bool HostIndex::bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, const int64_t *d_koff, uint32_t first_rec,
+                           int64_t *old_out) {
+    cudaStream_t st = S.st;
+    // live leaves of the tree (slot list) and their longest key
+    std::vector<uint32_t> live_slots;
+    live_slots.reserve(n_live);
+    {
+        std::vector<uint8_t> is_free(leaf_rec.size(), 0);
+        for (int32_t f : free_leaf) is_free[(size_t) f] = 1;
+        for (size_t sidx = 0; sidx < leaf_rec.size(); sidx++)
+            if (!is_free[sidx]) {
+                if (leaf_klen[sidx] > BULK_MAX_KEY) return false;
+                live_slots.push_back((uint32_t) sidx);
+            }
+    }
+    const uint32_t n_old = (uint32_t) live_slots.size();
+    const uint64_t E64 = (uint64_t) n_old + n;
+    if (E64 >= 0x7fffffffull) return false;
+    const uint32_t E = (uint32_t) E64;
+    // escaped batch keys on the device
+    d_qlen.reserve_discard(n + 1);
+    d_qoff.reserve_discard((size_t) n + 2);
+    uint32_t *ql = d_qlen.p;
+    uint64_t *qo = d_qoff.p;
+    k_query_len<<<div_up<uint32_t>(n, 256), 256, 0, st>>>(n, d_keys_raw, d_koff, ql);
+    device_scan<uint64_t>(
+        (size_t) n + 1, [=] __device__(size_t i) -> uint64_t { return i < n ? (uint64_t) ql[i] : 0ull; },
+        [=] __device__(size_t i, uint64_t v) { qo[i] = v; }, OpSum(), 0ull, true, S.es.scanws, st);
+    // (longest batch key: a max-scan's last element)
+    DevBuf<uint32_t> &tmp32 = S.iter_buf;
+    tmp32.reserve_discard(4 * (size_t) E + 64);
+    uint32_t *d_max = tmp32.p;
+    device_scan<uint32_t>(
+        (size_t) n, [=] __device__(size_t i) -> uint32_t { return ql[i]; },
+        [=] __device__(size_t i, uint32_t v) {
+            if (i + 1 == n) d_max[0] = v;
+        },
+        OpMax(), 0u, false, S.es.scanws, st);
+    uint64_t qbytes = 0;
+    uint32_t qmax = 0;
+    PX_CUDA(cudaMemcpyAsync(&qbytes, qo + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(&qmax, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    if (qmax > BULK_MAX_KEY) return false;
+    uint32_t lmax = qmax;
+    for (uint32_t sidx : live_slots) lmax = std::max(lmax, leaf_klen[sidx]);
+    // the batch keys join the key arena (device: appended behind the mirrored arena; host: one copy back)
+    device_view(st);   // the mirror is current (arena uploaded)
+    const uint64_t abase = arena.size();
+    this->d_keys.reserve_keep(abase + qbytes + 16, keys_uploaded, st);
+    k_query_write<<<div_up<uint32_t>(n, 256), 256, 0, st>>>(n, d_keys_raw, d_koff, qo, this->d_keys.p + abase);
+    arena.resize(abase + qbytes);
+    PX_CUDA(cudaMemcpyAsync(arena.data() + abase, this->d_keys.p + abase, qbytes, cudaMemcpyDeviceToHost, st));
+    keys_uploaded = arena.size();
+    // entries: live leaves first, then the batch in order
+    DevBuf<uint64_t> &eoff = S.es.qoff;          // (free here: the lookups' query offsets)
+    eoff.reserve_discard((size_t) E + 2);
+    DevBuf<uint32_t> elen, erec;
+    elen.reserve_discard(E + 1);
+    erec.reserve_discard(E + 1);
+    {
+        std::vector<uint64_t> ho(n_old);
+        std::vector<uint32_t> hl(n_old), hr(n_old);
+        for (uint32_t k = 0; k < n_old; k++) {
+            ho[k] = leaf_koff[live_slots[k]];
+            hl[k] = leaf_klen[live_slots[k]];
+            hr[k] = leaf_rec[live_slots[k]];
+        }
+        if (n_old) {
+            PX_CUDA(cudaMemcpyAsync(eoff.p, ho.data(), n_old * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            PX_CUDA(cudaMemcpyAsync(elen.p, hl.data(), n_old * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            PX_CUDA(cudaMemcpyAsync(erec.p, hr.data(), n_old * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            PX_CUDA(cudaStreamSynchronize(st));
+        }
+        uint64_t *eo = eoff.p;
+        uint32_t *el = elen.p, *er = erec.p;
+        device_scan<uint32_t>(
+            (size_t) n, [=] __device__(size_t i) -> uint32_t { return 0u; },
+            [=] __device__(size_t i, uint32_t) {
+                eo[n_old + i] = abase + qo[i];
+                el[n_old + i] = ql[i];
+                er[n_old + i] = first_rec + (uint32_t) i;
+            },
+            OpSum(), 0u, true, S.es.scanws, st);
+    }
+    // ---- 1. LSD radix sort by 8-byte chunks ----
+    EncodeScratch &X = S.es;
+    X.keys0.reserve_discard(E);
+    X.keys1.reserve_discard(E);
+    X.vals0.reserve_discard(E);
+    X.vals1.reserve_discard(E);
+    if (!X.counters.p) {
+        X.counters.reserve_discard(16);
+        PX_CUDA(cudaMemsetAsync(X.counters.p, 0, 16 * sizeof(uint32_t), st));
+    }
+    const uint32_t nchunks = div_up<uint32_t>(lmax, 8);
+    uint32_t *perm = nullptr;   // nullptr: identity
+    int launches_ = 0;
+    for (int c = (int) nchunks - 1; c >= 0; c--) {
+        uint32_t *vin = perm ? perm : X.vals0.p;
+        uint32_t *vother = vin == X.vals0.p ? X.vals1.p : X.vals0.p;
+        k_bulk_chunk<<<div_up<uint32_t>(E, 256), 256, 0, st>>>(E, perm, eoff.p, elen.p, this->d_keys.p, (uint32_t) c, X.keys0.p);
+        int cur;
+        if (!perm) {
+            cur = radix_sort_pairs<uint64_t>(X.keys0.p, X.keys1.p, X.vals0.p, X.vals1.p, E, 0, 64, true, X.rs, X.counters.p + 2, st, &launches_);
+            perm = cur ? X.vals1.p : X.vals0.p;
+        } else {
+            // values: the permutation so far (vin), ping-ponged with the other buffer
+            cur = radix_sort_pairs<uint64_t>(X.keys0.p, X.keys1.p, vin, vother, E, 0, 64, false, X.rs, X.counters.p + 2, st, &launches_);
+            perm = cur ? vother : vin;
+        }
+        launches_++;
+    }
+    if (!perm) {   // (no key bytes at all cannot happen: keys end with 251,0)
+        return false;
+    }
+    // ---- 2./3. neighbours ----
+    DevBuf<uint8_t> dup;
+    dup.reserve_discard(E + 1);
+    uint32_t *crit = tmp32.p, *uidx = tmp32.p + E, *cu = tmp32.p + 2 * (size_t) E + 8;
+    k_bulk_adjacent<<<div_up<uint32_t>(E, 256), 256, 0, st>>>(E, perm, eoff.p, elen.p, this->d_keys.p, dup.p, crit);
+    {
+        const uint8_t *dp = dup.p;
+        uint32_t *ui = uidx;
+        device_scan<uint32_t>(
+            (size_t) E + 1, [=] __device__(size_t j) -> uint32_t { return j < E && !dp[j] ? 1u : 0u; },
+            [=] __device__(size_t j, uint32_t v) {
+                if (j < E) ui[j] = v;
+                else ui[E] = v;   // (slot E: the number of unique keys)
+            },
+            OpSum(), 0u, true, S.es.scanws, st);
+    }
+    uint32_t m = 0;
+    PX_CUDA(cudaMemcpyAsync(&m, uidx + E, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DevBuf<long long> d_old;
+    d_old.reserve_discard(n + 1);
+    PX_CUDA(cudaMemsetAsync(d_old.p, 0xFF, (size_t) n * sizeof(long long), st));   // -1
+    PX_CUDA(cudaStreamSynchronize(st));
+    if (m == 0) return false;
+    // ---- leaves in key order ----
+    d_leaf_koff.reserve_discard(m + 1);
+    d_leaf_klen.reserve_discard(m + 1);
+    d_leaf_rec.reserve_discard(m + 1);
+    k_bulk_leaves<<<div_up<uint32_t>(E, 256), 256, 0, st>>>(E, n_old, perm, dup.p, crit, uidx, eoff.p, elen.p, erec.p, d_leaf_koff.p,
+                                                           d_leaf_klen.p, d_leaf_rec.p, cu, d_old.p);
+    // ---- 4. Cartesian tree of the critical positions ----
+    const uint32_t ni = m - 1;
+    d_child0.reserve_discard(ni + 1);
+    d_child1.reserve_discard(ni + 1);
+    d_diff.reserve_discard(ni + 1);
+    d_mask.reserve_discard(ni + 1);
+    DevBuf<int32_t> d_root;
+    d_root.reserve_discard(4);
+    int32_t h_root = ~0;   // a single leaf
+    if (ni) {
+        MinTree T{};
+        size_t total = 0;
+        uint32_t sz = ni;
+        int nlev = 1;
+        while (sz > 1 && nlev < TREE_MAX_LEVELS) {
+            sz = div_up<uint32_t>(sz, TREE_B);
+            total += sz;
+            nlev++;
+        }
+        X.tree_a.reserve_discard(total + 1);
+        T.a[0] = cu;
+        T.l[0] = cu;
+        T.size[0] = ni;
+        T.nlev = 1;
+        sz = ni;
+        size_t o = 0;
+        while (sz > 1 && T.nlev < TREE_MAX_LEVELS) {
+            const uint32_t so = div_up<uint32_t>(sz, TREE_B);
+            k_tree_level<<<div_up<uint32_t>(so, 256), 256, 0, st>>>(T.a[T.nlev - 1], T.a[T.nlev - 1], sz, X.tree_a.p + o, X.tree_a.p + o, so);
+            T.a[T.nlev] = X.tree_a.p + o;
+            T.l[T.nlev] = X.tree_a.p + o;
+            T.size[T.nlev] = so;
+            T.nlev++;
+            o += so;
+            sz = so;
+        }
+        k_bulk_tree<<<div_up<uint32_t>(ni, 256), 256, 0, st>>>(ni, T, cu, d_child0.p, d_child1.p, d_diff.p, d_mask.p, d_root.p);
+        PX_CUDA(cudaMemcpyAsync(&h_root, d_root.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    PX_LAUNCH_CHECK();
+    // ---- 5. back to the host mirror ----
+    child[0].resize(ni);
+    child[1].resize(ni);
+    diff_at.resize(ni);
+    mask.resize(ni);
+    leaf_rec.resize(m);
+    leaf_klen.resize(m);
+    leaf_koff.resize(m);
+    std::vector<long long> h_old(n);
+    if (ni) {
+        PX_CUDA(cudaMemcpyAsync(child[0].data(), d_child0.p, ni * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaMemcpyAsync(child[1].data(), d_child1.p, ni * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaMemcpyAsync(diff_at.data(), d_diff.p, ni * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        PX_CUDA(cudaMemcpyAsync(mask.data(), d_mask.p, ni * sizeof(uint8_t), cudaMemcpyDeviceToHost, st));
+    }
+    PX_CUDA(cudaMemcpyAsync(leaf_rec.data(), d_leaf_rec.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(leaf_klen.data(), d_leaf_klen.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(leaf_koff.data(), d_leaf_koff.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(h_old.data(), d_old.p, (size_t) n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < n; i++) old_out[i] = h_old[i];
+    free_inner.clear();
+    free_leaf.clear();
+    root = h_root;
+    has_root = true;
+    n_live = m;
+    // the device arrays ARE the mirror now; the packed walk copies follow
+    d_nodes.reserve_discard(ni + 1);
+    d_leaves.reserve_discard(m + 1);
+    if (ni) k_pack_nodes<<<div_up<uint32_t>(ni, 256), 256, 0, st>>>(0u, ni, d_child0.p, d_child1.p, d_diff.p, d_mask.p, d_nodes.p);
+    k_pack_leaves<<<div_up<uint32_t>(m, 256), 256, 0, st>>>(0u, m, d_leaf_koff.p, d_leaf_klen.p, d_leaf_rec.p, d_leaves.p);
+    synced_inner = ni;
+    synced_leaf = m;
+    dirty = false;
+    mod_child.clear();
+    mod_leaf.clear();
+    S.launches += launches_ + 12;
+    return true;
+}
+
 void HostIndex::insert_batch(Store &S, uint32_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *h_keys,
                              const int64_t *h_koff, uint32_t first_rec, int64_t *old_out) {
     cudaStream_t st = S.st;
@@ -572,6 +907,16 @@ void HostIndex::insert_batch(Store &S, uint32_t n, const uint8_t *d_keys, const 
     bool reserved = false;
     uint64_t n_fallback = 0, n_rounds = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
+    // a batch at least as large as the tree: rebuild the whole tree on the GPU from the sorted keys
+    if (n >= S.knobs.bulk_min && (size_t) n >= n_live) {
+        const auto t0 = now();
+        if (bulk_build(S, n, d_keys, d_koff, first_rec, old_out)) {
+            if (trace)
+                fprintf(stderr, "[index] %u keys: bulk build on the GPU, %zu leaves, %.1f ms\n", n, n_live,
+                        std::chrono::duration<double, std::milli>(now() - t0).count());
+            return;
+        }
+    }
     while (a < n) {
         // while the tree is small (or the rest of the batch is), plain host inserts; afterwards sub-batches of
         // at most a quarter of the tree, so that few keys of a sub-batch meet on the same edge

@@ -66,6 +66,8 @@ class HostIndex {
     // that key i replaced, or -1.
     void insert_batch(Store &S, uint32_t n, const uint8_t *d_keys, const int64_t *d_koff, const uint8_t *h_keys,
                       const int64_t *h_koff, uint32_t first_rec, int64_t *old_out);
+    // the whole tree rebuilt on the GPU from the sorted keys (live leaves + batch); false: not applicable (long keys)
+    bool bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, const int64_t *d_koff, uint32_t first_rec, int64_t *old_out);
     struct Probe {
         int32_t leaf;     // best-match leaf slot
         int32_t parent;   // node above the new inner node (-1: the root edge)

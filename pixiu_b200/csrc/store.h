@@ -75,6 +75,7 @@ struct Knobs {
     uint64_t dec_arena_limit = 7ull << 29;  // PIXIU_DEC_ARENA_LIMIT: decoded bytes of one decode pass (3.5 GiB)
     uint32_t piece_cap = 0xFFFFFFFFu;       // PIXIU_PIECE_CAP: pending pieces a decode tile keeps before it drains them
     uint32_t sleep_after = 16, sleep_ns = 64;  // PIXIU_SLEEP_AFTER / _NS: back-off of the decoder's polls
+    uint32_t bulk_min = 65536;     // PIXIU_BULK_MIN: smallest batch the index rebuilds on the GPU instead of splicing on the host
     uint32_t copy_ctas = 8;        // PIXIU_COPY_CTAS: resident CTAs per SM of the copy kernel (persistent warps)
     uint32_t sweep_gap = 0;        // PIXIU_SWEEP_GAP: ns a decode warp sleeps between two sweeps over its open pieces
     std::string dec_trace_file;    // PIXIU_DEC_TRACE_FILE: per-tile timestamps of a decode call
@@ -93,6 +94,7 @@ struct Knobs {
         sleep_ns = (uint32_t) num("PIXIU_SLEEP_NS", sleep_ns);
         sweep_gap = (uint32_t) num("PIXIU_SWEEP_GAP", sweep_gap);
         copy_ctas = (uint32_t) num("PIXIU_COPY_CTAS", copy_ctas);
+        bulk_min = (uint32_t) num("PIXIU_BULK_MIN", bulk_min);
         if (const char *f = getenv("PIXIU_DEC_TRACE_FILE")) dec_trace_file = f;
     }
     bool set(const std::string &name, int64_t v) {
@@ -102,6 +104,7 @@ struct Knobs {
         else if (name == "sleep_ns") sleep_ns = (uint32_t) v;
         else if (name == "sweep_gap") sweep_gap = (uint32_t) v;
         else if (name == "copy_ctas") copy_ctas = (uint32_t) v;
+        else if (name == "bulk_min") bulk_min = (uint32_t) v;
         else if (name == "trace") trace = v != 0;
         else if (name == "lcp_kasai") lcp_kasai = v != 0;
         else if (name == "no_spec_emit") no_spec_emit = v != 0;

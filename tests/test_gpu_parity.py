@@ -605,10 +605,12 @@ def test_config4_style_lookup_at_scale(ctrl_mod):
     c.free_prop()
 
 
-def test_batched_index_insert_with_conflicts(ctrl_mod):
-    """the batched CritBit insert (GPU probes + host splices) against a dict: monotone ids (most keys of a
-    sub-batch meet on the same edges), keys that replace stored ones, duplicates inside one batch, deletes followed
-    by re-inserts (slot reuse), binary keys with 251s, and prefix iteration order afterwards"""
+@pytest.mark.parametrize("bulk_min", [1 << 30, 1])
+def test_batched_index_insert_with_conflicts(ctrl_mod, bulk_min):
+    """the batched CritBit insert against a dict - GPU probes + host splices (bulk_min huge), and the bulk build of the
+    whole tree on the GPU from the sorted keys (bulk_min = 1: every batch at least as large as the tree rebuilds it):
+    monotone ids (most keys of a sub-batch meet on the same edges), keys that replace stored ones, duplicates inside
+    one batch, deletes followed by re-inserts (slot reuse), binary keys with 251s, and prefix iteration order afterwards"""
     rng = np.random.default_rng(12)
     model = {}
 
@@ -622,7 +624,9 @@ def test_batched_index_insert_with_conflicts(ctrl_mod):
         assert rc.tolist() == want, tag
 
     c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_BYTES, window_bytes=4 << 20)
+    c.debug_set_knob("bulk_min", bulk_min)
     base = [b"http://h%d.example.com/a/%08d.htm" % (i % 7, 1000 + 3 * i) for i in range(20000)]   # monotone ids
+    put(base[:5], b"0")                                  # (a tiny tree first: the next batch is the larger one)
     put(base, b"a")
     mixed = ([b"http://h%d.example.com/a/%08d.htm" % (i % 7, 1000 + 3 * i + 1) for i in range(9000)]   # neighbours of stored keys
              + [base[i] for i in rng.integers(0, len(base), 4000)]                                     # replace stored keys
@@ -636,6 +640,8 @@ def test_batched_index_insert_with_conflicts(ctrl_mod):
     for k in gone:
         del model[k]
     put(gone[::2] + [b"http://h9.example.com/z/%07d" % i for i in range(6000)], b"c")
+    big = [b"http://h%d.example.com/b/%08d.htm" % (i % 5, 7 * i) for i in range(60000)] + base[::3]   # larger than the tree again
+    put(big, b"d")
     keys = list(model)
     probe = keys + gone[1::2]
     found = c.contains_batch(probe)
