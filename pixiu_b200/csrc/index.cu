@@ -675,6 +675,15 @@ k_bulk_tree(uint32_t ni, MinTree T, const uint32_t *__restrict__ cu, int32_t *__
 bool HostIndex::bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, const int64_t *d_koff, uint32_t first_rec,
                            int64_t *old_out) {
     cudaStream_t st = S.st;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto t_prev = tnow();
+    auto lap = [&](const char *what) {   // (PIXIU_TRACE: where the time of a bulk build goes)
+        if (!S.knobs.trace) return;
+        cudaStreamSynchronize(st);
+        const auto t = tnow();
+        fprintf(stderr, "[index bulk] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
     // live leaves of the tree (slot list) and their longest key
     std::vector<uint32_t> live_slots;
     live_slots.reserve(n_live);
@@ -757,6 +766,7 @@ bool HostIndex::bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, cons
             },
             OpSum(), 0u, true, S.es.scanws, st);
     }
+    lap("entries + key arena");
     // ---- 1. LSD radix sort by 8-byte chunks ----
     EncodeScratch &X = S.es;
     X.keys0.reserve_discard(E);
@@ -788,6 +798,7 @@ bool HostIndex::bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, cons
     if (!perm) {   // (no key bytes at all cannot happen: keys end with 251,0)
         return false;
     }
+    lap("radix sort");
     // ---- 2./3. neighbours ----
     DevBuf<uint8_t> dup;
     dup.reserve_discard(E + 1);
@@ -857,6 +868,7 @@ bool HostIndex::bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, cons
         PX_CUDA(cudaMemcpyAsync(&h_root, d_root.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
     PX_LAUNCH_CHECK();
+    lap("neighbours + leaves + tree");
     // ---- 5. back to the host mirror ----
     child[0].resize(ni);
     child[1].resize(ni);
@@ -865,7 +877,7 @@ bool HostIndex::bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, cons
     leaf_rec.resize(m);
     leaf_klen.resize(m);
     leaf_koff.resize(m);
-    std::vector<long long> h_old(n);
+    static_assert(sizeof(long long) == sizeof(int64_t), "old_out copy");
     if (ni) {
         PX_CUDA(cudaMemcpyAsync(child[0].data(), d_child0.p, ni * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         PX_CUDA(cudaMemcpyAsync(child[1].data(), d_child1.p, ni * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -875,9 +887,8 @@ bool HostIndex::bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, cons
     PX_CUDA(cudaMemcpyAsync(leaf_rec.data(), d_leaf_rec.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaMemcpyAsync(leaf_klen.data(), d_leaf_klen.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaMemcpyAsync(leaf_koff.data(), d_leaf_koff.p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaMemcpyAsync(h_old.data(), d_old.p, (size_t) n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(old_out, d_old.p, (size_t) n * sizeof(long long), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
-    for (uint32_t i = 0; i < n; i++) old_out[i] = h_old[i];
     free_inner.clear();
     free_leaf.clear();
     root = h_root;
@@ -894,6 +905,7 @@ bool HostIndex::bulk_build(Store &S, uint32_t n, const uint8_t *d_keys_raw, cons
     mod_child.clear();
     mod_leaf.clear();
     S.launches += launches_ + 12;
+    lap("host mirror");
     return true;
 }
 
