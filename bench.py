@@ -704,8 +704,9 @@ def bench_sharded(args, env):
     rank, world = env.rank, env.world
     # The same corpus on every rank.  Large corpora (BASELINE config 5: 8 GB = ~200k pages) are generated in 8 parts,
     # each by one rank, and broadcast: the page generator is single-threaded Python/numpy (~1 min per GB).
+    # The corpus is the same for every N (strong scaling).
     PARTS = 8
-    if world > 1 and args.shard_pages >= 16 * PARTS:
+    if args.shard_pages >= 16 * PARTS:
         per = args.shard_pages // PARTS
         parts = [None] * PARTS
         for p in range(PARTS):
@@ -723,7 +724,7 @@ def bench_sharded(args, env):
                 for j in range(len(tag)):
                     kd2[ko2[1:] - len(tag) + j] = tag[j]
                 parts[p] = (kd2, ko2, a[2], a[3])
-        for p in range(PARTS):
+        for p in range(PARTS if world > 1 else 0):
             owner = p % world
             hdr = torch.zeros(4, dtype=torch.int64, device=env.dev)
             if owner == rank:

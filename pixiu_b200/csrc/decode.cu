@@ -41,6 +41,9 @@ constexpr int DEC_WARPS = 4;
 #define PIXIU_DEC_MINB 7     // resident CTAs per SM the decode kernels are compiled for (register budget 65536 / (128 x this))
 #endif
 constexpr uint32_t ENC_MAX = TILE + 16;           // encoded bytes a tile can span
+#ifndef PIXIU_DEC_TMA
+#define PIXIU_DEC_TMA 1           // stage a tile's encoded bytes with one bulk-async copy instead of a load/store loop
+#endif
 constexpr uint32_t STG_PAD = 16;                  // free bytes in front of the staged range (reads just before it stay in bounds)
 constexpr uint32_t STG_BYTES = STG_PAD + 16 + ENC_MAX + 16;  // pad + 16-byte alignment slack + range + token read-ahead
 constexpr uint32_t STG_WORDS = (STG_BYTES + 31) / 32 * 8;  // whole 32-byte bitmap words
@@ -135,6 +138,7 @@ struct alignas(16) WarpSmem {       // K10
     uint16_t heads[SEG_MAX + 8];    // staged positions of the reference heads, ascending
     uint2 piece[PIECE_BUF];         // the tile's copy pieces, flushed to the packed table at the end
     uint16_t first_tok[TILE / STRIP + 4];  // per strip: the token that governs its first byte (u <= 2062: 33 strips)
+    uint64_t mbar;                  // the staging copy of a tile completes here (cp.async.bulk transaction bytes)
 };
 struct alignas(16) CopySmem {       // K11
     Pending pc;
@@ -481,6 +485,18 @@ k_decode_literals(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr) {
     // order does not matter and one atomic serves several tiles), until none is left
     constexpr uint32_t TICKETS = 4;
     uint32_t w = 0, w_end = 0;
+    if (lane < 4) S.stg[lane] = 0;   // the pad in front of the staged bytes stays zero
+#if PIXIU_DEC_TMA
+    const uint32_t mbar = (uint32_t) __cvta_generic_to_shared(&S.mbar);
+    const uint32_t stg_dst = (uint32_t) __cvta_generic_to_shared(S.stg + 4);
+    uint32_t mphase = 0;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+#endif
 #pragma unroll 1
     for (;; w++) {
     __syncwarp();
@@ -513,13 +529,42 @@ k_decode_literals(DecodeView V, uint32_t n_work, uint32_t *__restrict__ ctr) {
     const uint32_t soff = STG_PAD + a16, nstg = soff + ne;
     uint32_t nheads = 0;
     if (!failed) {
+        const uint32_t n16 = (a16 + ne + 8 + 15) >> 4;
+#if PIXIU_DEC_TMA
+        // one bulk copy (TMA, cp.async.bulk) per tile; its bytes land on the warp's mbarrier.  The warp's reads of
+        // the previous tile are behind the __syncwarp at the top of the loop; the proxy fence orders them before the
+        // asynchronous write
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(n16 * 16) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             stg_dst), "l"(gsrc - a16), "r"(n16 * 16), "r"(mbar)
+                         : "memory");
+        }
+        {
+            uint32_t ok = 0, spins = 0;
+            while (true) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok)
+                             : "r"(mbar), "r"(mphase)
+                             : "memory");
+                if (ok) break;
+                if (++spins > (1u << 22)) {   // (never seen: a copy that does not land would hang the warp)
+                    atomicExch(err, 9u);
+                    failed = true;
+                    break;
+                }
+            }
+            mphase ^= 1u;
+            failed = __any_sync(FULL, failed);
+        }
+#else
         const uint4 *g4 = reinterpret_cast<const uint4 *>(gsrc - a16);
         uint4 *s4 = reinterpret_cast<uint4 *>(S.stg);
-        const uint32_t n16 = (a16 + ne + 8 + 15) >> 4;
 #pragma unroll 1
         for (uint32_t j = lane; j < n16; j += 32) s4[1 + j] = g4[j];
-        if (lane < 4) S.stg[lane] = 0;
         __syncwarp();
+#endif
     }
     const uint8_t *SB = reinterpret_cast<const uint8_t *>(S.stg);
     if (!failed) {
