@@ -250,6 +250,15 @@ def cpu_contains_c4(keys_n, procs):
                       f"{keys_n}-key tree is shallower than the 10 M-key one, which favours the CPU; aggregate = keys / slowest instance"}
 
 
+def workload_config(args):
+    """the workload both arms are quoted on (everything measured goes into `results`, so that the two lines carry the
+    same `config`)"""
+    return {"workload": f"C2: {args.pages} synthetic HTML-like pages x <=60KB (bytes 33..126), URL keys, batched setitem, per GPU",
+            "records_per_gpu": args.pages, "window_policy": args.window,
+            "l2": "inputs (~400 MB) and per-window scratch (~0.9 GB) exceed the 126 MB L2; no explicit flush",
+            "partitioning": "by key across ranks, no collective"}
+
+
 # ------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """the reference's own CPU implementation (unmodified, compiled into oracle/_ref) on ALL host cores: one
@@ -259,7 +268,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     procs = args.ref_procs or (os.cpu_count() or 1)
-    n_warm = max(args.warmup_ref, min(args.warmup, 1))  # one untimed pass at most: a pass is seconds of CPU work
+    n_warm = args.warmup   # (a pass is ~5 s of CPU work on every core)
     for _ in range(n_warm):
         ref_all_cores(args.ref_pages, procs)
     runs = [ref_all_cores(args.ref_pages, procs) for _ in range(args.steps)]
@@ -270,8 +279,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2: {args.pages} synthetic HTML-like pages x <=60KB, URL keys, batched setitem (reference timed on a "
-                                   f"bounded sample: {procs} instances x {args.ref_pages} pages per step)"},
+            "config": workload_config(args),
+            "results": {"sample": f"the reference is timed on a bounded sample of the workload: {procs} instances x "
+                                  f"{args.ref_pages} pages of its generator per step"},
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if args.mode == "all" and not args.no_read_side:
@@ -448,9 +458,8 @@ def bench_setitem(args, env):
         "metric": METRIC, "value": total_raw * args.steps / (dev_ms / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"C2: {args.pages} synthetic HTML-like pages x <=60KB (bytes 33..126), URL keys, batched setitem, per GPU",
-                   "raw_bytes_per_gpu": raw, "records_per_gpu": n, "window_policy": args.window,
-                   "windows_per_step": chunks_per_step, "stored_over_raw": ratio,
+        "config": workload_config(args),
+        "results": {"raw_bytes_per_gpu": raw, "windows_per_step": chunks_per_step, "stored_over_raw": ratio,
                    "stored_over_raw_strict251": strict_ratio,
                    "stored_over_raw_reference_full_corpus": reference_full_corpus_ratio(args.pages) if rank == 0 else None,
                    "ratio_note": "default mode writes a run of exactly 251 bytes in the 8-byte form (+2 B per such run; the "
@@ -459,9 +468,7 @@ def bench_setitem(args, env):
                                  "(tests/golden/c2_full_enc_len.npz)",
                    "steps_note": "every step re-inserts the same keys: after the first pass each record takes the index's "
                                  "REPLACE path and tombstones its previous copy; nothing is reclaimed between steps (the "
-                                 f"store grows by ~{(st1.encoded_bytes - st0.encoded_bytes) / max(args.steps, 1) / 1e6:.0f} MB per step)",
-                   "l2": "inputs (~400 MB) and per-window scratch (~0.9 GB) exceed the 126 MB L2; no explicit flush",
-                   "partitioning": "by key across ranks, no collective"},
+                                 f"store grows by ~{(st1.encoded_bytes - st0.encoded_bytes) / max(args.steps, 1) / 1e6:.0f} MB per step)"},
         "wall_ms_per_step": dev_wall_ms / args.steps,
         "e2e": {"value": total_raw * args.steps / (e2e_ms / 1e3) / 1e6, "unit": UNIT,
                 "h2d_bytes_per_step": int(kd.nbytes + ko.nbytes + vd.nbytes + vo.nbytes), "d2h_bytes_per_step": int(8 * n),
@@ -814,7 +821,6 @@ def main():
     ap.add_argument("--ref-records", type=int, default=12000, help="CPU getitem leg: C3 records per instance")
     ap.add_argument("--ref-keys", type=int, default=30000, help="CPU contains leg: C4 keys per instance")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference instances run side by side (0 = one per host core)")
-    ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-read-side", action="store_true", help="mode all: skip the getitem_c3 / lookup_c4 sub-records")
     ap.add_argument("--mode", default="all", choices=["all", "setitem", "partition", "shard", "getitem", "lookup"],

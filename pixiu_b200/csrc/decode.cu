@@ -4,7 +4,9 @@
 // record from its first byte for every back reference and bubbles each byte through one coroutine per nesting
 // level, by TWO kernels over a flat *decoded arena* (the records of every touched chunk, back to back,
 // u32-addressed), one warp per 2 KiB decode tile (tile descriptors make every tile independently parsable):
-//   K10 k_decode_literals  no dependencies, pure throughput.  The 251-dispatch of PiXiuStr.h:142-160 runs in parallel
+//   K10 k_decode_literals  no dependencies, pure throughput.  A tile's encoded bytes are staged in shared memory by one
+//                          bulk-async copy (cp.async.bulk onto a per-warp mbarrier).  The 251-dispatch of
+//                          PiXiuStr.h:142-160 runs in parallel
 //                          over the staged encoded bytes (bitmap of the 251s, one lane per token cluster), a scan of
 //                          (decoded - encoded) token bytes places every reference token, and the tile is then written
 //                          ONCE, each lane assembling a 64-byte strip of output words straight from the staged bytes:
@@ -462,7 +464,7 @@ __device__ __noinline__ uint32_t drain_pending(CopySmem &S, PubCtx P, uint32_t B
 
 
 // K10: one warp per 2 KiB tile of decoded output; no waiting anywhere.
-//   1. stage the tile's encoded bytes in shared memory (16-byte loads)
+//   1. stage the tile's encoded bytes in shared memory (one bulk-async copy per tile, completion on the warp's mbarrier)
 //   2. bitmap of the 251s; a 251 with no 251 among the 7 bytes before it surely starts a token: these cluster starts
 //      are listed, and one lane per cluster walks its tokens (PiXiuStr.h:142-160 dispatch) and counts / lists the
 //      reference heads (a cluster is almost always a single token)

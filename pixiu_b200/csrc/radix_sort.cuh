@@ -113,6 +113,11 @@ k_rs_onesweep(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, con
         __syncwarp();
         off[k] = (uint16_t) (c + __popc(m & lt_mask));
     }
+    // the values are pulled into L2 while the digits are scanned and the look-back runs (no register held for them)
+    if (vals_in && lane < RS_ITEMS) {
+        uint32_t i = wbase + lane * 32;
+        if (i < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals_in + i));
+    }
     __syncthreads();
     // digit `t` (threads 0..255): exclusive prefix over the warps, tile total, tile-local digit start,
     // decoupled look-back.  The other threads only take part in the barriers.
