@@ -368,6 +368,12 @@ def bench_setitem(args, env):
     policy = {"reference": ctrl.ROTATE_REFERENCE, "bytes": ctrl.ROTATE_BYTES, "records": ctrl.ROTATE_RECORDS}[args.window]
     c = ctrl.PiXiuCtrl(device=env.local_rank, rotate_policy=policy, window_bytes=args.window_bytes)
     ext = env.ext_stream(c)
+    # The store grows by ~0.82 x raw per step.  The compressed arena maps HBM ahead of use on a helper thread (on a freshly
+    # booted box one cuMemCreate / cuMemSetAccess of 256 MiB was measured at 20 - 200 ms, profiles/README.md), so the steps
+    # do not wait for it; --reserve additionally passes the run's size as a capacity hint (pixiu_reserve)
+    if args.reserve:
+        passes = 2 * args.steps + args.warmup + min(args.warmup, 1) + 2
+        c.reserve(int(0.86 * raw * passes) + (512 << 20))
 
     def step_dev():
         c.rotate()
@@ -822,6 +828,7 @@ def main():
     ap.add_argument("--ref-keys", type=int, default=30000, help="CPU contains leg: C4 keys per instance")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference instances run side by side (0 = one per host core)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reserve", action="store_true", help="pass the size of the run as a capacity hint (pixiu_reserve) before the steps")
     ap.add_argument("--no-read-side", action="store_true", help="mode all: skip the getitem_c3 / lookup_c4 sub-records")
     ap.add_argument("--mode", default="all", choices=["all", "setitem", "partition", "shard", "getitem", "lookup"],
                     help="all: headline setitem line + getitem_c3 / lookup_c4 (and, N > 1, sharded) sub-records; "

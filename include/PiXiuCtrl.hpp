@@ -150,6 +150,9 @@ struct PiXiuCtrl {
         return g;
     }
 
+    // capacity hint (std::vector::reserve): map room for this many more compressed bytes now, not inside a batch
+    int reserve(int64_t encoded_bytes) { return pixiu_reserve(store, encoded_bytes); }
+
     // encoded length of the record stored last - what the reference's REPL reads through
     // `ctrl.st.cbt_chunk->getitem(ctrl.st.local_chunk.used_num - 1)->len` to print the bytes saved (main.cpp:67)
     int last_encoded_len(void) {

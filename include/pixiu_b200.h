@@ -199,6 +199,13 @@ void *pixiu_stream(pixiu_store *s);
 /* force the open window to close (next setitem starts a new chunk) */
 int pixiu_rotate(pixiu_store *s);
 
+/* Capacity hint (the std::vector::reserve of the store; the reference's MemPool mallocs 64 KiB blocks as it goes,
+ * common/MemPool.cpp): make room NOW for `encoded_bytes` more bytes of compressed records.  The compressed arena is a
+ * reserved virtual range; physical HBM is mapped behind it in 256 MiB steps when a batch needs it, and on a freshly
+ * booted GPU a single cuMemCreate / cuMemSetAccess was measured at up to 75 ms (memory not scrubbed yet) - an ingest
+ * that knows its size pays that here instead of inside a batch.  Never needed for correctness. */
+int pixiu_reserve(pixiu_store *s, int64_t encoded_bytes);
+
 #ifdef __cplusplus
 }
 #endif

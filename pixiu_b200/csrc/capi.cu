@@ -697,6 +697,14 @@ int pixiu_rotate(pixiu_store *h) {
     }, G_PLAIN);
 }
 
+int pixiu_reserve(pixiu_store *h, int64_t encoded_bytes) {
+    return guarded(h, [&](Store &S) -> int {
+        if (encoded_bytes < 0) return PIXIU_EINVAL;
+        S.d_enc.ensure(S.enc_bytes + (uint64_t) encoded_bytes + 4096);
+        return PIXIU_OK;
+    }, G_READ);
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------

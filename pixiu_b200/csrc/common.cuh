@@ -1,10 +1,15 @@
 // Common host/device helpers for the pixiu_b200 CUDA library (sm_100a only).
 #pragma once
+#include <chrono>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -66,6 +71,7 @@ struct DevBuf {
         size_t want = std::max<size_t>(2 * cap, n + n / 2 + 256);
         T *q = nullptr;
         if (trace_on()) fprintf(stderr, "[mem] grow %zu -> %zu bytes (keep %zu)\n", cap * sizeof(T), want * sizeof(T), keep * sizeof(T));
+        const auto t0 = std::chrono::steady_clock::now();
         PX_CUDA(cudaMalloc(&q, want * sizeof(T)));
         if (p && keep) PX_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
         if (p) {
@@ -74,6 +80,7 @@ struct DevBuf {
         }
         p = q;
         cap = want;
+        if (trace_on()) fprintf(stderr, "[mem] grow took %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     }
 };
 
@@ -113,10 +120,20 @@ struct VmArena {
         }
     } drv;
     CUdeviceptr base = 0;
-    size_t reserved = 0, mapped = 0, gran = 0;
+    size_t reserved = 0, gran = 0;
+    std::atomic<size_t> mapped{0};       // bytes usable; only ever grows, published by whoever mapped them
     int device = 0;
-    std::vector<CUmemGenericAllocationHandle> handles;
+    std::vector<CUmemGenericAllocationHandle> handles;   // (guarded by mu)
     static constexpr size_t STEP = 256ull << 20;
+    // Growth runs AHEAD of use on a helper thread: on a freshly booted GPU one cuMemCreate / cuMemSetAccess of 256 MiB
+    // was measured at 20 - 200 ms (profiles/README.md) while kernel launches and stream synchronisation of another
+    // thread go on undisturbed, so the ingest path only ever finds the memory already there.
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::thread helper;
+    size_t target = 0;                   // the helper maps until mapped >= target (guarded by mu)
+    bool stop = false, helper_on = false;
+    std::string helper_err;              // first failure of the helper (guarded by mu)
     VmArena() = default;
     VmArena(const VmArena &) = delete;
     VmArena &operator=(const VmArena &) = delete;
@@ -139,26 +156,84 @@ struct VmArena {
         reserved = (reserve_bytes + STEP - 1) / STEP * STEP;
         check(drv.Reserve(&base, reserved, 0, 0, 0), "cuMemAddressReserve");
     }
-    // make bytes [0, n) usable
-    void ensure(size_t n) {
-        if (n <= mapped) return;
-        if (n > reserved) throw std::runtime_error("VmArena: reserved range exhausted");
+    // maps the next 256 MiB behind the range (one caller at a time: the helper, or ensure() while the helper is idle)
+    void map_step() {
         CUmemAllocationProp p = prop();
         CUmemAccessDesc acc = {};
         acc.location = p.location;
         acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-        while (mapped < n) {
-            CUmemGenericAllocationHandle h;
-            check(drv.Create(&h, STEP, &p, 0), "cuMemCreate");
-            check(drv.Map(base + mapped, STEP, 0, h, 0), "cuMemMap");
-            check(drv.SetAccess(base + mapped, STEP, &acc, 1), "cuMemSetAccess");
+        const size_t at = mapped.load(std::memory_order_relaxed);
+        CUmemGenericAllocationHandle h;
+        const auto t0 = std::chrono::steady_clock::now();
+        check(drv.Create(&h, STEP, &p, 0), "cuMemCreate");
+        const auto t1 = std::chrono::steady_clock::now();
+        CUresult r = drv.Map(base + at, STEP, 0, h, 0);
+        if (r == CUDA_SUCCESS) r = drv.SetAccess(base + at, STEP, &acc, 1);
+        if (r != CUDA_SUCCESS) {
+            drv.Release(h);
+            check(r, "cuMemMap / cuMemSetAccess");
+        }
+        const auto t2 = std::chrono::steady_clock::now();
+        {
+            std::lock_guard<std::mutex> g(mu);
             handles.push_back(h);
-            mapped += STEP;
+        }
+        mapped.store(at + STEP, std::memory_order_release);
+        if (trace_on())
+            fprintf(stderr, "[mem] arena mapped %zu MiB: create %.3f map+access %.3f ms\n", (at + STEP) >> 20,
+                    std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+    }
+    void helper_loop() {
+        cudaSetDevice(device);
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || (helper_err.empty() && mapped.load() < target); });
+            if (stop) return;
+            lk.unlock();
+            std::string e;
+            try {
+                map_step();
+            } catch (const std::exception &ex) {
+                e = ex.what();
+            }
+            lk.lock();
+            if (!e.empty()) helper_err = e;
+            cv_done.notify_all();
         }
     }
+    // make bytes [0, n) usable now, and ask for room ahead of them (a quarter of n, 256 MiB .. 4 GiB) in the background
+    void ensure(size_t n) {
+        if (n > reserved) throw std::runtime_error("VmArena: reserved range exhausted");
+        size_t ahead = 0;
+        if (n > STEP / 2) ahead = std::min<size_t>(std::max<size_t>(n / 4, STEP), 16 * STEP);   // (small stores never start the helper)
+        const size_t want = std::min(reserved, (n + ahead + STEP - 1) / STEP * STEP);
+        if (want <= mapped.load(std::memory_order_acquire)) return;
+        std::unique_lock<std::mutex> lk(mu);
+        if (!helper_on && ahead == 0) {   // first steps of a small store: inline
+            lk.unlock();
+            while (mapped.load() < n) map_step();
+            return;
+        }
+        if (!helper_on) {
+            helper = std::thread([this] { helper_loop(); });
+            helper_on = true;
+        }
+        if (want > target) target = want;
+        cv_work.notify_one();
+        cv_done.wait(lk, [&] { return mapped.load() >= n || !helper_err.empty(); });
+        if (mapped.load() < n) throw std::runtime_error("VmArena: " + helper_err);
+    }
     ~VmArena() {
+        if (helper_on) {
+            {
+                std::lock_guard<std::mutex> g(mu);
+                stop = true;
+            }
+            cv_work.notify_all();
+            helper.join();
+        }
         if (!base) return;
-        if (mapped) drv.Unmap(base, mapped);
+        if (mapped.load()) drv.Unmap(base, mapped.load());
         for (auto h : handles) drv.Release(h);
         drv.AddressFree(base, reserved);
     }

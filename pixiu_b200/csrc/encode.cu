@@ -1026,9 +1026,11 @@ uint32_t Store::count_nodes_and_cut(uint32_t first_new, uint32_t s0, uint32_t N)
     }
     if (knobs.trace) {
         auto t_c = std::chrono::steady_clock::now();
-        fprintf(stderr, "[rot] cand=%u accepted=%u nth=%u wait+d2h=%.3f ms replay=%.3f ms rho=%.3f\n", win_R - first_new, accepted,
+        static const auto t_origin = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rot] cand=%u accepted=%u nth=%u wait+d2h=%.3f ms replay=%.3f ms rho=%.3f at=%.3f ms\n", win_R - first_new, accepted,
                 pool_nth, std::chrono::duration<double, std::milli>(t_b - t_a).count(),
-                std::chrono::duration<double, std::milli>(t_c - t_b).count(), rho);
+                std::chrono::duration<double, std::milli>(t_c - t_b).count(), rho,
+                std::chrono::duration<double, std::milli>(t_c - t_origin).count());
     }
     // running estimate of nodes per byte (drives the next candidate selection only; the cut is exact)
     uint32_t bytes = h_win_rec_start[first_new + accepted] - s0;

@@ -56,7 +56,7 @@ EXPORTS = [
     "pixiu_default_config", "pixiu_create", "pixiu_destroy", "pixiu_last_error", "pixiu_get_stats",
     "pixiu_setitem_batch", "pixiu_setitem_batch_dev", "pixiu_contains_batch", "pixiu_contains_batch_dev", "pixiu_delitem_batch",
     "pixiu_getitem_batch", "pixiu_getitem_batch_dev", "pixiu_iter", "pixiu_encoded_view",
-    "pixiu_record_location", "pixiu_import_chunk", "pixiu_decode_chunk", "pixiu_rotate",
+    "pixiu_record_location", "pixiu_import_chunk", "pixiu_decode_chunk", "pixiu_rotate", "pixiu_reserve",
     "pixiu_profile_enable", "pixiu_profile_get", "pixiu_stream",
     "pixiu_reinsert_chunk", "pixiu_chunk_info",
     "pixiu_export_chunk", "pixiu_mg_config", "pixiu_mg_setitem_begin", "pixiu_mg_setitem_mid", "pixiu_mg_setitem_end",
@@ -109,6 +109,7 @@ def load_library():
     L.pixiu_import_chunk.restype = C.c_int64
     L.pixiu_decode_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, _i64p]
     L.pixiu_rotate.argtypes = [C.c_void_p]
+    L.pixiu_reserve.argtypes = [C.c_void_p, C.c_int64]
     L.pixiu_reinsert_chunk.argtypes = [C.c_void_p, C.c_int64]
     L.pixiu_reinsert_chunk.restype = C.c_int64
     L.pixiu_chunk_info.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p, _i32p]
@@ -526,6 +527,10 @@ class PiXiuCtrl:
 
     def rotate(self):
         self._check(self._L.pixiu_rotate(self._h))
+
+    def reserve(self, encoded_bytes: int):
+        """capacity hint: map room for `encoded_bytes` more compressed bytes now instead of inside the batches"""
+        self._check(self._L.pixiu_reserve(self._h, int(encoded_bytes)))
 
     def debug_set_knob(self, name: str, value: int):
         """tuning / test knob of a live store (Knobs::set in csrc/store.h)"""

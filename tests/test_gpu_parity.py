@@ -520,6 +520,15 @@ def test_api_edge_cases(ctrl_mod):
     rc, _ = c.setitem_batch([b"ab"], [b"1"])  # re-insert after delete: a new key again
     assert rc.tolist() == [0]
     assert c.stats().live_records == len(c.iter_docs(b""))
+    # capacity hint: maps room in the compressed arena, changes nothing that can be observed
+    before = [c.getitem(k).bytes() for k in (b"k", b"a", b"ab")]
+    c.reserve(300 << 20)
+    c.reserve(0)
+    with pytest.raises(ctrl_mod.PiXiuError):
+        c.reserve(-1)
+    rc, _ = c.setitem_batch([b"after-reserve"], [b"v" * 100])
+    assert rc.tolist() == [0] and [c.getitem(k).bytes() for k in (b"k", b"a", b"ab")] == before
+    assert ctrl_mod.split_doc(c.getitem(b"after-reserve").bytes()) == (b"after-reserve", b"v" * 100)
     c.free_prop()
 
 
