@@ -53,11 +53,10 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region, through NVML in a thread at 2 Hz.
-    Sampling is not free for a launch-heavy step (measured on this pool, scratch/nvml_cost.py: spawning
-    `nvidia-smi -lms 100` next to the run halves the throughput, NVML clock+reasons at 20 Hz costs 45 %,
-    at 4 Hz 14 %, one query kind at 4 Hz nothing measurable), so the rate is kept low and the two queries
-    alternate."""
+    """SM clock / throttle reasons DURING the timed region, through NVML in a thread at 2 Hz, the two queries
+    alternating.  (Round 1 measured large costs for faster sampling; those runs were confounded by the arena's mapping
+    stalls - profiles/README.md - and `nvidia-smi -lms 250` next to the run now costs nothing measurable.  The rate stays
+    low anyway: the step is a few thousand launches with a host synchronisation every half millisecond.)"""
 
     def __init__(self, index, first_delay=0.1, period=0.5):
         self.index = index
@@ -390,8 +389,7 @@ def bench_setitem(args, env):
 
     for _ in range(args.warmup):
         step_dev()
-    # NVML queries take a driver-wide lock: with one sampler per rank the ranks of a launch-bound step slow each other
-    # down, so only rank 0 (whose line is printed) samples its GPU
+    # only rank 0 (whose line is printed) samples its GPU
     sampler = ClockSampler(env.local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
