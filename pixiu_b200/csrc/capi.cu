@@ -779,7 +779,16 @@ int64_t pixiu_debug_window_array(pixiu_store *h, const char *name, void *out, in
     size_t esz = 4;
     if (nm == "sa") src = S.es.sa.p;
     else if (nm == "rank") src = S.es.rank.p;
-    else if (nm == "lcp") src = S.es.lcp.p;
+    else if (nm == "lcp") {
+        if (S.es.tree.leaf) {   // the lcp halves of the interleaved {sa, lcp} leaves
+            if ((int64_t) ((size_t) S.win_N * 4) > cap_bytes) return PIXIU_ENOSPC;
+            cudaSetDevice(S.cfg.device);
+            if (cudaMemcpy2D(out, 4, reinterpret_cast<const char *>(S.es.tree.leaf) + 4, 8, 4, S.win_N, cudaMemcpyDeviceToHost) != cudaSuccess)
+                return PIXIU_ECUDA;
+            return (int64_t) S.win_N;
+        }
+        src = S.es.lcp.p;
+    }
     else if (nm == "reach") src = S.es.reach.p;
     else if (nm == "off") src = S.es.off.p;
     else if (nm == "prevp") src = S.es.prevp.p;

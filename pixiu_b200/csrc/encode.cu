@@ -323,12 +323,13 @@ constexpr uint32_t LCP_CAP = 64;
 
 __global__ void __launch_bounds__(256)
 k_lcp_sa(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const uint32_t *__restrict__ sa, uint32_t n,
-         uint32_t *__restrict__ lcp, uint32_t *__restrict__ longmap) {
+         uint2 *__restrict__ leaf, uint32_t *__restrict__ longmap) {
     const uint32_t r = blockIdx.x * 256 + threadIdx.x;
     if (r >= n) return;
     uint32_t h = 0;
+    const uint32_t a = __ldcs(sa + r);
     if (r > 0) {
-        const uint32_t a = __ldcs(sa + r), b = __ldcs(sa + r - 1);
+        const uint32_t b = __ldcs(sa + r - 1);
         const uint32_t lim = min((uint32_t) dist[a], (uint32_t) dist[b]);
         const uint32_t stop = min(lim, LCP_CAP);
         bool diff = false;
@@ -347,12 +348,12 @@ k_lcp_sa(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, co
             atomicOr(longmap + (a >> 5), 1u << (a & 31));
         }
     }
-    __stcs(lcp + r, h);
+    leaf[r] = make_uint2(a, h);   // the leaf level of the block-min trees: {sa, lcp} side by side
 }
 
 __global__ void __launch_bounds__(128)
 k_lcp_long(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const uint32_t *__restrict__ sa,
-           const uint32_t *__restrict__ rank, const uint32_t *__restrict__ longmap, uint32_t n, uint32_t *__restrict__ lcp) {
+           const uint32_t *__restrict__ rank, const uint32_t *__restrict__ longmap, uint32_t n, uint2 *__restrict__ leaf) {
     // one thread per 32 text positions (one word of the bitmap); words without a long match cost one load
     const uint32_t w = blockIdx.x * 128 + threadIdx.x;
     if ((uint64_t) w * 32 >= n) return;
@@ -377,7 +378,7 @@ k_lcp_long(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, 
             h += 8;
         }
         if (h > lim) h = lim;
-        lcp[r] = h;
+        leaf[r].y = h;
         prev = i;
     }
 }
@@ -410,30 +411,39 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
         uint32_t best = 0;
         const uint32_t d = dist[s];
         if (d != 0) {
-            const uint32_t *A = T.a[0], *L = T.l[0];
+            // level 0 of the trees: {sa, lcp} interleaved, or the two arrays (knob lcp_kasai)
+            const uint2 *LF = T.leaf;
+            const uint32_t *A0 = T.a[0], *L0 = T.l[0];
+            auto AL = [&](uint32_t j) { return LF ? LF[j] : make_uint2(A0[j], L0[j]); };
             const uint32_t r = rank[s];
             // nearest smaller text position above r: lcp = min L[j+1..r].  Most searches end within a few
             // entries: a plain scan of up to LPF_FAST neighbours first, the block-min tree only for the rest
             constexpr int LPF_FAST = 12;
-            uint32_t l1 = L[r];
+            uint32_t l1 = AL(r).y;
+            uint32_t a_jl = 0;   // sa[jl]
             int64_t jl = -1;
             if (l1) {
                 uint32_t pos = r;
                 bool open = true;
                 for (int k = 0; k < LPF_FAST && pos > 0; k++) {
                     pos--;
-                    if (A[pos] < s) {
+                    const uint2 e = AL(pos);
+                    if (e.x < s) {
                         jl = pos;
+                        a_jl = e.x;
                         open = false;
                         break;
                     }
-                    l1 = min(l1, L[pos]);
+                    l1 = min(l1, e.y);
                     if (l1 == 0) {
                         open = false;
                         break;
                     }
                 }
-                if (open) jl = pos > 0 ? tree_search<true, false, true>(T, pos, s, l1, 0) : -1;
+                if (open) {
+                    jl = pos > 0 ? tree_search<true, false, true>(T, pos, s, l1, 0) : -1;
+                    if (NODES && jl >= 0) a_jl = AL((uint32_t) jl).x;
+                }
             }
             if (jl < 0) l1 = 0;
             // nearest smaller text position below r: lcp = min L[r+1..j]; ties with l1 matter for NODES
@@ -445,8 +455,9 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
                 bool open = true;
                 for (int k = 0; k < LPF_FAST && pos + 1 < n; k++) {
                     pos++;
-                    l2 = min(l2, L[pos]);
-                    if (A[pos] < s) {
+                    const uint2 e = AL(pos);
+                    l2 = min(l2, e.y);
+                    if (e.x < s) {
                         jr = pos;
                         open = false;
                         break;
@@ -464,7 +475,7 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
                 const uint32_t M = best;
                 leaf = M < d;
                 if (leaf && M > 0) {
-                    bool up = l1 == M && dist[A[jl]] > M;  // a continuing earlier occurrence above
+                    bool up = l1 == M && dist[a_jl] > M;   // a continuing earlier occurrence above
                     bool dn = l2 == M;                      // ... below (never terminal)
                     bool is_explicit = (up && dn) || (!up && !dn);  // two next bytes | only ex-leaf occurrences
                     if (!is_explicit) {
@@ -473,10 +484,10 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
                         if (up) {
                             uint32_t a2 = 0xFFFFFFFFu;
                             int64_t x1 = tree_search<true, true, false>(T, (uint32_t) jl + 1, M + 1, a2, -1);
-                            uint32_t acc2 = L[x1];
+                            uint32_t acc2 = AL((uint32_t) x1).y;
                             if (acc2 >= M) {
                                 int64_t j2 = tree_search<true, false, true>(T, (uint32_t) x1, s, acc2, (int64_t) M - 1);
-                                if (j2 >= 0 && acc2 >= M && dist[A[j2]] > M) is_explicit = true;
+                                if (j2 >= 0 && acc2 >= M && dist[AL((uint32_t) j2).x] > M) is_explicit = true;
                             }
                         } else {
                             uint32_t a2 = 0xFFFFFFFFu;
@@ -1056,21 +1067,23 @@ void Store::enc_phase_a(uint32_t first_new) {
     build_suffix_array(*this, N);
 
     // ---- LCP + trees ----
-    E.lcp.reserve_discard(N);
     prof.begin(PC_LCP, st);
-    if (knobs.lcp_kasai) {  // (knob: the one-pass Kasai walk, for A/B measurements)
+    MinTree T{};
+    if (knobs.lcp_kasai) {  // (knob: the one-pass Kasai walk into a plain lcp array, for A/B measurements)
+        E.lcp.reserve_discard(N);
         k_lcp<<<div_up<uint32_t>(div_up<uint32_t>(N, LCP_SEG), 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, N, E.lcp.p);
         L++;
     } else {
         const uint32_t words = div_up<uint32_t>(N, 32);
         E.longmap.reserve_discard(words + 1);
+        E.leaf.reserve_discard(N);
         PX_CUDA(cudaMemsetAsync(E.longmap.p, 0, (size_t) words * sizeof(uint32_t), st));
-        k_lcp_sa<<<div_up<uint32_t>(N, 256), 256, 0, st>>>(w_text.p, w_dist.p, E.sa.p, N, E.lcp.p, E.longmap.p);
-        k_lcp_long<<<div_up<uint32_t>(words, 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, E.longmap.p, N, E.lcp.p);
+        k_lcp_sa<<<div_up<uint32_t>(N, 256), 256, 0, st>>>(w_text.p, w_dist.p, E.sa.p, N, E.leaf.p, E.longmap.p);
+        k_lcp_long<<<div_up<uint32_t>(words, 128), 128, 0, st>>>(w_text.p, w_dist.p, E.sa.p, E.rank.p, E.longmap.p, N, E.leaf.p);
         L += 2;
+        T.leaf = E.leaf.p;
     }
-    prof.end(st, 16.0 * N, 2);
-    MinTree T{};
+    prof.end(st, 20.0 * N, 2);
     {
         size_t total = 0;
         uint32_t sz = N;
@@ -1084,15 +1097,18 @@ void Store::enc_phase_a(uint32_t first_new) {
         E.tree_l.reserve_discard(total + 1);
         prof.begin(PC_TREE, st);
         T.a[0] = E.sa.p;
-        T.l[0] = E.lcp.p;
+        T.l[0] = T.leaf ? nullptr : E.lcp.p;
         T.size[0] = N;
         T.nlev = 1;
         sz = N;
         size_t o = 0;
         while (sz > 1 && T.nlev < TREE_MAX_LEVELS) {
             uint32_t so = div_up<uint32_t>(sz, TREE_B);
-            k_tree_level<<<div_up<uint32_t>(so, 256), 256, 0, st>>>(T.a[T.nlev - 1], T.l[T.nlev - 1], sz,
-                                                                     E.tree_a.p + o, E.tree_l.p + o, so);
+            if (T.nlev == 1 && T.leaf)
+                k_tree_level_leaf<<<div_up<uint32_t>(so, 256), 256, 0, st>>>(T.leaf, sz, E.tree_a.p + o, E.tree_l.p + o, so);
+            else
+                k_tree_level<<<div_up<uint32_t>(so, 256), 256, 0, st>>>(T.a[T.nlev - 1], T.l[T.nlev - 1], sz,
+                                                                         E.tree_a.p + o, E.tree_l.p + o, so);
             L++;
             T.a[T.nlev] = E.tree_a.p + o;
             T.l[T.nlev] = E.tree_l.p + o;

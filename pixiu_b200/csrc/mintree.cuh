@@ -23,6 +23,23 @@ k_tree_level(const uint32_t *__restrict__ in_a, const uint32_t *__restrict__ in_
     out_l[o] = ml;
 }
 
+// first tree level from the interleaved leaves
+static __global__ void __launch_bounds__(256)
+k_tree_level_leaf(const uint2 *__restrict__ leaf, uint32_t n_in, uint32_t *__restrict__ out_a, uint32_t *__restrict__ out_l,
+                  uint32_t n_out) {
+    uint32_t o = blockIdx.x * 256 + threadIdx.x;
+    if (o >= n_out) return;
+    uint32_t b = o * TREE_B, e = min(b + TREE_B, n_in);
+    uint32_t ma = 0xFFFFFFFFu, ml = 0xFFFFFFFFu;
+    for (uint32_t j = b; j < e; j++) {
+        const uint2 x = leaf[j];
+        ma = min(ma, x.x);
+        ml = min(ml, x.y);
+    }
+    out_a[o] = ma;
+    out_l[o] = ml;
+}
+
 // Generic nearest-smaller search over the block-min tree.
 //  LEFT : visits j = start-1, start-2, ...      RIGHT: visits j = start+1, start+2, ...
 //  stops at the first visited j with KEY[j] < thr and returns it (else -1 / n).
@@ -34,6 +51,17 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
                                                int64_t floor_ /* -1: never give up */) {
     auto KEY = [&](int lv, uint32_t j) { return KEYA ? T.a[lv][j] : T.l[lv][j]; };
     auto ACC = [&](int lv, uint32_t j) { return KEYA ? T.l[lv][j] : T.a[lv][j]; };
+    // level 0: key and accumulated value of one entry (one 8-byte load when the leaves are interleaved)
+    auto LEAF = [&](uint32_t j, uint32_t &k, uint32_t &a) {
+        if (T.leaf) {
+            const uint2 x = T.leaf[j];
+            k = KEYA ? x.x : x.y;
+            a = KEYA ? x.y : x.x;
+        } else {
+            k = KEY(0, j);
+            a = ACC(0, j);
+        }
+    };
     int lv = 0;
     int64_t pos = start;  // in units of level lv; entries beyond pos (in walk direction) are unvisited
     const int64_t NOTFOUND = LEFT ? -1 : (int64_t) T.size[0];
@@ -44,12 +72,14 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
         if (LEFT) {
             while (pos % TREE_B != 0) {
                 pos--;
-                uint32_t k = KEY(lv, (uint32_t) pos);
                 if (lv == 0) {
-                    if (INCL) acc = min(acc, ACC(0, (uint32_t) pos));
+                    uint32_t k, a;
+                    LEAF((uint32_t) pos, k, a);
+                    if (INCL) acc = min(acc, a);
                     if (k < thr) return pos;
-                    if (!INCL) acc = min(acc, ACC(0, (uint32_t) pos));
+                    if (!INCL) acc = min(acc, a);
                 } else {
+                    uint32_t k = KEY(lv, (uint32_t) pos);
                     if (k < thr) { found = true; hit = pos; break; }
                     acc = min(acc, ACC(lv, (uint32_t) pos));
                 }
@@ -61,12 +91,14 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
         } else {
             while ((pos + 1) % TREE_B != 0 && pos + 1 < (int64_t) T.size[lv]) {
                 pos++;
-                uint32_t k = KEY(lv, (uint32_t) pos);
                 if (lv == 0) {
-                    if (INCL) acc = min(acc, ACC(0, (uint32_t) pos));
+                    uint32_t k, a;
+                    LEAF((uint32_t) pos, k, a);
+                    if (INCL) acc = min(acc, a);
                     if (k < thr) return pos;
-                    if (!INCL) acc = min(acc, ACC(0, (uint32_t) pos));
+                    if (!INCL) acc = min(acc, a);
                 } else {
+                    uint32_t k = KEY(lv, (uint32_t) pos);
                     if (k < thr) { found = true; hit = pos; break; }
                     acc = min(acc, ACC(lv, (uint32_t) pos));
                 }
@@ -86,12 +118,14 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
         bool found = false;
         if (LEFT) {
             for (int64_t c = e - 1; c >= b; c--) {
-                uint32_t k = KEY(lv, (uint32_t) c);
                 if (lv == 0) {
-                    if (INCL) acc = min(acc, ACC(0, (uint32_t) c));
+                    uint32_t k, a;
+                    LEAF((uint32_t) c, k, a);
+                    if (INCL) acc = min(acc, a);
                     if (k < thr) return c;
-                    if (!INCL) acc = min(acc, ACC(0, (uint32_t) c));
+                    if (!INCL) acc = min(acc, a);
                 } else {
+                    uint32_t k = KEY(lv, (uint32_t) c);
                     if (k < thr) { hit = c; found = true; break; }
                     acc = min(acc, ACC(lv, (uint32_t) c));
                 }
@@ -99,12 +133,14 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
             }
         } else {
             for (int64_t c = b; c < e; c++) {
-                uint32_t k = KEY(lv, (uint32_t) c);
                 if (lv == 0) {
-                    if (INCL) acc = min(acc, ACC(0, (uint32_t) c));
+                    uint32_t k, a;
+                    LEAF((uint32_t) c, k, a);
+                    if (INCL) acc = min(acc, a);
                     if (k < thr) return c;
-                    if (!INCL) acc = min(acc, ACC(0, (uint32_t) c));
+                    if (!INCL) acc = min(acc, a);
                 } else {
+                    uint32_t k = KEY(lv, (uint32_t) c);
                     if (k < thr) { hit = c; found = true; break; }
                     acc = min(acc, ACC(lv, (uint32_t) c));
                 }

@@ -41,6 +41,9 @@ struct MinTree {
     const uint32_t *l[TREE_MAX_LEVELS];   // block minima of the LCP array   (level 0 = lcp)
     uint32_t size[TREE_MAX_LEVELS];
     int nlev;
+    // level 0 interleaved, {sa[j], lcp[j]} in one 8-byte entry: a neighbour probe of the match finder touches ONE
+    // 32-byte sector where the two arrays cost two (nullptr: level 0 is read from a[0] / l[0])
+    const uint2 *leaf;
 };
 
 class HostIndex;  // CritBit (index.cu)
@@ -51,6 +54,7 @@ struct EncodeScratch {
     DevBuf<uint64_t> keys0, keys1;
     DevBuf<uint32_t> vals0, vals1, slot0, slot1, gk, sa, rank, lcp, reach, lastnon, prevp, nextp, off;
     DevBuf<uint64_t> qoff;
+    DevBuf<uint2> leaf;   // {sa, lcp} per suffix-array slot (MinTree::leaf)
     DevBuf<uint32_t> goff, glarge, key2;  // segmented group sort: group offsets, list of big groups, rank[i+h]
     ScanWorkspace scanws;
     DevBuf<uint32_t> tree_a, tree_l;
