@@ -493,8 +493,17 @@ NCU_TRAFFIC_OVER_ALGORITHMIC = {
     # k_rs_onesweep: 150.06 MB read + 100.93 MB written per launch of 12 M keys vs n x 24 B (L2 absorbs part of the scatter)
     "sort_pass": ((150.06e6 + 100.93e6) / (12e6 * 24), "profiles/r01_onesweep_12Mkeys_ncu_raw.csv"),
 }
-NCU_DECODE_TRAFFIC = {  # filled from this round's captures of the decode kernel (see profiles/README.md)
-    "c2": None, "c3": None,
+NCU_DECODE_TRAFFIC = {
+    # k_decode_literals + k_decode_copies, dram__bytes_read.sum + dram__bytes_write.sum of one decode call over its
+    # algorithmic bytes.  c2: 3,000 pages, (92.0 + 83.4) + (142.8 + 69.3) MB for 196.5 MB; c3: 400,000 records,
+    # (71.0 + 409.6) + (332.7 + 360.3) MB for 422.8 MB (the literals kernel writes every byte once - reference bytes as
+    # zero - the copy kernel writes the reference bytes again and reads their sources and the 8-byte pieces)
+    "c2": ((92.02 + 83.41 + 142.78 + 69.25) / 196.5,
+           "profiles/r02_decode_c2_3000pages_ncu_raw.csv (ratio of a committed ncu capture x this run's algorithmic bytes; "
+           "not measured in this run)"),
+    "c3": ((70.96 + 409.62 + 332.74 + 360.32) / 422.8,
+           "profiles/r02_decode_c3_400krecords_ncu_raw.csv (ratio of a committed ncu capture x this run's algorithmic bytes; "
+           "not measured in this run)"),
 }
 
 
@@ -565,7 +574,7 @@ def getitem_measure(args, env, c, corpus, workload, steps, cpu):
                     "h2d_bytes_per_step": int(kd.nbytes + ko.nbytes), "d2h_bytes_per_step": int(off[-1]) + 9 * n,
                     "ms_per_step": e2e_ms / steps, "wall_ms_per_step": e2e_wall / steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "decode kernels (k_decode_tiles ...)", "achieved": ach, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_decode_literals + k_decode_copies", "achieved": ach, "peak": peak,
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                          "traffic": (ncu[0] * alg) if ncu else None, "traffic_source": ncu[1] if ncu else None,
                          "algorithmic_bytes_per_launch": alg, "avg_launch_ms": pd["ms"], "launches": pd["launches"],
@@ -696,7 +705,10 @@ def bench_lookup(args, env):
                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall / args.steps},
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "kernel": "k_query_len + scan + k_query_write + k_lookup", "achieved": ach, "peak": peak,
-                        "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": 433.7 * n,
+                        "traffic_source": "profiles/r01_lookup_3Mkeys_ncu_raw.csv: k_lookup (unchanged since) read 1.287 GB and "
+                                          "wrote 14.7 MB of DRAM for 3 M queries = 433.7 B per query, x this run's queries; "
+                                          "not measured in this run",
                         "algorithmic_bytes_per_launch": alg, "avg_launch_ms": pl["ms"], "launches": pl["launches"],
                         "sector_granular_gbs": (pl["bytes"] + n * mean_depth * 32.0) / 1e9 / (pl["ms"] / 1e3),
                         "bytes_model": "2 x escaped query bytes + depth x 7 B per query (SURVEY 8d); sector-granular: depth x 32 B"},
