@@ -843,7 +843,7 @@ def main():
     ap.add_argument("--mode", default="all", choices=["all", "setitem", "partition", "shard", "getitem", "lookup"],
                     help="all: headline setitem line + getitem_c3 / lookup_c4 (and, N > 1, sharded) sub-records; "
                          "setitem (= partition): the headline alone; getitem / lookup / shard: that record as the line")
-    ap.add_argument("--batch-pages", type=int, default=256)
+    ap.add_argument("--batch-pages", type=int, default=1024)
     ap.add_argument("--shard-pages", type=int, default=3000, help="sharded mode: pages of the corpus (same on every rank)")
     ap.add_argument("--shard-window-bytes", type=int, default=64_000_000, help="sharded mode: window bytes per GPU")
     ap.add_argument("--workload", default="c3", choices=["c2", "c3"], help="--mode getitem: which corpus to decode")
