@@ -182,15 +182,24 @@ k_round_keys(uint32_t A, const uint32_t *__restrict__ vals, const uint32_t *__re
 // (bitonic network over shuffles), a CTA per larger group (bitonic in shared memory).
 // ---------------------------------------------------------------------------------
 constexpr uint32_t GS_MAX = 2048;
+constexpr uint32_t GS_WARP = 128;   // a warp sorts up to four members per lane in registers
 
-// per group: size; max size -> cnt[3]; ids of the groups with more than 32 members -> large[], count cnt[4]
+// per group: size; max size -> cnt[3]; ids of the groups with 33 .. GS_WARP members -> medium[] (count cnt[7]), with
+// GS_WARP + 1 .. GS_MAX members -> large[] (count cnt[4])
 __global__ void __launch_bounds__(256)
 k_group_stats(const uint32_t *__restrict__ cnt_in, const uint32_t *__restrict__ goff, uint32_t *__restrict__ cnt,
-              uint32_t *__restrict__ large) {
+              uint32_t *__restrict__ medium, uint32_t *__restrict__ large, uint32_t *__restrict__ huge) {
     const uint32_t G = cnt_in[1];
     const uint32_t g = blockIdx.x * 256 + threadIdx.x;
     uint32_t size = g < G ? goff[g + 1] - goff[g] : 0u;
-    if (size > 32) large[atomicAdd(&cnt[4], 1u)] = g;
+    if (size > GS_MAX) {   // no CTA can sort it: members -> cnt[5], id -> huge[], count cnt[6]
+        atomicAdd(&cnt[5], size);
+        huge[atomicAdd(&cnt[6], 1u)] = g;
+    } else if (size > GS_WARP) {
+        large[atomicAdd(&cnt[4], 1u)] = g;
+    } else if (size > 32) {
+        medium[atomicAdd(&cnt[7], 1u)] = g;
+    }
     uint32_t m = __reduce_max_sync(0xffffffffu, size);
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&cnt[3], m);
 }
@@ -228,7 +237,86 @@ k_group_sort_small(uint32_t G, const uint32_t *__restrict__ goff, const uint32_t
     }
 }
 
-// CTA per group (32 < size <= GS_MAX)
+// warp per group of 33 .. GS_WARP members: R members per lane (member i sits in lane i % 32, register i / 32), a
+// bitonic network whose exchanges at distance >= 32 stay inside the lane - no shared memory, no barrier
+template <int R>
+__device__ __forceinline__ void warp_bitonic(uint64_t (&e)[R], uint32_t lane) {
+#pragma unroll
+    for (uint32_t k = 2; k <= 32u * R; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const uint32_t jr = j >> 5;
+#pragma unroll
+                for (uint32_t r = 0; r < (uint32_t) R; r++) {
+                    if ((r & jr) == 0) {
+                        const uint32_t i = lane + 32 * r;
+                        const bool up = (i & k) == 0;
+                        const uint64_t a = e[r], b = e[r | jr];
+                        if ((a > b) == up) {
+                            e[r] = b;
+                            e[r | jr] = a;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (uint32_t r = 0; r < (uint32_t) R; r++) {
+                    const uint32_t i = lane + 32 * r;
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, e[r], j);
+                    const bool up = (i & k) == 0, lower = (lane & j) == 0;
+                    e[r] = (up == lower) ? (e[r] < o ? e[r] : o) : (e[r] > o ? e[r] : o);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_group_sort_medium(uint32_t nm, const uint32_t *__restrict__ medium, const uint32_t *__restrict__ goff,
+                    const uint32_t *__restrict__ key2, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
+                    uint32_t *__restrict__ vals_out) {
+    const uint32_t w = (blockIdx.x * 128 + threadIdx.x) >> 5;
+    if (w >= nm) return;
+    const uint32_t g = medium[w];
+    const uint32_t off = goff[g], size = goff[g + 1] - off;
+    const uint32_t lane = lane_id();
+    if (size <= 64) {
+        uint64_t e[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uint32_t i = lane + 32 * r;
+            e[r] = i < size ? ((uint64_t) key2[off + i] << 32) | vals[off + i] : ~0ull;
+        }
+        warp_bitonic<2>(e, lane);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uint32_t i = lane + 32 * r;
+            if (i < size) {
+                keys_out[off + i] = ((uint64_t) g << kb) | (e[r] >> 32);
+                vals_out[off + i] = (uint32_t) e[r];
+            }
+        }
+    } else {
+        uint64_t e[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t i = lane + 32 * r;
+            e[r] = i < size ? ((uint64_t) key2[off + i] << 32) | vals[off + i] : ~0ull;
+        }
+        warp_bitonic<4>(e, lane);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t i = lane + 32 * r;
+            if (i < size) {
+                keys_out[off + i] = ((uint64_t) g << kb) | (e[r] >> 32);
+                vals_out[off + i] = (uint32_t) e[r];
+            }
+        }
+    }
+}
+
+// CTA per group (GS_WARP < size <= GS_MAX)
 __global__ void __launch_bounds__(256)
 k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ key2,
                    const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
@@ -260,6 +348,61 @@ k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restric
         uint64_t e = sm[i];
         keys_out[off + i] = ((uint64_t) g << kb) | (e >> 32);
         vals_out[off + i] = (uint32_t) e;
+    }
+}
+
+// The few groups with more than GS_MAX members (a dozen per cent of the active suffixes after the first round, next
+// to none after the second) are gathered into compact buffers, ordered there by one radix sort on
+// (index in huge[], rank[i+h]) and written back in place, while every other group is sorted where it stands.
+// offsets of the huge groups in the compact buffers (one CTA; a few hundred groups at most per round)
+__global__ void __launch_bounds__(256)
+k_huge_offsets(uint32_t nh, const uint32_t *__restrict__ huge, const uint32_t *__restrict__ goff, uint32_t *__restrict__ hoff) {
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b < nh; b += 256) {
+        const uint32_t j = b + threadIdx.x;
+        const uint32_t g = j < nh ? huge[j] : 0u;
+        const uint32_t size = j < nh ? goff[g + 1] - goff[g] : 0u;
+        part[threadIdx.x] = size;
+        __syncthreads();
+        for (uint32_t d = 1; d < 256; d <<= 1) {
+            uint32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0u;
+            __syncthreads();
+            part[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (j < nh) hoff[j] = carry + part[threadIdx.x] - size;
+        __syncthreads();
+        if (threadIdx.x == 255) carry += part[255];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) hoff[nh] = carry;
+}
+
+__global__ void __launch_bounds__(256)
+k_huge_gather(const uint32_t *__restrict__ huge, const uint32_t *__restrict__ hoff, const uint32_t *__restrict__ goff,
+              const uint32_t *__restrict__ key2, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ ck,
+              uint32_t *__restrict__ cv) {
+    const uint32_t j = blockIdx.y, g = huge[j];
+    const uint32_t off = goff[g], size = goff[g + 1] - off, ho = hoff[j];
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < size; i += gridDim.x * 256) {
+        ck[ho + i] = ((uint64_t) j << kb) | key2[off + i];
+        cv[ho + i] = vals[off + i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_huge_scatter(const uint32_t *__restrict__ huge, const uint32_t *__restrict__ hoff, const uint32_t *__restrict__ goff,
+               const uint64_t *__restrict__ ck, const uint32_t *__restrict__ cv, int kb, uint64_t *__restrict__ keys_out,
+               uint32_t *__restrict__ vals_out) {
+    const uint32_t j = blockIdx.y, g = huge[j];
+    const uint32_t off = goff[g], size = goff[g + 1] - off, ho = hoff[j];
+    const uint64_t low = (1ull << kb) - 1;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < size; i += gridDim.x * 256) {
+        keys_out[off + i] = ((uint64_t) g << kb) | (ck[ho + i] & low);
+        vals_out[off + i] = cv[ho + i];
     }
 }
 
@@ -758,6 +901,9 @@ static void build_suffix_array(Store &S, uint32_t N) {
     PX_CUDA(cudaMemsetAsync(E.counters.p + 3, 0, 5 * sizeof(uint32_t), st));
     E.goff.reserve_discard((size_t) N / 2 + 4);
     E.glarge.reserve_discard((size_t) N / 32 + 4);
+    E.gmedium.reserve_discard((size_t) N / 32 + 4);
+    E.ghuge.reserve_discard((size_t) N / GS_MAX + 4);
+    E.hoff.reserve_discard((size_t) N / GS_MAX + 5);
     E.key2.reserve_discard(N);
     int L = 0;
 
@@ -836,21 +982,24 @@ static void build_suffix_array(Store &S, uint32_t N) {
             svals = vals_out;  // compacted values (unsorted for the next key) live here now
         }
         // group sizes: largest group and the list of groups too big for one warp
-        k_group_stats<<<div_up<uint32_t>(A / 2 + 1, 256), 256, 0, st>>>(d_cnt, E.goff.p, d_cnt, E.glarge.p);
+        k_group_stats<<<div_up<uint32_t>(A / 2 + 1, 256), 256, 0, st>>>(d_cnt, E.goff.p, d_cnt, E.gmedium.p, E.glarge.p, E.ghuge.p);
         L++;
         S.prof.end(st, 36.0 * A, 2);
-        uint32_t h_cnt[5];
+        uint32_t h_cnt[8];
         PX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         PX_CUDA(cudaStreamSynchronize(st));
         if (h_cnt[2]) throw std::runtime_error("radix sort look-back timed out");
         uint32_t An = h_cnt[0], G = h_cnt[1];
-        if (S.knobs.trace) fprintf(stderr, "[sa] N=%u sorted_by=%u active=%u groups=%u\n", N, h, An, G);
+        if (S.knobs.trace)
+            fprintf(stderr, "[sa] N=%u sorted_by=%u active=%u groups=%u largest=%u huge_groups=%u huge_members=%u\n", N, h, An, G, h_cnt[3],
+                    h_cnt[6], h_cnt[5]);
         if (An == 0) break;
         if (h > 65535u) throw std::runtime_error("suffix array: groups left after h > 65535");
-        const uint32_t gmax = h_cnt[3], nlarge = h_cnt[4];
-        PX_CUDA(cudaMemsetAsync(d_cnt + 3, 0, 2 * sizeof(uint32_t), st));
-        if (gmax <= GS_MAX && !S.knobs.no_segsort) {
-            // (3a) every group fits a CTA: sort the groups independently by rank[i+h]
+        const uint32_t nlarge = h_cnt[4], hmem = h_cnt[5], nhuge = h_cnt[6], nmedium = h_cnt[7];
+        PX_CUDA(cudaMemsetAsync(d_cnt + 3, 0, 5 * sizeof(uint32_t), st));
+        if (hmem <= An / 2 && !S.knobs.no_segsort) {
+            // (3a) the groups are sorted independently by rank[i+h], each where it stands: a warp or a CTA per group of
+            // up to GS_MAX members; the members of the few larger groups go through one radix sort of their own
             uint32_t *vout = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
             S.prof.begin(PC_ROUND_KEYS, st);
             k_round_key2<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, svals, rank, h, E.key2.p);
@@ -858,9 +1007,30 @@ static void build_suffix_array(Store &S, uint32_t N) {
             S.prof.begin(PC_SEG_SORT, st);
             k_group_sort_small<<<(unsigned) div_up<uint64_t>((uint64_t) G * 32, 256), 256, 0, st>>>(G, E.goff.p, E.key2.p, svals, kb,
                                                                                               E.keys0.p, vout);
+            if (nmedium)
+                k_group_sort_medium<<<div_up<uint32_t>(nmedium, 4), 128, 0, st>>>(nmedium, E.gmedium.p, E.goff.p, E.key2.p, svals, kb,
+                                                                                  E.keys0.p, vout);
             if (nlarge) k_group_sort_large<<<nlarge, 256, 0, st>>>(E.glarge.p, E.goff.p, E.key2.p, svals, kb, E.keys0.p, vout);
-            S.prof.end(st, 28.0 * An, nlarge ? 2 : 1);
-            L += nlarge ? 3 : 2;
+            S.prof.end(st, 28.0 * (An - hmem), 1 + (nmedium ? 1 : 0) + (nlarge ? 1 : 0));
+            L += 2 + (nmedium ? 1 : 0) + (nlarge ? 1 : 0);
+            if (nhuge) {
+                E.hv0.reserve_discard(hmem);
+                E.hv1.reserve_discard(hmem);
+                E.hk1.reserve_discard(hmem);
+                S.prof.begin(PC_ROUND_KEYS, st);
+                k_huge_offsets<<<1, 256, 0, st>>>(nhuge, E.ghuge.p, E.goff.p, E.hoff.p);
+                const dim3 hgrid(std::min<uint32_t>(div_up<uint32_t>(h_cnt[3], 256), 64), nhuge);
+                k_huge_gather<<<hgrid, 256, 0, st>>>(E.ghuge.p, E.hoff.p, E.goff.p, E.key2.p, svals, kb, E.keys1.p, E.hv0.p);
+                S.prof.end(st, 20.0 * hmem, 2);
+                const int hb = bits_for(nhuge - 1);
+                const int c3 = radix_sort_pairs<uint64_t>(E.keys1.p, E.hk1.p, E.hv0.p, E.hv1.p, hmem, 0, kb + hb, false, E.rs,
+                                                          E.counters.p + 2, st, &L, PF);
+                S.prof.begin(PC_ROUND_KEYS, st);
+                k_huge_scatter<<<hgrid, 256, 0, st>>>(E.ghuge.p, E.hoff.p, E.goff.p, c3 ? E.hk1.p : E.keys1.p, c3 ? E.hv1.p : E.hv0.p, kb,
+                                                      E.keys0.p, vout);
+                S.prof.end(st, 24.0 * hmem, 1);
+                L += 3;
+            }
             skeys = E.keys0.p;
             svals = vout;
             slot_cur = slot_next;

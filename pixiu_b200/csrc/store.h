@@ -56,6 +56,10 @@ struct EncodeScratch {
     DevBuf<uint64_t> qoff;
     DevBuf<uint2> leaf;   // {sa, lcp} per suffix-array slot (MinTree::leaf)
     DevBuf<uint32_t> goff, glarge, key2;  // segmented group sort: group offsets, list of big groups, rank[i+h]
+    // groups no CTA can sort (> GS_MAX members): their ids, their offsets in the compact buffers, and the compact
+    // (key, value) pairs a radix sort orders while every other group is sorted in place
+    DevBuf<uint32_t> gmedium, ghuge, hoff, hv0, hv1;   // (gmedium: groups of 33 .. 128 members, a warp each)
+    DevBuf<uint64_t> hk1;
     ScanWorkspace scanws;
     DevBuf<uint32_t> tree_a, tree_l;
     DevBuf<uint8_t> flagp, flagc, symmap;
