@@ -237,6 +237,60 @@ k_group_sort_small(uint32_t G, const uint32_t *__restrict__ goff, const uint32_t
     }
 }
 
+// Groups of up to 32 members, a warp per 32 CONSECUTIVE active suffixes (coalesced, and one sorting network serves all the
+// groups that lie inside the block instead of one network per group of a handful of members): the block is sorted by
+// (group, rank[i+h], suffix) with the members of a group that began before the block pinned in front and those of a
+// group that runs past its end pinned behind - groups occupy fixed positions, so every member lands inside its own
+// group.  A second network sorts the group that starts in the block and ends in the next one.
+// (key layout: 6 bits of group, 29 + 29 bits of rank and suffix: windows below 2^29 positions)
+__global__ void __launch_bounds__(256)
+k_group_sort_blocks(uint32_t A, const uint32_t *__restrict__ gk, const uint32_t *__restrict__ goff,
+                    const uint32_t *__restrict__ key2, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
+                    uint32_t *__restrict__ vals_out) {
+    const uint32_t x = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t lane = lane_id(), base = x - lane, bend = base + 32;
+    if (base >= A) return;
+    const uint32_t FULL = 0xffffffffu;
+    const bool valid = x < A;
+    const uint32_t g = valid ? gk[x] : 0u;
+    const uint32_t off = valid ? goff[g] : 0u, end = valid ? goff[g + 1] : 0u;
+    const uint32_t g0 = __shfl_sync(FULL, g, 0);
+    const bool interior = valid && off >= base && end <= bend;
+    constexpr uint64_t M29 = (1ull << 29) - 1;
+    uint64_t e = ~0ull;
+    if (interior) e = ((uint64_t) (g - g0) << 58) | ((uint64_t) key2[x] << 29) | vals[x];
+    else if (valid && off < base) e = 0;
+    auto network = [&](uint64_t v) {
+#pragma unroll
+        for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                const uint64_t o = __shfl_xor_sync(FULL, v, j);
+                const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+                v = (up == lower) ? (v < o ? v : o) : (v > o ? v : o);
+            }
+        }
+        return v;
+    };
+    if (__any_sync(FULL, interior && end - off > 1)) e = network(e);
+    if (interior) {
+        keys_out[x] = ((uint64_t) g << kb) | ((e >> 29) & M29);
+        vals_out[x] = (uint32_t) (e & M29);
+    }
+    // the group that starts in this block and runs into the next one
+    const uint32_t last = min(31u, A - 1 - base);
+    const uint32_t gs = __shfl_sync(FULL, g, last), so = __shfl_sync(FULL, off, last), se = __shfl_sync(FULL, end, last);
+    if (se > bend && so >= base && se - so <= 32) {
+        const uint32_t size = se - so;
+        uint64_t v = lane < size ? ((uint64_t) key2[so + lane] << 32) | vals[so + lane] : ~0ull;
+        v = network(v);
+        if (lane < size) {
+            keys_out[so + lane] = ((uint64_t) gs << kb) | (v >> 32);
+            vals_out[so + lane] = (uint32_t) v;
+        }
+    }
+}
+
 // warp per group of 33 .. GS_WARP members: R members per lane (member i sits in lane i % 32, register i / 32), a
 // bitonic network whose exchanges at distance >= 32 stay inside the lane - no shared memory, no barrier
 template <int R>
@@ -1005,8 +1059,11 @@ static void build_suffix_array(Store &S, uint32_t N) {
             k_round_key2<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, svals, rank, h, E.key2.p);
             S.prof.end(st, 12.0 * An, 1);
             S.prof.begin(PC_SEG_SORT, st);
-            k_group_sort_small<<<(unsigned) div_up<uint64_t>((uint64_t) G * 32, 256), 256, 0, st>>>(G, E.goff.p, E.key2.p, svals, kb,
-                                                                                              E.keys0.p, vout);
+            if (kb <= 29)
+                k_group_sort_blocks<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, gk, E.goff.p, E.key2.p, svals, kb, E.keys0.p, vout);
+            else
+                k_group_sort_small<<<(unsigned) div_up<uint64_t>((uint64_t) G * 32, 256), 256, 0, st>>>(G, E.goff.p, E.key2.p, svals,
+                                                                                                  kb, E.keys0.p, vout);
             if (nmedium)
                 k_group_sort_medium<<<div_up<uint32_t>(nmedium, 4), 128, 0, st>>>(nmedium, E.gmedium.p, E.goff.p, E.key2.p, svals, kb,
                                                                                   E.keys0.p, vout);
