@@ -31,7 +31,10 @@ constexpr uint32_t RS_FLAG_AGG = 1u << 30;
 constexpr uint32_t RS_FLAG_PREFIX = 2u << 30;
 constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
 constexpr uint32_t RS_SPIN_LIMIT = 1u << 27;
-constexpr int RS_LOOK = 8;
+#ifndef PIXIU_RS_LOOK
+#define PIXIU_RS_LOOK 8
+#endif
+constexpr int RS_LOOK = PIXIU_RS_LOOK;
 
 // hist[pass][bin] += count, for passes [0, npass) covering bits [begin_bit + 8*pass, ..)
 template <typename KeyT>
