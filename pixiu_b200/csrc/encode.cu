@@ -596,6 +596,9 @@ k_lcp_long(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, 
 // Earlier occurrences of w with a smaller next byte sit above rank[s] in the suffix array, those with a
 // larger one below; occurrences that end their record ("terminal") sort first.  One bit per position.
 // ---------------------------------------------------------------------------------
+#ifndef PIXIU_LPF_FAST
+#define PIXIU_LPF_FAST 12
+#endif
 template <bool NODES>
 __global__ void __launch_bounds__(256)
 k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ rank, const uint16_t *__restrict__ dist,
@@ -615,7 +618,7 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
             const uint32_t r = rank[s];
             // nearest smaller text position above r: lcp = min L[j+1..r].  Most searches end within a few
             // entries: a plain scan of up to LPF_FAST neighbours first, the block-min tree only for the rest
-            constexpr int LPF_FAST = 12;
+            constexpr int LPF_FAST = PIXIU_LPF_FAST;
             uint32_t l1 = AL(r).y;
             uint32_t a_jl = 0;   // sa[jl]
             int64_t jl = -1;
@@ -807,9 +810,18 @@ k_candidates(MinTree T, const uint16_t *__restrict__ dist, const uint16_t *__res
              const uint8_t *__restrict__ flagc, const uint32_t *__restrict__ prevp, const uint32_t *__restrict__ nextp,
              const uint32_t *__restrict__ runidx, const uint16_t *__restrict__ gidx, uint32_t s0, uint32_t n, int strict251,
              uint32_t *__restrict__ cand) {
-    uint32_t i = s0 + blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    if (contrib_at(i, flagc, dist, prevp, nextp, strict251) <= 1) return;
+    // (the run ends of a CTA are handled by consecutive threads, see k_emit)
+    __shared__ uint32_t task[256];
+    __shared__ uint32_t ntask;
+    if (threadIdx.x == 0) ntask = 0;
+    __syncthreads();
+    {
+        const uint32_t i0 = s0 + blockIdx.x * 256 + threadIdx.x;
+        if (i0 < n && contrib_at(i0, flagc, dist, prevp, nextp, strict251) > 1) task[atomicAdd(&ntask, 1u)] = i0;
+    }
+    __syncthreads();
+    if (threadIdx.x >= ntask) return;
+    const uint32_t i = task[threadIdx.x];
     cand[runidx[i]] = run_pointer(T, recid, rec_start, rank, reach, gidx, i, nextp[i] - prevp[i]);
 }
 
@@ -820,17 +832,27 @@ k_emit(MinTree T, const uint8_t *__restrict__ text, const uint16_t *__restrict__
        const uint32_t *__restrict__ nextp, const uint32_t *__restrict__ off, uint32_t s0, uint32_t n, int strict251,
        uint8_t *__restrict__ enc_out /* already offset so that off[] indexes it directly */, uint32_t *__restrict__ err,
        const uint32_t *__restrict__ cand, const uint32_t *__restrict__ runidx, const uint16_t *__restrict__ gidx) {
-    uint32_t i = s0 + blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    uint32_t c = contrib_at(i, flagc, dist, prevp, nextp, strict251);
-    if (c == 0) return;
-    uint32_t o = off[i];
-    if (c == 1) {
-        enc_out[o] = text[i];
-        return;
+    // Literals are written by the thread of their position.  The ends of the long runs - one position in ten, each a
+    // binary search plus two walks of the block-min trees, all dependent random loads - are first collected per CTA and
+    // then handled by consecutive threads: a warp with 32 searches in flight instead of three
+    __shared__ uint32_t task[256];
+    __shared__ uint32_t ntask;
+    if (threadIdx.x == 0) ntask = 0;
+    __syncthreads();
+    {
+        const uint32_t i0 = s0 + blockIdx.x * 256 + threadIdx.x;
+        if (i0 < n) {
+            const uint32_t c0 = contrib_at(i0, flagc, dist, prevp, nextp, strict251);
+            if (c0 == 1) enc_out[off[i0]] = text[i0];
+            else if (c0 > 1) task[atomicAdd(&ntask, 1u)] = i0;
+        }
     }
-    // long run ending at i
-    uint32_t rl = nextp[i] - prevp[i];
+    __syncthreads();
+    if (threadIdx.x >= ntask) return;
+    const uint32_t i = task[threadIdx.x];
+    const uint32_t rl = nextp[i] - prevp[i];   // long run ending at i
+    const uint32_t c = (rl > 255 || (rl == 251 && !strict251)) ? 8u : 6u;
+    const uint32_t o = off[i];
     uint32_t src, to;
     if (cand) {  // multi-GPU: the pointer was min-reduced across the shards
         uint32_t key = cand[runidx[i]];
