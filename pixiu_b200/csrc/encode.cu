@@ -1073,7 +1073,7 @@ static void build_suffix_array(Store &S, uint32_t N) {
         if (h > 65535u) throw std::runtime_error("suffix array: groups left after h > 65535");
         const uint32_t nlarge = h_cnt[4], hmem = h_cnt[5], nhuge = h_cnt[6], nmedium = h_cnt[7];
         PX_CUDA(cudaMemsetAsync(d_cnt + 3, 0, 5 * sizeof(uint32_t), st));
-        if (hmem <= An / 2 && !S.knobs.no_segsort) {
+        if (hmem <= An / 2 && nhuge <= 65535u && !S.knobs.no_segsort) {   // (nhuge is a grid dimension below)
             // (3a) the groups are sorted independently by rank[i+h], each where it stands: a warp or a CTA per group of
             // up to GS_MAX members; the members of the few larger groups go through one radix sort of their own
             uint32_t *vout = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
