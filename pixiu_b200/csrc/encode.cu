@@ -603,7 +603,7 @@ template <bool NODES>
 __global__ void __launch_bounds__(256)
 k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ rank, const uint16_t *__restrict__ dist,
       uint32_t s0, uint32_t n, uint32_t *__restrict__ reach, uint32_t *__restrict__ leafmask,
-      uint32_t *__restrict__ splitmask) {
+      uint32_t *__restrict__ splitmask, uint8_t *__restrict__ flagp /* nullptr: k_flag_scatter does it later */) {
     const uint32_t k = blockIdx.x * 256 + threadIdx.x;
     const uint32_t s = s0 + k;
     bool leaf = false, split = false;
@@ -717,6 +717,7 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
             }
         }
         reach[s] = s + best;
+        if (flagp) flagp[s + best] = 1;   // PASS flags = image of reach, plus the separators (d == 0: best == 0)
     }
     if (NODES) {
         uint32_t lm = __ballot_sync(0xffffffffu, leaf), sm = __ballot_sync(0xffffffffu, split);
@@ -740,16 +741,11 @@ k_flag_scatter(const uint32_t *__restrict__ reach, const uint16_t *__restrict__ 
     else flagp[reach[s]] = 1;
 }
 
-// escape-pair coherence (PiXiuStr.cpp:34-54): flagc[i] = 1 iff byte i stays COMPRESS
-__global__ void __launch_bounds__(256)
-k_pair_rule(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, const uint8_t *__restrict__ flagp,
-            const uint32_t *__restrict__ lastnon, uint32_t s0, uint32_t n, uint8_t *__restrict__ flagc) {
-    uint32_t i = s0 + blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    if (dist[i] == 0) {
-        flagc[i] = 0;
-        return;
-    }
+// escape-pair coherence (PiXiuStr.cpp:34-54): 1 iff byte i stays COMPRESS
+__device__ __forceinline__ uint8_t pair_rule(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist,
+                                             const uint8_t *__restrict__ flagp, const uint32_t *__restrict__ lastnon, uint32_t s0,
+                                             uint32_t n, uint32_t i) {
+    if (dist[i] == 0) return 0;
     bool c = !flagp[i];
     int64_t partner = -1;
     if (text[i] == 251) {
@@ -759,7 +755,7 @@ k_pair_rule(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist,
         partner = (int64_t) i - 1;
     }
     if (partner >= 0 && partner < (int64_t) n && dist[partner] != 0 && flagp[partner]) c = false;
-    flagc[i] = c;
+    return c ? 1 : 0;
 }
 
 // output bytes contributed by position i: PASS / short run byte -> 1; last byte of a long run -> 6 or 8
@@ -1305,7 +1301,7 @@ uint32_t Store::count_nodes_and_cut(uint32_t first_new, uint32_t s0, uint32_t N)
 
 // Phase A: suffix array, LCP, trees, longest previous factor of the records [first_new, win_R) of the open
 // window (and, under the reference policy, the cut of the candidates at the rotation record).
-void Store::enc_phase_a(uint32_t first_new) {
+void Store::enc_phase_a(uint32_t first_new, bool fuse_flags) {
     EncodeScratch &E = es;
     uint32_t N = win_N, R = win_R;
     const uint32_t s0 = h_win_rec_start[first_new];
@@ -1383,10 +1379,13 @@ void Store::enc_phase_a(uint32_t first_new) {
     if (cfg.rotate_policy == PIXIU_ROTATE_REFERENCE) {
         E.leafmask.reserve_discard((size_t) gridM * 8);
         E.splitmask.reserve_discard((size_t) gridM * 8);
-        k_lpf<true><<<gridM, 256, 0, st>>>(T, w_text.p, E.rank.p, w_dist.p, s0, N, E.reach.p, E.leafmask.p, E.splitmask.p);
+        k_lpf<true><<<gridM, 256, 0, st>>>(T, w_text.p, E.rank.p, w_dist.p, s0, N, E.reach.p, E.leafmask.p, E.splitmask.p,
+                                           fuse_flags ? E.flagp.p : nullptr);
     } else {
-        k_lpf<false><<<gridM, 256, 0, st>>>(T, w_text.p, E.rank.p, w_dist.p, s0, N, E.reach.p, nullptr, nullptr);
+        k_lpf<false><<<gridM, 256, 0, st>>>(T, w_text.p, E.rank.p, w_dist.p, s0, N, E.reach.p, nullptr, nullptr,
+                                            fuse_flags ? E.flagp.p : nullptr);
     }
+    ep_flags_done = fuse_flags;
     prof.end(st, 18.0 * M, 1);
     L++;
     // reference rotation rule: the arena replay needs the node masks on the host; they are copied
@@ -1408,8 +1407,10 @@ void Store::enc_phase_b() {
     const uint32_t gridM = div_up<uint32_t>(M, 256);
     int L = 0;
     prof.begin(PC_FLAGS, st);
-    k_flag_scatter<<<gridM, 256, 0, st>>>(E.reach.p, w_dist.p, s0, N, E.flagp.p);
-    L++;
+    if (!ep_flags_done) {   // (multi-GPU: reach has just been MAX-reduced over the shards)
+        k_flag_scatter<<<gridM, 256, 0, st>>>(E.reach.p, w_dist.p, s0, N, E.flagp.p);
+        L++;
+    }
     {
         // lastnon[i] = index of the last non-251 byte at or before i (max-scan of index+1, stored -1).
         // Position s0-1 is a separator (or the text start), i.e. "non-251": seed element 0 with it.
@@ -1423,14 +1424,22 @@ void Store::enc_phase_b() {
             [=] __device__(size_t k, uint32_t v) { ln[s0 + k] = v - 1u; }, OpMax(), 0u, false, E.scanws, st);
         L += 1;
     }
-    k_pair_rule<<<gridM, 256, 0, st>>>(w_text.p, w_dist.p, E.flagp.p, E.lastnon.p, s0, N, E.flagc.p);
-    L++;
     {
+        uint8_t *fcw = E.flagc.p;
         const uint8_t *fc = E.flagc.p;
+        const uint8_t *text = w_text.p, *fp = E.flagp.p;
+        const uint16_t *dist = w_dist.p;
+        const uint32_t *ln = E.lastnon.p;
         uint32_t *pp = E.prevp.p, *np = E.nextp.p;
-        // prevp[i] = 1 + index of the last non-COMPRESS position at or before i  (run start if i is COMPRESS)
+        // prevp[i] = 1 + index of the last non-COMPRESS position at or before i  (run start if i is COMPRESS); the
+        // input functor also applies the pair rule and leaves flagc for the passes that follow
         device_scan<uint32_t>(
-            M, [=] __device__(size_t k) -> uint32_t { return fc[s0 + k] ? (k == 0 ? s0 : 0u) : (uint32_t) (s0 + k) + 1u; },
+            M,
+            [=] __device__(size_t k) -> uint32_t {
+                const uint8_t c = pair_rule(text, dist, fp, ln, s0, N, (uint32_t) (s0 + k));
+                fcw[s0 + k] = c;
+                return c ? (k == 0 ? s0 : 0u) : (uint32_t) (s0 + k) + 1u;
+            },
             [=] __device__(size_t k, uint32_t v) { pp[s0 + k] = v; }, OpMax(), 0u, false, E.scanws, st);
         // nextp[i] = index of the first non-COMPRESS position at or after i (suffix min-scan, reversed index)
         const uint32_t last = N - 1;
@@ -1452,7 +1461,7 @@ void Store::enc_phase_b() {
             [=] __device__(size_t k, uint32_t v) { off[s0 + k] = v; }, OpSum(), 0u, true, E.scanws, st);
         L += 1;
     }
-    prof.end(st, 45.0 * M, 6);
+    prof.end(st, 45.0 * M, L);
     launches += L;
 }
 
@@ -1566,7 +1575,7 @@ void Store::enc_emit_all() {
 }
 
 uint32_t Store::encode_window_records(uint32_t first_new) {
-    enc_phase_a(first_new);
+    enc_phase_a(first_new, true);
     enc_phase_b();
     if (!knobs.no_spec_emit) enc_emit_all();  // (knob: A/B measurement)
     apply_rotation_cut();

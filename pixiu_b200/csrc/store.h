@@ -233,7 +233,8 @@ struct Store {
                       const int64_t *d_voff, const uint8_t *h_keys, const int64_t *h_koff,
                       const int64_t *h_voff, int32_t *rc, int32_t *saved);
     uint32_t encode_window_records(uint32_t first_new);  // returns the number of records accepted
-    void enc_phase_a(uint32_t first_new);
+    void enc_phase_a(uint32_t first_new, bool fuse_flags = false);   // fuse_flags: k_lpf also scatters the PASS flags
+    bool ep_flags_done = false;
     void enc_phase_b();
     uint32_t enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const uint16_t *gidx);
     uint32_t ep_first_new = 0, ep_s0 = 0, ep_N = 0, ep_n_new = 0;  // state shared by the phases
