@@ -204,16 +204,9 @@ k_group_stats(const uint32_t *__restrict__ cnt_in, const uint32_t *__restrict__ 
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&cnt[3], m);
 }
 
-__global__ void __launch_bounds__(256)
-k_round_key2(uint32_t A, const uint32_t *__restrict__ vals, const uint32_t *__restrict__ rank, uint32_t h,
-             uint32_t *__restrict__ key2) {
-    uint32_t x = blockIdx.x * 256 + threadIdx.x;
-    if (x < A) key2[x] = rank[vals[x] + h];
-}
-
 // warp per group (size <= 32)
 __global__ void __launch_bounds__(256)
-k_group_sort_small(uint32_t G, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ key2,
+k_group_sort_small(uint32_t G, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ rank, uint32_t h,
                    const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
                    uint32_t *__restrict__ vals_out) {
     const uint32_t g = (blockIdx.x * 256 + threadIdx.x) >> 5;
@@ -221,7 +214,7 @@ k_group_sort_small(uint32_t G, const uint32_t *__restrict__ goff, const uint32_t
     const uint32_t off = goff[g], size = goff[g + 1] - off;
     if (size > 32) return;
     const uint32_t lane = lane_id();
-    uint64_t e = lane < size ? ((uint64_t) key2[off + lane] << 32) | vals[off + lane] : ~0ull;
+    uint64_t e = lane < size ? ((uint64_t) rank[vals[off + lane] + h] << 32) | vals[off + lane] : ~0ull;
 #pragma unroll
     for (uint32_t k = 2; k <= 32; k <<= 1) {
 #pragma unroll
@@ -245,7 +238,7 @@ k_group_sort_small(uint32_t G, const uint32_t *__restrict__ goff, const uint32_t
 // (key layout: 6 bits of group, 29 + 29 bits of rank and suffix: windows below 2^29 positions)
 __global__ void __launch_bounds__(256)
 k_group_sort_blocks(uint32_t A, const uint32_t *__restrict__ gk, const uint32_t *__restrict__ goff,
-                    const uint32_t *__restrict__ key2, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
+                    const uint32_t *__restrict__ rank, uint32_t h, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
                     uint32_t *__restrict__ vals_out) {
     const uint32_t x = blockIdx.x * 256 + threadIdx.x;
     const uint32_t lane = lane_id(), base = x - lane, bend = base + 32;
@@ -258,7 +251,7 @@ k_group_sort_blocks(uint32_t A, const uint32_t *__restrict__ gk, const uint32_t 
     const bool interior = valid && off >= base && end <= bend;
     constexpr uint64_t M29 = (1ull << 29) - 1;
     uint64_t e = ~0ull;
-    if (interior) e = ((uint64_t) (g - g0) << 58) | ((uint64_t) key2[x] << 29) | vals[x];
+    if (interior) e = ((uint64_t) (g - g0) << 58) | ((uint64_t) rank[vals[x] + h] << 29) | vals[x];
     else if (valid && off < base) e = 0;
     auto network = [&](uint64_t v) {
 #pragma unroll
@@ -282,7 +275,7 @@ k_group_sort_blocks(uint32_t A, const uint32_t *__restrict__ gk, const uint32_t 
     const uint32_t gs = __shfl_sync(FULL, g, last), so = __shfl_sync(FULL, off, last), se = __shfl_sync(FULL, end, last);
     if (se > bend && so >= base && se - so <= 32) {
         const uint32_t size = se - so;
-        uint64_t v = lane < size ? ((uint64_t) key2[so + lane] << 32) | vals[so + lane] : ~0ull;
+        uint64_t v = lane < size ? ((uint64_t) rank[vals[so + lane] + h] << 32) | vals[so + lane] : ~0ull;
         v = network(v);
         if (lane < size) {
             keys_out[so + lane] = ((uint64_t) gs << kb) | (v >> 32);
@@ -328,7 +321,7 @@ __device__ __forceinline__ void warp_bitonic(uint64_t (&e)[R], uint32_t lane) {
 
 __global__ void __launch_bounds__(128)
 k_group_sort_medium(uint32_t nm, const uint32_t *__restrict__ medium, const uint32_t *__restrict__ goff,
-                    const uint32_t *__restrict__ key2, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
+                    const uint32_t *__restrict__ rank, uint32_t h, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
                     uint32_t *__restrict__ vals_out) {
     const uint32_t w = (blockIdx.x * 128 + threadIdx.x) >> 5;
     if (w >= nm) return;
@@ -340,7 +333,7 @@ k_group_sort_medium(uint32_t nm, const uint32_t *__restrict__ medium, const uint
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             const uint32_t i = lane + 32 * r;
-            e[r] = i < size ? ((uint64_t) key2[off + i] << 32) | vals[off + i] : ~0ull;
+            e[r] = i < size ? ((uint64_t) rank[vals[off + i] + h] << 32) | vals[off + i] : ~0ull;
         }
         warp_bitonic<2>(e, lane);
 #pragma unroll
@@ -356,7 +349,7 @@ k_group_sort_medium(uint32_t nm, const uint32_t *__restrict__ medium, const uint
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const uint32_t i = lane + 32 * r;
-            e[r] = i < size ? ((uint64_t) key2[off + i] << 32) | vals[off + i] : ~0ull;
+            e[r] = i < size ? ((uint64_t) rank[vals[off + i] + h] << 32) | vals[off + i] : ~0ull;
         }
         warp_bitonic<4>(e, lane);
 #pragma unroll
@@ -372,7 +365,7 @@ k_group_sort_medium(uint32_t nm, const uint32_t *__restrict__ medium, const uint
 
 // CTA per group (GS_WARP < size <= GS_MAX)
 __global__ void __launch_bounds__(256)
-k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ key2,
+k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ rank, uint32_t h,
                    const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
                    uint32_t *__restrict__ vals_out) {
     __shared__ uint64_t sm[GS_MAX];
@@ -381,7 +374,7 @@ k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restric
     uint32_t n2 = 64;
     while (n2 < size) n2 <<= 1;
     for (uint32_t i = threadIdx.x; i < n2; i += 256)
-        sm[i] = i < size ? ((uint64_t) key2[off + i] << 32) | vals[off + i] : ~0ull;
+        sm[i] = i < size ? ((uint64_t) rank[vals[off + i] + h] << 32) | vals[off + i] : ~0ull;
     __syncthreads();
     for (uint32_t k = 2; k <= n2; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
@@ -437,12 +430,12 @@ k_huge_offsets(uint32_t nh, const uint32_t *__restrict__ huge, const uint32_t *_
 
 __global__ void __launch_bounds__(256)
 k_huge_gather(const uint32_t *__restrict__ huge, const uint32_t *__restrict__ hoff, const uint32_t *__restrict__ goff,
-              const uint32_t *__restrict__ key2, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ ck,
+              const uint32_t *__restrict__ rank, uint32_t h, const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ ck,
               uint32_t *__restrict__ cv) {
     const uint32_t j = blockIdx.y, g = huge[j];
     const uint32_t off = goff[g], size = goff[g + 1] - off, ho = hoff[j];
     for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < size; i += gridDim.x * 256) {
-        ck[ho + i] = ((uint64_t) j << kb) | key2[off + i];
+        ck[ho + i] = ((uint64_t) j << kb) | rank[vals[off + i] + h];
         cv[ho + i] = vals[off + i];
     }
 }
@@ -976,7 +969,6 @@ static void build_suffix_array(Store &S, uint32_t N) {
     E.gmedium.reserve_discard((size_t) N / 32 + 4);
     E.ghuge.reserve_discard((size_t) N / GS_MAX + 4);
     E.hoff.reserve_discard((size_t) N / GS_MAX + 5);
-    E.key2.reserve_discard(N);
     int L = 0;
 
     Profiler *PF = S.prof.on ? &S.prof : nullptr;
@@ -1073,21 +1065,19 @@ static void build_suffix_array(Store &S, uint32_t N) {
             // (3a) the groups are sorted independently by rank[i+h], each where it stands: a warp or a CTA per group of
             // up to GS_MAX members; the members of the few larger groups go through one radix sort of their own
             uint32_t *vout = (svals == E.vals0.p) ? E.vals1.p : E.vals0.p;
-            S.prof.begin(PC_ROUND_KEYS, st);
-            k_round_key2<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, svals, rank, h, E.key2.p);
-            S.prof.end(st, 12.0 * An, 1);
+            // (the keys rank[i + h] are gathered by the sort kernels themselves: no pass that writes them out first)
             S.prof.begin(PC_SEG_SORT, st);
             if (kb <= 29)
-                k_group_sort_blocks<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, gk, E.goff.p, E.key2.p, svals, kb, E.keys0.p, vout);
+                k_group_sort_blocks<<<div_up<uint32_t>(An, 256), 256, 0, st>>>(An, gk, E.goff.p, rank, h, svals, kb, E.keys0.p, vout);
             else
-                k_group_sort_small<<<(unsigned) div_up<uint64_t>((uint64_t) G * 32, 256), 256, 0, st>>>(G, E.goff.p, E.key2.p, svals,
-                                                                                                  kb, E.keys0.p, vout);
+                k_group_sort_small<<<(unsigned) div_up<uint64_t>((uint64_t) G * 32, 256), 256, 0, st>>>(G, E.goff.p, rank, h, svals, kb,
+                                                                                                  E.keys0.p, vout);
             if (nmedium)
-                k_group_sort_medium<<<div_up<uint32_t>(nmedium, 4), 128, 0, st>>>(nmedium, E.gmedium.p, E.goff.p, E.key2.p, svals, kb,
+                k_group_sort_medium<<<div_up<uint32_t>(nmedium, 4), 128, 0, st>>>(nmedium, E.gmedium.p, E.goff.p, rank, h, svals, kb,
                                                                                   E.keys0.p, vout);
-            if (nlarge) k_group_sort_large<<<nlarge, 256, 0, st>>>(E.glarge.p, E.goff.p, E.key2.p, svals, kb, E.keys0.p, vout);
+            if (nlarge) k_group_sort_large<<<nlarge, 256, 0, st>>>(E.glarge.p, E.goff.p, rank, h, svals, kb, E.keys0.p, vout);
             S.prof.end(st, 28.0 * (An - hmem), 1 + (nmedium ? 1 : 0) + (nlarge ? 1 : 0));
-            L += 2 + (nmedium ? 1 : 0) + (nlarge ? 1 : 0);
+            L += 1 + (nmedium ? 1 : 0) + (nlarge ? 1 : 0);
             if (nhuge) {
                 E.hv0.reserve_discard(hmem);
                 E.hv1.reserve_discard(hmem);
@@ -1095,7 +1085,7 @@ static void build_suffix_array(Store &S, uint32_t N) {
                 S.prof.begin(PC_ROUND_KEYS, st);
                 k_huge_offsets<<<1, 256, 0, st>>>(nhuge, E.ghuge.p, E.goff.p, E.hoff.p);
                 const dim3 hgrid(std::min<uint32_t>(div_up<uint32_t>(h_cnt[3], 256), 64), nhuge);
-                k_huge_gather<<<hgrid, 256, 0, st>>>(E.ghuge.p, E.hoff.p, E.goff.p, E.key2.p, svals, kb, E.keys1.p, E.hv0.p);
+                k_huge_gather<<<hgrid, 256, 0, st>>>(E.ghuge.p, E.hoff.p, E.goff.p, rank, h, svals, kb, E.keys1.p, E.hv0.p);
                 S.prof.end(st, 20.0 * hmem, 2);
                 const int hb = bits_for(nhuge - 1);
                 const int c3 = radix_sort_pairs<uint64_t>(E.keys1.p, E.hk1.p, E.hv0.p, E.hv1.p, hmem, 0, kb + hb, false, E.rs,

@@ -55,7 +55,7 @@ struct EncodeScratch {
     DevBuf<uint32_t> vals0, vals1, slot0, slot1, gk, sa, rank, lcp, reach, lastnon, prevp, nextp, off;
     DevBuf<uint64_t> qoff;
     DevBuf<uint2> leaf;   // {sa, lcp} per suffix-array slot (MinTree::leaf)
-    DevBuf<uint32_t> goff, glarge, key2;  // segmented group sort: group offsets, list of big groups, rank[i+h]
+    DevBuf<uint32_t> goff, glarge;  // segmented group sort: group offsets, list of big groups
     // groups no CTA can sort (> GS_MAX members): their ids, their offsets in the compact buffers, and the compact
     // (key, value) pairs a radix sort orders while every other group is sorted in place
     DevBuf<uint32_t> gmedium, ghuge, hoff, hv0, hv1;   // (gmedium: groups of 33 .. 128 members, a warp each)
