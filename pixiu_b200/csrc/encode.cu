@@ -182,7 +182,7 @@ k_round_keys(uint32_t A, const uint32_t *__restrict__ vals, const uint32_t *__re
 // (bitonic network over shuffles), a CTA per larger group (bitonic in shared memory).
 // ---------------------------------------------------------------------------------
 constexpr uint32_t GS_MAX = 2048;
-constexpr uint32_t GS_WARP = 128;   // a warp sorts up to four members per lane in registers
+constexpr uint32_t GS_WARP = 256;   // a warp sorts up to eight members per lane in registers
 
 // per group: size; max size -> cnt[3]; ids of the groups with 33 .. GS_WARP members -> medium[] (count cnt[7]), with
 // GS_WARP + 1 .. GS_MAX members -> large[] (count cnt[4])
@@ -284,38 +284,47 @@ k_group_sort_blocks(uint32_t A, const uint32_t *__restrict__ gk, const uint32_t 
     }
 }
 
-// warp per group of 33 .. GS_WARP members: R members per lane (member i sits in lane i % 32, register i / 32), a
+// warp per group of 33 .. GS_WARP members: R = 2, 4 or 8 members per lane (member i sits in lane i % 32, register i / 32), a
 // bitonic network whose exchanges at distance >= 32 stay inside the lane - no shared memory, no barrier
-template <int R>
-__device__ __forceinline__ void warp_bitonic(uint64_t (&e)[R], uint32_t lane) {
+// steps j = JSTART, JSTART / 2, ..., 1 of stage k of the bitonic network over the warp's 32 * R consecutive members
+// (member with local index lane + 32 r, global index base + that; base is a multiple of 32 * R)
+template <int R, uint32_t JSTART>
+__device__ __forceinline__ void warp_bitonic_steps(uint64_t (&e)[R], uint32_t lane, uint32_t base, uint32_t k) {
 #pragma unroll
-    for (uint32_t k = 2; k <= 32u * R; k <<= 1) {
+    for (uint32_t j = JSTART; j > 0; j >>= 1) {
+        if (j >= 32) {
+            const uint32_t jr = j >> 5;
 #pragma unroll
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const uint32_t jr = j >> 5;
-#pragma unroll
-                for (uint32_t r = 0; r < (uint32_t) R; r++) {
-                    if ((r & jr) == 0) {
-                        const uint32_t i = lane + 32 * r;
-                        const bool up = (i & k) == 0;
-                        const uint64_t a = e[r], b = e[r | jr];
-                        if ((a > b) == up) {
-                            e[r] = b;
-                            e[r | jr] = a;
-                        }
+            for (uint32_t r = 0; r < (uint32_t) R; r++) {
+                if ((r & jr) == 0) {
+                    const uint32_t i = base + lane + 32 * r;
+                    const bool up = (i & k) == 0;
+                    const uint64_t a = e[r], b = e[r | jr];
+                    if ((a > b) == up) {
+                        e[r] = b;
+                        e[r | jr] = a;
                     }
                 }
-            } else {
+            }
+        } else {
 #pragma unroll
-                for (uint32_t r = 0; r < (uint32_t) R; r++) {
-                    const uint32_t i = lane + 32 * r;
-                    const uint64_t o = __shfl_xor_sync(0xffffffffu, e[r], j);
-                    const bool up = (i & k) == 0, lower = (lane & j) == 0;
-                    e[r] = (up == lower) ? (e[r] < o ? e[r] : o) : (e[r] > o ? e[r] : o);
-                }
+            for (uint32_t r = 0; r < (uint32_t) R; r++) {
+                const uint32_t i = base + lane + 32 * r;
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, e[r], j);
+                const bool up = (i & k) == 0, lower = (lane & j) == 0;
+                e[r] = (up == lower) ? (e[r] < o ? e[r] : o) : (e[r] > o ? e[r] : o);
             }
         }
+    }
+}
+
+// all stages k = 2 .. 32 * R (a full sort of the warp's members when base == 0; with a base, the last stage follows the
+// direction of the enclosing network)
+template <int R, uint32_t K = 2>
+__device__ __forceinline__ void warp_bitonic(uint64_t (&e)[R], uint32_t lane, uint32_t base = 0) {
+    if constexpr (K <= 32u * R) {
+        warp_bitonic_steps<R, K / 2>(e, lane, base, K);
+        warp_bitonic<R, K * 2>(e, lane, base);
     }
 }
 
@@ -344,7 +353,7 @@ k_group_sort_medium(uint32_t nm, const uint32_t *__restrict__ medium, const uint
                 vals_out[off + i] = (uint32_t) e[r];
             }
         }
-    } else {
+    } else if (size <= 128) {
         uint64_t e[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
@@ -360,10 +369,28 @@ k_group_sort_medium(uint32_t nm, const uint32_t *__restrict__ medium, const uint
                 vals_out[off + i] = (uint32_t) e[r];
             }
         }
+    } else {
+        uint64_t e[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t i = lane + 32 * r;
+            e[r] = i < size ? ((uint64_t) rank[vals[off + i] + h] << 32) | vals[off + i] : ~0ull;
+        }
+        warp_bitonic<8>(e, lane);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t i = lane + 32 * r;
+            if (i < size) {
+                keys_out[off + i] = ((uint64_t) g << kb) | (e[r] >> 32);
+                vals_out[off + i] = (uint32_t) e[r];
+            }
+        }
     }
 }
 
-// CTA per group (GS_WARP < size <= GS_MAX)
+// CTA per group (GS_WARP < size <= GS_MAX): every warp keeps 256 consecutive members in registers; the stages of the
+// bitonic network up to k = 256 and the steps at distance < 256 of the later stages run there (shuffles, no barrier),
+// only the steps at distance >= 256 go through shared memory: 13 barriers for 2,048 members instead of 66
 __global__ void __launch_bounds__(256)
 k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ rank, uint32_t h,
                    const uint32_t *__restrict__ vals, int kb, uint64_t *__restrict__ keys_out,
@@ -371,18 +398,29 @@ k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restric
     __shared__ uint64_t sm[GS_MAX];
     const uint32_t g = large[blockIdx.x];
     const uint32_t off = goff[g], size = goff[g + 1] - off;
-    uint32_t n2 = 64;
+    uint32_t n2 = 512;
     while (n2 < size) n2 <<= 1;
-    for (uint32_t i = threadIdx.x; i < n2; i += 256)
-        sm[i] = i < size ? ((uint64_t) rank[vals[off + i] + h] << 32) | vals[off + i] : ~0ull;
-    __syncthreads();
-    for (uint32_t k = 2; k <= n2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, base = warp * 256;
+    const bool mine = base < n2;   // (warps beyond the padded size only take part in the barriers and the shared steps)
+    uint64_t e[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t i = base + lane + 32 * r;
+        e[r] = (mine && i < size) ? ((uint64_t) rank[vals[off + i] + h] << 32) | vals[off + i] : ~0ull;
+    }
+    if (mine) warp_bitonic<8>(e, lane, base);
+    for (uint32_t k = 512; k <= n2; k <<= 1) {
+        if (mine) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) sm[base + lane + 32 * r] = e[r];
+        }
+        __syncthreads();
+        for (uint32_t j = k >> 1; j >= 256; j >>= 1) {
             for (uint32_t t = threadIdx.x; t < n2 / 2; t += 256) {
-                uint32_t i = 2 * t - (t & (j - 1));  // lower index of the pair (bit j clear)
-                uint32_t p = i + j;
-                uint64_t a = sm[i], b = sm[p];
-                bool up = (i & k) == 0;
+                const uint32_t i = 2 * t - (t & (j - 1));  // lower index of the pair (bit j clear)
+                const uint32_t p = i + j;
+                const uint64_t a = sm[i], b = sm[p];
+                const bool up = (i & k) == 0;
                 if ((a > b) == up) {
                     sm[i] = b;
                     sm[p] = a;
@@ -390,11 +428,21 @@ k_group_sort_large(const uint32_t *__restrict__ large, const uint32_t *__restric
             }
             __syncthreads();
         }
+        if (mine) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) e[r] = sm[base + lane + 32 * r];
+            warp_bitonic_steps<8, 128>(e, lane, base, k);
+        }
     }
-    for (uint32_t i = threadIdx.x; i < size; i += 256) {
-        uint64_t e = sm[i];
-        keys_out[off + i] = ((uint64_t) g << kb) | (e >> 32);
-        vals_out[off + i] = (uint32_t) e;
+    if (mine) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t i = base + lane + 32 * r;
+            if (i < size) {
+                keys_out[off + i] = ((uint64_t) g << kb) | (e[r] >> 32);
+                vals_out[off + i] = (uint32_t) e[r];
+            }
+        }
     }
 }
 
