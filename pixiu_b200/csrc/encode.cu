@@ -204,6 +204,15 @@ k_group_stats(const uint32_t *__restrict__ cnt_in, const uint32_t *__restrict__ 
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&cnt[3], m);
 }
 
+// the counters of a round go to the host through pinned memory the host polls: a copy and a stream synchronisation per
+// round cost twice as much (measured: 16.5 against 7.3 us per hand-over, nine rounds per window)
+__global__ void k_publish_counts(const uint32_t *__restrict__ cnt, volatile uint32_t *host, uint32_t seq) {
+    if (threadIdx.x < 8) host[threadIdx.x] = cnt[threadIdx.x];
+    __syncwarp();
+    __threadfence_system();
+    if (threadIdx.x == 0) host[8] = seq;
+}
+
 // warp per group (size <= 32)
 __global__ void __launch_bounds__(256)
 k_group_sort_small(uint32_t G, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ rank, uint32_t h,
@@ -1098,8 +1107,25 @@ static void build_suffix_array(Store &S, uint32_t N) {
         L++;
         S.prof.end(st, 36.0 * A, 2);
         uint32_t h_cnt[8];
-        PX_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
-        PX_CUDA(cudaStreamSynchronize(st));
+        {
+            if (!E.h_round.p) {
+                E.h_round.reserve_discard(16);
+                memset(E.h_round.p, 0, 16 * sizeof(uint32_t));
+            }
+            volatile uint32_t *hr = E.h_round.p;
+            if (++S.round_seq == 0) S.round_seq = 1;   // (0 is what a fresh buffer holds)
+            const uint32_t seq = S.round_seq;
+            k_publish_counts<<<1, 32, 0, st>>>(d_cnt, hr, seq);
+            L++;
+            for (uint32_t spins = 0; hr[8] != seq; spins++) {
+                if ((spins & 0xFFFu) == 0xFFFu) {   // (a failed launch would never publish)
+                    const cudaError_t q = cudaStreamQuery(st);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) PX_CUDA(q);
+                    if (q == cudaSuccess && hr[8] != seq) throw std::runtime_error("suffix array: round counters never arrived");
+                }
+            }
+            for (int i = 0; i < 8; i++) h_cnt[i] = hr[i];
+        }
         if (h_cnt[2]) throw std::runtime_error("radix sort look-back timed out");
         uint32_t An = h_cnt[0], G = h_cnt[1];
         if (S.knobs.trace)

@@ -65,6 +65,7 @@ struct EncodeScratch {
     DevBuf<uint8_t> flagp, flagc, symmap;
     DevBuf<uint32_t> leafmask, splitmask, wordpre, longmap;
     PinnedBuf<uint32_t> h_leafmask, h_splitmask, h_wordpre;
+    PinnedBuf<uint32_t> h_round;   // [0..7] counters of a suffix-array round, [8] sequence number (polled by the host)
     DevBuf<uint32_t> counters;  // [0] active count, [1] group count, [2] error flag, [3..] misc
     RadixSortTemp rs;
     MinTree tree{};  // block-min trees of the last phase A
@@ -235,6 +236,7 @@ struct Store {
     uint32_t encode_window_records(uint32_t first_new);  // returns the number of records accepted
     void enc_phase_a(uint32_t first_new, bool fuse_flags = false);   // fuse_flags: k_lpf also scatters the PASS flags
     bool ep_flags_done = false;
+    uint32_t round_seq = 0;   // hand-overs of round counters so far (k_publish_counts)
     void enc_phase_b();
     uint32_t enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const uint16_t *gidx);
     uint32_t ep_first_new = 0, ep_s0 = 0, ep_N = 0, ep_n_new = 0;  // state shared by the phases
