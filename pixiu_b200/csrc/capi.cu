@@ -785,6 +785,7 @@ int64_t pixiu_debug_window_array(pixiu_store *h, const char *name, void *out, in
             cudaSetDevice(S.cfg.device);
             if (cudaMemcpy2D(out, 4, reinterpret_cast<const char *>(S.es.tree.leaf) + 4, 8, 4, S.win_N, cudaMemcpyDeviceToHost) != cudaSuccess)
                 return PIXIU_ECUDA;
+            for (uint32_t i = 0; i < S.win_N; i++) static_cast<uint32_t *>(out)[i] &= 0xFFFFu;   // (upper half: dist[sa])
             return (int64_t) S.win_N;
         }
         src = S.es.lcp.p;

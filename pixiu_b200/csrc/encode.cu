@@ -595,7 +595,7 @@ k_lcp_sa(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, co
             atomicOr(longmap + (a >> 5), 1u << (a & 31));
         }
     }
-    leaf[r] = make_uint2(a, h);   // the leaf level of the block-min trees: {sa, lcp} side by side
+    leaf[r] = make_uint2(a, h | ((uint32_t) dist[a] << 16));   // the leaf level of the block-min trees (MinTree::leaf)
 }
 
 __global__ void __launch_bounds__(128)
@@ -625,7 +625,7 @@ k_lcp_long(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist, 
             h += 8;
         }
         if (h > lim) h = lim;
-        leaf[r].y = h;
+        leaf[r].y = h | ((uint32_t) dist[i] << 16);
         prev = i;
     }
 }
@@ -664,13 +664,18 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
             // level 0 of the trees: {sa, lcp} interleaved, or the two arrays (knob lcp_kasai)
             const uint2 *LF = T.leaf;
             const uint32_t *A0 = T.a[0], *L0 = T.l[0];
-            auto AL = [&](uint32_t j) { return LF ? LF[j] : make_uint2(A0[j], L0[j]); };
+            // entry j as {sa, lcp | dist[sa] << 16}
+            auto AL = [&](uint32_t j) {
+                if (LF) return LF[j];
+                const uint32_t a = A0[j];
+                return make_uint2(a, L0[j] | ((uint32_t) dist[a] << 16));
+            };
             const uint32_t r = rank[s];
             // nearest smaller text position above r: lcp = min L[j+1..r].  Most searches end within a few
             // entries: a plain scan of up to LPF_FAST neighbours first, the block-min tree only for the rest
             constexpr int LPF_FAST = PIXIU_LPF_FAST;
-            uint32_t l1 = AL(r).y;
-            uint32_t a_jl = 0;   // sa[jl]
+            uint32_t l1 = AL(r).y & 0xFFFFu;
+            uint32_t d_jl = 0;   // dist[sa[jl]]: bytes left in the record of the occurrence above
             int64_t jl = -1;
             if (l1) {
                 uint32_t pos = r;
@@ -680,11 +685,11 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
                     const uint2 e = AL(pos);
                     if (e.x < s) {
                         jl = pos;
-                        a_jl = e.x;
+                        d_jl = e.y >> 16;
                         open = false;
                         break;
                     }
-                    l1 = min(l1, e.y);
+                    l1 = min(l1, e.y & 0xFFFFu);
                     if (l1 == 0) {
                         open = false;
                         break;
@@ -692,7 +697,7 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
                 }
                 if (open) {
                     jl = pos > 0 ? tree_search<true, false, true>(T, pos, s, l1, 0) : -1;
-                    if (NODES && jl >= 0) a_jl = AL((uint32_t) jl).x;
+                    if (NODES && jl >= 0) d_jl = AL((uint32_t) jl).y >> 16;
                 }
             }
             if (jl < 0) l1 = 0;
@@ -706,7 +711,7 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
                 for (int k = 0; k < LPF_FAST && pos + 1 < n; k++) {
                     pos++;
                     const uint2 e = AL(pos);
-                    l2 = min(l2, e.y);
+                    l2 = min(l2, e.y & 0xFFFFu);
                     if (e.x < s) {
                         jr = pos;
                         open = false;
@@ -725,7 +730,7 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
                 const uint32_t M = best;
                 leaf = M < d;
                 if (leaf && M > 0) {
-                    bool up = l1 == M && dist[a_jl] > M;   // a continuing earlier occurrence above
+                    bool up = l1 == M && d_jl > M;          // a continuing earlier occurrence above
                     bool dn = l2 == M;                      // ... below (never terminal)
                     bool is_explicit = (up && dn) || (!up && !dn);  // two next bytes | only ex-leaf occurrences
                     if (!is_explicit) {
@@ -734,10 +739,10 @@ k_lpf(MinTree T, const uint8_t *__restrict__ text, const uint32_t *__restrict__ 
                         if (up) {
                             uint32_t a2 = 0xFFFFFFFFu;
                             int64_t x1 = tree_search<true, true, false>(T, (uint32_t) jl + 1, M + 1, a2, -1);
-                            uint32_t acc2 = AL((uint32_t) x1).y;
+                            uint32_t acc2 = AL((uint32_t) x1).y & 0xFFFFu;
                             if (acc2 >= M) {
                                 int64_t j2 = tree_search<true, false, true>(T, (uint32_t) x1, s, acc2, (int64_t) M - 1);
-                                if (j2 >= 0 && acc2 >= M && dist[AL((uint32_t) j2).x] > M) is_explicit = true;
+                                if (j2 >= 0 && acc2 >= M && (AL((uint32_t) j2).y >> 16) > M) is_explicit = true;
                             }
                         } else {
                             uint32_t a2 = 0xFFFFFFFFu;

@@ -34,7 +34,7 @@ k_tree_level_leaf(const uint2 *__restrict__ leaf, uint32_t n_in, uint32_t *__res
     for (uint32_t j = b; j < e; j++) {
         const uint2 x = leaf[j];
         ma = min(ma, x.x);
-        ml = min(ml, x.y);
+        ml = min(ml, x.y & 0xFFFFu);
     }
     out_a[o] = ma;
     out_l[o] = ml;
@@ -55,8 +55,8 @@ __device__ __forceinline__ int64_t tree_search(const MinTree &T, uint32_t start,
     auto LEAF = [&](uint32_t j, uint32_t &k, uint32_t &a) {
         if (T.leaf) {
             const uint2 x = T.leaf[j];
-            k = KEYA ? x.x : x.y;
-            a = KEYA ? x.y : x.x;
+            k = KEYA ? x.x : (x.y & 0xFFFFu);   // (the upper half of .y carries dist[sa], see MinTree::leaf)
+            a = KEYA ? (x.y & 0xFFFFu) : x.x;
         } else {
             k = KEY(0, j);
             a = ACC(0, j);

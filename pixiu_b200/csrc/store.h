@@ -41,8 +41,9 @@ struct MinTree {
     const uint32_t *l[TREE_MAX_LEVELS];   // block minima of the LCP array   (level 0 = lcp)
     uint32_t size[TREE_MAX_LEVELS];
     int nlev;
-    // level 0 interleaved, {sa[j], lcp[j]} in one 8-byte entry: a neighbour probe of the match finder touches ONE
-    // 32-byte sector where the two arrays cost two (nullptr: level 0 is read from a[0] / l[0])
+    // level 0 interleaved, {sa[j], lcp[j] | dist[sa[j]] << 16} in one 8-byte entry: a neighbour probe of the match finder
+    // touches ONE 32-byte sector where the two arrays cost two, and "does that occurrence continue past the match"
+    // (the node rule of the rotation law) needs no further lookup (nullptr: level 0 is read from a[0] / l[0])
     const uint2 *leaf;
 };
 
