@@ -782,6 +782,10 @@ def bench_sharded(args, env):
             multigpu.init_comm_torch(c)       # bootstrap only: the 128-byte NCCL id travels over the process group
         else:
             c.mg_comm_init(0, 1, c.mg_unique_id())
+        # every pass starts from a NEW store: without the capacity hint its first batch would map the first 256 MiB of the
+        # compressed arena inside the timed region (20 - 200 ms per cuMemCreate on a freshly booted box: the 2-GPU line
+        # read 146 or 215 ms per pass depending on that alone)
+        c.reserve(int(0.86 * raw) + (64 << 20))
         env.barrier()
         t0 = time.perf_counter()
         for kb, vb in batches:
