@@ -1,6 +1,6 @@
 """Measurement aid for the decode kernel: python profiles/prof_decode.py {c2|c3} N [trace]
 c2: N synthetic HTML-like pages; c3: N nested 1 KB records.  Stores them, decodes every record three times (the last
-call is the one ncu captures with `-k regex:k_decode_tiles -s 2 -c 1`), prints the kernel time and the decoder's
+call is the one ncu captures with `-k regex:k_decode_ -s 4 -c 2`), prints the kernel time and the decoder's
 counters; with `trace` also the per-tile timeline (PIXIU_DEC_TRACE_FILE)."""
 import os
 import sys
