@@ -52,6 +52,7 @@ void Store::open_window() {
     pool_nth = 1;  // SuffixTree::init_prop allocates the root: first pool, 5 blocks (SuffixTree.cpp:69)
     pool_used = 5;
     for (int w = 0; w < 8; w++) win_present[w] = 0;
+    win_long251 = false;
     win_present[0] |= 1u | (1u << 2);  // terminator bytes 0 and 2 ...
     win_present[251 >> 5] |= 1u << (251 & 31);  // ... and 251 are in every record
     chunk_first.push_back((uint32_t) n_records());

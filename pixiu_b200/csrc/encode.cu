@@ -35,25 +35,39 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 __global__ void __launch_bounds__(256)
 k_doc_len(uint32_t n, const uint8_t *__restrict__ keys, const int64_t *__restrict__ koff,
           const uint8_t *__restrict__ vals, const int64_t *__restrict__ voff, uint32_t *__restrict__ doc_len,
-          uint32_t *__restrict__ present /* 256-bit set of the byte values seen (for the dense symbol map) */) {
+          uint32_t *__restrict__ present /* [0..7] 256-bit set of the byte values seen (for the dense symbol map),
+                                             [8] != 0: some key or value holds 63 or more consecutive 251s */) {
     uint32_t r = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (r >= n) return;
     const int lane = lane_id();
     int64_t k0 = koff[r], k1 = koff[r + 1], v0 = voff[r], v1 = voff[r + 1];
     uint32_t c = 0;
     uint32_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t i = k0 + lane; i < k1; i += 32) {
-        uint8_t b = keys[i];
-        c += b == 251;
+    // (32 consecutive bytes that are all 251: the only way a run of 63 or more of them can look - see present[8])
+    bool longrun = false;
+    for (int64_t base = k0; base < k1; base += 32) {
+        const int64_t i = base + lane;
+        const bool valid = i < k1;
+        const uint8_t b = valid ? keys[i] : 0;
+        c += valid && b == 251;
+        if (valid) {
 #pragma unroll
-        for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
+            for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
+        }
+        longrun |= __all_sync(0xffffffffu, valid && b == 251) != 0;
     }
-    for (int64_t i = v0 + lane; i < v1; i += 32) {
-        uint8_t b = vals[i];
-        c += b == 251;
+    for (int64_t base = v0; base < v1; base += 32) {
+        const int64_t i = base + lane;
+        const bool valid = i < v1;
+        const uint8_t b = valid ? vals[i] : 0;
+        c += valid && b == 251;
+        if (valid) {
 #pragma unroll
-        for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
+            for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
+        }
+        longrun |= __all_sync(0xffffffffu, valid && b == 251) != 0;
     }
+    if (present && longrun && lane == 0) atomicOr(&present[8], 1u);
     if (present) {
 #pragma unroll
         for (int w = 0; w < 8; w++) {
@@ -796,6 +810,17 @@ k_flag_scatter(const uint32_t *__restrict__ reach, const uint16_t *__restrict__ 
     else flagp[reach[s]] = 1;
 }
 
+// 1-based position of byte j (a 251) inside its run of 251s: from the max-scan of "last non-251 position" when the
+// window may hold long runs, else by walking back to `lo` at most (the runs are then at most 125 long: 62 escaped pairs
+// and a terminator; no run crosses a record start)
+__device__ __forceinline__ uint32_t run_pos251(const uint8_t *__restrict__ text, const uint32_t *__restrict__ lastnon, uint32_t lo,
+                                               uint32_t j) {
+    if (lastnon) return j - lastnon[j];
+    uint32_t p = j;
+    while (p > lo && text[p - 1] == 251) p--;
+    return j - p + 1;
+}
+
 // escape-pair coherence (PiXiuStr.cpp:34-54): 1 iff byte i stays COMPRESS
 __device__ __forceinline__ uint8_t pair_rule(const uint8_t *__restrict__ text, const uint16_t *__restrict__ dist,
                                              const uint8_t *__restrict__ flagp, const uint32_t *__restrict__ lastnon, uint32_t s0,
@@ -804,9 +829,9 @@ __device__ __forceinline__ uint8_t pair_rule(const uint8_t *__restrict__ text, c
     bool c = !flagp[i];
     int64_t partner = -1;
     if (text[i] == 251) {
-        uint32_t k = i - lastnon[i];  // 1-based position inside the run of 251s (lastnon is +1 biased)
+        const uint32_t k = run_pos251(text, lastnon, s0, i);
         partner = (k & 1) ? (int64_t) i + 1 : (int64_t) i - 1;
-    } else if (i > s0 && text[i - 1] == 251 && ((i - 1 - lastnon[i - 1]) & 1)) {
+    } else if (i > s0 && text[i - 1] == 251 && (run_pos251(text, lastnon, s0, i - 1) & 1)) {
         partner = (int64_t) i - 1;
     }
     if (partner >= 0 && partner < (int64_t) n && dist[partner] != 0 && flagp[partner]) c = false;
@@ -990,8 +1015,8 @@ k_tile_desc(uint32_t n_tiles_new, uint32_t tile_first, uint32_t n_new, uint32_t 
         // a tile that starts on the 2nd byte of an escape pair must take that byte literally
         uint8_t b = text[i];
         bool second = false;
-        if (b == 251) second = ((i - lastnon[i]) & 1) == 0;
-        else if (i > a && text[i - 1] == 251) second = ((i - 1 - lastnon[i - 1]) & 1) != 0;
+        if (b == 251) second = (run_pos251(text, lastnon, a, i) & 1) == 0;
+        else if (i > a && text[i - 1] == 251) second = (run_pos251(text, lastnon, a, i - 1) & 1) != 0;
         if (second) skip = 0xFFFF;
     }
     tile_desc[gt] = (off[i] - off[a]) | (skip << 16);
@@ -1480,7 +1505,7 @@ void Store::enc_phase_b() {
         k_flag_scatter<<<gridM, 256, 0, st>>>(E.reach.p, w_dist.p, s0, N, E.flagp.p);
         L++;
     }
-    {
+    if (win_long251) {
         // lastnon[i] = index of the last non-251 byte at or before i (max-scan of index+1, stored -1).
         // Position s0-1 is a separator (or the text start), i.e. "non-251": seed element 0 with it.
         const uint8_t *text = w_text.p;
@@ -1498,7 +1523,7 @@ void Store::enc_phase_b() {
         const uint8_t *fc = E.flagc.p;
         const uint8_t *text = w_text.p, *fp = E.flagp.p;
         const uint16_t *dist = w_dist.p;
-        const uint32_t *ln = E.lastnon.p;
+        const uint32_t *ln = win_long251 ? E.lastnon.p : nullptr;   // (nullptr: pair_rule walks the short runs itself)
         uint32_t *pp = E.prevp.p, *np = E.nextp.p;
         // prevp[i] = 1 + index of the last non-COMPRESS position at or before i  (run start if i is COMPRESS); the
         // input functor also applies the pair rule and leaves flagc for the passes that follow
@@ -1574,7 +1599,7 @@ uint32_t Store::enc_phase_c(const uint32_t *cand, const uint32_t *runidx, const 
     if (new_tiles)
         k_tile_desc<<<div_up<uint32_t>((uint32_t) new_tiles, 256), 256, 0, st>>>(
             (uint32_t) new_tiles, (uint32_t) n_tiles, n_new, first_new, (uint32_t) g_first, d_tile_base.p,
-            w_rec_start.p, E.off.p, E.flagc.p, E.prevp.p, E.nextp.p, w_text.p, E.lastnon.p, d_tile_desc.p);
+            w_rec_start.p, E.off.p, E.flagc.p, E.prevp.p, E.nextp.p, w_text.p, win_long251 ? E.lastnon.p : nullptr, d_tile_desc.p);
     prof.end(st, 24.0 * n_new, 2);
     L += 2;
     // host mirrors
@@ -1677,10 +1702,10 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     PX_CUDA(cudaEventRecord(ev0, st));
     doc_len.reserve_discard(nn);
     if (!es.counters.p) {
-        es.counters.reserve_discard(16);
-        PX_CUDA(cudaMemsetAsync(es.counters.p, 0, 16 * sizeof(uint32_t), st));
+        es.counters.reserve_discard(24);
+        PX_CUDA(cudaMemsetAsync(es.counters.p, 0, 24 * sizeof(uint32_t), st));
     }
-    PX_CUDA(cudaMemsetAsync(es.counters.p + 8, 0, 8 * sizeof(uint32_t), st));
+    PX_CUDA(cudaMemsetAsync(es.counters.p + 8, 0, 9 * sizeof(uint32_t), st));
     prof.begin(PC_DOCS, st);
     k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p,
                                                                                     es.counters.p + 8);
@@ -1688,7 +1713,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
     launches++;
     std::vector<uint32_t> h_doc_len(nn);
     PX_CUDA(cudaMemcpyAsync(h_doc_len.data(), doc_len.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaMemcpyAsync(batch_present, es.counters.p + 8, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(batch_present, es.counters.p + 8, 9 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
     for (uint32_t i = 0; i < nn; i++) {
         if (h_doc_len[i] == 0xFFFFFFFFu) {
@@ -1716,6 +1741,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         }
         if (!win_open) open_window();
         for (int w8 = 0; w8 < 8; w8++) win_present[w8] |= batch_present[w8];
+        win_long251 = win_long251 || batch_present[8] != 0;
         int64_t lim = budget;
         if (ref_policy) {
             // candidates: what the remaining arena is expected to hold (+4% and one record); the exact cut is
@@ -1808,16 +1834,16 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
     PX_CUDA(cudaEventRecord(ev0, st));
     doc_len.reserve_discard(nn);
     if (!es.counters.p) {
-        es.counters.reserve_discard(16);
-        PX_CUDA(cudaMemsetAsync(es.counters.p, 0, 16 * sizeof(uint32_t), st));
+        es.counters.reserve_discard(24);
+        PX_CUDA(cudaMemsetAsync(es.counters.p, 0, 24 * sizeof(uint32_t), st));
     }
-    PX_CUDA(cudaMemsetAsync(es.counters.p + 8, 0, 8 * sizeof(uint32_t), st));
+    PX_CUDA(cudaMemsetAsync(es.counters.p + 8, 0, 9 * sizeof(uint32_t), st));
     k_doc_len<<<(unsigned) div_up<uint64_t>((uint64_t) nn * 32u, 256), 256, 0, st>>>(nn, d_keys, d_koff, d_vals, d_voff, doc_len.p,
                                                                                     es.counters.p + 8);
     launches++;
     mg_doc_len.resize(nn);
     PX_CUDA(cudaMemcpyAsync(mg_doc_len.data(), doc_len.p, nn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    PX_CUDA(cudaMemcpyAsync(batch_present, es.counters.p + 8, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PX_CUDA(cudaMemcpyAsync(batch_present, es.counters.p + 8, 9 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PX_CUDA(cudaStreamSynchronize(st));
     uint64_t batch_bytes = 0;
     for (uint32_t i = 0; i < nn; i++) {
@@ -1842,6 +1868,7 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
         mg_h_gidx.clear();
     }
     for (int w8 = 0; w8 < 8; w8++) win_present[w8] |= batch_present[w8];
+    win_long251 = win_long251 || batch_present[8] != 0;
     // local window = shard records + the whole batch
     const uint32_t first_new = win_R;
     uint64_t bytes = win_N;

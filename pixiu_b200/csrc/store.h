@@ -187,7 +187,8 @@ struct Store {
     uint32_t pool_nth = 1, pool_used = 5;
     double rho = 1.35;  // running estimate of suffix-tree nodes per window byte
     double rho_err = 0.02;  // recent relative error of that estimate
-    uint32_t win_present[8] = {0}, batch_present[8] = {0};  // byte values present in the open window / last batch
+    uint32_t win_present[8] = {0}, batch_present[9] = {0};  // byte values present in the open window / last batch ([8]: long 251 run)
+    bool win_long251 = false;   // the open window may hold a run of more than 125 bytes 251 (then the flag phase scans for it)
 
     EncodeScratch es;
     std::unique_ptr<HostIndex> index;

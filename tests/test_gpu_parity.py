@@ -191,6 +191,38 @@ def test_edge_records(ctrl_mod):
     c.free_prop()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_run", [62, 200])
+def test_runs_of_251(ctrl_mod, max_run):
+    """escape pairs and tile starts inside runs of 251: batches whose runs stay below 63 raw bytes take the walk-back
+    path of the pair rule, longer ones the max-scan (k_doc_len decides per batch); both against the oracle, with runs
+    placed around the 2,048-byte tile boundaries of the decoder"""
+    rng = np.random.default_rng(251 + max_run)
+    keys, vals = [], []
+    lens = sorted(set(list(range(1, 12)) + [30, 31, 32, 33, 61, 62] + ([63, 64, 65, 127, 128, 200] if max_run > 62 else [])))
+    lens = [n for n in lens if n <= max_run]
+    for j, n in enumerate(lens):
+        for pad in (0, 1, 1000, 1019, 1020, 1021, 1022, 1023, 1024, 2045):
+            filler = bytes(rng.integers(97, 123, size=pad, dtype=np.uint8))
+            vals.append(filler + bytes([251]) * n + b"tail" + filler[:7] + bytes([251]) * (n // 2 + 1))
+            keys.append(b"r%03d-%04d" % (n, pad) + (bytes([251]) * (n % 5)))
+    # a key that ends in a run (the terminator 251 follows it directly) and repeated content (long references)
+    keys.append(b"end" + bytes([251]) * min(max_run, 9))
+    vals.append(vals[3] * 3)
+    docs, encs = _oracle_encode_all(keys, vals, strict=False)
+    c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
+    half = len(keys) // 2
+    c.setitem_batch(keys[:half], vals[:half])        # (two batches into one window)
+    c.setitem_batch(keys[half:], vals[half:])
+    for i in range(len(keys)):
+        assert c.encoded(0, i) == encs[i], f"record {i} ({keys[i][:9]})"
+    buf, off, found = c.getitem_batch(keys)
+    assert found.all()
+    for i, d in enumerate(docs):
+        assert buf[off[i]:off[i + 1]].tobytes() == d, f"record {i}"
+    c.free_prop()
+
+
 def test_decode_request_split_into_passes(ctrl_mod):
     """a request whose touched chunks decode to more than the 32-bit arena of one pass is split by chunk; the knob
     shrinks the limit so that a small store needs many passes (shuffled request, device and host outputs)"""
