@@ -36,37 +36,34 @@ __global__ void __launch_bounds__(256)
 k_doc_len(uint32_t n, const uint8_t *__restrict__ keys, const int64_t *__restrict__ koff,
           const uint8_t *__restrict__ vals, const int64_t *__restrict__ voff, uint32_t *__restrict__ doc_len,
           uint32_t *__restrict__ present /* [0..7] 256-bit set of the byte values seen (for the dense symbol map),
-                                             [8] != 0: some key or value holds 63 or more consecutive 251s */) {
+                                             [8] != 0: some key or value may hold more than 32 consecutive 251s */) {
     uint32_t r = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (r >= n) return;
     const int lane = lane_id();
     int64_t k0 = koff[r], k1 = koff[r + 1], v0 = voff[r], v1 = voff[r + 1];
     uint32_t c = 0;
     uint32_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    // (32 consecutive bytes that are all 251: the only way a run of 63 or more of them can look - see present[8])
-    bool longrun = false;
-    for (int64_t base = k0; base < k1; base += 32) {
-        const int64_t i = base + lane;
-        const bool valid = i < k1;
-        const uint8_t b = valid ? keys[i] : 0;
-        c += valid && b == 251;
-        if (valid) {
+    // a lane that meets 251 in two consecutive rounds (bytes 32 apart): what every run of more than 32 raw 251s produces
+    // in some lane (present[8]; a coincidence only costs the scan)
+    bool longrun = false, prev251 = false;
+    for (int64_t i = k0 + lane; i < k1; i += 32) {
+        const uint8_t b = keys[i];
+        c += b == 251;
+        longrun |= prev251 && b == 251;
+        prev251 = b == 251;
 #pragma unroll
-            for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
-        }
-        longrun |= __all_sync(0xffffffffu, valid && b == 251) != 0;
+        for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
     }
-    for (int64_t base = v0; base < v1; base += 32) {
-        const int64_t i = base + lane;
-        const bool valid = i < v1;
-        const uint8_t b = valid ? vals[i] : 0;
-        c += valid && b == 251;
-        if (valid) {
+    prev251 = false;
+    for (int64_t i = v0 + lane; i < v1; i += 32) {
+        const uint8_t b = vals[i];
+        c += b == 251;
+        longrun |= prev251 && b == 251;
+        prev251 = b == 251;
 #pragma unroll
-            for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
-        }
-        longrun |= __all_sync(0xffffffffu, valid && b == 251) != 0;
+        for (int w = 0; w < 8; w++) seen[w] |= (b >> 5) == w ? 1u << (b & 31) : 0u;
     }
+    longrun = __any_sync(0xffffffffu, longrun) != 0;
     if (present && longrun && lane == 0) atomicOr(&present[8], 1u);
     if (present) {
 #pragma unroll
@@ -811,7 +808,7 @@ k_flag_scatter(const uint32_t *__restrict__ reach, const uint16_t *__restrict__ 
 }
 
 // 1-based position of byte j (a 251) inside its run of 251s: from the max-scan of "last non-251 position" when the
-// window may hold long runs, else by walking back to `lo` at most (the runs are then at most 125 long: 62 escaped pairs
+// window may hold long runs, else by walking back to `lo` at most (the runs are then at most 65 long: 32 escaped pairs
 // and a terminator; no run crosses a record start)
 __device__ __forceinline__ uint32_t run_pos251(const uint8_t *__restrict__ text, const uint32_t *__restrict__ lastnon, uint32_t lo,
                                                uint32_t j) {
@@ -1741,7 +1738,7 @@ int Store::setitem_batch(int64_t n, const uint8_t *d_keys, const int64_t *d_koff
         }
         if (!win_open) open_window();
         for (int w8 = 0; w8 < 8; w8++) win_present[w8] |= batch_present[w8];
-        win_long251 = win_long251 || batch_present[8] != 0;
+        win_long251 = knobs.lastnon_mode == 2 ? false : (win_long251 || batch_present[8] != 0 || knobs.lastnon_mode == 1);
         int64_t lim = budget;
         if (ref_policy) {
             // candidates: what the remaining arena is expected to hold (+4% and one record); the exact cut is
@@ -1868,7 +1865,7 @@ int Store::mg_begin(int64_t n, const uint8_t *d_keys, const int64_t *d_koff, con
         mg_h_gidx.clear();
     }
     for (int w8 = 0; w8 < 8; w8++) win_present[w8] |= batch_present[w8];
-    win_long251 = win_long251 || batch_present[8] != 0;
+    win_long251 = knobs.lastnon_mode == 2 ? false : (win_long251 || batch_present[8] != 0 || knobs.lastnon_mode == 1);
     // local window = shard records + the whole batch
     const uint32_t first_new = win_R;
     uint64_t bytes = win_N;

@@ -82,6 +82,8 @@ struct Knobs {
     bool lcp_kasai = false;        // PIXIU_LCP_KASAI: the one-pass Kasai walk (A/B measurements)
     bool no_spec_emit = false;     // PIXIU_NO_SPEC_EMIT: emit after the rotation cut instead of beside it (A/B)
     bool no_segsort = false;       // PIXIU_NO_SEGSORT: radix sort only (A/B)
+    uint32_t lastnon_mode = 0;     // tests: 0 the batch decides (k_doc_len), 1 always run the last-non-251 scan, 2 never (only
+                                   // valid when no run of 251s is longer than the walk-back of the pair rule may go)
     uint64_t dec_arena_limit = 7ull << 29;  // PIXIU_DEC_ARENA_LIMIT: decoded bytes of one decode pass (3.5 GiB)
     uint32_t piece_cap = 0xFFFFFFFFu;       // PIXIU_PIECE_CAP: pending pieces a decode tile keeps before it drains them
     uint32_t sleep_after = 16, sleep_ns = 64;  // PIXIU_SLEEP_AFTER / _NS: back-off of the decoder's polls
@@ -119,6 +121,7 @@ struct Knobs {
         else if (name == "lcp_kasai") lcp_kasai = v != 0;
         else if (name == "no_spec_emit") no_spec_emit = v != 0;
         else if (name == "no_segsort") no_segsort = v != 0;
+        else if (name == "lastnon_mode") lastnon_mode = (uint32_t) v;
         else return false;
         return true;
     }
@@ -188,7 +191,7 @@ struct Store {
     double rho = 1.35;  // running estimate of suffix-tree nodes per window byte
     double rho_err = 0.02;  // recent relative error of that estimate
     uint32_t win_present[8] = {0}, batch_present[9] = {0};  // byte values present in the open window / last batch ([8]: long 251 run)
-    bool win_long251 = false;   // the open window may hold a run of more than 125 bytes 251 (then the flag phase scans for it)
+    bool win_long251 = false;   // the open window may hold a run of more than 65 bytes 251 (then the flag phase scans for it)
 
     EncodeScratch es;
     std::unique_ptr<HostIndex> index;

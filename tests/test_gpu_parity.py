@@ -192,14 +192,14 @@ def test_edge_records(ctrl_mod):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("max_run", [62, 200])
-def test_runs_of_251(ctrl_mod, max_run):
-    """escape pairs and tile starts inside runs of 251: batches whose runs stay below 63 raw bytes take the walk-back
+@pytest.mark.parametrize("max_run,mode", [(32, 0), (32, 1), (32, 2), (200, 0), (200, 1)])
+def test_runs_of_251(ctrl_mod, max_run, mode):
+    """escape pairs and tile starts inside runs of 251: batches whose runs stay within 32 raw bytes take the walk-back
     path of the pair rule, longer ones the max-scan (k_doc_len decides per batch); both against the oracle, with runs
     placed around the 2,048-byte tile boundaries of the decoder"""
     rng = np.random.default_rng(251 + max_run)
     keys, vals = [], []
-    lens = sorted(set(list(range(1, 12)) + [30, 31, 32, 33, 61, 62] + ([63, 64, 65, 127, 128, 200] if max_run > 62 else [])))
+    lens = sorted(set(list(range(1, 12)) + [15, 16, 17, 30, 31, 32] + ([33, 61, 62, 63, 64, 65, 127, 128, 200] if max_run > 32 else [])))
     lens = [n for n in lens if n <= max_run]
     for j, n in enumerate(lens):
         for pad in (0, 1, 1000, 1019, 1020, 1021, 1022, 1023, 1024, 2045):
@@ -211,6 +211,7 @@ def test_runs_of_251(ctrl_mod, max_run):
     vals.append(vals[3] * 3)
     docs, encs = _oracle_encode_all(keys, vals, strict=False)
     c = ctrl_mod.PiXiuCtrl(rotate_policy=ctrl_mod.ROTATE_RECORDS)
+    c.debug_set_knob("lastnon_mode", mode)           # 0: k_doc_len decides per batch, 1: always the scan, 2: always the walk
     half = len(keys) // 2
     c.setitem_batch(keys[:half], vals[:half])        # (two batches into one window)
     c.setitem_batch(keys[half:], vals[half:])
