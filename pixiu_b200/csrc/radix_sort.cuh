@@ -1,14 +1,15 @@
 // Hand-written LSD radix sort of (key, u32 value) pairs for sm_100a.
 //
 // One up-front histogram launch counts every 8-bit digit of every pass; each pass
-// is then ONE launch ("onesweep"): a CTA takes a tile of 256 x 16 keys in ticket
+// is then ONE launch ("onesweep"): a CTA takes a tile of 256 x 8 keys in ticket
 // order, ranks them stably with warp match-any + shared-memory digit counters,
 // resolves its global digit offsets by decoupled look-back over the tile-status
 // table, and scatters keys and values.  Per pass each element is read once and
 // written once (8|4 B key + 4 B value), the histogram launch reads the keys once.
 //
-// Used by the suffix-array construction (encode.cu): the initial 63-bit
-// 7-symbol keys and the (group, rank[i+h]) keys of every prefix-doubling round.
+// Used by the suffix-array construction (encode.cu): the initial 56-bit keys of 8 symbols (63-bit / 7 symbols for rich
+// alphabets), the members of the groups too large for a CTA in a prefix-doubling round, and the (group, rank[i+h]) keys
+// of a whole round when most suffixes sit in such groups; by the bulk build of the CritBit tree (index.cu).
 #pragma once
 #include "common.cuh"
 #include "prof.h"
