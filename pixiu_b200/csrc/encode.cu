@@ -3,9 +3,13 @@
 // Replaces, with flat-array kernels (all HBM-bound integer work, no tensor cores):
 //   doc assembly + 251 escaping   PiXiuCtrl.cpp:31-44, PiXiuStr.cpp:228-271      -> k_doc_len, k_write_docs
 //   online suffix tree            SuffixTree.cpp:144-304 (+ScapegoatTree.h)       -> suffix array by prefix
-//                                 doubling over radix sort, LCP, block-min trees, longest previous factor
-//   stream encoder                PiXiuStr.cpp:16-118                              -> flag scatter, pair rule,
-//                                 run scans, output-size scan, token emission
+//                                 doubling (one radix sort of the first 8 symbols, then every round sorts its groups
+//                                 where they stand: a warp per 32 consecutive suffixes / per group up to 256 members,
+//                                 a CTA up to 2,048, a radix sort of their own for the members of larger groups),
+//                                 LCP, block-min trees over {sa, lcp, dist} leaves, longest previous factor
+//   stream encoder                PiXiuStr.cpp:16-118                              -> PASS flags (set by the match
+//                                 finder), pair rule (inside the run-start scan), run scans, output-size scan, token
+//                                 emission (run ends regrouped per CTA)
 // The closed form (checked against the reference by the oracle and by
 // tests/pipeline_model.py):  M(s) = longest prefix of D[s..] starting earlier in the window,
 // reach(s) = s+M(s);  byte i is PASS iff i is a value of reach;  the pointer of a run ending at j
